@@ -1,0 +1,114 @@
+// fz_common.cuh -- shared constants and small helpers of the B200 float-zip codec.
+//
+// Everything in the *.cuh codec headers is `__host__ __device__`: the CUDA kernels are the product,
+// and tests/hostmodel compiles the very same source for the CPU to check the bit-level logic
+// against zlib without a GPU.  No reference code is used here; the container and stream
+// format follow /root/reference (citations in include/mrczip_b200.h and DESIGN.md).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define FZ_HD __host__ __device__ __forceinline__
+#define FZ_D __device__ __forceinline__
+#else
+#define FZ_HD inline
+#endif
+
+// ---- container constants (reference: constant.h:22-27, mrczip.h:116-121, common.c:137-149)
+#define FZ_PLANES 4
+#define FZ_REF_CHUNK_WORDS (6u * 1048576u)
+#define FZ_FILE_HEADER_BYTES 17
+#define FZ_CHUNK_HEADER_BYTES 16
+#define FZ_MRC_HEADER_WORDS 256
+#define FZ_RAW_FLAG 0x80000000u
+
+// ---- sub-block geometry of the GPU deflate encoder
+// Every (chunk, plane) stream is cut in independent sub-blocks of FZ_SUB bytes; each sub-block is one
+// deflate block (dynamic Huffman, distance-1 matches only -- the reference's Z_RLE strategy) or one
+// stored block, followed by an empty stored block (`00 00 FF FF` after byte alignment, exactly zlib's
+// sync-flush marker).  The marker makes sub-blocks concatenate at byte granularity and is what the
+// GPU inflater searches for to decode a stream with one thread per sub-block.
+#define FZ_SUB_LOG2 14
+#define FZ_SUB (1u << FZ_SUB_LOG2)        // 16 KiB
+#define FZ_SLOT_STRIDE (FZ_SUB + 32u)     // scratch bytes reserved per encoded sub-block
+#define FZ_STORED_OVERHEAD 10u            // 5 (stored header) + 5 (empty stored block)
+#define FZ_SIZE_STORED_FLAG 0x80000000u   // in the per-sub-block size word: emit as stored block
+
+#define FZ_MAX_MATCH 258
+#define FZ_MIN_MATCH 3
+#define FZ_NUM_LL 286
+#define FZ_NUM_D 30
+#define FZ_NUM_CL 19
+#define FZ_EOB 256
+
+// error codes of the C ABI (0 = ok, like the reference's run_* return value)
+#define FZ_OK 0
+#define FZ_E_ARG (-1)
+#define FZ_E_CUDA (-2)
+#define FZ_E_NOMEM (-3)
+#define FZ_E_FORMAT (-4)   // malformed container / stream
+#define FZ_E_SPACE (-5)    // output buffer too small
+#define FZ_E_IO (-6)
+
+FZ_HD uint32_t fz_mask_for_bits(int bits)
+{
+    // reference workers.c:29-37: 0xFFFFFFFF << b for b in 0..31, 0 for b == 32
+    return bits >= 32 ? 0u : (0xFFFFFFFFu << bits);
+}
+
+FZ_HD uint32_t fz_bitrev(uint32_t v, int nbits)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - nbits);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < nbits; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+#endif
+}
+
+FZ_HD int fz_ilog2(uint32_t v)  // floor(log2(v)), v > 0
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz(v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
+// length 3..258 -> (length code index 0..28, number of extra bits, extra value)   (RFC 1951 3.2.5)
+FZ_HD void fz_len_code(uint32_t len, uint32_t &lc, uint32_t &eb, uint32_t &ev)
+{
+    uint32_t x = len - 3;
+    if (x < 8) { lc = x; eb = 0; ev = 0; return; }
+    if (x == 255) { lc = 28; eb = 0; ev = 0; return; }
+    eb = (uint32_t)fz_ilog2(x) - 2;
+    lc = 4 * eb + 4 + ((x >> eb) & 3);
+    ev = x & ((1u << eb) - 1);
+}
+
+FZ_HD uint32_t fz_len_extra_bits(uint32_t lc)  // extra bits of length code index lc (0..28)
+{
+    return (lc < 8 || lc == 28) ? 0u : ((lc - 4) >> 2);
+}
+
+FZ_HD uint32_t fz_len_base(uint32_t lc)  // base length of length code index lc
+{
+    if (lc < 8) return lc + 3;
+    if (lc == 28) return 258;
+    uint32_t eb = (lc - 4) >> 2;
+    return 3 + ((4 + ((lc - 4) & 3)) << eb);
+}
+
+FZ_HD uint32_t fz_dist_extra_bits(uint32_t dc)  // distance code 0..29
+{
+    return dc < 4 ? 0u : ((dc - 2) >> 1);
+}
+
+FZ_HD uint32_t fz_dist_base(uint32_t dc)
+{
+    if (dc < 4) return dc + 1;
+    uint32_t eb = (dc - 2) >> 1;
+    return 1 + ((2 + (dc & 1)) << eb);
+}

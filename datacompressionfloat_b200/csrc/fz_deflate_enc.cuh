@@ -1,0 +1,632 @@
+// fz_deflate_enc.cuh -- warp-cooperative deflate encoder for ONE sub-block (<= FZ_SUB bytes) of a byte plane.
+//
+// Replaces, for one sub-block, what the reference gets from zlib's deflate(Z_RLE, level 6) behind
+// mzlib_def (reference zip.c:164-196, constants constant.h:22-24): distance-1 run matches of
+// 3..258 bytes, one dynamic-Huffman block, then an empty stored block (the sync-flush marker) so
+// the next sub-block starts byte aligned.  BFINAL is never set (reference decoder requirement,
+// SURVEY.md 7.2).  The produced bytes are a valid raw-deflate fragment, not zlib's bytes.
+//
+// SPMD style: `lane` is 0..31; a phase may only communicate through FzEncState (shared memory on the
+// GPU).  FZ_PHASE(x) runs x for this lane and then __syncwarp() on the device; on the host
+// (tests/hostmodel) it loops the 32 lanes sequentially -- so the same source is checked on the CPU.
+#pragma once
+#include "fz_common.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define FZ_PHASE(stmt) do { stmt; __syncwarp(); } while (0)
+#define FZ_LANE_DECL
+#else
+#define FZ_PHASE(stmt) do { for (int lane = 0; lane < 32; ++lane) { stmt; } } while (0)
+#endif
+
+struct FzVec16 { uint32_t w[4]; };
+
+// Per-warp encoder state.  ~7.3 KB; lives in shared memory on the GPU.
+struct FzEncState {
+    uint32_t hist[288];      // literal/length frequencies (286 used)
+    uint32_t nmatch;         // number of matches (all use distance code 0)
+    uint32_t n_active;       // literal/length symbols with freq > 0
+    uint32_t hlit;           // number of literal/length code lengths sent (>= 257)
+    uint32_t ncl;            // number of code-length code lengths sent (>= 4)
+    uint32_t ntok;           // code-length RLE tokens
+    uint32_t hdr_nbits;      // bits in hdr[] (block header incl. the 3 type bits)
+    uint32_t dyn_bits;       // exact size of the dynamic block incl. header and EOB
+    uint32_t pad0;
+    uint32_t keys[512];      // sort workspace; then Moffat-Katajainen array
+    uint16_t ssym[320];      // symbols in ascending frequency order
+    uint16_t code[288];      // bit-reversed canonical codes
+    uint8_t len[288];        // code lengths
+    uint8_t seq[320];        // hlit literal/length lengths followed by the distance lengths
+    uint16_t cltok[320];     // code-length tokens: sym | extra << 5
+    uint32_t hdr[160];       // bit-packed block header
+    uint32_t lane_cnt[32];   // scratch: per-lane counts
+    uint32_t lane_bits[32];  // bits each lane will emit
+    uint32_t num_codes[32];  // symbols per code length (1..15), litlen
+    uint32_t next_code[16];
+    uint16_t rank[32 * 16];  // per-lane per-length symbol counts -> exclusive prefix
+    uint32_t clfreq[19];
+    uint8_t cllen[19];
+    uint8_t clcode[19];
+    uint8_t pad1[2];
+    uint32_t nzmask[10];
+    // bit-merge of lane outputs
+    uint32_t fw_idx[32], fw_bits[32], tw_bits[32], crossed[32];
+};
+
+// -------------------------------------------------------------------------------------------------
+// Run tokeniser: the greedy distance-1 matcher (what zlib's Z_RLE strategy does): bytes equal to
+// their predecessor accumulate in `pend`; 258 of them, or a run end with >= 3, become a match,
+// shorter tails become literals.  `prev_init` < 0 means "no byte before `begin`" (sub-block start:
+// sub-blocks never reference earlier data).
+// -------------------------------------------------------------------------------------------------
+template <class Load16, class Sink>
+FZ_HD void fz_scan_piece(const Load16 &ld, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
+{
+    int prev = prev_init;
+    uint32_t pend = 0;
+    for (uint32_t i = begin; i < end; i += 16) {
+        const FzVec16 v = ld(i);
+        const uint32_t lim = end - i;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if ((uint32_t)k < lim) {
+                const int c = (int)((v.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+                if (c == prev) {
+                    if (++pend == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); pend = 0; }
+                } else {
+                    if (pend) {
+                        if (pend >= FZ_MIN_MATCH) sink.match(pend); else sink.literal((uint32_t)prev, pend);
+                        pend = 0;
+                    }
+                    sink.literal((uint32_t)c, 1);
+                    prev = c;
+                }
+            }
+        }
+    }
+    if (pend) {
+        if (pend >= FZ_MIN_MATCH) sink.match(pend); else sink.literal((uint32_t)prev, pend);
+    }
+}
+
+FZ_HD void fz_atomic_add(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+
+struct FzHistSink {
+    FzEncState *st;
+    FZ_HD void literal(uint32_t c, uint32_t n) { fz_atomic_add(&st->hist[c], n); }
+    FZ_HD void match(uint32_t len)
+    {
+        uint32_t lc, eb, ev;
+        fz_len_code(len, lc, eb, ev);
+        fz_atomic_add(&st->hist[257 + lc], 1);
+        fz_atomic_add(&st->nmatch, 1);
+    }
+};
+
+struct FzCountSink {
+    const FzEncState *st;
+    uint32_t bits;
+    FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * st->len[c]; }
+    FZ_HD void match(uint32_t len)
+    {
+        uint32_t lc, eb, ev;
+        fz_len_code(len, lc, eb, ev);
+        bits += st->len[257 + lc] + eb + 1;  // + 1-bit distance code
+    }
+};
+
+// LSB-first bit writer into 32-bit words.  The first word a lane touches and its last partial
+// word are NOT stored: they are returned for the cross-lane merge (several lanes may share a word).
+struct FzBitWriter {
+    uint32_t *out;       // word-addressed output (4-byte aligned)
+    uint64_t acc;
+    uint32_t nbits;      // valid bits in acc (< 32 between puts)
+    uint32_t widx;       // index of the word acc's low 32 bits go to
+    uint32_t first_idx, first_bits;
+    bool crossed;
+    FZ_HD void init(uint32_t *o, uint32_t bit_off)
+    {
+        out = o; acc = 0; nbits = bit_off & 31; widx = bit_off >> 5;
+        first_idx = widx; first_bits = 0; crossed = false;
+    }
+    FZ_HD void put(uint32_t v, uint32_t n)  // n <= 32
+    {
+        acc |= (uint64_t)v << nbits;
+        nbits += n;
+        if (nbits >= 32) {
+            const uint32_t w = (uint32_t)acc;
+            if (!crossed) { first_bits = w; crossed = true; } else out[widx] = w;
+            widx++; acc >>= 32; nbits -= 32;
+        }
+    }
+    FZ_HD void align_byte() { nbits = (nbits + 7) & ~7u; if (nbits >= 32) put(0, 0); }
+    FZ_HD uint32_t bitpos() const { return widx * 32 + nbits; }
+};
+
+struct FzEmitSink {
+    const FzEncState *st;
+    FzBitWriter bw;
+    FZ_HD void literal(uint32_t c, uint32_t n)
+    {
+        const uint32_t code = st->code[c], l = st->len[c];
+        for (uint32_t i = 0; i < n; i++) bw.put(code, l);
+    }
+    FZ_HD void match(uint32_t len)
+    {
+        uint32_t lc, eb, ev;
+        fz_len_code(len, lc, eb, ev);
+        bw.put(st->code[257 + lc], st->len[257 + lc]);
+        bw.put(ev, eb + 1);  // extra bits, then the 1-bit distance code '0' (distance 1)
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// Huffman construction phases (literal/length alphabet).
+// -------------------------------------------------------------------------------------------------
+#define FZ_SYMS_PER_LANE 9  // 32 * 9 = 288
+
+FZ_HD void fz_ph_zero(FzEncState *st, int lane)
+{
+    for (int i = lane; i < 288; i += 32) { st->hist[i] = 0; st->len[i] = 0; }
+    if (lane == 0) st->nmatch = 0;
+}
+
+FZ_HD void fz_ph_count_active(FzEncState *st, int lane)
+{
+    uint32_t c = 0;
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
+        const int s = lane * FZ_SYMS_PER_LANE + k;
+        c += (s == FZ_EOB || st->hist[s] != 0) ? 1u : 0u;
+    }
+    st->lane_cnt[lane] = c;
+}
+
+FZ_HD void fz_ph_compact(FzEncState *st, int lane)
+{
+    uint32_t off = 0, total = 0;
+    for (int l = 0; l < 32; l++) { const uint32_t c = st->lane_cnt[l]; if (l < lane) off += c; total += c; }
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
+        const int s = lane * FZ_SYMS_PER_LANE + k;
+        const uint32_t f = (s == FZ_EOB) ? 1u : st->hist[s];
+        if (f) st->keys[off++] = (f << 9) | (uint32_t)s;
+    }
+    // pad to the next power of two with +inf keys for the bitonic network
+    uint32_t np2 = 32;
+    while (np2 < total) np2 <<= 1;
+    for (uint32_t i = total + lane; i < np2; i += 32) st->keys[i] = 0xFFFFFFFFu;
+    if (lane == 0) st->n_active = total;
+}
+
+// one compare-exchange layer (k, j) of the bitonic network over np2 keys
+FZ_HD void fz_ph_bitonic(uint32_t *keys, uint32_t np2, uint32_t k, uint32_t j, int lane)
+{
+    for (uint32_t t = lane; t < np2 / 2; t += 32) {
+        const uint32_t i = 2 * t - (t & (j - 1));  // insert a 0 bit at position log2(j)
+        const uint32_t p = i | j;
+        const uint32_t a = keys[i], b = keys[p];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+    }
+}
+
+// serial (lane 0): in-place minimum-redundancy code lengths (Moffat & Katajainen 1995) over the
+// ascending frequencies, then the length limit.  keys[] holds freq << 9 | sym on entry.
+FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n, int maxbits, int lane)
+{
+    if (lane != 0) return;
+    for (int i = 0; i < n; i++) { const uint32_t k = A[i]; ssym[i] = (uint16_t)(k & 511u); A[i] = k >> 9; }
+    for (int l = 0; l < 32; l++) num_codes[l] = 0;
+    if (n == 1) { A[0] = 1; num_codes[1] = 1; return; }
+    // phase 1: internal node weights + parent pointers
+    A[0] += A[1];
+    int root = 0, leaf = 2, next;
+    for (next = 1; next < n - 1; next++) {
+        if (leaf >= n || A[root] < A[leaf]) { A[next] = A[root]; A[root++] = (uint32_t)next; } else A[next] = A[leaf++];
+        if (leaf >= n || (root < next && A[root] < A[leaf])) { A[next] += A[root]; A[root++] = (uint32_t)next; } else A[next] += A[leaf++];
+    }
+    // phase 2: internal node depths
+    A[n - 2] = 0;
+    for (next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
+    // phase 3: leaf depths
+    int avbl = 1, used = 0, dpth = 0;
+    root = n - 2; next = n - 1;
+    while (avbl > 0) {
+        while (root >= 0 && (int)A[root] == dpth) { used++; root--; }
+        while (avbl > used) { A[next--] = (uint32_t)dpth; avbl--; }
+        avbl = 2 * used; dpth++; used = 0;
+    }
+    // histogram of lengths, clamped at 31
+    for (int i = 0; i < n; i++) { uint32_t l = A[i]; if (l > 31) l = 31; num_codes[l]++; }
+    // enforce maxbits: fold the overflow into maxbits, then repair the Kraft sum
+    uint32_t over = 0;
+    for (int l = maxbits + 1; l < 32; l++) { over += num_codes[l]; num_codes[l] = 0; }
+    if (over) {
+        num_codes[maxbits] += over;
+        uint32_t total = 0;
+        for (int l = maxbits; l > 0; l--) total += num_codes[l] << (maxbits - l);
+        while (total != (1u << maxbits)) {
+            num_codes[maxbits]--;
+            for (int l = maxbits - 1; l > 0; l--)
+                if (num_codes[l]) { num_codes[l]--; num_codes[l + 1] += 2; break; }
+            total--;
+        }
+    }
+    // lengths by ascending frequency: longest first
+    int i = 0;
+    for (int l = maxbits; l > 0; l--)
+        for (uint32_t c = 0; c < num_codes[l]; c++) A[i++] = (uint32_t)l;
+}
+
+FZ_HD void fz_ph_scatter_len(FzEncState *st, int lane)
+{
+    const int n = (int)st->n_active;
+    for (int i = lane; i < n; i += 32) st->len[st->ssym[i]] = (uint8_t)st->keys[i];
+    if (lane == 0) {
+        uint32_t code = 0;
+        st->next_code[0] = 0;
+        for (int l = 1; l <= 15; l++) { code = (code + st->num_codes[l - 1]) << 1; st->next_code[l] = code; }
+        // num_codes[0] is 0 here (only active symbols were counted)
+    }
+}
+
+FZ_HD void fz_ph_rank_count(FzEncState *st, int lane)
+{
+    uint16_t *r = &st->rank[lane * 16];
+    for (int l = 0; l < 16; l++) r[l] = 0;
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) r[st->len[lane * FZ_SYMS_PER_LANE + k]]++;
+}
+
+FZ_HD void fz_ph_rank_scan(FzEncState *st, int lane)
+{
+    if (lane >= 16) return;  // lane = code length
+    uint32_t run = 0;
+    for (int l = 0; l < 32; l++) { const uint16_t c = st->rank[l * 16 + lane]; st->rank[l * 16 + lane] = (uint16_t)run; run += c; }
+}
+
+FZ_HD void fz_ph_assign_codes(FzEncState *st, int lane)
+{
+    uint16_t *r = &st->rank[lane * 16];
+    uint32_t hi = 0;
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
+        const int s = lane * FZ_SYMS_PER_LANE + k;
+        const uint32_t l = st->len[s];
+        if (l) {
+            st->code[s] = (uint16_t)fz_bitrev(st->next_code[l] + r[l], (int)l);
+            r[l]++;
+            hi = (uint32_t)s + 1;
+        } else st->code[s] = 0;
+    }
+    st->lane_cnt[lane] = hi;  // highest used symbol + 1 in this lane's range
+}
+
+// hlit, the code-length sequence and its non-zero bitmap
+FZ_HD void fz_ph_seq(FzEncState *st, int lane)
+{
+    uint32_t hlit = 257;
+    for (int l = 0; l < 32; l++) if (st->lane_cnt[l] > hlit) hlit = st->lane_cnt[l];
+    const uint32_t total = hlit + 2;  // two distance codes of one bit each (zlib also always sends >= 2)
+    for (uint32_t i = lane; i < 320; i += 32) st->seq[i] = i < hlit ? st->len[i] : (i < total ? 1 : 0);
+    if (lane == 0) st->hlit = hlit;
+}
+
+FZ_HD void fz_ph_nzmask(FzEncState *st, int lane)
+{
+    if (lane >= 10) return;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; b++) if (st->seq[lane * 32 + b]) m |= 1u << b;
+    st->nzmask[lane] = m;
+}
+
+FZ_HD int fz_ctz(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
+// serial (lane 0): run-length code the length sequence with the 16/17/18 repeat codes (RFC 1951 3.2.7)
+FZ_HD void fz_ph_cl_tokens(FzEncState *st, int lane)
+{
+    if (lane != 0) return;
+    for (int i = 0; i < 19; i++) st->clfreq[i] = 0;
+    const uint32_t total = st->hlit + 2;
+    uint32_t i = 0, nt = 0;
+    while (i < total) {
+        const uint32_t v = st->seq[i];
+        uint32_t j;
+        if (v == 0) {
+            // next non-zero entry at or after i (the sequence ends with the two distance lengths, non-zero)
+            uint32_t w = i >> 5;
+            uint32_t m = st->nzmask[w] & (0xFFFFFFFFu << (i & 31));
+            while (m == 0) m = st->nzmask[++w];
+            j = w * 32 + (uint32_t)fz_ctz(m);
+            uint32_t r = j - i;
+            while (r >= 11) { const uint32_t t = r < 138 ? r : 138; st->cltok[nt++] = (uint16_t)(18 | ((t - 11) << 5)); st->clfreq[18]++; r -= t; }
+            if (r >= 3) { st->cltok[nt++] = (uint16_t)(17 | ((r - 3) << 5)); st->clfreq[17]++; r = 0; }
+            while (r--) { st->cltok[nt++] = 0; st->clfreq[0]++; }
+        } else {
+            j = i + 1;
+            while (j < total && st->seq[j] == v) j++;
+            uint32_t r = j - i - 1;
+            st->cltok[nt++] = (uint16_t)v; st->clfreq[v]++;
+            while (r >= 3) { const uint32_t t = r < 6 ? r : 6; st->cltok[nt++] = (uint16_t)(16 | ((t - 3) << 5)); st->clfreq[16]++; r -= t; }
+            while (r--) { st->cltok[nt++] = (uint16_t)v; st->clfreq[v]++; }
+        }
+        i = j;
+    }
+    st->ntok = nt;
+}
+
+// serial (lane 0): Huffman code for the 19 code-length symbols (7-bit limit) and the packed header
+FZ_HD void fz_ph_header(FzEncState *st, int lane)
+{
+    if (lane != 0) return;
+    // tiny alphabet: insertion sort of the active symbols by (freq, sym)
+    uint32_t *A = st->keys;
+    int n = 0;
+    for (int s = 0; s < 19; s++) {
+        st->cllen[s] = 0;
+        if (st->clfreq[s]) {
+            const uint32_t key = (st->clfreq[s] << 9) | (uint32_t)s;
+            int p = n++;
+            while (p > 0 && A[p - 1] > key) { A[p] = A[p - 1]; p--; }
+            A[p] = key;
+        }
+    }
+    if (n == 1) {
+        // the code-length code must be complete for zlib's inflate: add a second, unused symbol
+        const uint32_t s0 = A[0] & 511u;
+        const uint32_t dummy = s0 == 0 ? 1u : 0u;
+        st->cllen[s0] = 1; st->cllen[dummy] = 1;
+    } else {
+        uint16_t *ssym = st->ssym;
+        uint32_t *nc = st->num_codes;  // litlen counts no longer needed
+        fz_ph_lengths(A, ssym, nc, n, 7, 0);
+        for (int i = 0; i < n; i++) st->cllen[ssym[i]] = (uint8_t)A[i];
+    }
+    // canonical codes
+    uint32_t blc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nx[8];
+    for (int s = 0; s < 19; s++) blc[st->cllen[s]]++;
+    blc[0] = 0;
+    uint32_t code = 0;
+    nx[0] = 0;
+    for (int l = 1; l <= 7; l++) { code = (code + blc[l - 1]) << 1; nx[l] = code; }
+    for (int s = 0; s < 19; s++) {
+        const uint32_t l = st->cllen[s];
+        st->clcode[s] = l ? (uint8_t)fz_bitrev(nx[l]++, (int)l) : 0;
+    }
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint32_t ncl = 19;
+    while (ncl > 4 && st->cllen[order[ncl - 1]] == 0) ncl--;
+    st->ncl = ncl;
+    // pack: BFINAL=0, BTYPE=10, HLIT, HDIST, HCLEN, 3-bit lengths, RLE tokens
+    uint64_t acc = 0;
+    uint32_t nb = 0, w = 0;
+#define FZ_HPUT(v, n_)                                                          \
+    do {                                                                        \
+        acc |= (uint64_t)(v) << nb; nb += (n_);                                 \
+        if (nb >= 32) { st->hdr[w++] = (uint32_t)acc; acc >>= 32; nb -= 32; }   \
+    } while (0)
+    FZ_HPUT(0u, 1);
+    FZ_HPUT(2u, 2);
+    FZ_HPUT(st->hlit - 257, 5);
+    FZ_HPUT(1u, 5);  // HDIST = 2 - 1
+    FZ_HPUT(ncl - 4, 4);
+    for (uint32_t i = 0; i < ncl; i++) FZ_HPUT((uint32_t)st->cllen[order[i]], 3);
+    for (uint32_t t = 0; t < st->ntok; t++) {
+        const uint32_t tok = st->cltok[t], s = tok & 31u, ex = tok >> 5;
+        FZ_HPUT((uint32_t)st->clcode[s], (uint32_t)st->cllen[s]);
+        if (s == 16) FZ_HPUT(ex, 2);
+        else if (s == 17) FZ_HPUT(ex, 3);
+        else if (s == 18) FZ_HPUT(ex, 7);
+    }
+    st->hdr_nbits = w * 32 + nb;
+    st->hdr[w] = (uint32_t)acc;
+#undef FZ_HPUT
+}
+
+// exact size of the dynamic block from the histogram
+FZ_HD void fz_ph_cost_partial(FzEncState *st, int lane)
+{
+    uint32_t b = 0;
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
+        const int s = lane * FZ_SYMS_PER_LANE + k;
+        if (s >= FZ_NUM_LL) break;
+        const uint32_t f = (s == FZ_EOB) ? 1u : st->hist[s];
+        b += f * st->len[s];
+        if (s > FZ_EOB) b += f * (fz_len_extra_bits((uint32_t)(s - 257)) + 1);
+    }
+    st->lane_cnt[lane] = b;
+}
+
+FZ_HD void fz_ph_cost_total(FzEncState *st, int lane)
+{
+    if (lane != 0) return;
+    uint32_t b = st->hdr_nbits;
+    for (int l = 0; l < 32; l++) b += st->lane_cnt[l];
+    st->dyn_bits = b;
+}
+
+// Shannon lower bound of the literal/length coding cost in bits (an early-out for incompressible
+// sub-blocks: no Huffman code can beat it).  Host and device use log2f.
+#if defined(__CUDA_ARCH__)
+#define FZ_LOG2F(x) __log2f(x)
+#else
+#include <math.h>
+#include <string.h>
+#define FZ_LOG2F(x) log2f(x)
+#endif
+
+FZ_HD uint32_t fz_f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+FZ_HD float fz_u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+FZ_HD void fz_ph_entropy_partial(FzEncState *st, uint32_t ntokens_hint, int lane)
+{
+    (void)ntokens_hint;
+    float h = 0.f;
+    uint32_t tot = 0;
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
+        const int s = lane * FZ_SYMS_PER_LANE + k;
+        const uint32_t f = (s == FZ_EOB) ? 1u : st->hist[s];
+        if (f) { h -= (float)f * FZ_LOG2F((float)f); tot += f; }
+    }
+    st->lane_cnt[lane] = tot;
+    st->lane_bits[lane] = fz_f2u(h);
+}
+
+// true when the entropy bound says a dynamic block cannot be smaller than a stored one
+FZ_HD bool fz_entropy_says_stored(const FzEncState *st, uint32_t n)
+{
+    float h = 0.f;
+    uint32_t tot = 0;
+    for (int l = 0; l < 32; l++) { h += fz_u2f(st->lane_bits[l]); tot += st->lane_cnt[l]; }
+    h += (float)tot * FZ_LOG2F((float)tot);   // sum f*log2(tot/f)
+    // + a header of at least ~40 bytes for an alphabet this flat; keep 1% safety so that blocks the
+    // exact computation could still win by a hair are not mis-classified the other way round
+    const float bound_bytes = h * 0.125f + 40.f;
+    return bound_bytes >= (float)n * 0.995f + (float)FZ_STORED_OVERHEAD;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Piece geometry: lane l owns bytes [l*P, min(n, (l+1)*P)), P a multiple of 16.
+// -------------------------------------------------------------------------------------------------
+FZ_HD uint32_t fz_piece_len(uint32_t n) { return (((n + 31) / 32) + 15) & ~15u; }
+
+template <class Load16, class LoadByte>
+FZ_HD void fz_ph_hist(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
+{
+    const uint32_t P = fz_piece_len(n);
+    uint32_t b = lane * P, e = b + P;
+    if (e > n) e = n;
+    if (b >= e) return;
+    FzHistSink sink{st};
+    fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+}
+
+template <class Load16, class LoadByte>
+FZ_HD void fz_ph_count(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
+{
+    const uint32_t P = fz_piece_len(n);
+    uint32_t b = lane * P, e = b + P;
+    if (e > n) e = n;
+    FzCountSink sink{st, 0};
+    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    if (lane == 0) sink.bits += st->hdr_nbits;
+    st->lane_bits[lane] = sink.bits;
+}
+
+// emit this lane's tokens at its bit offset; lane 0 prepends the block header, lane 31 appends
+// EOB + the empty stored block (000, pad to byte, 00 00 FF FF)
+template <class Load16, class LoadByte>
+FZ_HD void fz_ph_emit(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
+{
+    uint32_t off = 0;
+    for (int l = 0; l < lane; l++) off += st->lane_bits[l];
+    const uint32_t P = fz_piece_len(n);
+    uint32_t b = lane * P, e = b + P;
+    if (e > n) e = n;
+    FzEmitSink sink;
+    sink.st = st;
+    sink.bw.init(out, off);
+    if (lane == 0) {
+        uint32_t nb = st->hdr_nbits, w = 0;
+        while (nb >= 32) { sink.bw.put(st->hdr[w++], 32); nb -= 32; }
+        if (nb) sink.bw.put(st->hdr[w] & ((1u << nb) - 1), nb);
+    }
+    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    if (lane == 31) {
+        sink.bw.put(st->code[FZ_EOB], st->len[FZ_EOB]);
+        sink.bw.put(0, 3);
+        sink.bw.align_byte();
+        sink.bw.put(0x0000u, 16);
+        sink.bw.put(0xFFFFu, 16);
+        st->dyn_bits = sink.bw.bitpos();  // now: total bits of the sub-block fragment (byte aligned)
+    }
+    st->fw_idx[lane] = sink.bw.first_idx;
+    st->crossed[lane] = sink.bw.crossed ? 1u : 0u;
+    if (sink.bw.crossed) { st->fw_bits[lane] = sink.bw.first_bits; st->tw_bits[lane] = (uint32_t)sink.bw.acc; }
+    else { st->fw_bits[lane] = (uint32_t)sink.bw.acc; st->tw_bits[lane] = 0; }
+}
+
+// words shared by several lanes: the lane that completes a word ORs in what earlier lanes left there
+FZ_HD void fz_ph_merge(FzEncState *st, uint32_t *out, int lane)
+{
+    uint32_t carry = 0;
+    for (int j = lane - 1; j >= 0; j--) {
+        if (st->crossed[j]) { carry |= st->tw_bits[j]; break; }
+        carry |= st->fw_bits[j];
+    }
+    if (st->crossed[lane]) out[st->fw_idx[lane]] = st->fw_bits[lane] | carry;
+    if (lane == 31) {
+        const uint32_t total_bits = st->dyn_bits;
+        if (total_bits & 31) out[total_bits >> 5] = st->crossed[31] ? st->tw_bits[31] : (st->fw_bits[31] | carry);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The whole sub-block.  Returns the fragment size in bytes, or n + FZ_STORED_OVERHEAD with
+// FZ_SIZE_STORED_FLAG set when a stored block is the better (or only safe) choice; in that case
+// nothing is written to `out` (the gather kernel synthesises stored blocks from the plane bytes).
+// On the device every lane of the warp calls this with its own `lane`; on the host `lane` is unused.
+// `out` needs room for FZ_SLOT_STRIDE bytes.
+// -------------------------------------------------------------------------------------------------
+template <class Load16, class LoadByte>
+FZ_HD uint32_t fz_encode_subblock(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n,
+                                  uint32_t *out, int lane)
+{
+    (void)lane;
+    const uint32_t stored = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG;
+    FZ_PHASE(fz_ph_zero(st, lane));
+    FZ_PHASE(fz_ph_hist(st, ld, lb, n, lane));
+    FZ_PHASE(fz_ph_entropy_partial(st, n, lane));
+    if (fz_entropy_says_stored(st, n)) return stored;
+    FZ_PHASE(fz_ph_count_active(st, lane));
+    FZ_PHASE(fz_ph_compact(st, lane));
+    {
+        uint32_t np2 = 32;
+        while (np2 < st->n_active) np2 <<= 1;
+        for (uint32_t k = 2; k <= np2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) FZ_PHASE(fz_ph_bitonic(st->keys, np2, k, j, lane));
+    }
+    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, 15, lane));
+    FZ_PHASE(fz_ph_scatter_len(st, lane));
+    FZ_PHASE(fz_ph_rank_count(st, lane));
+    FZ_PHASE(fz_ph_rank_scan(st, lane));
+    FZ_PHASE(fz_ph_assign_codes(st, lane));
+    FZ_PHASE(fz_ph_seq(st, lane));
+    FZ_PHASE(fz_ph_nzmask(st, lane));
+    FZ_PHASE(fz_ph_cl_tokens(st, lane));
+    FZ_PHASE(fz_ph_header(st, lane));
+    FZ_PHASE(fz_ph_cost_partial(st, lane));
+    FZ_PHASE(fz_ph_cost_total(st, lane));
+    // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
+    const uint32_t dyn_bytes = (st->dyn_bits + 3 + 7) / 8 + 4;
+    if (dyn_bytes >= n + FZ_STORED_OVERHEAD) return stored;
+    FZ_PHASE(fz_ph_count(st, ld, lb, n, lane));
+    FZ_PHASE(fz_ph_emit(st, ld, lb, n, out, lane));
+    FZ_PHASE(fz_ph_merge(st, out, lane));
+    return st->dyn_bits / 8;
+}
