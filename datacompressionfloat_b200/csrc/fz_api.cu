@@ -1,0 +1,420 @@
+// fz_api.cu -- the mzb_* C ABI (include/mrczip_b200.h, group 2): contexts, batching, and the
+// compress / decompress pipelines that string the kernels of fz_kernels.cu together.
+//
+// compress:   split -> encode -> layout (stream sums, RAW rule, scan, chunk headers) -> gather     per batch
+// decompress: walk -> marker scan -> classify -> inflate (fast / general) -> RAW copy -> merge      per batch
+//
+// The container offset runs on the device (FzStatus.out_end) so that batches need no host sync.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/mrczip_b200.h"
+#include "fz_kernels.h"
+
+#define FZ_CHECK(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            fprintf(stderr, "[mrczip_b200] %s:%d CUDA error: %s\n", __FILE__, __LINE__,      \
+                    cudaGetErrorString(e_));                                                 \
+            return MZB_E_CUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct mzb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t batch_chunks = 128;
+    int split_variant = 0, merge_variant = 0;
+    DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out;
+    FzStatus *d_status = nullptr;
+    FzStatus *h_status = nullptr;  // pinned
+    mzb_stats stats;
+};
+
+static int ensure(DevBuf &b, size_t need)
+{
+    if (b.cap >= need) return MZB_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    need = (need + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, need);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[mrczip_b200] cudaMalloc(%zu) failed: %s\n", need, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MZB_E_NOMEM;
+    }
+    b.cap = need;
+    return MZB_OK;
+}
+
+static void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+extern "C" const char *mzb_version(void) { return "mrczip_b200 0.1 (sm_100a; sub-block " "16 KiB" ")"; }
+
+extern "C" const char *mzb_strerror(int code)
+{
+    switch (code) {
+        case MZB_OK: return "ok";
+        case MZB_E_ARG: return "invalid argument";
+        case MZB_E_CUDA: return "CUDA error (no device, or a runtime call failed)";
+        case MZB_E_NOMEM: return "out of device memory";
+        case MZB_E_FORMAT: return "malformed container or deflate stream";
+        case MZB_E_SPACE: return "output buffer too small";
+        case MZB_E_IO: return "file I/O error";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int mzb_create(mzb_ctx **out, int device, void *cuda_stream)
+{
+    if (!out) return MZB_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[mrczip_b200] no CUDA device: this library has no CPU fallback\n");
+        cudaGetLastError();
+        return MZB_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) return MZB_E_ARG;
+    FZ_CHECK(cudaSetDevice(device));
+    mzb_ctx *c = new mzb_ctx();
+    c->device = device;
+    if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MZB_E_CUDA; }
+        c->own_stream = true;
+    }
+    if (cudaMalloc((void **)&c->d_status, sizeof(FzStatus)) != cudaSuccess ||
+        cudaHostAlloc((void **)&c->h_status, sizeof(FzStatus), cudaHostAllocDefault) != cudaSuccess) {
+        mzb_destroy(c);
+        return MZB_E_NOMEM;
+    }
+    memset(&c->stats, 0, sizeof(c->stats));
+    *out = c;
+    return MZB_OK;
+}
+
+extern "C" void mzb_destroy(mzb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out};
+    for (DevBuf *b : all) release(*b);
+    if (c->d_status) cudaFree(c->d_status);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int mzb_set_batch_chunks(mzb_ctx *c, uint32_t chunks)
+{
+    if (!c || chunks == 0 || chunks > 4096) return MZB_E_ARG;
+    c->batch_chunks = chunks;
+    return MZB_OK;
+}
+
+extern "C" int mzb_set_variant(mzb_ctx *c, int split_variant, int merge_variant)
+{
+    if (!c) return MZB_E_ARG;
+    c->split_variant = split_variant;
+    c->merge_variant = merge_variant;
+    return MZB_OK;
+}
+
+extern "C" size_t mzb_compress_bound(uint64_t nwords, uint32_t chk)
+{
+    if (chk == 0) return 0;
+    const uint64_t chunks = (nwords + chk - 1) / chk;
+    // every stream is at most n bytes (RAW rule), plus 16 bytes of header per chunk
+    return (size_t)(MZB_FILE_HEADER_BYTES + chunks * FZ_CHUNK_HEADER_BYTES + nwords * 4 + 64);
+}
+
+extern "C" int mzb_last_stats(mzb_ctx *c, mzb_stats *out)
+{
+    if (!c || !out) return MZB_E_ARG;
+    *out = c->stats;
+    return MZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static uint32_t batch_chunks_for(const mzb_ctx *c, uint32_t chk)
+{
+    // the kernels address stream (c, j) at plane_j + c * chk and need 16-byte aligned sub-blocks:
+    // a chunk size that is not a multiple of 16 (never written by the reference) goes one chunk at a time
+    return (chk % 16u) ? 1u : c->batch_chunks;
+}
+
+static int status_reset(mzb_ctx *c, uint64_t out_end)
+{
+    memset(c->h_status, 0, sizeof(FzStatus));
+    c->h_status->out_end = out_end;
+    FZ_CHECK(cudaMemcpyAsync(c->d_status, c->h_status, sizeof(FzStatus), cudaMemcpyHostToDevice, c->stream));
+    return MZB_OK;
+}
+
+static int status_fetch(mzb_ctx *c)
+{
+    FZ_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(FzStatus), cudaMemcpyDeviceToHost, c->stream));
+    FZ_CHECK(cudaStreamSynchronize(c->stream));
+    FZ_CHECK(cudaGetLastError());
+    return MZB_OK;
+}
+
+static FzBatchGeom make_geom(uint32_t nchunks, uint32_t chk, uint64_t nwords_batch, uint64_t plane_stride)
+{
+    FzBatchGeom g;
+    g.nchunks = nchunks;
+    g.chk = chk;
+    g.last_n = (uint32_t)(nwords_batch - (uint64_t)(nchunks - 1) * chk);
+    g.nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
+    g.plane_stride = plane_stride;
+    return g;
+}
+
+static uint64_t plane_stride_for(uint32_t bchunks, uint32_t chk)
+{
+    return (((uint64_t)bchunks * chk + 64) + 255) & ~(uint64_t)255;
+}
+
+extern "C" int mzb_mask_split_device(mzb_ctx *c, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,
+                                     void *d_planes, uint64_t plane_stride)
+{
+    if (!c || bits < 0 || bits > 32 || ((uintptr_t)d_words & 15) || ((uintptr_t)d_planes & 15) || (plane_stride & 15) ||
+        plane_stride < nwords)
+        return MZB_E_ARG;
+    FZ_CHECK(cudaSetDevice(c->device));
+    fz_launch_split((const uint32_t *)d_words, nwords, fz_mask_for_bits(bits), exempt_words, (uint8_t *)d_planes,
+                    plane_stride, c->split_variant, c->stream);
+    FZ_CHECK(cudaGetLastError());
+    return MZB_OK;
+}
+
+extern "C" int mzb_merge_device(mzb_ctx *c, const void *d_planes, uint64_t plane_stride, uint64_t nwords, void *d_words_out)
+{
+    if (!c || ((uintptr_t)d_words_out & 15) || ((uintptr_t)d_planes & 15) || (plane_stride & 15) || plane_stride < nwords)
+        return MZB_E_ARG;
+    FZ_CHECK(cudaSetDevice(c->device));
+    fz_launch_merge((const uint8_t *)d_planes, plane_stride, nwords, (uint32_t *)d_words_out, c->merge_variant, c->stream);
+    FZ_CHECK(cudaGetLastError());
+    return MZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,
+                                   uint32_t chk, uint64_t fsz, int write_file_header, void *d_out, size_t out_cap,
+                                   uint64_t *out_size)
+{
+    if (!c || !out_size || bits < 0 || bits > 32 || chk == 0 || chk >= 0x80000000u || ((uintptr_t)d_words & 15))
+        return MZB_E_ARG;
+    *out_size = 0;
+    memset(&c->stats, 0, sizeof(c->stats));
+    if (nwords == 0) return MZB_OK;  // reference workers.c:757-764: an empty input writes nothing, not even the header
+    FZ_CHECK(cudaSetDevice(c->device));
+    const uint64_t nchunks_total = (nwords + chk - 1) / chk;
+    const uint32_t bmax = (uint32_t)(nchunks_total < batch_chunks_for(c, chk) ? nchunks_total : batch_chunks_for(c, chk));
+    const uint64_t pstride = plane_stride_for(bmax, chk);
+    const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
+    const size_t nslots = (size_t)bmax * FZ_PLANES * nsub_full;
+    int rc;
+    if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->scratch, nslots * FZ_SLOT_STRIDE + 256)) ||
+        (rc = ensure(c->sizes, nslots * 4)) || (rc = ensure(c->sub_off, nslots * 4)) ||
+        (rc = ensure(c->stream_hdr, (size_t)bmax * FZ_PLANES * 4)) || (rc = ensure(c->stream_off, (size_t)bmax * FZ_PLANES * 8)))
+        return rc;
+
+    uint64_t start = 0;
+    if (write_file_header) {
+        if (out_cap < MZB_FILE_HEADER_BYTES) return MZB_E_SPACE;
+        // common.c:137-149: u64 fsz, u32 chk, u8 type = 0, u8 ztypes[4] = 0 (ZLIB_DEF)
+        uint8_t hdr[MZB_FILE_HEADER_BYTES];
+        memset(hdr, 0, sizeof(hdr));
+        memcpy(hdr, &fsz, 8);
+        memcpy(hdr + 8, &chk, 4);
+        FZ_CHECK(cudaMemcpyAsync(d_out, hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->stream));
+        FZ_CHECK(cudaStreamSynchronize(c->stream));  // hdr is a stack buffer
+        start = MZB_FILE_HEADER_BYTES;
+    }
+    if ((rc = status_reset(c, start))) return rc;
+
+    const uint32_t mask = fz_mask_for_bits(bits);
+    uint32_t launches = 0;
+    for (uint64_t c0 = 0; c0 < nchunks_total; c0 += bmax) {
+        const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
+        const uint64_t w0 = c0 * chk;
+        const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
+        const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
+        const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
+        fz_launch_split((const uint32_t *)d_words + w0, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
+        fz_launch_encode((const uint8_t *)c->planes.p, g, (uint8_t *)c->scratch.p, (uint32_t *)c->sizes.p, c->d_status, c->stream);
+        fz_launch_layout((const uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
+                         (unsigned long long *)c->stream_off.p, (uint8_t *)d_out, out_cap, c->d_status, c->stream);
+        fz_launch_gather((const uint8_t *)c->planes.p, (const uint8_t *)c->scratch.p, (const uint32_t *)c->sizes.p,
+                         (const uint32_t *)c->sub_off.p, (const uint32_t *)c->stream_hdr.p,
+                         (const unsigned long long *)c->stream_off.p, g, (uint8_t *)d_out, c->d_status, c->stream);
+        launches += 5 + ((nw & 3) ? 1 : 0);
+    }
+    if ((rc = status_fetch(c))) return rc;
+    c->stats.bytes_in = nwords * 4;
+    c->stats.bytes_out = c->h_status->out_end;
+    c->stats.chunks = (uint32_t)nchunks_total;
+    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
+    c->stats.raw_streams = c->h_status->n_raw_streams;
+    c->stats.stored_subblocks = c->h_status->n_stored_sub;
+    c->stats.kernel_launches = launches;
+    if (c->h_status->error) return c->h_status->error;
+    *out_size = c->h_status->out_end;
+    return MZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_size, int has_file_header, uint32_t chk,
+                                     uint64_t nwords, void *d_words_out, uint64_t out_cap_words, uint64_t *nwords_out)
+{
+    if (!c || !nwords_out || ((uintptr_t)d_words_out & 15)) return MZB_E_ARG;
+    *nwords_out = 0;
+    memset(&c->stats, 0, sizeof(c->stats));
+    FZ_CHECK(cudaSetDevice(c->device));
+    uint64_t start = 0;
+    if (has_file_header) {
+        if (in_size == 0) return MZB_OK;  // the reference writes no header for an empty file
+        if (in_size < MZB_FILE_HEADER_BYTES) return MZB_E_FORMAT;  // common.c:119-123
+        uint8_t hdr[MZB_FILE_HEADER_BYTES];
+        FZ_CHECK(cudaMemcpyAsync(hdr, d_in, sizeof(hdr), cudaMemcpyDeviceToHost, c->stream));
+        FZ_CHECK(cudaStreamSynchronize(c->stream));
+        uint64_t fsz;
+        memcpy(&fsz, hdr, 8);
+        memcpy(&chk, hdr + 8, 4);
+        for (int j = 0; j < MZB_PLANES; j++)
+            if (hdr[13 + j] != 0) return MZB_E_FORMAT;  // only ztype 0 (zlib) is ever written (workers.c:719)
+        nwords = fsz / 4;  // workers.c:577
+        start = MZB_FILE_HEADER_BYTES;
+    }
+    if (chk == 0 || chk >= 0x80000000u) return MZB_E_FORMAT;  // zip.c:325-329
+    if (nwords > out_cap_words) return MZB_E_SPACE;
+    if (nwords == 0) return MZB_OK;
+    const uint64_t nchunks_total = (nwords + chk - 1) / chk;
+    if (in_size < start + nchunks_total * FZ_CHUNK_HEADER_BYTES) return MZB_E_FORMAT;
+    const uint32_t bmax = (uint32_t)(nchunks_total < batch_chunks_for(c, chk) ? nchunks_total : batch_chunks_for(c, chk));
+    const uint64_t pstride = plane_stride_for(bmax, chk);
+    const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
+    const uint32_t nstreams = bmax * FZ_PLANES;
+    FzInflateBufs ib;
+    ib.tiles_per_stream = chk / 4096 + 2;
+    const size_t ntiles = (size_t)nstreams * ib.tiles_per_stream;
+    ib.hits_cap = (uint32_t)((size_t)nstreams * nsub_full * 2 + 1024);
+    const size_t nbsum = (ntiles + 4095) / 4096 + 2;
+    int rc;
+    if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->stream_hdr, (size_t)nstreams * 4)) ||
+        (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
+        (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
+        (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib.hits_cap * 4)))
+        return rc;
+    ib.tile_cnt = (uint32_t *)c->tile_cnt.p;
+    ib.block_sums = (uint32_t *)c->block_sums.p;
+    ib.hits = (uint32_t *)c->hits.p;
+    ib.stream_mode = (uint32_t *)c->stream_mode.p;
+    ib.stream_fail = (uint32_t *)c->stream_fail.p;
+    if ((rc = status_reset(c, start))) return rc;
+
+    uint32_t launches = 0;
+    for (uint64_t c0 = 0; c0 < nchunks_total; c0 += bmax) {
+        const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
+        const uint64_t w0 = c0 * chk;
+        const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
+        const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
+        fz_launch_walk((const uint8_t *)d_in, in_size, g, (uint32_t *)c->stream_hdr.p, (unsigned long long *)c->stream_off.p,
+                       c->d_status, c->stream);
+        fz_launch_inflate((const uint8_t *)d_in, in_size, g, (const uint32_t *)c->stream_hdr.p,
+                          (const unsigned long long *)c->stream_off.p, ib, (uint8_t *)c->planes.p, c->d_status, c->stream);
+        fz_launch_merge((const uint8_t *)c->planes.p, pstride, nw, (uint32_t *)d_words_out + w0, c->merge_variant, c->stream);
+        launches += 1 + 9 + 1 + ((nw & 3) ? 1 : 0);
+    }
+    if ((rc = status_fetch(c))) return rc;
+    c->stats.bytes_in = c->h_status->out_end;
+    c->stats.bytes_out = nwords * 4;
+    c->stats.chunks = (uint32_t)nchunks_total;
+    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
+    c->stats.general_streams = c->h_status->n_general;
+    c->stats.fast_failed = c->h_status->n_fast_failed;
+    c->stats.kernel_launches = launches;
+    if (c->h_status->error) return c->h_status->error;
+    *nwords_out = nwords;
+    return MZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer versions: H2D, device pipeline, D2H
+extern "C" int mzb_compress_host(mzb_ctx *c, const void *h_words, uint64_t nwords, int bits, uint32_t exempt_words,
+                                 uint32_t chk, uint64_t fsz, int write_file_header, void *h_out, size_t out_cap,
+                                 uint64_t *out_size)
+{
+    if (!c || !out_size || chk == 0) return MZB_E_ARG;
+    *out_size = 0;
+    if (nwords == 0) return MZB_OK;
+    FZ_CHECK(cudaSetDevice(c->device));
+    const size_t bound = mzb_compress_bound(nwords, chk);
+    int rc;
+    if ((rc = ensure(c->io_in, nwords * 4 + 256)) || (rc = ensure(c->io_out, bound + 256))) return rc;
+    FZ_CHECK(cudaMemcpyAsync(c->io_in.p, h_words, nwords * 4, cudaMemcpyHostToDevice, c->stream));
+    uint64_t sz = 0;
+    rc = mzb_compress_device(c, c->io_in.p, nwords, bits, exempt_words, chk, fsz, write_file_header, c->io_out.p, bound, &sz);
+    if (rc) return rc;
+    if (sz > out_cap) return MZB_E_SPACE;
+    FZ_CHECK(cudaMemcpyAsync(h_out, c->io_out.p, sz, cudaMemcpyDeviceToHost, c->stream));
+    FZ_CHECK(cudaStreamSynchronize(c->stream));
+    *out_size = sz;
+    return MZB_OK;
+}
+
+extern "C" int mzb_decompress_host(mzb_ctx *c, const void *h_in, size_t in_size, int has_file_header, uint32_t chk,
+                                   uint64_t nwords, void *h_words_out, uint64_t out_cap_words, uint64_t *nwords_out)
+{
+    if (!c || !nwords_out) return MZB_E_ARG;
+    *nwords_out = 0;
+    if (in_size == 0) return MZB_OK;
+    FZ_CHECK(cudaSetDevice(c->device));
+    if (has_file_header) {
+        if (in_size < MZB_FILE_HEADER_BYTES) return MZB_E_FORMAT;
+        uint64_t fsz;
+        memcpy(&fsz, h_in, 8);
+        nwords = fsz / 4;
+    }
+    if (nwords > out_cap_words) return MZB_E_SPACE;
+    int rc;
+    if ((rc = ensure(c->io_in, in_size + 256)) || (rc = ensure(c->io_out, nwords * 4 + 256))) return rc;
+    FZ_CHECK(cudaMemcpyAsync(c->io_in.p, h_in, in_size, cudaMemcpyHostToDevice, c->stream));
+    uint64_t nw = 0;
+    rc = mzb_decompress_device(c, c->io_in.p, in_size, has_file_header, chk, nwords, c->io_out.p, nwords, &nw);
+    if (rc) return rc;
+    FZ_CHECK(cudaMemcpyAsync(h_words_out, c->io_out.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+    FZ_CHECK(cudaStreamSynchronize(c->stream));
+    *nwords_out = nw;
+    return MZB_OK;
+}
+
+// pinned host memory for the C host layer (mrczip_host.c has no CUDA headers)
+extern "C" void *mzb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void mzb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}

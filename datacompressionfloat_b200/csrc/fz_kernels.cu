@@ -1,0 +1,844 @@
+// fz_kernels.cu -- hand-written sm_100a kernels of the float-zip hot path.
+//
+//   split / merge      reference workers.c:82-101,180-203 / 423-442   (HBM-bound, 8 B per word)
+//   encode             reference zip.c:164-196 (mzlib_def -> zlib deflate, Z_RLE)   one warp per 16 KiB sub-block
+//   layout + gather    reference workers.c:837-850 + zip.c:177-190,381-391          device scan of payload sizes
+//   walk               reference workers.c:52-69 (chunk header chain)
+//   marker scan, inflate (fast: one thread per sub-block; general: one thread per stream)
+//                      reference zip.c:262-284 (mzlib_inf -> zlib inflate)
+//
+// No tensor cores: nothing here is a contraction.  Integer / byte work only.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fz_deflate_enc.cuh"
+#include "fz_inflate.cuh"
+#include "fz_kernels.h"
+
+#define FZ_WARP 32
+
+// =================================================================================================
+// helpers
+// =================================================================================================
+__device__ __forceinline__ uint4 fz_ld_stream(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t fz_ld_stream32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// 4x4 byte transpose: words (AoS) <-> plane bytes (SoA); the network is its own inverse
+__device__ __forceinline__ void fz_transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                              uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
+{
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
+    const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
+    o0 = __byte_perm(t0, t1, 0x5410);
+    o1 = __byte_perm(t0, t1, 0x7632);
+    o2 = __byte_perm(t2, t3, 0x5410);
+    o3 = __byte_perm(t2, t3, 0x7632);
+}
+
+// bytes [sh, sh+16) of the 32-byte pair A||B  (sh in 0..15, warp-uniform)
+__device__ __forceinline__ uint4 fz_funnel16(uint4 A, uint4 B, uint32_t sh)
+{
+    const uint32_t r = (sh & 3) * 8;
+    uint32_t w0, w1, w2, w3, w4;
+    switch (sh >> 2) {
+        case 0: w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; break;
+        case 1: w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; break;
+        case 2: w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; break;
+        default: w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; break;
+    }
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, r);
+    o.y = __funnelshift_r(w1, w2, r);
+    o.z = __funnelshift_r(w2, w3, r);
+    o.w = __funnelshift_r(w3, w4, r);
+    return o;
+}
+
+// Warp-cooperative copy of n bytes between arbitrarily aligned global addresses: 16-byte aligned stores,
+// source re-aligned with a funnel shift.  May read up to 31 bytes past src + n inside the same
+// allocation (all our buffers carry that slack); `src_end` clamps reads for foreign buffers.
+__device__ __forceinline__ void fz_warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, const uint8_t *src_end, int lane)
+{
+    uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t nvec = n >> 4;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 15u);
+    const uint4 *s0 = (const uint4 *)(src - sh);
+    const uint4 *send = (const uint4 *)(((uintptr_t)src_end + 15u) & ~(uintptr_t)15u);
+    for (uint32_t v = lane; v < nvec; v += FZ_WARP) {
+        const uint4 A = s0[v];
+        uint4 B = A;
+        if (sh && (s0 + v + 1) < send) B = s0[v + 1];
+        ((uint4 *)dst)[v] = sh ? fz_funnel16(A, B, sh) : A;
+    }
+    const uint32_t tail = n & 15u;
+    if ((uint32_t)lane < tail) dst[(nvec << 4) + lane] = src[(nvec << 4) + lane];
+}
+
+// =================================================================================================
+// mask + byte-plane split      words[i] -> planes[j][i] = byte j of (words[i] & mask)   (i >= exempt)
+// =================================================================================================
+#define FZ_SPLIT_THREADS 256
+#define FZ_SPLIT_UNROLL 4
+
+// variant 0: warp-coalesced 128-bit loads, four 32-bit stores (one per plane) per load; every warp
+// store instruction covers one full 128-byte line.
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
+fz_split_kernel_v0(const uint4 *__restrict__ words4, uint64_t nvec, uint32_t mask, uint64_t exempt,
+                   uint8_t *__restrict__ planes, uint64_t plane_stride)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL) + threadIdx.x;
+    uint4 v[FZ_SPLIT_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint64_t i = base + (uint64_t)k * FZ_SPLIT_THREADS;
+        if (i < nvec) v[k] = fz_ld_stream(words4 + i);
+    }
+    uint32_t *p0 = (uint32_t *)planes, *p1 = (uint32_t *)(planes + plane_stride);
+    uint32_t *p2 = (uint32_t *)(planes + 2 * plane_stride), *p3 = (uint32_t *)(planes + 3 * plane_stride);
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint64_t i = base + (uint64_t)k * FZ_SPLIT_THREADS;
+        if (i < nvec) {
+            uint4 w = v[k];
+            const uint64_t wi = i * 4;
+            if (wi >= exempt) { w.x &= mask; w.y &= mask; w.z &= mask; w.w &= mask; }
+            else {
+                if (wi + 0 >= exempt) w.x &= mask;
+                if (wi + 1 >= exempt) w.y &= mask;
+                if (wi + 2 >= exempt) w.z &= mask;
+                if (wi + 3 >= exempt) w.w &= mask;
+            }
+            uint32_t a, b, c, d;
+            fz_transpose4(w.x, w.y, w.z, w.w, a, b, c, d);
+            p0[i] = a; p1[i] = b; p2[i] = c; p3[i] = d;
+        }
+    }
+}
+
+// variant 1: each thread owns 16 consecutive words (four 128-bit loads), one 128-bit store per plane
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
+fz_split_kernel_v1(const uint4 *__restrict__ words4, uint64_t nvec, uint32_t mask, uint64_t exempt,
+                   uint8_t *__restrict__ planes, uint64_t plane_stride)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * FZ_SPLIT_THREADS + threadIdx.x;  // group of 4 vectors
+    const uint64_t i0 = t * 4;
+    if (i0 >= nvec) return;
+    if (i0 + 4 <= nvec) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = words4[i0 + k];
+        uint32_t o[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 w = v[k];
+            const uint64_t wi = (i0 + k) * 4;
+            if (wi + 0 >= exempt) w.x &= mask;
+            if (wi + 1 >= exempt) w.y &= mask;
+            if (wi + 2 >= exempt) w.z &= mask;
+            if (wi + 3 >= exempt) w.w &= mask;
+            fz_transpose4(w.x, w.y, w.z, w.w, o[0][k], o[1][k], o[2][k], o[3][k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            ((uint4 *)(planes + j * plane_stride))[t] = make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+    } else {
+        for (uint64_t i = i0; i < nvec; i++) {
+            uint4 w = words4[i];
+            const uint64_t wi = i * 4;
+            if (wi + 0 >= exempt) w.x &= mask;
+            if (wi + 1 >= exempt) w.y &= mask;
+            if (wi + 2 >= exempt) w.z &= mask;
+            if (wi + 3 >= exempt) w.w &= mask;
+            uint32_t a, b, c, d;
+            fz_transpose4(w.x, w.y, w.z, w.w, a, b, c, d);
+            ((uint32_t *)planes)[i] = a;
+            ((uint32_t *)(planes + plane_stride))[i] = b;
+            ((uint32_t *)(planes + 2 * plane_stride))[i] = c;
+            ((uint32_t *)(planes + 3 * plane_stride))[i] = d;
+        }
+    }
+}
+
+// ragged tail: the last nwords % 4 words
+__global__ void fz_split_tail_kernel(const uint32_t *__restrict__ words, uint64_t first, uint64_t nwords, uint32_t mask,
+                                     uint64_t exempt, uint8_t *__restrict__ planes, uint64_t plane_stride)
+{
+    const uint64_t i = first + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t w = words[i];
+    if (i >= exempt) w &= mask;
+    for (int j = 0; j < 4; j++) planes[j * plane_stride + i] = (uint8_t)(w >> (8 * j));
+}
+
+void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint64_t exempt_words, uint8_t *planes,
+                     uint64_t plane_stride, int variant, cudaStream_t st)
+{
+    const uint64_t nvec = nwords / 4;
+    if (nvec) {
+        if (variant == 1) {
+            const uint64_t groups = (nvec + 3) / 4;
+            const unsigned grid = (unsigned)((groups + FZ_SPLIT_THREADS - 1) / FZ_SPLIT_THREADS);
+            fz_split_kernel_v1<<<grid, FZ_SPLIT_THREADS, 0, st>>>((const uint4 *)words, nvec, mask, exempt_words, planes, plane_stride);
+        } else {
+            const uint64_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
+            const unsigned grid = (unsigned)((nvec + per - 1) / per);
+            fz_split_kernel_v0<<<grid, FZ_SPLIT_THREADS, 0, st>>>((const uint4 *)words, nvec, mask, exempt_words, planes, plane_stride);
+        }
+    }
+    if (nwords & 3) fz_split_tail_kernel<<<1, 4, 0, st>>>(words, nvec * 4, nwords, mask, exempt_words, planes, plane_stride);
+}
+
+// =================================================================================================
+// byte-plane merge       words[i] = planes[0][i] | planes[1][i] << 8 | planes[2][i] << 16 | planes[3][i] << 24
+// =================================================================================================
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
+fz_merge_kernel_v0(const uint8_t *__restrict__ planes, uint64_t plane_stride, uint64_t nvec, uint4 *__restrict__ words4)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL) + threadIdx.x;
+    const uint32_t *p0 = (const uint32_t *)planes, *p1 = (const uint32_t *)(planes + plane_stride);
+    const uint32_t *p2 = (const uint32_t *)(planes + 2 * plane_stride), *p3 = (const uint32_t *)(planes + 3 * plane_stride);
+    uint32_t a[FZ_SPLIT_UNROLL], b[FZ_SPLIT_UNROLL], c[FZ_SPLIT_UNROLL], d[FZ_SPLIT_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint64_t i = base + (uint64_t)k * FZ_SPLIT_THREADS;
+        if (i < nvec) { a[k] = fz_ld_stream32(p0 + i); b[k] = fz_ld_stream32(p1 + i); c[k] = fz_ld_stream32(p2 + i); d[k] = fz_ld_stream32(p3 + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint64_t i = base + (uint64_t)k * FZ_SPLIT_THREADS;
+        if (i < nvec) {
+            uint4 w;
+            fz_transpose4(a[k], b[k], c[k], d[k], w.x, w.y, w.z, w.w);
+            words4[i] = w;
+        }
+    }
+}
+
+// variant 1: one 128-bit load per plane (16 words per thread), four 128-bit stores
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
+fz_merge_kernel_v1(const uint8_t *__restrict__ planes, uint64_t plane_stride, uint64_t nvec, uint4 *__restrict__ words4)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * FZ_SPLIT_THREADS + threadIdx.x;
+    const uint64_t i0 = t * 4;
+    if (i0 >= nvec) return;
+    if (i0 + 4 <= nvec) {
+        uint4 p[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[j] = fz_ld_stream((const uint4 *)(planes + j * plane_stride) + t);
+        uint4 w;
+        fz_transpose4(p[0].x, p[1].x, p[2].x, p[3].x, w.x, w.y, w.z, w.w); words4[i0 + 0] = w;
+        fz_transpose4(p[0].y, p[1].y, p[2].y, p[3].y, w.x, w.y, w.z, w.w); words4[i0 + 1] = w;
+        fz_transpose4(p[0].z, p[1].z, p[2].z, p[3].z, w.x, w.y, w.z, w.w); words4[i0 + 2] = w;
+        fz_transpose4(p[0].w, p[1].w, p[2].w, p[3].w, w.x, w.y, w.z, w.w); words4[i0 + 3] = w;
+    } else {
+        for (uint64_t i = i0; i < nvec; i++) {
+            uint4 w;
+            fz_transpose4(((const uint32_t *)planes)[i], ((const uint32_t *)(planes + plane_stride))[i],
+                          ((const uint32_t *)(planes + 2 * plane_stride))[i], ((const uint32_t *)(planes + 3 * plane_stride))[i],
+                          w.x, w.y, w.z, w.w);
+            words4[i] = w;
+        }
+    }
+}
+
+__global__ void fz_merge_tail_kernel(const uint8_t *__restrict__ planes, uint64_t plane_stride, uint64_t first, uint64_t nwords,
+                                     uint32_t *__restrict__ words)
+{
+    const uint64_t i = first + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t w = 0;
+    for (int j = 0; j < 4; j++) w |= (uint32_t)planes[j * plane_stride + i] << (8 * j);
+    words[i] = w;
+}
+
+void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwords, uint32_t *words, int variant, cudaStream_t st)
+{
+    const uint64_t nvec = nwords / 4;
+    if (nvec) {
+        if (variant == 1) {
+            const uint64_t groups = (nvec + 3) / 4;
+            const unsigned grid = (unsigned)((groups + FZ_SPLIT_THREADS - 1) / FZ_SPLIT_THREADS);
+            fz_merge_kernel_v1<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, plane_stride, nvec, (uint4 *)words);
+        } else {
+            const uint64_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
+            const unsigned grid = (unsigned)((nvec + per - 1) / per);
+            fz_merge_kernel_v0<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, plane_stride, nvec, (uint4 *)words);
+        }
+    }
+    if (nwords & 3) fz_merge_tail_kernel<<<1, 4, 0, st>>>(planes, plane_stride, nvec * 4, nwords, words);
+}
+
+// =================================================================================================
+// deflate: one warp per sub-block
+// =================================================================================================
+#define FZ_ENC_WARPS 4
+#define FZ_STAGE_BYTES (32 * (FZ_SUB / 32 + 16))
+
+struct __align__(16) FzEncSmem {
+    FzEncState st;
+    alignas(16) uint8_t stage[FZ_STAGE_BYTES];
+};
+
+size_t fz_encode_smem_bytes() { return sizeof(FzEncSmem) * FZ_ENC_WARPS; }
+
+struct DevLoad16 {
+    const uint8_t *sm;
+    uint32_t adj;  // lane * 16: the padding in front of this lane's piece
+    __device__ __forceinline__ FzVec16 operator()(uint32_t i) const
+    {
+        const uint4 v = *(const uint4 *)(sm + i + adj);
+        FzVec16 r;
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        return r;
+    }
+};
+struct DevLoadByte {
+    const uint8_t *sm;
+    uint32_t P;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return sm[i + (i / P) * 16]; }
+};
+
+__device__ __forceinline__ const uint8_t *fz_sub_src(const uint8_t *planes, const FzBatchGeom &g, uint32_t s, uint32_t k)
+{
+    const uint32_t c = s >> 2, j = s & 3;
+    return planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk + (uint64_t)k * FZ_SUB;
+}
+
+__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
+fz_encode_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint8_t *__restrict__ scratch,
+                 uint32_t *__restrict__ sizes, FzStatus *status)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
+    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
+    if (t >= total) return;
+    const uint32_t s = t / g.nsub_full, k = t - s * g.nsub_full;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t off = k * FZ_SUB;
+    if (off >= n_s) return;
+    const uint32_t n = min((uint32_t)FZ_SUB, n_s - off);
+    FzEncSmem *sm = (FzEncSmem *)fz_smem + warp;
+    const uint8_t *src = fz_sub_src(planes, g, s, k);
+
+    // stage the sub-block: lane l's piece [l*P, (l+1)*P) is stored at l*(P+16) (bank-conflict-free 128-bit reads)
+    const uint32_t P = fz_piece_len(n);
+    if (((uintptr_t)src & 15u) == 0) {
+        for (uint32_t i = lane * 16; i < n; i += FZ_WARP * 16) {
+            const uint4 v = *(const uint4 *)(src + i);
+            *(uint4 *)(sm->stage + i + (i / P) * 16) = v;
+        }
+    } else {
+        for (uint32_t i = lane; i < n; i += FZ_WARP) sm->stage[i + (i / P) * 16] = src[i];
+    }
+    __syncwarp();
+
+    DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
+    DevLoadByte lb{sm->stage, P};
+    uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
+    const uint32_t r = fz_encode_subblock(&sm->st, ld, lb, n, out, lane);
+    if (lane == 0) {
+        sizes[t] = r;
+        if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
+    }
+}
+
+void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint8_t *scratch, uint32_t *sizes, FzStatus *status, cudaStream_t st)
+{
+    cudaFuncSetAttribute(fz_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_encode_smem_bytes());
+    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
+    const unsigned grid = (total + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS;
+    fz_encode_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, fz_encode_smem_bytes(), st>>>(planes, g, scratch, sizes, status);
+}
+
+// =================================================================================================
+// layout: per-stream sums + RAW rule, scan over chunk records, chunk headers
+// =================================================================================================
+__device__ __forceinline__ uint32_t fz_warp_incl_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// one warp per stream: sub_off[t] = exclusive prefix of the sub-block sizes inside the stream;
+// stream_hdr[s] = payload length | RAW flag, with the reference's rule "compressed iff n > len + 4" (zip.c:177)
+__global__ void __launch_bounds__(128)
+fz_layout_streams_kernel(const uint32_t *__restrict__ sizes, FzBatchGeom g, uint32_t *__restrict__ sub_off,
+                         uint32_t *__restrict__ stream_hdr, FzStatus *status)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (s >= g.nchunks * FZ_PLANES) return;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t nsub = (n_s + FZ_SUB - 1) / FZ_SUB;
+    uint32_t carry = 0;
+    for (uint32_t k0 = 0; k0 < nsub; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const uint32_t v = k < nsub ? (sizes[s * g.nsub_full + k] & ~FZ_SIZE_STORED_FLAG) : 0u;
+        const uint32_t inc = fz_warp_incl_scan(v, lane);
+        if (k < nsub) sub_off[s * g.nsub_full + k] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+        const bool compressed = n_s > carry + 4u;
+        stream_hdr[s] = compressed ? carry : (n_s | FZ_RAW_FLAG);
+        if (!compressed) atomicAdd(&status->n_raw_streams, 1u);
+    }
+}
+
+// single block: exclusive scan of the chunk record sizes (16 + four payloads), starting at status->out_end;
+// writes the 16-byte chunk headers (reference workers.c:837-842) and the payload offset of every stream.
+#define FZ_LAYOUT_THREADS 1024
+__global__ void __launch_bounds__(FZ_LAYOUT_THREADS)
+fz_layout_chunks_kernel(const uint32_t *__restrict__ stream_hdr, FzBatchGeom g, unsigned long long *__restrict__ stream_off,
+                        uint8_t *__restrict__ container, uint64_t container_cap, FzStatus *status)
+{
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long base_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_sh = status->out_end;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < g.nchunks; c0 += FZ_LAYOUT_THREADS) {
+        const uint32_t c = c0 + threadIdx.x;
+        uint32_t h[4] = {0, 0, 0, 0};
+        unsigned long long rec = 0;
+        if (c < g.nchunks) {
+            rec = FZ_CHUNK_HEADER_BYTES;
+            for (int j = 0; j < 4; j++) { h[j] = stream_hdr[c * 4 + j]; rec += h[j] & ~FZ_RAW_FLAG; }
+        }
+        // block exclusive scan of rec
+        unsigned long long inc = rec;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - ws;  // exclusive
+        }
+        __syncthreads();
+        const unsigned long long base = base_sh;
+        const unsigned long long off = base + warp_sums[warp] + inc - rec;
+        if (c < g.nchunks) {
+            if (off + rec > container_cap) atomicCAS(&status->error, 0, FZ_E_SPACE);
+            else {
+                unsigned long long p = off + FZ_CHUNK_HEADER_BYTES;
+                for (int j = 0; j < 4; j++) {
+                    // pack_header (reference zip.c:381-391): little-endian length, bit 31 = RAW
+                    container[off + 4 * j + 0] = (uint8_t)(h[j]);
+                    container[off + 4 * j + 1] = (uint8_t)(h[j] >> 8);
+                    container[off + 4 * j + 2] = (uint8_t)(h[j] >> 16);
+                    container[off + 4 * j + 3] = (uint8_t)(h[j] >> 24);
+                    stream_off[c * 4 + j] = p;
+                    p += h[j] & ~FZ_RAW_FLAG;
+                }
+            }
+        }
+        __syncthreads();
+        // total of this tile = exclusive offset of the last thread + its value
+        if (threadIdx.x == FZ_LAYOUT_THREADS - 1) base_sh = off + rec;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) status->out_end = base_sh;
+}
+
+void fz_launch_layout(const uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
+                      unsigned long long *stream_off, uint8_t *container, uint64_t container_cap, FzStatus *status, cudaStream_t st)
+{
+    const uint32_t nstreams = g.nchunks * FZ_PLANES;
+    fz_layout_streams_kernel<<<(nstreams + 3) / 4, 128, 0, st>>>(sizes, g, sub_off, stream_hdr, status);
+    fz_layout_chunks_kernel<<<1, FZ_LAYOUT_THREADS, 0, st>>>(stream_hdr, g, stream_off, container, container_cap, status);
+}
+
+// one warp per sub-block: move the encoded fragment (or the raw / stored plane bytes) to its place in the container
+__global__ void __launch_bounds__(128)
+fz_gather_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ scratch, const uint32_t *__restrict__ sizes,
+                 const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ stream_hdr,
+                 const unsigned long long *__restrict__ stream_off, FzBatchGeom g, uint8_t *__restrict__ container,
+                 const FzStatus *status)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
+    if (t >= total || status->error) return;
+    const uint32_t s = t / g.nsub_full, k = t - s * g.nsub_full;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t off = k * FZ_SUB;
+    if (off >= n_s) return;
+    const uint32_t n = min((uint32_t)FZ_SUB, n_s - off);
+    const uint8_t *psrc = fz_sub_src(planes, g, s, k);
+    uint8_t *dst = container + stream_off[s];
+    if (stream_hdr[s] & FZ_RAW_FLAG) {
+        fz_warp_copy(dst + off, psrc, n, psrc + n + 32, lane);
+        return;
+    }
+    dst += sub_off[t];
+    const uint32_t sz = sizes[t];
+    if (sz & FZ_SIZE_STORED_FLAG) {
+        // stored block (BFINAL=0, BTYPE=00, LEN, NLEN) + data + empty stored block
+        if (lane == 0) {
+            dst[0] = 0x00;
+            dst[1] = (uint8_t)n; dst[2] = (uint8_t)(n >> 8);
+            dst[3] = (uint8_t)~n; dst[4] = (uint8_t)(~n >> 8);
+            uint8_t *t5 = dst + 5 + n;
+            t5[0] = 0x00; t5[1] = 0x00; t5[2] = 0x00; t5[3] = 0xFF; t5[4] = 0xFF;
+        }
+        fz_warp_copy(dst + 5, psrc, n, psrc + n + 32, lane);
+    } else {
+        const uint8_t *ssrc = scratch + (uint64_t)t * FZ_SLOT_STRIDE;
+        fz_warp_copy(dst, ssrc, sz, ssrc + FZ_SLOT_STRIDE, lane);
+    }
+}
+
+void fz_launch_gather(const uint8_t *planes, const uint8_t *scratch, const uint32_t *sizes, const uint32_t *sub_off,
+                      const uint32_t *stream_hdr, const unsigned long long *stream_off, FzBatchGeom g, uint8_t *container,
+                      const FzStatus *status, cudaStream_t st)
+{
+    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
+    fz_gather_kernel<<<(total + 3) / 4, 128, 0, st>>>(planes, scratch, sizes, sub_off, stream_hdr, stream_off, g, container, status);
+}
+
+// =================================================================================================
+// inflate side
+// =================================================================================================
+
+// chunk-header chain (reference workers.c:61-69): serial by nature, 16 bytes per hop
+__global__ void fz_walk_kernel(const uint8_t *__restrict__ container, uint64_t container_size, FzBatchGeom g,
+                               uint32_t *__restrict__ stream_hdr, unsigned long long *__restrict__ stream_off, FzStatus *status)
+{
+    if (threadIdx.x != 0 || status->error) return;
+    unsigned long long off = status->out_end;
+    for (uint32_t c = 0; c < g.nchunks; c++) {
+        if (off + FZ_CHUNK_HEADER_BYTES > container_size) { status->error = FZ_E_FORMAT; return; }
+        uint8_t b[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i] = container[off + i];
+        off += FZ_CHUNK_HEADER_BYTES;
+        const uint32_t n_s = (c == g.nchunks - 1) ? g.last_n : g.chk;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            // unpack_header (reference zip.c:394-399)
+            const uint32_t h = (uint32_t)b[4 * j] | ((uint32_t)b[4 * j + 1] << 8) | ((uint32_t)b[4 * j + 2] << 16) | ((uint32_t)b[4 * j + 3] << 24);
+            const uint32_t len = h & ~FZ_RAW_FLAG;
+            if ((h & FZ_RAW_FLAG) && len != n_s) { status->error = FZ_E_FORMAT; return; }
+            if (off + len > container_size) { status->error = FZ_E_FORMAT; return; }
+            stream_hdr[c * 4 + j] = h;
+            stream_off[c * 4 + j] = off;
+            off += len;
+        }
+    }
+    status->out_end = off;
+}
+
+void fz_launch_walk(const uint8_t *container, uint64_t container_size, FzBatchGeom g, uint32_t *stream_hdr,
+                    unsigned long long *stream_off, FzStatus *status, cudaStream_t st)
+{
+    fz_walk_kernel<<<1, 32, 0, st>>>(container, container_size, g, stream_hdr, stream_off, status);
+}
+
+// ---- sync-marker scan: positions p (stream relative) with bytes p..p+3 == 00 00 FF FF
+#define FZ_TILE_BYTES 4096
+#define FZ_SCAN_THREADS 256
+
+__device__ __forceinline__ uint32_t fz_marker_mask(const uint8_t *base, uint32_t len, uint32_t p0)
+{
+    // 16 candidate positions p0 .. p0+15; needs bytes [p0, p0+19)
+    if (p0 + 4 > len) return 0;
+    const uint8_t *addr = base + p0;
+    const uint32_t sk = (uint32_t)((uintptr_t)addr & 3u);
+    const uint32_t *a0 = (const uint32_t *)(addr - sk);
+    const uint32_t *aend = (const uint32_t *)(((uintptr_t)(base + len) + 3u) & ~(uintptr_t)3u);
+    uint32_t W[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) W[k] = (a0 + k) < aend ? a0[k] : 0u;
+    uint32_t V[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) V[k] = __funnelshift_r(W[k], W[k + 1], sk * 8);
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const uint32_t v = __funnelshift_r(V[b >> 2], V[(b >> 2) + 1], (b & 3) * 8);
+        if (v == 0xFFFF0000u && p0 + b + 4 <= len) m |= 1u << b;
+    }
+    return m;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(FZ_SCAN_THREADS)
+fz_marker_kernel(const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
+                 const unsigned long long *__restrict__ stream_off, uint32_t tiles_per_stream, uint32_t *__restrict__ tile_cnt,
+                 uint32_t *__restrict__ hits, uint32_t hits_cap, const FzStatus *status)
+{
+    __shared__ uint32_t wsum[FZ_SCAN_THREADS / 32];
+    const uint32_t b = blockIdx.x;
+    if (status->error) {  // a broken chunk chain leaves the stream table undefined: touch nothing
+        if (!WRITE && threadIdx.x == 0) tile_cnt[b] = 0;
+        return;
+    }
+    const uint32_t s = b / tiles_per_stream, tile = b - s * tiles_per_stream;
+    const uint32_t h = stream_hdr[s];
+    const uint32_t len = h & ~FZ_RAW_FLAG;
+    const bool skip = (h & FZ_RAW_FLAG) || (uint64_t)tile * FZ_TILE_BYTES + 4 > len;
+    uint32_t out_base = 0;
+    if (WRITE) {
+        out_base = tile_cnt[b];
+        if (skip || tile_cnt[b + 1] == out_base) return;
+    } else if (skip) {
+        if (threadIdx.x == 0) tile_cnt[b] = 0;
+        return;
+    }
+    const uint32_t p0 = tile * FZ_TILE_BYTES + threadIdx.x * 16;
+    const uint32_t m = fz_marker_mask(container + stream_off[s], len, p0);
+    const uint32_t cnt = __popc(m);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = fz_warp_incl_scan(cnt, lane);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FZ_SCAN_THREADS / 32; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+    if (!WRITE) {
+        if (threadIdx.x == 0) tile_cnt[b] = total;
+    } else {
+        uint32_t o = out_base + wbase + inc - cnt;
+        uint32_t mm = m;
+        while (mm) {
+            const int bit = __ffs((int)mm) - 1;
+            mm &= mm - 1;
+            if (o < hits_cap) hits[o] = p0 + (uint32_t)bit;
+            o++;
+        }
+    }
+}
+
+// ---- exclusive scan of a uint32 array (n elements, writes n + 1: the last is the total)
+#define FZ_XS_THREADS 256
+#define FZ_XS_ITEMS 16
+#define FZ_XS_TILE (FZ_XS_THREADS * FZ_XS_ITEMS)
+
+__global__ void __launch_bounds__(FZ_XS_THREADS)
+fz_xscan_reduce_kernel(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ bsum)
+{
+    __shared__ uint32_t wsum[FZ_XS_THREADS / 32];
+    const uint32_t base = blockIdx.x * FZ_XS_TILE + threadIdx.x * FZ_XS_ITEMS;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < FZ_XS_ITEMS; i++) if (base + i < n) v += a[base + i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < FZ_XS_THREADS / 32; w++) t += wsum[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) fz_xscan_top_kernel(uint32_t *__restrict__ bsum, uint32_t nb)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nb; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < nb ? bsum[i] : 0u;
+        const uint32_t inc = fz_warp_incl_scan(v, lane);
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ws = wsum[lane];
+            const uint32_t wi = fz_warp_incl_scan(ws, lane);
+            wsum[lane] = wi - ws;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_sh;
+        const uint32_t ex = carry + wsum[warp] + inc - v;
+        if (i < nb) bsum[i] = ex;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_sh = ex + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bsum[nb] = carry_sh;
+}
+
+__global__ void __launch_bounds__(FZ_XS_THREADS)
+fz_xscan_apply_kernel(uint32_t *__restrict__ a, uint32_t n, const uint32_t *__restrict__ bsum, uint32_t nb)
+{
+    __shared__ uint32_t wsum[FZ_XS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * FZ_XS_TILE + threadIdx.x * FZ_XS_ITEMS;
+    uint32_t x[FZ_XS_ITEMS];
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < FZ_XS_ITEMS; i++) { x[i] = base + i < n ? a[base + i] : 0u; v += x[i]; }
+    const uint32_t inc = fz_warp_incl_scan(v, lane);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < FZ_XS_THREADS / 32; w++) if (w < warp) wbase += wsum[w];
+    uint32_t run = bsum[blockIdx.x] + wbase + inc - v;
+#pragma unroll
+    for (int i = 0; i < FZ_XS_ITEMS; i++) { if (base + i < n) a[base + i] = run; run += x[i]; }
+    if (blockIdx.x == nb - 1 && threadIdx.x == 0) a[n] = bsum[nb];
+}
+
+static void fz_exclusive_scan(uint32_t *a, uint32_t n, uint32_t *bsum, cudaStream_t st)
+{
+    const uint32_t nb = (n + FZ_XS_TILE - 1) / FZ_XS_TILE;
+    fz_xscan_reduce_kernel<<<nb, FZ_XS_THREADS, 0, st>>>(a, n, bsum);
+    fz_xscan_top_kernel<<<1, 1024, 0, st>>>(bsum, nb);
+    fz_xscan_apply_kernel<<<nb, FZ_XS_THREADS, 0, st>>>(a, n, bsum, nb);
+}
+
+// ---- classify streams: RAW, fast (our sub-block framing: one marker per sub-block, last one ends the payload), general
+__global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBatchGeom g, const uint32_t *__restrict__ tile_off,
+                                   uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, uint32_t hits_cap,
+                                   uint32_t *__restrict__ stream_mode, uint32_t *__restrict__ stream_fail, const FzStatus *status)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.nchunks * FZ_PLANES) return;
+    stream_fail[s] = 0;
+    if (status->error) { stream_mode[s] = 0; return; }
+    const uint32_t h = stream_hdr[s];
+    if (h & FZ_RAW_FLAG) { stream_mode[s] = 0; return; }
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t h0 = tile_off[s * tiles_per_stream], h1 = tile_off[(s + 1) * tiles_per_stream];
+    const uint32_t m = h1 - h0;
+    uint32_t mode = 2;
+    if (m >= 1 && h1 <= hits_cap && hits[h1 - 1] + 4 == h) {
+        for (int L = 15; L >= 10; L--) {
+            if (((n_s + (1u << L) - 1) >> L) == m) { mode = 1u | ((uint32_t)L << 8); break; }
+        }
+    }
+    stream_mode[s] = mode;
+}
+
+// ---- fast path: one THREAD per sub-block fragment
+#define FZ_INF_THREADS 64
+__global__ void __launch_bounds__(FZ_INF_THREADS)
+fz_inflate_fast_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
+                       const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ tile_off,
+                       uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
+                       uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, const FzStatus *status)
+{
+    __shared__ uint16_t tabs[320 * FZ_INF_THREADS];
+    if (status->error) return;
+    const uint32_t nstreams = g.nchunks * FZ_PLANES;
+    const uint32_t total_hits = tile_off[nstreams * tiles_per_stream];
+    const uint32_t hidx = blockIdx.x * FZ_INF_THREADS + threadIdx.x;
+    if (hidx >= total_hits) return;
+    // stream owning this hit: largest s with tile_off[s * tps] <= hidx
+    uint32_t lo = 0, hi = nstreams;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tile_off[mid * tiles_per_stream] <= hidx) lo = mid; else hi = mid;
+    }
+    const uint32_t s = lo;
+    const uint32_t mode = stream_mode[s];
+    if ((mode & 0xffu) != 1u) return;
+    const uint32_t L = mode >> 8;
+    const uint32_t k = hidx - tile_off[s * tiles_per_stream];
+    const uint32_t start = k ? hits[hidx - 1] + 4 : 0u;
+    const uint32_t end = hits[hidx] + 4;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t obeg = k << L;
+    const uint32_t expect = min(1u << L, n_s - obeg);
+    uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
+    FzInfTab<FZ_INF_THREADS> tab{tabs + threadIdx.x, tabs + 288 * FZ_INF_THREADS + threadIdx.x};
+    uint32_t out_n = 0;
+    size_t used = 0;
+    const int rc = fz_inflate(container + stream_off[s] + start, (size_t)(end - start), out, expect, tab, &out_n, &used);
+    if (rc != FZ_INF_OK || out_n != expect || used != (size_t)(end - start)) atomicExch(&stream_fail[s], 1u);
+}
+
+// ---- general path: one thread per stream (reference-made streams: back-to-back blocks, no byte alignment between them)
+__global__ void __launch_bounds__(32)
+fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
+                          const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_mode,
+                          const uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, FzStatus *status)
+{
+    __shared__ uint16_t tabs[320];
+    const uint32_t s = blockIdx.x;
+    if (threadIdx.x != 0 || status->error) return;
+    const uint32_t mode = stream_mode[s] & 0xffu;
+    const bool failed = mode == 1u && stream_fail[s];
+    if (!(mode == 2u || failed)) return;
+    if (failed) atomicAdd(&status->n_fast_failed, 1u);
+    atomicAdd(&status->n_general, 1u);
+    const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk;
+    FzInfTab<1> tab{tabs, tabs + 288};
+    uint32_t out_n = 0;
+    size_t used = 0;
+    const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used);
+    if (rc != FZ_INF_OK || out_n != n_s) atomicCAS(&status->error, 0, FZ_E_FORMAT);
+}
+
+// ---- RAW payloads: verbatim plane bytes (reference zip.c:264-267)
+__global__ void __launch_bounds__(128)
+fz_rawcopy_kernel(const uint8_t *__restrict__ container, uint64_t container_size, FzBatchGeom g,
+                  const uint32_t *__restrict__ stream_hdr, const unsigned long long *__restrict__ stream_off,
+                  uint8_t *__restrict__ planes, const FzStatus *status)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
+    if (t >= total || status->error) return;
+    const uint32_t s = t / g.nsub_full, k = t - s * g.nsub_full;
+    if (!(stream_hdr[s] & FZ_RAW_FLAG)) return;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t off = k * FZ_SUB;
+    if (off >= n_s) return;
+    const uint32_t n = min((uint32_t)FZ_SUB, n_s - off);
+    uint8_t *dst = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + off;
+    fz_warp_copy(dst, container + stream_off[s] + off, n, container + container_size, lane);
+}
+
+void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
+                       const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status, cudaStream_t st)
+{
+    const uint32_t nstreams = g.nchunks * FZ_PLANES;
+    const uint32_t ntiles = nstreams * b.tiles_per_stream;
+    fz_marker_kernel<false><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
+    fz_exclusive_scan(b.tile_cnt, ntiles, b.block_sums, st);
+    fz_marker_kernel<true><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
+    fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, status);
+    // the hit count lives on the device; launch for the capacity and let surplus threads exit
+    const uint32_t max_hits = b.hits_cap;
+    fz_inflate_fast_kernel<<<(max_hits + FZ_INF_THREADS - 1) / FZ_INF_THREADS, FZ_INF_THREADS, 0, st>>>(
+        container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, planes, status);
+    fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, planes, status);
+    const uint32_t total = nstreams * g.nsub_full;
+    fz_rawcopy_kernel<<<(total + 3) / 4, 128, 0, st>>>(container, container_size, g, stream_hdr, stream_off, planes, status);
+}

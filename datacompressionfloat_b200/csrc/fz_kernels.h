@@ -1,0 +1,68 @@
+// fz_kernels.h -- launch wrappers of the sm_100a kernels (internal C++ interface between fz_kernels.cu and fz_api.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fz_common.cuh"
+
+// geometry of one batch of chunks handed to the kernels
+struct FzBatchGeom {
+    uint32_t nchunks;      // chunks in this batch
+    uint32_t chk;          // words per full chunk (== plane bytes per full stream)
+    uint32_t last_n;       // words in the last chunk of the batch (== chk unless it is the ragged file tail)
+    uint32_t nsub_full;    // ceil(chk / FZ_SUB): sub-block slots reserved per stream
+    uint64_t plane_stride; // bytes between plane j and plane j+1 in the plane buffer
+};
+
+static inline uint32_t fz_stream_n(const FzBatchGeom &g, uint32_t stream)
+{
+    return (stream / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+}
+
+// device status block (one per context)
+struct FzStatus {
+    unsigned long long out_end;   // running end offset of the container being written / read
+    int error;                    // first FZ_E_* raised by a kernel
+    unsigned int n_general;       // streams decoded by the general (one thread per stream) inflater
+    unsigned int n_fast_failed;   // streams whose sub-block decode failed validation and fell back
+    unsigned int n_stored_sub;    // sub-blocks emitted as stored blocks
+    unsigned int n_raw_streams;   // streams written RAW
+    unsigned int pad;
+};
+
+// ---- mask + byte-plane split / merge (HBM-bound)
+void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint64_t exempt_words,
+                     uint8_t *planes, uint64_t plane_stride, int variant, cudaStream_t st);
+void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwords, uint32_t *words,
+                     int variant, cudaStream_t st);
+
+// ---- deflate side
+void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint8_t *scratch, uint32_t *sizes, FzStatus *status,
+                      cudaStream_t st);
+// stream sums + RAW decision + scan over chunk records + chunk headers; container offsets continue from status->out_end
+void fz_launch_layout(const uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
+                      unsigned long long *stream_off, uint8_t *container, uint64_t container_cap, FzStatus *status,
+                      cudaStream_t st);
+void fz_launch_gather(const uint8_t *planes, const uint8_t *scratch, const uint32_t *sizes, const uint32_t *sub_off,
+                      const uint32_t *stream_hdr, const unsigned long long *stream_off, FzBatchGeom g,
+                      uint8_t *container, const FzStatus *status, cudaStream_t st);
+
+// ---- inflate side
+// walks nchunks chunk records starting at status->out_end, fills the stream table, advances status->out_end
+void fz_launch_walk(const uint8_t *container, uint64_t container_size, FzBatchGeom g, uint32_t *stream_hdr,
+                    unsigned long long *stream_off, FzStatus *status, cudaStream_t st);
+// marker scan (count), scan, marker scan (write), classify, fast inflate, general inflate, RAW copy
+struct FzInflateBufs {
+    uint32_t *tile_cnt;      // [nstreams * tiles_per_stream + 1] counts -> exclusive offsets
+    uint32_t *block_sums;    // scan scratch
+    uint32_t *hits;          // marker positions (stream relative), capacity hits_cap
+    uint32_t hits_cap;
+    uint32_t *stream_mode;   // [nstreams] 0 raw, 1 fast | sub_log2 << 8, 2 general
+    uint32_t *stream_fail;   // [nstreams]
+    uint32_t tiles_per_stream;
+};
+void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
+                       const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status,
+                       cudaStream_t st);
+
+size_t fz_encode_smem_bytes();

@@ -1,0 +1,179 @@
+/*
+ * mrczip_b200.h -- C ABI of libmrczip_b200.so: the B200 (sm_100a) drop-in for the float32
+ * compress / decompress hot path of ruanhuabin/DataCompressionFloat.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The reference's own names and signatures, so a reference build can link this library
+ *      instead of its src/core objects (boundary B of SURVEY.md):
+ *        run_compress / run_uncompress        reference src/include/workers.h:30-31
+ *        zip_compress / zip_uncompress        reference src/include/adapt.h:30-31
+ *        pack_header / unpack_header          reference src/include/mrczip.h:123-124
+ *        init/read/write/print_mrczip_header, init/reset/update_context, print_context_info,
+ *        get_file_size, now_sec               reference src/include/common.h:43-81
+ *        isTestThroughput                     reference src/core/workers.c:39
+ *      Types ctx_t and mrczip_header_t are layout-compatible with common.h:33-56.
+ *
+ *  (2) mzb_* : the thin CUDA layer underneath (plain pointers and sizes, no torch types), for
+ *      callers that already hold the data in host or device memory.
+ *
+ * Conventions: every function returns 0 on success (the reference's only return value) and a
+ * negative MZB_E_* where the reference would exit(-1) or silently produce garbage.  There is NO CPU
+ * fallback: without a CUDA device the calls fail with MZB_E_CUDA.
+ */
+#ifndef MRCZIP_B200_H_
+#define MRCZIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MZB_OK 0
+#define MZB_E_ARG (-1)
+#define MZB_E_CUDA (-2)
+#define MZB_E_NOMEM (-3)
+#define MZB_E_FORMAT (-4)
+#define MZB_E_SPACE (-5)
+#define MZB_E_IO (-6)
+
+#define MZB_PLANES 4                     /* constant.h:27 COMPRESSION_PATH_NUM */
+#define MZB_CHUNK_WORDS (6u * 1048576u)  /* constant.h:25 CHUNK_SIZE (elements) */
+#define MZB_FILE_HEADER_BYTES 17         /* common.c:137-149 */
+#define MZB_MRC_HEADER_WORDS 256         /* workers.c:90-94 */
+
+/* ------------------------------------------------------------------ (1) reference-named interface */
+
+/* common.h:33-41 */
+typedef struct _context_t {
+    uint32_t fileCount;
+    uint64_t allFileSize;
+    uint64_t allZipFileSize;
+    double zipTime;
+    double unzipTime;
+} ctx_t;
+
+/* common.h:50-56 (COMPRESSION_PATH_NUM == 4) */
+typedef struct _mrczip_header_t {
+    uint64_t fsz;
+    uint32_t chk;
+    char type;
+    char ztypes[MZB_PLANES];
+} mrczip_header_t;
+
+/* mrczip.h:31-34 */
+typedef enum { COMPRESSED = 0, RAW } btype_t;
+
+extern int isTestThroughput; /* workers.c:39: 1 = suppress every fwrite */
+
+/* workers.h:30: fin at offset 0; writes the 17-byte file header + chunk records to fout.
+ * compressPrecision = bits to erase, 0..32 (values outside are rejected with MZB_E_ARG; the reference
+ * indexes its 33-entry table unchecked).  dataConvertedType must be "float" ("int" is out of scope). */
+int run_compress(FILE *fin, ctx_t *ctx, FILE *fout, const int compressPrecision, const char *dataConvertedType);
+/* workers.h:31: fin positioned just past the 17-byte header the caller already parsed into hd. */
+int run_uncompress(FILE *fin, ctx_t *ctx, mrczip_header_t *hd, FILE *fout, const char *dataConvertedType);
+/* adapt.h:30-31 */
+int zip_compress(ctx_t *ctx, const char *src, const char *dst, int bitsToLoss);
+int zip_uncompress(ctx_t *ctx, const char *src, const char *dst);
+
+/* mrczip.h:123-124 / zip.c:381-399 */
+void pack_header(char *buf, btype_t btype, uint32_t len);
+void unpack_header(const char *buf, btype_t *btype, uint32_t *len);
+
+/* common.h:43-81 / common.c */
+void init_context(ctx_t *ctx);
+void reset_context(ctx_t *ctx);
+void update_context(ctx_t *dst, ctx_t *src);
+void print_context_info(ctx_t *ctx, const char *hintMsg);
+void init_mrczip_header(mrczip_header_t *hd, char type);
+int read_mrczip_header(FILE *fin, mrczip_header_t *hd);
+int write_mrczip_header(FILE *fout, mrczip_header_t *hd);
+void print_mrczip_header(mrczip_header_t *hd, const char *hintMsg);
+uint64_t get_file_size(FILE *fp);
+double now_sec(void);
+
+/* ------------------------------------------------------------------ (2) CUDA layer */
+
+typedef struct mzb_ctx mzb_ctx;
+
+/* One context per (device, stream).  cuda_stream is a cudaStream_t (NULL: the context creates its own
+ * non-blocking stream).  All device work of a context is ordered on that stream.  A context is not
+ * thread-safe; use one per thread (the reference calls run_* from N pthreads, mrc_tarx.c:145-161). */
+int mzb_create(mzb_ctx **out, int device, void *cuda_stream);
+void mzb_destroy(mzb_ctx *ctx);
+/* Chunks processed per kernel batch (bounds scratch memory: about 8 bytes per word of a batch). Default 128. */
+int mzb_set_batch_chunks(mzb_ctx *ctx, uint32_t chunks);
+/* kernel variant selectors used by the benchmarks (0 = default) */
+int mzb_set_variant(mzb_ctx *ctx, int split_variant, int merge_variant);
+
+/* Upper bound of the container for nwords words cut in chk-word chunks (header included). */
+size_t mzb_compress_bound(uint64_t nwords, uint32_t chk);
+
+/* Device-resident compress.  d_words: nwords uint32 (16-byte aligned device pointer).
+ *   bits          0..32 low mantissa bits to erase (workers.c:29-37)
+ *   exempt_words  leading words left unmasked: 256 for the first chunk range of an MRC file, 0 for a
+ *                 later chunk range (multi-GPU sharding) -- workers.c:90-94
+ *   chk           words per chunk written to the file header; MZB_CHUNK_WORDS is the reference value
+ *   fsz           original file size in bytes for the 17-byte header; write_file_header = 0 emits chunk
+ *                 records only (a shard of a larger container)
+ * Writes to d_out (device, capacity out_cap); *out_size = bytes produced. Synchronises the stream. */
+int mzb_compress_device(mzb_ctx *ctx, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,
+                        uint32_t chk, uint64_t fsz, int write_file_header, void *d_out, size_t out_cap,
+                        uint64_t *out_size);
+
+/* Device-resident decompress of chunk records.  d_in/in_size: container bytes on the device;
+ * has_file_header != 0: d_in starts with the 17-byte header (chk and nwords are then read from it and the
+ * arguments ignored); otherwise d_in starts at a chunk record and (chk, nwords) describe the shard.
+ * d_words_out: device buffer for nwords uint32 (capacity out_cap_words). Synchronises the stream. */
+int mzb_decompress_device(mzb_ctx *ctx, const void *d_in, size_t in_size, int has_file_header, uint32_t chk,
+                          uint64_t nwords, void *d_words_out, uint64_t out_cap_words, uint64_t *nwords_out);
+
+/* Intermediates, for parity checks against the reference's split/merge (workers.c:180-203, 423-442):
+ * d_planes holds 4 planes of nwords bytes, plane j at d_planes + j * plane_stride (stride % 16 == 0). */
+int mzb_mask_split_device(mzb_ctx *ctx, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,
+                          void *d_planes, uint64_t plane_stride);
+int mzb_merge_device(mzb_ctx *ctx, const void *d_planes, uint64_t plane_stride, uint64_t nwords, void *d_words_out);
+
+/* Host-buffer versions (end to end: H2D, kernels, D2H inside the call).  Pinned host memory gives
+ * full PCIe rate; pageable memory works. */
+int mzb_compress_host(mzb_ctx *ctx, const void *h_words, uint64_t nwords, int bits, uint32_t exempt_words,
+                      uint32_t chk, uint64_t fsz, int write_file_header, void *h_out, size_t out_cap,
+                      uint64_t *out_size);
+int mzb_decompress_host(mzb_ctx *ctx, const void *h_in, size_t in_size, int has_file_header, uint32_t chk,
+                        uint64_t nwords, void *h_words_out, uint64_t out_cap_words, uint64_t *nwords_out);
+
+/* pinned (page-locked) host memory for callers written in C without the CUDA headers */
+void *mzb_host_alloc(size_t bytes);
+void mzb_host_free(void *p);
+
+/* counters of the last compress / decompress call */
+typedef struct {
+    uint64_t bytes_in, bytes_out;
+    uint32_t chunks, streams;
+    uint32_t raw_streams;      /* streams written RAW (zip.c:186-190) */
+    uint32_t stored_subblocks; /* sub-blocks emitted as stored deflate blocks */
+    uint32_t general_streams;  /* decode: streams that took the one-thread-per-stream inflater */
+    uint32_t fast_failed;      /* decode: streams whose sub-block decode failed validation (fell back) */
+    uint32_t kernel_launches;  /* kernels launched by the call */
+    uint32_t pad;
+} mzb_stats;
+int mzb_last_stats(mzb_ctx *ctx, mzb_stats *out);
+
+const char *mzb_version(void);
+const char *mzb_strerror(int code);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRCZIP_B200_H_ */

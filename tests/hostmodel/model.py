@@ -1,0 +1,33 @@
+"""ctypes front end of the CPU model of the device codec (tests only)."""
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+
+_L = C.CDLL(str(_build.build()))
+_L.hm_encode_subblock.restype = C.c_uint32
+_L.hm_encode_subblock.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_int)]
+_L.hm_encode_stream.restype = C.c_uint64
+_L.hm_encode_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+_L.hm_inflate.restype = C.c_int
+_L.hm_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+_L.hm_sub_bytes.restype = C.c_uint32
+SUB = int(_L.hm_sub_bytes())
+
+
+def encode_stream(a: np.ndarray, sub: int = SUB):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    out = np.empty(a.size + (a.size // sub + 1) * 64 + 64, dtype=np.uint8)
+    ns = C.c_uint64()
+    n = _L.hm_encode_stream(a.ctypes.data, a.size, out.ctypes.data, out.size, sub, C.byref(ns))
+    assert n != 2**64 - 1
+    return out[:n].copy(), int(ns.value)
+
+
+def inflate(b: np.ndarray, n_out: int):
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.empty(n_out + 8, dtype=np.uint8)
+    on, used = C.c_uint32(), C.c_uint64()
+    rc = _L.hm_inflate(b.ctypes.data, b.size, out.ctypes.data, n_out, C.byref(on), C.byref(used))
+    return rc, out[:on.value].copy(), int(used.value)

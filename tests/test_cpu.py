@@ -1,0 +1,243 @@
+"""CPU suite (-m "not gpu"): oracle vs the reference (golden fixtures, and live when oracle/_ref is built),
+the CPU model of the device codec vs zlib, the host logic, and the C-ABI exports.  No compute call
+into libmrczip_b200.so here: it has no CPU path."""
+import ctypes as C
+import json
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import synth_words
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+# ----------------------------------------------------------------------------- oracle: mask / split / merge
+@pytest.mark.parametrize("bits", list(range(0, 33)))
+def test_oracle_mask_table(oracle, bits):
+    # reference workers.c:29-37
+    assert oracle.mask_for_bits(bits) == ((0xFFFFFFFF << bits) & 0xFFFFFFFF if bits < 32 else 0)
+
+
+def test_oracle_split_merge_roundtrip(oracle):
+    w = synth_words("G", 5000)
+    masked, planes = oracle.split(w, 0, True)
+    assert np.array_equal(masked, w)
+    assert np.array_equal(oracle.merge(planes), w)
+    for j in range(4):
+        assert np.array_equal(planes[j], (w >> (8 * j)).astype(np.uint8))
+
+
+@pytest.mark.parametrize("bits", [1, 8, 13, 24, 32])
+def test_oracle_header_exemption(oracle, bits):
+    w = synth_words("R", 1000)
+    masked, _ = oracle.split(w, bits, True)
+    assert np.array_equal(masked[:256], w[:256])                     # workers.c:90-94
+    assert np.array_equal(masked[256:], w[256:] & np.uint32(oracle.mask_for_bits(bits)))
+    masked2, _ = oracle.split(w, bits, False)
+    assert np.array_equal(masked2, w & np.uint32(oracle.mask_for_bits(bits)))
+
+
+def test_oracle_pack_header(oracle):
+    buf = (C.c_uint8 * 4)()
+    for bt, ln in [(0, 0), (1, 6291456), (0, 0x7FFFFFFF), (1, 1)]:
+        oracle.lib().orc_pack_header(buf, bt, ln)
+        assert int.from_bytes(bytes(buf), "little") == (ln | (bt << 31))
+        b2, l2 = C.c_int(), C.c_uint32()
+        oracle.lib().orc_unpack_header(buf, C.byref(b2), C.byref(l2))
+        assert (b2.value, l2.value) == (bt, ln)
+
+
+# ----------------------------------------------------------------------------- oracle vs golden fixtures (made by the reference binary)
+def _golden_cases():
+    man = GOLDEN / "manifest.json"
+    if not man.exists():
+        return []
+    return json.loads(man.read_text())["cases"]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_oracle_matches_reference_golden(oracle, case):
+    src = np.fromfile(GOLDEN / case["input"], dtype=np.uint8)
+    ref_zip = np.fromfile(GOLDEN / case["ref_container"], dtype=np.uint8)
+    ref_erase = np.fromfile(GOLDEN / case["ref_erasebytes"], dtype=np.uint8)
+    bits = case["bits"]
+    assert np.array_equal(oracle.erasebytes(src, bits), ref_erase)          # erasebytes.c:109-134
+    assert np.array_equal(oracle.compress(src, bits), ref_zip)              # byte-identical container
+    assert np.array_equal(oracle.decompress(ref_zip), ref_erase[: (src.size // 4) * 4])
+    assert np.array_equal(oracle.decompress(ref_zip, use_zlib=False), ref_erase[: (src.size // 4) * 4])
+    for j in range(4):
+        assert np.array_equal(oracle.split_file(src[: src.size // 4 * 4].view(np.uint32), bits)[1][j],
+                              np.fromfile(GOLDEN / case["ref_planes"][j], dtype=np.uint8))
+
+
+def test_oracle_live_against_reference(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    assert oracle.ref_zlib_version() == "1.2.8"
+    for kind, bits, n in [("G", 0, 70000), ("P", 0, 70000), ("S", 12, 30001), ("Z", 5, 9000), ("R", 31, 5000)]:
+        src = synth_words(kind, n).view(np.uint8)
+        assert np.array_equal(oracle.compress(src, bits), oracle.ref_compress(src, bits)), (kind, bits)
+        assert np.array_equal(oracle.erasebytes(src, bits), oracle.ref_erasebytes(src, bits))
+        masked, planes = oracle.ref_split(src, bits)
+        m2, p2 = oracle.split_file(src.view(np.uint32), bits)
+        assert np.array_equal(masked, m2) and all(np.array_equal(a, b) for a, b in zip(planes, p2))
+        assert np.array_equal(oracle.ref_merge(planes), masked)
+        assert np.array_equal(oracle.ref_decompress(oracle.compress(src, bits)), oracle.erasebytes(src, bits))
+
+
+def test_oracle_small_chunks_and_ragged(oracle):
+    # the decoder honours any chk in the file header (workers.c:578,584); ragged tails are dropped (workers.c:744)
+    for nbytes in [0, 3, 4, 1024, 1027, 4096 + 2, 100001]:
+        src = np.random.default_rng(nbytes).integers(0, 256, nbytes, dtype=np.uint8)
+        for chk in [1000, 4096, 65536]:
+            c = oracle.compress(src, 7, chk=chk)
+            if nbytes < 4:
+                assert c.size == 0                                      # workers.c:757-764: nothing is written
+                continue
+            fsz, chk2, streams = oracle.parse_container(c)
+            assert (fsz, chk2) == (nbytes, chk) and len(streams) == 4 * -(-(nbytes // 4) // chk)
+            assert np.array_equal(oracle.decompress(c), oracle.erasebytes(src, 7)[: nbytes // 4 * 4])
+
+
+def test_oracle_inflate_is_independent_of_zlib(oracle):
+    rng = np.random.default_rng(5)
+    a = rng.choice([1, 2, 3, 200], 50000, p=[.5, .3, .15, .05]).astype(np.uint8)
+    for strat in (zlib.Z_RLE, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, strat)
+        z = co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH)
+        out, used = oracle.inflate_raw(np.frombuffer(z, np.uint8), a.size)
+        assert np.array_equal(out, a) and used == len(z)
+
+
+# ----------------------------------------------------------------------------- CPU model of the device codec
+def _plane_cases():
+    rng = np.random.default_rng(0)
+    fib = [1, 1]
+    while sum(fib) < 16000:
+        fib.append(fib[-1] + fib[-2])
+    cases = {
+        "zeros": np.zeros(50000, np.uint8),
+        "one": np.array([7], np.uint8),
+        "two": np.array([7, 7], np.uint8),
+        "three_same": np.array([9, 9, 9, 9], np.uint8),
+        "short": np.arange(37, dtype=np.uint8),
+        "rand": rng.integers(0, 256, 40000).astype(np.uint8),
+        "skew": rng.choice([0x3f, 0xbf, 0x3e, 0xbe, 0x40, 0xc0, 0x3d], 40000, p=[.3, .3, .15, .15, .04, .04, .02]).astype(np.uint8),
+        "runs": np.repeat(rng.integers(0, 256, 3000).astype(np.uint8), rng.integers(1, 600, 3000))[:100000],
+        "geo": np.minimum(rng.geometric(0.5, 60000), 255).astype(np.uint8),
+        "fib": np.concatenate([np.full(f, i, np.uint8) for i, f in enumerate(fib)])[rng.permutation(sum(fib))][:16384],
+        "exact16k": rng.choice([1, 2, 3], 16384).astype(np.uint8),
+        "16k+1": rng.choice([1, 2, 3], 16385).astype(np.uint8),
+        "run258": np.concatenate([np.full(259, 5, np.uint8), np.full(260, 6, np.uint8), np.full(517, 7, np.uint8), [1, 2]]).astype(np.uint8),
+        "mid_entropy": rng.integers(0, 200, 33000).astype(np.uint8),
+    }
+    g = synth_words("G", 65536).view(np.uint8).reshape(-1, 4)
+    p = synth_words("P", 65536).view(np.uint8).reshape(-1, 4)
+    for j in range(4):
+        cases[f"G_p{j}"] = g[:, j].copy()
+        cases[f"P_p{j}"] = p[:, j].copy()
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
+def test_model_encoder_streams_inflate_with_zlib(hostmodel, oracle, name):
+    a = _plane_cases()[name]
+    c, _ = hostmodel.encode_stream(a)
+    d = zlib.decompressobj(-15)
+    assert d.decompress(c.tobytes()) == a.tobytes()
+    assert not d.eof and d.unused_data == b""          # BFINAL never set; ends on a block boundary
+    out, used = oracle.inflate_raw(c, a.size)           # independent inflater agrees
+    assert np.array_equal(out, a) and used == c.size
+    assert c[-4:].tobytes() == b"\x00\x00\xff\xff"     # sync-flush marker, like zlib's Z_FULL_FLUSH
+    rc, o, used = hostmodel.inflate(c, a.size)
+    assert rc == 0 and np.array_equal(o, a) and used == c.size
+    # size next to the reference codec (zlib level 6, Z_RLE, memLevel 9): within 5 % (+ a constant for tiny inputs)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+    z = co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH)
+    assert c.size <= 1.05 * len(z) + 64 * (a.size // hostmodel.SUB + 1)  # ~45 B of header+marker per 16 KiB sub-block
+
+
+@pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
+def test_model_inflater_on_zlib_streams(hostmodel, name):
+    a = _plane_cases()[name]
+    for strat, lvl in [(zlib.Z_RLE, 6), (zlib.Z_DEFAULT_STRATEGY, 6), (zlib.Z_FIXED, 6), (zlib.Z_DEFAULT_STRATEGY, 0),
+                       (zlib.Z_HUFFMAN_ONLY, 1), (zlib.Z_DEFAULT_STRATEGY, 9)]:
+        co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 9, strat)
+        z = co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH)
+        rc, o, used = hostmodel.inflate(np.frombuffer(z, np.uint8), a.size)
+        assert rc == 0 and np.array_equal(o, a) and used == len(z), (strat, lvl)
+
+
+def test_model_inflater_rejects_garbage(hostmodel):
+    rng = np.random.default_rng(3)
+    a = rng.choice([1, 2, 3], 5000).astype(np.uint8)
+    c, _ = hostmodel.encode_stream(a)
+    rc, o, used = hostmodel.inflate(c[: c.size // 2], a.size)      # truncated
+    assert rc != 0 or o.size != a.size
+    bad = c.copy()
+    bad[0] |= 0x06                                                 # block type 3
+    rc, _, _ = hostmodel.inflate(bad, a.size)
+    assert rc != 0
+    rc, o, _ = hostmodel.inflate(c, a.size - 10)                   # output too small
+    assert rc != 0
+
+
+def test_model_bfinal_and_history_rules(hostmodel):
+    a = np.tile(np.arange(50, dtype=np.uint8), 400)                # long-distance matches under the default strategy
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9)
+    z = co.compress(a.tobytes()) + co.flush(zlib.Z_FINISH)         # BFINAL = 1
+    rc, o, used = hostmodel.inflate(np.frombuffer(z, np.uint8), a.size)
+    assert rc == 0 and np.array_equal(o, a) and used == len(z)
+
+
+# ----------------------------------------------------------------------------- host logic + C ABI
+def test_abi_exports_every_declared_symbol():
+    from datacompressionfloat_b200 import lib
+    L = lib.load()
+    for sym in lib.EXPORTS:
+        assert hasattr(L, sym), sym
+    assert b"sm_100a" in L.mzb_version()
+    assert lib.strerror(lib.E_FORMAT).startswith("malformed")
+    # declared in the header <-> listed in EXPORTS
+    import re
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "mrczip_b200.h").read_text()
+    declared = set(re.findall(r"\b(mzb_\w+|run_\w+|zip_\w+|pack_header|unpack_header|\w+_context\w*|\w+_mrczip_header|get_file_size|now_sec)\s*\(", hdr))
+    declared -= {"mzb_ctx"}
+    assert declared <= set(lib.EXPORTS), declared - set(lib.EXPORTS)
+
+
+def test_abi_pack_header_matches_oracle(oracle):
+    from datacompressionfloat_b200 import lib
+    L = lib.load()
+    buf = C.create_string_buffer(4)
+    for bt, ln in [(0, 0), (1, 6291456), (0, 0x7FFFFFFF), (1, 77)]:
+        L.pack_header(buf, bt, ln)
+        assert int.from_bytes(buf.raw, "little") == (ln | (bt << 31))
+        b2, l2 = C.c_int(), C.c_uint32()
+        L.unpack_header(buf, C.byref(b2), C.byref(l2))
+        assert (b2.value, l2.value) == (bt, ln)
+
+
+def test_compress_bound_and_header_helpers(oracle):
+    from datacompressionfloat_b200 import Codec, file_header, chunk_range, segment_offsets, CHUNK_WORDS
+    assert Codec.compress_bound(10, 4) >= 17 + 3 * 16 + 40
+    h = file_header(67109888)
+    assert h.size == 17 and int(h[:8].view(np.uint64)[0]) == 67109888 and int(h[8:12].view(np.uint32)[0]) == CHUNK_WORDS
+    # the header the oracle (== reference) writes for the same file
+    c = oracle.compress(np.zeros(4096, np.uint8), 0)
+    assert np.array_equal(c[:17], file_header(4096))
+    assert [chunk_range(171, r, 8) for r in range(8)][-1] == (154, 171)
+    assert sum(hi - lo for lo, hi in (chunk_range(5, r, 8) for r in range(8))) == 5
+    assert segment_offsets([10, 20, 5]) == ([17, 27, 47], 52)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from datacompressionfloat_b200 import Codec, MzbError
+    with pytest.raises(MzbError):
+        Codec(0)

@@ -1,0 +1,287 @@
+"""GPU parity suite (-m gpu): every call goes through the C ABI of libmrczip_b200.so; the oracle
+(oracle/liboracle.so, and the reference binaries in oracle/_ref when present) is the checker.
+
+The three integer-exact checks of BASELINE.json:
+  (1) masked / shuffled byte planes == the reference's intermediates
+  (2) every GPU-produced stream inflates with the reference's libz to the masked floats
+  (3) every reference-produced stream inflates on the GPU to the same bits
+plus the reference's own test procedure (script/run_full_test.sh:84-108):
+  unzip(zip(x, b)) == erasebytes(x, b) for b = 0..N, byte-exact.
+"""
+import os
+import tempfile
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import synth_words
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def dev(a: np.ndarray):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def host_u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+# ----------------------------------------------------------------------------- (1) planes
+@pytest.mark.parametrize("bits", list(range(0, 33)))
+def test_split_planes_match_reference_intermediates(codec, oracle, bits):
+    w = synth_words("R", 10007 + bits)            # ragged length, random bits in every plane
+    planes = codec.mask_split(dev(w), bits, 256)
+    torch.cuda.synchronize()
+    masked, ref_planes = oracle.split(w, bits, True)
+    got = planes.cpu().numpy()
+    for j in range(4):
+        assert np.array_equal(got[j, : w.size], ref_planes[j]), (bits, j)
+    # merge is the exact inverse
+    back = codec.merge(planes, w.size)
+    assert np.array_equal(host_u32(back), masked)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 255, 256, 257, 1023, 4096, 65537, 1 << 20])
+def test_split_merge_sizes_and_variants(codec, oracle, n, variant):
+    w = synth_words("R", n)[: max(n, 1)] if n < 256 else synth_words("R", n - 256)
+    w = w[:n]
+    codec.set_variant(variant, variant)
+    try:
+        for exempt, first in [(256, True), (0, False)]:
+            planes = codec.mask_split(dev(w), 11, exempt)
+            masked, ref_planes = oracle.split(w, 11, first)
+            got = planes.cpu().numpy()
+            for j in range(4):
+                assert np.array_equal(got[j, : w.size], ref_planes[j]), (n, variant, j)
+            assert np.array_equal(host_u32(codec.merge(planes, w.size)), masked)
+    finally:
+        codec.set_variant(0, 0)
+
+
+def test_split_against_reference_binary(codec, oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    w = synth_words("G", 300001)
+    for bits in (0, 9, 23):
+        masked, ref_planes = oracle.ref_split(w.view(np.uint8), bits)   # the reference's own split_float_to_byte_stream
+        got = codec.mask_split(dev(w), bits, 256).cpu().numpy()
+        for j in range(4):
+            assert np.array_equal(got[j, : w.size], ref_planes[j])
+
+
+# ----------------------------------------------------------------------------- (2) GPU streams -> reference inflate
+CASES = [("G", 0), ("G", 8), ("G", 16), ("P", 0), ("S", 0), ("S", 12), ("Z", 3), ("R", 0), ("R", 28)]
+
+
+@pytest.mark.parametrize("kind,bits", CASES)
+@pytest.mark.parametrize("chk", [65536, 16384 * 3 + 16])
+def test_gpu_container_decodes_with_zlib_and_matches_golden(codec, oracle, kind, bits, chk):
+    w = synth_words(kind, 200000 - 256 + 777)
+    src = w.view(np.uint8)
+    cont = codec.compress(dev(w), bits, chk=chk).cpu().numpy()
+    golden = oracle.erasebytes(src, bits)
+    # container structure
+    fsz, chk2, streams = oracle.parse_container(cont)
+    assert (fsz, chk2) == (src.size, chk)
+    assert len(streams) == 4 * -(-w.size // chk)
+    _, ref_planes = oracle.split_file(w, bits, chk)
+    pos = [0, 0, 0, 0]
+    for i, s in enumerate(streams):
+        j = i % 4
+        payload = cont[s["offset"]: s["offset"] + s["len"]]
+        want = ref_planes[j][pos[j]: pos[j] + s["n"]]
+        pos[j] += s["n"]
+        if s["raw"]:
+            assert s["len"] == s["n"] and np.array_equal(payload, want)
+            continue
+        assert s["n"] > s["len"] + 4                          # zip.c:177 rule
+        assert s["len"] <= chk + 4                            # reader buffer of the reference (zip.c:334)
+        d = zlib.decompressobj(-15)                           # each payload decodes standalone
+        assert d.decompress(payload.tobytes()) == want.tobytes()
+        assert not d.eof and d.unused_data == b""             # BFINAL never set
+        out, used = oracle.inflate_raw(payload, s["n"])       # independent inflater
+        assert np.array_equal(out, want) and used == s["len"]
+    # whole container through the oracle's restatement of run_uncompress (persistent inflate per plane)
+    assert np.array_equal(oracle.decompress(cont), golden)
+
+
+@pytest.mark.parametrize("kind,bits", [("G", 8), ("P", 0), ("S", 12)])
+def test_gpu_container_decodes_with_reference_binary(codec, oracle, kind, bits):
+    """mrc_tar_c -t unzip (reference code + its libz 1.2.8) on a GPU-made container, reference chunking."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    w = synth_words(kind, 6291456 + 100000)                  # 2 chunks at the reference CHUNK_SIZE, second ragged
+    cont = codec.compress(dev(w), bits).cpu().numpy()
+    golden = oracle.ref_erasebytes(w.view(np.uint8), bits)   # the reference's own golden generator
+    assert np.array_equal(oracle.ref_decompress(cont), golden)
+    # ratio next to the reference's at the same level / strategy: within 5 %
+    ref_cont = oracle.ref_compress(w.view(np.uint8), bits)
+    assert cont.size <= 1.05 * ref_cont.size, (cont.size, ref_cont.size)
+    # and every compressed payload through the reference's mzlib_inf
+    _, _, streams = oracle.parse_container(cont)
+    _, ref_planes = oracle.split_file(w, bits)
+    s = next(s for s in streams if not s["raw"])
+    j = streams.index(s) % 4
+    out = oracle.ref_inflate(cont[s["offset"]: s["offset"] + s["len"]], s["n"])
+    assert np.array_equal(out, ref_planes[j][: s["n"]])
+
+
+# ----------------------------------------------------------------------------- (3) reference streams -> GPU inflate
+@pytest.mark.parametrize("kind,bits", CASES)
+@pytest.mark.parametrize("chk", [65536, 50000])
+def test_reference_container_decodes_on_gpu(codec, oracle, kind, bits, chk):
+    w = synth_words(kind, 150000 + 3)
+    src = w.view(np.uint8)
+    ref_cont = oracle.compress(src, bits, chk=chk)            # byte-identical to the reference's output (test_cpu)
+    back = codec.decompress(torch.from_numpy(ref_cont).cuda())
+    assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(src, bits))
+    st = codec.stats()
+    assert st["general_streams"] > 0 or kind == "R"           # zlib streams take the general inflater
+
+
+def test_reference_binary_container_decodes_on_gpu(codec, oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    w = synth_words("P", 6291456 + 5000)
+    ref_cont = oracle.ref_compress(w.view(np.uint8), 4)
+    back = codec.decompress(torch.from_numpy(ref_cont).cuda())
+    assert np.array_equal(host_u32(back).view(np.uint8), oracle.ref_erasebytes(w.view(np.uint8), 4))
+
+
+def test_foreign_deflate_streams_decode_on_gpu(codec, oracle):
+    """Default-strategy (long distances), fixed-Huffman and stored blocks inside a legal container."""
+    w = synth_words("S", 40000)
+    chk = 16384
+    _, planes = oracle.split_file(w, 10, chk)
+    for strat, lvl in [(zlib.Z_DEFAULT_STRATEGY, 6), (zlib.Z_FIXED, 6), (zlib.Z_DEFAULT_STRATEGY, 0), (zlib.Z_HUFFMAN_ONLY, 3)]:
+        parts = [np.zeros(17, np.uint8)]
+        parts[0][:8] = np.frombuffer(np.uint64(w.size * 4).tobytes(), np.uint8)
+        parts[0][8:12] = np.frombuffer(np.uint32(chk).tobytes(), np.uint8)
+        for w0 in range(0, w.size, chk):
+            n = min(chk, w.size - w0)
+            hdr, pay = [], []
+            for j in range(4):
+                co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 9, strat)
+                z = co.compress(planes[j][w0: w0 + n].tobytes()) + co.flush(zlib.Z_FULL_FLUSH)
+                hdr.append(np.uint32(len(z)))
+                pay.append(np.frombuffer(z, np.uint8))
+            parts.append(np.array(hdr, np.uint32).view(np.uint8))
+            parts.extend(pay)
+        cont = np.concatenate(parts)
+        back = codec.decompress(torch.from_numpy(cont).cuda())
+        assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(w.view(np.uint8), 10)), (strat, lvl)
+
+
+# ----------------------------------------------------------------------------- the reference's own procedure, b = 0..32
+@pytest.mark.parametrize("bits", list(range(0, 33)))
+def test_roundtrip_equals_erasebytes_all_bits(codec, oracle, bits):
+    w = synth_words("G" if bits % 2 else "S", 3 * 65536 + 12345)   # >= 3 chunks incl. a partial last chunk
+    cont = codec.compress(dev(w), bits, chk=65536)
+    back = codec.decompress(cont)
+    assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(w.view(np.uint8), bits))
+    assert codec.stats()["general_streams"] == 0 and codec.stats()["fast_failed"] == 0   # own streams: sub-block path
+
+
+@pytest.mark.parametrize("nwords", [1, 2, 255, 256, 257, 4095, 4096, 4097, 16384, 16385, 65536 * 2, 65536 * 2 + 1])
+@pytest.mark.parametrize("chk", [4096, 1000])
+def test_roundtrip_edge_sizes(codec, oracle, nwords, chk):
+    w = synth_words("P", max(nwords, 256))[:nwords]
+    cont = codec.compress(dev(w), 6, chk=chk)
+    assert np.array_equal(oracle.decompress(cont.cpu().numpy()), oracle.erasebytes(w.view(np.uint8), 6))
+    back = codec.decompress(cont)
+    assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(w.view(np.uint8), 6))
+
+
+def test_empty_input(codec):
+    cont = codec.compress(torch.empty(0, dtype=torch.int32, device="cuda"), 0)
+    assert cont.numel() == 0                                   # workers.c:757-764: nothing written
+    assert codec.decompress(cont).numel() == 0
+
+
+def test_batches_and_shards(codec, oracle):
+    """Several kernel batches, and chunk-range shards assembled into one container (multi-GPU layout)."""
+    from datacompressionfloat_b200 import file_header, chunk_range
+    w = synth_words("P", 20 * 8192 + 333)
+    chk = 8192
+    codec.set_batch_chunks(3)
+    try:
+        whole = codec.compress(dev(w), 5, chk=chk).cpu().numpy()
+        nchunks = -(-w.size // chk)
+        segs = []
+        for r in range(4):
+            lo, hi = chunk_range(nchunks, r, 4)
+            part = w[lo * chk: hi * chk]
+            segs.append(codec.compress(dev(part), 5, chk=chk, exempt_words=256 if r == 0 else 0,
+                                       write_file_header=False).cpu().numpy())
+        assembled = np.concatenate([file_header(w.size * 4, chk)] + segs)
+        assert np.array_equal(assembled, whole)
+        assert np.array_equal(oracle.decompress(assembled), oracle.erasebytes(w.view(np.uint8), 5))
+        # shard-wise decode
+        off = 17
+        outs = []
+        for r in range(4):
+            lo, hi = chunk_range(nchunks, r, 4)
+            nw = min(w.size, hi * chk) - lo * chk
+            seg = torch.from_numpy(assembled[off: off + segs[r].size].copy()).cuda()
+            outs.append(host_u32(codec.decompress(seg, has_file_header=False, chk=chk, nwords=nw)))
+            off += segs[r].size
+        assert np.array_equal(np.concatenate(outs).view(np.uint8), oracle.erasebytes(w.view(np.uint8), 5))
+    finally:
+        codec.set_batch_chunks(128)
+
+
+def test_ratio_next_to_reference(codec, oracle):
+    """Compression ratio (compressed / original, zip.c:434) within 5 % of the reference's at level 6 / Z_RLE."""
+    for kind, bits in [("G", 0), ("G", 8), ("G", 16), ("P", 0), ("S", 12)]:
+        w = synth_words(kind, 1 << 20)
+        ours = codec.compress(dev(w), bits).numel() - 17
+        ref = oracle.compress(w.view(np.uint8), bits).size - 17
+        assert ours <= 1.05 * ref, (kind, bits, ours, ref)
+
+
+def test_host_buffer_api_and_file_api(codec, oracle):
+    from datacompressionfloat_b200 import zip_compress, zip_uncompress
+    w = synth_words("S", 100000)
+    cont = codec.compress_host(w, 9, chk=32768)
+    assert np.array_equal(oracle.decompress(cont), oracle.erasebytes(w.view(np.uint8), 9))
+    assert np.array_equal(codec.decompress_host(cont).view(np.uint8), oracle.erasebytes(w.view(np.uint8), 9))
+    with tempfile.TemporaryDirectory() as d:
+        src, z, out = os.path.join(d, "v.mrc"), os.path.join(d, "v.mrc.zip"), os.path.join(d, "v.out")
+        raw = np.concatenate([w.view(np.uint8), np.array([1, 2, 3], np.uint8)])   # ragged tail is dropped (workers.c:744)
+        raw.tofile(src)
+        ctx = zip_compress(src, z, 9)
+        assert ctx["fileCount"] == 1 and ctx["allFileSize"] == raw.size
+        cont2 = np.fromfile(z, dtype=np.uint8)
+        assert ctx["allZipFileSize"] == cont2.size - 17
+        fsz, chk, _ = oracle.parse_container(cont2)
+        assert fsz == raw.size and chk == 6 * 1048576
+        assert np.array_equal(oracle.decompress(cont2), oracle.erasebytes(raw, 9))
+        zip_uncompress(z, out)
+        assert np.array_equal(np.fromfile(out, dtype=np.uint8), oracle.erasebytes(raw, 9))
+        if oracle.have_ref():
+            assert np.array_equal(oracle.ref_decompress(cont2), oracle.ref_erasebytes(raw, 9))
+
+
+def test_malformed_inputs_are_rejected(codec, oracle):
+    from datacompressionfloat_b200 import MzbError
+    w = synth_words("P", 50000)
+    cont = codec.compress(dev(w), 0, chk=16384)
+    with pytest.raises(MzbError):
+        codec.compress(dev(w), 33)
+    with pytest.raises(MzbError):
+        codec.decompress(cont[: cont.numel() // 2].clone())           # truncated
+    bad = cont.clone()
+    bad[17 + 3] = 0x7F                                                # absurd payload length
+    with pytest.raises(MzbError):
+        codec.decompress(bad)
+    bad = cont.cpu().numpy().copy()
+    _, _, streams = oracle.parse_container(bad)
+    s = next(s for s in streams if not s["raw"])
+    bad[s["offset"]] |= 0x06                                          # block type 3 in the first sub-block
+    with pytest.raises(MzbError):
+        codec.decompress(torch.from_numpy(bad).cuda())
