@@ -76,6 +76,16 @@ class Codec:
     def set_batch_chunks(self, n: int):
         check(self._L.mzb_set_batch_chunks(self._h, n), "mzb_set_batch_chunks")
 
+    def set_profiling(self, on: bool = True):
+        check(self._L.mzb_set_profiling(self._h, int(on)), "mzb_set_profiling")
+
+    def stage_ms(self) -> dict:
+        """Device time per pipeline stage of the last call (CUDA events on the context's stream)."""
+        n = self._L.mzb_stage_count()
+        buf = (C.c_float * n)()
+        check(self._L.mzb_stage_ms(self._h, buf, n), "mzb_stage_ms")
+        return {self._L.mzb_stage_name(i).decode(): float(buf[i]) for i in range(n)}
+
     def stats(self) -> dict:
         s = _lib.Stats()
         check(self._L.mzb_last_stats(self._h, C.byref(s)), "mzb_last_stats")

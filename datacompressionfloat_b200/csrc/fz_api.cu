@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/mrczip_b200.h"
 #include "fz_kernels.h"
 
@@ -40,7 +42,63 @@ struct mzb_ctx {
     FzStatus *d_status = nullptr;
     FzStatus *h_status = nullptr;  // pinned
     mzb_stats stats;
+    // per-stage CUDA-event timing (off by default)
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage;  // stage id of event i (-1 = start marker)
+    size_t ev_used = 0;
+    float stage_ms[FZ_ST_COUNT] = {0};
 };
+
+static void prof_mark(void *user, int stage)
+{
+    mzb_ctx *c = (mzb_ctx *)user;
+    if (!c->prof) return;
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->ev_pool.push_back(e);
+        c->ev_stage.push_back(0);
+    }
+    c->ev_stage[c->ev_used] = stage;
+    cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+    c->ev_used++;
+}
+
+static void prof_begin(mzb_ctx *c)
+{
+    c->ev_used = 0;
+    for (int i = 0; i < FZ_ST_COUNT; i++) c->stage_ms[i] = 0.f;
+    prof_mark(c, -1);
+}
+
+static void prof_collect(mzb_ctx *c)  // after the stream was synchronised
+{
+    if (!c->prof) return;
+    for (size_t i = 1; i < c->ev_used; i++) {
+        float ms = 0.f;
+        if (c->ev_stage[i] >= 0 && cudaEventElapsedTime(&ms, c->ev_pool[i - 1], c->ev_pool[i]) == cudaSuccess)
+            c->stage_ms[c->ev_stage[i]] += ms;
+    }
+}
+
+static const char *kStageNames[FZ_ST_COUNT] = {"split", "encode", "layout", "gather", "walk", "markers", "classify",
+                                                "inflate_fast", "inflate_general", "rawcopy", "merge"};
+
+extern "C" int mzb_set_profiling(mzb_ctx *c, int on)
+{
+    if (!c) return MZB_E_ARG;
+    c->prof = on != 0;
+    return MZB_OK;
+}
+extern "C" int mzb_stage_count(void) { return FZ_ST_COUNT; }
+extern "C" const char *mzb_stage_name(int i) { return (i >= 0 && i < FZ_ST_COUNT) ? kStageNames[i] : ""; }
+extern "C" int mzb_stage_ms(mzb_ctx *c, float *out, int n)
+{
+    if (!c || !out) return MZB_E_ARG;
+    for (int i = 0; i < n && i < FZ_ST_COUNT; i++) out[i] = c->stage_ms[i];
+    return MZB_OK;
+}
 
 static int ensure(DevBuf &b, size_t need)
 {
@@ -116,6 +174,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
                      &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out};
     for (DevBuf *b : all) release(*b);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -253,6 +312,7 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
 
     const uint32_t mask = fz_mask_for_bits(bits);
     uint32_t launches = 0;
+    prof_begin(c);
     for (uint64_t c0 = 0; c0 < nchunks_total; c0 += bmax) {
         const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
         const uint64_t w0 = c0 * chk;
@@ -260,15 +320,20 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
         const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
         const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
         fz_launch_split((const uint32_t *)d_words + w0, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
+        prof_mark(c, FZ_ST_SPLIT);
         fz_launch_encode((const uint8_t *)c->planes.p, g, (uint8_t *)c->scratch.p, (uint32_t *)c->sizes.p, c->d_status, c->stream);
+        prof_mark(c, FZ_ST_ENCODE);
         fz_launch_layout((const uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
                          (unsigned long long *)c->stream_off.p, (uint8_t *)d_out, out_cap, c->d_status, c->stream);
+        prof_mark(c, FZ_ST_LAYOUT);
         fz_launch_gather((const uint8_t *)c->planes.p, (const uint8_t *)c->scratch.p, (const uint32_t *)c->sizes.p,
                          (const uint32_t *)c->sub_off.p, (const uint32_t *)c->stream_hdr.p,
                          (const unsigned long long *)c->stream_off.p, g, (uint8_t *)d_out, c->d_status, c->stream);
+        prof_mark(c, FZ_ST_GATHER);
         launches += 5 + ((nw & 3) ? 1 : 0);
     }
     if ((rc = status_fetch(c))) return rc;
+    prof_collect(c);
     c->stats.bytes_in = nwords * 4;
     c->stats.bytes_out = c->h_status->out_end;
     c->stats.chunks = (uint32_t)nchunks_total;
@@ -332,6 +397,7 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
     if ((rc = status_reset(c, start))) return rc;
 
     uint32_t launches = 0;
+    prof_begin(c);
     for (uint64_t c0 = 0; c0 < nchunks_total; c0 += bmax) {
         const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
         const uint64_t w0 = c0 * chk;
@@ -339,12 +405,15 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
         const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
         fz_launch_walk((const uint8_t *)d_in, in_size, g, (uint32_t *)c->stream_hdr.p, (unsigned long long *)c->stream_off.p,
                        c->d_status, c->stream);
+        prof_mark(c, FZ_ST_WALK);
         fz_launch_inflate((const uint8_t *)d_in, in_size, g, (const uint32_t *)c->stream_hdr.p,
-                          (const unsigned long long *)c->stream_off.p, ib, (uint8_t *)c->planes.p, c->d_status, c->stream);
+                          (const unsigned long long *)c->stream_off.p, ib, (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c);
         fz_launch_merge((const uint8_t *)c->planes.p, pstride, nw, (uint32_t *)d_words_out + w0, c->merge_variant, c->stream);
+        prof_mark(c, FZ_ST_MERGE);
         launches += 1 + 9 + 1 + ((nw & 3) ? 1 : 0);
     }
     if ((rc = status_fetch(c))) return rc;
+    prof_collect(c);
     c->stats.bytes_in = c->h_status->out_end;
     c->stats.bytes_out = nwords * 4;
     c->stats.chunks = (uint32_t)nchunks_total;

@@ -826,19 +826,25 @@ fz_rawcopy_kernel(const uint8_t *__restrict__ container, uint64_t container_size
 }
 
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
-                       const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status, cudaStream_t st)
+                       const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status, cudaStream_t st,
+                       fz_mark_fn mark, void *mark_user)
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t ntiles = nstreams * b.tiles_per_stream;
     fz_marker_kernel<false><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
     fz_exclusive_scan(b.tile_cnt, ntiles, b.block_sums, st);
     fz_marker_kernel<true><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
+    if (mark) mark(mark_user, FZ_ST_MARKERS);
     fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, status);
+    if (mark) mark(mark_user, FZ_ST_CLASSIFY);
     // the hit count lives on the device; launch for the capacity and let surplus threads exit
     const uint32_t max_hits = b.hits_cap;
     fz_inflate_fast_kernel<<<(max_hits + FZ_INF_THREADS - 1) / FZ_INF_THREADS, FZ_INF_THREADS, 0, st>>>(
         container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, planes, status);
+    if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, planes, status);
+    if (mark) mark(mark_user, FZ_ST_INFLATE_GENERAL);
     const uint32_t total = nstreams * g.nsub_full;
     fz_rawcopy_kernel<<<(total + 3) / 4, 128, 0, st>>>(container, container_size, g, stream_hdr, stream_off, planes, status);
+    if (mark) mark(mark_user, FZ_ST_RAWCOPY);
 }

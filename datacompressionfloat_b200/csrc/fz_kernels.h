@@ -30,6 +30,14 @@ struct FzStatus {
     unsigned int pad;
 };
 
+// optional per-stage timing hook: called after the launches of a stage were enqueued
+typedef void (*fz_mark_fn)(void *user, int stage);
+enum {
+    FZ_ST_SPLIT = 0, FZ_ST_ENCODE, FZ_ST_LAYOUT, FZ_ST_GATHER,
+    FZ_ST_WALK, FZ_ST_MARKERS, FZ_ST_CLASSIFY, FZ_ST_INFLATE_FAST, FZ_ST_INFLATE_GENERAL, FZ_ST_RAWCOPY, FZ_ST_MERGE,
+    FZ_ST_COUNT
+};
+
 // ---- mask + byte-plane split / merge (HBM-bound)
 void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint64_t exempt_words,
                      uint8_t *planes, uint64_t plane_stride, int variant, cudaStream_t st);
@@ -63,6 +71,6 @@ struct FzInflateBufs {
 };
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status,
-                       cudaStream_t st);
+                       cudaStream_t st, fz_mark_fn mark, void *mark_user);
 
 size_t fz_encode_smem_bytes();

@@ -55,6 +55,7 @@ EXPORTS = [
     "mzb_create", "mzb_destroy", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_compress_bound",
     "mzb_compress_device", "mzb_decompress_device", "mzb_mask_split_device", "mzb_merge_device",
     "mzb_compress_host", "mzb_decompress_host", "mzb_host_alloc", "mzb_host_free", "mzb_last_stats",
+    "mzb_set_profiling", "mzb_stage_count", "mzb_stage_name", "mzb_stage_ms",
     "mzb_version", "mzb_strerror",
 ]
 
@@ -109,6 +110,13 @@ def load():
     L.mzb_host_free.argtypes = [vp]
     L.mzb_last_stats.restype = i32
     L.mzb_last_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.mzb_set_profiling.restype = i32
+    L.mzb_set_profiling.argtypes = [vp, i32]
+    L.mzb_stage_count.restype = i32
+    L.mzb_stage_name.restype = C.c_char_p
+    L.mzb_stage_name.argtypes = [i32]
+    L.mzb_stage_ms.restype = i32
+    L.mzb_stage_ms.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.mzb_version.restype = C.c_char_p
     L.mzb_strerror.restype = C.c_char_p
     L.mzb_strerror.argtypes = [i32]

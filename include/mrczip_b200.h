@@ -166,6 +166,13 @@ typedef struct {
 } mzb_stats;
 int mzb_last_stats(mzb_ctx *ctx, mzb_stats *out);
 
+/* Per-stage device times of the last compress / decompress call, measured with CUDA events on the
+ * context's stream (off by default; the events cost a few microseconds per batch). */
+int mzb_set_profiling(mzb_ctx *ctx, int on);
+int mzb_stage_count(void);
+const char *mzb_stage_name(int stage);
+int mzb_stage_ms(mzb_ctx *ctx, float *out_ms, int n);
+
 const char *mzb_version(void);
 const char *mzb_strerror(int code);
 
