@@ -41,7 +41,10 @@ class Codec:
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.device = int(device)
-        check(self._L.mzb_create(C.byref(self._h), self.device, C.c_void_p(stream) if stream else None), "mzb_create")
+        if stream is None:   # the context makes its own non-blocking stream
+            check(self._L.mzb_create(C.byref(self._h), self.device, None), "mzb_create")
+        else:                # a cudaStream_t handle; 0 is the legacy default stream
+            check(self._L.mzb_create_on_stream(C.byref(self._h), self.device, C.c_void_p(int(stream))), "mzb_create_on_stream")
         if batch_chunks:
             check(self._L.mzb_set_batch_chunks(self._h, int(batch_chunks)), "mzb_set_batch_chunks")
 

@@ -137,7 +137,19 @@ extern "C" const char *mzb_strerror(int code)
     }
 }
 
+static int create_impl(mzb_ctx **out, int device, void *cuda_stream, bool use_given);
+
 extern "C" int mzb_create(mzb_ctx **out, int device, void *cuda_stream)
+{
+    return create_impl(out, device, cuda_stream, cuda_stream != nullptr);
+}
+
+extern "C" int mzb_create_on_stream(mzb_ctx **out, int device, void *cuda_stream)
+{
+    return create_impl(out, device, cuda_stream, true);
+}
+
+static int create_impl(mzb_ctx **out, int device, void *cuda_stream, bool use_given)
 {
     if (!out) return MZB_E_ARG;
     *out = nullptr;
@@ -151,7 +163,7 @@ extern "C" int mzb_create(mzb_ctx **out, int device, void *cuda_stream)
     FZ_CHECK(cudaSetDevice(device));
     mzb_ctx *c = new mzb_ctx();
     c->device = device;
-    if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
+    if (use_given) c->stream = (cudaStream_t)cuda_stream;
     else {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MZB_E_CUDA; }
         c->own_stream = true;

@@ -1,25 +1,30 @@
 // fz_inflate.cuh -- thread-serial raw-inflate (RFC 1951: stored / fixed / dynamic, any distance) of ONE
 // deflate fragment.  Replaces what the reference gets from zlib's inflate() behind mzlib_inf
 // (reference zip.c:262-284) for one payload -- or, on streams made by our encoder, for one
-// sub-block (one GPU thread per sub-block; see fz_kernels_inflate.cu).
+// sub-block (one GPU thread per sub-block; see fz_kernels.cu).
 //
 // `__host__ __device__`: tests/hostmodel runs this very source on the CPU against zlib streams.
 //
-// Decoding uses left-aligned canonical codes: for the next 15 stream bits, bit-reversed into a
-// 15-bit number w, the code length is the first l with w < limit[l]; the symbol index is
-// (w >> (15-l)) + delta[l] into the symbols sorted by (length, value).  limit/delta live in
-// registers (all loops over l are fully unrolled); only the sorted symbol tables are in memory.
+// Decoding uses left-aligned canonical codes: take the next 15 stream bits, bit-reversed into a
+// 15-bit number w; the code length is the first l with w < limit[l]; the symbol index is
+// (w >> (15-l)) + delta[l] into the symbols sorted by (length, value).  limit and delta are packed
+// into one 32-bit word per length (limit << 16 | delta & 0xffff) held in fifteen SCALAR fields, so
+// they live in registers (arrays ended up in local memory and made the kernel 50x slower); only the
+// sorted symbol tables and the per-length counters are in (shared) memory.
 #pragma once
 #include "fz_common.cuh"
 
-// sorted-symbol tables of one decoding thread; STRIDE interleaves the threads of a warp in shared memory
+// per-thread tables; STRIDE interleaves the threads of a block in shared memory
 template <int STRIDE>
 struct FzInfTab {
-    uint16_t *ll;  // 288 entries
-    uint16_t *dd;  // 32 entries
+    uint16_t *ll;   // 288 sorted literal/length symbols
+    uint16_t *dd;   // 32 sorted distance symbols
+    uint16_t *cnt;  // 32 counters: [0..15] literal/length per code length, [16..31] distance
     FZ_HD uint16_t &L(int i) const { return ll[i * STRIDE]; }
     FZ_HD uint16_t &D(int i) const { return dd[i * STRIDE]; }
+    FZ_HD uint16_t &C(int i) const { return cnt[i * STRIDE]; }
 };
+#define FZ_INF_TAB_U16 (288 + 32 + 32)  // uint16 entries per decoding thread
 
 struct FzBitReader {
     const uint32_t *w;   // aligned word pointer
@@ -82,29 +87,33 @@ struct FzByteWriter {
 #define FZ_INF_E_SPACE (-3)     // more output than out_cap
 #define FZ_INF_E_HISTORY (-4)   // distance reaches before the start of this fragment
 
-struct FzCodeRegs {
-    uint32_t limit[16];  // left-aligned (15-bit) exclusive upper bound per length, [0] unused
-    int32_t delta[16];   // sorted-index offset minus first code per length
+// one canonical code: p<l> = limit_l << 16 | (delta_l & 0xffff) for code length l
+struct FzCode {
+    uint32_t p1, p2, p3, p4, p5, p6, p7, p8, p9, p10, p11, p12, p13, p14, p15;
 };
 
-// limit/delta from per-length counts; returns <0 if over-subscribed
-FZ_HD int fz_code_regs(FzCodeRegs &r, const uint16_t *cnt /*[16]*/, uint16_t *offs /*[16] out: first index per length*/)
+#define FZ_FOR_LEN_1_15(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15)
+
+// Build the code from per-length counts cnt(l), l = 1..15 (read through `rd`), and turn the counts
+// into first-index offsets in place (written through `wr`).  Returns the Kraft remainder:
+// 0 complete, > 0 incomplete, < 0 over-subscribed.
+template <class Rd, class Wr>
+FZ_HD int fz_code_build(FzCode &r, const Rd &rd, const Wr &wr)
 {
     uint32_t code = 0, idx = 0;
     int left = 1;
-    r.limit[0] = 0; r.delta[0] = 0;
-#pragma unroll
-    for (int l = 1; l <= 15; l++) {
-        code <<= 1;
-        left <<= 1;
-        const uint32_t c = cnt[l];
-        left -= (int)c;
-        offs[l] = (uint16_t)idx;
-        r.delta[l] = (int32_t)idx - (int32_t)code;
-        code += c;
-        idx += c;
-        r.limit[l] = code << (15 - l);
+#define FZ_BUILD_STEP(L)                                                         \
+    {                                                                            \
+        code <<= 1; left <<= 1;                                                  \
+        const uint32_t c = rd(L);                                                \
+        left -= (int)c;                                                          \
+        wr(L, idx);                                                              \
+        const uint32_t delta = (idx - code) & 0xffffu;                           \
+        code += c; idx += c;                                                     \
+        r.p##L = ((code << (15 - L)) << 16) | delta;                             \
     }
+    FZ_FOR_LEN_1_15(FZ_BUILD_STEP)
+#undef FZ_BUILD_STEP
     return left;
 }
 
@@ -119,14 +128,15 @@ FZ_HD uint32_t fz_rev15(uint32_t v)  // reverse the low 15 bits
 #endif
 }
 
-// decode one symbol index (into the sorted table); returns length used (0 = invalid code)
-FZ_HD int fz_decode_idx(const FzCodeRegs &r, uint32_t bits15, uint32_t &idx)
+// decode one symbol index (into the sorted table) from the next 15 bits; returns the code length (0 = invalid)
+FZ_HD int fz_decode_idx(const FzCode &r, uint32_t bits15, uint32_t &idx)
 {
     const uint32_t w = fz_rev15(bits15);
-#pragma unroll
-    for (int l = 1; l <= 15; l++) {
-        if (w < r.limit[l]) { idx = (uint32_t)((int32_t)(w >> (15 - l)) + r.delta[l]); return l; }
-    }
+    const uint32_t x = (w << 16) | 0xffffu;  // x < p_l  <=>  w < limit_l
+#define FZ_DEC_STEP(L)                                                                      \
+    if (x < r.p##L) { idx = (w >> (15 - L)) + (uint32_t)((int32_t)(r.p##L << 16) >> 16); return L; }
+    FZ_FOR_LEN_1_15(FZ_DEC_STEP)
+#undef FZ_DEC_STEP
     return 0;
 }
 
@@ -144,7 +154,15 @@ FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t ou
     bw.init(out, out_cap);
     int rc = FZ_INF_OK;
     bool last = false;
-    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    // order of the code-length code lengths (RFC 1951 3.2.7), 5 bits each, packed
+    const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) | (9ull << 30) |
+                              (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
+    const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+
+    auto rd_ll = [&](int l) -> uint32_t { return tab.C(l); };
+    auto wr_ll = [&](int l, uint32_t v) { tab.C(l) = (uint16_t)v; };
+    auto rd_dd = [&](int l) -> uint32_t { return tab.C(16 + l); };
+    auto wr_dd = [&](int l, uint32_t v) { tab.C(16 + l) = (uint16_t)v; };
 
     while (!last) {
         if (br.bits_left < 3) break;                       // nothing but padding left
@@ -166,47 +184,54 @@ FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t ou
         }
         if (type == 3) { rc = FZ_INF_E_DATA; break; }
 
-        FzCodeRegs LL, DD;
-        uint16_t cnt[16], offs[16];
+        FzCode LL, DD;
         if (type == 1) {
-            // fixed code: litlen lengths 8 (0-143), 9 (144-255), 7 (256-279), 8 (280-287); 30 distance codes of 5 bits
-            for (int l = 0; l < 16; l++) cnt[l] = 0;
-            cnt[7] = 24; cnt[8] = 152; cnt[9] = 112;
-            fz_code_regs(LL, cnt, offs);
+            // fixed code: litlen lengths 8 (0-143), 9 (144-255), 7 (256-279), 8 (280-287); 32 distance codes of 5 bits
+            for (int l = 0; l < 32; l++) tab.C(l) = 0;
+            tab.C(7) = 24; tab.C(8) = 152; tab.C(9) = 112;
+            tab.C(16 + 5) = 32;
+            fz_code_build(LL, rd_ll, wr_ll);
+            fz_code_build(DD, rd_dd, wr_dd);
             for (int i = 0; i < 24; i++) tab.L(i) = (uint16_t)(256 + i);
             for (int i = 0; i < 144; i++) tab.L(24 + i) = (uint16_t)i;
             for (int i = 0; i < 8; i++) tab.L(168 + i) = (uint16_t)(280 + i);
             for (int i = 0; i < 112; i++) tab.L(176 + i) = (uint16_t)(144 + i);
-            for (int l = 0; l < 16; l++) cnt[l] = 0;
-            cnt[5] = 32;
-            fz_code_regs(DD, cnt, offs);
             for (int i = 0; i < 32; i++) tab.D(i) = (uint16_t)i;
         } else {
             br.refill();
             const uint32_t hlit = br.get(5) + 257, hdist = br.get(5) + 1, hclen = br.get(4) + 4;
             if (hlit > 286 || hdist > 30) { rc = FZ_INF_E_DATA; break; }
-            // code-length code: 19 symbols, <= 7 bits
-            uint8_t cl[19];
-            for (int i = 0; i < 19; i++) cl[i] = 0;
-            for (uint32_t i = 0; i < hclen; i++) { br.refill(); cl[order[i]] = (uint8_t)br.get(3); }
-            uint16_t ccnt[16], coffs[16];
-            for (int l = 0; l < 16; l++) ccnt[l] = 0;
-            for (int i = 0; i < 19; i++) ccnt[cl[i]]++;
-            ccnt[0] = 0;
-            FzCodeRegs CL;
-            if (fz_code_regs(CL, ccnt, coffs) != 0) { rc = FZ_INF_E_DATA; break; }  // zlib requires a complete code here
-            uint8_t clsym[19];
-            for (int i = 0; i < 19; i++) if (cl[i]) clsym[coffs[cl[i]]++] = (uint8_t)i;
+            // code-length code: 19 symbols of <= 7 bits; everything about it is kept packed in registers
+            uint64_t clpack = 0;  // 3 bits per symbol
+            for (uint32_t i = 0; i < hclen; i++) {
+                br.refill();
+                const uint32_t sym = (uint32_t)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31u);
+                clpack |= (uint64_t)br.get(3) << (3 * sym);
+            }
+            uint64_t ccnt = 0;  // 8 bits per code length 0..7
+            for (int s = 0; s < 19; s++) ccnt += 1ull << (8 * ((clpack >> (3 * s)) & 7u));
+            uint64_t coffs = 0;  // first sorted index per code length, 8 bits each
+            FzCode CL;
+            auto rd_cl = [&](int l) -> uint32_t { return l <= 7 ? (uint32_t)((ccnt >> (8 * l)) & 0xffu) : 0u; };
+            auto wr_cl = [&](int l, uint32_t v) { if (l <= 7) coffs |= (uint64_t)v << (8 * l); };
+            if (fz_code_build(CL, rd_cl, wr_cl) != 0) { rc = FZ_INF_E_DATA; break; }  // zlib requires a complete code here
+            uint64_t clsym_lo = 0, clsym_hi = 0;  // sorted symbols, 5 bits each (12 + 7)
+            for (uint32_t s = 0; s < 19; s++) {
+                const uint32_t l = (uint32_t)((clpack >> (3 * s)) & 7u);
+                if (l) {
+                    const uint32_t pos = (uint32_t)((coffs >> (8 * l)) & 0xffu);
+                    coffs += 1ull << (8 * l);
+                    if (pos < 12) clsym_lo |= (uint64_t)s << (5 * pos); else clsym_hi |= (uint64_t)s << (5 * (pos - 12));
+                }
+            }
 
             // two passes over the code-length data: count per length, then place the sorted symbols
             const FzBitReader mark = br;
-            uint16_t cnt_d[16], offs_d[16];
             for (int pass = 0; pass < 2 && rc == FZ_INF_OK; pass++) {
-                if (pass == 0) { for (int l = 0; l < 16; l++) { cnt[l] = 0; cnt_d[l] = 0; } }
+                if (pass == 0) { for (int l = 0; l < 32; l++) tab.C(l) = 0; }
                 else {
-                    cnt[0] = 0; cnt_d[0] = 0;
-                    const int e1 = fz_code_regs(LL, cnt, offs);
-                    const int e2 = fz_code_regs(DD, cnt_d, offs_d);
+                    const int e1 = fz_code_build(LL, rd_ll, wr_ll);
+                    const int e2 = fz_code_build(DD, rd_dd, wr_dd);
                     if (e1 < 0 || e2 < 0) { rc = FZ_INF_E_DATA; break; }  // over-subscribed
                     br = mark;
                 }
@@ -216,22 +241,24 @@ FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t ou
                     br.refill();
                     uint32_t idx;
                     const int l = fz_decode_idx(CL, br.peek(15), idx);
-                    if (l == 0 || l > 7) { rc = FZ_INF_E_DATA; break; }
+                    if (l == 0 || l > 7 || idx >= 19) { rc = FZ_INF_E_DATA; break; }
                     br.drop(l);
-                    const uint32_t s = clsym[idx];
+                    const uint32_t s = (uint32_t)((idx < 12 ? clsym_lo >> (5 * idx) : clsym_hi >> (5 * (idx - 12))) & 31u);
                     uint32_t rep = 1, val = s;
                     if (s == 16) { if (i == 0) { rc = FZ_INF_E_DATA; break; } val = prev; rep = 3 + br.get(2); }
                     else if (s == 17) { val = 0; rep = 3 + br.get(3); }
                     else if (s == 18) { val = 0; rep = 11 + br.get(7); }
                     if (i + rep > total) { rc = FZ_INF_E_DATA; break; }
                     prev = val;
+                    if (val == 0) { i += rep; continue; }
                     if (pass == 0) {
-                        for (uint32_t k = 0; k < rep; k++, i++) { if (i < hlit) cnt[val]++; else cnt_d[val]++; }
-                    } else if (val) {
+                        for (uint32_t k = 0; k < rep; k++, i++) tab.C((i < hlit ? 0 : 16) + (int)val)++;
+                    } else {
                         for (uint32_t k = 0; k < rep; k++, i++) {
-                            if (i < hlit) tab.L(offs[val]++) = (uint16_t)i; else tab.D(offs_d[val]++) = (uint16_t)(i - hlit);
+                            if (i < hlit) { const int o = tab.C((int)val)++; tab.L(o) = (uint16_t)i; }
+                            else { const int o = tab.C(16 + (int)val)++; tab.D(o) = (uint16_t)(i - hlit); }
                         }
-                    } else i += rep;
+                    }
                 }
                 if (br.bits_left < 0) rc = FZ_INF_E_INPUT;
             }

@@ -751,7 +751,7 @@ fz_inflate_fast_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
                        uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
                        uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, const FzStatus *status)
 {
-    __shared__ uint16_t tabs[320 * FZ_INF_THREADS];
+    __shared__ uint16_t tabs[FZ_INF_TAB_U16 * FZ_INF_THREADS];
     if (status->error) return;
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t total_hits = tile_off[nstreams * tiles_per_stream];
@@ -774,7 +774,8 @@ fz_inflate_fast_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
     const uint32_t obeg = k << L;
     const uint32_t expect = min(1u << L, n_s - obeg);
     uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
-    FzInfTab<FZ_INF_THREADS> tab{tabs + threadIdx.x, tabs + 288 * FZ_INF_THREADS + threadIdx.x};
+    FzInfTab<FZ_INF_THREADS> tab{tabs + threadIdx.x, tabs + 288 * FZ_INF_THREADS + threadIdx.x,
+                                 tabs + 320 * FZ_INF_THREADS + threadIdx.x};
     uint32_t out_n = 0;
     size_t used = 0;
     const int rc = fz_inflate(container + stream_off[s] + start, (size_t)(end - start), out, expect, tab, &out_n, &used);
@@ -787,7 +788,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
                           const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_mode,
                           const uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, FzStatus *status)
 {
-    __shared__ uint16_t tabs[320];
+    __shared__ uint16_t tabs[FZ_INF_TAB_U16];
     const uint32_t s = blockIdx.x;
     if (threadIdx.x != 0 || status->error) return;
     const uint32_t mode = stream_mode[s] & 0xffu;
@@ -798,7 +799,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
     const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
     uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk;
-    FzInfTab<1> tab{tabs, tabs + 288};
+    FzInfTab<1> tab{tabs, tabs + 288, tabs + 320};
     uint32_t out_n = 0;
     size_t used = 0;
     const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used);

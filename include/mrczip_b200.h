@@ -107,6 +107,8 @@ typedef struct mzb_ctx mzb_ctx;
  * non-blocking stream).  All device work of a context is ordered on that stream.  A context is not
  * thread-safe; use one per thread (the reference calls run_* from N pthreads, mrc_tarx.c:145-161). */
 int mzb_create(mzb_ctx **out, int device, void *cuda_stream);
+/* Same, but always uses the given stream handle -- including NULL, the legacy default stream. */
+int mzb_create_on_stream(mzb_ctx **out, int device, void *cuda_stream);
 void mzb_destroy(mzb_ctx *ctx);
 /* Chunks processed per kernel batch (bounds scratch memory: about 8 bytes per word of a batch). Default 128. */
 int mzb_set_batch_chunks(mzb_ctx *ctx, uint32_t chunks);

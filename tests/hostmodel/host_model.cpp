@@ -76,8 +76,8 @@ int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_ca
     for (int mis = 0; mis < 1; mis++) {}
     uint8_t *ip = (uint8_t *)ibuf.data() + 1;  // deliberately misaligned input
     memcpy(ip, in, in_len);
-    uint16_t ll[288], dd[32];
-    FzInfTab<1> tab{ll, dd};
+    uint16_t ll[288], dd[32], cnt[32];
+    FzInfTab<1> tab{ll, dd, cnt};
     size_t used = 0;
     int rc = fz_inflate(ip, (size_t)in_len, (uint8_t *)obuf.data(), out_cap, tab, out_n, &used);
     memcpy(out, obuf.data(), *out_n);
