@@ -128,45 +128,118 @@ FZ_HD uint32_t fz_rev15(uint32_t v)  // reverse the low 15 bits
 #endif
 }
 
-// decode one symbol index (into the sorted table) from the next 15 bits; returns the code length (0 = invalid)
+// decode one symbol index (into the sorted table) from the next 15 bits; returns the code length (0 = invalid).
+// Branch-free on purpose: the 32 lanes of a warp decode 32 different streams, so any data-dependent
+// branch here would serialise them.
 FZ_HD int fz_decode_idx(const FzCode &r, uint32_t bits15, uint32_t &idx)
 {
     const uint32_t w = fz_rev15(bits15);
     const uint32_t x = (w << 16) | 0xffffu;  // x < p_l  <=>  w < limit_l
-#define FZ_DEC_STEP(L)                                                                      \
-    if (x < r.p##L) { idx = (w >> (15 - L)) + (uint32_t)((int32_t)(r.p##L << 16) >> 16); return L; }
-    FZ_FOR_LEN_1_15(FZ_DEC_STEP)
-#undef FZ_DEC_STEP
-    return 0;
+    // limits are non-decreasing in l: the code length is 1 + #{l : x >= p_l}; sel = p of that length
+    uint32_t len = 1, sel = r.p15;
+#define FZ_DEC_SEL(L) sel = (x < r.p##L) ? r.p##L : sel;
+    FZ_DEC_SEL(14) FZ_DEC_SEL(13) FZ_DEC_SEL(12) FZ_DEC_SEL(11) FZ_DEC_SEL(10) FZ_DEC_SEL(9) FZ_DEC_SEL(8)
+    FZ_DEC_SEL(7) FZ_DEC_SEL(6) FZ_DEC_SEL(5) FZ_DEC_SEL(4) FZ_DEC_SEL(3) FZ_DEC_SEL(2) FZ_DEC_SEL(1)
+#undef FZ_DEC_SEL
+#define FZ_DEC_CNT(L) len += (x >= r.p##L) ? 1u : 0u;
+    FZ_FOR_LEN_1_15(FZ_DEC_CNT)
+#undef FZ_DEC_CNT
+    idx = (w >> (15 - (len & 15))) + (uint32_t)((int32_t)(sel << 16) >> 16);
+    return len <= 15 ? (int)len : 0;
 }
 
-// Inflate one fragment.  Stops after a BFINAL block, or at the end of the input on a block boundary.
-//   *out_n   bytes produced
-//   *in_used input bytes consumed (rounded up to whole bytes)
-// `out` must be 4-byte aligned.  Reads whole aligned 32-bit words around [in, in+in_len).
+// ---------------------------------------------------------------------------------------------------
+// The inflater as a resumable state machine: step() does one unit of work (one block header, or one
+// literal/length symbol including its match copy) and returns false when the fragment is finished.
+// The GPU kernel drives the 32 lanes of a warp in lock step -- `while (__any_sync(~0u, live)) if (live)
+// live = inf.step();` -- so that lanes reconverge after every symbol; a plain nested loop left each lane
+// running on its own (1.25 active threads per instruction, 50x slower).
+// ---------------------------------------------------------------------------------------------------
 template <class Tab>
-FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t out_cap, const Tab &tab,
-                     uint32_t *out_n, size_t *in_used)
-{
+struct FzInflater {
     FzBitReader br;
-    br.init(in, in_len);
     FzByteWriter bw;
-    bw.init(out, out_cap);
-    int rc = FZ_INF_OK;
-    bool last = false;
-    // order of the code-length code lengths (RFC 1951 3.2.7), 5 bits each, packed
-    const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) | (9ull << 30) |
-                              (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
-    const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+    FzCode LL, DD;
+    Tab tab;
+    size_t in_len;
+    int rc;
+    bool last, in_body;
 
-    auto rd_ll = [&](int l) -> uint32_t { return tab.C(l); };
-    auto wr_ll = [&](int l, uint32_t v) { tab.C(l) = (uint16_t)v; };
-    auto rd_dd = [&](int l) -> uint32_t { return tab.C(16 + l); };
-    auto wr_dd = [&](int l, uint32_t v) { tab.C(16 + l) = (uint16_t)v; };
+    FZ_HD void start(const uint8_t *in, size_t in_len_, uint8_t *out, uint32_t out_cap, const Tab &t)
+    {
+        br.init(in, in_len_);
+        bw.init(out, out_cap);
+        tab = t;
+        in_len = in_len_;
+        rc = FZ_INF_OK;
+        last = false;
+        in_body = false;
+    }
 
-    while (!last) {
-        if (br.bits_left < 3) break;                       // nothing but padding left
-        if (bw.op == out_cap && br.bits_left < 8) break;  // full output, only pad bits left
+    // returns true while there is more to do
+    FZ_HD bool step()
+    {
+        if (in_body) return body_symbol();
+        return block_header();
+    }
+
+    FZ_HD int finish(uint32_t *out_n, size_t *in_used)
+    {
+        bw.finish();
+        if (rc == FZ_INF_OK && br.bits_left < 0) rc = FZ_INF_E_INPUT;
+        *out_n = bw.op;
+        const int64_t used_bits = (int64_t)in_len * 8 - br.bits_left;
+        *in_used = (size_t)((used_bits + 7) / 8);
+        return rc;
+    }
+
+    FZ_HD bool fail(int code) { rc = code; return false; }
+
+    FZ_HD bool body_symbol()
+    {
+        br.refill();
+        if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
+        uint32_t idx;
+        int l = fz_decode_idx(LL, br.peek(15), idx);
+        if (l == 0) return fail(FZ_INF_E_DATA);
+        br.drop(l);
+        uint32_t sym = tab.L((int)idx);
+        if (sym < 256) {
+            if (bw.op >= bw.cap) return fail(FZ_INF_E_SPACE);
+            bw.put(sym);
+            return true;
+        }
+        if (sym == FZ_EOB) {
+            in_body = false;
+            if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
+            return !last;
+        }
+        sym -= 257;
+        if (sym >= 29) return fail(FZ_INF_E_DATA);
+        br.refill();
+        const uint32_t len = fz_len_base(sym) + br.get((int)fz_len_extra_bits(sym));
+        l = fz_decode_idx(DD, br.peek(15), idx);
+        if (l == 0) return fail(FZ_INF_E_DATA);
+        br.drop(l);
+        const uint32_t ds = tab.D((int)idx);
+        if (ds >= 30) return fail(FZ_INF_E_DATA);
+        br.refill();
+        const uint32_t dist = fz_dist_base(ds) + br.get((int)fz_dist_extra_bits(ds));
+        if (dist > bw.op) return fail(FZ_INF_E_HISTORY);
+        if (bw.op + len > bw.cap) return fail(FZ_INF_E_SPACE);
+        if (dist == 1) {
+            const uint32_t c = bw.back(1);
+            for (uint32_t i = 0; i < len; i++) bw.put(c);
+        } else {
+            for (uint32_t i = 0; i < len; i++) bw.put(bw.back(dist));
+        }
+        return true;
+    }
+
+    FZ_HD bool block_header()
+    {
+        if (br.bits_left < 3) return false;                       // nothing but padding left
+        if (bw.op == bw.cap && br.bits_left < 8) return false;    // full output, only pad bits left
         br.refill();
         last = br.get(1) != 0;
         const uint32_t type = br.get(2);
@@ -176,15 +249,19 @@ FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t ou
             const uint32_t len = br.get(16);
             br.refill();
             const uint32_t nlen = br.get(16);
-            if ((len ^ 0xFFFFu) != nlen) { rc = FZ_INF_E_DATA; break; }
-            if (br.bits_left < (int64_t)len * 8) { rc = FZ_INF_E_INPUT; break; }
-            if (bw.op + len > out_cap) { rc = FZ_INF_E_SPACE; break; }
+            if ((len ^ 0xFFFFu) != nlen) return fail(FZ_INF_E_DATA);
+            if (br.bits_left < (int64_t)len * 8) return fail(FZ_INF_E_INPUT);
+            if (bw.op + len > bw.cap) return fail(FZ_INF_E_SPACE);
             for (uint32_t i = 0; i < len; i++) { br.refill(); bw.put(br.get(8)); }
-            continue;
+            return !last;
         }
-        if (type == 3) { rc = FZ_INF_E_DATA; break; }
+        if (type == 3) return fail(FZ_INF_E_DATA);
 
-        FzCode LL, DD;
+        auto rd_ll = [&](int l) -> uint32_t { return tab.C(l); };
+        auto wr_ll = [&](int l, uint32_t v) { tab.C(l) = (uint16_t)v; };
+        auto rd_dd = [&](int l) -> uint32_t { return tab.C(16 + l); };
+        auto wr_dd = [&](int l, uint32_t v) { tab.C(16 + l) = (uint16_t)v; };
+
         if (type == 1) {
             // fixed code: litlen lengths 8 (0-143), 9 (144-255), 7 (256-279), 8 (280-287); 32 distance codes of 5 bits
             for (int l = 0; l < 32; l++) tab.C(l) = 0;
@@ -197,116 +274,92 @@ FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t ou
             for (int i = 0; i < 8; i++) tab.L(168 + i) = (uint16_t)(280 + i);
             for (int i = 0; i < 112; i++) tab.L(176 + i) = (uint16_t)(144 + i);
             for (int i = 0; i < 32; i++) tab.D(i) = (uint16_t)i;
-        } else {
-            br.refill();
-            const uint32_t hlit = br.get(5) + 257, hdist = br.get(5) + 1, hclen = br.get(4) + 4;
-            if (hlit > 286 || hdist > 30) { rc = FZ_INF_E_DATA; break; }
-            // code-length code: 19 symbols of <= 7 bits; everything about it is kept packed in registers
-            uint64_t clpack = 0;  // 3 bits per symbol
-            for (uint32_t i = 0; i < hclen; i++) {
-                br.refill();
-                const uint32_t sym = (uint32_t)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31u);
-                clpack |= (uint64_t)br.get(3) << (3 * sym);
-            }
-            uint64_t ccnt = 0;  // 8 bits per code length 0..7
-            for (int s = 0; s < 19; s++) ccnt += 1ull << (8 * ((clpack >> (3 * s)) & 7u));
-            uint64_t coffs = 0;  // first sorted index per code length, 8 bits each
-            FzCode CL;
-            auto rd_cl = [&](int l) -> uint32_t { return l <= 7 ? (uint32_t)((ccnt >> (8 * l)) & 0xffu) : 0u; };
-            auto wr_cl = [&](int l, uint32_t v) { if (l <= 7) coffs |= (uint64_t)v << (8 * l); };
-            if (fz_code_build(CL, rd_cl, wr_cl) != 0) { rc = FZ_INF_E_DATA; break; }  // zlib requires a complete code here
-            uint64_t clsym_lo = 0, clsym_hi = 0;  // sorted symbols, 5 bits each (12 + 7)
-            for (uint32_t s = 0; s < 19; s++) {
-                const uint32_t l = (uint32_t)((clpack >> (3 * s)) & 7u);
-                if (l) {
-                    const uint32_t pos = (uint32_t)((coffs >> (8 * l)) & 0xffu);
-                    coffs += 1ull << (8 * l);
-                    if (pos < 12) clsym_lo |= (uint64_t)s << (5 * pos); else clsym_hi |= (uint64_t)s << (5 * (pos - 12));
-                }
-            }
+            in_body = true;
+            return true;
+        }
 
-            // two passes over the code-length data: count per length, then place the sorted symbols
-            const FzBitReader mark = br;
-            for (int pass = 0; pass < 2 && rc == FZ_INF_OK; pass++) {
-                if (pass == 0) { for (int l = 0; l < 32; l++) tab.C(l) = 0; }
-                else {
-                    const int e1 = fz_code_build(LL, rd_ll, wr_ll);
-                    const int e2 = fz_code_build(DD, rd_dd, wr_dd);
-                    if (e1 < 0 || e2 < 0) { rc = FZ_INF_E_DATA; break; }  // over-subscribed
-                    br = mark;
-                }
-                uint32_t i = 0, prev = 0;
-                const uint32_t total = hlit + hdist;
-                while (i < total) {
-                    br.refill();
-                    uint32_t idx;
-                    const int l = fz_decode_idx(CL, br.peek(15), idx);
-                    if (l == 0 || l > 7 || idx >= 19) { rc = FZ_INF_E_DATA; break; }
-                    br.drop(l);
-                    const uint32_t s = (uint32_t)((idx < 12 ? clsym_lo >> (5 * idx) : clsym_hi >> (5 * (idx - 12))) & 31u);
-                    uint32_t rep = 1, val = s;
-                    if (s == 16) { if (i == 0) { rc = FZ_INF_E_DATA; break; } val = prev; rep = 3 + br.get(2); }
-                    else if (s == 17) { val = 0; rep = 3 + br.get(3); }
-                    else if (s == 18) { val = 0; rep = 11 + br.get(7); }
-                    if (i + rep > total) { rc = FZ_INF_E_DATA; break; }
-                    prev = val;
-                    if (val == 0) { i += rep; continue; }
-                    if (pass == 0) {
-                        for (uint32_t k = 0; k < rep; k++, i++) tab.C((i < hlit ? 0 : 16) + (int)val)++;
-                    } else {
-                        for (uint32_t k = 0; k < rep; k++, i++) {
-                            if (i < hlit) { const int o = tab.C((int)val)++; tab.L(o) = (uint16_t)i; }
-                            else { const int o = tab.C(16 + (int)val)++; tab.D(o) = (uint16_t)(i - hlit); }
-                        }
+        // order of the code-length code lengths (RFC 1951 3.2.7), 5 bits each, packed
+        const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) | (9ull << 30) |
+                                  (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
+        const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+        br.refill();
+        const uint32_t hlit = br.get(5) + 257, hdist = br.get(5) + 1, hclen = br.get(4) + 4;
+        if (hlit > 286 || hdist > 30) return fail(FZ_INF_E_DATA);
+        // code-length code: 19 symbols of <= 7 bits; everything about it is kept packed in registers
+        uint64_t clpack = 0;  // 3 bits per symbol
+        for (uint32_t i = 0; i < hclen; i++) {
+            br.refill();
+            const uint32_t sym = (uint32_t)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31u);
+            clpack |= (uint64_t)br.get(3) << (3 * sym);
+        }
+        uint64_t ccnt = 0;  // 8 bits per code length 0..7
+        for (int s = 0; s < 19; s++) ccnt += 1ull << (8 * ((clpack >> (3 * s)) & 7u));
+        uint64_t coffs = 0;  // first sorted index per code length, 8 bits each
+        FzCode CL;
+        auto rd_cl = [&](int l) -> uint32_t { return l <= 7 ? (uint32_t)((ccnt >> (8 * l)) & 0xffu) : 0u; };
+        auto wr_cl = [&](int l, uint32_t v) { if (l <= 7) coffs |= (uint64_t)v << (8 * l); };
+        if (fz_code_build(CL, rd_cl, wr_cl) != 0) return fail(FZ_INF_E_DATA);  // zlib requires a complete code here
+        uint64_t clsym_lo = 0, clsym_hi = 0;  // sorted symbols, 5 bits each (12 + 7)
+        for (uint32_t s = 0; s < 19; s++) {
+            const uint32_t l = (uint32_t)((clpack >> (3 * s)) & 7u);
+            if (l) {
+                const uint32_t pos = (uint32_t)((coffs >> (8 * l)) & 0xffu);
+                coffs += 1ull << (8 * l);
+                if (pos < 12) clsym_lo |= (uint64_t)s << (5 * pos); else clsym_hi |= (uint64_t)s << (5 * (pos - 12));
+            }
+        }
+        // two passes over the code-length data: count per length, then place the sorted symbols
+        const FzBitReader mark = br;
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 0) { for (int l = 0; l < 32; l++) tab.C(l) = 0; }
+            else {
+                const int e1 = fz_code_build(LL, rd_ll, wr_ll);
+                const int e2 = fz_code_build(DD, rd_dd, wr_dd);
+                if (e1 < 0 || e2 < 0) return fail(FZ_INF_E_DATA);  // over-subscribed
+                br = mark;
+            }
+            uint32_t i = 0, prev = 0;
+            const uint32_t total = hlit + hdist;
+            while (i < total) {
+                br.refill();
+                uint32_t idx;
+                const int l = fz_decode_idx(CL, br.peek(15), idx);
+                if (l == 0 || l > 7 || idx >= 19) return fail(FZ_INF_E_DATA);
+                br.drop(l);
+                const uint32_t s = (uint32_t)((idx < 12 ? clsym_lo >> (5 * idx) : clsym_hi >> (5 * (idx - 12))) & 31u);
+                uint32_t rep = 1, val = s;
+                if (s == 16) { if (i == 0) return fail(FZ_INF_E_DATA); val = prev; rep = 3 + br.get(2); }
+                else if (s == 17) { val = 0; rep = 3 + br.get(3); }
+                else if (s == 18) { val = 0; rep = 11 + br.get(7); }
+                if (i + rep > total) return fail(FZ_INF_E_DATA);
+                prev = val;
+                if (val == 0) { i += rep; continue; }
+                if (pass == 0) {
+                    for (uint32_t k = 0; k < rep; k++, i++) tab.C((i < hlit ? 0 : 16) + (int)val)++;
+                } else {
+                    for (uint32_t k = 0; k < rep; k++, i++) {
+                        if (i < hlit) { const int o = tab.C((int)val)++; tab.L(o) = (uint16_t)i; }
+                        else { const int o = tab.C(16 + (int)val)++; tab.D(o) = (uint16_t)(i - hlit); }
                     }
                 }
-                if (br.bits_left < 0) rc = FZ_INF_E_INPUT;
             }
-            if (rc != FZ_INF_OK) break;
+            if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
         }
-
-        // ---- block body
-        for (;;) {
-            br.refill();
-            if (br.bits_left < 0) { rc = FZ_INF_E_INPUT; break; }
-            uint32_t idx;
-            int l = fz_decode_idx(LL, br.peek(15), idx);
-            if (l == 0) { rc = FZ_INF_E_DATA; break; }
-            br.drop(l);
-            uint32_t sym = tab.L((int)idx);
-            if (sym < 256) {
-                if (bw.op >= out_cap) { rc = FZ_INF_E_SPACE; break; }
-                bw.put(sym);
-                continue;
-            }
-            if (sym == FZ_EOB) break;
-            sym -= 257;
-            if (sym >= 29) { rc = FZ_INF_E_DATA; break; }
-            br.refill();
-            const uint32_t len = fz_len_base(sym) + br.get((int)fz_len_extra_bits(sym));
-            l = fz_decode_idx(DD, br.peek(15), idx);
-            if (l == 0) { rc = FZ_INF_E_DATA; break; }
-            br.drop(l);
-            const uint32_t ds = tab.D((int)idx);
-            if (ds >= 30) { rc = FZ_INF_E_DATA; break; }
-            br.refill();
-            const uint32_t dist = fz_dist_base(ds) + br.get((int)fz_dist_extra_bits(ds));
-            if (dist > bw.op) { rc = FZ_INF_E_HISTORY; break; }
-            if (bw.op + len > out_cap) { rc = FZ_INF_E_SPACE; break; }
-            if (dist == 1) {
-                const uint32_t c = bw.back(1);
-                for (uint32_t i = 0; i < len; i++) bw.put(c);
-            } else {
-                for (uint32_t i = 0; i < len; i++) bw.put(bw.back(dist));
-            }
-        }
-        if (rc != FZ_INF_OK) break;
-        if (br.bits_left < 0) { rc = FZ_INF_E_INPUT; break; }
+        in_body = true;
+        return true;
     }
-    bw.finish();
-    if (rc == FZ_INF_OK && br.bits_left < 0) rc = FZ_INF_E_INPUT;
-    *out_n = bw.op;
-    const int64_t used_bits = (int64_t)in_len * 8 - br.bits_left;
-    *in_used = (size_t)((used_bits + 7) / 8);
-    return rc;
+};
+
+// Inflate one fragment in one go.  Stops after a BFINAL block, or at the end of the input on a block boundary.
+//   *out_n   bytes produced
+//   *in_used input bytes consumed (rounded up to whole bytes)
+// `out` must be 4-byte aligned.  Reads whole aligned 32-bit words around [in, in+in_len).
+template <class Tab>
+FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t out_cap, const Tab &tab,
+                     uint32_t *out_n, size_t *in_used)
+{
+    FzInflater<Tab> inf;
+    inf.start(in, in_len, out, out_cap, tab);
+    while (inf.step()) {}
+    return inf.finish(out_n, in_used);
 }

@@ -756,30 +756,49 @@ fz_inflate_fast_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t total_hits = tile_off[nstreams * tiles_per_stream];
     const uint32_t hidx = blockIdx.x * FZ_INF_THREADS + threadIdx.x;
-    if (hidx >= total_hits) return;
-    // stream owning this hit: largest s with tile_off[s * tps] <= hidx
-    uint32_t lo = 0, hi = nstreams;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (tile_off[mid * tiles_per_stream] <= hidx) lo = mid; else hi = mid;
+    if (blockIdx.x * FZ_INF_THREADS >= total_hits) return;  // whole block idle
+    bool valid = hidx < total_hits;
+    uint32_t s = 0, start = 0, end = 0, expect = 0;
+    uint8_t *out = nullptr;
+    if (valid) {
+        // stream owning this hit: largest s with tile_off[s * tps] <= hidx
+        uint32_t lo = 0, hi = nstreams;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (tile_off[mid * tiles_per_stream] <= hidx) lo = mid; else hi = mid;
+        }
+        s = lo;
+        const uint32_t mode = stream_mode[s];
+        valid = (mode & 0xffu) == 1u;
+        if (valid) {
+            const uint32_t L = mode >> 8;
+            const uint32_t k = hidx - tile_off[s * tiles_per_stream];
+            start = k ? hits[hidx - 1] + 4 : 0u;
+            end = hits[hidx] + 4;
+            const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+            const uint32_t obeg = k << L;
+            expect = min(1u << L, n_s - obeg);
+            out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
+        }
     }
-    const uint32_t s = lo;
-    const uint32_t mode = stream_mode[s];
-    if ((mode & 0xffu) != 1u) return;
-    const uint32_t L = mode >> 8;
-    const uint32_t k = hidx - tile_off[s * tiles_per_stream];
-    const uint32_t start = k ? hits[hidx - 1] + 4 : 0u;
-    const uint32_t end = hits[hidx] + 4;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
-    const uint32_t obeg = k << L;
-    const uint32_t expect = min(1u << L, n_s - obeg);
-    uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
-    FzInfTab<FZ_INF_THREADS> tab{tabs + threadIdx.x, tabs + 288 * FZ_INF_THREADS + threadIdx.x,
-                                 tabs + 320 * FZ_INF_THREADS + threadIdx.x};
-    uint32_t out_n = 0;
-    size_t used = 0;
-    const int rc = fz_inflate(container + stream_off[s] + start, (size_t)(end - start), out, expect, tab, &out_n, &used);
-    if (rc != FZ_INF_OK || out_n != expect || used != (size_t)(end - start)) atomicExch(&stream_fail[s], 1u);
+    typedef FzInfTab<FZ_INF_THREADS> Tab;
+    Tab tab{tabs + threadIdx.x, tabs + 288 * FZ_INF_THREADS + threadIdx.x, tabs + 320 * FZ_INF_THREADS + threadIdx.x};
+    FzInflater<Tab> inf;
+    bool live = false;
+    if (valid) {
+        inf.start(container + stream_off[s] + start, (size_t)(end - start), out, expect, tab);
+        live = true;
+    }
+    // lock-step drive: the 32 lanes decode 32 different sub-blocks and reconverge after every symbol
+    while (__any_sync(0xffffffffu, live)) {
+        if (live) live = inf.step();
+    }
+    if (valid) {
+        uint32_t out_n = 0;
+        size_t used = 0;
+        const int rc = inf.finish(&out_n, &used);
+        if (rc != FZ_INF_OK || out_n != expect || used != (size_t)(end - start)) atomicExch(&stream_fail[s], 1u);
+    }
 }
 
 // ---- general path: one thread per stream (reference-made streams: back-to-back blocks, no byte alignment between them)

@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--cases", default="G0,G8,G16,P0,S12")
     ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-split", action="store_true")
+    ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     nwords = int(a.gib * (1 << 30)) // 4
     codec = Codec.on_current_stream(batch_chunks=a.batch)
@@ -59,7 +61,7 @@ def main():
     w = gen("G", nwords)
     planes = torch.empty((4, (nwords + 255) // 256 * 256), dtype=torch.uint8, device="cuda")
     back = torch.empty(nwords, dtype=torch.int32, device="cuda")
-    for v in (0, 1):
+    for v in (() if a.no_split else (0, 1)):
         codec.set_variant(v, v)
         t_s, _ = timeit(lambda: codec.mask_split(w, 8, 256, out=planes))
         t_m, _ = timeit(lambda: codec.merge(planes, nwords, out=back))
@@ -88,9 +90,9 @@ def main():
         def decomp():
             holder["d"] = codec.decompress(holder["c"], out=outw)
 
-        tc, tc_med = timeit(comp, iters=3, warm=1)
+        tc, tc_med = timeit(comp, iters=a.iters, warm=1)
         st_c, ms_c = codec.stats(), codec.stage_ms()
-        td, td_med = timeit(decomp, iters=3, warm=1)
+        td, td_med = timeit(decomp, iters=a.iters, warm=1)
         st_d, ms_d = codec.stats(), codec.stage_ms()
         mask = -1 << bits if bits < 32 else 0
         ref = w.clone()
