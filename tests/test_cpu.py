@@ -64,6 +64,9 @@ def test_oracle_matches_reference_golden(oracle, case):
     ref_zip = np.fromfile(GOLDEN / case["ref_container"], dtype=np.uint8)
     ref_erase = np.fromfile(GOLDEN / case["ref_erasebytes"], dtype=np.uint8)
     bits = case["bits"]
+    if src.size < 1024:
+        # erasebytes.c:111-112 always fwrite()s 1024 bytes of its (uninitialised) buffer; only the first fsz are defined
+        ref_erase = ref_erase[: src.size]
     assert np.array_equal(oracle.erasebytes(src, bits), ref_erase)          # erasebytes.c:109-134
     assert np.array_equal(oracle.compress(src, bits), ref_zip)              # byte-identical container
     assert np.array_equal(oracle.decompress(ref_zip), ref_erase[: (src.size // 4) * 4])
