@@ -38,7 +38,7 @@ struct mzb_ctx {
     uint32_t batch_chunks = 128;
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes;
     FzStatus *d_status = nullptr;
     FzStatus *h_status = nullptr;  // pinned
     mzb_stats stats;
@@ -184,7 +184,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->d_status) cudaFree(c->d_status);
@@ -307,6 +307,8 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
         (rc = ensure(c->sizes, nslots * 4)) || (rc = ensure(c->sub_off, nslots * 4)) ||
         (rc = ensure(c->stream_hdr, (size_t)bmax * FZ_PLANES * 4)) || (rc = ensure(c->stream_off, (size_t)bmax * FZ_PLANES * 8)))
         return rc;
+    const size_t ngroups = (size_t)bmax * FZ_PLANES * ((nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
+    if ((rc = ensure(c->ghist, ngroups * 288 * 4)) || (rc = ensure(c->gcodes, ngroups * fz_group_code_bytes()))) return rc;
 
     uint64_t start = 0;
     if (write_file_header) {
@@ -333,7 +335,8 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
         const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
         fz_launch_split((const uint32_t *)d_words + w0, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
         prof_mark(c, FZ_ST_SPLIT);
-        fz_launch_encode((const uint8_t *)c->planes.p, g, (uint8_t *)c->scratch.p, (uint32_t *)c->sizes.p, c->d_status, c->stream);
+        fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p,
+                         (uint32_t *)c->sizes.p, c->d_status, c->stream);
         prof_mark(c, FZ_ST_ENCODE);
         fz_launch_layout((const uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
                          (unsigned long long *)c->stream_off.p, (uint8_t *)d_out, out_cap, c->d_status, c->stream);
@@ -342,7 +345,7 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
                          (const uint32_t *)c->sub_off.p, (const uint32_t *)c->stream_hdr.p,
                          (const unsigned long long *)c->stream_off.p, g, (uint8_t *)d_out, c->d_status, c->stream);
         prof_mark(c, FZ_ST_GATHER);
-        launches += 5 + ((nw & 3) ? 1 : 0);
+        launches += 7 + ((nw & 3) ? 1 : 0);
     }
     if ((rc = status_fetch(c))) return rc;
     prof_collect(c);

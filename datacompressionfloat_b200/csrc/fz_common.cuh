@@ -32,6 +32,7 @@
 #define FZ_SUB_LOG2 14
 #define FZ_SUB (1u << FZ_SUB_LOG2)        // 16 KiB
 #define FZ_SLOT_STRIDE (FZ_SUB + 32u)     // scratch bytes reserved per encoded sub-block
+#define FZ_GROUP_SUBS 32u                 // sub-blocks that share one Huffman code (= one warp of the inflater)
 #define FZ_STORED_OVERHEAD 10u            // 5 (stored header) + 5 (empty stored block)
 #define FZ_SIZE_STORED_FLAG 0x80000000u   // in the per-sub-block size word: emit as stored block
 

@@ -6,6 +6,12 @@
 // the next sub-block starts byte aligned.  BFINAL is never set (reference decoder requirement,
 // SURVEY.md 7.2).  The produced bytes are a valid raw-deflate fragment, not zlib's bytes.
 //
+// One Huffman code serves a GROUP of FZ_GROUP_SUBS consecutive sub-blocks of a stream (512 KiB): the
+// histogram of the group is collected first, the code and the block header are built once per group
+// (fz_build_group_code), and every sub-block is then emitted as its own dynamic block carrying that
+// same header.  The GPU inflater exploits this: the 32 lanes of a warp decode the 32 sub-blocks of a
+// group with ONE shared lookup table (it verifies the headers really are identical).
+//
 // SPMD style: `lane` is 0..31; a phase may only communicate through FzEncState (shared memory on the
 // GPU).  FZ_PHASE(x) runs x for this lane and then __syncwarp() on the device; on the host
 // (tests/hostmodel) it loops the 32 lanes sequentially -- so the same source is checked on the CPU.
@@ -54,16 +60,20 @@ struct FzEncState {
 };
 
 // -------------------------------------------------------------------------------------------------
-// Run tokeniser: the greedy distance-1 matcher (what zlib's Z_RLE strategy does): bytes equal to
-// their predecessor accumulate in `pend`; 258 of them, or a run end with >= 3, become a match,
-// shorter tails become literals.  `prev_init` < 0 means "no byte before `begin`" (sub-block start:
-// sub-blocks never reference earlier data).
+// Run tokeniser (distance-1 matches only, the reference's Z_RLE strategy).  A byte equal to its
+// predecessor is a "repeat".  The first two repeats of a run are emitted as literals right away; from
+// the third repeat on bytes are withheld and leave as one match (3..258) when the run ends or 258 are
+// pending -- or as 1-2 literals if fewer than 3 were withheld.  (zlib withholds from the first repeat;
+// emitting two literals first costs nothing on short runs of frequent symbols and keeps the common
+// path of this loop free of data-dependent branches, which matters when 32 lanes scan 32 pieces.)
+// `prev_init` < 0 means "no byte before `begin`" (sub-block start: sub-blocks never reference earlier data).
 // -------------------------------------------------------------------------------------------------
 template <class Load16, class Sink>
 FZ_HD void fz_scan_piece(const Load16 &ld, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
 {
     int prev = prev_init;
-    uint32_t pend = 0;
+    uint32_t rep = 0;  // repeats of `prev` seen so far in this run (saturates at 2)
+    uint32_t m = 0;    // withheld bytes
     for (uint32_t i = begin; i < end; i += 16) {
         const FzVec16 v = ld(i);
         const uint32_t lim = end - i;
@@ -71,21 +81,23 @@ FZ_HD void fz_scan_piece(const Load16 &ld, uint32_t begin, uint32_t end, int pre
         for (int k = 0; k < 16; k++) {
             if ((uint32_t)k < lim) {
                 const int c = (int)((v.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
-                if (c == prev) {
-                    if (++pend == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); pend = 0; }
+                const bool eq = c == prev;
+                if (eq && rep >= 2) {
+                    if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
                 } else {
-                    if (pend) {
-                        if (pend >= FZ_MIN_MATCH) sink.match(pend); else sink.literal((uint32_t)prev, pend);
-                        pend = 0;
+                    if (m) {
+                        if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
+                        m = 0;
                     }
-                    sink.literal((uint32_t)c, 1);
+                    rep = eq ? rep + 1 : 0;
                     prev = c;
+                    sink.literal((uint32_t)c, 1);
                 }
             }
         }
     }
-    if (pend) {
-        if (pend >= FZ_MIN_MATCH) sink.match(pend); else sink.literal((uint32_t)prev, pend);
+    if (m) {
+        if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
     }
 }
 
@@ -99,26 +111,25 @@ FZ_HD void fz_atomic_add(uint32_t *p, uint32_t v)
 }
 
 struct FzHistSink {
-    FzEncState *st;
-    FZ_HD void literal(uint32_t c, uint32_t n) { fz_atomic_add(&st->hist[c], n); }
+    uint32_t *hist;  // 288 counters (shared memory on the GPU)
+    FZ_HD void literal(uint32_t c, uint32_t n) { fz_atomic_add(&hist[c], n); }
     FZ_HD void match(uint32_t len)
     {
         uint32_t lc, eb, ev;
         fz_len_code(len, lc, eb, ev);
-        fz_atomic_add(&st->hist[257 + lc], 1);
-        fz_atomic_add(&st->nmatch, 1);
+        fz_atomic_add(&hist[257 + lc], 1);
     }
 };
 
 struct FzCountSink {
-    const FzEncState *st;
+    const uint8_t *len;
     uint32_t bits;
-    FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * st->len[c]; }
-    FZ_HD void match(uint32_t len)
+    FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * len[c]; }
+    FZ_HD void match(uint32_t mlen)
     {
         uint32_t lc, eb, ev;
-        fz_len_code(len, lc, eb, ev);
-        bits += st->len[257 + lc] + eb + 1;  // + 1-bit distance code
+        fz_len_code(mlen, lc, eb, ev);
+        bits += len[257 + lc] + eb + 1;  // + 1-bit distance code
     }
 };
 
@@ -151,18 +162,19 @@ struct FzBitWriter {
 };
 
 struct FzEmitSink {
-    const FzEncState *st;
+    const uint16_t *code;
+    const uint8_t *len;
     FzBitWriter bw;
     FZ_HD void literal(uint32_t c, uint32_t n)
     {
-        const uint32_t code = st->code[c], l = st->len[c];
-        for (uint32_t i = 0; i < n; i++) bw.put(code, l);
+        const uint32_t cd = code[c], l = len[c];
+        for (uint32_t i = 0; i < n; i++) bw.put(cd, l);
     }
-    FZ_HD void match(uint32_t len)
+    FZ_HD void match(uint32_t mlen)
     {
         uint32_t lc, eb, ev;
-        fz_len_code(len, lc, eb, ev);
-        bw.put(st->code[257 + lc], st->len[257 + lc]);
+        fz_len_code(mlen, lc, eb, ev);
+        bw.put(code[257 + lc], len[257 + lc]);
         bw.put(ev, eb + 1);  // extra bits, then the 1-bit distance code '0' (distance 1)
     }
 };
@@ -172,10 +184,9 @@ struct FzEmitSink {
 // -------------------------------------------------------------------------------------------------
 #define FZ_SYMS_PER_LANE 9  // 32 * 9 = 288
 
-FZ_HD void fz_ph_zero(FzEncState *st, int lane)
+FZ_HD void fz_ph_zero_len(FzEncState *st, int lane)
 {
-    for (int i = lane; i < 288; i += 32) { st->hist[i] = 0; st->len[i] = 0; }
-    if (lane == 0) st->nmatch = 0;
+    for (int i = lane; i < 288; i += 32) st->len[i] = 0;
 }
 
 FZ_HD void fz_ph_count_active(FzEncState *st, int lane)
@@ -183,7 +194,7 @@ FZ_HD void fz_ph_count_active(FzEncState *st, int lane)
     uint32_t c = 0;
     for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
         const int s = lane * FZ_SYMS_PER_LANE + k;
-        c += (s == FZ_EOB || st->hist[s] != 0) ? 1u : 0u;
+        c += st->hist[s] != 0 ? 1u : 0u;
     }
     st->lane_cnt[lane] = c;
 }
@@ -194,7 +205,7 @@ FZ_HD void fz_ph_compact(FzEncState *st, int lane)
     for (int l = 0; l < 32; l++) { const uint32_t c = st->lane_cnt[l]; if (l < lane) off += c; total += c; }
     for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
         const int s = lane * FZ_SYMS_PER_LANE + k;
-        const uint32_t f = (s == FZ_EOB) ? 1u : st->hist[s];
+        const uint32_t f = st->hist[s];
         if (f) st->keys[off++] = (f << 9) | (uint32_t)s;
     }
     // pad to the next power of two with +inf keys for the bitonic network
@@ -434,80 +445,19 @@ FZ_HD void fz_ph_header(FzEncState *st, int lane)
 #undef FZ_HPUT
 }
 
-// exact size of the dynamic block from the histogram
+// exact payload bits (without headers) of coding the group's tokens with the code just built
 FZ_HD void fz_ph_cost_partial(FzEncState *st, int lane)
 {
-    uint32_t b = 0;
+    uint64_t b = 0;
     for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
         const int s = lane * FZ_SYMS_PER_LANE + k;
         if (s >= FZ_NUM_LL) break;
-        const uint32_t f = (s == FZ_EOB) ? 1u : st->hist[s];
+        const uint64_t f = st->hist[s];
         b += f * st->len[s];
         if (s > FZ_EOB) b += f * (fz_len_extra_bits((uint32_t)(s - 257)) + 1);
     }
-    st->lane_cnt[lane] = b;
-}
-
-FZ_HD void fz_ph_cost_total(FzEncState *st, int lane)
-{
-    if (lane != 0) return;
-    uint32_t b = st->hdr_nbits;
-    for (int l = 0; l < 32; l++) b += st->lane_cnt[l];
-    st->dyn_bits = b;
-}
-
-// Shannon lower bound of the literal/length coding cost in bits (an early-out for incompressible
-// sub-blocks: no Huffman code can beat it).  Host and device use log2f.
-#if defined(__CUDA_ARCH__)
-#define FZ_LOG2F(x) __log2f(x)
-#else
-#include <math.h>
-#include <string.h>
-#define FZ_LOG2F(x) log2f(x)
-#endif
-
-FZ_HD uint32_t fz_f2u(float f)
-{
-#if defined(__CUDA_ARCH__)
-    return __float_as_uint(f);
-#else
-    uint32_t u; memcpy(&u, &f, 4); return u;
-#endif
-}
-FZ_HD float fz_u2f(uint32_t u)
-{
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(u);
-#else
-    float f; memcpy(&f, &u, 4); return f;
-#endif
-}
-
-FZ_HD void fz_ph_entropy_partial(FzEncState *st, uint32_t ntokens_hint, int lane)
-{
-    (void)ntokens_hint;
-    float h = 0.f;
-    uint32_t tot = 0;
-    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
-        const int s = lane * FZ_SYMS_PER_LANE + k;
-        const uint32_t f = (s == FZ_EOB) ? 1u : st->hist[s];
-        if (f) { h -= (float)f * FZ_LOG2F((float)f); tot += f; }
-    }
-    st->lane_cnt[lane] = tot;
-    st->lane_bits[lane] = fz_f2u(h);
-}
-
-// true when the entropy bound says a dynamic block cannot be smaller than a stored one
-FZ_HD bool fz_entropy_says_stored(const FzEncState *st, uint32_t n)
-{
-    float h = 0.f;
-    uint32_t tot = 0;
-    for (int l = 0; l < 32; l++) { h += fz_u2f(st->lane_bits[l]); tot += st->lane_cnt[l]; }
-    h += (float)tot * FZ_LOG2F((float)tot);   // sum f*log2(tot/f)
-    // + a header of at least ~40 bytes for an alphabet this flat; keep 1% safety so that blocks the
-    // exact computation could still win by a hair are not mis-classified the other way round
-    const float bound_bytes = h * 0.125f + 40.f;
-    return bound_bytes >= (float)n * 0.995f + (float)FZ_STORED_OVERHEAD;
+    st->lane_cnt[lane] = (uint32_t)b;          // 64-bit partial sum, low / high halves
+    st->lane_bits[lane] = (uint32_t)(b >> 32);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -515,94 +465,36 @@ FZ_HD bool fz_entropy_says_stored(const FzEncState *st, uint32_t n)
 // -------------------------------------------------------------------------------------------------
 FZ_HD uint32_t fz_piece_len(uint32_t n) { return (((n + 31) / 32) + 15) & ~15u; }
 
+// histogram of one sub-block's tokens into hist[288] (must be zeroed; one warp's shared memory)
 template <class Load16, class LoadByte>
-FZ_HD void fz_ph_hist(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
+FZ_HD void fz_ph_hist(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
 {
     const uint32_t P = fz_piece_len(n);
     uint32_t b = lane * P, e = b + P;
     if (e > n) e = n;
     if (b >= e) return;
-    FzHistSink sink{st};
+    FzHistSink sink{hist};
     fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
 }
 
-template <class Load16, class LoadByte>
-FZ_HD void fz_ph_count(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
-{
-    const uint32_t P = fz_piece_len(n);
-    uint32_t b = lane * P, e = b + P;
-    if (e > n) e = n;
-    FzCountSink sink{st, 0};
-    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
-    if (lane == 0) sink.bits += st->hdr_nbits;
-    st->lane_bits[lane] = sink.bits;
-}
+// The code of a group as the emit kernel consumes it (global memory, copied to shared memory per warp)
+struct FzGroupCode {
+    uint16_t code[288];   // bit-reversed canonical codes
+    uint8_t len[288];
+    uint32_t hdr[160];    // bit-packed dynamic block header (BFINAL=0, BTYPE=10, lengths)
+    uint32_t hdr_nbits;
+    uint32_t stored;      // 1: coding this group cannot beat stored blocks -- emit every sub-block stored
+    uint32_t pad[2];
+};
 
-// emit this lane's tokens at its bit offset; lane 0 prepends the block header, lane 31 appends
-// EOB + the empty stored block (000, pad to byte, 00 00 FF FF)
-template <class Load16, class LoadByte>
-FZ_HD void fz_ph_emit(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
-{
-    uint32_t off = 0;
-    for (int l = 0; l < lane; l++) off += st->lane_bits[l];
-    const uint32_t P = fz_piece_len(n);
-    uint32_t b = lane * P, e = b + P;
-    if (e > n) e = n;
-    FzEmitSink sink;
-    sink.st = st;
-    sink.bw.init(out, off);
-    if (lane == 0) {
-        uint32_t nb = st->hdr_nbits, w = 0;
-        while (nb >= 32) { sink.bw.put(st->hdr[w++], 32); nb -= 32; }
-        if (nb) sink.bw.put(st->hdr[w] & ((1u << nb) - 1), nb);
-    }
-    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
-    if (lane == 31) {
-        sink.bw.put(st->code[FZ_EOB], st->len[FZ_EOB]);
-        sink.bw.put(0, 3);
-        sink.bw.align_byte();
-        sink.bw.put(0x0000u, 16);
-        sink.bw.put(0xFFFFu, 16);
-        st->dyn_bits = sink.bw.bitpos();  // now: total bits of the sub-block fragment (byte aligned)
-    }
-    st->fw_idx[lane] = sink.bw.first_idx;
-    st->crossed[lane] = sink.bw.crossed ? 1u : 0u;
-    if (sink.bw.crossed) { st->fw_bits[lane] = sink.bw.first_bits; st->tw_bits[lane] = (uint32_t)sink.bw.acc; }
-    else { st->fw_bits[lane] = (uint32_t)sink.bw.acc; st->tw_bits[lane] = 0; }
-}
-
-// words shared by several lanes: the lane that completes a word ORs in what earlier lanes left there
-FZ_HD void fz_ph_merge(FzEncState *st, uint32_t *out, int lane)
-{
-    uint32_t carry = 0;
-    for (int j = lane - 1; j >= 0; j--) {
-        if (st->crossed[j]) { carry |= st->tw_bits[j]; break; }
-        carry |= st->fw_bits[j];
-    }
-    if (st->crossed[lane]) out[st->fw_idx[lane]] = st->fw_bits[lane] | carry;
-    if (lane == 31) {
-        const uint32_t total_bits = st->dyn_bits;
-        if (total_bits & 31) out[total_bits >> 5] = st->crossed[31] ? st->tw_bits[31] : (st->fw_bits[31] | carry);
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
-// The whole sub-block.  Returns the fragment size in bytes, or n + FZ_STORED_OVERHEAD with
-// FZ_SIZE_STORED_FLAG set when a stored block is the better (or only safe) choice; in that case
-// nothing is written to `out` (the gather kernel synthesises stored blocks from the plane bytes).
-// On the device every lane of the warp calls this with its own `lane`; on the host `lane` is unused.
-// `out` needs room for FZ_SLOT_STRIDE bytes.
-// -------------------------------------------------------------------------------------------------
-template <class Load16, class LoadByte>
-FZ_HD uint32_t fz_encode_subblock(FzEncState *st, const Load16 &ld, const LoadByte &lb, uint32_t n,
-                                  uint32_t *out, int lane)
+// Build the group's Huffman code and block header from its token histogram.
+//   st->hist[0..287] = token frequencies of the whole group, st->hist[256] = number of sub-blocks (EOBs)
+//   group_bytes = plane bytes in the group, nsub = sub-blocks in the group
+template <int DUMMY = 0>
+FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t nsub, FzGroupCode *out, int lane)
 {
     (void)lane;
-    const uint32_t stored = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG;
-    FZ_PHASE(fz_ph_zero(st, lane));
-    FZ_PHASE(fz_ph_hist(st, ld, lb, n, lane));
-    FZ_PHASE(fz_ph_entropy_partial(st, n, lane));
-    if (fz_entropy_says_stored(st, n)) return stored;
+    FZ_PHASE(fz_ph_zero_len(st, lane));
     FZ_PHASE(fz_ph_count_active(st, lane));
     FZ_PHASE(fz_ph_compact(st, lane));
     {
@@ -621,12 +513,114 @@ FZ_HD uint32_t fz_encode_subblock(FzEncState *st, const Load16 &ld, const LoadBy
     FZ_PHASE(fz_ph_cl_tokens(st, lane));
     FZ_PHASE(fz_ph_header(st, lane));
     FZ_PHASE(fz_ph_cost_partial(st, lane));
-    FZ_PHASE(fz_ph_cost_total(st, lane));
+    // group decision: all sub-blocks dynamic vs all stored (the per-sub-block decision is exact, in fz_emit_subblock)
+    uint64_t bits = (uint64_t)nsub * (st->hdr_nbits + 3 + 4 + 32);  // header + empty stored block (avg pad 4) per sub-block
+    for (int l = 0; l < 32; l++) bits += ((uint64_t)st->lane_bits[l] << 32) | st->lane_cnt[l];
+    const uint64_t stored_bits = 8ull * ((uint64_t)group_bytes + (uint64_t)FZ_STORED_OVERHEAD * nsub);
+    const uint32_t stored = bits >= stored_bits ? 1u : 0u;
+#if defined(__CUDA_ARCH__)
+    for (int i = lane; i < 288; i += 32) { out->code[i] = st->code[i]; out->len[i] = st->len[i]; }
+    for (int i = lane; i < 160; i += 32) out->hdr[i] = st->hdr[i];
+    if (lane == 0) { out->hdr_nbits = st->hdr_nbits; out->stored = stored; }
+    __syncwarp();
+#else
+    for (int i = 0; i < 288; i++) { out->code[i] = st->code[i]; out->len[i] = st->len[i]; }
+    for (int i = 0; i < 160; i++) out->hdr[i] = st->hdr[i];
+    out->hdr_nbits = st->hdr_nbits; out->stored = stored;
+#endif
+}
+
+// per-warp scratch of the emit stage
+struct FzEmitState {
+    uint32_t lane_bits[32];
+    uint32_t fw_idx[32], fw_bits[32], tw_bits[32], crossed[32];
+    uint32_t total_bits;
+    uint32_t pad[3];
+};
+
+template <class Load16, class LoadByte>
+FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
+{
+    const uint32_t P = fz_piece_len(n);
+    uint32_t b = lane * P, e = b + P;
+    if (e > n) e = n;
+    FzCountSink sink{gc->len, 0};
+    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    if (lane == 0) sink.bits += gc->hdr_nbits;
+    es->lane_bits[lane] = sink.bits;
+}
+
+// emit this lane's tokens at its bit offset; lane 0 prepends the block header, lane 31 appends
+// EOB + the empty stored block (000, pad to byte, 00 00 FF FF)
+template <class Load16, class LoadByte>
+FZ_HD void fz_ph_emit(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, const LoadByte &lb, uint32_t n,
+                      uint32_t *out, int lane)
+{
+    uint32_t off = 0;
+    for (int l = 0; l < lane; l++) off += es->lane_bits[l];
+    const uint32_t P = fz_piece_len(n);
+    uint32_t b = lane * P, e = b + P;
+    if (e > n) e = n;
+    FzEmitSink sink;
+    sink.code = gc->code;
+    sink.len = gc->len;
+    sink.bw.init(out, off);
+    if (lane == 0) {
+        uint32_t nb = gc->hdr_nbits, w = 0;
+        while (nb >= 32) { sink.bw.put(gc->hdr[w++], 32); nb -= 32; }
+        if (nb) sink.bw.put(gc->hdr[w] & ((1u << nb) - 1), nb);
+    }
+    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    if (lane == 31) {
+        sink.bw.put(gc->code[FZ_EOB], gc->len[FZ_EOB]);
+        sink.bw.put(0, 3);
+        sink.bw.align_byte();
+        sink.bw.put(0x0000u, 16);
+        sink.bw.put(0xFFFFu, 16);
+        es->total_bits = sink.bw.bitpos();  // total bits of the sub-block fragment (byte aligned)
+    }
+    es->fw_idx[lane] = sink.bw.first_idx;
+    es->crossed[lane] = sink.bw.crossed ? 1u : 0u;
+    if (sink.bw.crossed) { es->fw_bits[lane] = sink.bw.first_bits; es->tw_bits[lane] = (uint32_t)sink.bw.acc; }
+    else { es->fw_bits[lane] = (uint32_t)sink.bw.acc; es->tw_bits[lane] = 0; }
+}
+
+// words shared by several lanes: the lane that completes a word ORs in what earlier lanes left there
+FZ_HD void fz_ph_merge(FzEmitState *es, uint32_t *out, int lane)
+{
+    uint32_t carry = 0;
+    for (int j = lane - 1; j >= 0; j--) {
+        if (es->crossed[j]) { carry |= es->tw_bits[j]; break; }
+        carry |= es->fw_bits[j];
+    }
+    if (es->crossed[lane]) out[es->fw_idx[lane]] = es->fw_bits[lane] | carry;
+    if (lane == 31) {
+        const uint32_t total_bits = es->total_bits;
+        if (total_bits & 31) out[total_bits >> 5] = es->crossed[31] ? es->tw_bits[31] : (es->fw_bits[31] | carry);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Emit one sub-block with its group's code.  Returns the fragment size in bytes, or
+// n + FZ_STORED_OVERHEAD with FZ_SIZE_STORED_FLAG set when a stored block is smaller; then nothing is
+// written to `out` (the gather kernel synthesises stored blocks from the plane bytes).
+// On the device every lane of the warp calls this with its own `lane`; on the host `lane` is unused.
+// `out` needs room for FZ_SLOT_STRIDE bytes.
+// -------------------------------------------------------------------------------------------------
+template <class Load16, class LoadByte>
+FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, const LoadByte &lb, uint32_t n,
+                                uint32_t *out, int lane)
+{
+    (void)lane;
+    const uint32_t stored = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG;
+    if (gc->stored) return stored;
+    FZ_PHASE(fz_ph_count(gc, es, ld, lb, n, lane));
+    uint32_t bits = gc->len[FZ_EOB];
+    for (int l = 0; l < 32; l++) bits += es->lane_bits[l];
     // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
-    const uint32_t dyn_bytes = (st->dyn_bits + 3 + 7) / 8 + 4;
+    const uint32_t dyn_bytes = (bits + 3 + 7) / 8 + 4;
     if (dyn_bytes >= n + FZ_STORED_OVERHEAD) return stored;
-    FZ_PHASE(fz_ph_count(st, ld, lb, n, lane));
-    FZ_PHASE(fz_ph_emit(st, ld, lb, n, out, lane));
-    FZ_PHASE(fz_ph_merge(st, out, lane));
-    return st->dyn_bits / 8;
+    FZ_PHASE(fz_ph_emit(gc, es, ld, lb, n, out, lane));
+    FZ_PHASE(fz_ph_merge(es, out, lane));
+    return es->total_bits / 8;
 }

@@ -74,12 +74,24 @@ struct FzByteWriter {
         if ((p >> 2) == (op >> 2)) return (ow >> ((p & 3) * 8)) & 0xffu;  // still pending in ow
         return out[p];
     }
+    FZ_HD void fill(uint32_t c, uint32_t len)  // len copies of byte c (a distance-1 match), whole words where possible
+    {
+        while (len && (op & 3)) { put(c); len--; }
+        const uint32_t w = c * 0x01010101u;
+        while (len >= 4) { *(uint32_t *)(out + op) = w; op += 4; len -= 4; }
+        while (len) { put(c); len--; }
+    }
     FZ_HD void finish()
     {
         const uint32_t r = op & 3;
         for (uint32_t i = 0; i < r; i++) out[op - r + i] = (uint8_t)(ow >> (8 * i));
     }
 };
+
+// first-level lookup table of the warp-shared fast path: index = next FZ_LUT_BITS stream bits,
+// entry = symbol | code length << 9 (0 = code longer than FZ_LUT_BITS: use the canonical search)
+#define FZ_LUT_BITS 10
+#define FZ_LUT_SIZE (1 << FZ_LUT_BITS)
 
 #define FZ_INF_OK 0
 #define FZ_INF_E_INPUT (-1)     // ran out of input / truncated
@@ -164,6 +176,7 @@ struct FzInflater {
     size_t in_len;
     int rc;
     bool last, in_body;
+    bool shared_tab;  // tables are shared with other lanes: this lane must not rebuild them (no further coded block)
 
     FZ_HD void start(const uint8_t *in, size_t in_len_, uint8_t *out, uint32_t out_cap, const Tab &t)
     {
@@ -174,12 +187,18 @@ struct FzInflater {
         rc = FZ_INF_OK;
         last = false;
         in_body = false;
+        shared_tab = false;
     }
 
     // returns true while there is more to do
     FZ_HD bool step()
     {
-        if (in_body) return body_symbol();
+        if (in_body) return body_symbol(nullptr);
+        return block_header();
+    }
+    FZ_HD bool step_lut(const uint16_t *lut)
+    {
+        if (in_body) return body_symbol(lut);
         return block_header();
     }
 
@@ -195,15 +214,22 @@ struct FzInflater {
 
     FZ_HD bool fail(int code) { rc = code; return false; }
 
-    FZ_HD bool body_symbol()
+    FZ_HD bool body_symbol(const uint16_t *lut)
     {
         br.refill();
         if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
-        uint32_t idx;
-        int l = fz_decode_idx(LL, br.peek(15), idx);
-        if (l == 0) return fail(FZ_INF_E_DATA);
-        br.drop(l);
-        uint32_t sym = tab.L((int)idx);
+        uint32_t idx, sym;
+        int l;
+        const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
+        if (e) {
+            sym = e & 511u;
+            br.drop((int)(e >> 9));
+        } else {
+            l = fz_decode_idx(LL, br.peek(15), idx);
+            if (l == 0) return fail(FZ_INF_E_DATA);
+            br.drop(l);
+            sym = tab.L((int)idx);
+        }
         if (sym < 256) {
             if (bw.op >= bw.cap) return fail(FZ_INF_E_SPACE);
             bw.put(sym);
@@ -228,8 +254,7 @@ struct FzInflater {
         if (dist > bw.op) return fail(FZ_INF_E_HISTORY);
         if (bw.op + len > bw.cap) return fail(FZ_INF_E_SPACE);
         if (dist == 1) {
-            const uint32_t c = bw.back(1);
-            for (uint32_t i = 0; i < len; i++) bw.put(c);
+            bw.fill(bw.back(1), len);
         } else {
             for (uint32_t i = 0; i < len; i++) bw.put(bw.back(dist));
         }
@@ -256,6 +281,7 @@ struct FzInflater {
             return !last;
         }
         if (type == 3) return fail(FZ_INF_E_DATA);
+        if (shared_tab) return fail(FZ_INF_E_DATA);  // a second coded block would overwrite the shared tables
 
         auto rd_ll = [&](int l) -> uint32_t { return tab.C(l); };
         auto wr_ll = [&](int l, uint32_t v) { tab.C(l) = (uint16_t)v; };

@@ -283,17 +283,13 @@ void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwor
 }
 
 // =================================================================================================
-// deflate: one warp per sub-block
+// deflate: three kernels
+//   fz_hist_kernel        one warp per 16 KiB sub-block: token histogram, accumulated per group of 32 sub-blocks
+//   fz_group_code_kernel  one warp per group: Huffman code + block header (once per 512 KiB of plane)
+//   fz_emit_kernel        one warp per sub-block: exact size, stored-vs-dynamic decision, lane-parallel bit emission
 // =================================================================================================
 #define FZ_ENC_WARPS 4
 #define FZ_STAGE_BYTES (32 * (FZ_SUB / 32 + 16))
-
-struct __align__(16) FzEncSmem {
-    FzEncState st;
-    alignas(16) uint8_t stage[FZ_STAGE_BYTES];
-};
-
-size_t fz_encode_smem_bytes() { return sizeof(FzEncSmem) * FZ_ENC_WARPS; }
 
 struct DevLoad16 {
     const uint8_t *sm;
@@ -318,52 +314,150 @@ __device__ __forceinline__ const uint8_t *fz_sub_src(const uint8_t *planes, cons
     return planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk + (uint64_t)k * FZ_SUB;
 }
 
+// sub-block slot t -> (stream, k, n); false if the slot is empty (ragged last chunk)
+__device__ __forceinline__ bool fz_slot(const FzBatchGeom &g, uint32_t t, uint32_t &s, uint32_t &k, uint32_t &n)
+{
+    s = t / g.nsub_full;
+    k = t - s * g.nsub_full;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t off = k * FZ_SUB;
+    if (off >= n_s) return false;
+    n = min((uint32_t)FZ_SUB, n_s - off);
+    return true;
+}
+
+// stage the sub-block in shared memory: lane l's piece [l*P, (l+1)*P) is stored at l*(P+16)
+// (bank-conflict-free 128-bit reads when every lane walks its own piece)
+__device__ __forceinline__ void fz_stage(uint8_t *stage, const uint8_t *src, uint32_t n, uint32_t P, int lane)
+{
+    if (((uintptr_t)src & 15u) == 0) {
+        for (uint32_t i = lane * 16; i < n; i += FZ_WARP * 16) {
+            const uint4 v = *(const uint4 *)(src + i);
+            *(uint4 *)(stage + i + (i / P) * 16) = v;
+        }
+    } else {
+        for (uint32_t i = lane; i < n; i += FZ_WARP) stage[i + (i / P) * 16] = src[i];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t fz_groups_per_stream(const FzBatchGeom &g)
+{
+    return (g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS;
+}
+
+struct __align__(16) FzHistSmem {
+    alignas(16) uint8_t stage[FZ_STAGE_BYTES];
+    uint32_t hist[288];
+};
+
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
-fz_encode_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint8_t *__restrict__ scratch,
-                 uint32_t *__restrict__ sizes, FzStatus *status)
+fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
-    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
-    if (t >= total) return;
-    const uint32_t s = t / g.nsub_full, k = t - s * g.nsub_full;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
-    const uint32_t off = k * FZ_SUB;
-    if (off >= n_s) return;
-    const uint32_t n = min((uint32_t)FZ_SUB, n_s - off);
-    FzEncSmem *sm = (FzEncSmem *)fz_smem + warp;
-    const uint8_t *src = fz_sub_src(planes, g, s, k);
-
-    // stage the sub-block: lane l's piece [l*P, (l+1)*P) is stored at l*(P+16) (bank-conflict-free 128-bit reads)
+    if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
+    uint32_t s, k, n;
+    if (!fz_slot(g, t, s, k, n)) return;
+    FzHistSmem *sm = (FzHistSmem *)fz_smem + warp;
     const uint32_t P = fz_piece_len(n);
-    if (((uintptr_t)src & 15u) == 0) {
-        for (uint32_t i = lane * 16; i < n; i += FZ_WARP * 16) {
-            const uint4 v = *(const uint4 *)(src + i);
-            *(uint4 *)(sm->stage + i + (i / P) * 16) = v;
-        }
-    } else {
-        for (uint32_t i = lane; i < n; i += FZ_WARP) sm->stage[i + (i / P) * 16] = src[i];
-    }
+    for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
+    fz_stage(sm->stage, fz_sub_src(planes, g, s, k), n, P, lane);
+    DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
+    DevLoadByte lb{sm->stage, P};
+    fz_ph_hist(sm->hist, ld, lb, n, lane);
     __syncwarp();
+    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+    for (int i = lane; i < 288; i += 32) {
+        const uint32_t v = sm->hist[i];
+        if (v) atomicAdd(gh + i, v);
+    }
+}
 
+__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
+fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupCode *__restrict__ gcodes)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gps = fz_groups_per_stream(g);
+    const uint32_t gi = blockIdx.x * FZ_ENC_WARPS + warp;
+    if (gi >= g.nchunks * FZ_PLANES * gps) return;
+    const uint32_t s = gi / gps, gk = gi - s * gps;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
+    if ((uint64_t)gk * gbytes >= n_s) return;
+    const uint32_t gn = (uint32_t)min((uint64_t)n_s - (uint64_t)gk * gbytes, gbytes);
+    const uint32_t nsub = (gn + FZ_SUB - 1) / FZ_SUB;
+    FzEncState *st = (FzEncState *)fz_smem + warp;
+    for (int i = lane; i < 288; i += 32) st->hist[i] = ghist[(uint64_t)gi * 288 + i];
+    __syncwarp();
+    if (lane == 0) st->hist[FZ_EOB] = nsub;  // one end-of-block per sub-block
+    __syncwarp();
+    fz_build_group_code(st, gn, nsub, gcodes + gi, lane);
+}
+
+struct __align__(16) FzEmitSmem {
+    alignas(16) uint8_t stage[FZ_STAGE_BYTES];
+    FzGroupCode gc;
+    FzEmitState es;
+};
+
+__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
+fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupCode *__restrict__ gcodes,
+               uint8_t *__restrict__ scratch, uint32_t *__restrict__ sizes, FzStatus *status)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
+    if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
+    uint32_t s, k, n;
+    if (!fz_slot(g, t, s, k, n)) return;
+    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
+    if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to stage or emit
+        if (lane == 0) { sizes[t] = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
+        return;
+    }
+    FzEmitSmem *sm = (FzEmitSmem *)fz_smem + warp;
+    {   // group code -> shared memory (word copy)
+        const uint32_t *src = (const uint32_t *)ggc;
+        uint32_t *dst = (uint32_t *)&sm->gc;
+        for (uint32_t i = lane; i < sizeof(FzGroupCode) / 4; i += 32) dst[i] = src[i];
+    }
+    const uint32_t P = fz_piece_len(n);
+    fz_stage(sm->stage, fz_sub_src(planes, g, s, k), n, P, lane);
     DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
     DevLoadByte lb{sm->stage, P};
     uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
-    const uint32_t r = fz_encode_subblock(&sm->st, ld, lb, n, out, lane);
+    const uint32_t r = fz_emit_subblock(&sm->gc, &sm->es, ld, lb, n, out, lane);
     if (lane == 0) {
         sizes[t] = r;
         if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
     }
 }
 
-void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint8_t *scratch, uint32_t *sizes, FzStatus *status, cudaStream_t st)
+size_t fz_encode_smem_bytes() { return sizeof(FzEmitSmem) * FZ_ENC_WARPS; }
+
+void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, void *gcodes, uint8_t *scratch, uint32_t *sizes,
+                      FzStatus *status, cudaStream_t st)
 {
-    cudaFuncSetAttribute(fz_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_encode_smem_bytes());
-    const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
+    const uint32_t nstreams = g.nchunks * FZ_PLANES;
+    const uint32_t total = nstreams * g.nsub_full;
+    const uint32_t gps = (g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS;
+    const uint32_t ngroups = nstreams * gps;
     const unsigned grid = (total + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS;
-    fz_encode_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, fz_encode_smem_bytes(), st>>>(planes, g, scratch, sizes, status);
+    cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzHistSmem) * FZ_ENC_WARPS));
+    cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
+    cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEmitSmem) * FZ_ENC_WARPS));
+    cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
+    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist);
+    fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
+        ghist, g, (FzGroupCode *)gcodes);
+    fz_emit_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEmitSmem) * FZ_ENC_WARPS, st>>>(planes, g, (const FzGroupCode *)gcodes,
+                                                                                          scratch, sizes, status);
 }
+
+size_t fz_group_code_bytes() { return sizeof(FzGroupCode); }
 
 // =================================================================================================
 // layout: per-stream sums + RAW rule, scan over chunk records, chunk headers
@@ -736,68 +830,137 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
     const uint32_t m = h1 - h0;
     uint32_t mode = 2;
     if (m >= 1 && h1 <= hits_cap && hits[h1 - 1] + 4 == h) {
-        for (int L = 15; L >= 10; L--) {
-            if (((n_s + (1u << L) - 1) >> L) == m) { mode = 1u | ((uint32_t)L << 8); break; }
-        }
+        // our framing: one marker per FZ_SUB-byte sub-block
+        if (((n_s + FZ_SUB - 1) >> FZ_SUB_LOG2) == m) mode = 1u | ((uint32_t)FZ_SUB_LOG2 << 8);
     }
     stream_mode[s] = mode;
 }
 
-// ---- fast path: one THREAD per sub-block fragment
-#define FZ_INF_THREADS 64
-__global__ void __launch_bounds__(FZ_INF_THREADS)
-fz_inflate_fast_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
-                       const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ tile_off,
-                       uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
-                       uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, const FzStatus *status)
+// ---- fast path: one WARP per group of 32 sub-blocks, one THREAD per sub-block fragment.
+// The 32 fragments of a group carry the same Huffman code (our encoder builds one per group), so the warp
+// parses the header once, builds ONE first-level lookup table in shared memory and every lane decodes its
+// own fragment with it.  Lanes verify that their header bits equal the leader's; any mismatch, parse error
+// or size mismatch flags the stream, which is then re-decoded by the general inflater.
+#define FZ_INF_WARPS 4
+struct FzGroupSmem {
+    uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
+    uint16_t lut[FZ_LUT_SIZE];
+};
+
+#define FZ_BCAST_CODE(C, src)                                                                                   \
+    C.p1 = __shfl_sync(0xffffffffu, C.p1, src); C.p2 = __shfl_sync(0xffffffffu, C.p2, src);                     \
+    C.p3 = __shfl_sync(0xffffffffu, C.p3, src); C.p4 = __shfl_sync(0xffffffffu, C.p4, src);                     \
+    C.p5 = __shfl_sync(0xffffffffu, C.p5, src); C.p6 = __shfl_sync(0xffffffffu, C.p6, src);                     \
+    C.p7 = __shfl_sync(0xffffffffu, C.p7, src); C.p8 = __shfl_sync(0xffffffffu, C.p8, src);                     \
+    C.p9 = __shfl_sync(0xffffffffu, C.p9, src); C.p10 = __shfl_sync(0xffffffffu, C.p10, src);                   \
+    C.p11 = __shfl_sync(0xffffffffu, C.p11, src); C.p12 = __shfl_sync(0xffffffffu, C.p12, src);                 \
+    C.p13 = __shfl_sync(0xffffffffu, C.p13, src); C.p14 = __shfl_sync(0xffffffffu, C.p14, src);                 \
+    C.p15 = __shfl_sync(0xffffffffu, C.p15, src);
+
+__global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP)
+fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
+                        const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ tile_off,
+                        uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
+                        uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, const FzStatus *status)
 {
-    __shared__ uint16_t tabs[FZ_INF_TAB_U16 * FZ_INF_THREADS];
+    __shared__ FzGroupSmem smem[FZ_INF_WARPS];
     if (status->error) return;
-    const uint32_t nstreams = g.nchunks * FZ_PLANES;
-    const uint32_t total_hits = tile_off[nstreams * tiles_per_stream];
-    const uint32_t hidx = blockIdx.x * FZ_INF_THREADS + threadIdx.x;
-    if (blockIdx.x * FZ_INF_THREADS >= total_hits) return;  // whole block idle
-    bool valid = hidx < total_hits;
-    uint32_t s = 0, start = 0, end = 0, expect = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gps = fz_groups_per_stream(g);
+    const uint32_t gi = blockIdx.x * FZ_INF_WARPS + warp;
+    if (gi >= g.nchunks * FZ_PLANES * gps) return;  // warp-uniform
+    const uint32_t s = gi / gps, gk = gi - s * gps;
+    if ((stream_mode[s] & 0xffu) != 1u) return;      // warp-uniform
+    const uint32_t h0 = tile_off[s * tiles_per_stream], h1 = tile_off[(s + 1) * tiles_per_stream];
+    const uint32_t m = h1 - h0;                      // sub-blocks in the stream
+    if (gk * FZ_GROUP_SUBS >= m) return;             // warp-uniform
+    FzGroupSmem *sm = &smem[warp];
+    const uint32_t k = gk * FZ_GROUP_SUBS + lane;
+    const bool valid = k < m;
+    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    uint32_t start = 0, end = 0, expect = 0;
     uint8_t *out = nullptr;
     if (valid) {
-        // stream owning this hit: largest s with tile_off[s * tps] <= hidx
-        uint32_t lo = 0, hi = nstreams;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (tile_off[mid * tiles_per_stream] <= hidx) lo = mid; else hi = mid;
-        }
-        s = lo;
-        const uint32_t mode = stream_mode[s];
-        valid = (mode & 0xffu) == 1u;
-        if (valid) {
-            const uint32_t L = mode >> 8;
-            const uint32_t k = hidx - tile_off[s * tiles_per_stream];
-            start = k ? hits[hidx - 1] + 4 : 0u;
-            end = hits[hidx] + 4;
-            const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
-            const uint32_t obeg = k << L;
-            expect = min(1u << L, n_s - obeg);
-            out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
-        }
+        start = k ? hits[h0 + k - 1] + 4 : 0u;
+        end = hits[h0 + k] + 4;
+        const uint32_t obeg = k << FZ_SUB_LOG2;
+        expect = min((uint32_t)FZ_SUB, n_s - obeg);
+        out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
     }
-    typedef FzInfTab<FZ_INF_THREADS> Tab;
-    Tab tab{tabs + threadIdx.x, tabs + 288 * FZ_INF_THREADS + threadIdx.x, tabs + 320 * FZ_INF_THREADS + threadIdx.x};
+    const uint8_t *frag = container + stream_off[s] + start;
+    const uint32_t flen = end - start;
+
+    typedef FzInfTab<1> Tab;
+    Tab tab{sm->tab, sm->tab + 288, sm->tab + 320};
     FzInflater<Tab> inf;
-    bool live = false;
-    if (valid) {
-        inf.start(container + stream_off[s] + start, (size_t)(end - start), out, expect, tab);
-        live = true;
+    bool live = false, bad = false;
+    if (valid) { inf.start(frag, flen, out, expect, tab); inf.shared_tab = true; live = true; }
+
+    // block type of every lane's first block: 2 (dynamic) lanes share the leader's code
+    uint32_t first3 = 7;
+    if (valid && flen >= 1) first3 = frag[0] & 7u;   // BFINAL (must be 0) | BTYPE << 1
+    const bool coded = valid && first3 == 4u;        // BFINAL = 0, BTYPE = 10
+    const uint32_t coded_mask = __ballot_sync(0xffffffffu, coded);
+    uint32_t hdr_bits = 0;
+    if (coded_mask) {
+        const int leader = __ffs((int)coded_mask) - 1;
+        if (lane == leader) {
+            inf.shared_tab = false;
+            const bool okh = inf.block_header();     // parses the header, fills sm->tab, LL / DD in registers
+            inf.shared_tab = true;
+            if (!okh || !inf.in_body) { bad = true; live = false; }
+            hdr_bits = (uint32_t)((int64_t)flen * 8 - inf.br.bits_left);
+        }
+        __syncwarp();
+        const uint32_t leader_ok = __shfl_sync(0xffffffffu, (uint32_t)(!bad), leader);
+        hdr_bits = __shfl_sync(0xffffffffu, hdr_bits, leader);
+        FZ_BCAST_CODE(inf.LL, leader)
+        FZ_BCAST_CODE(inf.DD, leader)
+        if (!leader_ok) {
+            if (coded) { bad = true; live = false; }
+        } else {
+            // every other coded lane: its first hdr_bits must equal the leader's, then skip them
+            const unsigned long long lfrag = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)frag, leader);
+            if (coded && lane != leader) {
+                const uint8_t *lf = (const uint8_t *)(uintptr_t)lfrag;
+                const uint32_t nby = hdr_bits >> 3, rem = hdr_bits & 7u;
+                bool same = (uint64_t)flen * 8 > hdr_bits;
+                if (same) {
+                    for (uint32_t i = 0; i < nby; i++) same &= frag[i] == lf[i];
+                    if (rem) same &= ((frag[nby] ^ lf[nby]) & ((1u << rem) - 1u)) == 0;
+                }
+                if (!same) { bad = true; live = false; }
+                else {
+                    inf.br.init(frag + nby, flen - nby);
+                    inf.br.refill();
+                    inf.br.drop((int)rem);
+                    inf.in_body = true;
+                    inf.last = false;
+                }
+            }
+            // first-level table: entry e = the symbol whose code is a prefix of the bit pattern e
+            for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) {
+                uint32_t idx;
+                const int l = fz_decode_idx(inf.LL, e, idx);
+                uint16_t v = 0;
+                if (l >= 1 && l <= FZ_LUT_BITS && idx < 288) v = (uint16_t)(sm->tab[idx] | (l << 9));
+                sm->lut[e] = v;
+            }
+        }
+        __syncwarp();
     }
-    // lock-step drive: the 32 lanes decode 32 different sub-blocks and reconverge after every symbol
+    // lock-step drive: lanes reconverge after every symbol
+    const uint16_t *lut = coded_mask ? sm->lut : nullptr;
     while (__any_sync(0xffffffffu, live)) {
-        if (live) live = inf.step();
+        if (live) live = inf.step_lut(lut);
     }
     if (valid) {
         uint32_t out_n = 0;
         size_t used = 0;
         const int rc = inf.finish(&out_n, &used);
-        if (rc != FZ_INF_OK || out_n != expect || used != (size_t)(end - start)) atomicExch(&stream_fail[s], 1u);
+        // `used` is relative to the (possibly re-based) reader: recompute the absolute end
+        const int64_t left = inf.br.bits_left;
+        if (bad || rc != FZ_INF_OK || out_n != expect || left != 0) atomicExch(&stream_fail[s], 1u);
     }
 }
 
@@ -857,9 +1020,8 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     if (mark) mark(mark_user, FZ_ST_MARKERS);
     fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, status);
     if (mark) mark(mark_user, FZ_ST_CLASSIFY);
-    // the hit count lives on the device; launch for the capacity and let surplus threads exit
-    const uint32_t max_hits = b.hits_cap;
-    fz_inflate_fast_kernel<<<(max_hits + FZ_INF_THREADS - 1) / FZ_INF_THREADS, FZ_INF_THREADS, 0, st>>>(
+    const uint32_t ngroups = nstreams * ((g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
+    fz_inflate_group_kernel<<<(ngroups + FZ_INF_WARPS - 1) / FZ_INF_WARPS, FZ_INF_WARPS * FZ_WARP, 0, st>>>(
         container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, planes, status);

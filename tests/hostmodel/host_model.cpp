@@ -19,51 +19,77 @@ struct HostLoadByte {
     const uint8_t *p;
     uint32_t operator()(uint32_t i) const { return p[i]; }
 };
+
+// what the gather kernel synthesises for a stored sub-block: stored block + empty stored block
+size_t put_stored(uint8_t *o, const uint8_t *in, uint32_t n)
+{
+    uint8_t *b = o;
+    *o++ = 0x00;
+    *o++ = (uint8_t)(n & 0xff); *o++ = (uint8_t)(n >> 8);
+    *o++ = (uint8_t)(~n & 0xff); *o++ = (uint8_t)((~n >> 8) & 0xff);
+    memcpy(o, in, n); o += n;
+    *o++ = 0x00; *o++ = 0x00; *o++ = 0x00; *o++ = 0xFF; *o++ = 0xFF;
+    return (size_t)(o - b);
+}
 }  // namespace
 
 extern "C" {
 
-// one sub-block (n <= FZ_SUB) -> complete fragment in out (cap >= n + 64); returns bytes; *stored = 1 if stored form
-uint32_t hm_encode_subblock(const uint8_t *in, uint32_t n, uint8_t *out, int *stored)
-{
-    std::vector<uint8_t> pad(n + 32, 0);
-    memcpy(pad.data(), in, n);
-    std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8, 0xDEADBEEFu);  // garbage: the encoder must write every word it owns
-    FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
-    memset(st, 0xCD, sizeof(FzEncState));
-    HostLoad16 ld{pad.data()};
-    HostLoadByte lb{pad.data()};
-    uint32_t r = fz_encode_subblock(st, ld, lb, n, slot.data(), 0);
-    free(st);
-    if (r & FZ_SIZE_STORED_FLAG) {
-        // what the gather kernel synthesises: stored block + empty stored block
-        uint8_t *o = out;
-        *o++ = 0x00;
-        *o++ = (uint8_t)(n & 0xff); *o++ = (uint8_t)(n >> 8);
-        *o++ = (uint8_t)(~n & 0xff); *o++ = (uint8_t)((~n >> 8) & 0xff);
-        memcpy(o, in, n); o += n;
-        *o++ = 0x00; *o++ = 0x00; *o++ = 0x00; *o++ = 0xFF; *o++ = 0xFF;
-        *stored = 1;
-        return (uint32_t)(o - out);
-    }
-    memcpy(out, slot.data(), r);
-    *stored = 0;
-    return r;
-}
-
-// a whole plane stream (any n) as the concatenation of its sub-blocks
+// a whole plane stream (any n): groups of FZ_GROUP_SUBS sub-blocks share one code, exactly like the
+// three GPU kernels (histogram, group code, emit) do it
 uint64_t hm_encode_stream(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint32_t sub, uint64_t *nstored)
 {
     uint64_t o = 0, ns = 0;
-    std::vector<uint8_t> tmp(FZ_SUB + 64);
-    for (uint64_t p = 0; p < n; p += sub) {
-        uint32_t m = (uint32_t)((n - p) < sub ? (n - p) : sub);
-        int stored = 0;
-        uint32_t r = hm_encode_subblock(in + p, m, tmp.data(), &stored);
-        if (o + r > cap) return (uint64_t)-1;
-        memcpy(out + o, tmp.data(), r);
-        o += r; ns += (uint64_t)stored;
+    if (sub != FZ_SUB) return (uint64_t)-1;
+    std::vector<uint8_t> pad(FZ_SUB + 32);
+    std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8);
+    FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
+    FzGroupCode *gc = (FzGroupCode *)malloc(sizeof(FzGroupCode));
+    FzEmitState *es = (FzEmitState *)malloc(sizeof(FzEmitState));
+    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
+    for (uint64_t g0 = 0; g0 < n; g0 += gbytes) {
+        const uint64_t gn = (n - g0) < gbytes ? (n - g0) : gbytes;
+        const uint32_t nsub = (uint32_t)((gn + FZ_SUB - 1) / FZ_SUB);
+        memset(st, 0xCD, sizeof(FzEncState));
+        memset(st->hist, 0, sizeof(st->hist));
+        // stage 1: histogram of the group's tokens
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
+            memset(pad.data(), 0, pad.size());
+            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
+            HostLoad16 ld{pad.data()};
+            HostLoadByte lb{pad.data()};
+            uint32_t h[288];
+            memset(h, 0, sizeof(h));
+            for (int lane = 0; lane < 32; lane++) fz_ph_hist(h, ld, lb, m, lane);
+            for (int i = 0; i < 288; i++) st->hist[i] += h[i];
+        }
+        st->hist[FZ_EOB] = nsub;
+        // stage 2: one code + header for the group
+        memset(gc, 0xEE, sizeof(FzGroupCode));
+        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0);
+        // stage 3: emit every sub-block with it
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
+            memset(pad.data(), 0, pad.size());
+            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
+            HostLoad16 ld{pad.data()};
+            HostLoadByte lb{pad.data()};
+            for (auto &w : slot) w = 0xDEADBEEFu;  // garbage: the encoder must write every word it owns
+            memset(es, 0xAB, sizeof(FzEmitState));
+            const uint32_t r = fz_emit_subblock(gc, es, ld, lb, m, slot.data(), 0);
+            if (r & FZ_SIZE_STORED_FLAG) {
+                if (o + m + FZ_STORED_OVERHEAD > cap) return (uint64_t)-1;
+                o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
+                ns++;
+            } else {
+                if (o + r > cap) return (uint64_t)-1;
+                memcpy(out + o, slot.data(), r);
+                o += r;
+            }
+        }
     }
+    free(st); free(gc); free(es);
     if (nstored) *nstored = ns;
     return o;
 }
@@ -73,7 +99,6 @@ int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_ca
     // word-aligned, padded copies (the device reads whole aligned words; out must be 4-byte aligned)
     std::vector<uint32_t> ibuf((in_len + 16) / 4 + 1, 0);
     std::vector<uint32_t> obuf(out_cap / 4 + 2, 0);
-    for (int mis = 0; mis < 1; mis++) {}
     uint8_t *ip = (uint8_t *)ibuf.data() + 1;  // deliberately misaligned input
     memcpy(ip, in, in_len);
     uint16_t ll[288], dd[32], cnt[32];
@@ -86,6 +111,7 @@ int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_ca
 }
 
 uint32_t hm_sub_bytes(void) { return FZ_SUB; }
+uint32_t hm_group_subs(void) { return FZ_GROUP_SUBS; }
 uint32_t hm_enc_state_bytes(void) { return (uint32_t)sizeof(FzEncState); }
 
 }  // extern "C"

@@ -6,8 +6,6 @@ import numpy as np
 from . import build as _build
 
 _L = C.CDLL(str(_build.build()))
-_L.hm_encode_subblock.restype = C.c_uint32
-_L.hm_encode_subblock.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_int)]
 _L.hm_encode_stream.restype = C.c_uint64
 _L.hm_encode_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
 _L.hm_inflate.restype = C.c_int
