@@ -77,6 +77,25 @@ FZ_HD void fz_scan_piece(const Load16 &ld, uint32_t begin, uint32_t end, int pre
     for (uint32_t i = begin; i < end; i += 16) {
         const FzVec16 v = ld(i);
         const uint32_t lim = end - i;
+        if (lim >= 16 && m == 0) {
+            // Fast path for a whole 16-byte group: bit k of eq = byte k equals its predecessor.  Byte k is
+            // withheld iff eq_k & eq_{k-1} & eq_{k-2} (third repeat in a row); bits below 0 come from `rep`.
+            uint32_t eq = 0;
+            int p = prev;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int c = (int)((v.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+                eq |= (uint32_t)(c == p) << (k + 2);
+                p = c;
+            }
+            const uint32_t ext = eq | (rep >= 1 ? 2u : 0u) | (rep >= 2 ? 1u : 0u);
+            if ((ext & (ext << 1) & (ext << 2)) == 0) {
+                sink.literal16(v);
+                rep = (eq >> 17) & 1u ? (((eq >> 16) & 1u) ? 2u : 1u) : 0u;
+                prev = p;
+                continue;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             if ((uint32_t)k < lim) {
@@ -110,9 +129,16 @@ FZ_HD void fz_atomic_add(uint32_t *p, uint32_t v)
 #endif
 }
 
+#define FZ_BYTE_OF(v, k) (((v).w[(k) >> 2] >> (((k) & 3) * 8)) & 0xffu)
+
 struct FzHistSink {
     uint32_t *hist;  // 288 counters (shared memory on the GPU)
     FZ_HD void literal(uint32_t c, uint32_t n) { fz_atomic_add(&hist[c], n); }
+    FZ_HD void literal16(const FzVec16 &v)
+    {
+#pragma unroll
+        for (int k = 0; k < 16; k++) fz_atomic_add(&hist[FZ_BYTE_OF(v, k)], 1);
+    }
     FZ_HD void match(uint32_t len)
     {
         uint32_t lc, eb, ev;
@@ -121,15 +147,23 @@ struct FzHistSink {
     }
 };
 
+// cl[sym] = bit-reversed code | code length << 16
 struct FzCountSink {
-    const uint8_t *len;
+    const uint32_t *cl;
     uint32_t bits;
-    FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * len[c]; }
+    FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * (cl[c] >> 16); }
+    FZ_HD void literal16(const FzVec16 &v)
+    {
+        uint32_t b = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) b += cl[FZ_BYTE_OF(v, k)] >> 16;
+        bits += b;
+    }
     FZ_HD void match(uint32_t mlen)
     {
         uint32_t lc, eb, ev;
         fz_len_code(mlen, lc, eb, ev);
-        bits += len[257 + lc] + eb + 1;  // + 1-bit distance code
+        bits += (cl[257 + lc] >> 16) + eb + 1;  // + 1-bit distance code
     }
 };
 
@@ -162,19 +196,27 @@ struct FzBitWriter {
 };
 
 struct FzEmitSink {
-    const uint16_t *code;
-    const uint8_t *len;
+    const uint32_t *cl;
     FzBitWriter bw;
     FZ_HD void literal(uint32_t c, uint32_t n)
     {
-        const uint32_t cd = code[c], l = len[c];
-        for (uint32_t i = 0; i < n; i++) bw.put(cd, l);
+        const uint32_t e = cl[c];
+        for (uint32_t i = 0; i < n; i++) bw.put(e & 0xffffu, e >> 16);
+    }
+    FZ_HD void literal16(const FzVec16 &v)
+    {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t e = cl[FZ_BYTE_OF(v, k)];
+            bw.put(e & 0xffffu, e >> 16);
+        }
     }
     FZ_HD void match(uint32_t mlen)
     {
         uint32_t lc, eb, ev;
         fz_len_code(mlen, lc, eb, ev);
-        bw.put(code[257 + lc], len[257 + lc]);
+        const uint32_t e = cl[257 + lc];
+        bw.put(e & 0xffffu, e >> 16);
         bw.put(ev, eb + 1);  // extra bits, then the 1-bit distance code '0' (distance 1)
     }
 };
@@ -479,13 +521,15 @@ FZ_HD void fz_ph_hist(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint
 
 // The code of a group as the emit kernel consumes it (global memory, copied to shared memory per warp)
 struct FzGroupCode {
-    uint16_t code[288];   // bit-reversed canonical codes
-    uint8_t len[288];
-    uint32_t hdr[160];    // bit-packed dynamic block header (BFINAL=0, BTYPE=10, lengths)
+    // hot part (copied to shared memory by every emitting warp): FZ_GROUP_CODE_HOT_BYTES
+    uint32_t cl[288];     // bit-reversed canonical code | code length << 16
     uint32_t hdr_nbits;
     uint32_t stored;      // 1: coding this group cannot beat stored blocks -- emit every sub-block stored
     uint32_t pad[2];
+    // cold part (read by lane 0 only)
+    uint32_t hdr[160];    // bit-packed dynamic block header (BFINAL=0, BTYPE=10, lengths)
 };
+#define FZ_GROUP_CODE_HOT_BYTES (288 * 4 + 16)
 
 // Build the group's Huffman code and block header from its token histogram.
 //   st->hist[0..287] = token frequencies of the whole group, st->hist[256] = number of sub-blocks (EOBs)
@@ -519,12 +563,12 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
     const uint64_t stored_bits = 8ull * ((uint64_t)group_bytes + (uint64_t)FZ_STORED_OVERHEAD * nsub);
     const uint32_t stored = bits >= stored_bits ? 1u : 0u;
 #if defined(__CUDA_ARCH__)
-    for (int i = lane; i < 288; i += 32) { out->code[i] = st->code[i]; out->len[i] = st->len[i]; }
+    for (int i = lane; i < 288; i += 32) out->cl[i] = (uint32_t)st->code[i] | ((uint32_t)st->len[i] << 16);
     for (int i = lane; i < 160; i += 32) out->hdr[i] = st->hdr[i];
     if (lane == 0) { out->hdr_nbits = st->hdr_nbits; out->stored = stored; }
     __syncwarp();
 #else
-    for (int i = 0; i < 288; i++) { out->code[i] = st->code[i]; out->len[i] = st->len[i]; }
+    for (int i = 0; i < 288; i++) out->cl[i] = (uint32_t)st->code[i] | ((uint32_t)st->len[i] << 16);
     for (int i = 0; i < 160; i++) out->hdr[i] = st->hdr[i];
     out->hdr_nbits = st->hdr_nbits; out->stored = stored;
 #endif
@@ -544,7 +588,7 @@ FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld,
     const uint32_t P = fz_piece_len(n);
     uint32_t b = lane * P, e = b + P;
     if (e > n) e = n;
-    FzCountSink sink{gc->len, 0};
+    FzCountSink sink{gc->cl, 0};
     if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
     if (lane == 0) sink.bits += gc->hdr_nbits;
     es->lane_bits[lane] = sink.bits;
@@ -553,8 +597,8 @@ FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld,
 // emit this lane's tokens at its bit offset; lane 0 prepends the block header, lane 31 appends
 // EOB + the empty stored block (000, pad to byte, 00 00 FF FF)
 template <class Load16, class LoadByte>
-FZ_HD void fz_ph_emit(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, const LoadByte &lb, uint32_t n,
-                      uint32_t *out, int lane)
+FZ_HD void fz_ph_emit(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Load16 &ld, const LoadByte &lb,
+                      uint32_t n, uint32_t *out, int lane)
 {
     uint32_t off = 0;
     for (int l = 0; l < lane; l++) off += es->lane_bits[l];
@@ -562,17 +606,16 @@ FZ_HD void fz_ph_emit(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, 
     uint32_t b = lane * P, e = b + P;
     if (e > n) e = n;
     FzEmitSink sink;
-    sink.code = gc->code;
-    sink.len = gc->len;
+    sink.cl = gc->cl;
     sink.bw.init(out, off);
     if (lane == 0) {
         uint32_t nb = gc->hdr_nbits, w = 0;
-        while (nb >= 32) { sink.bw.put(gc->hdr[w++], 32); nb -= 32; }
-        if (nb) sink.bw.put(gc->hdr[w] & ((1u << nb) - 1), nb);
+        while (nb >= 32) { sink.bw.put(hdr[w++], 32); nb -= 32; }
+        if (nb) sink.bw.put(hdr[w] & ((1u << nb) - 1), nb);
     }
     if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
     if (lane == 31) {
-        sink.bw.put(gc->code[FZ_EOB], gc->len[FZ_EOB]);
+        sink.bw.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
         sink.bw.put(0, 3);
         sink.bw.align_byte();
         sink.bw.put(0x0000u, 16);
@@ -608,19 +651,20 @@ FZ_HD void fz_ph_merge(FzEmitState *es, uint32_t *out, int lane)
 // `out` needs room for FZ_SLOT_STRIDE bytes.
 // -------------------------------------------------------------------------------------------------
 template <class Load16, class LoadByte>
-FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, const LoadByte &lb, uint32_t n,
-                                uint32_t *out, int lane)
+// `gc` needs only the hot part of FzGroupCode (FZ_GROUP_CODE_HOT_BYTES); `hdr` points at the group's header words.
+FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Load16 &ld,
+                                const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
 {
     (void)lane;
     const uint32_t stored = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG;
     if (gc->stored) return stored;
     FZ_PHASE(fz_ph_count(gc, es, ld, lb, n, lane));
-    uint32_t bits = gc->len[FZ_EOB];
+    uint32_t bits = gc->cl[FZ_EOB] >> 16;
     for (int l = 0; l < 32; l++) bits += es->lane_bits[l];
     // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
     const uint32_t dyn_bytes = (bits + 3 + 7) / 8 + 4;
     if (dyn_bytes >= n + FZ_STORED_OVERHEAD) return stored;
-    FZ_PHASE(fz_ph_emit(gc, es, ld, lb, n, out, lane));
+    FZ_PHASE(fz_ph_emit(gc, hdr, es, ld, lb, n, out, lane));
     FZ_PHASE(fz_ph_merge(es, out, lane));
     return es->total_bits / 8;
 }

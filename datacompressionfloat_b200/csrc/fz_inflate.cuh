@@ -27,34 +27,38 @@ struct FzInfTab {
 #define FZ_INF_TAB_U16 (288 + 32 + 32)  // uint16 entries per decoding thread
 
 struct FzBitReader {
-    const uint32_t *w;   // aligned word pointer
+    const uint32_t *w;     // next aligned word to load (may run past wend: zero bits are fed then)
+    const uint32_t *wend;  // one past the last word that holds input bytes
     uint64_t acc;
-    int nacc;            // valid bits in acc
-    int64_t nwords;      // words that may still be loaded
-    int64_t bits_left;   // bits of real input not yet consumed (goes negative on overrun)
+    int nacc;              // valid bits in acc
+    int tail_pad;          // bits of the last word that lie beyond the end of the input
     FZ_HD void init(const uint8_t *in, size_t in_len)
     {
         const uintptr_t a = (uintptr_t)in;
         const unsigned sk = (unsigned)(a & 3);
         w = (const uint32_t *)(a - sk);
-        nwords = (int64_t)((in_len + sk + 3) / 4);
-        bits_left = (int64_t)in_len * 8;
+        const size_t nw = (in_len + sk + 3) / 4;
+        wend = w + nw;
+        tail_pad = (int)(nw * 32 - 8 * sk - in_len * 8);
         acc = 0; nacc = 0;
-        if (nwords > 0) { acc = (uint64_t)(*w++ >> (8 * sk)); nacc = 32 - 8 * (int)sk; nwords--; }
+        if (nw > 0) { acc = (uint64_t)(*w++ >> (8 * sk)); nacc = 32 - 8 * (int)sk; }
+        else tail_pad = 0;
     }
+    // bits of real input not yet consumed (negative after an overrun); derived, not tracked per symbol
+    FZ_HD int64_t bits_left() const { return (int64_t)(wend - w) * 32 + nacc - tail_pad; }
     FZ_HD void refill()  // guarantees nacc >= 32 (zero bits past the end of the input)
     {
         if (nacc < 32) {
-            uint32_t v = 0;
-            if (nwords > 0) { v = *w++; nwords--; }
+            const uint32_t v = (w < wend) ? *w : 0u;
+            w++;
             acc |= (uint64_t)v << nacc;
             nacc += 32;
         }
     }
     FZ_HD uint32_t peek(int n) const { return (uint32_t)acc & ((1u << n) - 1); }
-    FZ_HD void drop(int n) { acc >>= n; nacc -= n; bits_left -= n; }
+    FZ_HD void drop(int n) { acc >>= n; nacc -= n; }
     FZ_HD uint32_t get(int n) { const uint32_t v = peek(n); drop(n); return v; }  // n <= 16, after refill
-    FZ_HD void align_byte() { const int k = (int)(bits_left & 7); drop(k); }
+    FZ_HD void align_byte() { const int k = (int)(bits_left() & 7); drop(k); }
 };
 
 struct FzByteWriter {
@@ -205,9 +209,9 @@ struct FzInflater {
     FZ_HD int finish(uint32_t *out_n, size_t *in_used)
     {
         bw.finish();
-        if (rc == FZ_INF_OK && br.bits_left < 0) rc = FZ_INF_E_INPUT;
+        if (rc == FZ_INF_OK && br.bits_left() < 0) rc = FZ_INF_E_INPUT;
         *out_n = bw.op;
-        const int64_t used_bits = (int64_t)in_len * 8 - br.bits_left;
+        const int64_t used_bits = (int64_t)in_len * 8 - br.bits_left();
         *in_used = (size_t)((used_bits + 7) / 8);
         return rc;
     }
@@ -217,7 +221,6 @@ struct FzInflater {
     FZ_HD bool body_symbol(const uint16_t *lut)
     {
         br.refill();
-        if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
         uint32_t idx, sym;
         int l;
         const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
@@ -237,7 +240,7 @@ struct FzInflater {
         }
         if (sym == FZ_EOB) {
             in_body = false;
-            if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
+            if (br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
             return !last;
         }
         sym -= 257;
@@ -263,8 +266,8 @@ struct FzInflater {
 
     FZ_HD bool block_header()
     {
-        if (br.bits_left < 3) return false;                       // nothing but padding left
-        if (bw.op == bw.cap && br.bits_left < 8) return false;    // full output, only pad bits left
+        if (br.bits_left() < 3) return false;                       // nothing but padding left
+        if (bw.op == bw.cap && br.bits_left() < 8) return false;    // full output, only pad bits left
         br.refill();
         last = br.get(1) != 0;
         const uint32_t type = br.get(2);
@@ -275,7 +278,7 @@ struct FzInflater {
             br.refill();
             const uint32_t nlen = br.get(16);
             if ((len ^ 0xFFFFu) != nlen) return fail(FZ_INF_E_DATA);
-            if (br.bits_left < (int64_t)len * 8) return fail(FZ_INF_E_INPUT);
+            if (br.bits_left() < (int64_t)len * 8) return fail(FZ_INF_E_INPUT);
             if (bw.op + len > bw.cap) return fail(FZ_INF_E_SPACE);
             for (uint32_t i = 0; i < len; i++) { br.refill(); bw.put(br.get(8)); }
             return !last;
@@ -369,7 +372,7 @@ struct FzInflater {
                     }
                 }
             }
-            if (br.bits_left < 0) return fail(FZ_INF_E_INPUT);
+            if (br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
         }
         in_body = true;
         return true;

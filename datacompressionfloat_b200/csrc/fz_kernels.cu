@@ -399,7 +399,7 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
 
 struct __align__(16) FzEmitSmem {
     alignas(16) uint8_t stage[FZ_STAGE_BYTES];
-    FzGroupCode gc;
+    uint32_t gc_hot[FZ_GROUP_CODE_HOT_BYTES / 4];  // the hot part of the group's FzGroupCode
     FzEmitState es;
 };
 
@@ -419,17 +419,16 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
         return;
     }
     FzEmitSmem *sm = (FzEmitSmem *)fz_smem + warp;
-    {   // group code -> shared memory (word copy)
+    {   // code table of the group -> shared memory (word copy of the hot part)
         const uint32_t *src = (const uint32_t *)ggc;
-        uint32_t *dst = (uint32_t *)&sm->gc;
-        for (uint32_t i = lane; i < sizeof(FzGroupCode) / 4; i += 32) dst[i] = src[i];
+        for (uint32_t i = lane; i < FZ_GROUP_CODE_HOT_BYTES / 4; i += 32) sm->gc_hot[i] = src[i];
     }
     const uint32_t P = fz_piece_len(n);
     fz_stage(sm->stage, fz_sub_src(planes, g, s, k), n, P, lane);
     DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
     DevLoadByte lb{sm->stage, P};
     uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
-    const uint32_t r = fz_emit_subblock(&sm->gc, &sm->es, ld, lb, n, out, lane);
+    const uint32_t r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, ld, lb, n, out, lane);
     if (lane == 0) {
         sizes[t] = r;
         if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
@@ -909,7 +908,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
             const bool okh = inf.block_header();     // parses the header, fills sm->tab, LL / DD in registers
             inf.shared_tab = true;
             if (!okh || !inf.in_body) { bad = true; live = false; }
-            hdr_bits = (uint32_t)((int64_t)flen * 8 - inf.br.bits_left);
+            hdr_bits = (uint32_t)((int64_t)flen * 8 - inf.br.bits_left());
         }
         __syncwarp();
         const uint32_t leader_ok = __shfl_sync(0xffffffffu, (uint32_t)(!bad), leader);
@@ -952,14 +951,28 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     // lock-step drive: lanes reconverge after every symbol
     const uint16_t *lut = coded_mask ? sm->lut : nullptr;
     while (__any_sync(0xffffffffu, live)) {
-        if (live) live = inf.step_lut(lut);
+        if (live) {
+            if (inf.in_body && lut) {
+                // fast run: up to 16 table-hit literals without leaving registers or re-voting
+#pragma unroll 1
+                for (int it = 0; it < 16; ++it) {
+                    inf.br.refill();
+                    const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
+                    const uint32_t sym = e & 511u;
+                    if (e == 0 || sym >= 256u || inf.bw.op >= inf.bw.cap) break;
+                    inf.br.drop((int)(e >> 9));
+                    inf.bw.put(sym);
+                }
+            }
+            live = inf.step_lut(lut);  // whatever comes next: long code, match, end of block, block header
+        }
     }
     if (valid) {
         uint32_t out_n = 0;
         size_t used = 0;
         const int rc = inf.finish(&out_n, &used);
         // `used` is relative to the (possibly re-based) reader: recompute the absolute end
-        const int64_t left = inf.br.bits_left;
+        const int64_t left = inf.br.bits_left();
         if (bad || rc != FZ_INF_OK || out_n != expect || left != 0) atomicExch(&stream_fail[s], 1u);
     }
 }

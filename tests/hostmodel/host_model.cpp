@@ -77,7 +77,7 @@ uint64_t hm_encode_stream(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t 
             HostLoadByte lb{pad.data()};
             for (auto &w : slot) w = 0xDEADBEEFu;  // garbage: the encoder must write every word it owns
             memset(es, 0xAB, sizeof(FzEmitState));
-            const uint32_t r = fz_emit_subblock(gc, es, ld, lb, m, slot.data(), 0);
+            const uint32_t r = fz_emit_subblock(gc, gc->hdr, es, ld, lb, m, slot.data(), 0);
             if (r & FZ_SIZE_STORED_FLAG) {
                 if (o + m + FZ_STORED_OVERHEAD > cap) return (uint64_t)-1;
                 o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
