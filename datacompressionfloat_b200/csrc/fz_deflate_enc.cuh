@@ -68,18 +68,18 @@ struct FzEncState {
 // path of this loop free of data-dependent branches, which matters when 32 lanes scan 32 pieces.)
 // `prev_init` < 0 means "no byte before `begin`" (sub-block start: sub-blocks never reference earlier data).
 // -------------------------------------------------------------------------------------------------
-template <class Load16, class Sink>
-FZ_HD void fz_scan_piece(const Load16 &ld, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
+template <class Load16, class LoadByte, class Sink>
+FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
 {
     int prev = prev_init;
     uint32_t rep = 0;  // repeats of `prev` seen so far in this run (saturates at 2)
     uint32_t m = 0;    // withheld bytes
     for (uint32_t i = begin; i < end; i += 16) {
-        const FzVec16 v = ld(i);
         const uint32_t lim = end - i;
-        if (lim >= 16 && m == 0) {
-            // Fast path for a whole 16-byte group: bit k of eq = byte k equals its predecessor.  Byte k is
-            // withheld iff eq_k & eq_{k-1} & eq_{k-2} (third repeat in a row); bits below 0 come from `rep`.
+        if (lim >= 16) {
+            // Whole 16-byte group at once.  Bit k+2 of eq = byte k equals its predecessor; bits 1, 0 = the same
+            // for the two bytes before the group (from `rep`).  Byte k is withheld iff eq_k & eq_{k-1} & eq_{k-2}.
+            const FzVec16 v = ld(i);
             uint32_t eq = 0;
             int p = prev;
 #pragma unroll
@@ -89,29 +89,34 @@ FZ_HD void fz_scan_piece(const Load16 &ld, uint32_t begin, uint32_t end, int pre
                 p = c;
             }
             const uint32_t ext = eq | (rep >= 1 ? 2u : 0u) | (rep >= 2 ? 1u : 0u);
-            if ((ext & (ext << 1) & (ext << 2)) == 0) {
+            const uint32_t held = (ext & (ext << 1) & (ext << 2)) >> 2;  // 16 bits
+            if (held == 0 && m == 0) {          // (A) sixteen literals
                 sink.literal16(v);
                 rep = (eq >> 17) & 1u ? (((eq >> 16) & 1u) ? 2u : 1u) : 0u;
                 prev = p;
                 continue;
             }
+            if (held == 0xffffu) {               // (B) the whole group continues a run that is already being withheld
+                m += 16;
+                if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
+                continue;                        // prev unchanged, rep stays 2
+            }
         }
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if ((uint32_t)k < lim) {
-                const int c = (int)((v.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
-                const bool eq = c == prev;
-                if (eq && rep >= 2) {
-                    if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
-                } else {
-                    if (m) {
-                        if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-                        m = 0;
-                    }
-                    rep = eq ? rep + 1 : 0;
-                    prev = c;
-                    sink.literal((uint32_t)c, 1);
+        // (C) a run starts or ends inside the group, or the ragged tail: byte by byte (rolled: keeps the code small)
+        const uint32_t cnt = lim < 16 ? lim : 16;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const int c = (int)lb(i + k);
+            const bool e = c == prev;
+            if (e && rep >= 2) {
+                if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
+            } else {
+                if (m) {
+                    if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
+                    m = 0;
                 }
+                rep = e ? rep + 1 : 0;
+                prev = c;
+                sink.literal((uint32_t)c, 1);
             }
         }
     }
@@ -516,7 +521,7 @@ FZ_HD void fz_ph_hist(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint
     if (e > n) e = n;
     if (b >= e) return;
     FzHistSink sink{hist};
-    fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
 }
 
 // The code of a group as the emit kernel consumes it (global memory, copied to shared memory per warp)
@@ -589,7 +594,7 @@ FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld,
     uint32_t b = lane * P, e = b + P;
     if (e > n) e = n;
     FzCountSink sink{gc->cl, 0};
-    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
     if (lane == 0) sink.bits += gc->hdr_nbits;
     es->lane_bits[lane] = sink.bits;
 }
@@ -613,7 +618,7 @@ FZ_HD void fz_ph_emit(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *e
         while (nb >= 32) { sink.bw.put(hdr[w++], 32); nb -= 32; }
         if (nb) sink.bw.put(hdr[w] & ((1u << nb) - 1), nb);
     }
-    if (b < e) fz_scan_piece(ld, b, e, b ? (int)lb(b - 1) : -1, sink);
+    if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
     if (lane == 31) {
         sink.bw.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
         sink.bw.put(0, 3);
