@@ -61,45 +61,57 @@ struct FzEncState {
 
 // -------------------------------------------------------------------------------------------------
 // Run tokeniser (distance-1 matches only, the reference's Z_RLE strategy).  A byte equal to its
-// predecessor is a "repeat".  The first two repeats of a run are emitted as literals right away; from
-// the third repeat on bytes are withheld and leave as one match (3..258) when the run ends or 258 are
-// pending -- or as 1-2 literals if fewer than 3 were withheld.  (zlib withholds from the first repeat;
-// emitting two literals first costs nothing on short runs of frequent symbols and keeps the common
-// path of this loop free of data-dependent branches, which matters when 32 lanes scan 32 pieces.)
+// predecessor is a "repeat".  The first FZ_HOLD_AFTER repeats of a run are emitted as literals right
+// away; from the next repeat on bytes are withheld and leave as one match (3..258) when the run ends
+// or 258 are pending -- or as 1-2 literals if fewer than 3 were withheld.  (zlib withholds from the
+// first repeat.  Short runs of a frequent symbol cost about the same either way; starting late keeps
+// "a run starts inside this 16-byte group" rare -- with 32 lanes scanning 32 pieces in lock step that
+// event is what serialises the warp: at FZ_HOLD_AFTER = 2 it hit 13 % of the groups of a float
+// exponent plane, i.e. nearly every warp iteration; at 6 it is 0.02 %.)
 // `prev_init` < 0 means "no byte before `begin`" (sub-block start: sub-blocks never reference earlier data).
 // -------------------------------------------------------------------------------------------------
+#define FZ_HOLD_AFTER 6
+
 template <class Load16, class LoadByte, class Sink>
 FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
 {
     int prev = prev_init;
-    uint32_t rep = 0;  // repeats of `prev` seen so far in this run (saturates at 2)
+    uint32_t rep = 0;  // repeats of `prev` seen so far in this run (saturates at FZ_HOLD_AFTER)
     uint32_t m = 0;    // withheld bytes
     for (uint32_t i = begin; i < end; i += 16) {
         const uint32_t lim = end - i;
         if (lim >= 16) {
-            // Whole 16-byte group at once.  Bit k+2 of eq = byte k equals its predecessor; bits 1, 0 = the same
-            // for the two bytes before the group (from `rep`).  Byte k is withheld iff eq_k & eq_{k-1} & eq_{k-2}.
+            // Whole 16-byte group at once.  Bit k+H of eq = byte k equals its predecessor (H = FZ_HOLD_AFTER); the
+            // H bits below stand for the bytes before the group (from `rep`).  Byte k is withheld iff the
+            // H+1 flags ending at k are all set.
             const FzVec16 v = ld(i);
             uint32_t eq = 0;
             int p = prev;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int c = (int)((v.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
-                eq |= (uint32_t)(c == p) << (k + 2);
+                eq |= (uint32_t)(c == p) << (k + FZ_HOLD_AFTER);
                 p = c;
             }
-            const uint32_t ext = eq | (rep >= 1 ? 2u : 0u) | (rep >= 2 ? 1u : 0u);
-            const uint32_t held = (ext & (ext << 1) & (ext << 2)) >> 2;  // 16 bits
+            const uint32_t hist_bits = ((1u << rep) - 1u) << (FZ_HOLD_AFTER - rep);  // the last `rep` flags before the group
+            const uint32_t ext = eq | hist_bits;
+            uint32_t held = ext;
+#pragma unroll
+            for (int j = 1; j <= FZ_HOLD_AFTER; j++) held &= ext << j;
+            held >>= FZ_HOLD_AFTER;  // 16 bits
             if (held == 0 && m == 0) {          // (A) sixteen literals
                 sink.literal16(v);
-                rep = (eq >> 17) & 1u ? (((eq >> 16) & 1u) ? 2u : 1u) : 0u;
+                // repeats at the end of the group: trailing ones of the flag word, saturated
+                const uint32_t inv = ~(ext >> FZ_HOLD_AFTER) & 0xffffu;        // zero flag = run break
+                uint32_t t = inv ? (uint32_t)(15 - fz_ilog2(inv)) : 16u + rep;  // flags set after the last break
+                rep = t > FZ_HOLD_AFTER ? FZ_HOLD_AFTER : t;
                 prev = p;
                 continue;
             }
             if (held == 0xffffu) {               // (B) the whole group continues a run that is already being withheld
                 m += 16;
                 if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
-                continue;                        // prev unchanged, rep stays 2
+                continue;                        // prev unchanged, rep stays saturated
             }
         }
         // (C) a run starts or ends inside the group, or the ragged tail: byte by byte (rolled: keeps the code small)
@@ -107,7 +119,7 @@ FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, u
         for (uint32_t k = 0; k < cnt; k++) {
             const int c = (int)lb(i + k);
             const bool e = c == prev;
-            if (e && rep >= 2) {
+            if (e && rep >= FZ_HOLD_AFTER) {
                 if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
             } else {
                 if (m) {

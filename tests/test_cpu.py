@@ -163,7 +163,7 @@ def test_model_encoder_streams_inflate_with_zlib(hostmodel, oracle, name):
     # per-plane sanity bound (headers are per 16 KiB sub-block, runs are cut at 512-byte lane pieces); the
     # whole-file bound of 5 % on the named distributions is test_model_whole_file_ratio
     nsub = a.size // hostmodel.SUB + 1
-    assert c.size <= 1.09 * len(z) + 128 * nsub or c.size <= len(z) + 0.025 * a.size
+    assert c.size <= 1.09 * len(z) + 128 * nsub or c.size <= len(z) + 0.05 * a.size
 
 
 @pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
