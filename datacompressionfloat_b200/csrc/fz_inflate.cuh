@@ -92,8 +92,11 @@ struct FzByteWriter {
     }
 };
 
-// first-level lookup table of the warp-shared fast path: index = next FZ_LUT_BITS stream bits,
-// entry = symbol | code length << 9 (0 = code longer than FZ_LUT_BITS: use the canonical search)
+// first-level lookup table of the warp-shared fast path: index = next FZ_LUT_BITS stream bits.
+//   entry == 0                     : code longer than FZ_LUT_BITS -> canonical search
+//   bits  0..8  sym1, 9..12 len1   : the first symbol and its code length
+//   bits 13..20 sym2, 21..24 total : when the bits after sym1 hold a second complete LITERAL code,
+//                                    sym2 and len1 + len2 (total != 0 marks a pair; sym1 is a literal too)
 #define FZ_LUT_BITS 10
 #define FZ_LUT_SIZE (1 << FZ_LUT_BITS)
 
@@ -200,7 +203,7 @@ struct FzInflater {
         if (in_body) return body_symbol(nullptr);
         return block_header();
     }
-    FZ_HD bool step_lut(const uint16_t *lut)
+    FZ_HD bool step_lut(const uint32_t *lut)
     {
         if (in_body) return body_symbol(lut);
         return block_header();
@@ -218,7 +221,7 @@ struct FzInflater {
 
     FZ_HD bool fail(int code) { rc = code; return false; }
 
-    FZ_HD bool body_symbol(const uint16_t *lut)
+    FZ_HD bool body_symbol(const uint32_t *lut)
     {
         br.refill();
         uint32_t idx, sym;
@@ -226,7 +229,7 @@ struct FzInflater {
         const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
         if (e) {
             sym = e & 511u;
-            br.drop((int)(e >> 9));
+            br.drop((int)((e >> 9) & 15u));
         } else {
             l = fz_decode_idx(LL, br.peek(15), idx);
             if (l == 0) return fail(FZ_INF_E_DATA);

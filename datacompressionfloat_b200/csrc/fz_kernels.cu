@@ -843,7 +843,7 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 #define FZ_INF_WARPS 4
 struct FzGroupSmem {
     uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
-    uint16_t lut[FZ_LUT_SIZE];
+    uint32_t lut[FZ_LUT_SIZE];
 };
 
 #define FZ_BCAST_CODE(C, src)                                                                                   \
@@ -941,15 +941,26 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
             for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) {
                 uint32_t idx;
                 const int l = fz_decode_idx(inf.LL, e, idx);
-                uint16_t v = 0;
-                if (l >= 1 && l <= FZ_LUT_BITS && idx < 288) v = (uint16_t)(sm->tab[idx] | (l << 9));
+                uint32_t v = 0;
+                if (l >= 1 && l <= FZ_LUT_BITS && idx < 288) {
+                    const uint32_t s1 = sm->tab[idx];
+                    v = s1 | ((uint32_t)l << 9);
+                    if (s1 < 256u && l < FZ_LUT_BITS) {  // room for a second literal in the remaining bits?
+                        uint32_t idx2;
+                        const int l2 = fz_decode_idx(inf.LL, e >> l, idx2);
+                        if (l2 >= 1 && l + l2 <= FZ_LUT_BITS && idx2 < 288) {
+                            const uint32_t s2 = sm->tab[idx2];
+                            if (s2 < 256u) v |= (s2 << 13) | ((uint32_t)(l + l2) << 21);
+                        }
+                    }
+                }
                 sm->lut[e] = v;
             }
         }
         __syncwarp();
     }
     // lock-step drive: lanes reconverge after every symbol
-    const uint16_t *lut = coded_mask ? sm->lut : nullptr;
+    const uint32_t *lut = coded_mask ? sm->lut : nullptr;
     while (__any_sync(0xffffffffu, live)) {
         if (live) {
             if (inf.in_body && lut) {
@@ -958,10 +969,12 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                 for (int it = 0; it < 16; ++it) {
                     inf.br.refill();
                     const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
-                    const uint32_t sym = e & 511u;
-                    if (e == 0 || sym >= 256u || inf.bw.op >= inf.bw.cap) break;
-                    inf.br.drop((int)(e >> 9));
+                    const uint32_t sym = e & 511u, tot = e >> 21;
+                    const uint32_t nsym = tot ? 2u : 1u;
+                    if (e == 0 || sym >= 256u || inf.bw.op + nsym > inf.bw.cap) break;
+                    inf.br.drop((int)(tot ? tot : ((e >> 9) & 15u)));
                     inf.bw.put(sym);
+                    if (tot) inf.bw.put((e >> 13) & 255u);
                 }
             }
             live = inf.step_lut(lut);  // whatever comes next: long code, match, end of block, block header
