@@ -394,10 +394,10 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
     const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
     const uint32_t nstreams = bmax * FZ_PLANES;
     FzInflateBufs ib;
-    ib.tiles_per_stream = chk / 4096 + 2;
+    ib.tiles_per_stream = chk / 65536 + 2;  // FZ_TILE_BYTES
     const size_t ntiles = (size_t)nstreams * ib.tiles_per_stream;
     ib.hits_cap = (uint32_t)((size_t)nstreams * nsub_full * 2 + 1024);
-    const size_t nbsum = (ntiles + 4095) / 4096 + 2;
+    const size_t nbsum = (ntiles + 4095) / 4096 + 4;
     int rc;
     if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->stream_hdr, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
@@ -410,6 +410,7 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
     ib.stream_mode = (uint32_t *)c->stream_mode.p;
     ib.stream_fail = (uint32_t *)c->stream_fail.p;
     if ((rc = status_reset(c, start))) return rc;
+    const bool in_place_raw = (chk % 16u) == 0;  // merge reads RAW payloads straight from the container
 
     uint32_t launches = 0;
     prof_begin(c);
@@ -422,10 +423,14 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
                        c->d_status, c->stream);
         prof_mark(c, FZ_ST_WALK);
         fz_launch_inflate((const uint8_t *)d_in, in_size, g, (const uint32_t *)c->stream_hdr.p,
-                          (const unsigned long long *)c->stream_off.p, ib, (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c);
-        fz_launch_merge((const uint8_t *)c->planes.p, pstride, nw, (uint32_t *)d_words_out + w0, c->merge_variant, c->stream);
+                          (const unsigned long long *)c->stream_off.p, ib, (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c, !in_place_raw);
+        if (in_place_raw)
+            fz_launch_merge_streams((const uint8_t *)c->planes.p, (const uint8_t *)d_in, (const uint32_t *)c->stream_hdr.p,
+                                    (const unsigned long long *)c->stream_off.p, g, (uint32_t *)d_words_out + w0, c->stream);
+        else
+            fz_launch_merge((const uint8_t *)c->planes.p, pstride, nw, (uint32_t *)d_words_out + w0, c->merge_variant, c->stream);
         prof_mark(c, FZ_ST_MERGE);
-        launches += 1 + 9 + 1 + ((nw & 3) ? 1 : 0);
+        launches += 1 + 8 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
     }
     if ((rc = status_fetch(c))) return rc;
     prof_collect(c);

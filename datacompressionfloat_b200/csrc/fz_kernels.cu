@@ -282,6 +282,72 @@ void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwor
     if (nwords & 3) fz_merge_tail_kernel<<<1, 4, 0, st>>>(planes, plane_stride, nvec * 4, nwords, words);
 }
 
+// merge for the decompress pipeline: plane j of chunk c comes from the plane buffer (inflated) or, for a RAW
+// stream, straight from its payload inside the container (arbitrary byte alignment: two aligned loads + funnel shift)
+__device__ __forceinline__ uint32_t fz_ld_u32_unaligned(const uint8_t *src, uint64_t byte_off, const uint8_t *end)
+{
+    const uint8_t *p = src + byte_off;
+    const uint32_t sk = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t *a = (const uint32_t *)(p - sk);
+    const uint32_t w0 = fz_ld_stream32(a);
+    if (sk == 0) return w0;
+    const uint32_t w1 = ((const uint8_t *)(a + 1) < end) ? fz_ld_stream32(a + 1) : 0u;
+    return __funnelshift_r(w0, w1, sk * 8);
+}
+
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
+fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
+                        const unsigned long long *__restrict__ stream_off, FzBatchGeom g, uint32_t *__restrict__ words)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t n_c = (c == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t nvec = n_c / 4;
+    const uint8_t *src[4];
+    const uint8_t *end[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t h = stream_hdr[c * 4 + j];
+        src[j] = (h & FZ_RAW_FLAG) ? container + stream_off[c * 4 + j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
+        end[j] = src[j] + n_c;
+    }
+    uint4 *out4 = (uint4 *)(words + (uint64_t)c * g.chk);
+    const uint32_t base = blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL) + threadIdx.x;
+    uint32_t a[FZ_SPLIT_UNROLL], b[FZ_SPLIT_UNROLL], cc[FZ_SPLIT_UNROLL], d[FZ_SPLIT_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint32_t i = base + k * FZ_SPLIT_THREADS;
+        if (i < nvec) {
+            a[k] = fz_ld_u32_unaligned(src[0], (uint64_t)i * 4, end[0]);
+            b[k] = fz_ld_u32_unaligned(src[1], (uint64_t)i * 4, end[1]);
+            cc[k] = fz_ld_u32_unaligned(src[2], (uint64_t)i * 4, end[2]);
+            d[k] = fz_ld_u32_unaligned(src[3], (uint64_t)i * 4, end[3]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint32_t i = base + k * FZ_SPLIT_THREADS;
+        if (i < nvec) {
+            uint4 w;
+            fz_transpose4(a[k], b[k], cc[k], d[k], w.x, w.y, w.z, w.w);
+            out4[i] = w;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n_c & 3u)) {  // ragged tail of the last chunk
+        const uint32_t i = nvec * 4 + threadIdx.x;
+        uint32_t w = 0;
+        for (int j = 0; j < 4; j++) w |= (uint32_t)src[j][i] << (8 * j);
+        words[(uint64_t)c * g.chk + i] = w;
+    }
+}
+
+void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, const uint32_t *stream_hdr,
+                             const unsigned long long *stream_off, FzBatchGeom g, uint32_t *words, cudaStream_t st)
+{
+    const uint32_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
+    dim3 grid((g.chk / 4 + per - 1) / per, g.nchunks);
+    fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, g, words);
+}
+
 // =================================================================================================
 // deflate: three kernels
 //   fz_hist_kernel        one warp per 16 KiB sub-block: token histogram, accumulated per group of 32 sub-blocks
@@ -351,8 +417,15 @@ struct __align__(16) FzHistSmem {
     uint32_t hist[288];
 };
 
+// Sub-blocks whose byte distribution is (nearly) flat cannot be entropy coded: a 2 KiB sample (the first 64
+// bytes of every lane piece) decides that before the 16 KiB are even read.  The plug-in entropy of 2048
+// samples of uniform bytes is about 7.91 bits (bias -255 / (2 N ln 2)); anything above FZ_SAMPLE_BITS is
+// emitted as a stored block (and, if the whole stream ends up like that, the stream becomes RAW).
+#define FZ_SAMPLE_BITS 7.85f
+
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
-fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist)
+fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist, uint32_t *__restrict__ sizes,
+               FzStatus *status)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -362,8 +435,37 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
     if (!fz_slot(g, t, s, k, n)) return;
     FzHistSmem *sm = (FzHistSmem *)fz_smem + warp;
     const uint32_t P = fz_piece_len(n);
+    const uint8_t *src = fz_sub_src(planes, g, s, k);
     for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
-    fz_stage(sm->stage, fz_sub_src(planes, g, s, k), n, P, lane);
+    __syncwarp();
+    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
+        // ---- sample pass
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = *(const uint4 *)(src + lane * (FZ_SUB / 32) + 16 * q);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int b = 0; b < 16; b++) atomicAdd(&sm->hist[(w[b >> 2] >> ((b & 3) * 8)) & 0xffu], 1u);
+        }
+        __syncwarp();
+        float acc = 0.f;
+        for (int i = lane; i < 256; i += 32) {
+            const float f = (float)sm->hist[i];
+            if (f > 0.f) acc += f * __log2f(f);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        const float bits = 11.f - acc * (1.f / 2048.f);  // log2(2048) - sum f log2 f / N
+        if (bits > FZ_SAMPLE_BITS) {
+            if (lane == 0) { sizes[t] = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
+            return;
+        }
+        __syncwarp();
+        for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
+        __syncwarp();
+    }
+    if (lane == 0) sizes[t] = 0;  // to be decided by the emit kernel
+    fz_stage(sm->stage, src, n, P, lane);
     DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
     DevLoadByte lb{sm->stage, P};
     fz_ph_hist(sm->hist, ld, lb, n, lane);
@@ -413,6 +515,7 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
     uint32_t s, k, n;
     if (!fz_slot(g, t, s, k, n)) return;
+    if (sizes[t] & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
     const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
     if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to stage or emit
         if (lane == 0) { sizes[t] = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
@@ -449,7 +552,7 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
     cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEmitSmem) * FZ_ENC_WARPS));
     cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
-    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist);
+    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, status);
     fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
         ghist, g, (FzGroupCode *)gcodes);
     fz_emit_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEmitSmem) * FZ_ENC_WARPS, st>>>(planes, g, (const FzGroupCode *)gcodes,
@@ -656,7 +759,8 @@ void fz_launch_walk(const uint8_t *container, uint64_t container_size, FzBatchGe
 }
 
 // ---- sync-marker scan: positions p (stream relative) with bytes p..p+3 == 00 00 FF FF
-#define FZ_TILE_BYTES 4096
+#define FZ_TILE_BYTES 65536   // payload bytes per marker-scan block (one count per tile)
+#define FZ_SLICE_BYTES 4096   // bytes the block covers per iteration (256 threads x 16 positions)
 #define FZ_SCAN_THREADS 256
 
 __device__ __forceinline__ uint32_t fz_marker_mask(const uint8_t *base, uint32_t len, uint32_t p0)
@@ -706,28 +810,35 @@ fz_marker_kernel(const uint8_t *__restrict__ container, const uint32_t *__restri
         if (threadIdx.x == 0) tile_cnt[b] = 0;
         return;
     }
-    const uint32_t p0 = tile * FZ_TILE_BYTES + threadIdx.x * 16;
-    const uint32_t m = fz_marker_mask(container + stream_off[s], len, p0);
-    const uint32_t cnt = __popc(m);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t inc = fz_warp_incl_scan(cnt, lane);
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
+    const uint8_t *base = container + stream_off[s];
+    uint32_t acc = 0;  // markers found in the earlier slices of this tile
+    for (uint32_t slice = 0; slice < FZ_TILE_BYTES / FZ_SLICE_BYTES; slice++) {
+        const uint32_t q0 = tile * FZ_TILE_BYTES + slice * FZ_SLICE_BYTES;
+        if ((uint64_t)q0 + 4 > len) break;  // block-uniform
+        const uint32_t p0 = q0 + threadIdx.x * 16;
+        const uint32_t m = fz_marker_mask(base, len, p0);
+        const uint32_t cnt = __popc(m);
+        const uint32_t inc = fz_warp_incl_scan(cnt, lane);
+        __syncthreads();
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < FZ_SCAN_THREADS / 32; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
-    if (!WRITE) {
-        if (threadIdx.x == 0) tile_cnt[b] = total;
-    } else {
-        uint32_t o = out_base + wbase + inc - cnt;
-        uint32_t mm = m;
-        while (mm) {
-            const int bit = __ffs((int)mm) - 1;
-            mm &= mm - 1;
-            if (o < hits_cap) hits[o] = p0 + (uint32_t)bit;
-            o++;
+        for (int w = 0; w < FZ_SCAN_THREADS / 32; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+        if (WRITE) {
+            uint32_t o = out_base + acc + wbase + inc - cnt;
+            uint32_t mm = m;
+            while (mm) {
+                const int bit = __ffs((int)mm) - 1;
+                mm &= mm - 1;
+                if (o < hits_cap) hits[o] = p0 + (uint32_t)bit;
+                o++;
+            }
         }
+        acc += total;
     }
+    if (!WRITE && threadIdx.x == 0) tile_cnt[b] = acc;
 }
 
 // ---- exclusive scan of a uint32 array (n elements, writes n + 1: the last is the total)
@@ -1036,7 +1147,7 @@ fz_rawcopy_kernel(const uint8_t *__restrict__ container, uint64_t container_size
 
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status, cudaStream_t st,
-                       fz_mark_fn mark, void *mark_user)
+                       fz_mark_fn mark, void *mark_user, bool copy_raw)
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t ntiles = nstreams * b.tiles_per_stream;
@@ -1052,7 +1163,9 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_GENERAL);
-    const uint32_t total = nstreams * g.nsub_full;
-    fz_rawcopy_kernel<<<(total + 3) / 4, 128, 0, st>>>(container, container_size, g, stream_hdr, stream_off, planes, status);
-    if (mark) mark(mark_user, FZ_ST_RAWCOPY);
+    if (copy_raw) {  // only when the merge cannot read RAW payloads in place (chunk size not a multiple of 16)
+        const uint32_t total = nstreams * g.nsub_full;
+        fz_rawcopy_kernel<<<(total + 3) / 4, 128, 0, st>>>(container, container_size, g, stream_hdr, stream_off, planes, status);
+        if (mark) mark(mark_user, FZ_ST_RAWCOPY);
+    }
 }

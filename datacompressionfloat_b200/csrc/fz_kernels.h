@@ -74,6 +74,9 @@ struct FzInflateBufs {
 };
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status,
-                       cudaStream_t st, fz_mark_fn mark, void *mark_user);
+                       cudaStream_t st, fz_mark_fn mark, void *mark_user, bool copy_raw);
+// merge that reads RAW streams in place from the container (needs chk % 16 == 0)
+void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, const uint32_t *stream_hdr,
+                             const unsigned long long *stream_off, FzBatchGeom g, uint32_t *words, cudaStream_t st);
 
 size_t fz_encode_smem_bytes();
