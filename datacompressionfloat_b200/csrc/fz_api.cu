@@ -16,6 +16,8 @@
 #include "../../include/mrczip_b200.h"
 #include "fz_kernels.h"
 
+#define FZ_MAX_HOST_BATCHES 8192
+
 #define FZ_CHECK(call)                                                                       \
     do {                                                                                     \
         cudaError_t e_ = (call);                                                             \
@@ -39,6 +41,10 @@ struct mzb_ctx {
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
     DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes;
+    // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_h2d, ev_comp, ev_d2h;
+    unsigned long long *h_ends = nullptr;  // pinned, FZ_MAX_HOST_BATCHES entries
     FzStatus *d_status = nullptr;
     FzStatus *h_status = nullptr;  // pinned
     mzb_stats stats;
@@ -187,6 +193,11 @@ extern "C" void mzb_destroy(mzb_ctx *c)
                      &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
+        for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    if (c->h_ends) cudaFreeHost(c->h_ends);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -284,6 +295,83 @@ extern "C" int mzb_merge_device(mzb_ctx *c, const void *d_planes, uint64_t plane
     fz_launch_merge((const uint8_t *)d_planes, plane_stride, nwords, (uint32_t *)d_words_out, c->merge_variant, c->stream);
     FZ_CHECK(cudaGetLastError());
     return MZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shared by the device-resident and the host-buffer paths
+static int compress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t *pstride_out)
+{
+    const uint64_t pstride = plane_stride_for(bmax, chk);
+    const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
+    const size_t nslots = (size_t)bmax * FZ_PLANES * nsub_full;
+    const size_t ngroups = (size_t)bmax * FZ_PLANES * ((nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
+    int rc;
+    if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->scratch, nslots * FZ_SLOT_STRIDE + 256)) ||
+        (rc = ensure(c->sizes, nslots * 4)) || (rc = ensure(c->sub_off, nslots * 4)) ||
+        (rc = ensure(c->stream_hdr, (size_t)bmax * FZ_PLANES * 4)) || (rc = ensure(c->stream_off, (size_t)bmax * FZ_PLANES * 8)) ||
+        (rc = ensure(c->ghist, ngroups * 288 * 4)) || (rc = ensure(c->gcodes, ngroups * fz_group_code_bytes())))
+        return rc;
+    *pstride_out = pstride;
+    return MZB_OK;
+}
+
+static void compress_enqueue_batch(mzb_ctx *c, const uint32_t *d_words, uint64_t nw, uint32_t nb, uint32_t chk, uint64_t pstride,
+                                   uint32_t mask, uint64_t exempt, uint8_t *d_out, size_t out_cap)
+{
+    const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
+    fz_launch_split(d_words, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
+    prof_mark(c, FZ_ST_SPLIT);
+    fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p,
+                     (uint32_t *)c->sizes.p, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_ENCODE);
+    fz_launch_layout((const uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
+                     (unsigned long long *)c->stream_off.p, d_out, out_cap, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_LAYOUT);
+    fz_launch_gather((const uint8_t *)c->planes.p, (const uint8_t *)c->scratch.p, (const uint32_t *)c->sizes.p,
+                     (const uint32_t *)c->sub_off.p, (const uint32_t *)c->stream_hdr.p,
+                     (const unsigned long long *)c->stream_off.p, g, d_out, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_GATHER);
+}
+
+static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t *pstride_out, FzInflateBufs *ib)
+{
+    const uint64_t pstride = plane_stride_for(bmax, chk);
+    const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
+    const uint32_t nstreams = bmax * FZ_PLANES;
+    ib->tiles_per_stream = chk / 65536 + 2;  // FZ_TILE_BYTES
+    const size_t ntiles = (size_t)nstreams * ib->tiles_per_stream;
+    ib->hits_cap = (uint32_t)((size_t)nstreams * nsub_full * 2 + 1024);
+    const size_t nbsum = (ntiles + 4095) / 4096 + 4;
+    int rc;
+    if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->stream_hdr, (size_t)nstreams * 4)) ||
+        (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
+        (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
+        (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib->hits_cap * 4)))
+        return rc;
+    ib->tile_cnt = (uint32_t *)c->tile_cnt.p;
+    ib->block_sums = (uint32_t *)c->block_sums.p;
+    ib->hits = (uint32_t *)c->hits.p;
+    ib->stream_mode = (uint32_t *)c->stream_mode.p;
+    ib->stream_fail = (uint32_t *)c->stream_fail.p;
+    *pstride_out = pstride;
+    return MZB_OK;
+}
+
+// records of the batch start at d_in + status->out_end
+static void decompress_enqueue_batch(mzb_ctx *c, const uint8_t *d_in, size_t in_size, FzBatchGeom g, const FzInflateBufs &ib,
+                                     uint32_t *d_words_out, bool in_place_raw)
+{
+    fz_launch_walk(d_in, in_size, g, (uint32_t *)c->stream_hdr.p, (unsigned long long *)c->stream_off.p, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_WALK);
+    fz_launch_inflate(d_in, in_size, g, (const uint32_t *)c->stream_hdr.p, (const unsigned long long *)c->stream_off.p, ib,
+                      (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c, !in_place_raw);
+    if (in_place_raw)
+        fz_launch_merge_streams((const uint8_t *)c->planes.p, d_in, (const uint32_t *)c->stream_hdr.p,
+                                (const unsigned long long *)c->stream_off.p, g, d_words_out, c->stream);
+    else
+        fz_launch_merge((const uint8_t *)c->planes.p, g.plane_stride, (uint64_t)(g.nchunks - 1) * g.chk + g.last_n, d_words_out,
+                        c->merge_variant, c->stream);
+    prof_mark(c, FZ_ST_MERGE);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -447,26 +535,104 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
 }
 
 // ---------------------------------------------------------------------------------------------------
-// host-buffer versions: H2D, device pipeline, D2H
+// host-buffer versions: a three-stage pipeline over batches of chunks -- H2D of batch b+1, kernels of batch b
+// and D2H of batch b-1 run concurrently on three streams (double-buffered device staging).
+static int host_pipe_init(mzb_ctx *c, size_t nbatches)
+{
+    if (!c->s_h2d) FZ_CHECK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    if (!c->s_d2h) FZ_CHECK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    if (!c->h_ends) FZ_CHECK(cudaHostAlloc((void **)&c->h_ends, FZ_MAX_HOST_BATCHES * sizeof(unsigned long long), cudaHostAllocDefault));
+    for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
+        while (v->size() < nbatches) {
+            cudaEvent_t e;
+            FZ_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            v->push_back(e);
+        }
+    return MZB_OK;
+}
+
+static uint32_t host_batch_chunks(const mzb_ctx *c, uint32_t chk)
+{
+    const uint32_t b = batch_chunks_for(c, chk);
+    return b > 24u ? 24u : b;  // finer batches than the device path: more overlap between copies and kernels
+}
+
 extern "C" int mzb_compress_host(mzb_ctx *c, const void *h_words, uint64_t nwords, int bits, uint32_t exempt_words,
                                  uint32_t chk, uint64_t fsz, int write_file_header, void *h_out, size_t out_cap,
                                  uint64_t *out_size)
 {
-    if (!c || !out_size || chk == 0) return MZB_E_ARG;
+    if (!c || !out_size || bits < 0 || bits > 32 || chk == 0 || chk >= 0x80000000u) return MZB_E_ARG;
     *out_size = 0;
+    memset(&c->stats, 0, sizeof(c->stats));
     if (nwords == 0) return MZB_OK;
     FZ_CHECK(cudaSetDevice(c->device));
+    const uint64_t nchunks_total = (nwords + chk - 1) / chk;
+    const uint32_t hb = host_batch_chunks(c, chk);
+    const uint32_t bmax = (uint32_t)(nchunks_total < hb ? nchunks_total : hb);
+    const size_t nbatches = (size_t)((nchunks_total + bmax - 1) / bmax);
+    if (nbatches > FZ_MAX_HOST_BATCHES) return MZB_E_ARG;
     const size_t bound = mzb_compress_bound(nwords, chk);
+    const size_t in_stride = (((size_t)bmax * chk * 4 + 255) & ~(size_t)255) + 256;
+    uint64_t pstride;
     int rc;
-    if ((rc = ensure(c->io_in, nwords * 4 + 256)) || (rc = ensure(c->io_out, bound + 256))) return rc;
-    FZ_CHECK(cudaMemcpyAsync(c->io_in.p, h_words, nwords * 4, cudaMemcpyHostToDevice, c->stream));
-    uint64_t sz = 0;
-    rc = mzb_compress_device(c, c->io_in.p, nwords, bits, exempt_words, chk, fsz, write_file_header, c->io_out.p, bound, &sz);
-    if (rc) return rc;
-    if (sz > out_cap) return MZB_E_SPACE;
-    FZ_CHECK(cudaMemcpyAsync(h_out, c->io_out.p, sz, cudaMemcpyDeviceToHost, c->stream));
-    FZ_CHECK(cudaStreamSynchronize(c->stream));
-    *out_size = sz;
+    if ((rc = compress_reserve(c, bmax, chk, &pstride)) || (rc = ensure(c->io_in, 2 * in_stride)) ||
+        (rc = ensure(c->io_out, bound + 256)) || (rc = host_pipe_init(c, nbatches)))
+        return rc;
+    uint8_t *d_out = (uint8_t *)c->io_out.p;
+    uint64_t start = 0;
+    if (write_file_header) {
+        if (out_cap < MZB_FILE_HEADER_BYTES) return MZB_E_SPACE;
+        uint8_t *hd = (uint8_t *)h_out;  // common.c:137-149
+        memset(hd, 0, MZB_FILE_HEADER_BYTES);
+        memcpy(hd, &fsz, 8);
+        memcpy(hd + 8, &chk, 4);
+        start = MZB_FILE_HEADER_BYTES;
+    }
+    if ((rc = status_reset(c, start))) return rc;
+    const uint32_t mask = fz_mask_for_bits(bits);
+    uint32_t launches = 0;
+    uint64_t copied_to = start;  // container bytes already on their way to the host
+    int result = MZB_OK;
+    prof_begin(c);
+    for (size_t b = 0; b <= nbatches; b++) {
+        if (b < nbatches) {
+            const uint64_t c0 = (uint64_t)b * bmax;
+            const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
+            const uint64_t w0 = c0 * chk;
+            const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
+            uint8_t *d_in = (uint8_t *)c->io_in.p + (b & 1) * in_stride;
+            if (b >= 2) FZ_CHECK(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b - 2], 0));  // staging buffer free again
+            FZ_CHECK(cudaMemcpyAsync(d_in, (const uint32_t *)h_words + w0, nw * 4, cudaMemcpyHostToDevice, c->s_h2d));
+            FZ_CHECK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+            FZ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+            const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
+            compress_enqueue_batch(c, (const uint32_t *)d_in, nw, nb, chk, pstride, mask, exempt, d_out, bound);
+            FZ_CHECK(cudaMemcpyAsync(&c->h_ends[b], &c->d_status->out_end, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            FZ_CHECK(cudaEventRecord(c->ev_comp[b], c->stream));
+            launches += 7 + ((nw & 3) ? 1 : 0);
+        }
+        if (b >= 1) {  // batch b-1 is done (or about to be): ship its part of the container while batch b computes
+            FZ_CHECK(cudaEventSynchronize(c->ev_comp[b - 1]));
+            const uint64_t end = c->h_ends[b - 1];
+            if (end > out_cap) { result = MZB_E_SPACE; break; }
+            if (end > copied_to)
+                FZ_CHECK(cudaMemcpyAsync((uint8_t *)h_out + copied_to, d_out + copied_to, end - copied_to, cudaMemcpyDeviceToHost, c->s_d2h));
+            copied_to = end;
+        }
+    }
+    FZ_CHECK(cudaStreamSynchronize(c->s_d2h));
+    if ((rc = status_fetch(c))) return rc;
+    prof_collect(c);
+    c->stats.bytes_in = nwords * 4;
+    c->stats.bytes_out = c->h_status->out_end;
+    c->stats.chunks = (uint32_t)nchunks_total;
+    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
+    c->stats.raw_streams = c->h_status->n_raw_streams;
+    c->stats.stored_subblocks = c->h_status->n_stored_sub;
+    c->stats.kernel_launches = launches;
+    if (result != MZB_OK) return result;
+    if (c->h_status->error) return c->h_status->error;
+    *out_size = c->h_status->out_end;
     return MZB_OK;
 }
 
@@ -475,24 +641,91 @@ extern "C" int mzb_decompress_host(mzb_ctx *c, const void *h_in, size_t in_size,
 {
     if (!c || !nwords_out) return MZB_E_ARG;
     *nwords_out = 0;
+    memset(&c->stats, 0, sizeof(c->stats));
     if (in_size == 0) return MZB_OK;
     FZ_CHECK(cudaSetDevice(c->device));
+    const uint8_t *in = (const uint8_t *)h_in;
+    uint64_t off = 0;
     if (has_file_header) {
-        if (in_size < MZB_FILE_HEADER_BYTES) return MZB_E_FORMAT;
+        if (in_size < MZB_FILE_HEADER_BYTES) return MZB_E_FORMAT;  // common.c:119-123
         uint64_t fsz;
-        memcpy(&fsz, h_in, 8);
+        memcpy(&fsz, in, 8);
+        memcpy(&chk, in + 8, 4);
+        for (int j = 0; j < MZB_PLANES; j++)
+            if (in[13 + j] != 0) return MZB_E_FORMAT;
         nwords = fsz / 4;
+        off = MZB_FILE_HEADER_BYTES;
     }
+    if (chk == 0 || chk >= 0x80000000u) return MZB_E_FORMAT;
     if (nwords > out_cap_words) return MZB_E_SPACE;
+    if (nwords == 0) return MZB_OK;
+    const uint64_t nchunks_total = (nwords + chk - 1) / chk;
+    const uint32_t hb = host_batch_chunks(c, chk);
+    const uint32_t bmax = (uint32_t)(nchunks_total < hb ? nchunks_total : hb);
+    const size_t nbatches = (size_t)((nchunks_total + bmax - 1) / bmax);
+    if (nbatches > FZ_MAX_HOST_BATCHES) return MZB_E_ARG;
+    // host walk of the chunk-header chain (workers.c:61-69): byte range of every batch of chunk records
+    std::vector<uint64_t> rec_off(nbatches + 1);
+    for (uint64_t ci = 0; ci < nchunks_total; ci++) {
+        if (ci % bmax == 0) rec_off[ci / bmax] = off;
+        if (off + FZ_CHUNK_HEADER_BYTES > in_size) return MZB_E_FORMAT;
+        uint64_t rec = FZ_CHUNK_HEADER_BYTES;
+        for (int j = 0; j < MZB_PLANES; j++) {
+            uint32_t h;
+            memcpy(&h, in + off + 4 * j, 4);
+            rec += h & ~FZ_RAW_FLAG;
+        }
+        if (off + rec > in_size) return MZB_E_FORMAT;
+        off += rec;
+    }
+    rec_off[nbatches] = off;
+    size_t max_rec = 0;
+    for (size_t b = 0; b < nbatches; b++) max_rec = max_rec > rec_off[b + 1] - rec_off[b] ? max_rec : (size_t)(rec_off[b + 1] - rec_off[b]);
+    const size_t in_stride = ((max_rec + 255) & ~(size_t)255) + 256;
+    const size_t out_stride = (((size_t)bmax * chk * 4 + 255) & ~(size_t)255) + 256;
+    uint64_t pstride;
+    FzInflateBufs ib;
     int rc;
-    if ((rc = ensure(c->io_in, in_size + 256)) || (rc = ensure(c->io_out, nwords * 4 + 256))) return rc;
-    FZ_CHECK(cudaMemcpyAsync(c->io_in.p, h_in, in_size, cudaMemcpyHostToDevice, c->stream));
-    uint64_t nw = 0;
-    rc = mzb_decompress_device(c, c->io_in.p, in_size, has_file_header, chk, nwords, c->io_out.p, nwords, &nw);
-    if (rc) return rc;
-    FZ_CHECK(cudaMemcpyAsync(h_words_out, c->io_out.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
-    FZ_CHECK(cudaStreamSynchronize(c->stream));
-    *nwords_out = nw;
+    if ((rc = decompress_reserve(c, bmax, chk, &pstride, &ib)) || (rc = ensure(c->io_in, 2 * in_stride)) ||
+        (rc = ensure(c->io_out, 2 * out_stride)) || (rc = host_pipe_init(c, nbatches)))
+        return rc;
+    if ((rc = status_reset(c, 0))) return rc;
+    const bool in_place_raw = (chk % 16u) == 0;
+    uint32_t launches = 0;
+    prof_begin(c);
+    for (size_t b = 0; b < nbatches; b++) {
+        const uint64_t c0 = (uint64_t)b * bmax;
+        const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
+        const uint64_t w0 = c0 * chk;
+        const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
+        const size_t rbytes = (size_t)(rec_off[b + 1] - rec_off[b]);
+        uint8_t *d_rec = (uint8_t *)c->io_in.p + (b & 1) * in_stride;
+        uint32_t *d_w = (uint32_t *)((uint8_t *)c->io_out.p + (b & 1) * out_stride);
+        if (b >= 2) FZ_CHECK(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b - 2], 0));
+        FZ_CHECK(cudaMemcpyAsync(d_rec, in + rec_off[b], rbytes, cudaMemcpyHostToDevice, c->s_h2d));
+        FZ_CHECK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+        FZ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+        if (b >= 2) FZ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_d2h[b - 2], 0));  // output staging buffer free again
+        FZ_CHECK(cudaMemsetAsync(&c->d_status->out_end, 0, sizeof(unsigned long long), c->stream));  // records start at 0
+        decompress_enqueue_batch(c, d_rec, rbytes, make_geom(nb, chk, nw, pstride), ib, d_w, in_place_raw);
+        FZ_CHECK(cudaEventRecord(c->ev_comp[b], c->stream));
+        FZ_CHECK(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+        FZ_CHECK(cudaMemcpyAsync((uint32_t *)h_words_out + w0, d_w, nw * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        FZ_CHECK(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
+        launches += 1 + 8 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+    }
+    FZ_CHECK(cudaStreamSynchronize(c->s_d2h));
+    if ((rc = status_fetch(c))) return rc;
+    prof_collect(c);
+    c->stats.bytes_in = off;
+    c->stats.bytes_out = nwords * 4;
+    c->stats.chunks = (uint32_t)nchunks_total;
+    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
+    c->stats.general_streams = c->h_status->n_general;
+    c->stats.fast_failed = c->h_status->n_fast_failed;
+    c->stats.kernel_launches = launches;
+    if (c->h_status->error) return c->h_status->error;
+    *nwords_out = nwords;
     return MZB_OK;
 }
 
