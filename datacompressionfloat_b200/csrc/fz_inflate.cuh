@@ -27,9 +27,10 @@ struct FzInfTab {
 #define FZ_INF_TAB_U16 (288 + 32 + 32)  // uint16 entries per decoding thread
 
 struct FzBitReader {
-    const uint32_t *w;     // next aligned word to load (may run past wend: zero bits are fed then)
+    const uint32_t *w;     // address of the word held in `nxt` (may run past wend: zero bits are fed then)
     const uint32_t *wend;  // one past the last word that holds input bytes
     uint64_t acc;
+    uint32_t nxt;          // the next word, loaded one refill ahead so its latency hides behind decoding
     int nacc;              // valid bits in acc
     int tail_pad;          // bits of the last word that lie beyond the end of the input
     FZ_HD void init(const uint8_t *in, size_t in_len)
@@ -40,19 +41,20 @@ struct FzBitReader {
         const size_t nw = (in_len + sk + 3) / 4;
         wend = w + nw;
         tail_pad = (int)(nw * 32 - 8 * sk - in_len * 8);
-        acc = 0; nacc = 0;
+        acc = 0; nacc = 0; nxt = 0;
         if (nw > 0) { acc = (uint64_t)(*w++ >> (8 * sk)); nacc = 32 - 8 * (int)sk; }
         else tail_pad = 0;
+        if (w < wend) nxt = *w;
     }
     // bits of real input not yet consumed (negative after an overrun); derived, not tracked per symbol
     FZ_HD int64_t bits_left() const { return (int64_t)(wend - w) * 32 + nacc - tail_pad; }
     FZ_HD void refill()  // guarantees nacc >= 32 (zero bits past the end of the input)
     {
         if (nacc < 32) {
-            const uint32_t v = (w < wend) ? *w : 0u;
-            w++;
-            acc |= (uint64_t)v << nacc;
+            acc |= (uint64_t)nxt << nacc;
             nacc += 32;
+            w++;
+            nxt = (w < wend) ? *w : 0u;
         }
     }
     FZ_HD uint32_t peek(int n) const { return (uint32_t)acc & ((1u << n) - 1); }
