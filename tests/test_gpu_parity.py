@@ -314,3 +314,51 @@ def test_golden_fixtures_on_gpu(codec, oracle, gdir, case):
     cont = codec.compress(dev(w), bits, fsz=src.size).cpu().numpy()
     assert np.array_equal(cont[:17], ref_zip[:17])                       # identical file header
     assert np.array_equal(oracle.decompress(cont), ref_erase)
+
+
+# ----------------------------------------------------------------------------- CLIs with the reference's flags
+def test_cli_mrc_tar_and_tarx(codec, oracle):
+    import subprocess
+    from pathlib import Path
+    bindir = Path(__file__).resolve().parent.parent / "datacompressionfloat_b200" / "bin"
+    tar, tarx = bindir / "mrc_tar_b200", bindir / "mrc_tarx_b200"
+    if not (tar.exists() and tarx.exists()):
+        pytest.skip("CLIs not built")
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        files = []
+        for i, (kind, n) in enumerate([("P", 70000), ("G", 50001), ("S", 123457)]):
+            w = synth_words(kind, n, seed=i)
+            p = d / f"v{i}.mrc"
+            w.tofile(p)
+            files.append((p, w))
+        # mrc_tar_b200 -t zip / -t unzip (reference flags, mrc_tar.c:104)
+        z, out = d / "v0.zip", d / "v0.out"
+        subprocess.run([tar, "-i", files[0][0], "-o", z, "-b", "5", "-t", "zip"], check=True, stdout=subprocess.DEVNULL)
+        cont = np.fromfile(z, dtype=np.uint8)
+        golden = oracle.erasebytes(files[0][1].view(np.uint8), 5)
+        assert np.array_equal(oracle.decompress(cont), golden)
+        if oracle.have_ref():
+            assert np.array_equal(oracle.ref_decompress(cont), golden)      # the reference binary reads our file
+        subprocess.run([tar, "-i", z, "-o", out, "-t", "unzip"], check=True, stdout=subprocess.DEVNULL)
+        assert np.array_equal(np.fromfile(out, dtype=np.uint8), golden)
+        # mrc_tarx_b200: file list, N worker threads, DIR/<name>.mrc.zip <-> DIR/<name>.mrc (adapt.c:297-304)
+        (d / "zip").mkdir(); (d / "unz").mkdir()
+        (d / "list.txt").write_text("".join(f"{p}\n" for p, _ in files))
+        subprocess.run([tarx, "-i", d / "list.txt", "-o", d / "zip", "-t", "zip", "-b", "9", "-n", "3"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        (d / "zlist.txt").write_text("".join(f"{d / 'zip' / (p.name + '.zip')}\n" for p, _ in files))
+        subprocess.run([tarx, "-i", d / "zlist.txt", "-o", d / "unz", "-t", "unzip", "-n", "2"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for p, w in files:
+            assert np.array_equal(np.fromfile(d / "unz" / p.name, dtype=np.uint8), oracle.erasebytes(w.view(np.uint8), 9))
+        # a reference-made .zip goes through the same CLI
+        ref_zip = d / "ref.mrc.zip"
+        oracle.compress(files[1][1].view(np.uint8), 3).tofile(ref_zip)
+        subprocess.run([tar, "-i", ref_zip, "-o", d / "ref.out", "-t", "unzip"], check=True, stdout=subprocess.DEVNULL)
+        assert np.array_equal(np.fromfile(d / "ref.out", dtype=np.uint8), oracle.erasebytes(files[1][1].view(np.uint8), 3))
+        # -d 1 (isTestThroughput): nothing is written
+        (d / "dry").mkdir()
+        subprocess.run([tarx, "-i", d / "list.txt", "-o", d / "dry", "-t", "zip", "-n", "2", "-d", "1"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert all((d / "dry" / (p.name + ".zip")).stat().st_size == 0 for p, _ in files)
