@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--gib", type=float, default=4.0, help="GiB of float32 per GPU (default 4 = 1024^3)")
     ap.add_argument("--kind", default="G", choices=["G", "P", "S"], help="synthetic distribution (SURVEY 8d)")
     ap.add_argument("--bits", type=int, default=8, help="low mantissa bits erased")
+    ap.add_argument("--batch-chunks", type=int, default=0, help="chunks per kernel batch (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-chunks-per-file", type=int, default=6)
@@ -269,7 +270,7 @@ def run_b200(a):
         words[0:3] = 1024
         words[3] = 2
     exempt = 256 if rank == 0 else 0
-    codec = Codec.on_current_stream()
+    codec = Codec.on_current_stream(batch_chunks=a.batch_chunks or None)
     codec.set_profiling(True)
     cont_buf = torch.empty(Codec.compress_bound(nwords), dtype=torch.uint8, device=dev)
     out_words = torch.empty(nwords, dtype=torch.int32, device=dev)
