@@ -37,7 +37,7 @@ struct mzb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    uint32_t batch_chunks = 128;
+    uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
     DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes;

@@ -110,7 +110,7 @@ int mzb_create(mzb_ctx **out, int device, void *cuda_stream);
 /* Same, but always uses the given stream handle -- including NULL, the legacy default stream. */
 int mzb_create_on_stream(mzb_ctx **out, int device, void *cuda_stream);
 void mzb_destroy(mzb_ctx *ctx);
-/* Chunks processed per kernel batch (bounds scratch memory: about 8 bytes per word of a batch). Default 128. */
+/* Chunks processed per kernel batch (bounds scratch memory: about 8 bytes per word of a batch). Default 192 (4.5 GiB of input). */
 int mzb_set_batch_chunks(mzb_ctx *ctx, uint32_t chunks);
 /* kernel variant selectors used by the benchmarks (0 = default) */
 int mzb_set_variant(mzb_ctx *ctx, int split_variant, int merge_variant);
