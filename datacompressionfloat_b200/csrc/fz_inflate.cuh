@@ -80,6 +80,16 @@ struct FzByteWriter {
         if ((p >> 2) == (op >> 2)) return (ow >> ((p & 3) * 8)) & 0xffu;  // still pending in ow
         return out[p];
     }
+    // append cnt (1..3) bytes packed little-endian in v; the caller checked op + cnt <= cap
+    FZ_HD void putn(uint32_t v, uint32_t cnt)
+    {
+        const uint32_t sh = (op & 3) * 8;
+        const uint64_t t = (uint64_t)ow | ((uint64_t)v << sh);
+        const uint32_t nb = sh + cnt * 8;  // bits now pending
+        op += cnt;
+        if (nb >= 32) { *(uint32_t *)(out + (op & ~3u) - 4) = (uint32_t)t; ow = (uint32_t)(t >> 32); }
+        else ow = (uint32_t)t;
+    }
     FZ_HD void fill(uint32_t c, uint32_t len)  // len copies of byte c (a distance-1 match), whole words where possible
     {
         while (len && (op & 3)) { put(c); len--; }
@@ -95,12 +105,15 @@ struct FzByteWriter {
 };
 
 // first-level lookup table of the warp-shared fast path: index = next FZ_LUT_BITS stream bits.
-//   entry == 0                     : code longer than FZ_LUT_BITS -> canonical search
-//   bits  0..8  sym1, 9..12 len1   : the first symbol and its code length
-//   bits 13..20 sym2, 21..24 total : when the bits after sym1 hold a second complete LITERAL code,
-//                                    sym2 and len1 + len2 (total != 0 marks a pair; sym1 is a literal too)
-#define FZ_LUT_BITS 10
+//   entry == 0                 : code longer than FZ_LUT_BITS -> canonical search
+//   bits  0..8   sym1          : first symbol (literal, end-of-block or length code)
+//   bits  9..16  sym2          : second literal, bits 17..24 sym3: third literal (when count says so)
+//   bits 25..28  total length  : code bits consumed by the `count` symbols of this entry
+//   bits 29..30  count         : 1..3 symbols; entries with count > 1 hold literals only
+#define FZ_LUT_BITS 11
 #define FZ_LUT_SIZE (1 << FZ_LUT_BITS)
+#define FZ_LUT_ENTRY(s1, s2, s3, total, cnt) \
+    ((uint32_t)(s1) | ((uint32_t)(s2) << 9) | ((uint32_t)(s3) << 17) | ((uint32_t)(total) << 25) | ((uint32_t)(cnt) << 29))
 
 #define FZ_INF_OK 0
 #define FZ_INF_E_INPUT (-1)     // ran out of input / truncated
@@ -229,9 +242,9 @@ struct FzInflater {
         uint32_t idx, sym;
         int l;
         const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
-        if (e) {
+        if (e && (e >> 29) == 1u) {   // (multi-literal entries are consumed by the kernel's fast loop only)
             sym = e & 511u;
-            br.drop((int)((e >> 9) & 15u));
+            br.drop((int)((e >> 25) & 15u));
         } else {
             l = fz_decode_idx(LL, br.peek(15), idx);
             if (l == 0) return fail(FZ_INF_E_DATA);

@@ -1048,22 +1048,27 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                     inf.last = false;
                 }
             }
-            // first-level table: entry e = the symbol whose code is a prefix of the bit pattern e
+            // first-level table: entry e = the first symbol (and up to two more literals) coded by the bit pattern e
             for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) {
                 uint32_t idx;
-                const int l = fz_decode_idx(inf.LL, e, idx);
+                int l = fz_decode_idx(inf.LL, e, idx);
                 uint32_t v = 0;
                 if (l >= 1 && l <= FZ_LUT_BITS && idx < 288) {
                     const uint32_t s1 = sm->tab[idx];
-                    v = s1 | ((uint32_t)l << 9);
-                    if (s1 < 256u && l < FZ_LUT_BITS) {  // room for a second literal in the remaining bits?
-                        uint32_t idx2;
-                        const int l2 = fz_decode_idx(inf.LL, e >> l, idx2);
-                        if (l2 >= 1 && l + l2 <= FZ_LUT_BITS && idx2 < 288) {
-                            const uint32_t s2 = sm->tab[idx2];
-                            if (s2 < 256u) v |= (s2 << 13) | ((uint32_t)(l + l2) << 21);
+                    uint32_t s2 = 0, s3 = 0, cnt = 1, total = (uint32_t)l;
+                    if (s1 < 256u && total < FZ_LUT_BITS) {
+                        l = fz_decode_idx(inf.LL, e >> total, idx);
+                        if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && sm->tab[idx] < 256u) {
+                            s2 = sm->tab[idx]; total += l; cnt = 2;
+                            if (total < FZ_LUT_BITS) {
+                                l = fz_decode_idx(inf.LL, e >> total, idx);
+                                if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && sm->tab[idx] < 256u) {
+                                    s3 = sm->tab[idx]; total += l; cnt = 3;
+                                }
+                            }
                         }
                     }
+                    v = FZ_LUT_ENTRY(s1, s2, s3, total, cnt);
                 }
                 sm->lut[e] = v;
             }
@@ -1075,17 +1080,16 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     while (__any_sync(0xffffffffu, live)) {
         if (live) {
             if (inf.in_body && lut) {
-                // fast run: up to 16 table-hit literals without leaving registers or re-voting
+                // fast run: up to 16 table hits (1-3 literals each) without leaving registers or re-voting
 #pragma unroll 1
                 for (int it = 0; it < 16; ++it) {
                     inf.br.refill();
                     const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
-                    const uint32_t sym = e & 511u, tot = e >> 21;
-                    const uint32_t nsym = tot ? 2u : 1u;
-                    if (e == 0 || sym >= 256u || inf.bw.op + nsym > inf.bw.cap) break;
-                    inf.br.drop((int)(tot ? tot : ((e >> 9) & 15u)));
-                    inf.bw.put(sym);
-                    if (tot) inf.bw.put((e >> 13) & 255u);
+                    const uint32_t cnt = e >> 29;
+                    if (e == 0 || (e & 511u) >= 256u || inf.bw.op + cnt > inf.bw.cap) break;
+                    inf.br.drop((int)((e >> 25) & 15u));
+                    // sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that count)
+                    inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
                 }
             }
             live = inf.step_lut(lut);  // whatever comes next: long code, match, end of block, block header
