@@ -33,7 +33,11 @@
 #define FZ_SUB (1u << FZ_SUB_LOG2)        // 16 KiB (8 KiB: +5 % speed at 4 GiB, 2x decode speed on small inputs, +0.5..1.5 % size)
 #define FZ_SLOT_STRIDE (FZ_SUB + 32u)     // scratch bytes reserved per encoded sub-block
 #define FZ_GROUP_SUBS 32u                 // sub-blocks that share one Huffman code (= one warp of the inflater)
-#define FZ_STORED_OVERHEAD 10u            // 5 (stored header) + 5 (empty stored block)
+// A stored sub-block is written as TWO stored blocks (5-byte headers) + the empty stored block (5 bytes): the
+// split point is chosen so that the raw bytes can never show the sync marker 00 00 FF FF to the inflater's
+// marker scan (see fz_stored_split).  One-byte sub-blocks use a single stored block.
+#define FZ_STORED_OVERHEAD 15u
+#define FZ_MARKER_LE 0xFFFF0000u          // bytes 00 00 FF FF read as a little-endian uint32
 #define FZ_SIZE_STORED_FLAG 0x80000000u   // in the per-sub-block size word: emit as stored block
 
 #define FZ_MAX_MATCH 258
@@ -112,4 +116,23 @@ FZ_HD uint32_t fz_dist_base(uint32_t dc)
     if (dc < 4) return dc + 1;
     uint32_t eb = (dc - 2) >> 1;
     return 1 + ((2 + (dc & 1)) << eb);
+}
+
+FZ_HD uint32_t fz_stored_size(uint32_t n) { return n >= 2 ? n + FZ_STORED_OVERHEAD : n + 10u; }
+
+// Split point s (1 <= s <= n-1) of a stored sub-block of n >= 2 bytes.  `first` = offset of the first
+// 00 00 FF FF inside the data, or >= n if there is none.  Splitting inside the four bytes breaks the
+// pattern (a 5-byte block header lands in the middle); LEN values of 255 are avoided because
+// `.. 00 | FF 00 | 00 FF | FF ..` (LEN = 0x00FF followed by a data byte FF) would spell the marker.
+FZ_HD uint32_t fz_stored_split(uint32_t n, uint32_t first)
+{
+    if (first < n) {
+        for (uint32_t k = 0; k < 3; k++) {
+            const uint32_t s = first + (k == 0 ? 2u : (k == 1 ? 1u : 3u));
+            if (s >= 1 && s <= n - 1 && s != 255 && n - s != 255) return s;
+        }
+    }
+    uint32_t s = n / 2;
+    while (s == 255 || n - s == 255) s++;  // at most two steps; n >= 2 keeps 1 <= s <= n - 1 (n - s == 255 needs n >= 510)
+    return s;
 }

@@ -596,7 +596,8 @@ struct FzEmitState {
     uint32_t lane_bits[32];
     uint32_t fw_idx[32], fw_bits[32], tw_bits[32], crossed[32];
     uint32_t total_bits;
-    uint32_t pad[3];
+    uint32_t false_marker;  // the fragment contains 00 00 FF FF before its final four bytes
+    uint32_t pad[2];
 };
 
 template <class Load16, class LoadByte>
@@ -660,6 +661,25 @@ FZ_HD void fz_ph_merge(FzEmitState *es, uint32_t *out, int lane)
     }
 }
 
+// Does the emitted fragment show the sync marker anywhere but in its last four bytes?  (About one
+// fragment in a million does; the inflater finds sub-blocks by that marker, so such a fragment is
+// emitted stored instead.)  out[] was written by this warp; volatile reads keep L1 out of the way.
+FZ_HD void fz_ph_check_marker(FzEmitState *es, const uint32_t *out, uint32_t total_bytes, int lane)
+{
+    const volatile uint32_t *o = (const volatile uint32_t *)out;
+    const uint32_t nwords = (total_bytes + 3) / 4;
+    bool hit = false;
+    for (uint32_t i = lane; i < nwords; i += 32) {
+        const uint32_t w0 = o[i];
+        const uint32_t w1 = (i + 1 < nwords) ? o[i + 1] : 0u;
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t v = k ? ((w0 >> (8 * k)) | (w1 << (32 - 8 * k))) : w0;
+            if (v == FZ_MARKER_LE && i * 4 + k + 4 < total_bytes) hit = true;  // position + 4 == total_bytes is the real one
+        }
+    }
+    if (hit) es->false_marker = 1;
+}
+
 // -------------------------------------------------------------------------------------------------
 // Emit one sub-block with its group's code.  Returns the fragment size in bytes, or
 // n + FZ_STORED_OVERHEAD with FZ_SIZE_STORED_FLAG set when a stored block is smaller; then nothing is
@@ -673,15 +693,17 @@ FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, const uint32_t *hdr, FzEm
                                 const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
 {
     (void)lane;
-    const uint32_t stored = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG;
+    const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
     if (gc->stored) return stored;
     FZ_PHASE(fz_ph_count(gc, es, ld, lb, n, lane));
     uint32_t bits = gc->cl[FZ_EOB] >> 16;
     for (int l = 0; l < 32; l++) bits += es->lane_bits[l];
     // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
     const uint32_t dyn_bytes = (bits + 3 + 7) / 8 + 4;
-    if (dyn_bytes >= n + FZ_STORED_OVERHEAD) return stored;
-    FZ_PHASE(fz_ph_emit(gc, hdr, es, ld, lb, n, out, lane));
+    if (dyn_bytes >= fz_stored_size(n)) return stored;
+    FZ_PHASE(if (lane == 0) es->false_marker = 0; fz_ph_emit(gc, hdr, es, ld, lb, n, out, lane));
     FZ_PHASE(fz_ph_merge(es, out, lane));
+    FZ_PHASE(fz_ph_check_marker(es, out, es->total_bits / 8, lane));
+    if (es->false_marker) return stored;
     return es->total_bits / 8;
 }

@@ -457,7 +457,7 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         const float bits = 11.f - acc * (1.f / 2048.f);  // log2(2048) - sum f log2 f / N
         if (bits > FZ_SAMPLE_BITS) {
-            if (lane == 0) { sizes[t] = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
+            if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
             return;
         }
         __syncwarp();
@@ -518,7 +518,7 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     if (sizes[t] & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
     const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
     if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to stage or emit
-        if (lane == 0) { sizes[t] = (n + FZ_STORED_OVERHEAD) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
+        if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
         return;
     }
     FzEmitSmem *sm = (FzEmitSmem *)fz_smem + warp;
@@ -697,15 +697,59 @@ fz_gather_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__
     dst += sub_off[t];
     const uint32_t sz = sizes[t];
     if (sz & FZ_SIZE_STORED_FLAG) {
-        // stored block (BFINAL=0, BTYPE=00, LEN, NLEN) + data + empty stored block
+        // two stored blocks (BFINAL=0, BTYPE=00, LEN, NLEN, data) + empty stored block; the split point breaks a
+        // sync-marker pattern in the raw bytes, if there is one (fz_stored_split)
+        if (n < 2) {
+            if (lane == 0) {
+                dst[0] = 0x00; dst[1] = (uint8_t)n; dst[2] = 0; dst[3] = (uint8_t)~n; dst[4] = 0xFF;
+                for (uint32_t i = 0; i < n; i++) dst[5 + i] = psrc[i];
+                uint8_t *t5 = dst + 5 + n;
+                t5[0] = 0x00; t5[1] = 0x00; t5[2] = 0x00; t5[3] = 0xFF; t5[4] = 0xFF;
+            }
+            return;
+        }
+        uint32_t first = 0xFFFFFFFFu;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32 * 16) {   // warp-uniform trip count
+            const uint32_t i = i0 + lane * 16;
+            uint32_t m = 0;
+            if (i < n) {
+                // 16 candidate positions i .. i+15 need bytes [i, i+19); psrc is 16-byte aligned or handled bytewise
+                uint32_t W[5];
+                if (((uintptr_t)psrc & 3u) == 0) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) W[k] = (i + 4 * k < n) ? *(const uint32_t *)(psrc + i + 4 * k) : 0u;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        uint32_t v = 0;
+                        for (int b = 0; b < 4; b++) if (i + 4 * k + b < n) v |= (uint32_t)psrc[i + 4 * k + b] << (8 * b);
+                        W[k] = v;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const uint32_t v = __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], (b & 3) * 8);
+                    if (v == FZ_MARKER_LE && i + b + 4 <= n) m |= 1u << b;
+                }
+            }
+            const uint32_t any = __ballot_sync(0xffffffffu, m != 0);
+            if (any && first == 0xFFFFFFFFu) {
+                const int src_lane = __ffs((int)any) - 1;
+                const uint32_t mm = __shfl_sync(0xffffffffu, m, src_lane);
+                first = i0 + (uint32_t)src_lane * 16 + (uint32_t)(__ffs((int)mm) - 1);
+            }
+        }
+        const uint32_t s = fz_stored_split(n, first);
+        const uint32_t r = n - s;
         if (lane == 0) {
-            dst[0] = 0x00;
-            dst[1] = (uint8_t)n; dst[2] = (uint8_t)(n >> 8);
-            dst[3] = (uint8_t)~n; dst[4] = (uint8_t)(~n >> 8);
-            uint8_t *t5 = dst + 5 + n;
+            dst[0] = 0x00; dst[1] = (uint8_t)s; dst[2] = (uint8_t)(s >> 8); dst[3] = (uint8_t)~s; dst[4] = (uint8_t)(~s >> 8);
+            uint8_t *h2 = dst + 5 + s;
+            h2[0] = 0x00; h2[1] = (uint8_t)r; h2[2] = (uint8_t)(r >> 8); h2[3] = (uint8_t)~r; h2[4] = (uint8_t)(~r >> 8);
+            uint8_t *t5 = dst + 10 + n;
             t5[0] = 0x00; t5[1] = 0x00; t5[2] = 0x00; t5[3] = 0xFF; t5[4] = 0xFF;
         }
-        fz_warp_copy(dst + 5, psrc, n, psrc + n + 32, lane);
+        fz_warp_copy(dst + 5, psrc, s, psrc + n + 32, lane);
+        fz_warp_copy(dst + 10 + s, psrc + s, r, psrc + n + 32, lane);
     } else {
         const uint8_t *ssrc = scratch + (uint64_t)t * FZ_SLOT_STRIDE;
         fz_warp_copy(dst, ssrc, sz, ssrc + FZ_SLOT_STRIDE, lane);

@@ -20,14 +20,24 @@ struct HostLoadByte {
     uint32_t operator()(uint32_t i) const { return p[i]; }
 };
 
-// what the gather kernel synthesises for a stored sub-block: stored block + empty stored block
+// what the gather kernel synthesises for a stored sub-block: two stored blocks + empty stored block
 size_t put_stored(uint8_t *o, const uint8_t *in, uint32_t n)
 {
     uint8_t *b = o;
-    *o++ = 0x00;
-    *o++ = (uint8_t)(n & 0xff); *o++ = (uint8_t)(n >> 8);
-    *o++ = (uint8_t)(~n & 0xff); *o++ = (uint8_t)((~n >> 8) & 0xff);
-    memcpy(o, in, n); o += n;
+    auto hdr = [&](uint32_t len) {
+        *o++ = 0x00;
+        *o++ = (uint8_t)(len & 0xff); *o++ = (uint8_t)(len >> 8);
+        *o++ = (uint8_t)(~len & 0xff); *o++ = (uint8_t)((~len >> 8) & 0xff);
+    };
+    if (n < 2) { hdr(n); memcpy(o, in, n); o += n; }
+    else {
+        uint32_t first = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i + 4 <= n; i++)
+            if (in[i] == 0 && in[i + 1] == 0 && in[i + 2] == 0xFF && in[i + 3] == 0xFF) { first = i; break; }
+        const uint32_t s = fz_stored_split(n, first);
+        hdr(s); memcpy(o, in, s); o += s;
+        hdr(n - s); memcpy(o, in + s, n - s); o += n - s;
+    }
     *o++ = 0x00; *o++ = 0x00; *o++ = 0x00; *o++ = 0xFF; *o++ = 0xFF;
     return (size_t)(o - b);
 }
@@ -79,7 +89,7 @@ uint64_t hm_encode_stream(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t 
             memset(es, 0xAB, sizeof(FzEmitState));
             const uint32_t r = fz_emit_subblock(gc, gc->hdr, es, ld, lb, m, slot.data(), 0);
             if (r & FZ_SIZE_STORED_FLAG) {
-                if (o + m + FZ_STORED_OVERHEAD > cap) return (uint64_t)-1;
+                if (o + fz_stored_size(m) > cap) return (uint64_t)-1;
                 o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
                 ns++;
             } else {
@@ -109,6 +119,18 @@ int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_ca
     *in_used = used;
     return rc;
 }
+
+// test hooks: the false-marker check of the emit stage, and the stored form
+uint32_t hm_check_marker(const uint8_t *frag, uint32_t total_bytes)
+{
+    std::vector<uint32_t> w((total_bytes + 7) / 4 + 1, 0);
+    memcpy(w.data(), frag, total_bytes);
+    FzEmitState es;
+    memset(&es, 0, sizeof es);
+    for (int lane = 0; lane < 32; lane++) fz_ph_check_marker(&es, w.data(), total_bytes, lane);
+    return es.false_marker;
+}
+uint32_t hm_put_stored(const uint8_t *in, uint32_t n, uint8_t *out) { return (uint32_t)put_stored(out, in, n); }
 
 uint32_t hm_sub_bytes(void) { return FZ_SUB; }
 uint32_t hm_group_subs(void) { return FZ_GROUP_SUBS; }

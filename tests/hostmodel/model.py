@@ -29,3 +29,21 @@ def inflate(b: np.ndarray, n_out: int):
     on, used = C.c_uint32(), C.c_uint64()
     rc = _L.hm_inflate(b.ctypes.data, b.size, out.ctypes.data, n_out, C.byref(on), C.byref(used))
     return rc, out[:on.value].copy(), int(used.value)
+
+
+_L.hm_check_marker.restype = C.c_uint32
+_L.hm_check_marker.argtypes = [C.c_void_p, C.c_uint32]
+_L.hm_put_stored.restype = C.c_uint32
+_L.hm_put_stored.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+
+
+def check_marker(frag: np.ndarray) -> bool:
+    frag = np.ascontiguousarray(frag, dtype=np.uint8)
+    return bool(_L.hm_check_marker(frag.ctypes.data, frag.size))
+
+
+def put_stored(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    out = np.empty(a.size + 32, dtype=np.uint8)
+    n = _L.hm_put_stored(a.ctypes.data, a.size, out.ctypes.data)
+    return out[:n].copy()

@@ -205,6 +205,37 @@ def test_model_inflater_rejects_garbage(hostmodel):
     assert rc != 0
 
 
+def test_model_no_false_sync_markers(hostmodel):
+    """The inflater finds sub-blocks by the marker 00 00 FF FF, so the encoder must never show it elsewhere."""
+    MARK = bytes([0, 0, 0xFF, 0xFF])
+    rng = np.random.default_rng(11)
+    # (a) the check the emit stage runs on a coded fragment
+    frag = rng.integers(1, 255, 5000).astype(np.uint8)
+    frag[-4:] = np.frombuffer(MARK, np.uint8)
+    assert not hostmodel.check_marker(frag)
+    for pos in (0, 1, 2, 3, 777, 4990, 4995):
+        bad = frag.copy()
+        bad[pos:pos + 4] = np.frombuffer(MARK, np.uint8)
+        assert hostmodel.check_marker(bad), pos
+    # (b) the stored form: two stored blocks whose split breaks a marker inside the raw bytes
+    for n in (1, 2, 3, 5, 254, 255, 256, 257, 509, 510, 511, 512, 8192, 16384):
+        for pos in (None, 0, 1, 2, 3, 120, 251, 252, 253, 254, 255, 256, max(0, n // 2 - 2), max(0, n - 4)):
+            a = rng.integers(1, 255, n).astype(np.uint8)
+            a[0] = 0xFF
+            if pos is not None and pos + 4 <= n:
+                a[pos:pos + 4] = np.frombuffer(MARK, np.uint8)
+            st = hostmodel.put_stored(a)
+            assert st.size == (n + 15 if n >= 2 else n + 10)
+            assert zlib.decompressobj(-15).decompress(st.tobytes()) == a.tobytes()
+            assert st.tobytes().find(MARK) == st.size - 4, (n, pos)
+    # (c) whole streams: markers only at sub-block ends
+    for name in ("rand", "zeros", "skew", "runs", "G_p3", "mid_entropy"):
+        a = _plane_cases()[name]
+        c, _ = hostmodel.encode_stream(a)
+        nsub = -(-a.size // hostmodel.SUB)
+        assert c.tobytes().count(MARK) == nsub, name
+
+
 def test_model_bfinal_and_history_rules(hostmodel):
     a = np.tile(np.arange(50, dtype=np.uint8), 400)                # long-distance matches under the default strategy
     co = zlib.compressobj(6, zlib.DEFLATED, -15, 9)
