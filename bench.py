@@ -340,6 +340,7 @@ def run_b200(a):
         cap = Codec.compress_bound(nwords)
         h_cont = torch.empty(cap, dtype=torch.uint8).pin_memory()
         h_out = torch.empty(nwords, dtype=torch.int32).pin_memory()
+        h_ref = (words[exempt:exempt + 65536] & mask).cpu().numpy()
         torch.cuda.synchronize()
 
         def e2e_step():
@@ -359,7 +360,8 @@ def run_b200(a):
         dt = torch.tensor([(time.perf_counter() - w0) / k2], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_ok = bool(np.array_equal(h_out.numpy()[exempt:exempt + 4096] , (words[exempt:exempt + 4096] & mask).cpu().numpy()))
+        e2e_ok = bool(got == nwords and np.array_equal(h_out.numpy()[exempt:exempt + 65536], h_ref) and
+                      np.array_equal(h_out.numpy()[-4096:], (words[-4096:] & mask).cpu().numpy()))
         e2e = {"value": total_bytes / float(dt) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nwords * 4 + sz),
                "d2h_bytes_per_step": int(sz + nwords * 4), "steps": k2, "ok": e2e_ok,
                "api": "mzb_compress_host + mzb_decompress_host on pinned host buffers"}
