@@ -222,10 +222,12 @@ struct FzEmitSink {
     }
     FZ_HD void literal16(const FzVec16 &v)
     {
+        // two codes (<= 15 bits each) per append
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const uint32_t e = cl[FZ_BYTE_OF(v, k)];
-            bw.put(e & 0xffffu, e >> 16);
+        for (int k = 0; k < 16; k += 2) {
+            const uint32_t e0 = cl[FZ_BYTE_OF(v, k)], e1 = cl[FZ_BYTE_OF(v, k + 1)];
+            const uint32_t l0 = e0 >> 16;
+            bw.put((e0 & 0xffffu) | ((e1 & 0xffffu) << l0), l0 + (e1 >> 16));
         }
     }
     FZ_HD void match(uint32_t mlen)
