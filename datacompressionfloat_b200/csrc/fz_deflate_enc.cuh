@@ -72,6 +72,29 @@ struct FzEncState {
 // -------------------------------------------------------------------------------------------------
 #define FZ_HOLD_AFTER 6
 
+FZ_HD int fz_ctz32(uint32_t v)  // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
+FZ_HD uint32_t fz_byte_dyn(const FzVec16 &v, uint32_t k)  // byte k (0..15) of a register-resident group
+{
+    const uint32_t w = k < 8 ? (k < 4 ? v.w[0] : v.w[1]) : (k < 12 ? v.w[2] : v.w[3]);
+    return (w >> ((k & 3) * 8)) & 0xffu;
+}
+
+// number of consecutive bits equal to bit 0 of x, starting at bit 0 (x != 0 and x != ~0 is not required: capped by `width`)
+FZ_HD uint32_t fz_run_len(uint32_t x, uint32_t width)
+{
+    const uint32_t y = (x & 1u) ? ~x : x;  // now the run is a run of zeros
+    const uint32_t r = y ? (uint32_t)fz_ctz32(y) : 32u;
+    return r < width ? r : width;
+}
+
 template <class Load16, class LoadByte, class Sink>
 FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
 {
@@ -98,25 +121,48 @@ FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, u
             uint32_t held = ext;
 #pragma unroll
             for (int j = 1; j <= FZ_HOLD_AFTER; j++) held &= ext << j;
-            held >>= FZ_HOLD_AFTER;  // 16 bits
-            if (held == 0 && m == 0) {          // (A) sixteen literals
-                sink.literal16(v);
-                // repeats at the end of the group: trailing ones of the flag word, saturated
-                const uint32_t inv = ~(ext >> FZ_HOLD_AFTER) & 0xffffu;        // zero flag = run break
-                uint32_t t = inv ? (uint32_t)(15 - fz_ilog2(inv)) : 16u + rep;  // flags set after the last break
-                rep = t > FZ_HOLD_AFTER ? FZ_HOLD_AFTER : t;
-                prev = p;
-                continue;
+            held >>= FZ_HOLD_AFTER;  // 16 bits: byte k of the group is withheld
+            if (!Sink::kOrdered) {
+                // token order is irrelevant (histogram, bit count): every byte that is not withheld is a literal,
+                // all lanes run the same code whatever their data; runs are book-kept below (rare)
+                sink.literal_masked(v, ~held & 0xffffu);
+            } else if (held == 0 && m == 0) {
+                sink.literal16(v);                 // the common case of the ordered (emitting) pass
             }
-            if (held == 0xffffu) {               // (B) the whole group continues a run that is already being withheld
-                m += 16;
-                if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
-                continue;                        // prev unchanged, rep stays saturated
+            if (held | m) {
+                // runs: walk the alternating segments of `held`
+                uint32_t pos = 0;
+                while (pos < 16) {
+                    const uint32_t rest = held >> pos;
+                    const uint32_t r = fz_run_len(rest, 16 - pos);
+                    if (rest & 1u) {               // withheld bytes
+                        m += r;
+                        pos += r;
+                        if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
+                        if (pos < 16) {            // the run ends inside the group
+                            if (m >= FZ_MIN_MATCH) sink.match(m); else if (m) sink.literal(fz_byte_dyn(v, pos - 1), m);
+                            m = 0;
+                        }
+                    } else {                       // ordinary bytes
+                        if (m) {                   // a run carried over from the previous group ends here (pos == 0)
+                            if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
+                            m = 0;
+                        }
+                        if (Sink::kOrdered)
+                            for (uint32_t k = pos; k < pos + r; k++) sink.literal(fz_byte_dyn(v, k), 1);
+                        pos += r;
+                    }
+                }
             }
+            // repeats at the end of the group: trailing ones of the flag word, saturated
+            const uint32_t inv = ~(ext >> FZ_HOLD_AFTER) & 0xffffu;        // zero flag = run break
+            const uint32_t t = inv ? (uint32_t)(15 - fz_ilog2(inv)) : 16u + rep;  // flags set after the last break
+            rep = t > FZ_HOLD_AFTER ? FZ_HOLD_AFTER : t;
+            prev = p;
+            continue;
         }
-        // (C) a run starts or ends inside the group, or the ragged tail: byte by byte (rolled: keeps the code small)
-        const uint32_t cnt = lim < 16 ? lim : 16;
-        for (uint32_t k = 0; k < cnt; k++) {
+        // ragged tail (< 16 bytes): byte by byte
+        for (uint32_t k = 0; k < lim; k++) {
             const int c = (int)lb(i + k);
             const bool e = c == prev;
             if (e && rep >= FZ_HOLD_AFTER) {
@@ -149,7 +195,13 @@ FZ_HD void fz_atomic_add(uint32_t *p, uint32_t v)
 #define FZ_BYTE_OF(v, k) (((v).w[(k) >> 2] >> (((k) & 3) * 8)) & 0xffu)
 
 struct FzHistSink {
+    static constexpr bool kOrdered = false;
     uint32_t *hist;  // 288 counters (shared memory on the GPU)
+    FZ_HD void literal_masked(const FzVec16 &v, uint32_t mask)
+    {
+#pragma unroll
+        for (int k = 0; k < 16; k++) if ((mask >> k) & 1u) fz_atomic_add(&hist[FZ_BYTE_OF(v, k)], 1);
+    }
     FZ_HD void literal(uint32_t c, uint32_t n) { fz_atomic_add(&hist[c], n); }
     FZ_HD void literal16(const FzVec16 &v)
     {
@@ -166,8 +218,16 @@ struct FzHistSink {
 
 // cl[sym] = bit-reversed code | code length << 16
 struct FzCountSink {
+    static constexpr bool kOrdered = false;
     const uint32_t *cl;
     uint32_t bits;
+    FZ_HD void literal_masked(const FzVec16 &v, uint32_t mask)
+    {
+        uint32_t b = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) b += ((mask >> k) & 1u) ? (cl[FZ_BYTE_OF(v, k)] >> 16) : 0u;
+        bits += b;
+    }
     FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * (cl[c] >> 16); }
     FZ_HD void literal16(const FzVec16 &v)
     {
@@ -213,8 +273,10 @@ struct FzBitWriter {
 };
 
 struct FzEmitSink {
+    static constexpr bool kOrdered = true;
     const uint32_t *cl;
     FzBitWriter bw;
+    FZ_HD void literal_masked(const FzVec16 &, uint32_t) {}
     FZ_HD void literal(uint32_t c, uint32_t n)
     {
         const uint32_t e = cl[c];
