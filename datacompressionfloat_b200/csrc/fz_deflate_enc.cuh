@@ -25,6 +25,13 @@
 #define FZ_PHASE(stmt) do { for (int lane = 0; lane < 32; ++lane) { stmt; } } while (0)
 #endif
 
+// true if `pred` holds on every lane of the warp that is executing this line (the host model has one lane at a time)
+#if defined(__CUDA_ARCH__)
+#define FZ_WARP_ALL(pred) (__all_sync(__activemask(), (pred)) != 0)
+#else
+#define FZ_WARP_ALL(pred) (pred)
+#endif
+
 struct FzVec16 { uint32_t w[4]; };
 
 // Per-warp encoder state.  ~7.3 KB; lives in shared memory on the GPU.
@@ -125,7 +132,8 @@ FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, u
             if (!Sink::kOrdered) {
                 // token order is irrelevant (histogram, bit count): every byte that is not withheld is a literal,
                 // all lanes run the same code whatever their data; runs are book-kept below (rare)
-                sink.literal_masked(v, ~held & 0xffffu);
+                // (when no lane of the warp withholds anything the unpredicated form is a little cheaper)
+                if (FZ_WARP_ALL(held == 0)) sink.literal16(v); else sink.literal_masked(v, ~held & 0xffffu);
             } else if (held == 0 && m == 0) {
                 sink.literal16(v);                 // the common case of the ordered (emitting) pass
             }
