@@ -133,7 +133,8 @@ FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, u
                 // token order is irrelevant (histogram, bit count): every byte that is not withheld is a literal,
                 // all lanes run the same code whatever their data; runs are book-kept below (rare)
                 // (when no lane of the warp withholds anything the unpredicated form is a little cheaper)
-                if (FZ_WARP_ALL(held == 0)) sink.literal16(v); else sink.literal_masked(v, ~held & 0xffffu);
+                if (FZ_WARP_ALL(held == 0)) sink.literal16(v);
+                else if (!FZ_WARP_ALL(held == 0xffffu)) sink.literal_masked(v, ~held & 0xffffu);  // (all-run groups: nothing)
             } else if (held == 0 && m == 0) {
                 sink.literal16(v);                 // the common case of the ordered (emitting) pass
             }
