@@ -70,51 +70,60 @@ def gen_words(kind: str, nwords: int, seed_offset: int, device):
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every few ms by a thread (NVML) while the GPU is under load:
+    from the first warm-up step to the end of the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.timed = None   # (t0, t1) of the timed region, perf_counter
+        self.err = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+                time.sleep(0.004)
+        except Exception as ex:  # pragma: no cover
+            self.err = repr(ex)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"no samples ({self.err})"]}
+        sm = [m for _, m, _ in self.samples]
+        bits = 0
+        for _, _, r in self.samples:
+            bits |= r
+        in_timed = [m for t, m, _ in self.samples if self.timed and self.timed[0] <= t <= self.timed[1]]
+        return {"sm_mhz": float(np.median(in_timed if in_timed else sm)), "sm_max_mhz": float(getattr(self, "max_mhz", max(sm))),
+                "samples": len(sm), "samples_in_timed_region": len(in_timed), "window": "first warm-up step .. end of the timed region",
+                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k)}
 
 
 # ----------------------------------------------------------------------------- CPU baseline: the reference on the host cores
@@ -311,11 +320,13 @@ def run_b200(a):
     timed = []
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
     t0.record()
     for _ in range(a.steps):
         step(timed)
     t1.record()
     barrier()
+    sampler.timed = (wall0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = t0.elapsed_time(t1)
     comp_ms = float(np.mean([e[0].elapsed_time(e[1]) for e, _, _ in timed]))
