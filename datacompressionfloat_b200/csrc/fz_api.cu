@@ -375,6 +375,34 @@ static void decompress_enqueue_batch(mzb_ctx *c, const uint8_t *d_in, size_t in_
 }
 
 // ---------------------------------------------------------------------------------------------------
+static void fill_compress_stats(mzb_ctx *c, uint64_t nwords, uint64_t nchunks_total, uint32_t launches)
+{
+    c->stats.bytes_in = nwords * 4;
+    c->stats.bytes_out = c->h_status->out_end;
+    c->stats.chunks = (uint32_t)nchunks_total;
+    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
+    c->stats.raw_streams = c->h_status->n_raw_streams;
+    c->stats.stored_subblocks = c->h_status->n_stored_sub;
+    c->stats.kernel_launches = launches;
+}
+
+static void fill_decompress_stats(mzb_ctx *c, uint64_t bytes_in, uint64_t nwords, uint64_t nchunks_total, uint32_t launches)
+{
+    c->stats.bytes_in = bytes_in;
+    c->stats.bytes_out = nwords * 4;
+    c->stats.chunks = (uint32_t)nchunks_total;
+    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
+    c->stats.general_streams = c->h_status->n_general;
+    c->stats.fast_failed = c->h_status->n_fast_failed;
+    c->stats.kernel_launches = launches;
+}
+
+static uint32_t compress_launches(uint64_t nw) { return 7 + ((nw & 3) ? 1 : 0); }
+static uint32_t decompress_launches(uint64_t nw, bool in_place_raw)
+{
+    return 1 + 8 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+}
+
 extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,
                                    uint32_t chk, uint64_t fsz, int write_file_header, void *d_out, size_t out_cap,
                                    uint64_t *out_size)
@@ -387,16 +415,9 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
     FZ_CHECK(cudaSetDevice(c->device));
     const uint64_t nchunks_total = (nwords + chk - 1) / chk;
     const uint32_t bmax = (uint32_t)(nchunks_total < batch_chunks_for(c, chk) ? nchunks_total : batch_chunks_for(c, chk));
-    const uint64_t pstride = plane_stride_for(bmax, chk);
-    const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
-    const size_t nslots = (size_t)bmax * FZ_PLANES * nsub_full;
+    uint64_t pstride;
     int rc;
-    if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->scratch, nslots * FZ_SLOT_STRIDE + 256)) ||
-        (rc = ensure(c->sizes, nslots * 4)) || (rc = ensure(c->sub_off, nslots * 4)) ||
-        (rc = ensure(c->stream_hdr, (size_t)bmax * FZ_PLANES * 4)) || (rc = ensure(c->stream_off, (size_t)bmax * FZ_PLANES * 8)))
-        return rc;
-    const size_t ngroups = (size_t)bmax * FZ_PLANES * ((nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
-    if ((rc = ensure(c->ghist, ngroups * 288 * 4)) || (rc = ensure(c->gcodes, ngroups * fz_group_code_bytes()))) return rc;
+    if ((rc = compress_reserve(c, bmax, chk, &pstride))) return rc;
 
     uint64_t start = 0;
     if (write_file_header) {
@@ -419,31 +440,13 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
         const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
         const uint64_t w0 = c0 * chk;
         const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
-        const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
         const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
-        fz_launch_split((const uint32_t *)d_words + w0, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
-        prof_mark(c, FZ_ST_SPLIT);
-        fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p,
-                         (uint32_t *)c->sizes.p, c->d_status, c->stream);
-        prof_mark(c, FZ_ST_ENCODE);
-        fz_launch_layout((const uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
-                         (unsigned long long *)c->stream_off.p, (uint8_t *)d_out, out_cap, c->d_status, c->stream);
-        prof_mark(c, FZ_ST_LAYOUT);
-        fz_launch_gather((const uint8_t *)c->planes.p, (const uint8_t *)c->scratch.p, (const uint32_t *)c->sizes.p,
-                         (const uint32_t *)c->sub_off.p, (const uint32_t *)c->stream_hdr.p,
-                         (const unsigned long long *)c->stream_off.p, g, (uint8_t *)d_out, c->d_status, c->stream);
-        prof_mark(c, FZ_ST_GATHER);
-        launches += 7 + ((nw & 3) ? 1 : 0);
+        compress_enqueue_batch(c, (const uint32_t *)d_words + w0, nw, nb, chk, pstride, mask, exempt, (uint8_t *)d_out, out_cap);
+        launches += compress_launches(nw);
     }
     if ((rc = status_fetch(c))) return rc;
     prof_collect(c);
-    c->stats.bytes_in = nwords * 4;
-    c->stats.bytes_out = c->h_status->out_end;
-    c->stats.chunks = (uint32_t)nchunks_total;
-    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
-    c->stats.raw_streams = c->h_status->n_raw_streams;
-    c->stats.stored_subblocks = c->h_status->n_stored_sub;
-    c->stats.kernel_launches = launches;
+    fill_compress_stats(c, nwords, nchunks_total, launches);
     if (c->h_status->error) return c->h_status->error;
     *out_size = c->h_status->out_end;
     return MZB_OK;
@@ -478,25 +481,10 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
     const uint64_t nchunks_total = (nwords + chk - 1) / chk;
     if (in_size < start + nchunks_total * FZ_CHUNK_HEADER_BYTES) return MZB_E_FORMAT;
     const uint32_t bmax = (uint32_t)(nchunks_total < batch_chunks_for(c, chk) ? nchunks_total : batch_chunks_for(c, chk));
-    const uint64_t pstride = plane_stride_for(bmax, chk);
-    const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
-    const uint32_t nstreams = bmax * FZ_PLANES;
+    uint64_t pstride;
     FzInflateBufs ib;
-    ib.tiles_per_stream = chk / 65536 + 2;  // FZ_TILE_BYTES
-    const size_t ntiles = (size_t)nstreams * ib.tiles_per_stream;
-    ib.hits_cap = (uint32_t)((size_t)nstreams * nsub_full * 2 + 1024);
-    const size_t nbsum = (ntiles + 4095) / 4096 + 4;
     int rc;
-    if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->stream_hdr, (size_t)nstreams * 4)) ||
-        (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
-        (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
-        (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib.hits_cap * 4)))
-        return rc;
-    ib.tile_cnt = (uint32_t *)c->tile_cnt.p;
-    ib.block_sums = (uint32_t *)c->block_sums.p;
-    ib.hits = (uint32_t *)c->hits.p;
-    ib.stream_mode = (uint32_t *)c->stream_mode.p;
-    ib.stream_fail = (uint32_t *)c->stream_fail.p;
+    if ((rc = decompress_reserve(c, bmax, chk, &pstride, &ib))) return rc;
     if ((rc = status_reset(c, start))) return rc;
     const bool in_place_raw = (chk % 16u) == 0;  // merge reads RAW payloads straight from the container
 
@@ -506,29 +494,13 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
         const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
         const uint64_t w0 = c0 * chk;
         const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
-        const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
-        fz_launch_walk((const uint8_t *)d_in, in_size, g, (uint32_t *)c->stream_hdr.p, (unsigned long long *)c->stream_off.p,
-                       c->d_status, c->stream);
-        prof_mark(c, FZ_ST_WALK);
-        fz_launch_inflate((const uint8_t *)d_in, in_size, g, (const uint32_t *)c->stream_hdr.p,
-                          (const unsigned long long *)c->stream_off.p, ib, (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c, !in_place_raw);
-        if (in_place_raw)
-            fz_launch_merge_streams((const uint8_t *)c->planes.p, (const uint8_t *)d_in, (const uint32_t *)c->stream_hdr.p,
-                                    (const unsigned long long *)c->stream_off.p, g, (uint32_t *)d_words_out + w0, c->stream);
-        else
-            fz_launch_merge((const uint8_t *)c->planes.p, pstride, nw, (uint32_t *)d_words_out + w0, c->merge_variant, c->stream);
-        prof_mark(c, FZ_ST_MERGE);
-        launches += 1 + 8 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+        decompress_enqueue_batch(c, (const uint8_t *)d_in, in_size, make_geom(nb, chk, nw, pstride), ib,
+                                 (uint32_t *)d_words_out + w0, in_place_raw);
+        launches += decompress_launches(nw, in_place_raw);
     }
     if ((rc = status_fetch(c))) return rc;
     prof_collect(c);
-    c->stats.bytes_in = c->h_status->out_end;
-    c->stats.bytes_out = nwords * 4;
-    c->stats.chunks = (uint32_t)nchunks_total;
-    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
-    c->stats.general_streams = c->h_status->n_general;
-    c->stats.fast_failed = c->h_status->n_fast_failed;
-    c->stats.kernel_launches = launches;
+    fill_decompress_stats(c, c->h_status->out_end, nwords, nchunks_total, launches);
     if (c->h_status->error) return c->h_status->error;
     *nwords_out = nwords;
     return MZB_OK;
@@ -609,7 +581,7 @@ extern "C" int mzb_compress_host(mzb_ctx *c, const void *h_words, uint64_t nword
             compress_enqueue_batch(c, (const uint32_t *)d_in, nw, nb, chk, pstride, mask, exempt, d_out, bound);
             FZ_CHECK(cudaMemcpyAsync(&c->h_ends[b], &c->d_status->out_end, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
             FZ_CHECK(cudaEventRecord(c->ev_comp[b], c->stream));
-            launches += 7 + ((nw & 3) ? 1 : 0);
+            launches += compress_launches(nw);
         }
         if (b >= 1) {  // batch b-1 is done (or about to be): ship its part of the container while batch b computes
             FZ_CHECK(cudaEventSynchronize(c->ev_comp[b - 1]));
@@ -623,13 +595,7 @@ extern "C" int mzb_compress_host(mzb_ctx *c, const void *h_words, uint64_t nword
     FZ_CHECK(cudaStreamSynchronize(c->s_d2h));
     if ((rc = status_fetch(c))) return rc;
     prof_collect(c);
-    c->stats.bytes_in = nwords * 4;
-    c->stats.bytes_out = c->h_status->out_end;
-    c->stats.chunks = (uint32_t)nchunks_total;
-    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
-    c->stats.raw_streams = c->h_status->n_raw_streams;
-    c->stats.stored_subblocks = c->h_status->n_stored_sub;
-    c->stats.kernel_launches = launches;
+    fill_compress_stats(c, nwords, nchunks_total, launches);
     if (result != MZB_OK) return result;
     if (c->h_status->error) return c->h_status->error;
     *out_size = c->h_status->out_end;
@@ -712,18 +678,12 @@ extern "C" int mzb_decompress_host(mzb_ctx *c, const void *h_in, size_t in_size,
         FZ_CHECK(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
         FZ_CHECK(cudaMemcpyAsync((uint32_t *)h_words_out + w0, d_w, nw * 4, cudaMemcpyDeviceToHost, c->s_d2h));
         FZ_CHECK(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
-        launches += 1 + 8 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+        launches += decompress_launches(nw, in_place_raw);
     }
     FZ_CHECK(cudaStreamSynchronize(c->s_d2h));
     if ((rc = status_fetch(c))) return rc;
     prof_collect(c);
-    c->stats.bytes_in = off;
-    c->stats.bytes_out = nwords * 4;
-    c->stats.chunks = (uint32_t)nchunks_total;
-    c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
-    c->stats.general_streams = c->h_status->n_general;
-    c->stats.fast_failed = c->h_status->n_fast_failed;
-    c->stats.kernel_launches = launches;
+    fill_decompress_stats(c, off, nwords, nchunks_total, launches);
     if (c->h_status->error) return c->h_status->error;
     *nwords_out = nwords;
     return MZB_OK;
