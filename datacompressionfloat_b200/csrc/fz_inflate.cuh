@@ -182,6 +182,30 @@ FZ_HD int fz_decode_idx(const FzCode &r, uint32_t bits15, uint32_t &idx)
     return len <= 15 ? (int)len : 0;
 }
 
+// first-level table entry for the FZ_LUT_BITS-bit pattern e: the first symbol and up to two more literals
+template <class Tab>
+FZ_HD uint32_t fz_lut_entry(const FzCode &LL, const Tab &tab, uint32_t e)
+{
+    uint32_t idx;
+    int l = fz_decode_idx(LL, e, idx);
+    if (!(l >= 1 && l <= FZ_LUT_BITS && idx < 288)) return 0;
+    const uint32_t s1 = tab.L((int)idx);
+    uint32_t s2 = 0, s3 = 0, cnt = 1, total = (uint32_t)l;
+    if (s1 < 256u && total < FZ_LUT_BITS) {
+        l = fz_decode_idx(LL, e >> total, idx);
+        if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && tab.L((int)idx) < 256u) {
+            s2 = tab.L((int)idx); total += l; cnt = 2;
+            if (total < FZ_LUT_BITS) {
+                l = fz_decode_idx(LL, e >> total, idx);
+                if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && tab.L((int)idx) < 256u) {
+                    s3 = tab.L((int)idx); total += l; cnt = 3;
+                }
+            }
+        }
+    }
+    return FZ_LUT_ENTRY(s1, s2, s3, total, cnt);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // The inflater as a resumable state machine: step() does one unit of work (one block header, or one
 // literal/length symbol including its match copy) and returns false when the fragment is finished.
@@ -199,6 +223,7 @@ struct FzInflater {
     int rc;
     bool last, in_body;
     bool shared_tab;  // tables are shared with other lanes: this lane must not rebuild them (no further coded block)
+    uint32_t *own_lut;  // optional FZ_LUT_SIZE-entry table this thread (re)builds after every block header
 
     FZ_HD void start(const uint8_t *in, size_t in_len_, uint8_t *out, uint32_t out_cap, const Tab &t)
     {
@@ -210,12 +235,13 @@ struct FzInflater {
         last = false;
         in_body = false;
         shared_tab = false;
+        own_lut = nullptr;
     }
 
     // returns true while there is more to do
     FZ_HD bool step()
     {
-        if (in_body) return body_symbol(nullptr);
+        if (in_body) return body_symbol(own_lut);
         return block_header();
     }
     FZ_HD bool step_lut(const uint32_t *lut)
@@ -242,9 +268,20 @@ struct FzInflater {
         uint32_t idx, sym;
         int l;
         const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
-        if (e && (e >> 29) == 1u) {   // (multi-literal entries are consumed by the kernel's fast loop only)
+        if (e) {
+            const uint32_t cnt = e >> 29;
             sym = e & 511u;
-            br.drop((int)((e >> 25) & 15u));
+            if (sym < 256u && bw.op + cnt <= bw.cap) {   // 1..3 literals at once
+                br.drop((int)((e >> 25) & 15u));
+                bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
+                return true;
+            }
+            if (cnt > 1) {   // not enough room for all of them: take the first one the slow way
+                l = fz_decode_idx(LL, br.peek(15), idx);
+                if (l == 0) return fail(FZ_INF_E_DATA);
+                br.drop(l);
+                sym = tab.L((int)idx);
+            } else br.drop((int)((e >> 25) & 15u));
         } else {
             l = fz_decode_idx(LL, br.peek(15), idx);
             if (l == 0) return fail(FZ_INF_E_DATA);
@@ -321,6 +358,7 @@ struct FzInflater {
             for (int i = 0; i < 8; i++) tab.L(168 + i) = (uint16_t)(280 + i);
             for (int i = 0; i < 112; i++) tab.L(176 + i) = (uint16_t)(144 + i);
             for (int i = 0; i < 32; i++) tab.D(i) = (uint16_t)i;
+            if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(LL, tab, e);
             in_body = true;
             return true;
         }
@@ -392,6 +430,7 @@ struct FzInflater {
             }
             if (br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
         }
+        if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(LL, tab, e);
         in_body = true;
         return true;
     }
@@ -403,10 +442,11 @@ struct FzInflater {
 // `out` must be 4-byte aligned.  Reads whole aligned 32-bit words around [in, in+in_len).
 template <class Tab>
 FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t out_cap, const Tab &tab,
-                     uint32_t *out_n, size_t *in_used)
+                     uint32_t *out_n, size_t *in_used, uint32_t *lut = nullptr)
 {
     FzInflater<Tab> inf;
     inf.start(in, in_len, out, out_cap, tab);
+    inf.own_lut = lut;  // FZ_LUT_SIZE entries, or none
     while (inf.step()) {}
     return inf.finish(out_n, in_used);
 }

@@ -1093,29 +1093,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                 }
             }
             // first-level table: entry e = the first symbol (and up to two more literals) coded by the bit pattern e
-            for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) {
-                uint32_t idx;
-                int l = fz_decode_idx(inf.LL, e, idx);
-                uint32_t v = 0;
-                if (l >= 1 && l <= FZ_LUT_BITS && idx < 288) {
-                    const uint32_t s1 = sm->tab[idx];
-                    uint32_t s2 = 0, s3 = 0, cnt = 1, total = (uint32_t)l;
-                    if (s1 < 256u && total < FZ_LUT_BITS) {
-                        l = fz_decode_idx(inf.LL, e >> total, idx);
-                        if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && sm->tab[idx] < 256u) {
-                            s2 = sm->tab[idx]; total += l; cnt = 2;
-                            if (total < FZ_LUT_BITS) {
-                                l = fz_decode_idx(inf.LL, e >> total, idx);
-                                if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && sm->tab[idx] < 256u) {
-                                    s3 = sm->tab[idx]; total += l; cnt = 3;
-                                }
-                            }
-                        }
-                    }
-                    v = FZ_LUT_ENTRY(s1, s2, s3, total, cnt);
-                }
-                sm->lut[e] = v;
-            }
+            for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) sm->lut[e] = fz_lut_entry(inf.LL, tab, e);
         }
         __syncwarp();
     }
@@ -1156,6 +1134,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
                           const uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, FzStatus *status)
 {
     __shared__ uint16_t tabs[FZ_INF_TAB_U16];
+    __shared__ uint32_t lut[FZ_LUT_SIZE];
     const uint32_t s = blockIdx.x;
     if (threadIdx.x != 0 || status->error) return;
     const uint32_t mode = stream_mode[s] & 0xffu;
@@ -1169,7 +1148,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     FzInfTab<1> tab{tabs, tabs + 288, tabs + 320};
     uint32_t out_n = 0;
     size_t used = 0;
-    const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used);
+    const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used, lut);
     if (rc != FZ_INF_OK || out_n != n_s) atomicCAS(&status->error, 0, FZ_E_FORMAT);
 }
 

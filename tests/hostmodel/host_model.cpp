@@ -114,7 +114,13 @@ int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_ca
     uint16_t ll[288], dd[32], cnt[32];
     FzInfTab<1> tab{ll, dd, cnt};
     size_t used = 0;
+    // both paths of the general inflater must agree: canonical-only decode and table-driven decode
     int rc = fz_inflate(ip, (size_t)in_len, (uint8_t *)obuf.data(), out_cap, tab, out_n, &used);
+    std::vector<uint32_t> lut(FZ_LUT_SIZE), obuf2(out_cap / 4 + 2, 0);
+    uint32_t out_n2 = 0;
+    size_t used2 = 0;
+    int rc2 = fz_inflate(ip, (size_t)in_len, (uint8_t *)obuf2.data(), out_cap, tab, &out_n2, &used2, lut.data());
+    if (rc2 != rc || out_n2 != *out_n || used2 != used || memcmp(obuf.data(), obuf2.data(), *out_n) != 0) return -99;
     memcpy(out, obuf.data(), *out_n);
     *in_used = used;
     return rc;
