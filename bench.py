@@ -427,6 +427,11 @@ def run_b200(a):
         except Exception as ex:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
 
+    # whole-pipeline view: bytes a perfectly fused implementation would have to move (SURVEY 8d lower bound,
+    # 4 + 4r per word each way) over the measured step time, as a fraction of the measured HBM peak
+    fused_bytes = 2 * (nb + nb * ratio) * world
+    pipeline = {"fused_lower_bound_bytes": fused_bytes, "achieved": fused_bytes / (ms_per_step * 1e-3) / 1e9 / world,
+                "unit": "GB/s per GPU", "frac_of_hbm_peak": fused_bytes / (ms_per_step * 1e-3) / 1e9 / world / peak}
     launches = (state["cs"]["kernel_launches"] + state["ds"]["kernel_launches"]) * a.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -434,7 +439,7 @@ def run_b200(a):
         "dtype": "u8", "data": "synthetic", "config": workload_config(a, nwords),
         "compress_GBs": total_bytes / (comp_ms * 1e-3) / 1e9, "decompress_GBs": total_bytes / (decomp_ms * 1e-3) / 1e9,
         "ratio": total_comp / total_bytes, "ratio_definition": "compressed/original (reference zip.c:434), chunk records only",
-        "bit_exact_roundtrip": ok, "roofline": roofline, "roofline_kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+        "bit_exact_roundtrip": ok, "roofline": roofline, "roofline_kernels": kernels, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
         "decode_stats": {k: state["ds"][k] for k in ("general_streams", "fast_failed")},
         "encode_stats": {k: state["cs"][k] for k in ("raw_streams", "stored_subblocks", "streams")},

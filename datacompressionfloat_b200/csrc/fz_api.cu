@@ -526,7 +526,10 @@ static int host_pipe_init(mzb_ctx *c, size_t nbatches)
 static uint32_t host_batch_chunks(const mzb_ctx *c, uint32_t chk)
 {
     const uint32_t b = batch_chunks_for(c, chk);
-    return b > 24u ? 24u : b;  // finer batches than the device path: more overlap between copies and kernels
+    const char *e = getenv("MRCZIP_HOST_BATCH_CHUNKS");   // tuning knob; default 12 chunks = 288 MiB per batch
+    uint32_t hb = e ? (uint32_t)atoi(e) : 12u;
+    if (hb == 0) hb = 12u;
+    return b > hb ? hb : b;  // finer batches than the device path: more overlap between copies and kernels
 }
 
 extern "C" int mzb_compress_host(mzb_ctx *c, const void *h_words, uint64_t nwords, int bits, uint32_t exempt_words,

@@ -362,3 +362,45 @@ def test_cli_mrc_tar_and_tarx(codec, oracle):
         subprocess.run([tarx, "-i", d / "list.txt", "-o", d / "dry", "-t", "zip", "-n", "2", "-d", "1"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         assert all((d / "dry" / (p.name + ".zip")).stat().st_size == 0 for p, _ in files)
+
+
+# ----------------------------------------------------------------------------- full-size properties (reference chunking, 1 GiB)
+def test_full_size_properties(codec, oracle):
+    """Size-independent properties at the reference's chunk size on a 1 GiB volume (43 chunks, ragged last one)."""
+    n = (1 << 28) + 256 - 777
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    w = torch.randn(n, generator=g, device="cuda").view(torch.int32)
+    w[:256] = 123456789
+    bits = 11
+    cont = codec.compress(w, bits)
+    back = codec.decompress(cont)
+    masked = w.clone(); masked[256:] &= (-1 << bits)
+    assert torch.equal(back, masked)                                   # == erasebytes semantics at full size
+    st = codec.stats()
+    assert st["general_streams"] == 0 and st["fast_failed"] == 0
+    # idempotence: the masked volume compresses to the very same container
+    assert torch.equal(codec.compress(masked, bits), cont)
+    # container structure: header fields, chunk-header chain covers the whole payload, RAW rule per stream
+    h = cont[:17].cpu().numpy()
+    assert int(h[:8].view(np.uint64)[0]) == n * 4 and int(h[8:12].view(np.uint32)[0]) == 6291456
+    c = cont.cpu().numpy()
+    fsz, chk, streams = oracle.parse_container(c)
+    assert len(streams) == 4 * 43 and streams[-1]["offset"] + streams[-1]["len"] == c.size
+    assert all((s["raw"] and s["len"] == s["n"]) or (not s["raw"] and s["n"] > s["len"] + 4) for s in streams)
+    # a sample of streams through the independent inflater and zlib
+    planes = codec.mask_split(w, bits, 256).cpu().numpy()
+    for i in (0, 3, 4 * 21 + 3, 4 * 42 + 0, 4 * 42 + 3):
+        s = streams[i]
+        if s["raw"]:
+            continue
+        cidx, j = divmod(i, 4)
+        want = planes[j, cidx * 6291456: cidx * 6291456 + s["n"]]
+        got = zlib.decompressobj(-15).decompress(c[s["offset"]: s["offset"] + s["len"]].tobytes())
+        assert got == want.tobytes()
+    # chunk-range shards == whole (multi-GPU layout) at the reference chunk size
+    from datacompressionfloat_b200 import chunk_range
+    parts = []
+    for r in range(2):
+        lo, hi = chunk_range(43, r, 2)
+        parts.append(codec.compress(w[lo * 6291456: min(n, hi * 6291456)], bits, exempt_words=256 if r == 0 else 0, write_file_header=False))
+    assert torch.equal(torch.cat([cont[:17]] + parts), cont)
