@@ -41,6 +41,7 @@ class Codec:
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.device = int(device)
+        self._private_stream = stream is None
         if stream is None:   # the context makes its own non-blocking stream
             check(self._L.mzb_create(C.byref(self._h), self.device, None), "mzb_create")
         else:                # a cudaStream_t handle; 0 is the legacy default stream
@@ -99,10 +100,17 @@ class Codec:
         return int(_lib.load().mzb_compress_bound(nwords, chk))
 
     # ------------------------------------------------------------------ device tensors
+    def _order_inputs(self):
+        """A context with a private stream is not ordered after torch's current stream: wait for the producers of
+        the tensors we are about to read (the library synchronises its own stream before returning)."""
+        if self._private_stream:
+            torch.cuda.current_stream(self.device).synchronize()
+
     def _dev_words(self, words):
         _need_torch()
         if not (words.is_cuda and words.is_contiguous() and words.element_size() == 4):
             raise ValueError("words must be a contiguous 4-byte-element CUDA tensor")
+        self._order_inputs()
         return words
 
     def mask_split(self, words, bits: int, exempt_words: int = MRC_HEADER_WORDS, out=None):
@@ -120,6 +128,7 @@ class Codec:
     def merge(self, planes, nwords: int, out=None):
         """planes: uint8 tensor [4, stride] -> int32 tensor [nwords]."""
         _need_torch()
+        self._order_inputs()
         if out is None:
             out = torch.empty(max(nwords, 4), dtype=torch.int32, device=planes.device)
         check(self._L.mzb_merge_device(self._h, planes.data_ptr(), planes.stride(0), nwords, out.data_ptr()),
@@ -145,6 +154,7 @@ class Codec:
         _need_torch()
         if not (container.is_cuda and container.is_contiguous() and container.dtype == torch.uint8):
             raise ValueError("container must be a contiguous uint8 CUDA tensor")
+        self._order_inputs()
         if has_file_header:
             if container.numel() == 0:
                 return torch.empty(0, dtype=torch.int32, device=container.device)

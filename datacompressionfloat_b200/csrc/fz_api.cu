@@ -40,7 +40,7 @@ struct mzb_ctx {
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar;
     // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_comp, ev_d2h;
@@ -89,7 +89,7 @@ static void prof_collect(mzb_ctx *c)  // after the stream was synchronised
 }
 
 static const char *kStageNames[FZ_ST_COUNT] = {"split", "encode", "layout", "gather", "walk", "markers", "classify",
-                                                "inflate_fast", "inflate_general", "rawcopy", "merge"};
+                                                "inflate_fast", "inflate_blockpar", "inflate_general", "rawcopy", "merge"};
 
 extern "C" int mzb_set_profiling(mzb_ctx *c, int on)
 {
@@ -190,7 +190,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
@@ -284,6 +284,7 @@ extern "C" int mzb_mask_split_device(mzb_ctx *c, const void *d_words, uint64_t n
     fz_launch_split((const uint32_t *)d_words, nwords, fz_mask_for_bits(bits), exempt_words, (uint8_t *)d_planes,
                     plane_stride, c->split_variant, c->stream);
     FZ_CHECK(cudaGetLastError());
+    if (c->own_stream) FZ_CHECK(cudaStreamSynchronize(c->stream));  // nobody else can order against a private stream
     return MZB_OK;
 }
 
@@ -294,6 +295,7 @@ extern "C" int mzb_merge_device(mzb_ctx *c, const void *d_planes, uint64_t plane
     FZ_CHECK(cudaSetDevice(c->device));
     fz_launch_merge((const uint8_t *)d_planes, plane_stride, nwords, (uint32_t *)d_words_out, c->merge_variant, c->stream);
     FZ_CHECK(cudaGetLastError());
+    if (c->own_stream) FZ_CHECK(cudaStreamSynchronize(c->stream));
     return MZB_OK;
 }
 
@@ -346,8 +348,10 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
     if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->stream_hdr, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
-        (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib->hits_cap * 4)))
+        (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib->hits_cap * 4)) ||
+        (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams))))
         return rc;
+    ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams);
     ib->tile_cnt = (uint32_t *)c->tile_cnt.p;
     ib->block_sums = (uint32_t *)c->block_sums.p;
     ib->hits = (uint32_t *)c->hits.p;
@@ -394,13 +398,14 @@ static void fill_decompress_stats(mzb_ctx *c, uint64_t bytes_in, uint64_t nwords
     c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
     c->stats.general_streams = c->h_status->n_general;
     c->stats.fast_failed = c->h_status->n_fast_failed;
+    c->stats.blockpar_streams = c->h_status->n_blockpar;
     c->stats.kernel_launches = launches;
 }
 
 static uint32_t compress_launches(uint64_t nw) { return 7 + ((nw & 3) ? 1 : 0); }
 static uint32_t decompress_launches(uint64_t nw, bool in_place_raw)
 {
-    return 1 + 8 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+    return 1 + 8 + 6 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
 }
 
 extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,

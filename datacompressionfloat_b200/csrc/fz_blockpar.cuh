@@ -1,0 +1,520 @@
+// fz_blockpar.cuh -- block-parallel inflate of streams written by zlib (the reference's own containers).
+//
+// A reference payload (reference zip.c:164-196: deflate(level 6, Z_RLE), Z_FULL_FLUSH per chunk) is ~170
+// dynamic-Huffman blocks back to back with no byte alignment between them, so it offers no index.  We
+// recover one:
+//   1. candidates   every bit position is tested for "a dynamic block header starts here": the 17 fixed
+//                   header bits, a complete code-length code, then a full parse of the code lengths with
+//                   complete literal/length code and an end-of-block symbol (false positives are rare and harmless)
+//   2. measure      each candidate block is decoded without storing anything: end bit, output bytes, whether it
+//                   starts with a run that continues from the previous block, its last literal
+//   3. chain        one cheap serial walk per stream: start at bit 0, hop from block end to the candidate that
+//                   starts there (or over a stored block), accumulating output offsets; any inconsistency makes
+//                   the stream fall back to the serial inflater
+//   4. write        every block on the chain is decoded again, now storing at its offset
+// Only distance-1 matches are supported across and inside blocks during the measure pass (what Z_RLE
+// produces); a stream with other distances fails the chain and takes the serial path.
+//
+// `__host__ __device__`: tests/hostmodel runs the same functions on the CPU against zlib streams.
+#pragma once
+#include "fz_inflate.cuh"
+
+struct FzBlockInfo {
+    uint32_t end_bit;   // bit position (in the stream) just after the block's end-of-block symbol
+    uint32_t out_len;   // bytes the block inflates to
+    uint32_t flags;
+    uint32_t last;      // last literal of the block (valid with FZ_BLK_HAS_LITERAL)
+};
+#define FZ_BLK_OK 1u
+#define FZ_BLK_NON_RLE 2u
+#define FZ_BLK_STARTS_WITH_MATCH 4u
+#define FZ_BLK_HAS_LITERAL 8u
+#define FZ_BLK_FINAL 16u
+
+struct FzStoredItem {
+    uint32_t src_byte;  // offset of the data in the stream
+    uint32_t len;
+    uint32_t out_off;
+};
+
+// Kraft weight of three packed 3-bit code lengths: sum of 2^(7-len) over the non-zero ones (<= 192)
+FZ_HD uint32_t fz_kraft3(uint32_t three)
+{
+    uint32_t k = 0;
+    for (int i = 0; i < 3; i++) { const uint32_t v = (three >> (3 * i)) & 7u; if (v) k += 128u >> v; }
+    return k;
+}
+
+// cheap test on the first bits of a would-be dynamic block header; lo = stream bits [p, p+64), hi = [p+64, p+128).
+// kraft_lut: 512 bytes, kraft_lut[x] = fz_kraft3(x) (shared memory on the GPU), or nullptr
+FZ_HD bool fz_block_quick_test(uint64_t lo, uint64_t hi, const uint8_t *kraft_lut = nullptr)
+{
+    if (((lo >> 1) & 3u) != 2u) return false;                 // BTYPE = 10
+    if (((lo >> 3) & 31u) > 29u) return false;                // HLIT  <= 29 (286 codes)
+    if (((lo >> 8) & 31u) > 29u) return false;                // HDIST <= 29
+    const uint32_t ncl = (uint32_t)((lo >> 13) & 15u) + 4u;
+    // the code-length code must be complete (zlib's inflate rejects anything else): sum of 2^(7-len) == 128.
+    // The ncl 3-bit lengths start at bit 17: keep exactly those, nine bits (three lengths) per table lookup.
+    uint64_t f = (lo >> 17) | (hi << 47);                     // 57 bits = 19 fields
+    f &= (1ull << (3 * ncl)) - 1ull;                          // ncl <= 19: shift <= 57
+    uint32_t kraft = 0;
+    if (kraft_lut) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) kraft += kraft_lut[(uint32_t)(f >> (9 * i)) & 511u];
+    } else {
+        for (int i = 0; i < 7; i++) kraft += fz_kraft3((uint32_t)(f >> (9 * i)) & 511u);
+    }
+    return kraft == 128u;
+}
+
+// full validation: parse the header exactly like the inflater would
+template <class Tab>
+FZ_HD bool fz_block_candidate(const uint8_t *in, size_t in_len, uint64_t bit, const Tab &tab)
+{
+    FzInflater<Tab> inf;
+    inf.start_at_bit(in, in_len, bit, nullptr, 0, tab);
+    inf.bw.dry = true;
+    if (!inf.block_header() || !inf.in_body) return false;
+    // zlib always emits a complete literal/length code with an end-of-block symbol; distances: complete, or the
+    // degenerate single code
+    return inf.ll_left == 0 && inf.eob_len != 0 && inf.dd_left >= 0;
+}
+
+template <class Tab>
+FZ_HD void fz_block_measure(const uint8_t *in, size_t in_len, uint64_t bit, const Tab &tab, uint32_t *lut, FzBlockInfo *bi)
+{
+    FzInflater<Tab> inf;
+    inf.start_at_bit(in, in_len, bit, nullptr, 0xFFFFFFF0u, tab);
+    inf.bw.dry = true;
+    inf.bw.prev_byte = 0;       // a distance-1 run may continue from the previous block; its value is resolved later
+    inf.own_lut = lut;
+    inf.one_block = true;
+    while (inf.step()) {}
+    bi->end_bit = (uint32_t)((bit & ~7ull) + inf.consumed_bits());
+    bi->out_len = inf.bw.produced();
+    uint32_t f = 0;
+    if (inf.rc == FZ_INF_OK && inf.saw_eob && inf.br.bits_left() >= 0) f |= FZ_BLK_OK;
+    if (inf.bw.non_rle) f |= FZ_BLK_NON_RLE;
+    if (inf.bw.starts_with_match) f |= FZ_BLK_STARTS_WITH_MATCH;
+    if (inf.bw.lastc < 0x100u) f |= FZ_BLK_HAS_LITERAL;
+    if (inf.last) f |= FZ_BLK_FINAL;
+    bi->flags = f;
+    bi->last = inf.bw.lastc & 0xffu;
+}
+
+// decode the block at `bit` into out[0, out_len); prev_byte = the byte before out[0] (or -1 at the stream start)
+template <class Tab>
+FZ_HD bool fz_block_write(const uint8_t *in, size_t in_len, uint64_t bit, const Tab &tab, uint32_t *lut, uint8_t *out,
+                          uint32_t out_len, int prev_byte, uint32_t expect_end_bit)
+{
+    FzInflater<Tab> inf;
+    inf.start_at_bit(in, in_len, bit, out, out_len, tab);
+    inf.bw.prev_byte = prev_byte;
+    inf.own_lut = lut;
+    inf.one_block = true;
+    while (inf.step()) {}
+    inf.bw.finish();
+    const uint32_t end_bit = (uint32_t)((bit & ~7ull) + inf.consumed_bits());
+    return inf.rc == FZ_INF_OK && inf.saw_eob && inf.bw.produced() == out_len && end_bit == expect_end_bit;
+}
+
+FZ_HD uint32_t fz_stream_bits(const uint8_t *in, uint64_t bit, uint32_t n)  // n <= 24 bits at bit position `bit`
+{
+    const uint64_t by = bit >> 3;
+    const uint32_t v = (uint32_t)in[by] | ((uint32_t)in[by + 1] << 8) | ((uint32_t)in[by + 2] << 16) | ((uint32_t)in[by + 3] << 24);
+    return (v >> (bit & 7)) & ((1u << n) - 1u);
+}
+
+// Serial walk over one stream.  cand_pos[0, ncand) ascending.  On success blk_off[i] = output offset of block i if
+// it lies on the chain (else 0xFFFFFFFF), blk_prev[i] = the byte before it (-1 at the stream start), and the
+// stored blocks met on the way are listed.  A fixed-Huffman block (zlib picks one now and then for a short or
+// nearly incompressible stretch) has no header to search for: the walk measures it on the spot and appends it
+// to the block list (slots [ncand, *nblocks)).  Returns 0, or < 0 when the stream must take the serial path.
+// Reads up to 3 bytes past `in + in_len` (callers provide that slack, as everywhere in this library).
+template <class Tab>
+FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, uint32_t *cand_pos, FzBlockInfo *info,
+                           uint32_t ncand, uint32_t cap, uint32_t *nblocks, uint32_t *blk_off, int *blk_prev,
+                           FzStoredItem *stored, uint32_t stored_cap, uint32_t *nstored, const Tab &tab)
+{
+    for (uint32_t i = 0; i < ncand; i++) blk_off[i] = 0xFFFFFFFFu;
+    *nstored = 0;
+    *nblocks = ncand;
+    uint64_t pos = 0;
+    uint32_t out = 0;
+    int prev = -1;
+    const uint64_t total_bits = (uint64_t)in_len * 8;
+    for (uint32_t guard = 0; guard < 100000; guard++) {
+        if (total_bits - pos < 3) break;
+        if (out == n_out && total_bits - pos < 8) break;
+        const uint32_t h = fz_stream_bits(in, pos, 3);
+        const uint32_t type = h >> 1;
+        if (type == 0) {  // stored block: skip to the byte boundary, LEN, NLEN, data
+            const uint64_t by = (pos + 3 + 7) >> 3;
+            if (by + 4 > in_len) return -1;
+            const uint32_t len = (uint32_t)in[by] | ((uint32_t)in[by + 1] << 8);
+            const uint32_t nlen = (uint32_t)in[by + 2] | ((uint32_t)in[by + 3] << 8);
+            if ((len ^ 0xFFFFu) != nlen || by + 4 + len > in_len || out + len > n_out) return -2;
+            if (len) {
+                if (*nstored >= stored_cap) return -3;
+                stored[*nstored].src_byte = (uint32_t)by + 4;
+                stored[*nstored].len = len;
+                stored[*nstored].out_off = out;
+                (*nstored)++;
+                prev = in[by + 4 + len - 1];
+                out += len;
+            }
+            pos = (by + 4 + len) * 8;
+        } else if (type == 1 || type == 2) {
+            uint32_t k;
+            if (type == 2) {  // the candidate starting exactly here
+                uint32_t lo = 0, hi = ncand;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cand_pos[mid] < pos) lo = mid + 1; else hi = mid; }
+                if (lo >= ncand || cand_pos[lo] != pos) return -4;
+                k = lo;
+            } else {
+                if (*nblocks >= cap) return -8;
+                k = (*nblocks)++;
+                cand_pos[k] = (uint32_t)pos;
+                fz_block_measure(in, (size_t)in_len, pos, tab, (uint32_t *)nullptr, &info[k]);
+            }
+            const FzBlockInfo &b = info[k];
+            if (!(b.flags & FZ_BLK_OK) || (b.flags & FZ_BLK_NON_RLE)) return -5;
+            if ((b.flags & FZ_BLK_STARTS_WITH_MATCH) && prev < 0) return -6;
+            if (out + b.out_len > n_out || b.end_bit <= pos) return -7;
+            blk_off[k] = out;
+            blk_prev[k] = prev;
+            out += b.out_len;
+            if (b.flags & FZ_BLK_HAS_LITERAL) prev = (int)b.last;
+            pos = b.end_bit;
+        } else return -9;  // invalid block type
+        if (h & 1u) break;  // BFINAL
+    }
+    return out == n_out ? 0 : -10;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One block, one WARP: self-synchronising decode.
+//
+// A Huffman bit stream decoded from a wrong bit position falls back into step with the true symbol boundaries
+// after a few symbols.  The block body is cut into tiles of 32 sub-ranges of FZ_BP_SUB_BITS bits; every lane
+// decodes its sub-range speculatively from the grid position, then lanes re-decode from the position where
+// their predecessor actually stopped until nothing moves any more (lane 0 of a tile starts at a known symbol
+// boundary, so the fixed point is the true parse).  Byte counts are prefix-summed over the lanes; the write
+// variant then decodes every sub-range once more, now storing at its offset.  All matches must have
+// distance 1 (Z_RLE): a sub-range that starts inside a run only needs the last literal before it.
+// SPMD style as in fz_deflate_enc.cuh: phases communicate through FzSyncState (shared memory on the GPU).
+// ---------------------------------------------------------------------------------------------------
+#include "fz_deflate_enc.cuh"   // FZ_PHASE
+
+#if defined(__CUDA_ARCH__)
+#define FZ_WARP_ANY(pred) (__any_sync(0xffffffffu, (pred)) != 0)
+#else
+#define FZ_WARP_ANY(pred) (pred)
+#endif
+
+// the big phase bodies are real functions on the device: one copy each, and their registers do not add up
+#if defined(__CUDACC__)
+#define FZ_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define FZ_HD_NOINLINE inline
+#endif
+
+#define FZ_BP_SUB_BITS 2048u
+#define FZ_SY_EOB 1u        // the sub-range ended with the end-of-block symbol
+#define FZ_SY_ERR 2u        // decode error (normal for a speculative start; fatal once the parse is settled)
+#define FZ_SY_NONRLE 8u
+#define FZ_SY_SWM 16u       // starts with a match that reaches before the sub-range
+#define FZ_SY_REDO 32u
+#define FZ_SY_WERR 256u
+
+#if !defined(__CUDA_ARCH__) && defined(FZ_SY_STATS)
+static uint64_t fz_sy_stat_tiles, fz_sy_stat_rounds, fz_sy_stat_redos, fz_sy_stat_redo_lanes;
+#endif
+
+struct FzSyncState {
+    uint32_t lut[FZ_LUT_SIZE];
+    uint16_t tab[FZ_INF_TAB_U16];
+    FzCode LL, DD;
+    uint32_t start[32], end[32], n[32], flags[32], lastc[32], want[32], off[32];
+    int prev[32];
+    // written by lane 0 in dedicated phases, read by everybody afterwards
+    uint32_t hdr_ok, hdr_end, is_last;
+    uint32_t any_redo;
+    uint32_t tile_total, tile_eob_lane, tile_err, tile_nonrle, tile_werr;
+    int tile_carry;
+};
+
+FZ_HD_NOINLINE void fz_sy_ph_header(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t bit, int lane)
+{
+    if (lane != 0) return;
+    typedef FzInfTab<1> Tab;
+    const Tab tab{st->tab, st->tab + 288, st->tab + 320};
+    FzInflater<Tab> inf;
+    inf.start_at_bit(in, (size_t)in_len, (uint64_t)bit, nullptr, 0xFFFFFFF0u, tab);
+    inf.bw.dry = true;
+    const bool ok = inf.block_header() && inf.in_body && inf.rc == FZ_INF_OK;
+    st->hdr_ok = ok ? 1u : 0u;
+    st->hdr_end = (uint32_t)(((uint64_t)bit & ~7ull) + inf.consumed_bits());
+    st->is_last = inf.last ? 1u : 0u;
+    st->LL = inf.LL;
+    st->DD = inf.DD;
+}
+
+FZ_HD void fz_sy_ph_lut(FzSyncState *st, int lane)
+{
+    const FzInfTab<1> tab{st->tab, st->tab + 288, st->tab + 320};
+    const FzCode LL = st->LL;
+    for (uint32_t e = (uint32_t)lane; e < FZ_LUT_SIZE; e += 32) st->lut[e] = fz_lut_entry(LL, tab, e);
+}
+
+// decode the sub-range of `lane` in tile `tile_pos` from st->start[lane]; out == nullptr: count only
+FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, bool active, uint8_t *out, int lane)
+{
+    typedef FzInfTab<1> Tab;
+    const Tab tab{st->tab, st->tab + 288, st->tab + 320};
+    const uint32_t start = st->start[lane];
+    const uint64_t range_end = (uint64_t)tile_pos + (uint64_t)(lane + 1) * FZ_BP_SUB_BITS;
+    const bool write = out != nullptr;
+    FzInflater<Tab> inf;
+    bool live = active && (uint64_t)start < range_end && (uint64_t)start < (uint64_t)in_len * 8;
+    const bool ran = live;
+    int64_t stop_left = 0;   // bits_left() value at which the sub-range is finished
+    if (live) {
+        inf.start_at_bit(in, (size_t)in_len, (uint64_t)start, out, write ? st->n[lane] : 0xFFFFFFF0u, tab);
+        inf.bw.dry = !write;
+        inf.bw.prev_byte = write ? st->prev[lane] : 0;
+        inf.shared_tab = true;
+        inf.in_body = true;
+        inf.one_block = true;
+        inf.last = st->is_last != 0;
+        inf.LL = st->LL;
+        inf.DD = st->DD;
+        stop_left = (int64_t)in_len * 8 - (int64_t)range_end;
+    }
+    const uint32_t *lut = st->lut;
+    // Lock-step drive as in the sub-block inflater: a register-only run of up to 16 table hits (1-3 literals each),
+    // then one general step (long code, match, end of block), then the lanes re-vote.
+    if (write) {
+        // the counting pass may have taken up to three literals in one step across the end of the sub-range:
+        // stop by the byte count it recorded, not by position (plus the end-of-block symbol if it saw one)
+        const uint32_t n_goal = st->n[lane];
+        const bool want_eob = (st->flags[lane] & FZ_SY_EOB) != 0;
+        if (live && n_goal == 0 && !want_eob) live = false;
+        while (FZ_WARP_ANY(live)) {
+            if (live) {
+#pragma unroll 1
+                for (int it = 0; it < 16; ++it) {
+                    inf.br.refill();
+                    const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
+                    const uint32_t cnt = e >> 29;
+                    if (e == 0 || (e & 511u) >= 256u || inf.bw.op + cnt > inf.bw.cap) break;
+                    inf.br.drop((int)((e >> 25) & 15u));
+                    inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
+                }
+                if (inf.bw.produced() >= n_goal && !want_eob) live = false;
+                else {
+                    live = inf.step_lut(lut);
+                    if (live && inf.bw.produced() >= n_goal && !want_eob) live = false;
+                }
+            }
+        }
+    } else {
+        // The stop position must not depend on where the parse started: two parses that have fallen into step
+        // group literals into multi-literal table hits differently, so within reach of the end of the sub-range
+        // symbols are taken one at a time -- the sub-range then ends at the FIRST symbol boundary >= range_end.
+        const int64_t near_left = stop_left + (int64_t)FZ_LUT_BITS;
+        while (FZ_WARP_ANY(live)) {
+            if (live) {
+#pragma unroll 1
+                for (int it = 0; it < 16; ++it) {
+                    inf.br.refill();
+                    if (inf.br.bits_left() <= near_left) break;
+                    const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
+                    if (e == 0 || (e & 511u) >= 256u) break;
+                    inf.br.drop((int)((e >> 25) & 15u));
+                    inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), e >> 29);
+                }
+                const bool near_end = inf.br.bits_left() <= near_left;
+                live = inf.step_lut(near_end ? nullptr : lut);
+                if (live && inf.br.bits_left() <= stop_left) live = false;
+            }
+        }
+    }
+    if (!active) return;
+    uint32_t f = st->flags[lane] & ~(FZ_SY_EOB | FZ_SY_ERR | FZ_SY_NONRLE | FZ_SY_SWM);
+    if (!ran) {   // predecessor already reached past this sub-range (or the stream ended): nothing of it is ours
+        if (!write) { st->end[lane] = start; st->n[lane] = 0; st->lastc[lane] = 0x100; st->flags[lane] = f; }
+        return;
+    }
+    const uint32_t endpos = (uint32_t)((int64_t)in_len * 8 - inf.br.bits_left());
+    if (write) {
+        inf.bw.finish();
+        if (inf.rc != FZ_INF_OK || inf.bw.produced() != st->n[lane] || endpos != st->end[lane] ||
+            inf.saw_eob != ((st->flags[lane] & FZ_SY_EOB) != 0))
+            st->flags[lane] = st->flags[lane] | FZ_SY_WERR;
+        return;
+    }
+    if (inf.rc != FZ_INF_OK) {
+        f |= FZ_SY_ERR;
+        st->end[lane] = (uint32_t)(range_end < (uint64_t)in_len * 8 ? range_end : (uint64_t)in_len * 8);
+        st->n[lane] = 0;
+        st->lastc[lane] = 0x100;
+    } else {
+        if (inf.saw_eob) f |= FZ_SY_EOB;
+        if (inf.bw.non_rle) f |= FZ_SY_NONRLE;
+        if (inf.bw.starts_with_match) f |= FZ_SY_SWM;
+        st->end[lane] = endpos;
+        st->n[lane] = inf.bw.produced();
+        st->lastc[lane] = inf.bw.lastc;
+    }
+    st->flags[lane] = f;
+}
+
+FZ_HD void fz_sy_ph_spec(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, int lane)
+{
+    st->start[lane] = tile_pos + (uint32_t)lane * FZ_BP_SUB_BITS;
+    st->flags[lane] = 0;
+    fz_sy_decode(st, in, in_len, tile_pos, true, nullptr, lane);
+}
+
+// A sub-range is settled when it started where its (settled) predecessor stopped; lane 0 always is.  Lanes that
+// are not re-decode from their predecessor's current end -- all of them at once.
+FZ_HD void fz_sy_ph_look(FzSyncState *st, uint32_t tile_pos, int lane)
+{
+    uint32_t f = st->flags[lane] & ~FZ_SY_REDO;
+    const uint32_t want = lane == 0 ? tile_pos : st->end[lane - 1];
+    st->want[lane] = want;
+    if (st->start[lane] != want) f |= FZ_SY_REDO;
+    st->flags[lane] = f;
+}
+
+// lane 0: length of the settled prefix, and whether the block ends inside it (then the rest of the tile is moot:
+// what follows the end-of-block symbol is not this block's data, however the speculative lanes parsed it)
+FZ_HD void fz_sy_ph_summary(FzSyncState *st, int lane)
+{
+    if (lane != 0) return;
+    uint32_t settled = 32, eob_lane = 32;
+    for (int l = 0; l < 32; l++) {
+        if (st->flags[l] & FZ_SY_REDO) { settled = (uint32_t)l; break; }
+        if (st->flags[l] & (FZ_SY_EOB | FZ_SY_ERR)) { eob_lane = (uint32_t)l; break; }   // an error ends the tile as well
+    }
+    st->tile_eob_lane = eob_lane;
+    st->any_redo = (eob_lane == 32 && settled < 32) ? 1u : 0u;
+}
+
+FZ_HD void fz_sy_ph_apply(FzSyncState *st, int lane)
+{
+    if (st->flags[lane] & FZ_SY_REDO) st->start[lane] = st->want[lane];
+}
+
+FZ_HD void fz_sy_ph_redo(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, int lane)
+{
+    fz_sy_decode(st, in, in_len, tile_pos, (st->flags[lane] & FZ_SY_REDO) != 0, nullptr, lane);
+}
+
+// offsets, the byte before every sub-range, totals of the tile (lanes 0 .. last, last = the end-of-block lane or 31)
+FZ_HD void fz_sy_ph_scan(FzSyncState *st, int carry, int lane)
+{
+    if (lane != 0) return;
+    uint32_t total = 0, err = 0, nonrle = 0;
+    const int last = st->tile_eob_lane < 32u ? (int)st->tile_eob_lane : 31;
+    for (int l = 0; l <= last; l++) {
+        const uint32_t f = st->flags[l];
+        st->off[l] = total;
+        st->prev[l] = carry;
+        if (f & FZ_SY_ERR) { err = 1; break; }
+        if (f & FZ_SY_NONRLE) nonrle = 1;
+        total += st->n[l];
+        if (st->lastc[l] < 0x100u) carry = (int)st->lastc[l];
+    }
+    st->tile_total = total;
+    st->tile_err = err;
+    st->tile_nonrle = nonrle;
+    st->tile_carry = carry;
+}
+
+FZ_HD void fz_sy_ph_write(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, uint8_t *out_tile, int lane)
+{
+    const bool active = (uint32_t)lane <= st->tile_eob_lane;
+    fz_sy_decode(st, in, in_len, tile_pos, active, out_tile + (active ? st->off[lane] : 0u), lane);
+}
+
+FZ_HD void fz_sy_ph_werr(FzSyncState *st, int lane)
+{
+    if (lane != 0) return;
+    uint32_t w = 0;
+    for (int l = 0; l < 32; l++) w |= st->flags[l] & FZ_SY_WERR;
+    st->tile_werr = w;
+}
+
+// Decode the block whose header starts at `bit`.
+//   WRITE = false: fills *bi (as fz_block_measure does);  WRITE = true: stores out[0, out_len), returns success
+// in *ok (end position must equal expect_end).  Called by all 32 lanes on the device, once on the host.
+template <bool WRITE>
+FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t bit, uint8_t *out, uint32_t out_len,
+                       int prev_byte, uint32_t expect_end, FzBlockInfo *bi, bool *ok, int lane)
+{
+    (void)lane;
+    FZ_PHASE(fz_sy_ph_header(st, in, in_len, bit, lane));
+    uint32_t flags = 0, produced = 0, end_bit = bit;
+    int carry = WRITE ? prev_byte : -1;
+    bool good = st->hdr_ok != 0, done = false;
+    if (good) {
+        FZ_PHASE(fz_sy_ph_lut(st, lane));
+        uint32_t tile_pos = st->hdr_end;
+        const uint32_t max_tiles = (uint32_t)(((uint64_t)in_len * 8 - tile_pos) / (32u * FZ_BP_SUB_BITS)) + 2u;
+        for (uint32_t tile = 0; tile < max_tiles && good && !done; tile++) {
+            FZ_PHASE(fz_sy_ph_spec(st, in, in_len, tile_pos, lane));
+#if !defined(__CUDA_ARCH__) && defined(FZ_SY_STATS)
+            fz_sy_stat_tiles++;
+#endif
+            bool settled = false;
+            for (int round = 0; round < 34 && !settled; round++) {
+                FZ_PHASE(fz_sy_ph_look(st, tile_pos, lane));
+                FZ_PHASE(fz_sy_ph_summary(st, lane));
+#if !defined(__CUDA_ARCH__) && defined(FZ_SY_STATS)
+                fz_sy_stat_rounds++; if (st->any_redo) { fz_sy_stat_redos++; for (int l = 0; l < 32; l++) fz_sy_stat_redo_lanes += (st->flags[l] & FZ_SY_REDO) != 0; }
+#endif
+                if (st->any_redo) {
+                    FZ_PHASE(fz_sy_ph_apply(st, lane));
+                    FZ_PHASE(fz_sy_ph_redo(st, in, in_len, tile_pos, lane));
+                } else settled = true;
+            }
+            if (!settled) { good = false; break; }
+            FZ_PHASE(fz_sy_ph_scan(st, carry, lane));
+            const uint32_t total = st->tile_total;
+            if (st->tile_err) { good = false; break; }
+            if (st->tile_nonrle) flags |= FZ_BLK_NON_RLE;
+            if (tile == 0 && (st->flags[0] & FZ_SY_SWM)) flags |= FZ_BLK_STARTS_WITH_MATCH;
+            if (WRITE) {
+                if ((flags & FZ_BLK_NON_RLE) || (uint64_t)produced + total > out_len) { good = false; break; }
+                FZ_PHASE(fz_sy_ph_write(st, in, in_len, tile_pos, out + produced, lane));
+                FZ_PHASE(fz_sy_ph_werr(st, lane));
+                if (st->tile_werr) { good = false; break; }
+            }
+            produced += total;
+            carry = st->tile_carry;
+            if (st->tile_eob_lane < 32u) { done = true; end_bit = st->end[st->tile_eob_lane]; }
+            else {
+                const uint32_t next = st->end[31];
+                if (next <= tile_pos) { good = false; break; }
+                tile_pos = next;
+            }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();   // everybody has read the tile's summary before the next tile overwrites it
+#endif
+        }
+    }
+    good = good && done;
+    if (WRITE) {
+        *ok = good && produced == out_len && end_bit == expect_end;
+    } else {
+        if (good) flags |= FZ_BLK_OK;
+        if (carry >= 0) flags |= FZ_BLK_HAS_LITERAL;
+        if (st->is_last) flags |= FZ_BLK_FINAL;
+        bi->end_bit = end_bit;
+        bi->out_len = produced;
+        bi->flags = flags;
+        bi->last = carry >= 0 ? (uint32_t)carry : 0u;
+    }
+}

@@ -16,6 +16,7 @@
 #endif
 
 // ---- container constants (reference: constant.h:22-27, mrczip.h:116-121, common.c:137-149)
+#define FZ_SM_COUNT 148        // B200: persistent-style grids are sized in multiples of this
 #define FZ_PLANES 4
 #define FZ_REF_CHUNK_WORDS (6u * 1048576u)
 #define FZ_FILE_HEADER_BYTES 17

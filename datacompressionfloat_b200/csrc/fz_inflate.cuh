@@ -64,17 +64,35 @@ struct FzBitReader {
 };
 
 struct FzByteWriter {
-    uint8_t *out;     // 4-byte aligned
-    uint32_t op, cap;
-    uint32_t ow;      // pending bytes of the current word
-    FZ_HD void init(uint8_t *o, uint32_t c) { out = o; op = 0; cap = c; ow = 0; }
+    uint8_t *out;      // 4-byte aligned base; the fragment's bytes are out[op0 .. cap)
+    uint32_t op, cap;  // write position / end, both relative to `out`
+    uint32_t op0;      // 0..3: leading bytes of the first word that belong to a neighbouring fragment
+    uint32_t ow;       // pending bytes of the current word
+    int prev_byte;     // the byte just before the fragment (block-parallel decode), or -1: nothing may be referenced there
+    bool dry;          // count only, store nothing (measure pass of the block-parallel decode)
+    bool non_rle;      // dry: a match with a distance other than 1 was seen (its bytes are unknown without history)
+    bool starts_with_match;  // dry: the fragment begins with a distance-1 match reaching the byte before it
+    uint32_t lastc;    // dry: value of the last literal, 0x100 = none yet
+    FZ_HD void init(uint8_t *o, uint32_t c)
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)o & 3u);
+        out = o - mis; op0 = mis; op = mis; cap = c + mis; ow = 0;
+        prev_byte = -1; dry = false; non_rle = false; starts_with_match = false; lastc = 0x100;
+    }
+    FZ_HD uint32_t produced() const { return op - op0; }
+    FZ_HD void store_word(uint32_t widx_bytes, uint32_t w)  // the word starting at byte offset widx_bytes is complete
+    {
+        if (widx_bytes == 0 && op0) { for (uint32_t i = op0; i < 4; i++) out[i] = (uint8_t)(w >> (8 * i)); }
+        else *(uint32_t *)(out + widx_bytes) = w;
+    }
     FZ_HD void put(uint32_t c)
     {
+        if (dry) { op++; lastc = c; return; }
         ow |= c << ((op & 3) * 8);
         op++;
-        if ((op & 3) == 0) { *(uint32_t *)(out + op - 4) = ow; ow = 0; }
+        if ((op & 3) == 0) { store_word(op - 4, ow); ow = 0; }
     }
-    FZ_HD uint32_t back(uint32_t dist) const  // byte written `dist` positions ago (dist <= op)
+    FZ_HD uint32_t back(uint32_t dist) const  // byte written `dist` positions ago (dist <= produced())
     {
         const uint32_t p = op - dist;
         if ((p >> 2) == (op >> 2)) return (ow >> ((p & 3) * 8)) & 0xffu;  // still pending in ow
@@ -83,15 +101,17 @@ struct FzByteWriter {
     // append cnt (1..3) bytes packed little-endian in v; the caller checked op + cnt <= cap
     FZ_HD void putn(uint32_t v, uint32_t cnt)
     {
+        if (dry) { op += cnt; lastc = (v >> (8 * (cnt - 1))) & 0xffu; return; }
         const uint32_t sh = (op & 3) * 8;
         const uint64_t t = (uint64_t)ow | ((uint64_t)v << sh);
         const uint32_t nb = sh + cnt * 8;  // bits now pending
         op += cnt;
-        if (nb >= 32) { *(uint32_t *)(out + (op & ~3u) - 4) = (uint32_t)t; ow = (uint32_t)(t >> 32); }
+        if (nb >= 32) { store_word((op & ~3u) - 4, (uint32_t)t); ow = (uint32_t)(t >> 32); }
         else ow = (uint32_t)t;
     }
     FZ_HD void fill(uint32_t c, uint32_t len)  // len copies of byte c (a distance-1 match), whole words where possible
     {
+        if (dry) { op += len; return; }
         while (len && (op & 3)) { put(c); len--; }
         const uint32_t w = c * 0x01010101u;
         while (len >= 4) { *(uint32_t *)(out + op) = w; op += 4; len -= 4; }
@@ -99,8 +119,9 @@ struct FzByteWriter {
     }
     FZ_HD void finish()
     {
-        const uint32_t r = op & 3;
-        for (uint32_t i = 0; i < r; i++) out[op - r + i] = (uint8_t)(ow >> (8 * i));
+        if (dry) return;
+        const uint32_t r = op & 3, w0 = op - r;
+        for (uint32_t i = (w0 == 0 ? op0 : 0u); i < r; i++) out[w0 + i] = (uint8_t)(ow >> (8 * i));
     }
 };
 
@@ -224,6 +245,10 @@ struct FzInflater {
     bool last, in_body;
     bool shared_tab;  // tables are shared with other lanes: this lane must not rebuild them (no further coded block)
     uint32_t *own_lut;  // optional FZ_LUT_SIZE-entry table this thread (re)builds after every block header
+    bool one_block;     // stop after the first coded block (block-parallel decode of zlib-made streams)
+    bool saw_eob;       // ... and it ended properly with its end-of-block symbol
+    int ll_left, dd_left;  // Kraft remainders of the last dynamic header (0 = complete code)
+    uint32_t eob_len;      // code length of the end-of-block symbol in the last header
 
     FZ_HD void start(const uint8_t *in, size_t in_len_, uint8_t *out, uint32_t out_cap, const Tab &t)
     {
@@ -236,7 +261,16 @@ struct FzInflater {
         in_body = false;
         shared_tab = false;
         own_lut = nullptr;
+        one_block = false; saw_eob = false; ll_left = 0; dd_left = 0; eob_len = 1;
     }
+    // start `bit` bits into the input (block-parallel decode)
+    FZ_HD void start_at_bit(const uint8_t *in, size_t in_len_, uint64_t bit, uint8_t *out, uint32_t out_cap, const Tab &t)
+    {
+        start(in + (bit >> 3), in_len_ - (size_t)(bit >> 3), out, out_cap, t);
+        br.refill();
+        br.drop((int)(bit & 7));
+    }
+    FZ_HD uint64_t consumed_bits() const { return (uint64_t)((int64_t)in_len * 8 - br.bits_left()); }
 
     // returns true while there is more to do
     FZ_HD bool step()
@@ -254,7 +288,7 @@ struct FzInflater {
     {
         bw.finish();
         if (rc == FZ_INF_OK && br.bits_left() < 0) rc = FZ_INF_E_INPUT;
-        *out_n = bw.op;
+        *out_n = bw.produced();
         const int64_t used_bits = (int64_t)in_len * 8 - br.bits_left();
         *in_used = (size_t)((used_bits + 7) / 8);
         return rc;
@@ -265,6 +299,9 @@ struct FzInflater {
     FZ_HD bool body_symbol(const uint32_t *lut)
     {
         br.refill();
+        // measure pass over a speculative block: a false candidate may run off the end of the input, where the
+        // reader feeds zero bits for ever
+        if (bw.dry && br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
         uint32_t idx, sym;
         int l;
         const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
@@ -296,7 +333,8 @@ struct FzInflater {
         if (sym == FZ_EOB) {
             in_body = false;
             if (br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
-            return !last;
+            saw_eob = true;
+            return !last && !one_block;
         }
         sym -= 257;
         if (sym >= 29) return fail(FZ_INF_E_DATA);
@@ -309,8 +347,19 @@ struct FzInflater {
         if (ds >= 30) return fail(FZ_INF_E_DATA);
         br.refill();
         const uint32_t dist = fz_dist_base(ds) + br.get((int)fz_dist_extra_bits(ds));
-        if (dist > bw.op) return fail(FZ_INF_E_HISTORY);
         if (bw.op + len > bw.cap) return fail(FZ_INF_E_SPACE);
+        if (dist > bw.produced()) {
+            // only the byte just before the fragment may be reached, by a run that continues across the block boundary
+            if (!(bw.prev_byte >= 0 && dist == 1)) return fail(FZ_INF_E_HISTORY);
+            if (bw.dry) bw.starts_with_match = true;
+            bw.fill((uint32_t)bw.prev_byte, len);
+            return true;
+        }
+        if (bw.dry) {
+            if (dist != 1) bw.non_rle = true;
+            bw.op += len;
+            return true;
+        }
         if (dist == 1) {
             bw.fill(bw.back(1), len);
         } else {
@@ -401,10 +450,12 @@ struct FzInflater {
                 const int e1 = fz_code_build(LL, rd_ll, wr_ll);
                 const int e2 = fz_code_build(DD, rd_dd, wr_dd);
                 if (e1 < 0 || e2 < 0) return fail(FZ_INF_E_DATA);  // over-subscribed
+                ll_left = e1; dd_left = e2;
                 br = mark;
             }
             uint32_t i = 0, prev = 0;
             const uint32_t total = hlit + hdist;
+            if (pass == 0) eob_len = 0;
             while (i < total) {
                 br.refill();
                 uint32_t idx;
@@ -419,6 +470,7 @@ struct FzInflater {
                 if (i + rep > total) return fail(FZ_INF_E_DATA);
                 prev = val;
                 if (val == 0) { i += rep; continue; }
+                if (i <= FZ_EOB && FZ_EOB < i + rep) eob_len = val;
                 if (pass == 0) {
                     for (uint32_t k = 0; k < rep; k++, i++) tab.C((i < hlit ? 0 : 16) + (int)val)++;
                 } else {

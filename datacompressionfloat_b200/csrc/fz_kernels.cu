@@ -971,11 +971,14 @@ static void fz_exclusive_scan(uint32_t *a, uint32_t n, uint32_t *bsum, cudaStrea
 // ---- classify streams: RAW, fast (our sub-block framing: one marker per sub-block, last one ends the payload), general
 __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBatchGeom g, const uint32_t *__restrict__ tile_off,
                                    uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, uint32_t hits_cap,
-                                   uint32_t *__restrict__ stream_mode, uint32_t *__restrict__ stream_fail, const FzStatus *status)
+                                   uint32_t *__restrict__ stream_mode, uint32_t *__restrict__ stream_fail, FzBlockParBufs bp,
+                                   const FzStatus *status)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.nchunks * FZ_PLANES) return;
     stream_fail[s] = 0;
+    bp.cand_cnt[s] = 0;
+    bp.par_ok[s] = 0;
     if (status->error) { stream_mode[s] = 0; return; }
     const uint32_t h = stream_hdr[s];
     if (h & FZ_RAW_FLAG) { stream_mode[s] = 0; return; }
@@ -988,6 +991,7 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
         if (((n_s + FZ_SUB - 1) >> FZ_SUB_LOG2) == m) mode = 1u | ((uint32_t)FZ_SUB_LOG2 << 8);
     }
     stream_mode[s] = mode;
+    if (mode == 2) bp.gen_list[atomicAdd(&bp.ctl[0], 1u)] = s;   // zlib-made stream: block-parallel path first
 }
 
 // ---- fast path: one WARP per group of 32 sub-blocks, one THREAD per sub-block fragment.
@@ -1131,7 +1135,8 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
 __global__ void __launch_bounds__(32)
 fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
                           const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_mode,
-                          const uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, FzStatus *status)
+                          const uint32_t *__restrict__ stream_fail, const uint32_t *__restrict__ par_ok,
+                          uint8_t *__restrict__ planes, FzStatus *status)
 {
     __shared__ uint16_t tabs[FZ_INF_TAB_U16];
     __shared__ uint32_t lut[FZ_LUT_SIZE];
@@ -1142,6 +1147,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     if (!(mode == 2u || failed)) return;
     if (failed) atomicAdd(&status->n_fast_failed, 1u);
     atomicAdd(&status->n_general, 1u);
+    if (mode == 2u && par_ok[s]) { atomicAdd(&status->n_blockpar, 1u); return; }   // decoded block-parallel
     const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
     const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
     uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk;
@@ -1150,6 +1156,253 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     size_t used = 0;
     const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used, lut);
     if (rc != FZ_INF_OK || out_n != n_s) atomicCAS(&status->error, 0, FZ_E_FORMAT);
+}
+
+// =================================================================================================
+// block-parallel inflate of zlib-made streams (fz_blockpar.cuh): find -> sort -> measure -> chain -> write -> stored
+// Every kernel is a fixed-size grid looping over a work list whose length lives on the device (ctl[0] =
+// general streams of this batch), so a batch of our own streams costs six empty launches and no host sync.
+// =================================================================================================
+#define FZ_BP_FIND_THREADS 64
+#define FZ_BP_SEG_WORDS 2048            // 32-bit words of a stream searched by one block per work item
+#define FZ_BP_QCAP 96                   // per-warp queue of positions that passed the quick test
+
+__device__ __forceinline__ uint32_t fz_bp_stream_n(const FzBatchGeom &g, uint32_t s)
+{
+    return (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+}
+
+// candidates: every bit position p of the payload with a plausible dynamic-block header
+__global__ void __launch_bounds__(FZ_BP_FIND_THREADS)
+fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size, const uint32_t *__restrict__ stream_hdr,
+                  const unsigned long long *__restrict__ stream_off, FzBlockParBufs bp, uint32_t segs_per_stream,
+                  const FzStatus *status)
+{
+    __shared__ uint16_t tabs[FZ_BP_FIND_THREADS * FZ_INF_TAB_U16];   // per-thread tables, interleaved (no bank conflicts)
+    __shared__ uint32_t queue[FZ_BP_FIND_THREADS / 32][FZ_BP_QCAP];
+    __shared__ uint32_t qn[FZ_BP_FIND_THREADS / 32];
+    __shared__ uint8_t kraft_lut[512];
+    const uint32_t ngen = bp.ctl[0];
+    if (ngen == 0 || status->error) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint16_t *mine = tabs + threadIdx.x;
+    const FzInfTab<FZ_BP_FIND_THREADS> tab{mine, mine + 288 * FZ_BP_FIND_THREADS, mine + 320 * FZ_BP_FIND_THREADS};
+    for (uint32_t i = threadIdx.x; i < 512; i += FZ_BP_FIND_THREADS) kraft_lut[i] = (uint8_t)fz_kraft3(i);
+    __syncthreads();
+    const uint32_t *alloc_end = (const uint32_t *)(((uintptr_t)container + container_size + 3u) & ~(uintptr_t)3u);
+    if (lane == 0) qn[warp] = 0;
+    __syncwarp();
+    for (uint32_t item = blockIdx.x; item < ngen * segs_per_stream; item += gridDim.x) {
+        const uint32_t gi = item / segs_per_stream, seg = item - gi * segs_per_stream;
+        const uint32_t s = bp.gen_list[gi];
+        const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
+        const uint8_t *in = container + stream_off[s];
+        const uint32_t skew = (uint32_t)((uintptr_t)in & 3u);
+        const uint32_t *abase = (const uint32_t *)(in - skew);
+        const uint32_t nwords = (len + skew + 3) >> 2;
+        if (seg * FZ_BP_SEG_WORDS >= nwords) continue;   // block-uniform
+        const int64_t total_bits = (int64_t)len * 8;
+        auto validate = [&](uint32_t p) {
+            if (fz_block_candidate(in, (size_t)len, (uint64_t)p, tab)) {
+                const uint32_t idx = atomicAdd(&bp.cand_cnt[s], 1u);
+                if (idx < FZ_BP_CAP) bp.cand_pos[(size_t)s * FZ_BP_CAP + idx] = p;
+            }
+        };
+        for (uint32_t it = 0; it < FZ_BP_SEG_WORDS / FZ_BP_FIND_THREADS; it++) {
+            const uint32_t wi = seg * FZ_BP_SEG_WORDS + it * FZ_BP_FIND_THREADS + threadIdx.x;
+            if (wi < nwords) {
+                uint32_t x[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) x[k] = (abase + wi + k < alloc_end) ? __ldg(abase + wi + k) : 0u;
+                const uint64_t v = (uint64_t)x[0] | ((uint64_t)x[1] << 32);
+                uint32_t m = (uint32_t)(~(v >> 1) & (v >> 2));   // BTYPE == 10 at positions j = 0..31 of this word
+                while (m) {
+                    const int j = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const int64_t p = (int64_t)wi * 32 + j - (int64_t)skew * 8;
+                    if (p < 0 || p + 17 > total_bits) continue;
+                    const uint64_t lo = (uint64_t)__funnelshift_r(x[0], x[1], j) | ((uint64_t)__funnelshift_r(x[1], x[2], j) << 32);
+                    const uint64_t hi = (uint64_t)__funnelshift_r(x[2], x[3], j) | ((uint64_t)__funnelshift_r(x[3], x[4], j) << 32);
+                    if (!fz_block_quick_test(lo, hi, kraft_lut)) continue;
+                    const uint32_t slot = atomicAdd(&qn[warp], 1u);
+                    if (slot < FZ_BP_QCAP) queue[warp][slot] = (uint32_t)p;
+                    else validate((uint32_t)p);   // queue full (pathological data): validate in place
+                }
+            }
+            __syncwarp();
+            uint32_t n = qn[warp];
+            const bool last_it = it + 1 == FZ_BP_SEG_WORDS / FZ_BP_FIND_THREADS;
+            if (n >= 32 || (last_it && n)) {   // warp-uniform: validate with all lanes busy
+                if (n > FZ_BP_QCAP) n = FZ_BP_QCAP;
+                for (uint32_t i = lane; i < n; i += 32) validate(queue[warp][i]);
+                __syncwarp();
+                if (lane == 0) qn[warp] = 0;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ascending candidate positions per stream (bitonic sort of FZ_BP_CAP slots, unused ones padded with ~0)
+__global__ void __launch_bounds__(FZ_BP_CAP / 2)
+fz_bp_sort_kernel(FzBlockParBufs bp, const FzStatus *status)
+{
+    __shared__ uint32_t v[FZ_BP_CAP];
+    const uint32_t ngen = bp.ctl[0];
+    if (ngen == 0 || status->error) return;
+    for (uint32_t gi = blockIdx.x; gi < ngen; gi += gridDim.x) {
+        const uint32_t s = bp.gen_list[gi];
+        const uint32_t n = min(bp.cand_cnt[s], (uint32_t)FZ_BP_CAP);
+        uint32_t *pos = bp.cand_pos + (size_t)s * FZ_BP_CAP;
+        for (uint32_t i = threadIdx.x; i < FZ_BP_CAP; i += blockDim.x) v[i] = i < n ? pos[i] : 0xFFFFFFFFu;
+        __syncthreads();
+        for (uint32_t k = 2; k <= FZ_BP_CAP; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t t = threadIdx.x;
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t a = v[i], b = v[l];
+                if ((a > b) == up) { v[i] = b; v[l] = a; }
+                __syncthreads();
+            }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pos[i] = v[i];
+        // work list of the measure pass: one entry per candidate (cand_cnt > FZ_BP_CAP: the stream goes serial)
+        __shared__ uint32_t base;
+        if (threadIdx.x == 0) base = bp.cand_cnt[s] <= FZ_BP_CAP ? atomicAdd(&bp.ctl[FZ_BP_CTL_NMEASURE], n) : 0xFFFFFFFFu;
+        __syncthreads();
+        if (base != 0xFFFFFFFFu)
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) bp.items[base + i] = s * FZ_BP_CAP + i;
+        __syncthreads();
+    }
+}
+
+// measure (WRITE = false): decode every candidate block without storing; write (WRITE = true): decode the blocks
+// on the chain into the planes.  One WARP per block: the self-synchronising decoder of fz_blockpar.cuh.
+#define FZ_BP_SY_WARPS 4
+template <bool WRITE>
+__global__ void __launch_bounds__(FZ_BP_SY_WARPS * 32, 4)
+fz_bp_sync_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
+                  const unsigned long long *__restrict__ stream_off, FzBlockParBufs bp, uint8_t *__restrict__ planes,
+                  const FzStatus *status)
+{
+    __shared__ FzSyncState sm[FZ_BP_SY_WARPS];
+    const uint32_t ngen = bp.ctl[0];
+    if (ngen == 0 || status->error) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FzSyncState *st = &sm[warp];
+    // work list filled by the sort kernel (measure) / the chain kernel (write); warps take entries as they get free
+    const uint32_t *list = WRITE ? bp.items + (size_t)bp.nstreams * FZ_BP_CAP : bp.items;
+    const uint32_t total = bp.ctl[WRITE ? FZ_BP_CTL_NWRITE : FZ_BP_CTL_NMEASURE];
+    uint32_t *cursor = &bp.ctl[WRITE ? FZ_BP_CTL_CUR_WRITE : FZ_BP_CTL_CUR_MEASURE];
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(cursor, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= total) break;
+        const size_t ci = list[wi];
+        const uint32_t s = (uint32_t)(ci / FZ_BP_CAP);
+        if (WRITE && !bp.par_ok[s]) continue;   // a block of this stream already failed: the serial inflater redoes it
+        uint32_t off = 0;
+        if (WRITE) off = bp.blk_off[ci];
+        const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
+        const uint8_t *in = container + stream_off[s];
+        const uint32_t bit = bp.cand_pos[ci];
+        if (WRITE) {
+            const FzBlockInfo bi = bp.info[ci];
+            uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + off;
+            bool ok = false;
+            fz_sy_block<true>(st, in, len, bit, out, bi.out_len, bp.blk_prev[ci], bi.end_bit, nullptr, &ok, lane);
+            if (!ok && lane == 0) atomicExch(&bp.par_ok[s], 0u);
+        } else {
+            FzBlockInfo bi;
+            fz_sy_block<false>(st, in, len, bit, nullptr, 0, -1, 0, &bi, nullptr, lane);
+            if (lane == 0) bp.info[ci] = bi;
+        }
+        __syncwarp();
+    }
+}
+
+// chain: one thread per general stream walks block end -> next block start
+__global__ void __launch_bounds__(32)
+fz_bp_chain_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
+                   const unsigned long long *__restrict__ stream_off, FzBlockParBufs bp, const FzStatus *status)
+{
+    __shared__ uint16_t tabs[32 * FZ_INF_TAB_U16];   // only touched when a fixed-Huffman block is met
+    const uint32_t ngen = bp.ctl[0];
+    if (ngen == 0 || status->error) return;
+    uint16_t *mine = tabs + threadIdx.x;
+    const FzInfTab<32> tab{mine, mine + 288 * 32, mine + 320 * 32};
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngen; gi += gridDim.x * blockDim.x) {
+        const uint32_t s = bp.gen_list[gi];
+        const uint32_t ncand = bp.cand_cnt[s];
+        uint32_t ok = 0, nst = 0, nblocks = ncand;
+        if (ncand <= FZ_BP_CAP) {
+            const size_t c0 = (size_t)s * FZ_BP_CAP;
+            const int rc = fz_chain_resolve(container + stream_off[s], stream_hdr[s] & ~FZ_RAW_FLAG, fz_bp_stream_n(g, s),
+                                            bp.cand_pos + c0, bp.info + c0, ncand, (uint32_t)FZ_BP_CAP, &nblocks, bp.blk_off + c0,
+                                            bp.blk_prev + c0, bp.stored + (size_t)s * FZ_BP_STORED_CAP, FZ_BP_STORED_CAP, &nst, tab);
+            ok = rc == 0;
+        }
+        bp.cand_cnt[s] = ok ? nblocks : ncand;
+        bp.nstored[s] = ok ? nst : 0u;
+        bp.par_ok[s] = ok;
+        if (ok) {   // work list of the write pass: the blocks on the chain
+            const size_t c0 = (size_t)s * FZ_BP_CAP;
+            uint32_t non = 0;
+            for (uint32_t i = 0; i < nblocks; i++) non += bp.blk_off[c0 + i] != 0xFFFFFFFFu;
+            uint32_t at = atomicAdd(&bp.ctl[FZ_BP_CTL_NWRITE], non);
+            uint32_t *list = bp.items + (size_t)bp.nstreams * FZ_BP_CAP;
+            for (uint32_t i = 0; i < nblocks; i++)
+                if (bp.blk_off[c0 + i] != 0xFFFFFFFFu) list[at++] = (uint32_t)(c0 + i);
+        }
+    }
+}
+
+// stored blocks met on the chain: plain copies, one warp each
+__global__ void __launch_bounds__(128)
+fz_bp_stored_kernel(const uint8_t *__restrict__ container, uint64_t container_size, FzBatchGeom g,
+                    const unsigned long long *__restrict__ stream_off, FzBlockParBufs bp, uint8_t *__restrict__ planes,
+                    const FzStatus *status)
+{
+    const uint32_t ngen = bp.ctl[0];
+    if (ngen == 0 || status->error) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * 4;
+    for (uint32_t wi = blockIdx.x * 4 + (threadIdx.x >> 5); wi < ngen * FZ_BP_STORED_CAP; wi += nwarps) {
+        const uint32_t gi = wi / FZ_BP_STORED_CAP, k = wi - gi * FZ_BP_STORED_CAP;
+        const uint32_t s = bp.gen_list[gi];
+        if (!bp.par_ok[s] || k >= bp.nstored[s]) continue;
+        const FzStoredItem it = bp.stored[(size_t)s * FZ_BP_STORED_CAP + k];
+        uint8_t *dst = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + it.out_off;
+        fz_warp_copy(dst, container + stream_off[s] + it.src_byte, it.len, container + container_size, lane);
+    }
+}
+
+size_t fz_blockpar_bytes(uint32_t nstreams)
+{
+    const size_t per_stream = 4 /*gen_list*/ + 4 /*cand_cnt*/ + 4 /*nstored*/ + 4 /*par_ok*/ +
+                              (size_t)FZ_BP_CAP * (4 + sizeof(FzBlockInfo) + 4 + 4 + 8) + (size_t)FZ_BP_STORED_CAP * sizeof(FzStoredItem);
+    return 256 + per_stream * nstreams + 16 * 64;
+}
+
+FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams)
+{
+    FzBlockParBufs b;
+    uint8_t *p = (uint8_t *)blob;
+    auto take = [&](size_t bytes) { uint8_t *r = p; p += (bytes + 63) & ~(size_t)63; return r; };
+    b.ctl = (uint32_t *)take(256);
+    b.gen_list = (uint32_t *)take((size_t)nstreams * 4);
+    b.cand_cnt = (uint32_t *)take((size_t)nstreams * 4);
+    b.nstored = (uint32_t *)take((size_t)nstreams * 4);
+    b.par_ok = (uint32_t *)take((size_t)nstreams * 4);
+    b.cand_pos = (uint32_t *)take((size_t)nstreams * FZ_BP_CAP * 4);
+    b.info = (FzBlockInfo *)take((size_t)nstreams * FZ_BP_CAP * sizeof(FzBlockInfo));
+    b.blk_off = (uint32_t *)take((size_t)nstreams * FZ_BP_CAP * 4);
+    b.blk_prev = (int *)take((size_t)nstreams * FZ_BP_CAP * 4);
+    b.stored = (FzStoredItem *)take((size_t)nstreams * FZ_BP_STORED_CAP * sizeof(FzStoredItem));
+    b.items = (uint32_t *)take((size_t)nstreams * FZ_BP_CAP * 4 * 2);
+    b.nstreams = nstreams;
+    return b;
 }
 
 // ---- RAW payloads: verbatim plane bytes (reference zip.c:264-267)
@@ -1182,13 +1435,23 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     fz_exclusive_scan(b.tile_cnt, ntiles, b.block_sums, st);
     fz_marker_kernel<true><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
     if (mark) mark(mark_user, FZ_ST_MARKERS);
-    fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, status);
+    cudaMemsetAsync(b.bp.ctl, 0, 64, st);
+    fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, b.bp, status);
     if (mark) mark(mark_user, FZ_ST_CLASSIFY);
     const uint32_t ngroups = nstreams * ((g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
     fz_inflate_group_kernel<<<(ngroups + FZ_INF_WARPS - 1) / FZ_INF_WARPS, FZ_INF_WARPS * FZ_WARP, 0, st>>>(
         container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
-    fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, planes, status);
+    // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
+    const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;
+    fz_bp_find_kernel<<<FZ_SM_COUNT * 4, FZ_BP_FIND_THREADS, 0, st>>>(container, container_size, stream_hdr, stream_off, b.bp, segs, status);
+    fz_bp_sort_kernel<<<FZ_SM_COUNT, FZ_BP_CAP / 2, 0, st>>>(b.bp, status);
+    fz_bp_sync_kernel<false><<<FZ_SM_COUNT * 4, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
+    fz_bp_chain_kernel<<<FZ_SM_COUNT, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, status);
+    fz_bp_sync_kernel<true><<<FZ_SM_COUNT * 4, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
+    fz_bp_stored_kernel<<<FZ_SM_COUNT * 4, 128, 0, st>>>(container, container_size, g, stream_off, b.bp, planes, status);
+    if (mark) mark(mark_user, FZ_ST_INFLATE_BLOCKPAR);
+    fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, b.bp.par_ok, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_GENERAL);
     if (copy_raw) {  // only when the merge cannot read RAW payloads in place (chunk size not a multiple of 16)
         const uint32_t total = nstreams * g.nsub_full;

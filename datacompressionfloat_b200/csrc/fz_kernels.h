@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "fz_common.cuh"
+#include "fz_blockpar.cuh"
 
 // geometry of one batch of chunks handed to the kernels
 struct FzBatchGeom {
@@ -27,14 +28,14 @@ struct FzStatus {
     unsigned int n_fast_failed;   // streams whose sub-block decode failed validation and fell back
     unsigned int n_stored_sub;    // sub-blocks emitted as stored blocks
     unsigned int n_raw_streams;   // streams written RAW
-    unsigned int pad;
+    unsigned int n_blockpar;      // general streams decoded block-parallel (the rest took the serial inflater)
 };
 
 // optional per-stage timing hook: called after the launches of a stage were enqueued
 typedef void (*fz_mark_fn)(void *user, int stage);
 enum {
     FZ_ST_SPLIT = 0, FZ_ST_ENCODE, FZ_ST_LAYOUT, FZ_ST_GATHER,
-    FZ_ST_WALK, FZ_ST_MARKERS, FZ_ST_CLASSIFY, FZ_ST_INFLATE_FAST, FZ_ST_INFLATE_GENERAL, FZ_ST_RAWCOPY, FZ_ST_MERGE,
+    FZ_ST_WALK, FZ_ST_MARKERS, FZ_ST_CLASSIFY, FZ_ST_INFLATE_FAST, FZ_ST_INFLATE_BLOCKPAR, FZ_ST_INFLATE_GENERAL, FZ_ST_RAWCOPY, FZ_ST_MERGE,
     FZ_ST_COUNT
 };
 
@@ -63,6 +64,27 @@ void fz_launch_gather(const uint8_t *planes, const uint8_t *scratch, const uint3
 void fz_launch_walk(const uint8_t *container, uint64_t container_size, FzBatchGeom g, uint32_t *stream_hdr,
                     unsigned long long *stream_off, FzStatus *status, cudaStream_t st);
 // marker scan (count), scan, marker scan (write), classify, fast inflate, general inflate, RAW copy
+// scratch of the block-parallel inflate of zlib-made streams (fz_blockpar.cuh)
+#define FZ_BP_CAP 512          // candidate blocks per stream (a 6 MiB plane is ~190 zlib blocks)
+#define FZ_BP_STORED_CAP 128   // stored blocks per stream met on the chain
+struct FzBlockParBufs {
+    uint32_t *ctl;         // counters, zeroed per batch: FZ_BP_CTL_*
+    uint32_t *gen_list;    // [nstreams] streams classified "general"
+    uint32_t *cand_cnt;    // [nstreams]
+    uint32_t *nstored;     // [nstreams]
+    uint32_t *par_ok;      // [nstreams] 1 = decoded block-parallel
+    uint32_t *cand_pos;    // [nstreams * FZ_BP_CAP] bit positions, ascending after the sort
+    FzBlockInfo *info;     // [nstreams * FZ_BP_CAP]
+    uint32_t *blk_off;     // [nstreams * FZ_BP_CAP] output offset, ~0 = not on the chain
+    int *blk_prev;         // [nstreams * FZ_BP_CAP] byte before the block, -1 = none
+    FzStoredItem *stored;  // [nstreams * FZ_BP_STORED_CAP]
+    uint32_t *items;       // [2][nstreams * FZ_BP_CAP] work lists (block slot indices) of the measure / write pass
+    uint32_t nstreams;
+};
+enum { FZ_BP_CTL_NGEN = 0, FZ_BP_CTL_NMEASURE, FZ_BP_CTL_CUR_MEASURE, FZ_BP_CTL_NWRITE, FZ_BP_CTL_CUR_WRITE };
+size_t fz_blockpar_bytes(uint32_t nstreams);
+FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams);
+
 struct FzInflateBufs {
     uint32_t *tile_cnt;      // [nstreams * tiles_per_stream + 1] counts -> exclusive offsets
     uint32_t *block_sums;    // scan scratch
@@ -71,6 +93,7 @@ struct FzInflateBufs {
     uint32_t *stream_mode;   // [nstreams] 0 raw, 1 fast | sub_log2 << 8, 2 general
     uint32_t *stream_fail;   // [nstreams]
     uint32_t tiles_per_stream;
+    FzBlockParBufs bp;
 };
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status,

@@ -29,7 +29,7 @@ class MzbError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("chunks", C.c_uint32), ("streams", C.c_uint32),
                 ("raw_streams", C.c_uint32), ("stored_subblocks", C.c_uint32), ("general_streams", C.c_uint32),
-                ("fast_failed", C.c_uint32), ("kernel_launches", C.c_uint32), ("pad", C.c_uint32)]
+                ("fast_failed", C.c_uint32), ("kernel_launches", C.c_uint32), ("blockpar_streams", C.c_uint32)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "pad"}

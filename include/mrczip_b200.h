@@ -138,7 +138,8 @@ int mzb_decompress_device(mzb_ctx *ctx, const void *d_in, size_t in_size, int ha
                           uint64_t nwords, void *d_words_out, uint64_t out_cap_words, uint64_t *nwords_out);
 
 /* Intermediates, for parity checks against the reference's split/merge (workers.c:180-203, 423-442):
- * d_planes holds 4 planes of nwords bytes, plane j at d_planes + j * plane_stride (stride % 16 == 0). */
+ * d_planes holds 4 planes of nwords bytes, plane j at d_planes + j * plane_stride (stride % 16 == 0).
+ * Asynchronous on a caller-provided stream (mzb_create_on_stream); a context with its own stream synchronises. */
 int mzb_mask_split_device(mzb_ctx *ctx, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,
                           void *d_planes, uint64_t plane_stride);
 int mzb_merge_device(mzb_ctx *ctx, const void *d_planes, uint64_t plane_stride, uint64_t nwords, void *d_words_out);
@@ -161,10 +162,10 @@ typedef struct {
     uint32_t chunks, streams;
     uint32_t raw_streams;      /* streams written RAW (zip.c:186-190) */
     uint32_t stored_subblocks; /* sub-blocks emitted as stored deflate blocks */
-    uint32_t general_streams;  /* decode: streams that took the one-thread-per-stream inflater */
+    uint32_t general_streams;  /* decode: streams not in this library's sub-block framing (e.g. written by the reference's zlib) */
     uint32_t fast_failed;      /* decode: streams whose sub-block decode failed validation (fell back) */
     uint32_t kernel_launches;  /* kernels launched by the call */
-    uint32_t pad;
+    uint32_t blockpar_streams; /* decode: general streams inflated block-parallel (the rest: one thread per stream) */
 } mzb_stats;
 int mzb_last_stats(mzb_ctx *ctx, mzb_stats *out);
 

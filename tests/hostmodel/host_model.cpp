@@ -2,6 +2,9 @@
 // logic of the GPU encoder / inflater can be checked against zlib without a GPU.
 // TEST INFRASTRUCTURE ONLY (built by tests/hostmodel/build.py into tests/hostmodel/libhostmodel.so);
 // the product never loads it.
+#define FZ_SY_STATS 1
+#include <cstdio>
+#include <cstdlib>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -9,6 +12,7 @@
 
 #include "../../datacompressionfloat_b200/csrc/fz_deflate_enc.cuh"
 #include "../../datacompressionfloat_b200/csrc/fz_inflate.cuh"
+#include "../../datacompressionfloat_b200/csrc/fz_blockpar.cuh"
 
 namespace {
 struct HostLoad16 {
@@ -137,6 +141,83 @@ uint32_t hm_check_marker(const uint8_t *frag, uint32_t total_bytes)
     return es.false_marker;
 }
 uint32_t hm_put_stored(const uint8_t *in, uint32_t n, uint8_t *out) { return (uint32_t)put_stored(out, in, n); }
+
+// block-parallel inflate of a zlib-made stream, exactly the four stages the GPU runs (candidates, measure,
+// chain, write); returns 0, a negative chain code (the GPU would take the serial path), or 100+ on a write error
+void hm_sy_stats(uint64_t *o) { o[0] = fz_sy_stat_tiles; o[1] = fz_sy_stat_rounds; o[2] = fz_sy_stat_redos; o[3] = fz_sy_stat_redo_lanes; }
+void hm_sy_stats_reset(void) { fz_sy_stat_tiles = fz_sy_stat_rounds = fz_sy_stat_redos = fz_sy_stat_redo_lanes = 0; }
+int hm_blockpar_sync = 1;      // 1: warp-synchronising block decoder (what the GPU runs), 0: serial per-block functions
+void hm_set_blockpar_sync(int on) { hm_blockpar_sync = on; }
+uint64_t hm_quick_passes = 0;  // positions that passed fz_block_quick_test in the last hm_inflate_blockpar call
+uint64_t hm_last_quick_passes(void) { return hm_quick_passes; }
+
+int hm_inflate_blockpar(const uint8_t *in_, uint32_t in_len, uint8_t *out_, uint32_t n_out, uint32_t *ncand_out, uint32_t *nfalse_out)
+{
+    std::vector<uint32_t> ibuf(in_len / 4 + 8, 0);
+    uint8_t *in = (uint8_t *)ibuf.data() + 3;  // misaligned on purpose
+    memcpy(in, in_, in_len);
+    std::vector<uint32_t> obuf(n_out / 4 + 4, 0xA5A5A5A5u);
+    uint8_t *out = (uint8_t *)obuf.data();
+    uint16_t ll[288], dd[32], cnt[32];
+    FzInfTab<1> tab{ll, dd, cnt};
+    std::vector<uint32_t> lut(FZ_LUT_SIZE);
+    auto byte_at = [&](uint64_t by) -> uint64_t { return by < in_len ? in[by] : 0; };
+    auto bits64 = [&](uint64_t bit) -> uint64_t {  // stream bits [bit, bit + 64), zero past the end
+        const uint64_t by = bit >> 3;
+        const unsigned sh = (unsigned)(bit & 7);
+        uint64_t v = 0;
+        for (int k = 0; k < 8; k++) v |= byte_at(by + k) << (8 * k);
+        return sh ? (v >> sh) | (byte_at(by + 8) << (64 - sh)) : v;
+    };
+    std::vector<uint32_t> cand;
+    hm_quick_passes = 0;
+    const uint64_t total_bits = (uint64_t)in_len * 8;
+    for (uint64_t bit = 0; bit + 17 <= total_bits; bit++) {
+        if (!fz_block_quick_test(bits64(bit), bits64(bit + 64))) continue;
+        hm_quick_passes++;
+        if (fz_block_candidate(in, in_len, bit, tab)) cand.push_back((uint32_t)bit);
+    }
+    const uint32_t ncand = (uint32_t)cand.size();
+    const uint32_t cap = ncand + 64;
+    cand.resize(cap);
+    std::vector<FzBlockInfo> info(cap);
+    std::vector<FzSyncState> sy(1);
+    for (uint32_t i = 0; i < ncand; i++) {
+        if (hm_blockpar_sync) {
+            fz_sy_block<false>(sy.data(), in, in_len, cand[i], nullptr, 0, -1, 0, &info[i], nullptr, 0);
+            FzBlockInfo ref;   // the serial measure must agree exactly
+            fz_block_measure(in, in_len, cand[i], tab, lut.data(), &ref);
+            const bool ref_usable = (ref.flags & FZ_BLK_OK) && !(ref.flags & FZ_BLK_NON_RLE);
+            const bool got_usable = (info[i].flags & FZ_BLK_OK) && !(info[i].flags & FZ_BLK_NON_RLE);
+            if (ref_usable != got_usable) return 1000 + (int)i;
+            if (ref_usable && (ref.end_bit != info[i].end_bit || ref.out_len != info[i].out_len || ref.flags != info[i].flags ||
+                               ((ref.flags & FZ_BLK_HAS_LITERAL) && ref.last != info[i].last)))
+                return 2000 + (int)i;
+        } else fz_block_measure(in, in_len, cand[i], tab, lut.data(), &info[i]);
+    }
+    std::vector<uint32_t> off(cap);
+    std::vector<int> prev(cap);
+    std::vector<FzStoredItem> stored(64);
+    uint32_t nst = 0, nblocks = 0;
+    const int rc = fz_chain_resolve(in, in_len, n_out, cand.data(), info.data(), ncand, cap, &nblocks, off.data(), prev.data(),
+                                    stored.data(), 64, &nst, tab);
+    *ncand_out = ncand;
+    uint32_t nfalse = 0;
+    for (uint32_t i = 0; i < ncand; i++) nfalse += off[i] == 0xFFFFFFFFu;
+    *nfalse_out = nfalse;
+    if (rc != 0) return rc;
+    for (uint32_t i = 0; i < nblocks; i++) {
+        if (off[i] == 0xFFFFFFFFu) continue;
+        if (hm_blockpar_sync) {
+            bool ok = false;
+            fz_sy_block<true>(sy.data(), in, in_len, cand[i], out + off[i], info[i].out_len, prev[i], info[i].end_bit, nullptr, &ok, 0);
+            if (!ok) return 100 + (int)i;
+        } else if (!fz_block_write(in, in_len, cand[i], tab, lut.data(), out + off[i], info[i].out_len, prev[i], info[i].end_bit)) return 100 + (int)i;
+    }
+    for (uint32_t k = 0; k < nst; k++) memcpy(out + stored[k].out_off, in + stored[k].src_byte, stored[k].len);
+    memcpy(out_, out, n_out);
+    return 0;
+}
 
 uint32_t hm_sub_bytes(void) { return FZ_SUB; }
 uint32_t hm_group_subs(void) { return FZ_GROUP_SUBS; }

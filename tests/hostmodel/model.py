@@ -47,3 +47,16 @@ def put_stored(a: np.ndarray) -> np.ndarray:
     out = np.empty(a.size + 32, dtype=np.uint8)
     n = _L.hm_put_stored(a.ctypes.data, a.size, out.ctypes.data)
     return out[:n].copy()
+
+
+_L.hm_inflate_blockpar.restype = C.c_int
+_L.hm_inflate_blockpar.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+
+
+def inflate_blockpar(b: np.ndarray, n_out: int):
+    """-> (rc, bytes, candidates found, candidates off the chain)"""
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.zeros(n_out + 8, dtype=np.uint8)
+    nc, nf = C.c_uint32(), C.c_uint32()
+    rc = _L.hm_inflate_blockpar(b.ctypes.data, b.size, out.ctypes.data, n_out, C.byref(nc), C.byref(nf))
+    return rc, out[:n_out].copy(), int(nc.value), int(nf.value)

@@ -292,3 +292,40 @@ def test_no_gpu_fails_loudly():
     from datacompressionfloat_b200 import Codec, MzbError
     with pytest.raises(MzbError):
         Codec(0)
+
+
+# ----------------------------------------------------------------------------- block-parallel inflate of zlib-made streams (CPU model)
+def test_model_blockpar_inflate_of_reference_streams(hostmodel):
+    """Candidate search + measure + chain + write (fz_blockpar.cuh) on streams made with the reference's zlib
+    parameters; streams with other distances must be refused (the GPU then takes the serial inflater)."""
+    rng = np.random.default_rng(21)
+
+    def z(a, strat):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, strat)
+        return np.frombuffer(co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH), np.uint8)
+
+    cases = {
+        "exp": synth_words("G", 150000).view(np.uint8).reshape(-1, 4)[:, 3].copy(),       # several blocks
+        "counts": synth_words("P", 150000).view(np.uint8).reshape(-1, 4)[:, 2].copy(),
+        "zeros": np.zeros(300000, np.uint8),                                                 # run continues across blocks
+        "runs": np.repeat(rng.integers(0, 256, 2000).astype(np.uint8), rng.integers(1, 400, 2000))[:200000],
+        "stored_mix": np.concatenate([rng.integers(0, 256, 70000).astype(np.uint8), rng.choice([1, 2, 3], 90000).astype(np.uint8),
+                                      rng.integers(0, 256, 40000).astype(np.uint8)]),
+    }
+    for name, a in cases.items():
+        c = z(a, zlib.Z_RLE)
+        rc, o, ncand, noff = hostmodel.inflate_blockpar(c, a.size)
+        assert rc == 0 and np.array_equal(o, a), (name, rc)
+        assert ncand >= 1
+    # fixed-Huffman block (zlib picks it for tiny inputs): no header to search for, measured by the chain walk itself
+    tiny = np.array([5, 5, 5, 5, 5, 9], np.uint8)
+    rc, o, ncand, _ = hostmodel.inflate_blockpar(z(tiny, zlib.Z_RLE), tiny.size)
+    assert rc == 0 and ncand == 0 and np.array_equal(o, tiny)
+    # default strategy = long distances: refused, never wrong
+    a = np.tile(np.arange(200, dtype=np.uint8), 600)
+    rc, _, _, _ = hostmodel.inflate_blockpar(z(a, zlib.Z_DEFAULT_STRATEGY), a.size)
+    assert rc < 0
+    # truncated stream: refused
+    c = z(cases["exp"], zlib.Z_RLE)
+    rc, _, _, _ = hostmodel.inflate_blockpar(c[: c.size // 2], cases["exp"].size)
+    assert rc != 0

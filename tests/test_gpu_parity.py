@@ -141,7 +141,64 @@ def test_reference_container_decodes_on_gpu(codec, oracle, kind, bits, chk):
     back = codec.decompress(torch.from_numpy(ref_cont).cuda())
     assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(src, bits))
     st = codec.stats()
-    assert st["general_streams"] > 0 or kind == "R"           # zlib streams take the general inflater
+    assert st["general_streams"] > 0 or kind == "R"           # zlib streams are not in our sub-block framing
+    assert st["blockpar_streams"] <= st["general_streams"]
+
+
+def _zlib_container(words, chk, strategy):
+    """A container in the reference's layout whose payloads come from Python's zlib (any strategy)."""
+    import struct
+    import zlib
+    src = words.view(np.uint8)
+    out = [struct.pack("<QIB4B", src.size, chk, 0, 0, 0, 0, 0)]       # common.c:137-149: type 0, ztypes 0 (zlib)
+    for c0 in range(0, words.size, chk):
+        planes = words[c0:c0 + chk].view(np.uint8).reshape(-1, 4)
+        hdr, payloads = [], []
+        for j in range(4):
+            p = planes[:, j].tobytes()
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, strategy)
+            z = co.compress(p) + co.flush(zlib.Z_FULL_FLUSH)
+            if len(p) > len(z) + 4:
+                hdr.append(len(z)); payloads.append(z)
+            else:
+                hdr.append(len(p) | 0x80000000); payloads.append(p)
+        out.append(struct.pack("<4I", *hdr) + b"".join(payloads))
+    return np.frombuffer(b"".join(out), np.uint8)
+
+
+@pytest.mark.parametrize("kind,bits", [("G", 8), ("P", 0), ("S", 12), ("Z", 0)])
+def test_reference_streams_inflate_block_parallel(codec, oracle, kind, bits):
+    """Multi-block zlib streams (Z_RLE, what the reference writes): every one is found, chained and decoded
+    block-parallel; nothing is left to the one-thread-per-stream inflater."""
+    w = synth_words(kind, 3 * 1048576 + 500000 - 256)          # last chunk ragged but longer than one sub-block
+    src = w.view(np.uint8)
+    ref_cont = oracle.compress(src, bits, chk=1048576)
+    back = codec.decompress(torch.from_numpy(ref_cont).cuda())
+    assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(src, bits))
+    st = codec.stats()
+    _, _, streams = oracle.parse_container(ref_cont)
+    ncomp = sum(1 for s in streams if not s["raw"])
+    assert st["general_streams"] == ncomp
+    assert st["blockpar_streams"] == ncomp, st              # incl. streams with fixed-Huffman blocks (S plane 2)
+
+
+def test_default_strategy_streams_take_the_serial_inflater(codec, oracle):
+    """Streams with long-distance matches (not what the reference writes, but legal deflate) are refused by the
+    block-parallel path and decoded by the serial inflater: same bytes."""
+    import zlib
+    w = np.tile(synth_words("P", 4096), 100)[: 300000]
+    masked = oracle.erasebytes(w.view(np.uint8), 0).view(np.uint32)
+    cont = _zlib_container(masked, 131072, zlib.Z_DEFAULT_STRATEGY)
+    back = codec.decompress(torch.from_numpy(cont).cuda())
+    assert np.array_equal(host_u32(back), masked)
+    st = codec.stats()
+    assert st["general_streams"] > 0 and st["blockpar_streams"] < st["general_streams"]
+    # the same data with Z_RLE payloads goes block-parallel
+    cont = _zlib_container(masked, 131072, zlib.Z_RLE)
+    back = codec.decompress(torch.from_numpy(cont).cuda())
+    assert np.array_equal(host_u32(back), masked)
+    st = codec.stats()
+    assert st["blockpar_streams"] > 0
 
 
 def test_reference_binary_container_decodes_on_gpu(codec, oracle):
