@@ -349,9 +349,9 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
         (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
         (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib->hits_cap * 4)) ||
-        (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams))))
+        (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams, chk))))
         return rc;
-    ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams);
+    ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams, chk);
     ib->tile_cnt = (uint32_t *)c->tile_cnt.p;
     ib->block_sums = (uint32_t *)c->block_sums.p;
     ib->hits = (uint32_t *)c->hits.p;

@@ -67,6 +67,86 @@ FZ_HD bool fz_block_quick_test(uint64_t lo, uint64_t hi, const uint8_t *kraft_lu
     return kraft == 128u;
 }
 
+// Per-thread 128-entry table for the code-length code (7-bit index -> symbol | length << 5), STRIDE threads
+// interleaved word by word so that the lanes of a warp never collide on a bank.
+template <int STRIDE>
+struct FzClLut {
+    uint8_t *base;   // this thread's first word
+    FZ_HD uint8_t &at(uint32_t e) const { return base[(e >> 2) * (STRIDE * 4) + (e & 3u)]; }
+};
+
+// Second-stage test of a position that passed fz_block_quick_test: walk the code-length data of the header with
+// registers and the small table only -- no symbol tables are built -- and apply the same acceptance rules as
+// fz_block_candidate (a complete literal/length code with an end-of-block symbol, distances not over-subscribed).
+// ~30x cheaper than the full parse, and it rejects practically everything that is not a real header.
+template <class ClLut>
+FZ_HD bool fz_block_precheck(const uint8_t *in, size_t in_len, uint64_t bit, const ClLut &lut)
+{
+    FzBitReader br;
+    br.init(in + (bit >> 3), in_len - (size_t)(bit >> 3));
+    br.refill();
+    br.drop((int)(bit & 7));
+    br.refill();
+    br.drop(3);                                  // BFINAL, BTYPE (checked by the quick test)
+    const uint32_t hlit = br.get(5) + 257, hdist = br.get(5) + 1, hclen = br.get(4) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) | (9ull << 30) |
+                              (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
+    const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+    uint64_t clpack = 0;                         // 3 bits per symbol
+    for (uint32_t i = 0; i < hclen; i++) {
+        br.refill();
+        const uint32_t sym = (uint32_t)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31u);
+        clpack |= (uint64_t)br.get(3) << (3 * sym);
+    }
+    // canonical codes of the code-length code -> table (the quick test made sure the code is complete)
+    uint64_t ccnt = 0;                           // 8 bits per length 0..7
+    for (int sy = 0; sy < 19; sy++) ccnt += 1ull << (8 * ((clpack >> (3 * sy)) & 7u));
+    uint64_t next = 0;                           // next code per length, 8 bits each
+    {
+        uint32_t code = 0;
+        for (int l = 1; l <= 7; l++) {
+            code = (code + (uint32_t)((ccnt >> (8 * (l - 1))) & 0xffu) * (l > 1 ? 1u : 0u)) << 1;
+            next |= (uint64_t)(code & 0xffu) << (8 * l);
+        }
+    }
+    for (uint32_t sy = 0; sy < 19; sy++) {
+        const uint32_t l = (uint32_t)((clpack >> (3 * sy)) & 7u);
+        if (!l) continue;
+        const uint32_t c = (uint32_t)((next >> (8 * l)) & 0xffu);
+        next += 1ull << (8 * l);
+        uint32_t rev = 0;
+        for (uint32_t k = 0; k < l; k++) rev |= ((c >> k) & 1u) << (l - 1 - k);
+        for (uint32_t e = rev; e < 128u; e += 1u << l) lut.at(e) = (uint8_t)(sy | (l << 5));
+    }
+    const uint32_t total = hlit + hdist;
+    uint32_t i = 0, prev = 0, kll = 0, kdd = 0, eob = 0;
+    while (i < total) {
+        br.refill();
+        const uint32_t e = lut.at(br.peek(7));
+        br.drop((int)(e >> 5));
+        const uint32_t sy = e & 31u;
+        uint32_t rep = 1, val = sy;
+        if (sy >= 16) {
+            if (sy == 16 && i == 0) return false;
+            const int nb = sy == 16 ? 2 : (sy == 17 ? 3 : 7);
+            rep = (sy == 18 ? 11u : 3u) + br.get(nb);
+            val = sy == 16 ? prev : 0u;
+        }
+        if (i + rep > total) return false;
+        prev = val;
+        if (val) {
+            const uint32_t n_ll = i < hlit ? (rep < hlit - i ? rep : hlit - i) : 0u;
+            kll += n_ll << (15 - val);
+            kdd += (rep - n_ll) << (15 - val);
+            if (i <= FZ_EOB && FZ_EOB < i + rep) eob = val;
+            if (kll > 32768u || kdd > 32768u) return false;   // over-subscribed
+        }
+        i += rep;
+    }
+    return kll == 32768u && eob != 0 && br.bits_left() >= 0;
+}
+
 // full validation: parse the header exactly like the inflater would
 template <class Tab>
 FZ_HD bool fz_block_candidate(const uint8_t *in, size_t in_len, uint64_t bit, const Tab &tab)
@@ -220,6 +300,7 @@ FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, u
 #endif
 
 #define FZ_BP_SUB_BITS 2048u
+#define FZ_BP_PROBE_BITS 320u
 #define FZ_SY_EOB 1u        // the sub-range ended with the end-of-block symbol
 #define FZ_SY_ERR 2u        // decode error (normal for a speculative start; fatal once the parse is settled)
 #define FZ_SY_NONRLE 8u
@@ -231,18 +312,51 @@ FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, u
 static uint64_t fz_sy_stat_tiles, fz_sy_stat_rounds, fz_sy_stat_redos, fz_sy_stat_redo_lanes;
 #endif
 
+// What the measure pass learned about one tile, kept for the write pass (which then decodes every sub-range
+// exactly once): where each sub-range really starts, where its bytes go, the byte before it.
+struct FzTileRec {
+    uint32_t next;        // index of the block's next tile record, FZ_TILE_NONE at the end
+    uint32_t last_lane;   // sub-ranges 0 .. last_lane belong to the block
+    uint32_t has_eob;     // the last one ends with the end-of-block symbol
+    uint32_t end_bit;     // where the last sub-range stopped
+    uint32_t total;       // bytes of the tile
+    uint32_t pad[3];
+    uint32_t start[32];
+    uint32_t off[32];     // byte offset from the start of the block
+    uint16_t prev[32];    // byte before the sub-range + 1, 0 = the byte before the block (or nothing)
+};
+#define FZ_TILE_NONE 0xFFFFFFFFu
+
+struct FzTilePool {
+    FzTileRec *recs;
+    uint32_t cap;
+    uint32_t *cursor;     // bump allocator (atomic on the device)
+};
+
 struct FzSyncState {
     uint32_t lut[FZ_LUT_SIZE];
     uint16_t tab[FZ_INF_TAB_U16];
     FzCode LL, DD;
     uint32_t start[32], end[32], n[32], flags[32], lastc[32], want[32], off[32];
+    uint32_t rend[32];   // the sub-range of a lane ends at the first symbol boundary >= rend[lane]
     int prev[32];
     // written by lane 0 in dedicated phases, read by everybody afterwards
-    uint32_t hdr_ok, hdr_end, is_last;
+    uint32_t hdr_ok, hdr_end, is_last, dd1;
     uint32_t any_redo;
     uint32_t tile_total, tile_eob_lane, tile_err, tile_nonrle, tile_werr;
     int tile_carry;
+    uint32_t rec_idx, rec_prev;   // tile record being written / the one before it
 };
+
+FZ_HD uint32_t fz_tile_alloc(const FzTilePool &pool)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t i = atomicAdd(pool.cursor, 1u);
+#else
+    const uint32_t i = (*pool.cursor)++;
+#endif
+    return i < pool.cap ? i : FZ_TILE_NONE;
+}
 
 FZ_HD_NOINLINE void fz_sy_ph_header(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t bit, int lane)
 {
@@ -258,6 +372,7 @@ FZ_HD_NOINLINE void fz_sy_ph_header(FzSyncState *st, const uint8_t *in, uint32_t
     st->is_last = inf.last ? 1u : 0u;
     st->LL = inf.LL;
     st->DD = inf.DD;
+    st->dd1 = inf.dd1;
 }
 
 FZ_HD void fz_sy_ph_lut(FzSyncState *st, int lane)
@@ -268,15 +383,23 @@ FZ_HD void fz_sy_ph_lut(FzSyncState *st, int lane)
 }
 
 // decode the sub-range of `lane` in tile `tile_pos` from st->start[lane]; out == nullptr: count only
-FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, bool active, uint8_t *out, int lane)
+// probe = true: decode FZ_BP_PROBE_BITS from the grid position of the lane and leave the boundary reached there in
+// st->start[lane] -- by then the parse has almost surely fallen into step with the true one, so the counting pass
+// that follows starts most lanes on a true symbol boundary and only the unlucky ones have to be redone.
+FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, bool active, uint8_t *out, int lane,
+                                 bool probe = false)
 {
     typedef FzInfTab<1> Tab;
     const Tab tab{st->tab, st->tab + 288, st->tab + 320};
-    const uint32_t start = st->start[lane];
-    const uint64_t range_end = (uint64_t)tile_pos + (uint64_t)(lane + 1) * FZ_BP_SUB_BITS;
+    const uint32_t grid = tile_pos + (uint32_t)lane * FZ_BP_SUB_BITS;
+    const uint32_t start = probe ? grid : st->start[lane];
+    const uint64_t range_end = probe ? (uint64_t)grid + FZ_BP_PROBE_BITS : (uint64_t)st->rend[lane];
     const bool write = out != nullptr;
     FzInflater<Tab> inf;
-    bool live = active && (uint64_t)start < range_end && (uint64_t)start < (uint64_t)in_len * 8;
+    // counting: the sub-range is [start, first symbol boundary >= range_end); writing: the bytes (and the
+    // end-of-block symbol) the counting pass recorded for it
+    bool live = active && (uint64_t)start < (uint64_t)in_len * 8 &&
+                (write ? (st->n[lane] != 0 || (st->flags[lane] & FZ_SY_EOB) != 0) : (uint64_t)start < range_end);
     const bool ran = live;
     int64_t stop_left = 0;   // bits_left() value at which the sub-range is finished
     if (live) {
@@ -289,9 +412,11 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
         inf.last = st->is_last != 0;
         inf.LL = st->LL;
         inf.DD = st->DD;
+        inf.dd1 = st->dd1;
         stop_left = (int64_t)in_len * 8 - (int64_t)range_end;
     }
     const uint32_t *lut = st->lut;
+    const uint32_t run_bit = fz_dd1_run_bit(st->dd1);
     // Lock-step drive as in the sub-block inflater: a register-only run of up to 16 table hits (1-3 literals each),
     // then one general step (long code, match, end of block), then the lanes re-vote.
     if (write) {
@@ -299,7 +424,6 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
         // stop by the byte count it recorded, not by position (plus the end-of-block symbol if it saw one)
         const uint32_t n_goal = st->n[lane];
         const bool want_eob = (st->flags[lane] & FZ_SY_EOB) != 0;
-        if (live && n_goal == 0 && !want_eob) live = false;
         while (FZ_WARP_ANY(live)) {
             if (live) {
 #pragma unroll 1
@@ -307,7 +431,20 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
                     inf.br.refill();
                     const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
                     const uint32_t cnt = e >> 29;
-                    if (e == 0 || (e & 511u) >= 256u || inf.bw.op + cnt > inf.bw.cap) break;
+                    if ((e & 511u) >= 256u) {
+                        // a distance-1 match whole: length code, its extra bits, the one distance bit
+                        if (!(e & FZ_LUT_MATCH) || run_bit > 1u) break;
+                        const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
+                        const uint32_t a = (uint32_t)(inf.br.acc >> cl);
+                        const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
+                        if (((a >> xb) & 1u) != run_bit || inf.bw.op + len > inf.bw.cap) break;
+                        const int pv = inf.bw.produced() ? (int)inf.bw.back(1) : inf.bw.prev_byte;
+                        if (pv < 0) break;   // nothing before the fragment to repeat: the general step reports it
+                        inf.br.drop((int)(cl + xb + 1u));
+                        inf.bw.fill((uint32_t)pv, len);
+                        continue;
+                    }
+                    if (e == 0 || inf.bw.op + cnt > inf.bw.cap) break;
                     inf.br.drop((int)((e >> 25) & 15u));
                     inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
                 }
@@ -330,7 +467,17 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
                     inf.br.refill();
                     if (inf.br.bits_left() <= near_left) break;
                     const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
-                    if (e == 0 || (e & 511u) >= 256u) break;
+                    if ((e & 511u) >= 256u) {
+                        if (!(e & FZ_LUT_MATCH) || run_bit > 1u) break;
+                        const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
+                        const uint32_t a = (uint32_t)(inf.br.acc >> cl);
+                        if (((a >> xb) & 1u) != run_bit) break;
+                        inf.br.drop((int)(cl + xb + 1u));
+                        if (inf.bw.op == 0) inf.bw.starts_with_match = true;
+                        inf.bw.op += ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
+                        continue;
+                    }
+                    if (e == 0) break;
                     inf.br.drop((int)((e >> 25) & 15u));
                     inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), e >> 29);
                 }
@@ -341,6 +488,11 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
         }
     }
     if (!active) return;
+    if (probe) {
+        const bool fine = ran && inf.rc == FZ_INF_OK && !inf.saw_eob;
+        st->start[lane] = fine ? (uint32_t)((int64_t)in_len * 8 - inf.br.bits_left()) : grid;
+        return;
+    }
     uint32_t f = st->flags[lane] & ~(FZ_SY_EOB | FZ_SY_ERR | FZ_SY_NONRLE | FZ_SY_SWM);
     if (!ran) {   // predecessor already reached past this sub-range (or the stream ended): nothing of it is ours
         if (!write) { st->end[lane] = start; st->n[lane] = 0; st->lastc[lane] = 0x100; st->flags[lane] = f; }
@@ -370,10 +522,18 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
     st->flags[lane] = f;
 }
 
+FZ_HD void fz_sy_ph_probe(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, int lane)
+{
+    st->flags[lane] = 0;
+    if (lane == 0) st->start[0] = tile_pos;   // the one position known to be a symbol boundary
+    fz_sy_decode(st, in, in_len, tile_pos, lane != 0, nullptr, lane, true);
+}
+FZ_HD void fz_sy_ph_ranges(FzSyncState *st, uint32_t tile_pos, int lane)
+{
+    st->rend[lane] = lane < 31 ? st->start[lane + 1] : tile_pos + 32u * FZ_BP_SUB_BITS;
+}
 FZ_HD void fz_sy_ph_spec(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, int lane)
 {
-    st->start[lane] = tile_pos + (uint32_t)lane * FZ_BP_SUB_BITS;
-    st->flags[lane] = 0;
     fz_sy_decode(st, in, in_len, tile_pos, true, nullptr, lane);
 }
 
@@ -447,16 +607,102 @@ FZ_HD void fz_sy_ph_werr(FzSyncState *st, int lane)
     st->tile_werr = w;
 }
 
+// measure pass: keep the settled tile for the write pass (lane 0 allocates and links, every lane stores its entry)
+FZ_HD void fz_sy_ph_record_alloc(FzSyncState *st, const FzTilePool &pool, int lane)
+{
+    if (lane != 0) return;
+    st->rec_prev = st->rec_idx;
+    st->rec_idx = fz_tile_alloc(pool);
+}
+FZ_HD void fz_sy_ph_record(FzSyncState *st, const FzTilePool &pool, uint32_t out_base, int lane)
+{
+    if (st->rec_idx == FZ_TILE_NONE) return;
+    FzTileRec *r = &pool.recs[st->rec_idx];
+    const uint32_t last = st->tile_eob_lane < 32u ? st->tile_eob_lane : 31u;
+    r->start[lane] = st->start[lane];
+    r->off[lane] = out_base + st->off[lane];
+    r->prev[lane] = (uint16_t)(st->prev[lane] + 1);
+    if (lane == 0) {
+        r->next = FZ_TILE_NONE;
+        r->last_lane = last;
+        r->has_eob = st->tile_eob_lane < 32u ? 1u : 0u;
+        r->end_bit = st->end[last];
+        r->total = st->tile_total;
+        if (st->rec_prev != FZ_TILE_NONE) pool.recs[st->rec_prev].next = st->rec_idx;
+    }
+}
+
+// write pass, table driven: load one tile record into the state the decode phase reads
+FZ_HD void fz_sy_ph_load(FzSyncState *st, const FzTileRec *r, uint32_t out_len, int block_prev, int lane)
+{
+    const uint32_t last = r->last_lane;
+    uint32_t f = 0;
+    if ((uint32_t)lane <= last) {
+        const uint32_t off = r->off[lane];
+        const uint32_t next_off = (uint32_t)lane < last ? r->off[lane + 1] : r->off[0] + r->total;
+        st->start[lane] = r->start[lane];
+        st->end[lane] = (uint32_t)lane < last ? r->start[lane + 1] : r->end_bit;
+        st->off[lane] = off - r->off[0];
+        st->n[lane] = next_off - off;
+        st->prev[lane] = r->prev[lane] ? (int)r->prev[lane] - 1 : block_prev;
+        if ((uint32_t)lane == last && r->has_eob) f |= FZ_SY_EOB;
+        if (next_off < off || next_off > out_len) f |= FZ_SY_WERR;   // corrupt record: refuse
+    }
+    st->flags[lane] = f;
+    if (lane == 0) st->tile_eob_lane = last;   // fz_sy_ph_write decodes lanes 0 .. tile_eob_lane
+}
+
+// Write pass over the records the measure pass left: one decode per sub-range, no searching.
+FZ_HD void fz_sy_block_from_table(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t bit, uint8_t *out, uint32_t out_len,
+                                  int prev_byte, uint32_t expect_end, const FzTilePool &pool, uint32_t first_rec, bool *ok, int lane)
+{
+    (void)lane;
+    FZ_PHASE(fz_sy_ph_header(st, in, in_len, bit, lane));
+    bool good = st->hdr_ok != 0;
+    uint32_t produced = 0, end_bit = bit, rec = first_rec;
+    bool done = false;
+    if (good) {
+        FZ_PHASE(fz_sy_ph_lut(st, lane));
+        for (uint32_t guard = 0; guard < pool.cap && good && !done; guard++) {
+            if (rec == FZ_TILE_NONE || rec >= pool.cap) { good = false; break; }
+            const FzTileRec *r = &pool.recs[rec];
+            if (r->off[0] != produced || r->last_lane > 31u) { good = false; break; }
+            FZ_PHASE(fz_sy_ph_load(st, r, out_len, prev_byte, lane));
+            // tile_pos is only used for the sub-range grid in counting mode; the write mode stops by byte count
+            FZ_PHASE(fz_sy_ph_write(st, in, in_len, 0u, out + produced, lane));
+            FZ_PHASE(fz_sy_ph_werr(st, lane));
+            if (st->tile_werr) { good = false; break; }
+            produced += r->total;
+            end_bit = r->end_bit;
+            if (r->has_eob) done = true;
+            rec = r->next;
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+        }
+    }
+    *ok = good && done && produced == out_len && end_bit == expect_end;
+}
+
 // Decode the block whose header starts at `bit`.
 //   WRITE = false: fills *bi (as fz_block_measure does);  WRITE = true: stores out[0, out_len), returns success
 // in *ok (end position must equal expect_end).  Called by all 32 lanes on the device, once on the host.
 template <bool WRITE>
 FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t bit, uint8_t *out, uint32_t out_len,
-                       int prev_byte, uint32_t expect_end, FzBlockInfo *bi, bool *ok, int lane)
+                       int prev_byte, uint32_t expect_end, FzBlockInfo *bi, bool *ok, int lane,
+                       const FzTilePool *pool = nullptr, uint32_t *first_rec = nullptr)
 {
     (void)lane;
     FZ_PHASE(fz_sy_ph_header(st, in, in_len, bit, lane));
     uint32_t flags = 0, produced = 0, end_bit = bit;
+    uint32_t rec0 = FZ_TILE_NONE;
+    bool table_ok = !WRITE && pool != nullptr;
+#if defined(__CUDA_ARCH__)
+    if (lane == 0) st->rec_idx = FZ_TILE_NONE;
+    __syncwarp();
+#else
+    st->rec_idx = FZ_TILE_NONE;
+#endif
     int carry = WRITE ? prev_byte : -1;
     bool good = st->hdr_ok != 0, done = false;
     if (good) {
@@ -464,6 +710,8 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
         uint32_t tile_pos = st->hdr_end;
         const uint32_t max_tiles = (uint32_t)(((uint64_t)in_len * 8 - tile_pos) / (32u * FZ_BP_SUB_BITS)) + 2u;
         for (uint32_t tile = 0; tile < max_tiles && good && !done; tile++) {
+            FZ_PHASE(fz_sy_ph_probe(st, in, in_len, tile_pos, lane));
+            FZ_PHASE(fz_sy_ph_ranges(st, tile_pos, lane));
             FZ_PHASE(fz_sy_ph_spec(st, in, in_len, tile_pos, lane));
 #if !defined(__CUDA_ARCH__) && defined(FZ_SY_STATS)
             fz_sy_stat_tiles++;
@@ -492,6 +740,14 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
                 FZ_PHASE(fz_sy_ph_werr(st, lane));
                 if (st->tile_werr) { good = false; break; }
             }
+            if (table_ok) {
+                FZ_PHASE(fz_sy_ph_record_alloc(st, *pool, lane));
+                if (st->rec_idx == FZ_TILE_NONE) table_ok = false;   // pool exhausted: the write pass will search again
+                else {
+                    if (tile == 0) rec0 = st->rec_idx;
+                    FZ_PHASE(fz_sy_ph_record(st, *pool, produced, lane));
+                }
+            }
             produced += total;
             carry = st->tile_carry;
             if (st->tile_eob_lane < 32u) { done = true; end_bit = st->end[st->tile_eob_lane]; }
@@ -516,5 +772,6 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
         bi->out_len = produced;
         bi->flags = flags;
         bi->last = carry >= 0 ? (uint32_t)carry : 0u;
+        if (first_rec) *first_rec = (good && table_ok) ? rec0 : FZ_TILE_NONE;
     }
 }

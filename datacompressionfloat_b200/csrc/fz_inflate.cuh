@@ -133,6 +133,7 @@ struct FzByteWriter {
 //   bits 29..30  count         : 1..3 symbols; entries with count > 1 hold literals only
 #define FZ_LUT_BITS 11
 #define FZ_LUT_SIZE (1 << FZ_LUT_BITS)
+#define FZ_LUT_MATCH (1u << 24)   // entry of a length symbol: bits 9..17 base length, bits 18..20 extra bit count
 #define FZ_LUT_ENTRY(s1, s2, s3, total, cnt) \
     ((uint32_t)(s1) | ((uint32_t)(s2) << 9) | ((uint32_t)(s3) << 17) | ((uint32_t)(total) << 25) | ((uint32_t)(cnt) << 29))
 
@@ -224,7 +225,21 @@ FZ_HD uint32_t fz_lut_entry(const FzCode &LL, const Tab &tab, uint32_t e)
             }
         }
     }
-    return FZ_LUT_ENTRY(s1, s2, s3, total, cnt);
+    uint32_t ent = FZ_LUT_ENTRY(s1, s2, s3, total, cnt);
+    // length symbols: base length and number of extra bits ride in the (otherwise empty) literal slots, so that the
+    // register-only loops can take a whole distance-1 match without leaving for the general step
+    if (s1 >= 257u && s1 <= 285u) ent |= FZ_LUT_MATCH | (fz_len_base(s1 - 257u) << 9) | (fz_len_extra_bits(s1 - 257u) << 18);
+    return ent;
+}
+
+// Which value of a 1-bit distance code means "distance 1" (what run-length streams use): 0 or 1, or 2 = this block's
+// distance code is not of that kind (see FzInflater::dd1).
+FZ_HD uint32_t fz_dd1_run_bit(uint32_t dd1)
+{
+    if (!dd1) return 2u;
+    if ((dd1 & 0xffu) == 0u) return 0u;
+    if (((dd1 >> 16) & 3u) == 2u && ((dd1 >> 8) & 0xffu) == 0u) return 1u;
+    return 2u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -248,6 +263,8 @@ struct FzInflater {
     bool one_block;     // stop after the first coded block (block-parallel decode of zlib-made streams)
     bool saw_eob;       // ... and it ended properly with its end-of-block symbol
     int ll_left, dd_left;  // Kraft remainders of the last dynamic header (0 = complete code)
+    uint32_t dd1;          // distance code with 1-bit codes only (what RLE-style streams carry): 1 << 31 | number of codes
+                           // << 16 | symbol of code '1' << 8 | symbol of code '0'; 0 = general code
     uint32_t eob_len;      // code length of the end-of-block symbol in the last header
 
     FZ_HD void start(const uint8_t *in, size_t in_len_, uint8_t *out, uint32_t out_cap, const Tab &t)
@@ -261,7 +278,7 @@ struct FzInflater {
         in_body = false;
         shared_tab = false;
         own_lut = nullptr;
-        one_block = false; saw_eob = false; ll_left = 0; dd_left = 0; eob_len = 1;
+        one_block = false; saw_eob = false; ll_left = 0; dd_left = 0; eob_len = 1; dd1 = 0;
     }
     // start `bit` bits into the input (block-parallel decode)
     FZ_HD void start_at_bit(const uint8_t *in, size_t in_len_, uint64_t bit, uint8_t *out, uint32_t out_cap, const Tab &t)
@@ -340,10 +357,17 @@ struct FzInflater {
         if (sym >= 29) return fail(FZ_INF_E_DATA);
         br.refill();
         const uint32_t len = fz_len_base(sym) + br.get((int)fz_len_extra_bits(sym));
-        l = fz_decode_idx(DD, br.peek(15), idx);
-        if (l == 0) return fail(FZ_INF_E_DATA);
-        br.drop(l);
-        const uint32_t ds = tab.D((int)idx);
+        uint32_t ds;
+        if (dd1) {
+            const uint32_t b = br.get(1);
+            if (b >= ((dd1 >> 16) & 3u)) return fail(FZ_INF_E_DATA);
+            ds = (dd1 >> (8 * b)) & 0xffu;
+        } else {
+            l = fz_decode_idx(DD, br.peek(15), idx);
+            if (l == 0) return fail(FZ_INF_E_DATA);
+            br.drop(l);
+            ds = tab.D((int)idx);
+        }
         if (ds >= 30) return fail(FZ_INF_E_DATA);
         br.refill();
         const uint32_t dist = fz_dist_base(ds) + br.get((int)fz_dist_extra_bits(ds));
@@ -400,6 +424,7 @@ struct FzInflater {
             for (int l = 0; l < 32; l++) tab.C(l) = 0;
             tab.C(7) = 24; tab.C(8) = 152; tab.C(9) = 112;
             tab.C(16 + 5) = 32;
+            dd1 = 0;
             fz_code_build(LL, rd_ll, wr_ll);
             fz_code_build(DD, rd_dd, wr_dd);
             for (int i = 0; i < 24; i++) tab.L(i) = (uint16_t)(256 + i);
@@ -447,6 +472,10 @@ struct FzInflater {
         for (int pass = 0; pass < 2; pass++) {
             if (pass == 0) { for (int l = 0; l < 32; l++) tab.C(l) = 0; }
             else {
+                uint32_t dlong = 0;   // distance codes longer than one bit
+                for (int l = 2; l <= 15; l++) dlong += tab.C(16 + l);
+                const uint32_t d1 = tab.C(16 + 1);
+                dd1 = (dlong == 0 && d1 >= 1 && d1 <= 2) ? (0x80000000u | (d1 << 16)) : 0u;
                 const int e1 = fz_code_build(LL, rd_ll, wr_ll);
                 const int e2 = fz_code_build(DD, rd_dd, wr_dd);
                 if (e1 < 0 || e2 < 0) return fail(FZ_INF_E_DATA);  // over-subscribed
@@ -482,6 +511,7 @@ struct FzInflater {
             }
             if (br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
         }
+        if (dd1) dd1 |= (uint32_t)tab.D(0) | ((dd1 >> 16) & 2u ? (uint32_t)tab.D(1) << 8 : 0u);   // symbols are < 30
         if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(LL, tab, e);
         in_body = true;
         return true;

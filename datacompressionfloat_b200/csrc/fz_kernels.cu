@@ -1074,6 +1074,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
         hdr_bits = __shfl_sync(0xffffffffu, hdr_bits, leader);
         FZ_BCAST_CODE(inf.LL, leader)
         FZ_BCAST_CODE(inf.DD, leader)
+        inf.dd1 = __shfl_sync(0xffffffffu, inf.dd1, leader);
         if (!leader_ok) {
             if (coded) { bad = true; live = false; }
         } else {
@@ -1103,6 +1104,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     }
     // lock-step drive: lanes reconverge after every symbol
     const uint32_t *lut = coded_mask ? sm->lut : nullptr;
+    const uint32_t run_bit = fz_dd1_run_bit(inf.dd1);
     while (__any_sync(0xffffffffu, live)) {
         if (live) {
             if (inf.in_body && lut) {
@@ -1112,7 +1114,18 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                     inf.br.refill();
                     const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
                     const uint32_t cnt = e >> 29;
-                    if (e == 0 || (e & 511u) >= 256u || inf.bw.op + cnt > inf.bw.cap) break;
+                    if ((e & 511u) >= 256u) {
+                        // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
+                        if (!(e & FZ_LUT_MATCH) || run_bit > 1u) break;
+                        const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
+                        const uint32_t a = (uint32_t)(inf.br.acc >> cl);
+                        const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
+                        if (((a >> xb) & 1u) != run_bit || inf.bw.op + len > inf.bw.cap || inf.bw.produced() == 0) break;
+                        inf.br.drop((int)(cl + xb + 1u));
+                        inf.bw.fill(inf.bw.back(1), len);
+                        continue;
+                    }
+                    if (e == 0 || inf.bw.op + cnt > inf.bw.cap) break;
                     inf.br.drop((int)((e >> 25) & 15u));
                     // sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that count)
                     inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
@@ -1172,26 +1185,30 @@ __device__ __forceinline__ uint32_t fz_bp_stream_n(const FzBatchGeom &g, uint32_
     return (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
 }
 
-// candidates: every bit position p of the payload with a plausible dynamic-block header
+// candidates: every bit position p of the payload with a plausible dynamic-block header.
+// Three stages: (1) all 32 positions of a word against the fixed header fields and the Kraft sum of the
+// code-length code (registers + a 512-byte table); (2) survivors (~0.1 % of the positions) are queued per warp and,
+// 32 at a time, walk the code-length data with a 128-byte per-thread table (fz_block_precheck); (3) what is left
+// (real headers, practically) gets the inflater's own header parse, one lane at a time.
 __global__ void __launch_bounds__(FZ_BP_FIND_THREADS)
 fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size, const uint32_t *__restrict__ stream_hdr,
                   const unsigned long long *__restrict__ stream_off, FzBlockParBufs bp, uint32_t segs_per_stream,
                   const FzStatus *status)
 {
-    __shared__ uint16_t tabs[FZ_BP_FIND_THREADS * FZ_INF_TAB_U16];   // per-thread tables, interleaved (no bank conflicts)
+    __shared__ uint16_t tabs[FZ_BP_FIND_THREADS / 32][FZ_INF_TAB_U16];   // one full-parse table per warp
+    __shared__ uint32_t cl_luts[32 * FZ_BP_FIND_THREADS];                 // 128 bytes per thread, word-interleaved
     __shared__ uint32_t queue[FZ_BP_FIND_THREADS / 32][FZ_BP_QCAP];
     __shared__ uint32_t qn[FZ_BP_FIND_THREADS / 32];
     __shared__ uint8_t kraft_lut[512];
     const uint32_t ngen = bp.ctl[0];
     if (ngen == 0 || status->error) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint16_t *mine = tabs + threadIdx.x;
-    const FzInfTab<FZ_BP_FIND_THREADS> tab{mine, mine + 288 * FZ_BP_FIND_THREADS, mine + 320 * FZ_BP_FIND_THREADS};
-    for (uint32_t i = threadIdx.x; i < 512; i += FZ_BP_FIND_THREADS) kraft_lut[i] = (uint8_t)fz_kraft3(i);
-    __syncthreads();
+    const FzInfTab<1> tab{tabs[warp], tabs[warp] + 288, tabs[warp] + 320};
+    const FzClLut<FZ_BP_FIND_THREADS> cl_lut{(uint8_t *)(cl_luts + threadIdx.x)};
     const uint32_t *alloc_end = (const uint32_t *)(((uintptr_t)container + container_size + 3u) & ~(uintptr_t)3u);
+    for (uint32_t i = threadIdx.x; i < 512; i += FZ_BP_FIND_THREADS) kraft_lut[i] = (uint8_t)fz_kraft3(i);
     if (lane == 0) qn[warp] = 0;
-    __syncwarp();
+    __syncthreads();
     for (uint32_t item = blockIdx.x; item < ngen * segs_per_stream; item += gridDim.x) {
         const uint32_t gi = item / segs_per_stream, seg = item - gi * segs_per_stream;
         const uint32_t s = bp.gen_list[gi];
@@ -1202,10 +1219,18 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
         const uint32_t nwords = (len + skew + 3) >> 2;
         if (seg * FZ_BP_SEG_WORDS >= nwords) continue;   // block-uniform
         const int64_t total_bits = (int64_t)len * 8;
-        auto validate = [&](uint32_t p) {
-            if (fz_block_candidate(in, (size_t)len, (uint64_t)p, tab)) {
-                const uint32_t idx = atomicAdd(&bp.cand_cnt[s], 1u);
-                if (idx < FZ_BP_CAP) bp.cand_pos[(size_t)s * FZ_BP_CAP + idx] = p;
+        // stages 2 and 3 for the position in `p` of the lanes with `have` (warp-wide call)
+        auto validate = [&](bool have, uint32_t p) {
+            const bool pre = have && fz_block_precheck(in, (size_t)len, (uint64_t)p, cl_lut);
+            uint32_t m = __ballot_sync(0xffffffffu, pre);
+            while (m) {
+                const int l = __ffs((int)m) - 1;
+                m &= m - 1;
+                if (lane == l && fz_block_candidate(in, (size_t)len, (uint64_t)p, tab)) {
+                    const uint32_t idx = atomicAdd(&bp.cand_cnt[s], 1u);
+                    if (idx < FZ_BP_CAP) bp.cand_pos[(size_t)s * FZ_BP_CAP + idx] = p;
+                }
+                __syncwarp();
             }
         };
         for (uint32_t it = 0; it < FZ_BP_SEG_WORDS / FZ_BP_FIND_THREADS; it++) {
@@ -1226,15 +1251,21 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
                     if (!fz_block_quick_test(lo, hi, kraft_lut)) continue;
                     const uint32_t slot = atomicAdd(&qn[warp], 1u);
                     if (slot < FZ_BP_QCAP) queue[warp][slot] = (uint32_t)p;
-                    else validate((uint32_t)p);   // queue full (pathological data): validate in place
                 }
             }
             __syncwarp();
-            uint32_t n = qn[warp];
+            const uint32_t n = qn[warp];
             const bool last_it = it + 1 == FZ_BP_SEG_WORDS / FZ_BP_FIND_THREADS;
-            if (n >= 32 || (last_it && n)) {   // warp-uniform: validate with all lanes busy
-                if (n > FZ_BP_QCAP) n = FZ_BP_QCAP;
-                for (uint32_t i = lane; i < n; i += 32) validate(queue[warp][i]);
+            if (n > FZ_BP_QCAP) {
+                // more survivors than the queue holds (pathological data): give the stream to the serial inflater
+                if (lane == 0) atomicAdd(&bp.cand_cnt[s], FZ_BP_CAP + 1u);
+            }
+            if (n >= 32 || (last_it && n)) {   // warp-uniform: the second stage runs with (almost) all lanes busy
+                const uint32_t nq = n < FZ_BP_QCAP ? n : FZ_BP_QCAP;
+                for (uint32_t i0 = 0; i0 < nq; i0 += 32) {
+                    const bool have = i0 + lane < nq;
+                    validate(have, have ? queue[warp][i0 + lane] : 0u);
+                }
                 __syncwarp();
                 if (lane == 0) qn[warp] = 0;
             }
@@ -1307,16 +1338,22 @@ fz_bp_sync_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const ui
         const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
         const uint8_t *in = container + stream_off[s];
         const uint32_t bit = bp.cand_pos[ci];
+        const FzTilePool pool{bp.tiles, bp.tiles_cap, &bp.ctl[FZ_BP_CTL_TILES]};
         if (WRITE) {
             const FzBlockInfo bi = bp.info[ci];
             uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + off;
+            const uint32_t rec = bp.first_rec[ci];
             bool ok = false;
-            fz_sy_block<true>(st, in, len, bit, out, bi.out_len, bp.blk_prev[ci], bi.end_bit, nullptr, &ok, lane);
+            if (rec != FZ_TILE_NONE)   // the measure pass kept the settled parse: decode every sub-range once
+                fz_sy_block_from_table(st, in, len, bit, out, bi.out_len, bp.blk_prev[ci], bi.end_bit, pool, rec, &ok, lane);
+            else
+                fz_sy_block<true>(st, in, len, bit, out, bi.out_len, bp.blk_prev[ci], bi.end_bit, nullptr, &ok, lane);
             if (!ok && lane == 0) atomicExch(&bp.par_ok[s], 0u);
         } else {
             FzBlockInfo bi;
-            fz_sy_block<false>(st, in, len, bit, nullptr, 0, -1, 0, &bi, nullptr, lane);
-            if (lane == 0) bp.info[ci] = bi;
+            uint32_t rec = FZ_TILE_NONE;
+            fz_sy_block<false>(st, in, len, bit, nullptr, 0, -1, 0, &bi, nullptr, lane, &pool, &rec);
+            if (lane == 0) { bp.info[ci] = bi; bp.first_rec[ci] = rec; }
         }
         __syncwarp();
     }
@@ -1354,6 +1391,7 @@ fz_bp_chain_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const u
             uint32_t *list = bp.items + (size_t)bp.nstreams * FZ_BP_CAP;
             for (uint32_t i = 0; i < nblocks; i++)
                 if (bp.blk_off[c0 + i] != 0xFFFFFFFFu) list[at++] = (uint32_t)(c0 + i);
+            for (uint32_t i = ncand; i < nblocks; i++) bp.first_rec[c0 + i] = FZ_TILE_NONE;   // fixed-Huffman blocks met on the way
         }
     }
 }
@@ -1378,14 +1416,23 @@ fz_bp_stored_kernel(const uint8_t *__restrict__ container, uint64_t container_si
     }
 }
 
-size_t fz_blockpar_bytes(uint32_t nstreams)
+// tile records: a stream of <= chk + 4 compressed bytes is (chk * 8) / (32 * FZ_BP_SUB_BITS) tiles plus one partial
+// tile per block; false candidates may burn a few more.  When the pool runs dry the write pass searches again.
+static uint32_t fz_bp_tiles_cap(uint32_t nstreams, uint32_t chk)
 {
-    const size_t per_stream = 4 /*gen_list*/ + 4 /*cand_cnt*/ + 4 /*nstored*/ + 4 /*par_ok*/ +
-                              (size_t)FZ_BP_CAP * (4 + sizeof(FzBlockInfo) + 4 + 4 + 8) + (size_t)FZ_BP_STORED_CAP * sizeof(FzStoredItem);
-    return 256 + per_stream * nstreams + 16 * 64;
+    const uint64_t per_stream = (uint64_t)chk * 8 / (32u * FZ_BP_SUB_BITS) + 64;
+    const uint64_t cap = per_stream * nstreams;
+    return (uint32_t)(cap < 0x7FFFFFFFu ? cap : 0x7FFFFFFFu);
 }
 
-FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams)
+size_t fz_blockpar_bytes(uint32_t nstreams, uint32_t chk)
+{
+    const size_t per_stream = 4 /*gen_list*/ + 4 /*cand_cnt*/ + 4 /*nstored*/ + 4 /*par_ok*/ +
+                              (size_t)FZ_BP_CAP * (4 + sizeof(FzBlockInfo) + 4 + 4 + 8 + 4) + (size_t)FZ_BP_STORED_CAP * sizeof(FzStoredItem);
+    return 256 + per_stream * nstreams + (size_t)fz_bp_tiles_cap(nstreams, chk) * sizeof(FzTileRec) + 16 * 64;
+}
+
+FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams, uint32_t chk)
 {
     FzBlockParBufs b;
     uint8_t *p = (uint8_t *)blob;
@@ -1401,6 +1448,9 @@ FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams)
     b.blk_prev = (int *)take((size_t)nstreams * FZ_BP_CAP * 4);
     b.stored = (FzStoredItem *)take((size_t)nstreams * FZ_BP_STORED_CAP * sizeof(FzStoredItem));
     b.items = (uint32_t *)take((size_t)nstreams * FZ_BP_CAP * 4 * 2);
+    b.first_rec = (uint32_t *)take((size_t)nstreams * FZ_BP_CAP * 4);
+    b.tiles_cap = fz_bp_tiles_cap(nstreams, chk);
+    b.tiles = (FzTileRec *)take((size_t)b.tiles_cap * sizeof(FzTileRec));
     b.nstreams = nstreams;
     return b;
 }
@@ -1444,7 +1494,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
     const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;
-    fz_bp_find_kernel<<<FZ_SM_COUNT * 4, FZ_BP_FIND_THREADS, 0, st>>>(container, container_size, stream_hdr, stream_off, b.bp, segs, status);
+    fz_bp_find_kernel<<<FZ_SM_COUNT * 12, FZ_BP_FIND_THREADS, 0, st>>>(container, container_size, stream_hdr, stream_off, b.bp, segs, status);
     fz_bp_sort_kernel<<<FZ_SM_COUNT, FZ_BP_CAP / 2, 0, st>>>(b.bp, status);
     fz_bp_sync_kernel<false><<<FZ_SM_COUNT * 4, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
     fz_bp_chain_kernel<<<FZ_SM_COUNT, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, status);

@@ -79,11 +79,14 @@ struct FzBlockParBufs {
     int *blk_prev;         // [nstreams * FZ_BP_CAP] byte before the block, -1 = none
     FzStoredItem *stored;  // [nstreams * FZ_BP_STORED_CAP]
     uint32_t *items;       // [2][nstreams * FZ_BP_CAP] work lists (block slot indices) of the measure / write pass
+    uint32_t *first_rec;   // [nstreams * FZ_BP_CAP] first tile record of the block, FZ_TILE_NONE = none kept
+    FzTileRec *tiles;      // [tiles_cap] tile records of the measure pass (bump allocated through ctl[FZ_BP_CTL_TILES])
+    uint32_t tiles_cap;
     uint32_t nstreams;
 };
-enum { FZ_BP_CTL_NGEN = 0, FZ_BP_CTL_NMEASURE, FZ_BP_CTL_CUR_MEASURE, FZ_BP_CTL_NWRITE, FZ_BP_CTL_CUR_WRITE };
-size_t fz_blockpar_bytes(uint32_t nstreams);
-FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams);
+enum { FZ_BP_CTL_NGEN = 0, FZ_BP_CTL_NMEASURE, FZ_BP_CTL_CUR_MEASURE, FZ_BP_CTL_NWRITE, FZ_BP_CTL_CUR_WRITE, FZ_BP_CTL_TILES };
+size_t fz_blockpar_bytes(uint32_t nstreams, uint32_t chk);
+FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams, uint32_t chk);
 
 struct FzInflateBufs {
     uint32_t *tile_cnt;      // [nstreams * tiles_per_stream + 1] counts -> exclusive offsets

@@ -146,8 +146,13 @@ uint32_t hm_put_stored(const uint8_t *in, uint32_t n, uint8_t *out) { return (ui
 // chain, write); returns 0, a negative chain code (the GPU would take the serial path), or 100+ on a write error
 void hm_sy_stats(uint64_t *o) { o[0] = fz_sy_stat_tiles; o[1] = fz_sy_stat_rounds; o[2] = fz_sy_stat_redos; o[3] = fz_sy_stat_redo_lanes; }
 void hm_sy_stats_reset(void) { fz_sy_stat_tiles = fz_sy_stat_rounds = fz_sy_stat_redos = fz_sy_stat_redo_lanes = 0; }
+uint32_t hm_tile_pool_cap = 4096, hm_table_blocks = 0;
+void hm_set_tile_pool_cap(uint32_t n) { hm_tile_pool_cap = n; }
+uint32_t hm_get_table_blocks(void) { return hm_table_blocks; }
 int hm_blockpar_sync = 1;      // 1: warp-synchronising block decoder (what the GPU runs), 0: serial per-block functions
 void hm_set_blockpar_sync(int on) { hm_blockpar_sync = on; }
+uint64_t hm_precheck_passes = 0;
+uint64_t hm_last_precheck_passes(void) { return hm_precheck_passes; }
 uint64_t hm_quick_passes = 0;  // positions that passed fz_block_quick_test in the last hm_inflate_blockpar call
 uint64_t hm_last_quick_passes(void) { return hm_quick_passes; }
 
@@ -171,10 +176,21 @@ int hm_inflate_blockpar(const uint8_t *in_, uint32_t in_len, uint8_t *out_, uint
     };
     std::vector<uint32_t> cand;
     hm_quick_passes = 0;
+    hm_precheck_passes = 0;
+    hm_table_blocks = 0;
     const uint64_t total_bits = (uint64_t)in_len * 8;
     for (uint64_t bit = 0; bit + 17 <= total_bits; bit++) {
         if (!fz_block_quick_test(bits64(bit), bits64(bit + 64))) continue;
         hm_quick_passes++;
+        {   // the cheap second stage must never reject what the full parse accepts (and is run first on the GPU)
+            uint8_t cl[128 + 8];
+            const FzClLut<1> cl_lut{cl};
+            const bool pre = fz_block_precheck(in, in_len, bit, cl_lut);
+            const bool full = fz_block_candidate(in, in_len, bit, tab);
+            if (pre) hm_precheck_passes++;
+            if (full && !pre) return -1000;
+            if (!pre) continue;
+        }
         if (fz_block_candidate(in, in_len, bit, tab)) cand.push_back((uint32_t)bit);
     }
     const uint32_t ncand = (uint32_t)cand.size();
@@ -182,9 +198,14 @@ int hm_inflate_blockpar(const uint8_t *in_, uint32_t in_len, uint8_t *out_, uint
     cand.resize(cap);
     std::vector<FzBlockInfo> info(cap);
     std::vector<FzSyncState> sy(1);
+    // tile records of the measure pass; hm_tile_pool_cap = 0 exercises the "pool exhausted" path (write pass searches again)
+    std::vector<FzTileRec> recs(hm_tile_pool_cap ? hm_tile_pool_cap : 1);
+    uint32_t pool_cursor = 0;
+    FzTilePool pool{recs.data(), hm_tile_pool_cap, &pool_cursor};
+    std::vector<uint32_t> first_rec(cap, FZ_TILE_NONE);
     for (uint32_t i = 0; i < ncand; i++) {
         if (hm_blockpar_sync) {
-            fz_sy_block<false>(sy.data(), in, in_len, cand[i], nullptr, 0, -1, 0, &info[i], nullptr, 0);
+            fz_sy_block<false>(sy.data(), in, in_len, cand[i], nullptr, 0, -1, 0, &info[i], nullptr, 0, &pool, &first_rec[i]);
             FzBlockInfo ref;   // the serial measure must agree exactly
             fz_block_measure(in, in_len, cand[i], tab, lut.data(), &ref);
             const bool ref_usable = (ref.flags & FZ_BLK_OK) && !(ref.flags & FZ_BLK_NON_RLE);
@@ -210,7 +231,12 @@ int hm_inflate_blockpar(const uint8_t *in_, uint32_t in_len, uint8_t *out_, uint
         if (off[i] == 0xFFFFFFFFu) continue;
         if (hm_blockpar_sync) {
             bool ok = false;
-            fz_sy_block<true>(sy.data(), in, in_len, cand[i], out + off[i], info[i].out_len, prev[i], info[i].end_bit, nullptr, &ok, 0);
+            if (first_rec[i] != FZ_TILE_NONE) {
+                fz_sy_block_from_table(sy.data(), in, in_len, cand[i], out + off[i], info[i].out_len, prev[i], info[i].end_bit, pool,
+                                       first_rec[i], &ok, 0);
+                hm_table_blocks++;
+            } else
+                fz_sy_block<true>(sy.data(), in, in_len, cand[i], out + off[i], info[i].out_len, prev[i], info[i].end_bit, nullptr, &ok, 0);
             if (!ok) return 100 + (int)i;
         } else if (!fz_block_write(in, in_len, cand[i], tab, lut.data(), out + off[i], info[i].out_len, prev[i], info[i].end_bit)) return 100 + (int)i;
     }

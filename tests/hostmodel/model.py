@@ -60,3 +60,14 @@ def inflate_blockpar(b: np.ndarray, n_out: int):
     nc, nf = C.c_uint32(), C.c_uint32()
     rc = _L.hm_inflate_blockpar(b.ctypes.data, b.size, out.ctypes.data, n_out, C.byref(nc), C.byref(nf))
     return rc, out[:n_out].copy(), int(nc.value), int(nf.value)
+
+
+def set_tile_pool_cap(n: int):
+    """Capacity of the tile-record pool the measure pass fills for the write pass (0: the write pass searches again)."""
+    _L.hm_set_tile_pool_cap(C.c_uint32(n))
+
+
+def table_blocks() -> int:
+    """Blocks the last inflate_blockpar call wrote from tile records."""
+    _L.hm_get_table_blocks.restype = C.c_uint32
+    return int(_L.hm_get_table_blocks())

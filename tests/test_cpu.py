@@ -329,3 +329,19 @@ def test_model_blockpar_inflate_of_reference_streams(hostmodel):
     c = z(cases["exp"], zlib.Z_RLE)
     rc, _, _, _ = hostmodel.inflate_blockpar(c[: c.size // 2], cases["exp"].size)
     assert rc != 0
+
+
+def test_model_blockpar_tile_records_and_pool_exhaustion(hostmodel):
+    """The measure pass leaves tile records so that the write pass decodes every sub-range once; when the pool is
+    too small the write pass searches again -- same bytes either way."""
+    a = synth_words("G", 400000).view(np.uint8).reshape(-1, 4)[:, 3].copy()
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+    c = np.frombuffer(co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH), np.uint8)
+    try:
+        for cap, expect_all in [(4096, True), (0, False), (5, False)]:
+            hostmodel.set_tile_pool_cap(cap)
+            rc, o, ncand, _ = hostmodel.inflate_blockpar(c, a.size)
+            assert rc == 0 and np.array_equal(o, a), cap
+            assert (hostmodel.table_blocks() == ncand) == expect_all, (cap, hostmodel.table_blocks(), ncand)
+    finally:
+        hostmodel.set_tile_pool_cap(4096)
