@@ -49,7 +49,7 @@ FZ_HD uint32_t fz_kraft3(uint32_t three)
 // kraft_lut: 512 bytes, kraft_lut[x] = fz_kraft3(x) (shared memory on the GPU), or nullptr
 FZ_HD bool fz_block_quick_test(uint64_t lo, uint64_t hi, const uint8_t *kraft_lut = nullptr)
 {
-    if (((lo >> 1) & 3u) != 2u) return false;                 // BTYPE = 10
+    if ((lo & 7u) != 4u) return false;                        // BFINAL = 0, BTYPE = 10 (a final block: see fz_chain_resolve)
     if (((lo >> 3) & 31u) > 29u) return false;                // HLIT  <= 29 (286 codes)
     if (((lo >> 8) & 31u) > 29u) return false;                // HDIST <= 29
     const uint32_t ncl = (uint32_t)((lo >> 13) & 15u) + 4u;
@@ -208,8 +208,9 @@ FZ_HD uint32_t fz_stream_bits(const uint8_t *in, uint64_t bit, uint32_t n)  // n
 // Serial walk over one stream.  cand_pos[0, ncand) ascending.  On success blk_off[i] = output offset of block i if
 // it lies on the chain (else 0xFFFFFFFF), blk_prev[i] = the byte before it (-1 at the stream start), and the
 // stored blocks met on the way are listed.  A fixed-Huffman block (zlib picks one now and then for a short or
-// nearly incompressible stretch) has no header to search for: the walk measures it on the spot and appends it
-// to the block list (slots [ncand, *nblocks)).  Returns 0, or < 0 when the stream must take the serial path.
+// nearly incompressible stretch) has no header to search for, and a dynamic block with BFINAL = 1 (at most the
+// last one of a stream; the reference never finishes its streams) is not searched for: the walk measures those on
+// the spot and appends them to the block list (slots [ncand, *nblocks)).  Returns 0, or < 0 when the stream must take the serial path.
 // Reads up to 3 bytes past `in + in_len` (callers provide that slack, as everywhere in this library).
 template <class Tab>
 FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, uint32_t *cand_pos, FzBlockInfo *info,
@@ -246,12 +247,12 @@ FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, u
             pos = (by + 4 + len) * 8;
         } else if (type == 1 || type == 2) {
             uint32_t k;
-            if (type == 2) {  // the candidate starting exactly here
-                uint32_t lo = 0, hi = ncand;
+            uint32_t lo = 0, hi = ncand;
+            if (type == 2 && !(h & 1u)) {  // the candidate starting exactly here
                 while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cand_pos[mid] < pos) lo = mid + 1; else hi = mid; }
                 if (lo >= ncand || cand_pos[lo] != pos) return -4;
                 k = lo;
-            } else {
+            } else {   // fixed code, or a final dynamic block (the search only looks for BFINAL = 0): measured here
                 if (*nblocks >= cap) return -8;
                 k = (*nblocks)++;
                 cand_pos[k] = (uint32_t)pos;
@@ -300,7 +301,8 @@ FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, u
 #endif
 
 #define FZ_BP_SUB_BITS 2048u
-#define FZ_BP_PROBE_BITS 320u
+#define FZ_BP_PROBE_BITS 320u       // first probe length of a block ...
+#define FZ_BP_PROBE_MAX 1280u       // ... doubled after every tile that needed a redo round, up to this
 #define FZ_SY_EOB 1u        // the sub-range ended with the end-of-block symbol
 #define FZ_SY_ERR 2u        // decode error (normal for a speculative start; fatal once the parse is settled)
 #define FZ_SY_NONRLE 8u
@@ -346,6 +348,7 @@ struct FzSyncState {
     uint32_t tile_total, tile_eob_lane, tile_err, tile_nonrle, tile_werr;
     int tile_carry;
     uint32_t rec_idx, rec_prev;   // tile record being written / the one before it
+    uint32_t probe_bits;          // length of the probe decode; grows when a block's code is slow to fall into step
 };
 
 FZ_HD uint32_t fz_tile_alloc(const FzTilePool &pool)
@@ -393,7 +396,7 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
     const Tab tab{st->tab, st->tab + 288, st->tab + 320};
     const uint32_t grid = tile_pos + (uint32_t)lane * FZ_BP_SUB_BITS;
     const uint32_t start = probe ? grid : st->start[lane];
-    const uint64_t range_end = probe ? (uint64_t)grid + FZ_BP_PROBE_BITS : (uint64_t)st->rend[lane];
+    const uint64_t range_end = probe ? (uint64_t)grid + st->probe_bits : (uint64_t)st->rend[lane];
     const bool write = out != nullptr;
     FzInflater<Tab> inf;
     // counting: the sub-range is [start, first symbol boundary >= range_end); writing: the bytes (and the
@@ -483,6 +486,9 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
                 }
                 const bool near_end = inf.br.bits_left() <= near_left;
                 live = inf.step_lut(near_end ? nullptr : lut);
+                // a probe only looks for the true parse: an end-of-block symbol met on the way is (almost surely) part
+                // of the not-yet-synchronised garbage -- keep going
+                if (probe && !live && inf.saw_eob && inf.rc == FZ_INF_OK) { inf.saw_eob = false; inf.in_body = true; live = true; }
                 if (live && inf.br.bits_left() <= stop_left) live = false;
             }
         }
@@ -527,6 +533,10 @@ FZ_HD void fz_sy_ph_probe(FzSyncState *st, const uint8_t *in, uint32_t in_len, u
     st->flags[lane] = 0;
     if (lane == 0) st->start[0] = tile_pos;   // the one position known to be a symbol boundary
     fz_sy_decode(st, in, in_len, tile_pos, lane != 0, nullptr, lane, true);
+}
+FZ_HD void fz_sy_ph_longer_probe(FzSyncState *st, int lane)
+{
+    if (lane == 0 && st->probe_bits < FZ_BP_PROBE_MAX) st->probe_bits *= 2;
 }
 FZ_HD void fz_sy_ph_ranges(FzSyncState *st, uint32_t tile_pos, int lane)
 {
@@ -698,10 +708,11 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
     uint32_t rec0 = FZ_TILE_NONE;
     bool table_ok = !WRITE && pool != nullptr;
 #if defined(__CUDA_ARCH__)
-    if (lane == 0) st->rec_idx = FZ_TILE_NONE;
+    if (lane == 0) { st->rec_idx = FZ_TILE_NONE; st->probe_bits = FZ_BP_PROBE_BITS; }
     __syncwarp();
 #else
     st->rec_idx = FZ_TILE_NONE;
+    st->probe_bits = FZ_BP_PROBE_BITS;
 #endif
     int carry = WRITE ? prev_byte : -1;
     bool good = st->hdr_ok != 0, done = false;
@@ -716,7 +727,7 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
 #if !defined(__CUDA_ARCH__) && defined(FZ_SY_STATS)
             fz_sy_stat_tiles++;
 #endif
-            bool settled = false;
+            bool settled = false, redone = false;
             for (int round = 0; round < 34 && !settled; round++) {
                 FZ_PHASE(fz_sy_ph_look(st, tile_pos, lane));
                 FZ_PHASE(fz_sy_ph_summary(st, lane));
@@ -726,9 +737,11 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
                 if (st->any_redo) {
                     FZ_PHASE(fz_sy_ph_apply(st, lane));
                     FZ_PHASE(fz_sy_ph_redo(st, in, in_len, tile_pos, lane));
+                    redone = true;
                 } else settled = true;
             }
             if (!settled) { good = false; break; }
+            if (redone) FZ_PHASE(fz_sy_ph_longer_probe(st, lane));
             FZ_PHASE(fz_sy_ph_scan(st, carry, lane));
             const uint32_t total = st->tile_total;
             if (st->tile_err) { good = false; break; }

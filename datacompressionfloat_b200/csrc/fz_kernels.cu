@@ -1197,7 +1197,8 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
 {
     __shared__ uint16_t tabs[FZ_BP_FIND_THREADS / 32][FZ_INF_TAB_U16];   // one full-parse table per warp
     __shared__ uint32_t cl_luts[32 * FZ_BP_FIND_THREADS];                 // 128 bytes per thread, word-interleaved
-    __shared__ uint32_t queue[FZ_BP_FIND_THREADS / 32][FZ_BP_QCAP];
+    __shared__ uint32_t queue_p[FZ_BP_FIND_THREADS / 32][FZ_BP_QCAP];     // survivors of stage 1: bit position ...
+    __shared__ uint32_t queue_s[FZ_BP_FIND_THREADS / 32][FZ_BP_QCAP];     // ... and stream (the queue outlives a segment)
     __shared__ uint32_t qn[FZ_BP_FIND_THREADS / 32];
     __shared__ uint8_t kraft_lut[512];
     const uint32_t ngen = bp.ctl[0];
@@ -1209,6 +1210,43 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
     for (uint32_t i = threadIdx.x; i < 512; i += FZ_BP_FIND_THREADS) kraft_lut[i] = (uint8_t)fz_kraft3(i);
     if (lane == 0) qn[warp] = 0;
     __syncthreads();
+    // stages 2 and 3 for queue entries [i0, i0 + 32) of this warp (warp-wide call)
+    auto validate = [&](uint32_t i0, uint32_t nq) {
+        const bool have = i0 + lane < nq;
+        const uint32_t p = have ? queue_p[warp][i0 + lane] : 0u;
+        const uint32_t s = have ? queue_s[warp][i0 + lane] : 0u;
+        const uint8_t *in = container + stream_off[s];
+        const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
+        const bool pre = have && fz_block_precheck(in, (size_t)len, (uint64_t)p, cl_lut);
+        uint32_t m = __ballot_sync(0xffffffffu, pre);
+        while (m) {
+            const int l = __ffs((int)m) - 1;
+            m &= m - 1;
+            if (lane == l && fz_block_candidate(in, (size_t)len, (uint64_t)p, tab)) {
+                const uint32_t idx = atomicAdd(&bp.cand_cnt[s], 1u);
+                if (idx < FZ_BP_CAP) bp.cand_pos[(size_t)s * FZ_BP_CAP + idx] = p;
+            }
+            __syncwarp();
+        }
+    };
+    // drain the queue in batches of 32 (all of it when `all`), keep the remainder for later
+    auto drain = [&](bool all) {
+        __syncwarp();
+        uint32_t n = qn[warp];
+        if (n > FZ_BP_QCAP) n = FZ_BP_QCAP;
+        uint32_t done = 0;
+        while (done + 32 <= n || (all && done < n)) { validate(done, n); done += 32; }
+        if (done) {
+            __syncwarp();
+            const uint32_t rest = done < n ? n - done : 0u;   // < 32 entries: move them to the front
+            uint32_t mp = 0, ms = 0;
+            if ((uint32_t)lane < rest) { mp = queue_p[warp][done + lane]; ms = queue_s[warp][done + lane]; }
+            __syncwarp();
+            if ((uint32_t)lane < rest) { queue_p[warp][lane] = mp; queue_s[warp][lane] = ms; }
+            if (lane == 0) qn[warp] = rest;
+        }
+        __syncwarp();
+    };
     for (uint32_t item = blockIdx.x; item < ngen * segs_per_stream; item += gridDim.x) {
         const uint32_t gi = item / segs_per_stream, seg = item - gi * segs_per_stream;
         const uint32_t s = bp.gen_list[gi];
@@ -1219,20 +1257,6 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
         const uint32_t nwords = (len + skew + 3) >> 2;
         if (seg * FZ_BP_SEG_WORDS >= nwords) continue;   // block-uniform
         const int64_t total_bits = (int64_t)len * 8;
-        // stages 2 and 3 for the position in `p` of the lanes with `have` (warp-wide call)
-        auto validate = [&](bool have, uint32_t p) {
-            const bool pre = have && fz_block_precheck(in, (size_t)len, (uint64_t)p, cl_lut);
-            uint32_t m = __ballot_sync(0xffffffffu, pre);
-            while (m) {
-                const int l = __ffs((int)m) - 1;
-                m &= m - 1;
-                if (lane == l && fz_block_candidate(in, (size_t)len, (uint64_t)p, tab)) {
-                    const uint32_t idx = atomicAdd(&bp.cand_cnt[s], 1u);
-                    if (idx < FZ_BP_CAP) bp.cand_pos[(size_t)s * FZ_BP_CAP + idx] = p;
-                }
-                __syncwarp();
-            }
-        };
         for (uint32_t it = 0; it < FZ_BP_SEG_WORDS / FZ_BP_FIND_THREADS; it++) {
             const uint32_t wi = seg * FZ_BP_SEG_WORDS + it * FZ_BP_FIND_THREADS + threadIdx.x;
             if (wi < nwords) {
@@ -1240,7 +1264,7 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
 #pragma unroll
                 for (int k = 0; k < 5; k++) x[k] = (abase + wi + k < alloc_end) ? __ldg(abase + wi + k) : 0u;
                 const uint64_t v = (uint64_t)x[0] | ((uint64_t)x[1] << 32);
-                uint32_t m = (uint32_t)(~(v >> 1) & (v >> 2));   // BTYPE == 10 at positions j = 0..31 of this word
+                uint32_t m = (uint32_t)(~v & ~(v >> 1) & (v >> 2));   // BFINAL = 0, BTYPE = 10 at positions j = 0..31 of this word
                 while (m) {
                     const int j = __ffs((int)m) - 1;
                     m &= m - 1;
@@ -1250,28 +1274,15 @@ fz_bp_find_kernel(const uint8_t *__restrict__ container, uint64_t container_size
                     const uint64_t hi = (uint64_t)__funnelshift_r(x[2], x[3], j) | ((uint64_t)__funnelshift_r(x[3], x[4], j) << 32);
                     if (!fz_block_quick_test(lo, hi, kraft_lut)) continue;
                     const uint32_t slot = atomicAdd(&qn[warp], 1u);
-                    if (slot < FZ_BP_QCAP) queue[warp][slot] = (uint32_t)p;
+                    if (slot < FZ_BP_QCAP) { queue_p[warp][slot] = (uint32_t)p; queue_s[warp][slot] = s; }
+                    // more survivors than the queue holds (pathological data): give the stream to the serial inflater
+                    else atomicAdd(&bp.cand_cnt[s], FZ_BP_CAP + 1u);
                 }
             }
-            __syncwarp();
-            const uint32_t n = qn[warp];
-            const bool last_it = it + 1 == FZ_BP_SEG_WORDS / FZ_BP_FIND_THREADS;
-            if (n > FZ_BP_QCAP) {
-                // more survivors than the queue holds (pathological data): give the stream to the serial inflater
-                if (lane == 0) atomicAdd(&bp.cand_cnt[s], FZ_BP_CAP + 1u);
-            }
-            if (n >= 32 || (last_it && n)) {   // warp-uniform: the second stage runs with (almost) all lanes busy
-                const uint32_t nq = n < FZ_BP_QCAP ? n : FZ_BP_QCAP;
-                for (uint32_t i0 = 0; i0 < nq; i0 += 32) {
-                    const bool have = i0 + lane < nq;
-                    validate(have, have ? queue[warp][i0 + lane] : 0u);
-                }
-                __syncwarp();
-                if (lane == 0) qn[warp] = 0;
-            }
-            __syncwarp();
+            drain(false);
         }
     }
+    drain(true);
 }
 
 // ascending candidate positions per stream (bitonic sort of FZ_BP_CAP slots, unused ones padded with ~0)
@@ -1494,7 +1505,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
     const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;
-    fz_bp_find_kernel<<<FZ_SM_COUNT * 12, FZ_BP_FIND_THREADS, 0, st>>>(container, container_size, stream_hdr, stream_off, b.bp, segs, status);
+    fz_bp_find_kernel<<<FZ_SM_COUNT * 16, FZ_BP_FIND_THREADS, 0, st>>>(container, container_size, stream_hdr, stream_off, b.bp, segs, status);
     fz_bp_sort_kernel<<<FZ_SM_COUNT, FZ_BP_CAP / 2, 0, st>>>(b.bp, status);
     fz_bp_sync_kernel<false><<<FZ_SM_COUNT * 4, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
     fz_bp_chain_kernel<<<FZ_SM_COUNT, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, status);

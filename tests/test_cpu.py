@@ -321,6 +321,12 @@ def test_model_blockpar_inflate_of_reference_streams(hostmodel):
     tiny = np.array([5, 5, 5, 5, 5, 9], np.uint8)
     rc, o, ncand, _ = hostmodel.inflate_blockpar(z(tiny, zlib.Z_RLE), tiny.size)
     assert rc == 0 and ncand == 0 and np.array_equal(o, tiny)
+    # a finished stream (Z_FINISH): its last block has BFINAL = 1, which the header search skips -- the chain walk
+    # measures that block itself
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+    c = np.frombuffer(co.compress(cases["exp"].tobytes()) + co.flush(zlib.Z_FINISH), np.uint8)
+    rc, o, _, _ = hostmodel.inflate_blockpar(c, cases["exp"].size)
+    assert rc == 0 and np.array_equal(o, cases["exp"])
     # default strategy = long distances: refused, never wrong
     a = np.tile(np.arange(200, dtype=np.uint8), 600)
     rc, _, _, _ = hostmodel.inflate_blockpar(z(a, zlib.Z_DEFAULT_STRATEGY), a.size)
