@@ -245,6 +245,28 @@ def workload_config(a, nwords_per_gpu):
             "l2_policy": "inputs (>= 1 GiB per launch) exceed the 126 MB L2; no flush needed", "parallelism": f"chunk-range x{a.gpus}"}
 
 
+def bind_near_gpu(local_rank):
+    """Multi-rank runs: keep this process (and the pinned host buffers it is about to allocate) on the NUMA node
+    of its GPU, so that eight ranks do not pull 100+ GB per step across the socket interconnect."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # no sysfs / unknown properties: run unbound
+        return {"numa_node": None, "note": type(e).__name__}
+
+
 # ----------------------------------------------------------------------------- the B200 arm
 def run_b200(a):
     import torch
@@ -258,6 +280,7 @@ def run_b200(a):
         print(f"warning: WORLD_SIZE {world} != --gpus {a.gpus}", file=sys.stderr)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
+    affinity = bind_near_gpu(local) if world > 1 else {"numa_node": None}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -442,6 +465,7 @@ def run_b200(a):
         "bit_exact_roundtrip": ok, "roofline": roofline, "roofline_kernels": kernels, "pipeline_roofline": pipeline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
         "decode_stats": {k: state["ds"][k] for k in ("general_streams", "fast_failed")},
+        "host_affinity": affinity,
         "encode_stats": {k: state["cs"][k] for k in ("raw_streams", "stored_subblocks", "streams")},
         "stage_ms": {k: round(v, 4) for k, v in stages.items() if v > 0},
     }

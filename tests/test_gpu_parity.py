@@ -182,6 +182,76 @@ def test_reference_streams_inflate_block_parallel(codec, oracle, kind, bits):
     assert st["blockpar_streams"] == ncomp, st              # incl. streams with fixed-Huffman blocks (S plane 2)
 
 
+def _container_from_payloads(words, chk, make_payload):
+    """Reference layout (common.c:137-149, zip.c:186-196) around payloads made by `make_payload(plane_bytes, chunk, plane)`."""
+    import struct
+    out = [struct.pack("<QIB4B", words.size * 4, chk, 0, 0, 0, 0, 0)]
+    for ci, c0 in enumerate(range(0, words.size, chk)):
+        planes = words[c0:c0 + chk].view(np.uint8).reshape(-1, 4)
+        hdr, payloads = [], []
+        for j in range(4):
+            p = planes[:, j].tobytes()
+            z = make_payload(p, ci, j)
+            if len(p) > len(z) + 4:
+                hdr.append(len(z)); payloads.append(z)
+            else:
+                hdr.append(len(p) | 0x80000000); payloads.append(p)
+        out.append(struct.pack("<4I", *hdr) + b"".join(payloads))
+    return np.frombuffer(b"".join(out), np.uint8)
+
+
+def test_block_parallel_edge_streams(codec, oracle):
+    """Streams the block-parallel path must either decode or hand to the serial inflater, never get wrong:
+    finished streams (BFINAL = 1 last block), streams cut into many small blocks by frequent flushes, streams that
+    are mostly stored blocks, and a container mixing our own sub-block streams with zlib-made ones."""
+    import zlib
+    w = synth_words("P", 2 * 262144 + 1000 - 256)
+    masked = oracle.erasebytes(w.view(np.uint8), 0).view(np.uint32)
+    rng = np.random.default_rng(5)
+
+    def finished(p, ci, j):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+        return co.compress(p) + co.flush(zlib.Z_FINISH)
+
+    def many_blocks(p, ci, j):   # a full flush every 3000 bytes: ~90 short blocks + empty stored blocks in between
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+        out = b""
+        for k in range(0, len(p), 3000):
+            out += co.compress(p[k:k + 3000]) + co.flush(zlib.Z_FULL_FLUSH)
+        return out
+
+    def level0(p, ci, j):        # stored blocks only
+        co = zlib.compressobj(0, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+        return co.compress(p) + co.flush(zlib.Z_FULL_FLUSH)
+
+    for make, all_par in [(finished, True), (many_blocks, True), (level0, True)]:
+        cont = _container_from_payloads(masked, 262144, make)
+        back = codec.decompress(torch.from_numpy(cont.copy()).cuda())
+        assert np.array_equal(host_u32(back), masked), make.__name__
+        st = codec.stats()
+        assert st["general_streams"] > 0 or make is level0
+        # (tiny zlib payloads that happen to look like one of our sub-blocks -- one marker, at the end -- but hold a
+        # fixed-Huffman block fail the sub-block path's validation and are redone serially: "fast_failed")
+        if all_par:
+            assert st["blockpar_streams"] == st["general_streams"] - st["fast_failed"], (make.__name__, st)
+
+    # mixed: chunk 0 in our framing (cut out of a container we made), the rest zlib-made
+    ours = codec.compress(torch.from_numpy(masked.view(np.int32)).cuda(), 0, chk=262144).cpu().numpy()
+    _, _, streams = oracle.parse_container(ours)
+
+    def mixed(p, ci, j):
+        if ci == 0:
+            s = streams[j]
+            return ours[s["offset"]: s["offset"] + s["len"]].tobytes() if not s["raw"] else p + b"x" * 8   # forces RAW
+        return many_blocks(p, ci, j)
+
+    cont = _container_from_payloads(masked, 262144, mixed)
+    back = codec.decompress(torch.from_numpy(cont.copy()).cuda())
+    assert np.array_equal(host_u32(back), masked)
+    st = codec.stats()
+    assert 0 < st["general_streams"] < st["streams"]
+
+
 def test_default_strategy_streams_take_the_serial_inflater(codec, oracle):
     """Streams with long-distance matches (not what the reference writes, but legal deflate) are refused by the
     block-parallel path and decoded by the serial inflater: same bytes."""
@@ -189,13 +259,13 @@ def test_default_strategy_streams_take_the_serial_inflater(codec, oracle):
     w = np.tile(synth_words("P", 4096), 100)[: 300000]
     masked = oracle.erasebytes(w.view(np.uint8), 0).view(np.uint32)
     cont = _zlib_container(masked, 131072, zlib.Z_DEFAULT_STRATEGY)
-    back = codec.decompress(torch.from_numpy(cont).cuda())
+    back = codec.decompress(torch.from_numpy(cont.copy()).cuda())
     assert np.array_equal(host_u32(back), masked)
     st = codec.stats()
     assert st["general_streams"] > 0 and st["blockpar_streams"] < st["general_streams"]
     # the same data with Z_RLE payloads goes block-parallel
     cont = _zlib_container(masked, 131072, zlib.Z_RLE)
-    back = codec.decompress(torch.from_numpy(cont).cuda())
+    back = codec.decompress(torch.from_numpy(cont.copy()).cuda())
     assert np.array_equal(host_u32(back), masked)
     st = codec.stats()
     assert st["blockpar_streams"] > 0
@@ -230,7 +300,7 @@ def test_foreign_deflate_streams_decode_on_gpu(codec, oracle):
             parts.append(np.array(hdr, np.uint32).view(np.uint8))
             parts.extend(pay)
         cont = np.concatenate(parts)
-        back = codec.decompress(torch.from_numpy(cont).cuda())
+        back = codec.decompress(torch.from_numpy(cont.copy()).cuda())
         assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(w.view(np.uint8), 10)), (strat, lvl)
 
 
