@@ -152,7 +152,9 @@ template <class Tab>
 FZ_HD bool fz_block_candidate(const uint8_t *in, size_t in_len, uint64_t bit, const Tab &tab)
 {
     FzInflater<Tab> inf;
+    FzCode ll, dd;
     inf.start_at_bit(in, in_len, bit, nullptr, 0, tab);
+    inf.bind_codes(&ll, &dd);
     inf.bw.dry = true;
     if (!inf.block_header() || !inf.in_body) return false;
     // zlib always emits a complete literal/length code with an end-of-block symbol; distances: complete, or the
@@ -164,7 +166,9 @@ template <class Tab>
 FZ_HD void fz_block_measure(const uint8_t *in, size_t in_len, uint64_t bit, const Tab &tab, uint32_t *lut, FzBlockInfo *bi)
 {
     FzInflater<Tab> inf;
+    FzCode ll, dd;
     inf.start_at_bit(in, in_len, bit, nullptr, 0xFFFFFFF0u, tab);
+    inf.bind_codes(&ll, &dd);
     inf.bw.dry = true;
     inf.bw.prev_byte = 0;       // a distance-1 run may continue from the previous block; its value is resolved later
     inf.own_lut = lut;
@@ -188,7 +192,9 @@ FZ_HD bool fz_block_write(const uint8_t *in, size_t in_len, uint64_t bit, const 
                           uint32_t out_len, int prev_byte, uint32_t expect_end_bit)
 {
     FzInflater<Tab> inf;
+    FzCode ll, dd;
     inf.start_at_bit(in, in_len, bit, out, out_len, tab);
+    inf.bind_codes(&ll, &dd);
     inf.bw.prev_byte = prev_byte;
     inf.own_lut = lut;
     inf.one_block = true;
@@ -368,21 +374,19 @@ FZ_HD_NOINLINE void fz_sy_ph_header(FzSyncState *st, const uint8_t *in, uint32_t
     const Tab tab{st->tab, st->tab + 288, st->tab + 320};
     FzInflater<Tab> inf;
     inf.start_at_bit(in, (size_t)in_len, (uint64_t)bit, nullptr, 0xFFFFFFF0u, tab);
+    inf.bind_codes(&st->LL, &st->DD);   // the header parse leaves the codes where every lane reads them
     inf.bw.dry = true;
     const bool ok = inf.block_header() && inf.in_body && inf.rc == FZ_INF_OK;
     st->hdr_ok = ok ? 1u : 0u;
     st->hdr_end = (uint32_t)(((uint64_t)bit & ~7ull) + inf.consumed_bits());
     st->is_last = inf.last ? 1u : 0u;
-    st->LL = inf.LL;
-    st->DD = inf.DD;
     st->dd1 = inf.dd1;
 }
 
 FZ_HD void fz_sy_ph_lut(FzSyncState *st, int lane)
 {
     const FzInfTab<1> tab{st->tab, st->tab + 288, st->tab + 320};
-    const FzCode LL = st->LL;
-    for (uint32_t e = (uint32_t)lane; e < FZ_LUT_SIZE; e += 32) st->lut[e] = fz_lut_entry(LL, tab, e);
+    for (uint32_t e = (uint32_t)lane; e < FZ_LUT_SIZE; e += 32) st->lut[e] = fz_lut_entry(st->LL, tab, e);
 }
 
 // decode the sub-range of `lane` in tile `tile_pos` from st->start[lane]; out == nullptr: count only
@@ -413,8 +417,7 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
         inf.in_body = true;
         inf.one_block = true;
         inf.last = st->is_last != 0;
-        inf.LL = st->LL;
-        inf.DD = st->DD;
+        inf.bind_codes(&st->LL, &st->DD);
         inf.dd1 = st->dd1;
         stop_left = (int64_t)in_len * 8 - (int64_t)range_end;
     }

@@ -114,6 +114,17 @@ struct FzByteWriter {
         if (dry) { op += len; return; }
         while (len && (op & 3)) { put(c); len--; }
         const uint32_t w = c * 0x01010101u;
+        // long runs (zero planes are nothing else): 16-byte stores once the address allows it
+        while (len >= 4 && ((uintptr_t)(out + op) & 15u)) { *(uint32_t *)(out + op) = w; op += 4; len -= 4; }
+        while (len >= 16) {
+#if defined(__CUDA_ARCH__)
+            *(uint4 *)(out + op) = make_uint4(w, w, w, w);
+#else
+            uint32_t *q = (uint32_t *)(out + op);
+            q[0] = w; q[1] = w; q[2] = w; q[3] = w;
+#endif
+            op += 16; len -= 16;
+        }
         while (len >= 4) { *(uint32_t *)(out + op) = w; op += 4; len -= 4; }
         while (len) { put(c); len--; }
     }
@@ -253,7 +264,9 @@ template <class Tab>
 struct FzInflater {
     FzBitReader br;
     FzByteWriter bw;
-    FzCode LL, DD;
+    FzCode *LL, *DD;         // the codes of the current block, in storage the caller binds (bind_codes) before the first
+                             // step: 30 words that a warp decoding with ONE code keeps in shared memory instead of
+                             // 30 registers per lane
     Tab tab;
     size_t in_len;
     int rc;
@@ -287,6 +300,7 @@ struct FzInflater {
         br.refill();
         br.drop((int)(bit & 7));
     }
+    FZ_HD void bind_codes(FzCode *ll, FzCode *dd) { LL = ll; DD = dd; }
     FZ_HD uint64_t consumed_bits() const { return (uint64_t)((int64_t)in_len * 8 - br.bits_left()); }
 
     // returns true while there is more to do
@@ -331,13 +345,13 @@ struct FzInflater {
                 return true;
             }
             if (cnt > 1) {   // not enough room for all of them: take the first one the slow way
-                l = fz_decode_idx(LL, br.peek(15), idx);
+                l = fz_decode_idx(*LL, br.peek(15), idx);
                 if (l == 0) return fail(FZ_INF_E_DATA);
                 br.drop(l);
                 sym = tab.L((int)idx);
             } else br.drop((int)((e >> 25) & 15u));
         } else {
-            l = fz_decode_idx(LL, br.peek(15), idx);
+            l = fz_decode_idx(*LL, br.peek(15), idx);
             if (l == 0) return fail(FZ_INF_E_DATA);
             br.drop(l);
             sym = tab.L((int)idx);
@@ -363,7 +377,7 @@ struct FzInflater {
             if (b >= ((dd1 >> 16) & 3u)) return fail(FZ_INF_E_DATA);
             ds = (dd1 >> (8 * b)) & 0xffu;
         } else {
-            l = fz_decode_idx(DD, br.peek(15), idx);
+            l = fz_decode_idx(*DD, br.peek(15), idx);
             if (l == 0) return fail(FZ_INF_E_DATA);
             br.drop(l);
             ds = tab.D((int)idx);
@@ -425,14 +439,14 @@ struct FzInflater {
             tab.C(7) = 24; tab.C(8) = 152; tab.C(9) = 112;
             tab.C(16 + 5) = 32;
             dd1 = 0;
-            fz_code_build(LL, rd_ll, wr_ll);
-            fz_code_build(DD, rd_dd, wr_dd);
+            fz_code_build(*LL, rd_ll, wr_ll);
+            fz_code_build(*DD, rd_dd, wr_dd);
             for (int i = 0; i < 24; i++) tab.L(i) = (uint16_t)(256 + i);
             for (int i = 0; i < 144; i++) tab.L(24 + i) = (uint16_t)i;
             for (int i = 0; i < 8; i++) tab.L(168 + i) = (uint16_t)(280 + i);
             for (int i = 0; i < 112; i++) tab.L(176 + i) = (uint16_t)(144 + i);
             for (int i = 0; i < 32; i++) tab.D(i) = (uint16_t)i;
-            if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(LL, tab, e);
+            if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(*LL, tab, e);
             in_body = true;
             return true;
         }
@@ -476,8 +490,8 @@ struct FzInflater {
                 for (int l = 2; l <= 15; l++) dlong += tab.C(16 + l);
                 const uint32_t d1 = tab.C(16 + 1);
                 dd1 = (dlong == 0 && d1 >= 1 && d1 <= 2) ? (0x80000000u | (d1 << 16)) : 0u;
-                const int e1 = fz_code_build(LL, rd_ll, wr_ll);
-                const int e2 = fz_code_build(DD, rd_dd, wr_dd);
+                const int e1 = fz_code_build(*LL, rd_ll, wr_ll);
+                const int e2 = fz_code_build(*DD, rd_dd, wr_dd);
                 if (e1 < 0 || e2 < 0) return fail(FZ_INF_E_DATA);  // over-subscribed
                 ll_left = e1; dd_left = e2;
                 br = mark;
@@ -512,7 +526,7 @@ struct FzInflater {
             if (br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
         }
         if (dd1) dd1 |= (uint32_t)tab.D(0) | ((dd1 >> 16) & 2u ? (uint32_t)tab.D(1) << 8 : 0u);   // symbols are < 30
-        if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(LL, tab, e);
+        if (own_lut) for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) own_lut[e] = fz_lut_entry(*LL, tab, e);
         in_body = true;
         return true;
     }
@@ -524,10 +538,12 @@ struct FzInflater {
 // `out` must be 4-byte aligned.  Reads whole aligned 32-bit words around [in, in+in_len).
 template <class Tab>
 FZ_HD int fz_inflate(const uint8_t *in, size_t in_len, uint8_t *out, uint32_t out_cap, const Tab &tab,
-                     uint32_t *out_n, size_t *in_used, uint32_t *lut = nullptr)
+                     uint32_t *out_n, size_t *in_used, uint32_t *lut = nullptr, FzCode *codes = nullptr)
 {
     FzInflater<Tab> inf;
+    FzCode ll, dd;
     inf.start(in, in_len, out, out_cap, tab);
+    inf.bind_codes(codes ? &codes[0] : &ll, codes ? &codes[1] : &dd);
     inf.own_lut = lut;  // FZ_LUT_SIZE entries, or none
     while (inf.step()) {}
     return inf.finish(out_n, in_used);

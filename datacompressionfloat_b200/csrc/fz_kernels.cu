@@ -1003,17 +1003,8 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 struct FzGroupSmem {
     uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
     uint32_t lut[FZ_LUT_SIZE];
+    FzCode LL, DD;                 // the group's codes (long codes and distances; the LUT covers the rest)
 };
-
-#define FZ_BCAST_CODE(C, src)                                                                                   \
-    C.p1 = __shfl_sync(0xffffffffu, C.p1, src); C.p2 = __shfl_sync(0xffffffffu, C.p2, src);                     \
-    C.p3 = __shfl_sync(0xffffffffu, C.p3, src); C.p4 = __shfl_sync(0xffffffffu, C.p4, src);                     \
-    C.p5 = __shfl_sync(0xffffffffu, C.p5, src); C.p6 = __shfl_sync(0xffffffffu, C.p6, src);                     \
-    C.p7 = __shfl_sync(0xffffffffu, C.p7, src); C.p8 = __shfl_sync(0xffffffffu, C.p8, src);                     \
-    C.p9 = __shfl_sync(0xffffffffu, C.p9, src); C.p10 = __shfl_sync(0xffffffffu, C.p10, src);                   \
-    C.p11 = __shfl_sync(0xffffffffu, C.p11, src); C.p12 = __shfl_sync(0xffffffffu, C.p12, src);                 \
-    C.p13 = __shfl_sync(0xffffffffu, C.p13, src); C.p14 = __shfl_sync(0xffffffffu, C.p14, src);                 \
-    C.p15 = __shfl_sync(0xffffffffu, C.p15, src);
 
 __global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP)
 fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
@@ -1053,6 +1044,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     FzInflater<Tab> inf;
     bool live = false, bad = false;
     if (valid) { inf.start(frag, flen, out, expect, tab); inf.shared_tab = true; live = true; }
+    inf.bind_codes(&sm->LL, &sm->DD);
 
     // block type of every lane's first block: 2 (dynamic) lanes share the leader's code
     uint32_t first3 = 7;
@@ -1072,8 +1064,6 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
         __syncwarp();
         const uint32_t leader_ok = __shfl_sync(0xffffffffu, (uint32_t)(!bad), leader);
         hdr_bits = __shfl_sync(0xffffffffu, hdr_bits, leader);
-        FZ_BCAST_CODE(inf.LL, leader)
-        FZ_BCAST_CODE(inf.DD, leader)
         inf.dd1 = __shfl_sync(0xffffffffu, inf.dd1, leader);
         if (!leader_ok) {
             if (coded) { bad = true; live = false; }
@@ -1098,7 +1088,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                 }
             }
             // first-level table: entry e = the first symbol (and up to two more literals) coded by the bit pattern e
-            for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) sm->lut[e] = fz_lut_entry(inf.LL, tab, e);
+            for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) sm->lut[e] = fz_lut_entry(sm->LL, tab, e);
         }
         __syncwarp();
     }
@@ -1153,6 +1143,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
 {
     __shared__ uint16_t tabs[FZ_INF_TAB_U16];
     __shared__ uint32_t lut[FZ_LUT_SIZE];
+    __shared__ FzCode codes[2];
     const uint32_t s = blockIdx.x;
     if (threadIdx.x != 0 || status->error) return;
     const uint32_t mode = stream_mode[s] & 0xffu;
@@ -1167,7 +1158,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     FzInfTab<1> tab{tabs, tabs + 288, tabs + 320};
     uint32_t out_n = 0;
     size_t used = 0;
-    const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used, lut);
+    const int rc = fz_inflate(container + stream_off[s], (size_t)len, out, n_s, tab, &out_n, &used, lut, codes);
     if (rc != FZ_INF_OK || out_n != n_s) atomicCAS(&status->error, 0, FZ_E_FORMAT);
 }
 
@@ -1322,7 +1313,7 @@ fz_bp_sort_kernel(FzBlockParBufs bp, const FzStatus *status)
 // on the chain into the planes.  One WARP per block: the self-synchronising decoder of fz_blockpar.cuh.
 #define FZ_BP_SY_WARPS 4
 template <bool WRITE>
-__global__ void __launch_bounds__(FZ_BP_SY_WARPS * 32, 4)
+__global__ void __launch_bounds__(FZ_BP_SY_WARPS * 32, 5)
 fz_bp_sync_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
                   const unsigned long long *__restrict__ stream_off, FzBlockParBufs bp, uint8_t *__restrict__ planes,
                   const FzStatus *status)
@@ -1507,9 +1498,9 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;
     fz_bp_find_kernel<<<FZ_SM_COUNT * 16, FZ_BP_FIND_THREADS, 0, st>>>(container, container_size, stream_hdr, stream_off, b.bp, segs, status);
     fz_bp_sort_kernel<<<FZ_SM_COUNT, FZ_BP_CAP / 2, 0, st>>>(b.bp, status);
-    fz_bp_sync_kernel<false><<<FZ_SM_COUNT * 4, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
+    fz_bp_sync_kernel<false><<<FZ_SM_COUNT * 5, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
     fz_bp_chain_kernel<<<FZ_SM_COUNT, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, status);
-    fz_bp_sync_kernel<true><<<FZ_SM_COUNT * 4, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
+    fz_bp_sync_kernel<true><<<FZ_SM_COUNT * 5, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
     fz_bp_stored_kernel<<<FZ_SM_COUNT * 4, 128, 0, st>>>(container, container_size, g, stream_off, b.bp, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_BLOCKPAR);
     fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, b.bp.par_ok, planes, status);
