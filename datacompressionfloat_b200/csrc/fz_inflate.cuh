@@ -26,6 +26,10 @@ struct FzInfTab {
 };
 #define FZ_INF_TAB_U16 (288 + 32 + 32)  // uint16 entries per decoding thread
 
+// Bit reader over an arbitrarily aligned byte range: aligned 32-bit loads, the next word fetched one refill ahead.
+// (A variant fetching aligned 16-byte chunks one chunk ahead cut the L2 round trips fourfold -- ncu shows a 3.5 % L1
+// hit rate here, L1 being carved away by shared memory -- but its longer refill and 16 more registers cost more than
+// that bought on every input except exponent planes: measured, not kept.)
 struct FzBitReader {
     const uint32_t *w;     // address of the word held in `nxt` (may run past wend: zero bits are fed then)
     const uint32_t *wend;  // one past the last word that holds input bytes
@@ -61,6 +65,8 @@ struct FzBitReader {
     FZ_HD void drop(int n) { acc >>= n; nacc -= n; }
     FZ_HD uint32_t get(int n) { const uint32_t v = peek(n); drop(n); return v; }  // n <= 16, after refill
     FZ_HD void align_byte() { const int k = (int)(bits_left() & 7); drop(k); }
+    // byte-aligned reader: address of the next unread input byte (`nxt` holds the word at w, acc the bytes before it)
+    FZ_HD const uint8_t *byte_ptr() const { return (const uint8_t *)w - (nacc >> 3); }
 };
 
 struct FzByteWriter {
@@ -127,6 +133,32 @@ struct FzByteWriter {
         }
         while (len >= 4) { *(uint32_t *)(out + op) = w; op += 4; len -= 4; }
         while (len) { put(c); len--; }
+    }
+    // append len bytes read from src (any alignment; reads stay inside the aligned words that hold src[0, len))
+    FZ_HD void copy_in(const uint8_t *src, uint32_t len)
+    {
+        if (len == 0) return;
+        if (dry) { op += len; lastc = src[len - 1]; return; }
+        while (len && (op & 3)) { put(*src++); len--; }
+        if (len >= 4) {
+            const unsigned sk = (unsigned)((uintptr_t)src & 3);
+            const uint32_t *sw = (const uint32_t *)(src - sk);
+            const uint32_t nw = len >> 2;
+            if (sk == 0) {
+                for (uint32_t i = 0; i < nw; i++) { *(uint32_t *)(out + op) = sw[i]; op += 4; }
+            } else {
+                uint32_t a = sw[0];
+                for (uint32_t i = 0; i < nw; i++) {
+                    const uint32_t b = sw[i + 1];   // holds at least one byte of src[4i, 4i+4): inside the range
+                    *(uint32_t *)(out + op) = (a >> (8 * sk)) | (b << (32 - 8 * sk));
+                    op += 4;
+                    a = b;
+                }
+            }
+            src += (size_t)nw * 4;
+            len &= 3;
+        }
+        while (len) { put(*src++); len--; }
     }
     FZ_HD void finish()
     {
@@ -422,7 +454,11 @@ struct FzInflater {
             if ((len ^ 0xFFFFu) != nlen) return fail(FZ_INF_E_DATA);
             if (br.bits_left() < (int64_t)len * 8) return fail(FZ_INF_E_INPUT);
             if (bw.op + len > bw.cap) return fail(FZ_INF_E_SPACE);
-            for (uint32_t i = 0; i < len; i++) { br.refill(); bw.put(br.get(8)); }
+            // the payload of a stored block is copied word-wise straight from the input, not through the bit reader
+            const int64_t rest = br.bits_left() - (int64_t)len * 8;
+            const uint8_t *src = br.byte_ptr();
+            bw.copy_in(src, len);
+            br.init(src + len, (size_t)(rest >> 3));
             return !last;
         }
         if (type == 3) return fail(FZ_INF_E_DATA);
