@@ -40,7 +40,7 @@ struct mzb_ctx {
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags;
     // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_comp, ev_d2h;
@@ -190,7 +190,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
@@ -349,8 +349,10 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
         (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
         (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib->hits_cap * 4)) ||
-        (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams, chk))))
+        (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams, chk))) ||
+        (rc = ensure(c->zero_flags, (size_t)nstreams * nsub_full * 4)))
         return rc;
+    ib->zero_flags = (uint32_t *)c->zero_flags.p;
     ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams, chk);
     ib->tile_cnt = (uint32_t *)c->tile_cnt.p;
     ib->block_sums = (uint32_t *)c->block_sums.p;
@@ -371,7 +373,7 @@ static void decompress_enqueue_batch(mzb_ctx *c, const uint8_t *d_in, size_t in_
                       (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c, !in_place_raw);
     if (in_place_raw)
         fz_launch_merge_streams((const uint8_t *)c->planes.p, d_in, (const uint32_t *)c->stream_hdr.p,
-                                (const unsigned long long *)c->stream_off.p, g, d_words_out, c->stream);
+                                (const unsigned long long *)c->stream_off.p, ib.zero_flags, g, d_words_out, c->stream);
     else
         fz_launch_merge((const uint8_t *)c->planes.p, g.plane_stride, (uint64_t)(g.nchunks - 1) * g.chk + g.last_n, d_words_out,
                         c->merge_variant, c->stream);

@@ -115,14 +115,20 @@ FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, u
             // H bits below stand for the bytes before the group (from `rep`).  Byte k is withheld iff the
             // H+1 flags ending at k are all set.
             const FzVec16 v = ld(i);
+            // four bytes per step: XOR each word with itself shifted up one byte (the predecessor of byte 0 comes from
+            // the word before), find the zero bytes exactly, gather their flags with one multiply
             uint32_t eq = 0;
-            int p = prev;
+            uint32_t before = (uint32_t)prev << 24;   // prev = -1 (no predecessor) gives 0xFF...: compared as 0xFF, fixed below
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const int c = (int)((v.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
-                eq |= (uint32_t)(c == p) << (k + FZ_HOLD_AFTER);
-                p = c;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t w = v.w[j];
+                const uint32_t x = w ^ ((w << 8) | (before >> 24));
+                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
+                eq |= ((z * 0x00204081u) >> 28) << (4 * j + FZ_HOLD_AFTER);
+                before = w;
             }
+            if (prev < 0) eq &= ~(1u << FZ_HOLD_AFTER);   // the first byte of a piece has no predecessor
+            const int p = (int)(v.w[3] >> 24);
             const uint32_t hist_bits = ((1u << rep) - 1u) << (FZ_HOLD_AFTER - rep);  // the last `rep` flags before the group
             const uint32_t ext = eq | hist_bits;
             uint32_t held = ext;

@@ -79,11 +79,12 @@ struct FzByteWriter {
     bool non_rle;      // dry: a match with a distance other than 1 was seen (its bytes are unknown without history)
     bool starts_with_match;  // dry: the fragment begins with a distance-1 match reaching the byte before it
     uint32_t lastc;    // dry: value of the last literal, 0x100 = none yet
+    uint32_t orv;      // dry: OR of all literal values (0 = the fragment is nothing but zero bytes)
     FZ_HD void init(uint8_t *o, uint32_t c)
     {
         const uint32_t mis = (uint32_t)((uintptr_t)o & 3u);
         out = o - mis; op0 = mis; op = mis; cap = c + mis; ow = 0;
-        prev_byte = -1; dry = false; non_rle = false; starts_with_match = false; lastc = 0x100;
+        prev_byte = -1; dry = false; non_rle = false; starts_with_match = false; lastc = 0x100; orv = 0;
     }
     FZ_HD uint32_t produced() const { return op - op0; }
     FZ_HD void store_word(uint32_t widx_bytes, uint32_t w)  // the word starting at byte offset widx_bytes is complete
@@ -93,7 +94,7 @@ struct FzByteWriter {
     }
     FZ_HD void put(uint32_t c)
     {
-        if (dry) { op++; lastc = c; return; }
+        if (dry) { op++; lastc = c; orv |= c; return; }
         ow |= c << ((op & 3) * 8);
         op++;
         if ((op & 3) == 0) { store_word(op - 4, ow); ow = 0; }
@@ -107,7 +108,7 @@ struct FzByteWriter {
     // append cnt (1..3) bytes packed little-endian in v; the caller checked op + cnt <= cap
     FZ_HD void putn(uint32_t v, uint32_t cnt)
     {
-        if (dry) { op += cnt; lastc = (v >> (8 * (cnt - 1))) & 0xffu; return; }
+        if (dry) { op += cnt; lastc = (v >> (8 * (cnt - 1))) & 0xffu; orv |= v; return; }
         const uint32_t sh = (op & 3) * 8;
         const uint64_t t = (uint64_t)ow | ((uint64_t)v << sh);
         const uint32_t nb = sh + cnt * 8;  // bits now pending
@@ -138,7 +139,7 @@ struct FzByteWriter {
     FZ_HD void copy_in(const uint8_t *src, uint32_t len)
     {
         if (len == 0) return;
-        if (dry) { op += len; lastc = src[len - 1]; return; }
+        if (dry) { op += len; lastc = src[len - 1]; orv |= 1u; return; }   // (not examined: counts as "not all zero")
         while (len && (op & 3)) { put(*src++); len--; }
         if (len >= 4) {
             const unsigned sk = (unsigned)((uintptr_t)src & 3);

@@ -297,18 +297,31 @@ __device__ __forceinline__ uint32_t fz_ld_u32_unaligned(const uint8_t *src, uint
 
 __global__ void __launch_bounds__(FZ_SPLIT_THREADS)
 fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
-                        const unsigned long long *__restrict__ stream_off, FzBatchGeom g, uint32_t *__restrict__ words)
+                        const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ zero_flags, FzBatchGeom g,
+                        uint32_t *__restrict__ words)
 {
     const uint32_t c = blockIdx.y;
     const uint32_t n_c = (c == g.nchunks - 1) ? g.last_n : g.chk;
     const uint32_t nvec = n_c / 4;
     const uint8_t *src[4];
     const uint8_t *end[4];
+    bool zero[4];
+    // a CTA covers FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL * 4 = 4096 plane bytes: inside one 16 KiB sub-block
+    const uint32_t sub = (blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL * 4)) >> FZ_SUB_LOG2;
+    // sub-blocks the inflater found to be all zero were never written to the plane buffer (mask bits >= 8 zero
+    // whole byte planes: 1 GiB of stores and 1 GiB of loads per 4 GiB volume that nobody needs).
+    // All eight table loads are issued before anything depends on them: these CTAs live for a microsecond.
+    uint32_t h[4], zf[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t h = stream_hdr[c * 4 + j];
-        src[j] = (h & FZ_RAW_FLAG) ? container + stream_off[c * 4 + j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
+        h[j] = __ldg(stream_hdr + c * 4 + j);
+        zf[j] = zero_flags ? __ldg(zero_flags + (size_t)(c * 4 + j) * g.nsub_full + sub) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        src[j] = (h[j] & FZ_RAW_FLAG) ? container + stream_off[c * 4 + j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
         end[j] = src[j] + n_c;
+        zero[j] = zf[j] != 0 && !(h[j] & FZ_RAW_FLAG);
     }
     uint4 *out4 = (uint4 *)(words + (uint64_t)c * g.chk);
     const uint32_t base = blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL) + threadIdx.x;
@@ -317,10 +330,10 @@ fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__res
     for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
         const uint32_t i = base + k * FZ_SPLIT_THREADS;
         if (i < nvec) {
-            a[k] = fz_ld_u32_unaligned(src[0], (uint64_t)i * 4, end[0]);
-            b[k] = fz_ld_u32_unaligned(src[1], (uint64_t)i * 4, end[1]);
-            cc[k] = fz_ld_u32_unaligned(src[2], (uint64_t)i * 4, end[2]);
-            d[k] = fz_ld_u32_unaligned(src[3], (uint64_t)i * 4, end[3]);
+            a[k] = zero[0] ? 0u : fz_ld_u32_unaligned(src[0], (uint64_t)i * 4, end[0]);
+            b[k] = zero[1] ? 0u : fz_ld_u32_unaligned(src[1], (uint64_t)i * 4, end[1]);
+            cc[k] = zero[2] ? 0u : fz_ld_u32_unaligned(src[2], (uint64_t)i * 4, end[2]);
+            d[k] = zero[3] ? 0u : fz_ld_u32_unaligned(src[3], (uint64_t)i * 4, end[3]);
         }
     }
 #pragma unroll
@@ -335,17 +348,22 @@ fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__res
     if (blockIdx.x == 0 && threadIdx.x < (n_c & 3u)) {  // ragged tail of the last chunk
         const uint32_t i = nvec * 4 + threadIdx.x;
         uint32_t w = 0;
-        for (int j = 0; j < 4; j++) w |= (uint32_t)src[j][i] << (8 * j);
+        for (int j = 0; j < 4; j++) {
+            const bool zt = zero_flags && !(stream_hdr[c * 4 + j] & FZ_RAW_FLAG) &&
+                            zero_flags[(size_t)(c * 4 + j) * g.nsub_full + (i >> FZ_SUB_LOG2)] != 0;
+            w |= (zt ? 0u : (uint32_t)src[j][i]) << (8 * j);
+        }
         words[(uint64_t)c * g.chk + i] = w;
     }
 }
 
 void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, const uint32_t *stream_hdr,
-                             const unsigned long long *stream_off, FzBatchGeom g, uint32_t *words, cudaStream_t st)
+                             const unsigned long long *stream_off, const uint32_t *zero_flags, FzBatchGeom g, uint32_t *words,
+                             cudaStream_t st)
 {
     const uint32_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
     dim3 grid((g.chk / 4 + per - 1) / per, g.nchunks);
-    fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, g, words);
+    fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words);
 }
 
 // =================================================================================================
@@ -1000,6 +1018,8 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 // own fragment with it.  Lanes verify that their header bits equal the leader's; any mismatch, parse error
 // or size mismatch flags the stream, which is then re-decoded by the general inflater.
 #define FZ_INF_WARPS 4
+#define FZ_INF_CARVEOUT_PCT 72     // of 228 KB: 164 KB shared memory, 92 KB L1
+#define FZ_ZERO_PROBE_BYTES 96u   // 16 KiB of zeros is ~70 bytes of run codes
 struct FzGroupSmem {
     uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
     uint32_t lut[FZ_LUT_SIZE];
@@ -1010,7 +1030,8 @@ __global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP)
 fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
                         const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ tile_off,
                         uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
-                        uint32_t *__restrict__ stream_fail, uint8_t *__restrict__ planes, const FzStatus *status)
+                        uint32_t *__restrict__ stream_fail, uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes,
+                        const FzStatus *status)
 {
     __shared__ FzGroupSmem smem[FZ_INF_WARPS];
     if (status->error) return;
@@ -1095,6 +1116,34 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     // lock-step drive: lanes reconverge after every symbol
     const uint32_t *lut = coded_mask ? sm->lut : nullptr;
     const uint32_t run_bit = fz_dd1_run_bit(inf.dd1);
+    // Tiny fragments are almost always sub-blocks of zero bytes (mask bits >= 8 zero whole byte planes).  Count them
+    // first without storing: if the fragment is valid and all zero it is only flagged -- the merge supplies the
+    // zeros -- which saves 16 KiB of stores here and 16 KiB of loads there.
+    bool all_zero = false;
+    if (zero_flags) {
+        bool probe = live && coded && flen <= FZ_ZERO_PROBE_BYTES;
+        if (__any_sync(0xffffffffu, probe)) {
+            if (probe) inf.bw.dry = true;
+            bool pl = probe;
+            while (__any_sync(0xffffffffu, pl)) {
+                if (pl) pl = inf.step_lut(lut);
+            }
+            if (probe) {
+                all_zero = inf.rc == FZ_INF_OK && inf.bw.produced() == expect && inf.bw.orv == 0 && !inf.bw.non_rle &&
+                           inf.br.bits_left() == 0;
+                if (all_zero) live = false;
+                else {   // decode it for real: same state as after the header
+                    const uint32_t nby = hdr_bits >> 3, rem = hdr_bits & 7u;
+                    inf.bw.init(out, expect);
+                    inf.br.init(frag + nby, flen - nby);
+                    inf.br.refill();
+                    inf.br.drop((int)rem);
+                    inf.rc = FZ_INF_OK; inf.in_body = true; inf.last = false; inf.saw_eob = false;
+                }
+            }
+        }
+        if (valid) zero_flags[(size_t)s * g.nsub_full + k] = all_zero ? 1u : 0u;
+    }
     while (__any_sync(0xffffffffu, live)) {
         if (live) {
             if (inf.in_body && lut) {
@@ -1124,7 +1173,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
             live = inf.step_lut(lut);  // whatever comes next: long code, match, end of block, block header
         }
     }
-    if (valid) {
+    if (valid && !all_zero) {
         uint32_t out_n = 0;
         size_t used = 0;
         const int rc = inf.finish(&out_n, &used);
@@ -1139,7 +1188,7 @@ __global__ void __launch_bounds__(32)
 fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
                           const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_mode,
                           const uint32_t *__restrict__ stream_fail, const uint32_t *__restrict__ par_ok,
-                          uint8_t *__restrict__ planes, FzStatus *status)
+                          uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes, FzStatus *status)
 {
     __shared__ uint16_t tabs[FZ_INF_TAB_U16];
     __shared__ uint32_t lut[FZ_LUT_SIZE];
@@ -1152,6 +1201,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     if (failed) atomicAdd(&status->n_fast_failed, 1u);
     atomicAdd(&status->n_general, 1u);
     if (mode == 2u && par_ok[s]) { atomicAdd(&status->n_blockpar, 1u); return; }   // decoded block-parallel
+    if (zero_flags) for (uint32_t k = 0; k < g.nsub_full; k++) zero_flags[(size_t)s * g.nsub_full + k] = 0;   // all of it gets written
     const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
     const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
     uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk;
@@ -1488,11 +1538,18 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     fz_marker_kernel<true><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
     if (mark) mark(mark_user, FZ_ST_MARKERS);
     cudaMemsetAsync(b.bp.ctl, 0, 64, st);
+    // zero-sub-block flags only when the merge that follows reads them (copy_raw: the plain merge reads the plane buffer)
+    uint32_t *zf = copy_raw ? nullptr : b.zero_flags;
+    if (zf) cudaMemsetAsync(zf, 0, (size_t)nstreams * g.nsub_full * 4, st);
     fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, b.bp, status);
     if (mark) mark(mark_user, FZ_ST_CLASSIFY);
     const uint32_t ngroups = nstreams * ((g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
+    // Every lane streams its own fragment: what little L1 the shared-memory carve-out leaves decides how often an input
+    // word is an L2 round trip.  164 KB of shared memory (4 CTAs of 37 KB) and 92 KB of L1 beat 228 KB / 6 CTAs by
+    // 20-25 % on every input measured (sweep in profiles/README.md).
+    cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FZ_INF_CARVEOUT_PCT);
     fz_inflate_group_kernel<<<(ngroups + FZ_INF_WARPS - 1) / FZ_INF_WARPS, FZ_INF_WARPS * FZ_WARP, 0, st>>>(
-        container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, planes, status);
+        container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
     const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;
@@ -1503,7 +1560,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     fz_bp_sync_kernel<true><<<FZ_SM_COUNT * 5, FZ_BP_SY_WARPS * 32, 0, st>>>(container, g, stream_hdr, stream_off, b.bp, planes, status);
     fz_bp_stored_kernel<<<FZ_SM_COUNT * 4, 128, 0, st>>>(container, container_size, g, stream_off, b.bp, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_BLOCKPAR);
-    fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, b.bp.par_ok, planes, status);
+    fz_inflate_general_kernel<<<nstreams, 32, 0, st>>>(container, g, stream_hdr, stream_off, b.stream_mode, b.stream_fail, b.bp.par_ok, zf, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_GENERAL);
     if (copy_raw) {  // only when the merge cannot read RAW payloads in place (chunk size not a multiple of 16)
         const uint32_t total = nstreams * g.nsub_full;

@@ -95,6 +95,7 @@ struct FzInflateBufs {
     uint32_t hits_cap;
     uint32_t *stream_mode;   // [nstreams] 0 raw, 1 fast | sub_log2 << 8, 2 general
     uint32_t *stream_fail;   // [nstreams]
+    uint32_t *zero_flags;    // [nstreams * nsub_full] 1 = the sub-block is all zero bytes and was NOT written to the plane buffer
     uint32_t tiles_per_stream;
     FzBlockParBufs bp;
 };
@@ -103,6 +104,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
                        cudaStream_t st, fz_mark_fn mark, void *mark_user, bool copy_raw);
 // merge that reads RAW streams in place from the container (needs chk % 16 == 0)
 void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, const uint32_t *stream_hdr,
-                             const unsigned long long *stream_off, FzBatchGeom g, uint32_t *words, cudaStream_t st);
+                             const unsigned long long *stream_off, const uint32_t *zero_flags, FzBatchGeom g, uint32_t *words,
+                             cudaStream_t st);
 
 size_t fz_encode_smem_bytes();
