@@ -40,7 +40,8 @@ struct mzb_ctx {
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist;
+    bool zero_hist_ready = false;
     // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_comp, ev_d2h;
@@ -190,7 +191,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
@@ -311,7 +312,8 @@ static int compress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t *p
     if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->scratch, nslots * FZ_SLOT_STRIDE + 256)) ||
         (rc = ensure(c->sizes, nslots * 4)) || (rc = ensure(c->sub_off, nslots * 4)) ||
         (rc = ensure(c->stream_hdr, (size_t)bmax * FZ_PLANES * 4)) || (rc = ensure(c->stream_off, (size_t)bmax * FZ_PLANES * 8)) ||
-        (rc = ensure(c->ghist, ngroups * 288 * 4)) || (rc = ensure(c->gcodes, ngroups * fz_group_code_bytes())))
+        (rc = ensure(c->ghist, ngroups * 288 * 4)) || (rc = ensure(c->gcodes, ngroups * fz_group_code_bytes())) ||
+        (rc = ensure(c->zero_hist, 288 * 4)))
         return rc;
     *pstride_out = pstride;
     return MZB_OK;
@@ -323,10 +325,11 @@ static void compress_enqueue_batch(mzb_ctx *c, const uint32_t *d_words, uint64_t
     const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
     fz_launch_split(d_words, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
     prof_mark(c, FZ_ST_SPLIT);
+    if (!c->zero_hist_ready) { fz_launch_zero_hist((uint32_t *)c->zero_hist.p, c->stream); c->zero_hist_ready = true; }
     fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p,
-                     (uint32_t *)c->sizes.p, c->d_status, c->stream);
+                     (uint32_t *)c->sizes.p, (const uint32_t *)c->zero_hist.p, c->d_status, c->stream);
     prof_mark(c, FZ_ST_ENCODE);
-    fz_launch_layout((const uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
+    fz_launch_layout((uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
                      (unsigned long long *)c->stream_off.p, d_out, out_cap, c->d_status, c->stream);
     prof_mark(c, FZ_ST_LAYOUT);
     fz_launch_gather((const uint8_t *)c->planes.p, (const uint8_t *)c->scratch.p, (const uint32_t *)c->sizes.p,

@@ -40,6 +40,9 @@
 #define FZ_STORED_OVERHEAD 15u
 #define FZ_MARKER_LE 0xFFFF0000u          // bytes 00 00 FF FF read as a little-endian uint32
 #define FZ_SIZE_STORED_FLAG 0x80000000u   // in the per-sub-block size word: emit as stored block
+#define FZ_SIZE_ZERO_FLAG 0x40000000u     // the sub-block is 16 KiB of zero bytes (found by the histogram kernel)
+#define FZ_SIZE_COPY_FLAG 0x20000000u     // its fragment is byte-identical to the one of sub-block (bits 24..28) of its group
+#define FZ_SIZE_MASK 0x00FFFFFFu          // the size itself
 
 #define FZ_MAX_MATCH 258
 #define FZ_MIN_MATCH 3

@@ -443,7 +443,7 @@ struct __align__(16) FzHistSmem {
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
 fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist, uint32_t *__restrict__ sizes,
-               FzStatus *status)
+               const uint32_t *__restrict__ zero_hist, FzStatus *status)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -478,6 +478,27 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
             if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
             return;
         }
+        if (sm->hist[0] == 2048u) {
+            // The sample is all zeros: mask bits >= 8 zero whole byte planes, so most likely the sub-block is.  One OR
+            // over its 16 KiB settles it; then its tokens are known without scanning (the same for every such
+            // sub-block: zero_hist, made once by fz_zero_hist_kernel with this very tokeniser), and the emit kernel
+            // encodes only the first zero sub-block of each group -- the others are copies of its fragment.
+            uint32_t any = 0;
+#pragma unroll 4
+            for (uint32_t i = lane * 16; i < FZ_SUB; i += FZ_WARP * 16) {
+                const uint4 v = *(const uint4 *)(src + i);
+                any |= v.x | v.y | v.z | v.w;
+            }
+            if (!__any_sync(0xffffffffu, any != 0)) {
+                if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
+                uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+                for (int i = lane; i < 288; i += 32) {
+                    const uint32_t v = zero_hist[i];
+                    if (v) atomicAdd(gh + i, v);
+                }
+                return;
+            }
+        }
         __syncwarp();
         for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
         __syncwarp();
@@ -493,6 +514,23 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
         const uint32_t v = sm->hist[i];
         if (v) atomicAdd(gh + i, v);
     }
+}
+
+// token histogram of a sub-block of FZ_SUB zero bytes, by the tokeniser itself (one warp, once per context)
+__global__ void __launch_bounds__(FZ_WARP)
+fz_zero_hist_kernel(uint32_t *__restrict__ zero_hist)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    const int lane = threadIdx.x;
+    FzHistSmem *sm = (FzHistSmem *)fz_smem;
+    for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
+    for (uint32_t i = lane * 16; i < FZ_STAGE_BYTES; i += FZ_WARP * 16) *(uint4 *)(sm->stage + i) = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
+    DevLoadByte lb{sm->stage, fz_piece_len(FZ_SUB)};
+    fz_ph_hist(sm->hist, ld, lb, FZ_SUB, lane);
+    __syncwarp();
+    for (int i = lane; i < 288; i += 32) zero_hist[i] = sm->hist[i];
 }
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
@@ -533,11 +571,21 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
     uint32_t s, k, n;
     if (!fz_slot(g, t, s, k, n)) return;
-    if (sizes[t] & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
+    const uint32_t sz0 = sizes[t];
+    if (sz0 & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
     const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
     if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to stage or emit
         if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
         return;
+    }
+    if (sz0 & FZ_SIZE_ZERO_FLAG) {
+        // all-zero sub-blocks of a group are the same bytes coded with the same code: only the first one is encoded,
+        // the layout kernel gives the others its size and the gather kernel copies its fragment (bit 30 of a size
+        // word never changes while this kernel runs, so every warp sees the same leader)
+        const uint32_t kb = k & ~(uint32_t)(FZ_GROUP_SUBS - 1);
+        const uint32_t other = (kb + lane < g.nsub_full) ? sizes[t - (k - kb) + lane] : 0u;
+        const uint32_t zmask = __ballot_sync(0xffffffffu, (other & FZ_SIZE_ZERO_FLAG) != 0);
+        if ((uint32_t)(__ffs((int)zmask) - 1) != k - kb) return;
     }
     FzEmitSmem *sm = (FzEmitSmem *)fz_smem + warp;
     {   // code table of the group -> shared memory (word copy of the hot part)
@@ -551,15 +599,21 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
     const uint32_t r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, ld, lb, n, out, lane);
     if (lane == 0) {
-        sizes[t] = r;
+        sizes[t] = r | (sz0 & FZ_SIZE_ZERO_FLAG);
         if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
     }
 }
 
 size_t fz_encode_smem_bytes() { return sizeof(FzEmitSmem) * FZ_ENC_WARPS; }
 
+void fz_launch_zero_hist(uint32_t *zero_hist, cudaStream_t st)
+{
+    cudaFuncSetAttribute(fz_zero_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzHistSmem));
+    fz_zero_hist_kernel<<<1, FZ_WARP, sizeof(FzHistSmem), st>>>(zero_hist);
+}
+
 void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, void *gcodes, uint8_t *scratch, uint32_t *sizes,
-                      FzStatus *status, cudaStream_t st)
+                      const uint32_t *zero_hist, FzStatus *status, cudaStream_t st)
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t total = nstreams * g.nsub_full;
@@ -570,7 +624,7 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
     cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEmitSmem) * FZ_ENC_WARPS));
     cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
-    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, status);
+    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, zero_hist, status);
     fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
         ghist, g, (FzGroupCode *)gcodes);
     fz_emit_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEmitSmem) * FZ_ENC_WARPS, st>>>(planes, g, (const FzGroupCode *)gcodes,
@@ -595,7 +649,7 @@ __device__ __forceinline__ uint32_t fz_warp_incl_scan(uint32_t v, int lane)
 // one warp per stream: sub_off[t] = exclusive prefix of the sub-block sizes inside the stream;
 // stream_hdr[s] = payload length | RAW flag, with the reference's rule "compressed iff n > len + 4" (zip.c:177)
 __global__ void __launch_bounds__(128)
-fz_layout_streams_kernel(const uint32_t *__restrict__ sizes, FzBatchGeom g, uint32_t *__restrict__ sub_off,
+fz_layout_streams_kernel(uint32_t *__restrict__ sizes, FzBatchGeom g, uint32_t *__restrict__ sub_off,
                          uint32_t *__restrict__ stream_hdr, FzStatus *status)
 {
     const int lane = threadIdx.x & 31;
@@ -606,7 +660,20 @@ fz_layout_streams_kernel(const uint32_t *__restrict__ sizes, FzBatchGeom g, uint
     uint32_t carry = 0;
     for (uint32_t k0 = 0; k0 < nsub; k0 += 32) {
         const uint32_t k = k0 + lane;
-        const uint32_t v = k < nsub ? (sizes[s * g.nsub_full + k] & ~FZ_SIZE_STORED_FLAG) : 0u;
+        uint32_t raw = k < nsub ? sizes[s * g.nsub_full + k] : 0u;
+        // one iteration = one group: all-zero sub-blocks take size (and fragment) of the group's first one
+        const uint32_t zmask = __ballot_sync(0xffffffffu, (raw & FZ_SIZE_ZERO_FLAG) != 0);
+        if (zmask) {
+            const int leader = __ffs((int)zmask) - 1;
+            const uint32_t lv = __shfl_sync(0xffffffffu, raw, leader);
+            if ((raw & FZ_SIZE_ZERO_FLAG) && lane != leader) {
+                raw = (lv & FZ_SIZE_STORED_FLAG) ? (lv & (FZ_SIZE_MASK | FZ_SIZE_STORED_FLAG))
+                                                 : ((lv & FZ_SIZE_MASK) | FZ_SIZE_COPY_FLAG | ((uint32_t)leader << 24));
+                sizes[s * g.nsub_full + k] = raw;
+                if (lv & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
+            }
+        }
+        const uint32_t v = raw & FZ_SIZE_MASK;
         const uint32_t inc = fz_warp_incl_scan(v, lane);
         if (k < nsub) sub_off[s * g.nsub_full + k] = carry + inc - v;
         carry += __shfl_sync(0xffffffffu, inc, 31);
@@ -682,7 +749,7 @@ fz_layout_chunks_kernel(const uint32_t *__restrict__ stream_hdr, FzBatchGeom g, 
     if (threadIdx.x == 0) status->out_end = base_sh;
 }
 
-void fz_launch_layout(const uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
+void fz_launch_layout(uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
                       unsigned long long *stream_off, uint8_t *container, uint64_t container_cap, FzStatus *status, cudaStream_t st)
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
@@ -769,8 +836,10 @@ fz_gather_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__
         fz_warp_copy(dst + 5, psrc, s, psrc + n + 32, lane);
         fz_warp_copy(dst + 10 + s, psrc + s, r, psrc + n + 32, lane);
     } else {
-        const uint8_t *ssrc = scratch + (uint64_t)t * FZ_SLOT_STRIDE;
-        fz_warp_copy(dst, ssrc, sz, ssrc + FZ_SLOT_STRIDE, lane);
+        // (an all-zero sub-block that is not the first of its group: the first one's fragment, byte for byte)
+        const uint32_t tsrc = (sz & FZ_SIZE_COPY_FLAG) ? t - (k & (FZ_GROUP_SUBS - 1)) + ((sz >> 24) & 31u) : t;
+        const uint8_t *ssrc = scratch + (uint64_t)tsrc * FZ_SLOT_STRIDE;
+        fz_warp_copy(dst, ssrc, sz & FZ_SIZE_MASK, ssrc + FZ_SLOT_STRIDE, lane);
     }
 }
 

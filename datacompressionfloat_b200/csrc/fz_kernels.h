@@ -48,11 +48,13 @@ void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwor
 // ---- deflate side
 // ghist: 288 uint32 per group (zeroed by the call); gcodes: fz_group_code_bytes() per group;
 // groups per stream = ceil(nsub_full / FZ_GROUP_SUBS)
+// zero_hist: 288 uint32 made once per context by fz_launch_zero_hist (token histogram of an all-zero sub-block)
+void fz_launch_zero_hist(uint32_t *zero_hist, cudaStream_t st);
 void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, void *gcodes, uint8_t *scratch, uint32_t *sizes,
-                      FzStatus *status, cudaStream_t st);
+                      const uint32_t *zero_hist, FzStatus *status, cudaStream_t st);
 size_t fz_group_code_bytes();
 // stream sums + RAW decision + scan over chunk records + chunk headers; container offsets continue from status->out_end
-void fz_launch_layout(const uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
+void fz_launch_layout(uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
                       unsigned long long *stream_off, uint8_t *container, uint64_t container_cap, FzStatus *status,
                       cudaStream_t st);
 void fz_launch_gather(const uint8_t *planes, const uint8_t *scratch, const uint32_t *sizes, const uint32_t *sub_off,
