@@ -102,101 +102,140 @@ FZ_HD uint32_t fz_run_len(uint32_t x, uint32_t width)
     return r < width ? r : width;
 }
 
+// The tokeniser's state between 16-byte groups (so that a caller can feed a piece window by window).
+struct FzScan {
+    int prev;        // last byte seen, -1 = none
+    uint32_t rep;    // repeats of `prev` seen so far in this run (saturates at FZ_HOLD_AFTER)
+    uint32_t m;      // withheld bytes
+    FZ_HD void init(int prev_init) { prev = prev_init; rep = 0; m = 0; }
+
+    // Whole 16-byte group at once.  Bit k+H of eq = byte k equals its predecessor (H = FZ_HOLD_AFTER); the
+    // H bits below stand for the bytes before the group (from `rep`).  Byte k is withheld iff the
+    // H+1 flags ending at k are all set.
+    template <class Sink>
+    FZ_HD void group16(const FzVec16 &v, Sink &sink)
+    {
+        // four bytes per step: XOR each word with itself shifted up one byte (the predecessor of byte 0 comes from
+        // the word before), find the zero bytes exactly, gather their flags with one multiply
+        uint32_t eq = 0;
+        uint32_t before = (uint32_t)prev << 24;   // prev = -1 (no predecessor) gives 0xFF...: compared as 0xFF, fixed below
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = v.w[j];
+            const uint32_t x = w ^ ((w << 8) | (before >> 24));
+            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
+            eq |= ((z * 0x00204081u) >> 28) << (4 * j + FZ_HOLD_AFTER);
+            before = w;
+        }
+        if (prev < 0) eq &= ~(1u << FZ_HOLD_AFTER);   // the first byte of a piece has no predecessor
+        const int p = (int)(v.w[3] >> 24);
+        const uint32_t hist_bits = ((1u << rep) - 1u) << (FZ_HOLD_AFTER - rep);  // the last `rep` flags before the group
+        const uint32_t ext = eq | hist_bits;
+        uint32_t held = ext;
+#pragma unroll
+        for (int j = 1; j <= FZ_HOLD_AFTER; j++) held &= ext << j;
+        held >>= FZ_HOLD_AFTER;  // 16 bits: byte k of the group is withheld
+        if (!Sink::kOrdered) {
+            // token order is irrelevant (histogram, bit count): every byte that is not withheld is a literal,
+            // all lanes run the same code whatever their data; runs are book-kept below (rare)
+            // (when no lane of the warp withholds anything the unpredicated form is a little cheaper)
+            if (FZ_WARP_ALL(held == 0)) sink.literal16(v);
+            else if (!FZ_WARP_ALL(held == 0xffffu)) sink.literal_masked(v, ~held & 0xffffu);  // (all-run groups: nothing)
+        } else if (held == 0 && m == 0) {
+            sink.literal16(v);                 // the common case of the ordered (emitting) pass
+        }
+        if (held | m) {
+            // runs: walk the alternating segments of `held`
+            uint32_t pos = 0;
+            while (pos < 16) {
+                const uint32_t rest = held >> pos;
+                const uint32_t r = fz_run_len(rest, 16 - pos);
+                if (rest & 1u) {               // withheld bytes
+                    m += r;
+                    pos += r;
+                    if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
+                    if (pos < 16) {            // the run ends inside the group
+                        if (m >= FZ_MIN_MATCH) sink.match(m); else if (m) sink.literal(fz_byte_dyn(v, pos - 1), m);
+                        m = 0;
+                    }
+                } else {                       // ordinary bytes
+                    if (m) {                   // a run carried over from the previous group ends here (pos == 0)
+                        if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
+                        m = 0;
+                    }
+                    if (Sink::kOrdered)
+                        for (uint32_t k = pos; k < pos + r; k++) sink.literal(fz_byte_dyn(v, k), 1);
+                    pos += r;
+                }
+            }
+        }
+        // repeats at the end of the group: trailing ones of the flag word, saturated
+        const uint32_t inv = ~(ext >> FZ_HOLD_AFTER) & 0xffffu;        // zero flag = run break
+        const uint32_t t = inv ? (uint32_t)(15 - fz_ilog2(inv)) : 16u + rep;  // flags set after the last break
+        rep = t > FZ_HOLD_AFTER ? FZ_HOLD_AFTER : t;
+        prev = p;
+    }
+
+    // one byte (ragged tails)
+    template <class Sink>
+    FZ_HD void byte(int c, Sink &sink)
+    {
+        const bool e = c == prev;
+        if (e && rep >= FZ_HOLD_AFTER) {
+            if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
+        } else {
+            if (m) {
+                if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
+                m = 0;
+            }
+            rep = e ? rep + 1 : 0;
+            prev = c;
+            sink.literal((uint32_t)c, 1);
+        }
+    }
+
+    // end of the piece: what is still withheld leaves
+    template <class Sink>
+    FZ_HD void finish(Sink &sink)
+    {
+        if (m) {
+            if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
+            m = 0;
+        }
+    }
+};
+
 template <class Load16, class LoadByte, class Sink>
 FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
 {
-    int prev = prev_init;
-    uint32_t rep = 0;  // repeats of `prev` seen so far in this run (saturates at FZ_HOLD_AFTER)
-    uint32_t m = 0;    // withheld bytes
+    FzScan sc;
+    sc.init(prev_init);
     for (uint32_t i = begin; i < end; i += 16) {
         const uint32_t lim = end - i;
-        if (lim >= 16) {
-            // Whole 16-byte group at once.  Bit k+H of eq = byte k equals its predecessor (H = FZ_HOLD_AFTER); the
-            // H bits below stand for the bytes before the group (from `rep`).  Byte k is withheld iff the
-            // H+1 flags ending at k are all set.
-            const FzVec16 v = ld(i);
-            // four bytes per step: XOR each word with itself shifted up one byte (the predecessor of byte 0 comes from
-            // the word before), find the zero bytes exactly, gather their flags with one multiply
-            uint32_t eq = 0;
-            uint32_t before = (uint32_t)prev << 24;   // prev = -1 (no predecessor) gives 0xFF...: compared as 0xFF, fixed below
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t w = v.w[j];
-                const uint32_t x = w ^ ((w << 8) | (before >> 24));
-                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
-                eq |= ((z * 0x00204081u) >> 28) << (4 * j + FZ_HOLD_AFTER);
-                before = w;
-            }
-            if (prev < 0) eq &= ~(1u << FZ_HOLD_AFTER);   // the first byte of a piece has no predecessor
-            const int p = (int)(v.w[3] >> 24);
-            const uint32_t hist_bits = ((1u << rep) - 1u) << (FZ_HOLD_AFTER - rep);  // the last `rep` flags before the group
-            const uint32_t ext = eq | hist_bits;
-            uint32_t held = ext;
-#pragma unroll
-            for (int j = 1; j <= FZ_HOLD_AFTER; j++) held &= ext << j;
-            held >>= FZ_HOLD_AFTER;  // 16 bits: byte k of the group is withheld
-            if (!Sink::kOrdered) {
-                // token order is irrelevant (histogram, bit count): every byte that is not withheld is a literal,
-                // all lanes run the same code whatever their data; runs are book-kept below (rare)
-                // (when no lane of the warp withholds anything the unpredicated form is a little cheaper)
-                if (FZ_WARP_ALL(held == 0)) sink.literal16(v);
-                else if (!FZ_WARP_ALL(held == 0xffffu)) sink.literal_masked(v, ~held & 0xffffu);  // (all-run groups: nothing)
-            } else if (held == 0 && m == 0) {
-                sink.literal16(v);                 // the common case of the ordered (emitting) pass
-            }
-            if (held | m) {
-                // runs: walk the alternating segments of `held`
-                uint32_t pos = 0;
-                while (pos < 16) {
-                    const uint32_t rest = held >> pos;
-                    const uint32_t r = fz_run_len(rest, 16 - pos);
-                    if (rest & 1u) {               // withheld bytes
-                        m += r;
-                        pos += r;
-                        if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
-                        if (pos < 16) {            // the run ends inside the group
-                            if (m >= FZ_MIN_MATCH) sink.match(m); else if (m) sink.literal(fz_byte_dyn(v, pos - 1), m);
-                            m = 0;
-                        }
-                    } else {                       // ordinary bytes
-                        if (m) {                   // a run carried over from the previous group ends here (pos == 0)
-                            if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-                            m = 0;
-                        }
-                        if (Sink::kOrdered)
-                            for (uint32_t k = pos; k < pos + r; k++) sink.literal(fz_byte_dyn(v, k), 1);
-                        pos += r;
-                    }
-                }
-            }
-            // repeats at the end of the group: trailing ones of the flag word, saturated
-            const uint32_t inv = ~(ext >> FZ_HOLD_AFTER) & 0xffffu;        // zero flag = run break
-            const uint32_t t = inv ? (uint32_t)(15 - fz_ilog2(inv)) : 16u + rep;  // flags set after the last break
-            rep = t > FZ_HOLD_AFTER ? FZ_HOLD_AFTER : t;
-            prev = p;
-            continue;
-        }
-        // ragged tail (< 16 bytes): byte by byte
-        for (uint32_t k = 0; k < lim; k++) {
-            const int c = (int)lb(i + k);
-            const bool e = c == prev;
-            if (e && rep >= FZ_HOLD_AFTER) {
-                if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
-            } else {
-                if (m) {
-                    if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-                    m = 0;
-                }
-                rep = e ? rep + 1 : 0;
-                prev = c;
-                sink.literal((uint32_t)c, 1);
-            }
-        }
+        if (lim >= 16) { sc.group16(ld(i), sink); continue; }
+        for (uint32_t k = 0; k < lim; k++) sc.byte((int)lb(i + k), sink);   // ragged tail (< 16 bytes): byte by byte
     }
-    if (m) {
-        if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-    }
+    sc.finish(sink);
 }
+
+// A "piece scan" feeds this lane's piece of a sub-block through the tokeniser into a sink: scan(sink, lane).
+// Generic form: lane l owns bytes [l*P, min(n, (l+1)*P)) behind random-access loaders.  (The device's fast path
+// streams the pieces through a small shared-memory window instead: FzWindowScan in fz_kernels.cu.)
+FZ_HD uint32_t fz_piece_len(uint32_t n);
+template <class Load16, class LoadByte>
+struct FzPieceScan {
+    const Load16 &ld;
+    const LoadByte &lb;
+    uint32_t n;
+    template <class Sink>
+    FZ_HD void operator()(Sink &sink, int lane) const
+    {
+        const uint32_t P = fz_piece_len(n);
+        uint32_t b = lane * P, e = b + P;
+        if (e > n) e = n;
+        if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
+    }
+};
 
 FZ_HD void fz_atomic_add(uint32_t *p, uint32_t v)
 {
@@ -604,15 +643,16 @@ FZ_HD void fz_ph_cost_partial(FzEncState *st, int lane)
 FZ_HD uint32_t fz_piece_len(uint32_t n) { return (((n + 31) / 32) + 15) & ~15u; }
 
 // histogram of one sub-block's tokens into hist[288] (must be zeroed; one warp's shared memory)
+template <class Scan>
+FZ_HD void fz_ph_hist_sc(uint32_t *hist, const Scan &scan, int lane)
+{
+    FzHistSink sink{hist};
+    scan(sink, lane);
+}
 template <class Load16, class LoadByte>
 FZ_HD void fz_ph_hist(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
 {
-    const uint32_t P = fz_piece_len(n);
-    uint32_t b = lane * P, e = b + P;
-    if (e > n) e = n;
-    if (b >= e) return;
-    FzHistSink sink{hist};
-    fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
+    fz_ph_hist_sc(hist, FzPieceScan<Load16, LoadByte>{ld, lb, n}, lane);
 }
 
 // The code of a group as the emit kernel consumes it (global memory, copied to shared memory per warp)
@@ -679,29 +719,22 @@ struct FzEmitState {
     uint32_t pad[2];
 };
 
-template <class Load16, class LoadByte>
-FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
+template <class Scan>
+FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Scan &scan, int lane)
 {
-    const uint32_t P = fz_piece_len(n);
-    uint32_t b = lane * P, e = b + P;
-    if (e > n) e = n;
     FzCountSink sink{gc->cl, 0};
-    if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
+    scan(sink, lane);
     if (lane == 0) sink.bits += gc->hdr_nbits;
     es->lane_bits[lane] = sink.bits;
 }
 
 // emit this lane's tokens at its bit offset; lane 0 prepends the block header, lane 31 appends
 // EOB + the empty stored block (000, pad to byte, 00 00 FF FF)
-template <class Load16, class LoadByte>
-FZ_HD void fz_ph_emit(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Load16 &ld, const LoadByte &lb,
-                      uint32_t n, uint32_t *out, int lane)
+template <class Scan>
+FZ_HD void fz_ph_emit(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Scan &scan, uint32_t *out, int lane)
 {
     uint32_t off = 0;
     for (int l = 0; l < lane; l++) off += es->lane_bits[l];
-    const uint32_t P = fz_piece_len(n);
-    uint32_t b = lane * P, e = b + P;
-    if (e > n) e = n;
     FzEmitSink sink;
     sink.cl = gc->cl;
     sink.bw.init(out, off);
@@ -710,7 +743,7 @@ FZ_HD void fz_ph_emit(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *e
         while (nb >= 32) { sink.bw.put(hdr[w++], 32); nb -= 32; }
         if (nb) sink.bw.put(hdr[w] & ((1u << nb) - 1), nb);
     }
-    if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
+    scan(sink, lane);
     if (lane == 31) {
         sink.bw.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
         sink.bw.put(0, 3);
@@ -766,23 +799,31 @@ FZ_HD void fz_ph_check_marker(FzEmitState *es, const uint32_t *out, uint32_t tot
 // On the device every lane of the warp calls this with its own `lane`; on the host `lane` is unused.
 // `out` needs room for FZ_SLOT_STRIDE bytes.
 // -------------------------------------------------------------------------------------------------
-template <class Load16, class LoadByte>
 // `gc` needs only the hot part of FzGroupCode (FZ_GROUP_CODE_HOT_BYTES); `hdr` points at the group's header words.
-FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Load16 &ld,
-                                const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
+// `scan` is the piece scan of the sub-block (it runs twice: size, then emission).
+template <class Scan>
+FZ_HD uint32_t fz_emit_subblock_sc(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Scan &scan, uint32_t n,
+                                   uint32_t *out, int lane)
 {
     (void)lane;
     const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
     if (gc->stored) return stored;
-    FZ_PHASE(fz_ph_count(gc, es, ld, lb, n, lane));
+    FZ_PHASE(fz_ph_count(gc, es, scan, lane));
     uint32_t bits = gc->cl[FZ_EOB] >> 16;
     for (int l = 0; l < 32; l++) bits += es->lane_bits[l];
     // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
     const uint32_t dyn_bytes = (bits + 3 + 7) / 8 + 4;
     if (dyn_bytes >= fz_stored_size(n)) return stored;
-    FZ_PHASE(if (lane == 0) es->false_marker = 0; fz_ph_emit(gc, hdr, es, ld, lb, n, out, lane));
+    FZ_PHASE(if (lane == 0) es->false_marker = 0; fz_ph_emit(gc, hdr, es, scan, out, lane));
     FZ_PHASE(fz_ph_merge(es, out, lane));
     FZ_PHASE(fz_ph_check_marker(es, out, es->total_bits / 8, lane));
     if (es->false_marker) return stored;
     return es->total_bits / 8;
+}
+
+template <class Load16, class LoadByte>
+FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Load16 &ld,
+                                const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
+{
+    return fz_emit_subblock_sc(gc, hdr, es, FzPieceScan<Load16, LoadByte>{ld, lb, n}, n, out, lane);
 }

@@ -373,23 +373,98 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, co
 //   fz_emit_kernel        one warp per sub-block: exact size, stored-vs-dynamic decision, lane-parallel bit emission
 // =================================================================================================
 #define FZ_ENC_WARPS 4
-#define FZ_STAGE_BYTES (32 * (FZ_SUB / 32 + 16))
+// ---- how a warp reads its sub-block --------------------------------------------------------------------------
+// Lane l tokenises the contiguous piece [l*512, (l+1)*512) of the 16 KiB sub-block.  The pieces stream through a
+// two-stage shared-memory window of 64 bytes per lane: cp.async (16 B per lane and instruction, four per window,
+// arranged so that one instruction covers 8 pieces x 64 contiguous bytes = whole 32-byte sectors) fills stage
+// (w+1)&1 while the lanes tokenise window w out of stage w&1.  Rows are 80 bytes apart, which makes the per-lane
+// 128-bit reads bank-conflict free.  5 KB per warp instead of the 17 KB a fully staged sub-block took: 32 warps per
+// SM instead of 12, and no exposed load latency.
+#define FZ_WIN_BYTES 64
+#define FZ_WIN_ROW (FZ_WIN_BYTES + 16)
+#define FZ_WIN_STAGE (FZ_WARP * FZ_WIN_ROW)
+#define FZ_WIN_SMEM (2 * FZ_WIN_STAGE)
+#define FZ_PIECE (FZ_SUB / FZ_WARP)
 
-struct DevLoad16 {
-    const uint8_t *sm;
-    uint32_t adj;  // lane * 16: the padding in front of this lane's piece
+__device__ __forceinline__ void fz_cp_async16(uint32_t smem_addr, const void *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void fz_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fz_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// piece scan of a full, 16-byte aligned sub-block (all 32 lanes must call it: it synchronises the warp)
+struct FzWindowScan {
+    uint8_t *win;        // this warp's FZ_WIN_SMEM bytes
+    const uint8_t *src;  // FZ_SUB bytes
+    template <class Sink>
+    __device__ __forceinline__ void operator()(Sink &sink, int lane) const
+    {
+        const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
+        const uint32_t part = (uint32_t)lane & 3u, prow = (uint32_t)lane >> 2;
+        const uint8_t *gsrc = src + prow * FZ_PIECE + part * 16;
+        const uint32_t sdst = wbase + prow * FZ_WIN_ROW + part * 16;
+        // window w -> stage w & 1
+#define FZ_WIN_ISSUE(w)                                                                                              \
+        do {                                                                                                         \
+            const uint32_t st_ = sdst + ((w) & 1u) * FZ_WIN_STAGE;                                                   \
+            const uint8_t *g_ = gsrc + (w) * FZ_WIN_BYTES;                                                           \
+            _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++)                                                         \
+                fz_cp_async16(st_ + q_ * 8 * FZ_WIN_ROW, g_ + q_ * 8 * FZ_PIECE);                                    \
+            fz_cp_async_commit();                                                                                    \
+        } while (0)
+        FZ_WIN_ISSUE(0u);
+        FzScan sc;
+        sc.init(lane ? (int)src[lane * FZ_PIECE - 1] : -1);
+#pragma unroll 1
+        for (uint32_t w = 0; w < FZ_PIECE / FZ_WIN_BYTES; w++) {
+            if (w + 1 < FZ_PIECE / FZ_WIN_BYTES) { FZ_WIN_ISSUE(w + 1); fz_cp_async_wait<1>(); }
+            else fz_cp_async_wait<0>();
+            __syncwarp();
+            const uint8_t *row = win + (w & 1u) * FZ_WIN_STAGE + lane * FZ_WIN_ROW;
+#pragma unroll 1
+            for (uint32_t q = 0; q < FZ_WIN_BYTES / 16; q++) {
+                const uint4 v = *(const uint4 *)(row + q * 16);
+                FzVec16 r;
+                r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+                sc.group16(r, sink);
+            }
+            __syncwarp();   // everyone is done with this stage before window w + 2 lands in it
+        }
+#undef FZ_WIN_ISSUE
+        sc.finish(sink);
+    }
+};
+
+// ragged (last sub-block of a file) or unaligned (chunk sizes that are not a multiple of 16) sub-blocks: straight
+// from global memory, no staging -- rare, small, and not worth shared memory that would cost the fast path occupancy
+struct GlobLoad16 {
+    const uint8_t *src;
     __device__ __forceinline__ FzVec16 operator()(uint32_t i) const
     {
-        const uint4 v = *(const uint4 *)(sm + i + adj);
         FzVec16 r;
-        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        if (((uintptr_t)(src + i) & 15u) == 0) {
+            const uint4 v = *(const uint4 *)(src + i);
+            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                r.w[j] = (uint32_t)src[i + 4 * j] | ((uint32_t)src[i + 4 * j + 1] << 8) | ((uint32_t)src[i + 4 * j + 2] << 16) |
+                         ((uint32_t)src[i + 4 * j + 3] << 24);
+        }
         return r;
     }
 };
-struct DevLoadByte {
-    const uint8_t *sm;
-    uint32_t P;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return sm[i + (i / P) * 16]; }
+struct GlobLoadByte {
+    const uint8_t *src;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return src[i]; }
+};
+struct ZeroLoad16 {
+    __device__ __forceinline__ FzVec16 operator()(uint32_t) const { FzVec16 r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; return r; }
+};
+struct ZeroLoadByte {
+    __device__ __forceinline__ uint32_t operator()(uint32_t) const { return 0; }
 };
 
 __device__ __forceinline__ const uint8_t *fz_sub_src(const uint8_t *planes, const FzBatchGeom &g, uint32_t s, uint32_t k)
@@ -410,28 +485,13 @@ __device__ __forceinline__ bool fz_slot(const FzBatchGeom &g, uint32_t t, uint32
     return true;
 }
 
-// stage the sub-block in shared memory: lane l's piece [l*P, (l+1)*P) is stored at l*(P+16)
-// (bank-conflict-free 128-bit reads when every lane walks its own piece)
-__device__ __forceinline__ void fz_stage(uint8_t *stage, const uint8_t *src, uint32_t n, uint32_t P, int lane)
-{
-    if (((uintptr_t)src & 15u) == 0) {
-        for (uint32_t i = lane * 16; i < n; i += FZ_WARP * 16) {
-            const uint4 v = *(const uint4 *)(src + i);
-            *(uint4 *)(stage + i + (i / P) * 16) = v;
-        }
-    } else {
-        for (uint32_t i = lane; i < n; i += FZ_WARP) stage[i + (i / P) * 16] = src[i];
-    }
-    __syncwarp();
-}
-
 __device__ __forceinline__ uint32_t fz_groups_per_stream(const FzBatchGeom &g)
 {
     return (g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS;
 }
 
 struct __align__(16) FzHistSmem {
-    alignas(16) uint8_t stage[FZ_STAGE_BYTES];
+    alignas(16) uint8_t win[FZ_WIN_SMEM];
     uint32_t hist[288];
 };
 
@@ -452,7 +512,6 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
     uint32_t s, k, n;
     if (!fz_slot(g, t, s, k, n)) return;
     FzHistSmem *sm = (FzHistSmem *)fz_smem + warp;
-    const uint32_t P = fz_piece_len(n);
     const uint8_t *src = fz_sub_src(planes, g, s, k);
     for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
     __syncwarp();
@@ -504,10 +563,13 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
         __syncwarp();
     }
     if (lane == 0) sizes[t] = 0;  // to be decided by the emit kernel
-    fz_stage(sm->stage, src, n, P, lane);
-    DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
-    DevLoadByte lb{sm->stage, P};
-    fz_ph_hist(sm->hist, ld, lb, n, lane);
+    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
+        fz_ph_hist_sc(sm->hist, FzWindowScan{sm->win, src}, lane);
+    } else {
+        GlobLoad16 ld{src};
+        GlobLoadByte lb{src};
+        fz_ph_hist(sm->hist, ld, lb, n, lane);
+    }
     __syncwarp();
     uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
     for (int i = lane; i < 288; i += 32) {
@@ -524,11 +586,8 @@ fz_zero_hist_kernel(uint32_t *__restrict__ zero_hist)
     const int lane = threadIdx.x;
     FzHistSmem *sm = (FzHistSmem *)fz_smem;
     for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
-    for (uint32_t i = lane * 16; i < FZ_STAGE_BYTES; i += FZ_WARP * 16) *(uint4 *)(sm->stage + i) = make_uint4(0, 0, 0, 0);
     __syncwarp();
-    DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
-    DevLoadByte lb{sm->stage, fz_piece_len(FZ_SUB)};
-    fz_ph_hist(sm->hist, ld, lb, FZ_SUB, lane);
+    fz_ph_hist(sm->hist, ZeroLoad16{}, ZeroLoadByte{}, FZ_SUB, lane);
     __syncwarp();
     for (int i = lane; i < 288; i += 32) zero_hist[i] = sm->hist[i];
 }
@@ -556,7 +615,7 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
 }
 
 struct __align__(16) FzEmitSmem {
-    alignas(16) uint8_t stage[FZ_STAGE_BYTES];
+    alignas(16) uint8_t win[FZ_WIN_SMEM];
     uint32_t gc_hot[FZ_GROUP_CODE_HOT_BYTES / 4];  // the hot part of the group's FzGroupCode
     FzEmitState es;
 };
@@ -592,12 +651,17 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
         const uint32_t *src = (const uint32_t *)ggc;
         for (uint32_t i = lane; i < FZ_GROUP_CODE_HOT_BYTES / 4; i += 32) sm->gc_hot[i] = src[i];
     }
-    const uint32_t P = fz_piece_len(n);
-    fz_stage(sm->stage, fz_sub_src(planes, g, s, k), n, P, lane);
-    DevLoad16 ld{sm->stage, (uint32_t)lane * 16};
-    DevLoadByte lb{sm->stage, P};
+    __syncwarp();
+    const uint8_t *src = fz_sub_src(planes, g, s, k);
     uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
-    const uint32_t r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, ld, lb, n, out, lane);
+    uint32_t r;
+    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
+        r = fz_emit_subblock_sc((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, FzWindowScan{sm->win, src}, n, out, lane);
+    } else {
+        GlobLoad16 ld{src};
+        GlobLoadByte lb{src};
+        r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, ld, lb, n, out, lane);
+    }
     if (lane == 0) {
         sizes[t] = r | (sz0 & FZ_SIZE_ZERO_FLAG);
         if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
@@ -623,6 +687,8 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
     cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzHistSmem) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEmitSmem) * FZ_ENC_WARPS));
+    cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
     fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, zero_hist, status);
     fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
