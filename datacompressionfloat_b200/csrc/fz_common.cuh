@@ -30,7 +30,9 @@
 // stored block, followed by an empty stored block (`00 00 FF FF` after byte alignment, exactly zlib's
 // sync-flush marker).  The marker makes sub-blocks concatenate at byte granularity and is what the
 // GPU inflater searches for to decode a stream with one thread per sub-block.
+#ifndef FZ_SUB_LOG2
 #define FZ_SUB_LOG2 14
+#endif
 #define FZ_SUB (1u << FZ_SUB_LOG2)        // 16 KiB (8 KiB: +5 % speed at 4 GiB, 2x decode speed on small inputs, +0.5..1.5 % size)
 #define FZ_SLOT_STRIDE (FZ_SUB + 32u)     // scratch bytes reserved per encoded sub-block
 #define FZ_GROUP_SUBS 32u                 // sub-blocks that share one Huffman code (= one warp of the inflater)

@@ -89,6 +89,9 @@ struct FzByteWriter {
     FZ_HD uint32_t produced() const { return op - op0; }
     FZ_HD void store_word(uint32_t widx_bytes, uint32_t w)  // the word starting at byte offset widx_bytes is complete
     {
+#ifdef FZ_EXP_NOSTORE
+        if (w != 0x9e3779b9u) return;
+#endif
         if (widx_bytes == 0 && op0) { for (uint32_t i = op0; i < 4; i++) out[i] = (uint8_t)(w >> (8 * i)); }
         else *(uint32_t *)(out + widx_bytes) = w;
     }
@@ -175,7 +178,9 @@ struct FzByteWriter {
 //   bits  9..16  sym2          : second literal, bits 17..24 sym3: third literal (when count says so)
 //   bits 25..28  total length  : code bits consumed by the `count` symbols of this entry
 //   bits 29..30  count         : 1..3 symbols; entries with count > 1 hold literals only
+#ifndef FZ_LUT_BITS
 #define FZ_LUT_BITS 11
+#endif
 #define FZ_LUT_SIZE (1 << FZ_LUT_BITS)
 #define FZ_LUT_MATCH (1u << 24)   // entry of a length symbol: bits 9..17 base length, bits 18..20 extra bit count
 #define FZ_LUT_ENTRY(s1, s2, s3, total, cnt) \

@@ -1153,22 +1153,32 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 // own fragment with it.  Lanes verify that their header bits equal the leader's; any mismatch, parse error
 // or size mismatch flags the stream, which is then re-decoded by the general inflater.
 #define FZ_INF_WARPS 4
-#define FZ_INF_CARVEOUT_PCT 72     // of 228 KB: 164 KB shared memory, 92 KB L1
+#ifndef FZ_INF_CARVEOUT_PCT
+#define FZ_INF_CARVEOUT_PCT 100    // all of the 228 KB as shared memory: 4 CTAs x 54 KB
+#endif
+#ifndef FZ_INF_MINBLOCKS
+#define FZ_INF_MINBLOCKS 1
+#endif
 #define FZ_ZERO_PROBE_BYTES 96u   // 16 KiB of zeros is ~70 bytes of run codes
+#define FZ_RING_CHUNKS 8u                        // 16-byte chunks of input per lane
+#define FZ_RING_ROW_WORDS (FZ_RING_CHUNKS * 4u + 4u)  // row pitch in words (16 bytes of padding)
+#define FZ_FAST_ITERS 16
 struct FzGroupSmem {
+    alignas(16) uint32_t ring[FZ_WARP * FZ_RING_ROW_WORDS];  // every lane's window on its fragment (cp.async)
     uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
     uint32_t lut[FZ_LUT_SIZE];
     FzCode LL, DD;                 // the group's codes (long codes and distances; the LUT covers the rest)
 };
 
-__global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP)
+__global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP, FZ_INF_MINBLOCKS)
 fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
                         const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ tile_off,
                         uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
                         uint32_t *__restrict__ stream_fail, uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes,
                         const FzStatus *status)
 {
-    __shared__ FzGroupSmem smem[FZ_INF_WARPS];
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    FzGroupSmem *smem = (FzGroupSmem *)fz_smem;
     if (status->error) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t gps = fz_groups_per_stream(g);
@@ -1248,6 +1258,34 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
         }
         __syncwarp();
     }
+    // Stored sub-blocks (incompressible bytes: two stored blocks and the empty one) are copied by the whole warp, 16
+    // bytes per lane and step; left to their lane they would be a word-by-word loop that the 31 others wait for.
+    // Anything but exactly that layout stays with its lane and the general code.
+    bool done_stored = false;
+    {
+        uint32_t stored_mask = __ballot_sync(0xffffffffu, valid && first3 == 0u);
+        while (stored_mask) {
+            const int j = __ffs((int)stored_mask) - 1;
+            stored_mask &= stored_mask - 1;
+            const uint8_t *f = (const uint8_t *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)frag, j);
+            uint8_t *o = (uint8_t *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)out, j);
+            const uint32_t fl = __shfl_sync(0xffffffffu, flen, j), ex = __shfl_sync(0xffffffffu, expect, j);
+            uint32_t pos = 0, prod = 0;
+            bool ok = false;
+            for (int blk = 0; blk < 4; blk++) {   // warp-uniform: every lane reads the same header bytes
+                if (pos + 5 > fl) break;
+                const uint32_t b0 = f[pos], len = (uint32_t)f[pos + 1] | ((uint32_t)f[pos + 2] << 8);
+                const uint32_t nlen = (uint32_t)f[pos + 3] | ((uint32_t)f[pos + 4] << 8);
+                if ((b0 & 7u) != 0u || (len ^ 0xffffu) != nlen) break;      // BFINAL = 0, BTYPE = 00, LEN = ~NLEN
+                if (len == 0) { ok = pos + 5 == fl && prod == ex; break; }   // the empty block must close the fragment
+                if (prod + len > ex || pos + 5 + len > fl) break;
+                fz_warp_copy(o + prod, f + pos + 5, len, f + fl, lane);
+                pos += 5 + len;
+                prod += len;
+            }
+            if (lane == j && ok) { live = false; done_stored = true; }
+        }
+    }
     // lock-step drive: lanes reconverge after every symbol
     const uint32_t *lut = coded_mask ? sm->lut : nullptr;
     const uint32_t run_bit = fz_dd1_run_bit(inf.dd1);
@@ -1279,36 +1317,132 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
         }
         if (valid) zero_flags[(size_t)s * g.nsub_full + k] = all_zero ? 1u : 0u;
     }
-    while (__any_sync(0xffffffffu, live)) {
-        if (live) {
-            if (inf.in_body && lut) {
-                // fast run: up to 16 table hits (1-3 literals each) without leaving registers or re-voting
+    // ---- fast rounds.  The lane reads its fragment through a ring of FZ_RING_CHUNKS 16-byte chunks in shared memory
+    // that cp.async tops up once per round (<= 3 chunks; a round takes at most 16 x 17 bits), two rounds ahead of
+    // the decoder: `cp.async.wait_group 1` leaves only the newest top-up in flight, and what a round can reach was
+    // asked for at least two top-ups ago.  The bit buffer is refilled from the ring by predicated code -- no branch,
+    // no global load in the loop.  A lane leaves the fast rounds at the first thing that is not a table hit, a long
+    // literal or a run (end of block, errors, end of the output) and hands its position to the general inflater.
+    {
+        bool fast = live && coded && lut != nullptr && inf.in_body;
+        const uint32_t mis = (uint32_t)((uintptr_t)frag & 15u);
+        const uint8_t *gbase = frag - mis;                               // chunk 0
+        const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
+        uint32_t *row = sm->ring + lane * FZ_RING_ROW_WORDS;
+        const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(row);
+        uint64_t acc = 0;
+        uint32_t nxt = 0, rp = 0, fetched = 0;
+        int nacc = 0;
+        if (fast) {
+            const uint32_t abs_bit = mis * 8u + (uint32_t)((int64_t)flen * 8 - inf.br.bits_left());
+            rp = abs_bit >> 5;
+            fetched = rp >> 2;
+#pragma unroll
+            for (uint32_t q = 0; q < FZ_RING_CHUNKS; q++) {
+                if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
+                fetched++;
+            }
+        }
+        fz_cp_async_commit();
+        fz_cp_async_wait<0>();
+        if (fast) {
+            const uint32_t abs_bit = mis * 8u + (uint32_t)((int64_t)flen * 8 - inf.br.bits_left());
+            acc = (uint64_t)(row[rp & (FZ_RING_CHUNKS * 4 - 1)] >> (abs_bit & 31u));
+            nacc = 32 - (int)(abs_bit & 31u);
+            rp++;
+            nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
+        }
+        while (__any_sync(0xffffffffu, live)) {
+            if (fast) {
+                // chunks below this one are used up -- keeping the two words the bit buffer may still hold bits of:
+                // after a symbol taken by the general inflater the lane re-reads its buffer from the ring
+                const uint32_t cons = (rp >= 2u ? rp - 2u : 0u) >> 2;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    if (fetched < cons + FZ_RING_CHUNKS) {
+                        if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
+                        fetched++;
+                    }
+                }
+            }
+            fz_cp_async_commit();
+            fz_cp_async_wait<1>();
+            if (live && !fast) live = inf.step_lut(lut);   // end of block, the closing stored block, odd layouts
+            else if (live) {
+                int it = 0;
 #pragma unroll 1
-                for (int it = 0; it < 16; ++it) {
-                    inf.br.refill();
-                    const uint32_t e = lut[(uint32_t)inf.br.acc & (FZ_LUT_SIZE - 1)];
+                for (; it < FZ_FAST_ITERS; ++it) {
+                    if (nacc < 32) {
+                        acc |= (uint64_t)nxt << nacc;
+                        nacc += 32;
+                        rp++;
+                        nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
+                    }
+                    const uint32_t e = lut[(uint32_t)acc & (FZ_LUT_SIZE - 1)];
                     const uint32_t cnt = e >> 29;
                     if ((e & 511u) >= 256u) {
                         // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
                         if (!(e & FZ_LUT_MATCH) || run_bit > 1u) break;
                         const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
-                        const uint32_t a = (uint32_t)(inf.br.acc >> cl);
+                        const uint32_t a = (uint32_t)(acc >> cl);
                         const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
                         if (((a >> xb) & 1u) != run_bit || inf.bw.op + len > inf.bw.cap || inf.bw.produced() == 0) break;
-                        inf.br.drop((int)(cl + xb + 1u));
+                        acc >>= (cl + xb + 1u);
+                        nacc -= (int)(cl + xb + 1u);
                         inf.bw.fill(inf.bw.back(1), len);
                         continue;
                     }
-                    if (e == 0 || inf.bw.op + cnt > inf.bw.cap) break;
-                    inf.br.drop((int)((e >> 25) & 15u));
+                    if (e == 0) {
+                        // a code longer than the table's index: canonical search; literals stay in the loop
+                        uint32_t idx;
+                        const int l = fz_decode_idx(sm->LL, (uint32_t)acc & 0x7fffu, idx);
+                        if (l == 0 || idx >= 288u) break;
+                        const uint32_t sym = tab.L((int)idx);
+                        if (sym >= 256u || inf.bw.op >= inf.bw.cap) break;
+                        acc >>= l;
+                        nacc -= l;
+                        inf.bw.put(sym);
+                        continue;
+                    }
+                    if (inf.bw.op + cnt > inf.bw.cap) break;
+                    const int tl = (int)((e >> 25) & 15u);
+                    acc >>= tl;
+                    nacc -= tl;
                     // sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that count)
                     inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
                 }
+                if (it < FZ_FAST_ITERS) {
+                    // something else (a long length code, end of block, end of the output, an error): the general
+                    // inflater takes this one symbol at the lane's bit position, then the ring reader resumes behind it
+                    const int64_t rel = (int64_t)rp * 32 - nacc - (int64_t)mis * 8;
+                    if (rel < 0 || rel > (int64_t)flen * 8) { bad = true; live = false; fast = false; }
+                    else {
+                        const uint32_t nby = (uint32_t)(rel >> 3);
+                        inf.br.init(frag + nby, flen - nby);
+                        inf.br.refill();
+                        inf.br.drop((int)(rel & 7));
+                        live = inf.step_lut(lut);
+                        fast = false;
+                        if (live && inf.in_body) {
+                            const int64_t left = inf.br.bits_left();
+                            const uint32_t abs_bit = mis * 8u + (uint32_t)((int64_t)flen * 8 - left);
+                            const uint32_t r0 = abs_bit >> 5;
+                            // (one symbol is at most 48 bits: still inside what the ring holds)
+                            if (left >= 0 && ((r0 + 2) >> 2) < fetched && (r0 >> 2) + FZ_RING_CHUNKS >= fetched) {
+                                fast = true;
+                                rp = r0;
+                                acc = (uint64_t)(row[rp & (FZ_RING_CHUNKS * 4 - 1)] >> (abs_bit & 31u));
+                                nacc = 32 - (int)(abs_bit & 31u);
+                                rp++;
+                                nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
+                            }
+                        }
+                    }
+                }
             }
-            live = inf.step_lut(lut);  // whatever comes next: long code, match, end of block, block header
         }
     }
-    if (valid && !all_zero) {
+    if (valid && !all_zero && !done_stored) {
         uint32_t out_n = 0;
         size_t used = 0;
         const int rc = inf.finish(&out_n, &used);
@@ -1683,7 +1817,8 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     // word is an L2 round trip.  164 KB of shared memory (4 CTAs of 37 KB) and 92 KB of L1 beat 228 KB / 6 CTAs by
     // 20-25 % on every input measured (sweep in profiles/README.md).
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FZ_INF_CARVEOUT_PCT);
-    fz_inflate_group_kernel<<<(ngroups + FZ_INF_WARPS - 1) / FZ_INF_WARPS, FZ_INF_WARPS * FZ_WARP, 0, st>>>(
+    cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzGroupSmem) * FZ_INF_WARPS));
+    fz_inflate_group_kernel<<<(ngroups + FZ_INF_WARPS - 1) / FZ_INF_WARPS, FZ_INF_WARPS * FZ_WARP, sizeof(FzGroupSmem) * FZ_INF_WARPS, st>>>(
         container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
