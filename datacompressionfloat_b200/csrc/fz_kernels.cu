@@ -1324,7 +1324,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     // no global load in the loop.  A lane leaves the fast rounds at the first thing that is not a table hit, a long
     // literal or a run (end of block, errors, end of the output) and hands its position to the general inflater.
     {
-        bool fast = live && coded && lut != nullptr && inf.in_body;
+        bool fast = live && coded && lut != nullptr && inf.in_body && inf.bw.op0 == 0;
         const uint32_t mis = (uint32_t)((uintptr_t)frag & 15u);
         const uint8_t *gbase = frag - mis;                               // chunk 0
         const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
@@ -1369,49 +1369,59 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
             fz_cp_async_wait<1>();
             if (live && !fast) live = inf.step_lut(lut);   // end of block, the closing stored block, odd layouts
             else if (live) {
-                int it = 0;
+                // literals never overrun the output inside a round: it is cut to what fits (3 bytes per iteration)
+                const uint32_t room = inf.bw.cap - inf.bw.op;
+                const int iters = room >= 3u * FZ_FAST_ITERS ? FZ_FAST_ITERS : (int)(room / 3u);
+                bool slow = iters == 0;
 #pragma unroll 1
-                for (; it < FZ_FAST_ITERS; ++it) {
-                    if (nacc < 32) {
-                        acc |= (uint64_t)nxt << nacc;
-                        nacc += 32;
-                        rp++;
-                        nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
-                    }
+                for (int it = 0; it < iters; ++it) {
+                    // refill without a branch: ORing the next word in early is harmless (its bits land where they
+                    // belong and are ORed there again once they count), and `nxt` is re-read every iteration
+                    acc |= (uint64_t)nxt << nacc;
+                    const bool need = nacc < 32;
+                    nacc += need ? 32 : 0;
+                    rp += need ? 1u : 0u;
+                    nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
                     const uint32_t e = lut[(uint32_t)acc & (FZ_LUT_SIZE - 1)];
-                    const uint32_t cnt = e >> 29;
-                    if ((e & 511u) >= 256u) {
+                    if (e & 0x100u) {
                         // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
-                        if (!(e & FZ_LUT_MATCH) || run_bit > 1u) break;
+                        if (!(e & FZ_LUT_MATCH) || run_bit > 1u) { slow = true; break; }
                         const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
                         const uint32_t a = (uint32_t)(acc >> cl);
                         const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
-                        if (((a >> xb) & 1u) != run_bit || inf.bw.op + len > inf.bw.cap || inf.bw.produced() == 0) break;
+                        if (((a >> xb) & 1u) != run_bit || inf.bw.op + len > inf.bw.cap || inf.bw.produced() == 0) { slow = true; break; }
                         acc >>= (cl + xb + 1u);
                         nacc -= (int)(cl + xb + 1u);
                         inf.bw.fill(inf.bw.back(1), len);
+                        if (inf.bw.cap - inf.bw.op < 3u * (uint32_t)(iters - it)) break;   // the round's budget is gone
                         continue;
                     }
                     if (e == 0) {
                         // a code longer than the table's index: canonical search; literals stay in the loop
                         uint32_t idx;
                         const int l = fz_decode_idx(sm->LL, (uint32_t)acc & 0x7fffu, idx);
-                        if (l == 0 || idx >= 288u) break;
+                        if (l == 0 || idx >= 288u) { slow = true; break; }
                         const uint32_t sym = tab.L((int)idx);
-                        if (sym >= 256u || inf.bw.op >= inf.bw.cap) break;
+                        if (sym >= 256u) { slow = true; break; }
                         acc >>= l;
                         nacc -= l;
                         inf.bw.put(sym);
                         continue;
                     }
-                    if (inf.bw.op + cnt > inf.bw.cap) break;
-                    const int tl = (int)((e >> 25) & 15u);
+                    // 1..3 literals: sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that
+                    // count) appended to the pending word; a completed word is stored (op0 == 0 on this path)
+                    const uint32_t cnt = e >> 29, tl = (e >> 25) & 15u;
+                    const uint32_t v = (e & 255u) | ((e >> 1) & 0xffff00u);
+                    const uint32_t sh = (inf.bw.op & 3u) * 8u;
+                    const uint64_t t = (uint64_t)inf.bw.ow | ((uint64_t)v << sh);
+                    inf.bw.op += cnt;
+                    const bool full = sh + cnt * 8u >= 32u;
+                    if (full) *(uint32_t *)(inf.bw.out + ((inf.bw.op & ~3u) - 4u)) = (uint32_t)t;
+                    inf.bw.ow = full ? (uint32_t)(t >> 32) : (uint32_t)t;
                     acc >>= tl;
-                    nacc -= tl;
-                    // sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that count)
-                    inf.bw.putn((e & 255u) | ((e >> 1) & 0xffff00u), cnt);
+                    nacc -= (int)tl;
                 }
-                if (it < FZ_FAST_ITERS) {
+                if (slow) {
                     // something else (a long length code, end of block, end of the output, an error): the general
                     // inflater takes this one symbol at the lane's bit position, then the ring reader resumes behind it
                     const int64_t rel = (int64_t)rp * 32 - nacc - (int64_t)mis * 8;
