@@ -41,6 +41,12 @@
 // marker scan (see fz_stored_split).  One-byte sub-blocks use a single stored block.
 #define FZ_STORED_OVERHEAD 15u
 #define FZ_MARKER_LE 0xFFFF0000u          // bytes 00 00 FF FF read as a little-endian uint32
+// A sub-block (and a group) is coded only if that saves at least 1 / 2^FZ_MIN_GAIN_SHIFT of its bytes (3 %): nearly
+// incompressible bytes decode at one symbol per table lookup, a third of the speed of ordinary planes and a tenth of a
+// stored block's copy, for a gain nobody would miss.
+#ifndef FZ_MIN_GAIN_SHIFT
+#define FZ_MIN_GAIN_SHIFT 5
+#endif
 #define FZ_SIZE_STORED_FLAG 0x80000000u   // in the per-sub-block size word: emit as stored block
 #define FZ_SIZE_ZERO_FLAG 0x40000000u     // the sub-block is 16 KiB of zero bytes (found by the histogram kernel)
 #define FZ_SIZE_COPY_FLAG 0x20000000u     // its fragment is byte-identical to the one of sub-block (bits 24..28) of its group

@@ -697,7 +697,7 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
     uint64_t bits = (uint64_t)nsub * (st->hdr_nbits + 3 + 4 + 32);  // header + empty stored block (avg pad 4) per sub-block
     for (int l = 0; l < 32; l++) bits += ((uint64_t)st->lane_bits[l] << 32) | st->lane_cnt[l];
     const uint64_t stored_bits = 8ull * ((uint64_t)group_bytes + (uint64_t)FZ_STORED_OVERHEAD * nsub);
-    const uint32_t stored = bits >= stored_bits ? 1u : 0u;
+    const uint32_t stored = bits + (stored_bits >> FZ_MIN_GAIN_SHIFT) >= stored_bits ? 1u : 0u;
 #if defined(__CUDA_ARCH__)
     for (int i = lane; i < 288; i += 32) out->cl[i] = (uint32_t)st->code[i] | ((uint32_t)st->len[i] << 16);
     for (int i = lane; i < 160; i += 32) out->hdr[i] = st->hdr[i];
@@ -813,7 +813,7 @@ FZ_HD uint32_t fz_emit_subblock_sc(const FzGroupCode *gc, const uint32_t *hdr, F
     for (int l = 0; l < 32; l++) bits += es->lane_bits[l];
     // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
     const uint32_t dyn_bytes = (bits + 3 + 7) / 8 + 4;
-    if (dyn_bytes >= fz_stored_size(n)) return stored;
+    if (dyn_bytes + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
     FZ_PHASE(if (lane == 0) es->false_marker = 0; fz_ph_emit(gc, hdr, es, scan, out, lane));
     FZ_PHASE(fz_ph_merge(es, out, lane));
     FZ_PHASE(fz_ph_check_marker(es, out, es->total_bits / 8, lane));

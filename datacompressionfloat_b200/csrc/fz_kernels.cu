@@ -499,7 +499,9 @@ struct __align__(16) FzHistSmem {
 // bytes of every lane piece) decides that before the 16 KiB are even read.  The plug-in entropy of 2048
 // samples of uniform bytes is about 7.91 bits (bias -255 / (2 N ln 2)); anything above FZ_SAMPLE_BITS is
 // emitted as a stored block (and, if the whole stream ends up like that, the stream becomes RAW).
+#ifndef FZ_SAMPLE_BITS
 #define FZ_SAMPLE_BITS 7.85f
+#endif
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
 fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist, uint32_t *__restrict__ sizes,
