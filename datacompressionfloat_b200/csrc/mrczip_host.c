@@ -5,18 +5,29 @@
  * container primitives (src/core/common.c:26-149, src/core/zip.c:381-399), and calls CUDA only
  * through the mzb_* C ABI (fz_api.cu).  Nothing here compresses or inflates on the CPU.
  */
+#define _FILE_OFFSET_BITS 64
+#define _GNU_SOURCE
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <sys/time.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "../../include/mrczip_b200.h"
 
 int isTestThroughput = 0; /* reference workers.c:39 */
 
 /* chunks handed to the GPU per call from the FILE* API (bounds pinned + device memory per thread) */
-#define HOST_BATCH_CHUNKS 32
+#define HOST_BATCH_CHUNKS 16
+/* file I/O of the FILE* API: batches are read / written by IO_THREADS threads with pread / pwrite (a single
+ * thread copies page cache <-> pinned memory at a few GB/s, an order of magnitude below what the GPU path takes),
+ * and the read of batch b+1 and the write of batch b-1 overlap the GPU work on batch b (two buffers each way).
+ * Streams that cannot seek (pipes) take the plain fread / fwrite loop. */
+#define IO_THREADS 16 /* upper bound; MRCZIP_IO_THREADS (default 4) says how many are used */
+#define IO_SLICE_MIN ((size_t)8 << 20)
 
 /* ------------------------------------------------------------------ common.c equivalents */
 
@@ -135,10 +146,14 @@ static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 
 typedef struct {
     mzb_ctx *ctx;
-    void *pin_in;
+    void *pin_in;        /* [0] of the input double buffer (the only one the fread / fwrite loop uses) */
     size_t pin_in_cap;
     void *pin_out;
     size_t pin_out_cap;
+    void *pin_in2;       /* [1]: allocated on the first overlapped call */
+    size_t pin_in2_cap;
+    void *pin_out2;
+    size_t pin_out2_cap;
 } thread_state_t;
 
 static void thread_state_free(void *p)
@@ -147,6 +162,8 @@ static void thread_state_free(void *p)
     if (!ts) return;
     mzb_host_free(ts->pin_in);
     mzb_host_free(ts->pin_out);
+    mzb_host_free(ts->pin_in2);
+    mzb_host_free(ts->pin_out2);
     mzb_destroy(ts->ctx);
     free(ts);
 }
@@ -225,6 +242,261 @@ static void print_result_like(const plane_acct_t *a, double seconds, int is_zip,
     }
 }
 
+/* ------------------------------------------------------------------ overlapped, multi-threaded file I/O */
+
+typedef struct {
+    int fd, wr;
+    unsigned char *buf;
+    size_t n, done;
+    off_t off;
+} io_slice_t;
+
+static void *io_slice_run(void *p)
+{
+    io_slice_t *s = (io_slice_t *)p;
+    while (s->done < s->n) {
+        const ssize_t r = s->wr ? pwrite(s->fd, s->buf + s->done, s->n - s->done, s->off + (off_t)s->done)
+                                : pread(s->fd, s->buf + s->done, s->n - s->done, s->off + (off_t)s->done);
+        if (r <= 0) break; /* end of file (read) or an error: the caller sees a short count */
+        s->done += (size_t)r;
+    }
+    return NULL;
+}
+
+/* n bytes at file offset off, split over up to IO_THREADS threads; returns the contiguous byte count done */
+static size_t io_parallel(int fd, int wr, void *buf, size_t n, off_t off)
+{
+    io_slice_t sl[IO_THREADS];
+    pthread_t th[IO_THREADS];
+    static int want = 0;
+    if (want == 0) {
+        const char *e = getenv("MRCZIP_IO_THREADS");
+        int w = e ? atoi(e) : 4;
+        want = w < 1 ? 1 : (w > IO_THREADS ? IO_THREADS : w);
+    }
+    int k = (int)(n / IO_SLICE_MIN);
+    if (k < 1) k = 1;
+    if (k > want) k = want;
+    const size_t per = ((n + (size_t)k - 1) / (size_t)k + 4095) & ~(size_t)4095;
+    int started = 0;
+    for (int i = 0; i < k; i++) {
+        const size_t b = (size_t)i * per;
+        sl[i].fd = fd; sl[i].wr = wr; sl[i].done = 0;
+        sl[i].buf = (unsigned char *)buf + (b < n ? b : n);
+        sl[i].n = b < n ? (n - b < per ? n - b : per) : 0;
+        sl[i].off = off + (off_t)b;
+        if (i + 1 < k && pthread_create(&th[i], NULL, io_slice_run, &sl[i]) == 0) started |= 1 << i;
+        else io_slice_run(&sl[i]);
+    }
+    size_t total = 0;
+    int whole = 1;
+    for (int i = 0; i < k; i++) {
+        if (started & (1 << i)) pthread_join(th[i], NULL);
+        if (whole) total += sl[i].done;
+        if (sl[i].done < sl[i].n) whole = 0;
+    }
+    return total;
+}
+
+/* one background transfer (a batch read ahead, or a batch written behind) */
+typedef struct {
+    pthread_t th;
+    int active;
+    int fd, wr;
+    void *buf;
+    size_t n, done;
+    off_t off;
+} io_job_t;
+
+static void *io_job_run(void *p)
+{
+    io_job_t *j = (io_job_t *)p;
+    j->done = io_parallel(j->fd, j->wr, j->buf, j->n, j->off);
+    return NULL;
+}
+
+static void io_job_start(io_job_t *j, int fd, int wr, void *buf, size_t n, off_t off)
+{
+    j->fd = fd; j->wr = wr; j->buf = buf; j->n = n; j->off = off; j->done = 0;
+    j->active = pthread_create(&j->th, NULL, io_job_run, j) == 0;
+    if (!j->active) io_job_run(j);
+}
+
+static size_t io_job_wait(io_job_t *j)
+{
+    if (j->active) { pthread_join(j->th, NULL); j->active = 0; }
+    return j->done;
+}
+
+/* a regular file we may address by offset: its descriptor and current position; -1 otherwise */
+static int io_seekable(FILE *fp, int for_write, off_t *pos)
+{
+    if (!fp || getenv("MRCZIP_SERIAL_IO")) return -1;
+    const int fd = fileno(fp);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return -1;
+    if (for_write && fflush(fp) != 0) return -1;
+    *pos = ftello(fp);
+    return *pos < 0 ? -1 : fd;
+}
+
+/* pinned staging, sized by what the file needs (a 64 MiB stack does not pin 1.5 GiB); the second pair only when
+ * there is more than one batch to overlap */
+static int pin_pair(thread_state_t *ts, size_t in_need, size_t out_need, int two)
+{
+    if (pin_reserve(&ts->pin_in, &ts->pin_in_cap, in_need) || pin_reserve(&ts->pin_out, &ts->pin_out_cap, out_need)) return -1;
+    if (!two) return 0;
+    return pin_reserve(&ts->pin_in2, &ts->pin_in2_cap, in_need) || pin_reserve(&ts->pin_out2, &ts->pin_out2_cap, out_need);
+}
+
+/* run_compress over seekable files: read b+1 | GPU b | write b-1 */
+static int compress_overlapped(thread_state_t *ts, FILE *fin, int fdin, off_t pos_in, FILE *fout, mrczip_header_t *hd,
+                               int bitsToMask, plane_acct_t *acct, uint64_t *zbytes)
+{
+    const uint32_t chk = hd->chk;
+    const size_t batch_words = (size_t)HOST_BATCH_CHUNKS * chk;
+    const uint64_t avail = hd->fsz > (uint64_t)pos_in ? hd->fsz - (uint64_t)pos_in : 0;
+    const uint64_t words_total = avail / 4; /* a ragged tail of 1..3 bytes is dropped (workers.c:744) */
+    if (words_total == 0) return MZB_OK;     /* workers.c:757-764: nothing read, nothing written */
+    const uint64_t nb = (words_total + batch_words - 1) / batch_words;
+    const size_t max_words = nb > 1 ? batch_words : (size_t)words_total;
+    const size_t out_cap = mzb_compress_bound(max_words, chk);
+    if (pin_pair(ts, max_words * 4, out_cap, nb > 1)) {
+        fprintf(stderr, "[%s:%d] ERROR: fail to alloc mem\n", __FILE__, __LINE__);
+        return MZB_E_NOMEM;
+    }
+    int fdout = -1;
+    off_t pos_out = 0;
+    if (isTestThroughput != 1) {
+        write_mrczip_header(fout, hd);
+        fdout = io_seekable(fout, 1, &pos_out);
+        if (fdout < 0) return MZB_E_IO;
+    }
+    void *in[2] = {ts->pin_in, ts->pin_in2}, *out[2] = {ts->pin_out, ts->pin_out2};
+    io_job_t jr, jw;
+    memset(&jr, 0, sizeof(jr));
+    memset(&jw, 0, sizeof(jw));
+    int rc = MZB_OK, writing = 0;
+    {
+        const uint64_t w = words_total < batch_words ? words_total : batch_words;
+        io_job_start(&jr, fdin, 0, in[0], (size_t)w * 4, pos_in);
+    }
+    for (uint64_t b = 0; b < nb && rc == MZB_OK; b++) {
+        const uint64_t w0 = b * batch_words;
+        const uint64_t want = (words_total - w0) < batch_words ? (words_total - w0) : batch_words;
+        const uint64_t num = io_job_wait(&jr) / 4;
+        if (num < want) { rc = MZB_E_IO; break; }   /* the file shrank under us */
+        if (b + 1 < nb) {
+            const uint64_t w1 = w0 + batch_words;
+            const uint64_t nxt = (words_total - w1) < batch_words ? (words_total - w1) : batch_words;
+            io_job_start(&jr, fdin, 0, in[(b + 1) & 1], (size_t)nxt * 4, pos_in + (off_t)(w1 * 4));
+        }
+        uint64_t sz = 0;
+        rc = mzb_compress_host(ts->ctx, in[b & 1], num, bitsToMask, b == 0 ? MZB_MRC_HEADER_WORDS : 0, chk, hd->fsz, 0,
+                               out[b & 1], out_cap, &sz);
+        if (rc != MZB_OK) {
+            fprintf(stderr, "[%s:%d] ERROR: GPU compress failed: %s\n", __FILE__, __LINE__, mzb_strerror(rc));
+            break;
+        }
+        account_records((const unsigned char *)out[b & 1], sz, chk, num, acct);
+        *zbytes += sz;
+        if (writing && io_job_wait(&jw) != jw.n) { rc = MZB_E_IO; break; }
+        writing = 0;
+        if (isTestThroughput != 1) {
+            io_job_start(&jw, fdout, 1, out[b & 1], (size_t)sz, pos_out);
+            writing = 1;
+            pos_out += (off_t)sz;
+        }
+    }
+    io_job_wait(&jr);
+    if (writing && io_job_wait(&jw) != jw.n && rc == MZB_OK) rc = MZB_E_IO;
+    fseeko(fin, 0, SEEK_END);                       /* where the reference's fread loop leaves it */
+    if (fdout >= 0) fseeko(fout, pos_out, SEEK_SET);
+    return rc;
+}
+
+/* extent of the next batch of a container: up to bchunks chunk records starting at file offset off */
+static int walk_batch(int fd, off_t off, uint64_t bchunks, uint64_t words_left, uint32_t chk, size_t *bytes, uint64_t *bw)
+{
+    size_t fill = 0;
+    uint64_t w = 0;
+    for (uint64_t c = 0; c < bchunks && w < words_left; c++) {
+        unsigned char h[16];
+        if (pread(fd, h, 16, off + (off_t)fill) != 16) return MZB_E_FORMAT;
+        size_t payload = 0;
+        for (int j = 0; j < MZB_PLANES; j++) {
+            btype_t bt;
+            uint32_t len;
+            unpack_header((const char *)h + 4 * j, &bt, &len);
+            if (len > chk + 4u) return MZB_E_FORMAT; /* the reference's reader buffer is chk + 4 (zip.c:334) */
+            payload += len;
+        }
+        fill += 16 + payload;
+        w += (words_left - w) < chk ? (words_left - w) : chk;
+    }
+    *bytes = fill;
+    *bw = w;
+    return MZB_OK;
+}
+
+/* run_uncompress over seekable files: read b+1 | GPU b | write b-1 */
+static int uncompress_overlapped(thread_state_t *ts, FILE *fin, int fdin, off_t pos_in, FILE *fout, uint32_t chk, uint64_t words,
+                                 uint64_t bchunks, plane_acct_t *acct, uint64_t *zbytes)
+{
+    const uint64_t nchunks = (words + chk - 1) / chk;
+    if (bchunks > nchunks && nchunks > 0) bchunks = nchunks;
+    const size_t in_cap = (size_t)(bchunks * (16 + 4ull * chk)) + 64, out_cap = (size_t)bchunks * chk * 4 + 64;
+    if (pin_pair(ts, in_cap, out_cap, nchunks > bchunks)) {
+        fprintf(stderr, "[%s:%d] ERROR: fail to alloc mem\n", __FILE__, __LINE__);
+        return MZB_E_NOMEM;
+    }
+    int fdout = -1;
+    off_t pos_out = 0;
+    if (isTestThroughput != 1) {
+        fdout = io_seekable(fout, 1, &pos_out);
+        if (fdout < 0) return MZB_E_IO;
+    }
+    void *in[2] = {ts->pin_in, ts->pin_in2}, *out[2] = {ts->pin_out, ts->pin_out2};
+    io_job_t jr, jw;
+    memset(&jr, 0, sizeof(jr));
+    memset(&jw, 0, sizeof(jw));
+    int rc = MZB_OK, writing = 0;
+    size_t bytes = 0, nbytes = 0;
+    uint64_t bw = 0, nbw = 0;
+    off_t off = pos_in;
+    if (words > 0 && (rc = walk_batch(fdin, off, bchunks, words, chk, &bytes, &bw)) == MZB_OK)
+        io_job_start(&jr, fdin, 0, in[0], bytes, off);
+    uint64_t b = 0;
+    for (uint64_t w0 = 0; w0 < words && rc == MZB_OK; b++) {
+        if (io_job_wait(&jr) != bytes) { rc = MZB_E_FORMAT; break; }   /* truncated container */
+        off += (off_t)bytes;
+        if (w0 + bw < words) {
+            if ((rc = walk_batch(fdin, off, bchunks, words - w0 - bw, chk, &nbytes, &nbw)) != MZB_OK) break;
+            io_job_start(&jr, fdin, 0, in[(b + 1) & 1], nbytes, off);
+        }
+        uint64_t nw = 0;
+        rc = mzb_decompress_host(ts->ctx, in[b & 1], bytes, 0, chk, bw, out[b & 1], out_cap / 4, &nw);
+        if (rc != MZB_OK) break;
+        account_records((const unsigned char *)in[b & 1], bytes, chk, bw, acct);
+        *zbytes += bytes;
+        if (writing && io_job_wait(&jw) != jw.n) { rc = MZB_E_IO; break; }
+        writing = 0;
+        if (isTestThroughput != 1) {
+            io_job_start(&jw, fdout, 1, out[b & 1], (size_t)nw * 4, pos_out);
+            writing = 1;
+            pos_out += (off_t)(nw * 4);
+        }
+        w0 += bw;
+        bytes = nbytes;
+        bw = nbw;
+    }
+    io_job_wait(&jr);
+    if (writing && io_job_wait(&jw) != jw.n && rc == MZB_OK) rc = MZB_E_IO;
+    fseeko(fin, off, SEEK_SET);
+    if (fdout >= 0) fseeko(fout, pos_out, SEEK_SET);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ run_compress / run_uncompress */
 
 int run_compress(FILE *fin, ctx_t *ctx, FILE *fout, const int bitsToMask, const char *dataConvertedType)
@@ -243,6 +515,25 @@ int run_compress(FILE *fin, ctx_t *ctx, FILE *fout, const int bitsToMask, const 
     const double begin = now_sec();
     const uint32_t chk = MZB_CHUNK_WORDS;
     const size_t batch_words = (size_t)HOST_BATCH_CHUNKS * chk;
+    {   /* regular files: multi-threaded, overlapped I/O (same bytes, same accounting) */
+        off_t pos_in = 0, pos_chk = 0;
+        const int fdin = io_seekable(fin, 0, &pos_in);
+        if (fdin >= 0 && (isTestThroughput == 1 || io_seekable(fout, 1, &pos_chk) >= 0)) {
+            mrczip_header_t hd2;
+            init_mrczip_header(&hd2, 0);
+            hd2.chk = chk;
+            hd2.fsz = get_file_size(fin); /* workers.c:743 */
+            plane_acct_t acct2;
+            memset(&acct2, 0, sizeof(acct2));
+            uint64_t zb = 0;
+            const int rc2 = compress_overlapped(ts, fin, fdin, pos_in, fout, &hd2, bitsToMask, &acct2, &zb);
+            const double dt2 = now_sec() - begin;
+            ctx->zipTime += dt2;
+            ctx->allZipFileSize += zb; /* workers.c:869-872 */
+            print_result_like(&acct2, dt2, 1, "Compression Summary Result");
+            return rc2;
+        }
+    }
     if (pin_reserve(&ts->pin_in, &ts->pin_in_cap, batch_words * 4) ||
         pin_reserve(&ts->pin_out, &ts->pin_out_cap, mzb_compress_bound(batch_words, chk))) {
         fprintf(stderr, "[%s:%d] ERROR: fail to alloc mem\n", __FILE__, __LINE__);
@@ -305,6 +596,23 @@ int run_uncompress(FILE *fin, ctx_t *ctx, mrczip_header_t *hd, FILE *fout, const
     uint64_t bchunks = ((uint64_t)HOST_BATCH_CHUNKS * MZB_CHUNK_WORDS) / chk;
     if (bchunks == 0) bchunks = 1;
     if (bchunks > 4096) bchunks = 4096;
+    {   /* regular files: multi-threaded, overlapped I/O */
+        off_t pos_in = 0, pos_chk = 0;
+        const int fdin = io_seekable(fin, 0, &pos_in);
+        if (fdin >= 0 && (isTestThroughput == 1 || io_seekable(fout, 1, &pos_chk) >= 0)) {
+            plane_acct_t acct2;
+            memset(&acct2, 0, sizeof(acct2));
+            uint64_t zb = 0;
+            const int rc2 = uncompress_overlapped(ts, fin, fdin, pos_in, fout, chk, words, bchunks, &acct2, &zb);
+            if (rc2 != MZB_OK) fprintf(stderr, "[%s:%d] ERROR: GPU decompress failed: %s\n", __FILE__, __LINE__, mzb_strerror(rc2));
+            const double dt2 = now_sec() - begin;
+            ctx->allFileSize += words * MZB_PLANES; /* workers.c:679-684 */
+            ctx->allZipFileSize += zb;
+            ctx->unzipTime += dt2;
+            print_result_like(&acct2, dt2, 0, "Decompress Result Info");
+            return rc2;
+        }
+    }
     const size_t in_cap = (size_t)(bchunks * (16 + 4ull * chk)) + 64;
     if (pin_reserve(&ts->pin_in, &ts->pin_in_cap, in_cap) || pin_reserve(&ts->pin_out, &ts->pin_out_cap, (size_t)bchunks * chk * 4 + 64)) {
         fprintf(stderr, "[%s:%d] ERROR: fail to alloc mem\n", __FILE__, __LINE__);

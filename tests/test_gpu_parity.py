@@ -394,6 +394,45 @@ def test_host_buffer_api_and_file_api(codec, oracle):
             assert np.array_equal(oracle.ref_decompress(cont2), oracle.ref_erasebytes(raw, 9))
 
 
+def test_file_api_overlapped_io_many_batches(codec, oracle, monkeypatch):
+    """run_compress / run_uncompress over regular files: batches of 16 chunks are read ahead and written behind by
+    several threads (pread / pwrite).  More than two batches, a partial last chunk and a ragged byte tail; the file
+    made that way is byte-identical to the one the plain fread / fwrite loop makes and to the device API's container."""
+    from datacompressionfloat_b200 import zip_compress, zip_uncompress, file_header
+    chunk = 6 * 1048576
+    nwords = 33 * chunk + 12345                      # 3 batches (16 + 16 + 2 chunks), last chunk partial
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    d_words = (torch.randn(nwords, generator=g, device="cuda") * 3).round().view(torch.int32)   # small integers: P-like planes
+    raw = np.concatenate([d_words.cpu().numpy().view(np.uint8), np.array([7, 8, 9], np.uint8)])
+    bits = 5
+    golden = oracle.erasebytes(raw, bits)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        src, z, z2, out = (os.path.join(d, n) for n in ("v.mrc", "v.zip", "v2.zip", "v.out"))
+        raw.tofile(src)
+        ctx = zip_compress(src, z, bits)
+        cont = np.fromfile(z, dtype=np.uint8)
+        assert ctx["allFileSize"] == raw.size and ctx["allZipFileSize"] == cont.size - 17
+        monkeypatch.setenv("MRCZIP_SERIAL_IO", "1")
+        zip_compress(src, z2, bits)
+        monkeypatch.delenv("MRCZIP_SERIAL_IO")
+        assert np.array_equal(cont, np.fromfile(z2, dtype=np.uint8)), "overlapped and serial I/O paths differ"
+        dev_cont = codec.compress(d_words, bits, fsz=raw.size)
+        assert np.array_equal(cont, dev_cont.cpu().numpy()), "file path and device path differ"
+        del dev_cont
+        zip_uncompress(z, out)
+        assert np.array_equal(np.fromfile(out, dtype=np.uint8), golden)
+        monkeypatch.setenv("MRCZIP_SERIAL_IO", "1")
+        zip_uncompress(z, out)
+        assert np.array_equal(np.fromfile(out, dtype=np.uint8), golden)
+        # a truncated container is an error, not a short file
+        cont[: cont.size - 1000].tofile(z2)
+        monkeypatch.delenv("MRCZIP_SERIAL_IO")
+        with pytest.raises(Exception):
+            zip_uncompress(z2, out)
+
+
 def test_malformed_inputs_are_rejected(codec, oracle):
     from datacompressionfloat_b200 import MzbError
     w = synth_words("P", 50000)
