@@ -227,7 +227,7 @@ def run_reference_arm(a):
         "compress_GBs": r.get("compress_GBs"), "decompress_GBs": r.get("decompress_GBs"), "ratio": r.get("ratio"),
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -285,6 +285,10 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's version / debug lines must not land on stdout next to the JSON line (NCCL_DEBUG=VERSION printf's there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -469,14 +473,33 @@ def run_b200(a):
         "encode_stats": {k: state["cs"][k] for k in ("raw_streams", "stored_subblocks", "streams")},
         "stage_ms": {k: round(v, 4) for k, v in stages.items() if v > 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     a = parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner, the reference
+    # binaries' tables) is sent to stderr instead
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         return run_reference_arm(a)
     return run_b200(a)
