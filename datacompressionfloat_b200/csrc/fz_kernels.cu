@@ -1326,7 +1326,39 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     // no global load in the loop.  A lane leaves the fast rounds at the first thing that is not a table hit, a long
     // literal or a run (end of block, errors, end of the output) and hands its position to the general inflater.
     {
-        bool fast = live && coded && lut != nullptr && inf.in_body && inf.bw.op0 == 0;
+        bool fast = live && coded && lut != nullptr && inf.in_body && inf.bw.op0 == 0 && ((uintptr_t)inf.bw.out & 15u) == 0;
+        // completed output words wait in pw0..pw2 until the fourth of their 16-byte group arrives and leave as one
+        // 128-bit store (4-byte stores cost a 32-byte sector each on the way to L2: 8x the bytes written).  Outside
+        // the literal path nothing is pending: FZ_FLUSH_PW stores what is (word index & 3 words) before anything else
+        // touches the writer.
+        uint32_t pw0 = 0, pw1 = 0, pw2 = 0, lastw = 0;   // lastw: the last completed word (a run needs the byte before it)
+#define FZ_FLUSH_PW()                                                                           \
+        do {                                                                                    \
+            const uint32_t k_ = (inf.bw.op >> 2) & 3u;                                          \
+            uint32_t *q_ = (uint32_t *)(inf.bw.out + (inf.bw.op & ~15u));                       \
+            if (k_ > 0) q_[0] = pw0;                                                            \
+            if (k_ > 1) q_[1] = pw1;                                                            \
+            if (k_ > 2) q_[2] = pw2;                                                            \
+        } while (0)
+        // after the general inflater wrote (it stores every completed word itself): what precedes the pending word
+#define FZ_RELOAD_PW()                                                                          \
+        do {                                                                                    \
+            const uint32_t k_ = (inf.bw.op >> 2) & 3u;                                          \
+            const uint32_t *q_ = (const uint32_t *)(inf.bw.out + (inf.bw.op & ~15u));           \
+            if (k_ > 0) pw0 = q_[0];                                                            \
+            if (k_ > 1) pw1 = q_[1];                                                            \
+            if (k_ > 2) pw2 = q_[2];                                                            \
+            lastw = inf.bw.op >= 4u ? *(const uint32_t *)(inf.bw.out + (inf.bw.op & ~3u) - 4u) : 0u; \
+        } while (0)
+        // word w_ completes place kq_ (0..3) of the 16-byte group at gaddr_
+#define FZ_WORD_DONE(w_, kq_, gaddr_)                                                           \
+        do {                                                                                    \
+            if ((kq_) == 3u) *(uint4 *)(gaddr_) = make_uint4(pw0, pw1, pw2, (w_));              \
+            pw0 = (kq_) == 0u ? (w_) : pw0;                                                     \
+            pw1 = (kq_) == 1u ? (w_) : pw1;                                                     \
+            pw2 = (kq_) == 2u ? (w_) : pw2;                                                     \
+            lastw = (w_);                                                                       \
+        } while (0)
         const uint32_t mis = (uint32_t)((uintptr_t)frag & 15u);
         const uint8_t *gbase = frag - mis;                               // chunk 0
         const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
@@ -1394,7 +1426,36 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                         if (((a >> xb) & 1u) != run_bit || inf.bw.op + len > inf.bw.cap || inf.bw.produced() == 0) { slow = true; break; }
                         acc >>= (cl + xb + 1u);
                         nacc -= (int)(cl + xb + 1u);
-                        inf.bw.fill(inf.bw.back(1), len);
+                        {   // len copies of the byte before, through the pending-word logic (no read of what was written)
+                            const uint32_t r = inf.bw.op & 3u;
+                            const uint32_t c = r ? (inf.bw.ow >> ((r - 1u) * 8u)) & 0xffu : lastw >> 24;
+                            const uint32_t cw = c * 0x01010101u;
+                            uint32_t left = len;
+                            if (r) {   // complete the pending word first
+                                const uint32_t take = left < 4u - r ? left : 4u - r;
+                                inf.bw.ow |= (cw & (0xffffffffu >> (32u - 8u * take))) << (8u * r);
+                                left -= take;
+                                if (r + take == 4u) {
+                                    FZ_WORD_DONE(inf.bw.ow, (inf.bw.op >> 2) & 3u, inf.bw.out + (inf.bw.op & ~15u));
+                                    inf.bw.ow = 0;
+                                }
+                                inf.bw.op += take;
+                            }
+                            while (left >= 4u) {
+                                const uint32_t kq = (inf.bw.op >> 2) & 3u;
+                                if (kq == 0u && left >= 16u) {
+                                    *(uint4 *)(inf.bw.out + inf.bw.op) = make_uint4(cw, cw, cw, cw);
+                                    lastw = cw;
+                                    inf.bw.op += 16u;
+                                    left -= 16u;
+                                } else {
+                                    FZ_WORD_DONE(cw, kq, inf.bw.out + (inf.bw.op & ~15u));
+                                    inf.bw.op += 4u;
+                                    left -= 4u;
+                                }
+                            }
+                            if (left) { inf.bw.ow = cw & (0xffffffffu >> (32u - 8u * left)); inf.bw.op += left; }
+                        }
                         if (inf.bw.cap - inf.bw.op < 3u * (uint32_t)(iters - it)) break;   // the round's budget is gone
                         continue;
                     }
@@ -1407,7 +1468,15 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                         if (sym >= 256u) { slow = true; break; }
                         acc >>= l;
                         nacc -= l;
-                        inf.bw.put(sym);
+                        {   // one byte through the same pending-word logic as below
+                            const uint32_t sh1 = (inf.bw.op & 3u) * 8u;
+                            const uint32_t t1 = inf.bw.ow | (sym << sh1);
+                            if (sh1 == 24u) {
+                                FZ_WORD_DONE(t1, (inf.bw.op >> 2) & 3u, inf.bw.out + (inf.bw.op & ~15u));
+                                inf.bw.ow = 0;
+                            } else inf.bw.ow = t1;
+                            inf.bw.op += 1;
+                        }
                         continue;
                     }
                     // 1..3 literals: sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that
@@ -1416,14 +1485,20 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                     const uint32_t v = (e & 255u) | ((e >> 1) & 0xffff00u);
                     const uint32_t sh = (inf.bw.op & 3u) * 8u;
                     const uint64_t t = (uint64_t)inf.bw.ow | ((uint64_t)v << sh);
+                    const uint32_t kq = (inf.bw.op >> 2) & 3u;     // place of the pending word in its 16-byte group
                     inf.bw.op += cnt;
                     const bool full = sh + cnt * 8u >= 32u;
-                    if (full) *(uint32_t *)(inf.bw.out + ((inf.bw.op & ~3u) - 4u)) = (uint32_t)t;
+                    if (full && kq == 3u) *(uint4 *)(inf.bw.out + ((inf.bw.op & ~3u) - 16u)) = make_uint4(pw0, pw1, pw2, (uint32_t)t);
+                    pw0 = (full && kq == 0u) ? (uint32_t)t : pw0;
+                    pw1 = (full && kq == 1u) ? (uint32_t)t : pw1;
+                    pw2 = (full && kq == 2u) ? (uint32_t)t : pw2;
+                    lastw = full ? (uint32_t)t : lastw;
                     inf.bw.ow = full ? (uint32_t)(t >> 32) : (uint32_t)t;
                     acc >>= tl;
                     nacc -= (int)tl;
                 }
                 if (slow) {
+                    FZ_FLUSH_PW();
                     // something else (a long length code, end of block, end of the output, an error): the general
                     // inflater takes this one symbol at the lane's bit position, then the ring reader resumes behind it
                     const int64_t rel = (int64_t)rp * 32 - nacc - (int64_t)mis * 8;
@@ -1442,6 +1517,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                             // (one symbol is at most 48 bits: still inside what the ring holds)
                             if (left >= 0 && ((r0 + 2) >> 2) < fetched && (r0 >> 2) + FZ_RING_CHUNKS >= fetched) {
                                 fast = true;
+                                FZ_RELOAD_PW();
                                 rp = r0;
                                 acc = (uint64_t)(row[rp & (FZ_RING_CHUNKS * 4 - 1)] >> (abs_bit & 31u));
                                 nacc = 32 - (int)(abs_bit & 31u);
