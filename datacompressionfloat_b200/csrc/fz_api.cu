@@ -326,8 +326,11 @@ static void compress_enqueue_batch(mzb_ctx *c, const uint32_t *d_words, uint64_t
     fz_launch_split(d_words, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
     prof_mark(c, FZ_ST_SPLIT);
     if (!c->zero_hist_ready) { fz_launch_zero_hist((uint32_t *)c->zero_hist.p, c->stream); c->zero_hist_ready = true; }
+    uint32_t zero_planes = 0;
+    for (int j = 0; j < FZ_PLANES; j++)
+        if (((mask >> (8 * j)) & 0xffu) == 0) zero_planes |= 1u << j;
     fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p,
-                     (uint32_t *)c->sizes.p, (const uint32_t *)c->zero_hist.p, c->d_status, c->stream);
+                     (uint32_t *)c->sizes.p, (const uint32_t *)c->zero_hist.p, zero_planes, exempt, c->d_status, c->stream);
     prof_mark(c, FZ_ST_ENCODE);
     fz_launch_layout((uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p,
                      (unsigned long long *)c->stream_off.p, d_out, out_cap, c->d_status, c->stream);

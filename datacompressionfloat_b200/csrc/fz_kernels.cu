@@ -505,7 +505,7 @@ struct __align__(16) FzHistSmem {
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
 fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist, uint32_t *__restrict__ sizes,
-               const uint32_t *__restrict__ zero_hist, FzStatus *status)
+               const uint32_t *__restrict__ zero_hist, uint32_t zero_planes, uint64_t zero_from, FzStatus *status)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -515,6 +515,17 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
     if (!fz_slot(g, t, s, k, n)) return;
     FzHistSmem *sm = (FzHistSmem *)fz_smem + warp;
     const uint8_t *src = fz_sub_src(planes, g, s, k);
+    if (n == FZ_SUB && ((zero_planes >> (s & 3u)) & 1u) && (uint64_t)(s >> 2) * g.chk + (uint64_t)k * FZ_SUB >= zero_from) {
+        // the mask erases this whole byte plane (8 or more bits erased) and the sub-block lies behind the exempt
+        // header words: 16 KiB of zeros, known without reading them
+        if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
+        uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+        for (int i = lane; i < 288; i += 32) {
+            const uint32_t v = zero_hist[i];
+            if (v) atomicAdd(gh + i, v);
+        }
+        return;
+    }
     for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
     __syncwarp();
     if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
@@ -679,7 +690,7 @@ void fz_launch_zero_hist(uint32_t *zero_hist, cudaStream_t st)
 }
 
 void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, void *gcodes, uint8_t *scratch, uint32_t *sizes,
-                      const uint32_t *zero_hist, FzStatus *status, cudaStream_t st)
+                      const uint32_t *zero_hist, uint32_t zero_planes, uint64_t zero_from, FzStatus *status, cudaStream_t st)
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t total = nstreams * g.nsub_full;
@@ -692,7 +703,7 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
     cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
-    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, zero_hist, status);
+    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, zero_hist, zero_planes, zero_from, status);
     fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
         ghist, g, (FzGroupCode *)gcodes);
     fz_emit_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEmitSmem) * FZ_ENC_WARPS, st>>>(planes, g, (const FzGroupCode *)gcodes,

@@ -50,8 +50,10 @@ void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwor
 // groups per stream = ceil(nsub_full / FZ_GROUP_SUBS)
 // zero_hist: 288 uint32 made once per context by fz_launch_zero_hist (token histogram of an all-zero sub-block)
 void fz_launch_zero_hist(uint32_t *zero_hist, cudaStream_t st);
+// zero_planes: bit j = the mask erases byte plane j entirely; zero_from: first word of the batch that is masked
+// (sub-blocks of such planes behind it are all zero and are not even read)
 void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, void *gcodes, uint8_t *scratch, uint32_t *sizes,
-                      const uint32_t *zero_hist, FzStatus *status, cudaStream_t st);
+                      const uint32_t *zero_hist, uint32_t zero_planes, uint64_t zero_from, FzStatus *status, cudaStream_t st);
 size_t fz_group_code_bytes();
 // stream sums + RAW decision + scan over chunk records + chunk headers; container offsets continue from status->out_end
 void fz_launch_layout(uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_t *stream_hdr,
