@@ -312,14 +312,16 @@ fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__res
     // whole byte planes: 1 GiB of stores and 1 GiB of loads per 4 GiB volume that nobody needs).
     // All eight table loads are issued before anything depends on them: these CTAs live for a microsecond.
     uint32_t h[4], zf[4];
+    unsigned long long so[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         h[j] = __ldg(stream_hdr + c * 4 + j);
+        so[j] = __ldg(stream_off + c * 4 + j);
         zf[j] = zero_flags ? __ldg(zero_flags + (size_t)(c * 4 + j) * g.nsub_full + sub) : 0u;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        src[j] = (h[j] & FZ_RAW_FLAG) ? container + stream_off[c * 4 + j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
+        src[j] = (h[j] & FZ_RAW_FLAG) ? container + so[j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
         end[j] = src[j] + n_c;
         zero[j] = zf[j] != 0 && !(h[j] & FZ_RAW_FLAG);
     }
