@@ -324,6 +324,27 @@ def test_roundtrip_edge_sizes(codec, oracle, nwords, chk):
     assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(w.view(np.uint8), 6))
 
 
+@pytest.mark.parametrize("shift", [1, 5, 13, 16, 31])
+@pytest.mark.parametrize("kind,bits", [("G", 8), ("P", 0), ("S", 12)])
+def test_decompress_from_misaligned_container(codec, oracle, shift, kind, bits):
+    """The container may start at any byte address: the inflater's 16-byte cp.async chunks, the marker scan and
+    the merge's in-place read of RAW payloads all re-align by themselves.  The buffer ends right behind the container."""
+    w = synth_words(kind, 5 * 65536 + 4321)
+    cont = codec.compress(dev(w), bits, chk=65536)
+    n = cont.numel()
+    buf = torch.empty(shift + n, dtype=torch.uint8, device="cuda")
+    buf[shift:].copy_(cont)
+    back = codec.decompress(buf[shift:])
+    assert np.array_equal(host_u32(back).view(np.uint8), oracle.erasebytes(w.view(np.uint8), bits))
+    assert codec.stats()["general_streams"] == 0 and codec.stats()["fast_failed"] == 0
+    # and a container made by the reference's zlib parameters, from the same odd address
+    ref = torch.from_numpy(oracle.compress(w.view(np.uint8), bits, chk=65536)).cuda()
+    buf2 = torch.empty(shift + ref.numel(), dtype=torch.uint8, device="cuda")
+    buf2[shift:].copy_(ref)
+    back2 = codec.decompress(buf2[shift:])
+    assert np.array_equal(host_u32(back2).view(np.uint8), oracle.erasebytes(w.view(np.uint8), bits))
+
+
 def test_empty_input(codec):
     cont = codec.compress(torch.empty(0, dtype=torch.int32, device="cuda"), 0)
     assert cont.numel() == 0                                   # workers.c:757-764: nothing written
