@@ -374,7 +374,9 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, co
 //   fz_group_code_kernel  one warp per group: Huffman code + block header (once per 512 KiB of plane)
 //   fz_emit_kernel        one warp per sub-block: exact size, stored-vs-dynamic decision, lane-parallel bit emission
 // =================================================================================================
+#ifndef FZ_ENC_WARPS
 #define FZ_ENC_WARPS 4
+#endif
 // ---- how a warp reads its sub-block --------------------------------------------------------------------------
 // Lane l tokenises the contiguous piece [l*512, (l+1)*512) of the 16 KiB sub-block.  The pieces stream through a
 // two-stage shared-memory window of 64 bytes per lane: cp.async (16 B per lane and instruction, four per window,
@@ -382,7 +384,10 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, co
 // (w+1)&1 while the lanes tokenise window w out of stage w&1.  Rows are 80 bytes apart, which makes the per-lane
 // 128-bit reads bank-conflict free.  5 KB per warp instead of the 17 KB a fully staged sub-block took: 32 warps per
 // SM instead of 12, and no exposed load latency.
+#ifndef FZ_WIN_BYTES
 #define FZ_WIN_BYTES 64
+#endif
+#define FZ_WIN_C (FZ_WIN_BYTES / 16)     // 16-byte chunks per lane and window = cp.async instructions per window
 #define FZ_WIN_ROW (FZ_WIN_BYTES + 16)
 #define FZ_WIN_STAGE (FZ_WARP * FZ_WIN_ROW)
 #define FZ_WIN_SMEM (2 * FZ_WIN_STAGE)
@@ -404,7 +409,7 @@ struct FzWindowScan {
     __device__ __forceinline__ void operator()(Sink &sink, int lane) const
     {
         const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
-        const uint32_t part = (uint32_t)lane & 3u, prow = (uint32_t)lane >> 2;
+        const uint32_t part = (uint32_t)lane % FZ_WIN_C, prow = (uint32_t)lane / FZ_WIN_C;
         const uint8_t *gsrc = src + prow * FZ_PIECE + part * 16;
         const uint32_t sdst = wbase + prow * FZ_WIN_ROW + part * 16;
         // window w -> stage w & 1
@@ -412,8 +417,8 @@ struct FzWindowScan {
         do {                                                                                                         \
             const uint32_t st_ = sdst + ((w) & 1u) * FZ_WIN_STAGE;                                                   \
             const uint8_t *g_ = gsrc + (w) * FZ_WIN_BYTES;                                                           \
-            _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++)                                                         \
-                fz_cp_async16(st_ + q_ * 8 * FZ_WIN_ROW, g_ + q_ * 8 * FZ_PIECE);                                    \
+            _Pragma("unroll") for (int q_ = 0; q_ < FZ_WIN_C; q_++)                                                  \
+                fz_cp_async16(st_ + q_ * (32 / FZ_WIN_C) * FZ_WIN_ROW, g_ + q_ * (32 / FZ_WIN_C) * FZ_PIECE);        \
             fz_cp_async_commit();                                                                                    \
         } while (0)
         FZ_WIN_ISSUE(0u);
@@ -1167,7 +1172,9 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 // parses the header once, builds ONE first-level lookup table in shared memory and every lane decodes its
 // own fragment with it.  Lanes verify that their header bits equal the leader's; any mismatch, parse error
 // or size mismatch flags the stream, which is then re-decoded by the general inflater.
+#ifndef FZ_INF_WARPS
 #define FZ_INF_WARPS 4
+#endif
 #ifndef FZ_INF_CARVEOUT_PCT
 #define FZ_INF_CARVEOUT_PCT 100    // all of the 228 KB as shared memory: 4 CTAs x 54 KB
 #endif
@@ -1175,9 +1182,16 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 #define FZ_INF_MINBLOCKS 1
 #endif
 #define FZ_ZERO_PROBE_BYTES 96u   // 16 KiB of zeros is ~70 bytes of run codes
+#ifndef FZ_RING_CHUNKS
 #define FZ_RING_CHUNKS 8u                        // 16-byte chunks of input per lane
+#endif
+#ifndef FZ_RING_TOPUPS
+#define FZ_RING_TOPUPS 3                         // chunks a round can use up (16 iterations x 17 bits + one symbol)
+#endif
 #define FZ_RING_ROW_WORDS (FZ_RING_CHUNKS * 4u + 4u)  // row pitch in words (16 bytes of padding)
+#ifndef FZ_FAST_ITERS
 #define FZ_FAST_ITERS 16
+#endif
 struct FzGroupSmem {
     alignas(16) uint32_t ring[FZ_WARP * FZ_RING_ROW_WORDS];  // every lane's window on its fragment (cp.async)
     uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
@@ -1405,7 +1419,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                 // after a symbol taken by the general inflater the lane re-reads its buffer from the ring
                 const uint32_t cons = (rp >= 2u ? rp - 2u : 0u) >> 2;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < FZ_RING_TOPUPS; q++) {
                     if (fetched < cons + FZ_RING_CHUNKS) {
                         if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
                         fetched++;
