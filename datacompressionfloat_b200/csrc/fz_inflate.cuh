@@ -89,9 +89,6 @@ struct FzByteWriter {
     FZ_HD uint32_t produced() const { return op - op0; }
     FZ_HD void store_word(uint32_t widx_bytes, uint32_t w)  // the word starting at byte offset widx_bytes is complete
     {
-#ifdef FZ_EXP_NOSTORE
-        if (w != 0x9e3779b9u) return;
-#endif
         if (widx_bytes == 0 && op0) { for (uint32_t i = op0; i < 4; i++) out[i] = (uint8_t)(w >> (8 * i)); }
         else *(uint32_t *)(out + widx_bytes) = w;
     }
