@@ -312,16 +312,14 @@ fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__res
     // whole byte planes: 1 GiB of stores and 1 GiB of loads per 4 GiB volume that nobody needs).
     // All eight table loads are issued before anything depends on them: these CTAs live for a microsecond.
     uint32_t h[4], zf[4];
-    unsigned long long so[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         h[j] = __ldg(stream_hdr + c * 4 + j);
-        so[j] = __ldg(stream_off + c * 4 + j);
         zf[j] = zero_flags ? __ldg(zero_flags + (size_t)(c * 4 + j) * g.nsub_full + sub) : 0u;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        src[j] = (h[j] & FZ_RAW_FLAG) ? container + so[j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
+        src[j] = (h[j] & FZ_RAW_FLAG) ? container + stream_off[c * 4 + j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
         end[j] = src[j] + n_c;
         zero[j] = zf[j] != 0 && !(h[j] & FZ_RAW_FLAG);
     }
@@ -627,7 +625,14 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
     const uint32_t gn = (uint32_t)min((uint64_t)n_s - (uint64_t)gk * gbytes, gbytes);
     const uint32_t nsub = (gn + FZ_SUB - 1) / FZ_SUB;
     FzEncState *st = (FzEncState *)fz_smem + warp;
-    for (int i = lane; i < 288; i += 32) st->hist[i] = ghist[(uint64_t)gi * 288 + i];
+    uint32_t any = 0;
+    for (int i = lane; i < 288; i += 32) { const uint32_t v = ghist[(uint64_t)gi * 288 + i]; st->hist[i] = v; any |= v; }
+    if (!__any_sync(0xffffffffu, any != 0)) {
+        // no tokens at all: every sub-block of the group was ruled incompressible by its sample (flat mantissa
+        // planes) and is already marked stored -- nobody will read this group's code
+        if (lane == 0) gcodes[gi].stored = 1u;
+        return;
+    }
     __syncwarp();
     if (lane == 0) st->hist[FZ_EOB] = nsub;  // one end-of-block per sub-block
     __syncwarp();
@@ -994,11 +999,28 @@ __device__ __forceinline__ uint32_t fz_marker_mask(const uint8_t *base, uint32_t
     uint32_t V[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) V[k] = __funnelshift_r(W[k], W[k + 1], sk * 8);
-    uint32_t m = 0;
+    // bit i of F: byte i of the 20-byte window is 0xFF (zero-byte trick on ~V, four flags gathered by one multiply).
+    // A marker at position b needs FF at b + 2 and b + 3: in compressed data that is one window in four thousand, so
+    // the zero bytes are only looked at then.
+    uint32_t F = 0;
 #pragma unroll
-    for (int b = 0; b < 16; b++) {
-        const uint32_t v = __funnelshift_r(V[b >> 2], V[(b >> 2) + 1], (b & 3) * 8);
-        if (v == 0xFFFF0000u && p0 + b + 4 <= len) m |= 1u << b;
+    for (int k = 0; k < 5; k++) {
+        const uint32_t x = ~V[k];
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
+        F |= ((z * 0x00204081u) >> 28) << (4 * k);
+    }
+    uint32_t m = (F >> 2) & (F >> 3) & 0xffffu;
+    if (m) {
+        uint32_t Z = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const uint32_t x = V[k];
+            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+            Z |= ((z * 0x00204081u) >> 28) << (4 * k);
+        }
+        m &= Z & (Z >> 1);
+        const uint32_t nvalid = len - p0 - 3u;   // positions b with p0 + b + 4 <= len (>= 1 here)
+        if (nvalid < 16u) m &= (1u << nvalid) - 1u;
     }
     return m;
 }
