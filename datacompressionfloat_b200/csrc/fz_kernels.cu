@@ -849,7 +849,7 @@ void fz_launch_layout(uint32_t *sizes, FzBatchGeom g, uint32_t *sub_off, uint32_
 }
 
 // one warp per sub-block: move the encoded fragment (or the raw / stored plane bytes) to its place in the container
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 16)
 fz_gather_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ scratch, const uint32_t *__restrict__ sizes,
                  const uint32_t *__restrict__ sub_off, const uint32_t *__restrict__ stream_hdr,
                  const unsigned long long *__restrict__ stream_off, FzBatchGeom g, uint8_t *__restrict__ container,
