@@ -827,3 +827,142 @@ FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, const uint32_t *hdr, FzEm
 {
     return fz_emit_subblock_sc(gc, hdr, es, FzPieceScan<Load16, LoadByte>{ld, lb, n}, n, out, lane);
 }
+
+// =================================================================================================
+// Window-interleaved piece geometry (lead #1) -- NOT used by the kernels yet; checked on the CPU by
+// tests/hostmodel against zlib.
+//
+// Today lane l owns ONE contiguous 512-byte piece of the sub-block, so the bit offset of lane l + 1 is known only
+// after lane l's whole piece has been counted: fz_emit_subblock scans the sub-block twice (count, emit).  Here the
+// sub-block is cut into windows of 32 pieces of FZ_IPIECE bytes, piece p = window p / 32, lane p % 32, emitted in
+// piece order.  Inside a window the count, the warp prefix and the emission all work on the 2 KiB the warp already
+// holds in shared memory, and the only thing carried from window to window is the running bit position and the
+// partial word at its end.  The tokeniser restarts at every piece start, as it does today at the 32 piece starts;
+// tools/piece_geometry_study.py: no measurable size cost except on all-zero sub-blocks.
+// =================================================================================================
+#define FZ_IPIECE 64u
+#define FZ_IWIN (FZ_IPIECE * 32u)
+
+template <class Load16, class LoadByte>
+struct FzWindowPieceScan {
+    const Load16 &ld;
+    const LoadByte &lb;
+    uint32_t n, w;
+    template <class Sink>
+    FZ_HD void operator()(Sink &sink, int lane) const
+    {
+        const uint32_t b = w * FZ_IWIN + (uint32_t)lane * FZ_IPIECE;
+        uint32_t e = b + FZ_IPIECE;
+        if (e > n) e = n;
+        if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
+    }
+};
+
+template <class Load16, class LoadByte>
+FZ_HD void fz_ph_hist_interleaved(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
+{
+    for (uint32_t w = 0; w * FZ_IWIN < n; w++) fz_ph_hist_sc(hist, FzWindowPieceScan<Load16, LoadByte>{ld, lb, n, w}, lane);
+}
+
+struct FzEmitStateI {
+    FzEmitState es;        // per-window lane exchange (lane_bits, first / last word of every lane)
+    uint32_t base_bits;    // bits emitted by the windows before this one
+    uint32_t carry_in;     // what they left in the word that holds bit `base_bits` (its low base_bits & 31 bits)
+    uint32_t carry_next;
+    uint32_t pad;
+};
+
+template <class Scan>
+FZ_HD void fz_ph_count_window(const FzGroupCode *gc, FzEmitStateI *st, const Scan &scan, bool first, int lane)
+{
+    FzCountSink cs{gc->cl, 0};
+    scan(cs, lane);
+    if (first && lane == 0) cs.bits += gc->hdr_nbits;
+    st->es.lane_bits[lane] = cs.bits;
+}
+
+template <class Scan>
+FZ_HD void fz_ph_emit_window(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, const Scan &scan, bool first, bool last,
+                             uint32_t *out, int lane)
+{
+    FzEmitState *es = &st->es;
+    uint32_t off = st->base_bits;
+    for (int l = 0; l < lane; l++) off += es->lane_bits[l];
+    FzEmitSink sink;
+    sink.cl = gc->cl;
+    sink.bw.init(out, off);
+    if (first && lane == 0) {
+        uint32_t nb = gc->hdr_nbits, w = 0;
+        while (nb >= 32) { sink.bw.put(hdr[w++], 32); nb -= 32; }
+        if (nb) sink.bw.put(hdr[w] & ((1u << nb) - 1), nb);
+    }
+    scan(sink, lane);
+    if (last && lane == 31) {
+        sink.bw.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
+        sink.bw.put(0, 3);
+        sink.bw.align_byte();
+        sink.bw.put(0x0000u, 16);
+        sink.bw.put(0xFFFFu, 16);
+        es->total_bits = sink.bw.bitpos();
+    }
+    es->fw_idx[lane] = sink.bw.first_idx;
+    es->crossed[lane] = sink.bw.crossed ? 1u : 0u;
+    if (sink.bw.crossed) { es->fw_bits[lane] = sink.bw.first_bits; es->tw_bits[lane] = (uint32_t)sink.bw.acc; }
+    else { es->fw_bits[lane] = (uint32_t)sink.bw.acc; es->tw_bits[lane] = 0; }
+}
+
+// words shared by several lanes (and by the window before): the lane that completes a word ORs in what the others left
+FZ_HD void fz_ph_merge_window(FzEmitStateI *st, bool last, uint32_t *out, int lane)
+{
+    FzEmitState *es = &st->es;
+    uint32_t carry = 0;
+    int j = lane - 1;
+    for (; j >= 0; j--) {
+        if (es->crossed[j]) { carry |= es->tw_bits[j]; break; }
+        carry |= es->fw_bits[j];
+    }
+    if (j < 0) carry |= st->carry_in;   // nobody before this lane completed a word: the previous window's bits are still in it
+    if (es->crossed[lane]) out[es->fw_idx[lane]] = es->fw_bits[lane] | carry;
+    if (lane == 31) {
+        const uint32_t tail = es->crossed[31] ? es->tw_bits[31] : (es->fw_bits[31] | carry);
+        if (last) {
+            const uint32_t total_bits = es->total_bits;
+            if (total_bits & 31) out[total_bits >> 5] = tail;
+        } else st->carry_next = tail;
+    }
+}
+
+FZ_HD void fz_ph_advance_window(FzEmitStateI *st, int lane)
+{
+    if (lane != 0) return;
+    uint32_t b = st->base_bits;
+    for (int l = 0; l < 32; l++) b += st->es.lane_bits[l];
+    st->base_bits = b;
+    st->carry_in = st->carry_next;
+}
+
+// Emit one sub-block with its group's code, window by window.  Same contract as fz_emit_subblock_sc; the exact size
+// is known only after the emission (nothing is lost: a stored result ignores what was written to `out`).
+template <class Load16, class LoadByte>
+FZ_HD uint32_t fz_emit_subblock_interleaved(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, const Load16 &ld,
+                                            const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
+{
+    (void)lane;
+    const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
+    if (gc->stored) return stored;
+    FZ_PHASE(if (lane == 0) { st->base_bits = 0; st->carry_in = 0; st->carry_next = 0; st->es.false_marker = 0; st->es.total_bits = 0; });
+    const uint32_t nwin = (n + FZ_IWIN - 1) / FZ_IWIN;
+    for (uint32_t w = 0; w < nwin; w++) {
+        const FzWindowPieceScan<Load16, LoadByte> scan{ld, lb, n, w};
+        const bool first = w == 0, last = w + 1 == nwin;
+        FZ_PHASE(fz_ph_count_window(gc, st, scan, first, lane));
+        FZ_PHASE(fz_ph_emit_window(gc, hdr, st, scan, first, last, out, lane));
+        FZ_PHASE(fz_ph_merge_window(st, last, out, lane));
+        FZ_PHASE(fz_ph_advance_window(st, lane));
+    }
+    const uint32_t total_bytes = st->es.total_bits / 8;
+    if (total_bytes + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
+    FZ_PHASE(fz_ph_check_marker(&st->es, out, total_bytes, lane));
+    if (st->es.false_marker) return stored;
+    return total_bytes;
+}

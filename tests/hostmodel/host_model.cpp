@@ -108,6 +108,60 @@ uint64_t hm_encode_stream(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t 
     return o;
 }
 
+// the same with the window-interleaved piece geometry (fz_emit_subblock_interleaved; not used by the kernels yet)
+uint64_t hm_encode_stream_interleaved(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *nstored)
+{
+    uint64_t o = 0, ns = 0;
+    std::vector<uint8_t> pad(FZ_SUB + 32);
+    std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8);
+    FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
+    FzGroupCode *gc = (FzGroupCode *)malloc(sizeof(FzGroupCode));
+    FzEmitStateI *es = (FzEmitStateI *)malloc(sizeof(FzEmitStateI));
+    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
+    for (uint64_t g0 = 0; g0 < n; g0 += gbytes) {
+        const uint64_t gn = (n - g0) < gbytes ? (n - g0) : gbytes;
+        const uint32_t nsub = (uint32_t)((gn + FZ_SUB - 1) / FZ_SUB);
+        memset(st, 0xCD, sizeof(FzEncState));
+        memset(st->hist, 0, sizeof(st->hist));
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
+            memset(pad.data(), 0, pad.size());
+            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
+            HostLoad16 ld{pad.data()};
+            HostLoadByte lb{pad.data()};
+            uint32_t h[288];
+            memset(h, 0, sizeof(h));
+            for (int lane = 0; lane < 32; lane++) fz_ph_hist_interleaved(h, ld, lb, m, lane);
+            for (int i = 0; i < 288; i++) st->hist[i] += h[i];
+        }
+        st->hist[FZ_EOB] = nsub;
+        memset(gc, 0xEE, sizeof(FzGroupCode));
+        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0);
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
+            memset(pad.data(), 0, pad.size());
+            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
+            HostLoad16 ld{pad.data()};
+            HostLoadByte lb{pad.data()};
+            for (auto &w : slot) w = 0xDEADBEEFu;  // garbage: the encoder must write every word it owns
+            memset(es, 0xAB, sizeof(FzEmitStateI));
+            const uint32_t r = fz_emit_subblock_interleaved(gc, gc->hdr, es, ld, lb, m, slot.data(), 0);
+            if (r & FZ_SIZE_STORED_FLAG) {
+                if (o + fz_stored_size(m) > cap) return (uint64_t)-1;
+                o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
+                ns++;
+            } else {
+                if (o + r > cap) return (uint64_t)-1;
+                memcpy(out + o, slot.data(), r);
+                o += r;
+            }
+        }
+    }
+    free(st); free(gc); free(es);
+    if (nstored) *nstored = ns;
+    return o;
+}
+
 int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_cap, uint32_t *out_n, uint64_t *in_used)
 {
     // word-aligned, padded copies (the device reads whole aligned words; out must be 4-byte aligned)

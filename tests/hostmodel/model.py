@@ -23,6 +23,20 @@ def encode_stream(a: np.ndarray, sub: int = SUB):
     return out[:n].copy(), int(ns.value)
 
 
+_L.hm_encode_stream_interleaved.restype = C.c_uint64
+_L.hm_encode_stream_interleaved.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+
+
+def encode_stream_interleaved(a: np.ndarray):
+    """the window-interleaved piece geometry (fz_emit_subblock_interleaved): not used by the kernels yet"""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    out = np.empty(a.size + (a.size // SUB + 1) * 64 + 64, dtype=np.uint8)
+    ns = C.c_uint64()
+    n = _L.hm_encode_stream_interleaved(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ns))
+    assert n != 2**64 - 1
+    return out[:n].copy(), int(ns.value)
+
+
 def inflate(b: np.ndarray, n_out: int):
     b = np.ascontiguousarray(b, dtype=np.uint8)
     out = np.empty(n_out + 8, dtype=np.uint8)

@@ -167,6 +167,42 @@ def test_model_encoder_streams_inflate_with_zlib(hostmodel, oracle, name):
 
 
 @pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
+def test_model_interleaved_geometry_streams_inflate_with_zlib(hostmodel, oracle, name):
+    """The window-interleaved piece geometry (fz_emit_subblock_interleaved: 64-byte pieces, one window of 32 pieces at
+    a time, no counting pass over the whole sub-block -- DESIGN 9 lead #1, not used by the kernels yet) produces valid
+    raw deflate with the same framing, and costs next to nothing in size except on all-zero input."""
+    a = _plane_cases()[name]
+    c, _ = hostmodel.encode_stream_interleaved(a)
+    d = zlib.decompressobj(-15)
+    assert d.decompress(c.tobytes()) == a.tobytes()
+    assert not d.eof and d.unused_data == b""
+    out, used = oracle.inflate_raw(c, a.size)
+    assert np.array_equal(out, a) and used == c.size
+    assert c[-4:].tobytes() == b"\x00\x00\xff\xff"
+    rc, o, used = hostmodel.inflate(c, a.size)
+    assert rc == 0 and np.array_equal(o, a) and used == c.size
+    c0, _ = hostmodel.encode_stream(a)
+    nsub = a.size // hostmodel.SUB + 1
+    if name == "runs":
+        # the known price: pieces of 64 bytes cut long runs of many different values eight times as often as pieces
+        # of 512 (2.7x the size here) -- such sub-blocks must keep today's geometry (the choice is free per sub-block)
+        assert c.size <= 3.0 * c0.size
+    else:
+        assert c.size <= 1.02 * c0.size + 256 * nsub, (c.size, c0.size)
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 2047, 2048, 2049, 4095, 16383, 16384, 16385, 16384 * 32 + 77])
+def test_model_interleaved_geometry_ragged_sizes(hostmodel, n):
+    rng = np.random.default_rng(n)
+    for a in (rng.choice([0, 0, 0, 1, 2, 255], n).astype(np.uint8), np.zeros(n, np.uint8),
+              rng.integers(0, 256, n).astype(np.uint8), np.repeat(rng.integers(0, 4, n // 40 + 1), 40)[:n].astype(np.uint8)):
+        c, _ = hostmodel.encode_stream_interleaved(a)
+        d = zlib.decompressobj(-15)
+        assert d.decompress(c.tobytes()) == a.tobytes()
+        assert c[-4:].tobytes() == b"\x00\x00\xff\xff"
+
+
+@pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
 def test_model_inflater_on_zlib_streams(hostmodel, name):
     a = _plane_cases()[name]
     for strat, lvl in [(zlib.Z_RLE, 6), (zlib.Z_DEFAULT_STRATEGY, 6), (zlib.Z_FIXED, 6), (zlib.Z_DEFAULT_STRATEGY, 0),
