@@ -943,9 +943,11 @@ FZ_HD void fz_ph_advance_window(FzEmitStateI *st, int lane)
 
 // Emit one sub-block with its group's code, window by window.  Same contract as fz_emit_subblock_sc; the exact size
 // is known only after the emission (nothing is lost: a stored result ignores what was written to `out`).
-template <class Load16, class LoadByte>
-FZ_HD uint32_t fz_emit_subblock_interleaved(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, const Load16 &ld,
-                                            const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
+// `win` supplies the windows: win.enter(w, lane) / win.leave(w, lane) bracket the work on window w (the device stages
+// the 2 KiB there), win.scan(w) is the piece scan of that window.
+template <class Windows>
+FZ_HD uint32_t fz_emit_subblock_iw(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, Windows &win, uint32_t n,
+                                   uint32_t *out, int lane)
 {
     (void)lane;
     const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
@@ -953,16 +955,36 @@ FZ_HD uint32_t fz_emit_subblock_interleaved(const FzGroupCode *gc, const uint32_
     FZ_PHASE(if (lane == 0) { st->base_bits = 0; st->carry_in = 0; st->carry_next = 0; st->es.false_marker = 0; st->es.total_bits = 0; });
     const uint32_t nwin = (n + FZ_IWIN - 1) / FZ_IWIN;
     for (uint32_t w = 0; w < nwin; w++) {
-        const FzWindowPieceScan<Load16, LoadByte> scan{ld, lb, n, w};
         const bool first = w == 0, last = w + 1 == nwin;
-        FZ_PHASE(fz_ph_count_window(gc, st, scan, first, lane));
-        FZ_PHASE(fz_ph_emit_window(gc, hdr, st, scan, first, last, out, lane));
+        FZ_PHASE(win.enter(w, lane));
+        FZ_PHASE(fz_ph_count_window(gc, st, win.scan(w), first, lane));
+        FZ_PHASE(fz_ph_emit_window(gc, hdr, st, win.scan(w), first, last, out, lane));
         FZ_PHASE(fz_ph_merge_window(st, last, out, lane));
         FZ_PHASE(fz_ph_advance_window(st, lane));
+        FZ_PHASE(win.leave(w, lane));
     }
     const uint32_t total_bytes = st->es.total_bits / 8;
     if (total_bytes + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
     FZ_PHASE(fz_ph_check_marker(&st->es, out, total_bytes, lane));
     if (st->es.false_marker) return stored;
     return total_bytes;
+}
+
+// windows behind random-access loaders (the CPU model; ragged or unaligned sub-blocks on the device)
+template <class Load16, class LoadByte>
+struct FzLoaderWindows {
+    const Load16 &ld;
+    const LoadByte &lb;
+    uint32_t n;
+    FZ_HD void enter(uint32_t, int) {}
+    FZ_HD void leave(uint32_t, int) {}
+    FZ_HD FzWindowPieceScan<Load16, LoadByte> scan(uint32_t w) const { return FzWindowPieceScan<Load16, LoadByte>{ld, lb, n, w}; }
+};
+
+template <class Load16, class LoadByte>
+FZ_HD uint32_t fz_emit_subblock_interleaved(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, const Load16 &ld,
+                                            const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
+{
+    FzLoaderWindows<Load16, LoadByte> win{ld, lb, n};
+    return fz_emit_subblock_iw(gc, hdr, st, win, n, out, lane);
 }

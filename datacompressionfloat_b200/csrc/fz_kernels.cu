@@ -472,6 +472,60 @@ struct ZeroLoadByte {
     __device__ __forceinline__ uint32_t operator()(uint32_t) const { return 0; }
 };
 
+#ifdef FZ_INTERLEAVED_PIECES
+// EXPERIMENTAL (lead #1; off by default, never run on a GPU yet): the window-interleaved piece geometry of
+// fz_emit_subblock_iw on the device.  Window w is the 2 KiB [w * 2048, (w + 1) * 2048) of the sub-block, lane l owns its
+// bytes [l * 64, l * 64 + 64): the cp.async fill is plainly coalesced, the rows are the same 80-byte pitch.
+static_assert(FZ_WIN_BYTES == FZ_IPIECE, "the interleaved geometry uses one window row per piece");
+struct FzDevWinScan {
+    const uint8_t *row;   // this lane's 64 bytes
+    int prev;             // the byte before them, -1 at the start of the sub-block
+    template <class Sink>
+    __device__ __forceinline__ void operator()(Sink &sink, int) const
+    {
+        FzScan sc;
+        sc.init(prev);
+#pragma unroll 1
+        for (uint32_t q = 0; q < FZ_IPIECE / 16; q++) {
+            const uint4 v = *(const uint4 *)(row + q * 16);
+            FzVec16 r;
+            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+            sc.group16(r, sink);
+        }
+        sc.finish(sink);
+    }
+};
+struct FzDevWindows {
+    uint8_t *win;         // this warp's FZ_WIN_SMEM bytes (two stages)
+    const uint8_t *src;   // FZ_SUB bytes, 16-byte aligned
+    int prev0;            // last byte of the window before (lane 0's predecessor)
+    int lane_;
+    __device__ __forceinline__ void issue(uint32_t w) const
+    {
+        const uint32_t st = (uint32_t)__cvta_generic_to_shared(win) + (w & 1u) * FZ_WIN_STAGE;
+#pragma unroll
+        for (uint32_t q = 0; q < FZ_IWIN / (16 * FZ_WARP); q++) {
+            const uint32_t c = (uint32_t)lane_ + FZ_WARP * q;   // 16-byte chunk of the window
+            fz_cp_async16(st + (c >> 2) * FZ_WIN_ROW + (c & 3u) * 16u, src + w * FZ_IWIN + c * 16u);
+        }
+        fz_cp_async_commit();
+    }
+    __device__ __forceinline__ void enter(uint32_t w, int)
+    {
+        if (w == 0) issue(0);
+        if (w + 1 < FZ_SUB / FZ_IWIN) { issue(w + 1); fz_cp_async_wait<1>(); }
+        else fz_cp_async_wait<0>();
+        // (the caller's FZ_PHASE synchronises the warp: every lane's copies have landed)
+    }
+    __device__ __forceinline__ const uint8_t *row(uint32_t w, int l) const { return win + (w & 1u) * FZ_WIN_STAGE + l * FZ_WIN_ROW; }
+    __device__ __forceinline__ void leave(uint32_t w, int) { prev0 = (int)row(w, FZ_WARP - 1)[FZ_IPIECE - 1]; }
+    __device__ __forceinline__ FzDevWinScan scan(uint32_t w) const
+    {
+        return FzDevWinScan{row(w, lane_), lane_ ? (int)row(w, lane_ - 1)[FZ_IPIECE - 1] : (w ? prev0 : -1)};
+    }
+};
+#endif
+
 __device__ __forceinline__ const uint8_t *fz_sub_src(const uint8_t *planes, const FzBatchGeom &g, uint32_t s, uint32_t k)
 {
     const uint32_t c = s >> 2, j = s & 3;
@@ -581,6 +635,23 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
         __syncwarp();
     }
     if (lane == 0) sizes[t] = 0;  // to be decided by the emit kernel
+#ifdef FZ_INTERLEAVED_PIECES
+    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
+        FzDevWindows win{sm->win, src, -1, lane};
+        for (uint32_t w = 0; w < FZ_SUB / FZ_IWIN; w++) {
+            win.enter(w, lane);
+            __syncwarp();
+            fz_ph_hist_sc(sm->hist, win.scan(w), lane);
+            __syncwarp();
+            win.leave(w, lane);
+            __syncwarp();
+        }
+    } else {
+        GlobLoad16 ld{src};
+        GlobLoadByte lb{src};
+        fz_ph_hist_interleaved(sm->hist, ld, lb, n, lane);
+    }
+#else
     if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
         fz_ph_hist_sc(sm->hist, FzWindowScan{sm->win, src}, lane);
     } else {
@@ -588,6 +659,7 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
         GlobLoadByte lb{src};
         fz_ph_hist(sm->hist, ld, lb, n, lane);
     }
+#endif
     __syncwarp();
     uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
     for (int i = lane; i < 288; i += 32) {
@@ -642,7 +714,13 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
 struct __align__(16) FzEmitSmem {
     alignas(16) uint8_t win[FZ_WIN_SMEM];
     uint32_t gc_hot[FZ_GROUP_CODE_HOT_BYTES / 4];  // the hot part of the group's FzGroupCode
+#ifdef FZ_INTERLEAVED_PIECES
+    FzEmitStateI esi;
+#define FZ_EMIT_ES(sm_) (&(sm_)->esi.es)
+#else
     FzEmitState es;
+#define FZ_EMIT_ES(sm_) (&(sm_)->es)
+#endif
 };
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
@@ -680,13 +758,26 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     const uint8_t *src = fz_sub_src(planes, g, s, k);
     uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
     uint32_t r;
-    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
-        r = fz_emit_subblock_sc((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, FzWindowScan{sm->win, src}, n, out, lane);
+#ifdef FZ_INTERLEAVED_PIECES
+    if (sz0 & FZ_SIZE_ZERO_FLAG) {   // the leader of the group's all-zero sub-blocks: contiguous pieces, like fz_zero_hist_kernel
+        r = fz_emit_subblock_sc((const FzGroupCode *)sm->gc_hot, ggc->hdr, FZ_EMIT_ES(sm), FzWindowScan{sm->win, src}, n, out, lane);
+    } else if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
+        FzDevWindows win{sm->win, src, -1, lane};
+        r = fz_emit_subblock_iw((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->esi, win, n, out, lane);
     } else {
         GlobLoad16 ld{src};
         GlobLoadByte lb{src};
-        r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->es, ld, lb, n, out, lane);
+        r = fz_emit_subblock_interleaved((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->esi, ld, lb, n, out, lane);
     }
+#else
+    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
+        r = fz_emit_subblock_sc((const FzGroupCode *)sm->gc_hot, ggc->hdr, FZ_EMIT_ES(sm), FzWindowScan{sm->win, src}, n, out, lane);
+    } else {
+        GlobLoad16 ld{src};
+        GlobLoadByte lb{src};
+        r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, FZ_EMIT_ES(sm), ld, lb, n, out, lane);
+    }
+#endif
     if (lane == 0) {
         sizes[t] = r | (sz0 & FZ_SIZE_ZERO_FLAG);
         if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
