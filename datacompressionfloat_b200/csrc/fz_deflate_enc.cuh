@@ -958,6 +958,13 @@ FZ_HD uint32_t fz_emit_subblock_iw(const FzGroupCode *gc, const uint32_t *hdr, F
         const bool first = w == 0, last = w + 1 == nwin;
         FZ_PHASE(win.enter(w, lane));
         FZ_PHASE(fz_ph_count_window(gc, st, win.scan(w), first, lane));
+        {   // Stop as soon as the sub-block cannot beat a stored block any more: nothing beyond the slot is ever
+            // written (a stored block is smaller than FZ_SLOT_STRIDE), and hopeless sub-blocks cost one count.
+            // Every lane reads the same 32 counts, so the decision is uniform.  + 64 bits: end of block and marker.
+            uint32_t tot = st->base_bits;
+            for (int l = 0; l < 32; l++) tot += st->es.lane_bits[l];
+            if ((tot + 64u) / 8u + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
+        }
         FZ_PHASE(fz_ph_emit_window(gc, hdr, st, win.scan(w), first, last, out, lane));
         FZ_PHASE(fz_ph_merge_window(st, last, out, lane));
         FZ_PHASE(fz_ph_advance_window(st, lane));

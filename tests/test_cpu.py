@@ -191,6 +191,20 @@ def test_model_interleaved_geometry_streams_inflate_with_zlib(hostmodel, oracle,
         assert c.size <= 1.02 * c0.size + 256 * nsub, (c.size, c0.size)
 
 
+def test_model_interleaved_geometry_incompressible_subblock_in_a_coded_group(hostmodel):
+    """One sub-block of random bytes among compressible ones: the group is coded, that sub-block must come out stored
+    -- and its emission must stop before it could run past its 16 KiB slot (the size is only known window by window)."""
+    rng = np.random.default_rng(5)
+    sub = hostmodel.SUB
+    a = rng.choice([1, 2, 3, 4], 12 * sub).astype(np.uint8)
+    a[5 * sub: 6 * sub] = rng.integers(0, 256, sub)
+    a[9 * sub + 100: 10 * sub] = rng.integers(0, 256, sub - 100)    # compressible start, hopeless rest
+    c, nstored = hostmodel.encode_stream_interleaved(a)
+    assert nstored == 2
+    d = zlib.decompressobj(-15)
+    assert d.decompress(c.tobytes()) == a.tobytes()
+
+
 @pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 2047, 2048, 2049, 4095, 16383, 16384, 16385, 16384 * 32 + 77])
 def test_model_interleaved_geometry_ragged_sizes(hostmodel, n):
     rng = np.random.default_rng(n)
