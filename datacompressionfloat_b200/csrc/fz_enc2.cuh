@@ -1,0 +1,513 @@
+// fz_enc2.cuh -- the warp-interleaved, single-pass deflate encoder for ONE sub-block (<= FZ_SUB bytes) of a byte plane.
+//
+// Same contract as fz_deflate_enc.cuh (what the reference gets from zlib's deflate(Z_RLE, level 6) behind mzlib_def,
+// reference zip.c:164-196): distance-1 run matches of 3..258 bytes, one dynamic-Huffman block with the group's code,
+// then an empty stored block (the sync-flush marker).  What changed is HOW the 32 lanes of the warp share the work:
+//
+//   * step geometry: in step s lane l owns the 16 bytes [s*512 + l*16, +16) of the sub-block.  The warp reads 512
+//     contiguous bytes per step (one coalesced 128-bit load per lane, no staging), and the token order is simply
+//     the byte order -- there are no piece boundaries inside a sub-block any more.
+//   * the run tokeniser is data parallel and works on aligned quads of 4 bytes: a quad is "held" (part of a distance-1
+//     match) when its bytes and the quad before it repeat one byte; one shuffle brings the neighbour's flag, one
+//     ballot the lanes whose four quads are all held, and that is all the cross-lane traffic a run needs.  Runs are
+//     therefore multiples of 4 bytes at multiples of 4: a lane's output is four slots, each either the codes of
+//     four literals or one match token -- the same instructions either way.
+//   * ONE pass: every lane looks its 16 codes up, a warp prefix sum over the lanes' bit counts gives each lane its
+//     bit offset, and the bits are ORed into a 2 KiB ring in shared memory (shared-memory atomics: neighbouring
+//     lanes share words).  Completed 16-byte vectors leave the ring as coalesced 128-bit stores, and are checked
+//     for a chance occurrence of the sync marker on the way out.  The counting pass of the first encoder (a full
+//     second tokenisation of the sub-block) and its cp.async window are gone.
+//
+// The code is written against a tiny warp interface (shuffle, ballot, shared-memory atomics) so that the very same
+// source runs on the CPU in tests/hostmodel (32 host threads in lock step) and is checked there against zlib and
+// against a plain sequential restatement of the token rule.
+#pragma once
+#include "fz_deflate_enc.cuh"
+
+#if !defined(__CUDA_ARCH__)
+#include <pthread.h>
+#endif
+
+FZ_HD uint32_t fz_popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+FZ_HD uint32_t fz_clz32(uint32_t v)  // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)v);
+#else
+    return (uint32_t)__builtin_clz(v);
+#endif
+}
+
+// ---- the warp interface ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+struct FzWarp {
+    int lane;
+    FZ_D uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    FZ_D uint32_t shfl_up(uint32_t v, int d) const { return __shfl_up_sync(0xffffffffu, v, d); }
+    FZ_D uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    FZ_D void sync() const { __syncwarp(); }
+    FZ_D void atom_or(uint32_t *p, uint32_t v) const { atomicOr(p, v); }
+    FZ_D void atom_add(uint32_t *p, uint32_t v) const { atomicAdd(p, v); }
+};
+#else
+// host model: 32 threads, every collective is a pair of barriers around an exchange array
+struct FzWarpShared {
+    pthread_barrier_t bar;
+    uint32_t x[32];
+};
+struct FzWarp {
+    int lane;
+    FzWarpShared *sh;
+    void wait() const { pthread_barrier_wait(&sh->bar); }
+    uint32_t shfl(uint32_t v, int src) const
+    {
+        sh->x[lane] = v; wait();
+        const uint32_t r = sh->x[src & 31]; wait();
+        return r;
+    }
+    uint32_t shfl_up(uint32_t v, int d) const
+    {
+        sh->x[lane] = v; wait();
+        const uint32_t r = lane >= d ? sh->x[lane - d] : v; wait();
+        return r;
+    }
+    uint32_t ballot(bool p) const
+    {
+        sh->x[lane] = p ? 1u : 0u; wait();
+        uint32_t r = 0;
+        for (int i = 0; i < 32; i++) r |= sh->x[i] << i;
+        wait();
+        return r;
+    }
+    void sync() const { wait(); }
+    void atom_or(uint32_t *p, uint32_t v) const { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+    void atom_add(uint32_t *p, uint32_t v) const { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+};
+#endif
+
+template <class W>
+FZ_HD uint32_t fz_warp_incl_sum(const W &w, uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = w.shfl_up(v, d);
+        if (w.lane >= d) v += o;
+    }
+    return v;
+}
+
+// ---- the tokeniser -------------------------------------------------------------------------------------------------
+// Token rule (sequential definition; seq_tokens in tests/hostmodel restates it quad by quad):
+//   the sub-block is cut into aligned quads of 4 bytes.  E[q] = the four bytes of quad q all equal the byte before
+//   them (E = 0 for the first quad, which has no byte before it, and for a ragged last quad of fewer than 4 bytes).
+//   Quad q is HELD iff E[q] and E[q-1]: its bytes continue a run that is at least 5 bytes long already.  Every byte
+//   outside a held quad is a literal.  A maximal run of held quads leaves as distance-1 matches: one of 256 bytes at
+//   every 64th quad of the run, and one of 4 * (count mod 64) bytes at its last quad.  Tokens leave in byte order.
+// (The first encoder withheld bytes one by one; quads make a lane's output four uniform slots, cost nothing measurable
+//  on float planes -- tools/token_rule_study.py -- and let an inflater copy runs as whole words.)
+#define FZ_E2_MAX_QUADS 64u    // 256 bytes: the longest match the encoder writes
+
+// what the warp carries from step to step (the same value in every lane)
+struct FzTokCarry {
+    uint32_t prev;     // last byte of the step before; 0x100 = none (start of the sub-block)
+    uint32_t prevE;    // E of its last quad
+    uint32_t m;        // held quads pending (0..63)
+    FZ_HD void init() { prev = 0x100u; prevE = 0; m = 0; }
+};
+
+// this lane's four quads, tokenised
+struct FzTok {
+    uint32_t hq;      // bit 4g: quad g is held
+    uint32_t m_in;    // held quads pending in front of quad 0 (0..63)
+};
+
+// 16 equality flags of v against the byte before each byte (`before` = byte before byte 0)
+FZ_HD uint32_t fz_eq_flags(const FzVec16 &v, uint32_t before)
+{
+    uint32_t eq = 0;
+    uint32_t b = before << 24;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t x = v.w[j] ^ ((v.w[j] << 8) | (b >> 24));
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
+        eq |= ((z * 0x00204081u) >> 28) << (4 * j);
+        b = v.w[j];
+    }
+    return eq;
+}
+
+// bit k: byte k of v equals the byte splatted in `splat4` (b * 0x01010101)
+FZ_HD uint32_t fz_byte_eq_mask(const FzVec16 &v, uint32_t splat4)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t x = v.w[j] ^ splat4;
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        m |= ((z * 0x00204081u) >> 28) << (4 * j);
+    }
+    return m;
+}
+
+FZ_HD void fz_store_vec16(uint32_t *p, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3)
+{
+#if defined(__CUDA_ARCH__)
+    *(uint4 *)p = make_uint4(x0, x1, x2, x3);
+#else
+    p[0] = x0; p[1] = x1; p[2] = x2; p[3] = x3;
+#endif
+}
+
+// Tokenise one step.  nv = valid bytes of this lane (0..16; < 16 only in the ragged last step of a short sub-block).
+// Returns true (in every lane) when the step has runs to book-keep (t.hq / t.m_in say which); otherwise every valid
+// byte is a literal.  `c` is advanced.
+template <class W>
+FZ_HD bool fz_tok_step(const W &w, const FzVec16 &v, uint32_t nv, FzTokCarry &c, FzTok &t)
+{
+    const int lane = w.lane;
+    const uint32_t lastb = v.w[3] >> 24;
+    uint32_t pb = w.shfl_up(lastb, 1);
+    if (lane == 0) pb = c.prev;
+    uint32_t eq = fz_eq_flags(v, pb & 0xffu);
+    if (pb > 0xffu) eq &= ~1u;                       // no byte before the sub-block
+    uint32_t E = eq & (eq >> 1);
+    E &= E >> 2;
+    E &= 0x1111u & ((1u << (nv & ~3u)) - 1u);        // bit 4g: quad g is whole and repeats the byte before it
+    uint32_t pE = w.shfl_up(E >> 12, 1);
+    if (lane == 0) pE = c.prevE;
+    const uint32_t hq = E & ((E << 4) | pE);
+    t.hq = hq;
+    t.m_in = 0;
+    const uint32_t anyh = w.ballot(hq != 0);
+    const uint32_t m0 = c.m;
+    c.prev = w.shfl(lastb, 31);
+    c.prevE = w.shfl(E >> 12, 31);
+    if (anyh == 0 && m0 == 0) return false;
+    // ---- runs.  A lane "passes" when its four quads are held: the run goes through it.
+    const bool passes = hq == 0x1111u;
+    const uint32_t B = w.ballot(passes);
+    // held quads at the top of a lane that does not pass: what it hands to the next lane
+    const uint32_t top = (hq & 0x1000u) ? ((hq & 0x0100u) ? ((hq & 0x0010u) ? 3u : 2u) : 1u) : 0u;
+    const uint32_t below = ~B & ((1u << lane) - 1u);          // lanes before this one that do not pass
+    const int j = below ? 31 - (int)fz_clz32(below) : 0;
+    const uint32_t tj = w.shfl(top, j);
+    const uint32_t m = (below ? tj + 4u * (uint32_t)(lane - 1 - j) : m0 + 4u * (uint32_t)lane) & (FZ_E2_MAX_QUADS - 1u);
+    t.m_in = m;
+    c.m = w.shfl(passes ? ((m + 4u) & (FZ_E2_MAX_QUADS - 1u)) : top, 31);
+    return true;
+}
+
+// the run tokens of a tokenised lane, as lengths in quads (0 = none): tin = in front of quad 0 (the run ended with the
+// lane before), tl[g] = at held quad g
+FZ_HD void fz_tok_lens(const FzTok &t, uint32_t &tin, uint32_t tl[4])
+{
+    uint32_t cnt = t.m_in;
+    tin = (t.hq & 1u) ? 0u : cnt;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        tl[g] = 0;
+        if ((t.hq >> (4 * g)) & 1u) {
+            cnt = (cnt + 1u) & (FZ_E2_MAX_QUADS - 1u);
+            const bool more = g < 3 ? ((t.hq >> (4 * g + 4)) & 1u) != 0 : true;   // quad 3: the next lane knows
+            if (cnt == 0) tl[g] = FZ_E2_MAX_QUADS;
+            else if (!more) tl[g] = cnt;
+        } else cnt = 0;
+    }
+}
+
+// the bits of a match of 4 * nq bytes at distance 1: bits | nbits << 24 (<= 21 bits).  cl[] = code | len << 16.
+FZ_HD uint32_t fz_run_token(const uint32_t *cl, uint32_t nq)
+{
+    uint32_t lc, eb, ev;
+    fz_len_code(4u * nq, lc, eb, ev);
+    const uint32_t e = cl[257 + lc];
+    return (e & 0xffffu) | (ev << (e >> 16)) | (((e >> 16) + eb + 1u) << 24);   // length code, extra bits, 1-bit distance code '0'
+}
+
+// ---- histogram of one sub-block's tokens -------------------------------------------------------------------------
+// hist[288] (this warp's, zeroed).  skip1 / skip2: byte values counted in registers instead of shared memory (the two
+// most frequent bytes of the sub-block's sample: same-address shared atomics serialise, and on exponent planes two
+// values are most of the plane); 0x100 = none.
+template <class W, class Load16>
+FZ_HD void fz_hist2_subblock(const W &w, uint32_t *hist, const Load16 &ld, uint32_t n, uint32_t skip1, uint32_t skip2)
+{
+    const int lane = w.lane;
+    FzTokCarry c;
+    c.init();
+    uint32_t n1 = 0, n2 = 0;
+    const uint32_t nsteps = (n + 511u) / 512u;
+    const uint32_t s1 = (skip1 & 0xffu) * 0x01010101u, s2 = (skip2 & 0xffu) * 0x01010101u;
+    FzVec16 v;
+    v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0;
+    if ((uint32_t)lane * 16u < n) v = ld((uint32_t)lane * 16u);
+    for (uint32_t s = 0; s < nsteps; s++) {
+        const uint32_t pos = s * 512u + (uint32_t)lane * 16u;
+        const uint32_t nv = n > pos ? (n - pos < 16u ? n - pos : 16u) : 0u;
+        FzVec16 vn;
+        vn.w[0] = vn.w[1] = vn.w[2] = vn.w[3] = 0;
+        if (pos + 512u < n) vn = ld(pos + 512u);
+        FzTok t;
+        const bool slow = fz_tok_step(w, v, nv, c, t);
+        uint32_t lit = ((1u << nv) - 1u) & ~(t.hq * 15u);
+        if (skip1 < 0x100u) {
+            const uint32_t m1 = fz_byte_eq_mask(v, s1) & lit;
+            n1 += fz_popc32(m1);
+            lit &= ~m1;
+        }
+        if (skip2 < 0x100u) {
+            const uint32_t m2 = fz_byte_eq_mask(v, s2) & lit;
+            n2 += fz_popc32(m2);
+            lit &= ~m2;
+        }
+        if (lit == 0xffffu) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) w.atom_add(&hist[FZ_BYTE_OF(v, k)], 1u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if ((lit >> k) & 1u) w.atom_add(&hist[FZ_BYTE_OF(v, k)], 1u);
+        }
+        if (slow) {
+            uint32_t tin, tl[4];
+            fz_tok_lens(t, tin, tl);
+#pragma unroll
+            for (int g = -1; g < 4; g++) {
+                const uint32_t nq = g < 0 ? tin : tl[g < 0 ? 0 : g];
+                if (nq) {
+                    uint32_t lc, eb, ev;
+                    fz_len_code(4u * nq, lc, eb, ev);
+                    w.atom_add(&hist[257 + lc], 1u);
+                }
+            }
+        }
+        v = vn;
+    }
+    if (lane == 0 && c.m) {   // the run that reaches the end of the sub-block
+        uint32_t lc, eb, ev;
+        fz_len_code(4u * c.m, lc, eb, ev);
+        w.atom_add(&hist[257 + lc], 1u);
+    }
+    if (n1) w.atom_add(&hist[skip1 & 0xffu], n1);
+    if (n2) w.atom_add(&hist[skip2 & 0xffu], n2);
+    w.sync();
+}
+
+// ---- emission ------------------------------------------------------------------------------------------------------
+#define FZ_E2_RING_WORDS 512u                      // 2 KiB: < 33 vectors waiting + at most 32 x (16 x 15 + 21) bits of a step
+#define FZ_E2_RING_MASK (FZ_E2_RING_WORDS - 1u)
+#define FZ_E2_FLUSH_VECS 32u                       // vectors leave the ring 32 at a time (one per lane)
+
+// <= 32 bits at bit offset `off` of the ring
+template <class W>
+FZ_HD void fz_ring_put32(const W &w, uint32_t *ring, uint32_t off, uint32_t bits, uint32_t nbits)
+{
+    const uint32_t s = off & 31u, wi = (off >> 5) & FZ_E2_RING_MASK;
+    w.atom_or(&ring[wi], bits << s);
+    if (s + nbits > 32u) w.atom_or(&ring[(wi + 1u) & FZ_E2_RING_MASK], bits >> (32u - s));
+}
+
+// <= 64 bits
+template <class W>
+FZ_HD void fz_ring_put64(const W &w, uint32_t *ring, uint32_t off, uint64_t bits, uint32_t nbits)
+{
+    const uint32_t s = off & 31u, wi = off >> 5;
+    const uint64_t lo = bits << s;
+    w.atom_or(&ring[wi & FZ_E2_RING_MASK], (uint32_t)lo);
+    if (s + nbits > 32u) w.atom_or(&ring[(wi + 1u) & FZ_E2_RING_MASK], (uint32_t)(lo >> 32));
+    if (s + nbits > 64u) w.atom_or(&ring[(wi + 2u) & FZ_E2_RING_MASK], (uint32_t)(bits >> (64u - s)));
+}
+
+// Does the 20-byte window prev | v show 00 00 FF FF at byte offsets 1..16 (i.e. ending inside v)?  bit o - 1 of the result.
+FZ_HD uint32_t fz_marker_in20(uint32_t prev, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3)
+{
+    const uint32_t a[5] = {prev, x0, x1, x2, x3};
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint32_t x = ~a[k];
+        any |= (x - 0x01010101u) & ~x & 0x80808080u;          // non-zero iff a[k] has an FF byte
+    }
+    if (any == 0) return 0;
+    uint32_t F = 0, Z = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        uint32_t x = ~a[k];
+        uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        F |= ((z * 0x00204081u) >> 28) << (4 * k);
+        x = a[k];
+        z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        Z |= ((z * 0x00204081u) >> 28) << (4 * k);
+    }
+    return ((Z & (Z >> 1) & (F >> 2) & (F >> 3)) >> 1) & 0xffffu;
+}
+
+// the ring's flush state (the same in every lane)
+struct FzRingOut {
+    uint32_t *ring;
+    uint32_t *out;        // the fragment's slot in global memory, 16-byte aligned
+    uint32_t vdone;       // 16-byte vectors already written to `out`
+    uint32_t tailw;       // the last word written (what a marker window may start in)
+    uint32_t bad;         // this lane saw the sync marker somewhere it must not be
+    FZ_HD void init(uint32_t *r, uint32_t *o) { ring = r; out = o; vdone = 0; tailw = 0x55555555u; bad = 0; }
+
+    // vectors [vdone, vend) leave the ring.  total_bytes != 0: the fragment ends there (its last four bytes are the one
+    // marker that is supposed to be there).
+    template <class W>
+    FZ_HD void flush(const W &w, uint32_t vend, uint32_t total_bytes)
+    {
+        for (uint32_t base = vdone; base < vend; base += 32u) {
+            const uint32_t vi = base + (uint32_t)w.lane;
+            const bool act = vi < vend;
+            uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+            if (act) {
+                uint32_t *p = ring + ((vi * 4u) & FZ_E2_RING_MASK);
+                x0 = p[0]; x1 = p[1]; x2 = p[2]; x3 = p[3];
+                p[0] = 0; p[1] = 0; p[2] = 0; p[3] = 0;
+                fz_store_vec16(out + (size_t)vi * 4u, x0, x1, x2, x3);
+            }
+            uint32_t pw = w.shfl_up(x3, 1);
+            if (w.lane == 0) pw = tailw;
+            if (act) {
+                uint32_t m = fz_marker_in20(pw, x0, x1, x2, x3);
+                if (m && total_bytes) {
+                    // window o (1..16) starts at byte 16 vi - 4 + o; only starts below total_bytes - 4 count
+                    const int64_t lim = (int64_t)total_bytes - 1 - (int64_t)vi * 16;   // number of counted windows
+                    if (lim <= 0) m = 0;
+                    else if (lim < 16) m &= (1u << lim) - 1u;
+                }
+                if (m) bad = 1;
+            }
+            const uint32_t last = vend - base < 32u ? vend - base - 1u : 31u;
+            tailw = w.shfl(x3, (int)last);
+        }
+        if (vend > vdone) vdone = vend;
+        w.sync();
+    }
+};
+
+// Emit one sub-block with its group's code.  Returns the fragment size in bytes, or fz_stored_size(n) |
+// FZ_SIZE_STORED_FLAG when a stored block is the better (or the only safe) choice; then what was written to `out` is
+// ignored (the gather kernel synthesises stored blocks from the plane bytes).
+//   cl[288]   the group's code table (code | len << 16), in shared memory on the device
+//   hdr       the group's block header (hdr_nbits bits)
+//   ring      FZ_E2_RING_WORDS words of this warp (any content)
+//   tt        64 words of this warp: filled here with the group's run tokens (fz_run_token)
+//   out       FZ_SLOT_STRIDE bytes, 16-byte aligned
+template <class W, class Load16>
+FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t *hdr, uint32_t hdr_nbits, uint32_t *ring,
+                                 uint32_t *tt, const Load16 &ld, uint32_t n, uint32_t *out)
+{
+    const int lane = w.lane;
+    const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
+    const uint32_t limit = fz_stored_size(n) - (n >> FZ_MIN_GAIN_SHIFT);   // a coded fragment must stay below this many bytes
+    if ((hdr_nbits >> 3) + 5u >= limit) return stored;
+    for (uint32_t i = lane; i < FZ_E2_RING_WORDS; i += 32u) ring[i] = 0;
+    tt[lane] = fz_run_token(cl, (uint32_t)lane + 1u);
+    tt[lane + 32] = fz_run_token(cl, (uint32_t)lane + 33u);
+    w.sync();
+    {   // the block header (<= 160 words)
+        const uint32_t nw = (hdr_nbits + 31u) >> 5;
+        for (uint32_t i = lane; i < nw; i += 32u) {
+            uint32_t x = hdr[i];
+            if (i == nw - 1u && (hdr_nbits & 31u)) x &= (1u << (hdr_nbits & 31u)) - 1u;
+            ring[i] = x;
+        }
+        w.sync();
+    }
+    FzRingOut ro;
+    ro.init(ring, out);
+    uint32_t P = hdr_nbits;                          // bits emitted so far
+    ro.flush(w, P >> 7, 0);
+
+    FzTokCarry c;
+    c.init();
+    const uint32_t nsteps = (n + 511u) / 512u;
+    FzVec16 v;
+    v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0;
+    if ((uint32_t)lane * 16u < n) v = ld((uint32_t)lane * 16u);
+    for (uint32_t s = 0; s < nsteps; s++) {
+        const uint32_t pos = s * 512u + (uint32_t)lane * 16u;
+        const uint32_t nv = n > pos ? (n - pos < 16u ? n - pos : 16u) : 0u;
+        FzVec16 vn;
+        vn.w[0] = vn.w[1] = vn.w[2] = vn.w[3] = 0;
+        if (pos + 512u < n) vn = ld(pos + 512u);
+        FzTok t;
+        const bool slow = fz_tok_step(w, v, nv, c, t);
+        uint32_t e[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) e[k] = cl[FZ_BYTE_OF(v, k)];
+        if (nv != 16u) {   // the ragged last step of a short sub-block
+#pragma unroll
+            for (int k = 0; k < 16; k++) if ((uint32_t)k >= nv) e[k] = 0;
+        }
+        // four slots: the codes of four literals each ...
+        uint64_t qv[4];
+        uint32_t ql[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t e0 = e[4 * g], e1 = e[4 * g + 1], e2 = e[4 * g + 2], e3 = e[4 * g + 3];
+            const uint32_t l0 = e0 >> 16, l2 = e2 >> 16;
+            const uint32_t p0 = (e0 & 0xffffu) | ((e1 & 0xffffu) << l0), pl0 = l0 + (e1 >> 16);
+            const uint32_t p1 = (e2 & 0xffffu) | ((e3 & 0xffffu) << l2), pl1 = l2 + (e3 >> 16);
+            qv[g] = (uint64_t)p0 | ((uint64_t)p1 << pl0);
+            ql[g] = pl0 + pl1;
+        }
+        uint32_t tinb = 0, tinl = 0;
+        if (slow) {   // ... or, for a held quad, its run token (if a run ends or reaches 256 bytes there) or nothing
+            uint32_t tin, tl[4];
+            fz_tok_lens(t, tin, tl);
+            if (tin) { const uint32_t x = tt[tin - 1u]; tinb = x & 0xffffffu; tinl = x >> 24; }
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                if ((t.hq >> (4 * g)) & 1u) {
+                    const uint32_t x = tl[g] ? tt[tl[g] - 1u] : 0u;
+                    qv[g] = x & 0xffffffu;
+                    ql[g] = x >> 24;
+                }
+        }
+        const uint32_t tot = tinl + ql[0] + ql[1] + ql[2] + ql[3];
+        const uint32_t inc = fz_warp_incl_sum(w, tot);
+        uint32_t off = P + inc - tot;
+        if (tinl) { fz_ring_put32(w, ring, off, tinb, tinl); off += tinl; }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (ql[g]) fz_ring_put64(w, ring, off, qv[g], ql[g]);
+            off += ql[g];
+        }
+        P += w.shfl(inc, 31);
+        w.sync();
+        if ((P >> 3) + 5u >= limit) return stored;   // cannot beat a stored block any more (and must not outgrow the slot)
+        if ((P >> 7) - ro.vdone >= FZ_E2_FLUSH_VECS) ro.flush(w, P >> 7, 0);
+        v = vn;
+    }
+    // ---- the run that reaches the end of the sub-block, end of block, the empty stored block
+    if (lane == 0) {
+        uint32_t off = P;
+        if (c.m) {
+            const uint32_t x = tt[c.m - 1u];
+            fz_ring_put32(w, ring, off, x & 0xffffffu, x >> 24);
+            off += x >> 24;
+        }
+        fz_ring_put32(w, ring, off, cl[FZ_EOB] & 0xffffu, cl[FZ_EOB] >> 16);
+        off += cl[FZ_EOB] >> 16;
+        off += 3u;                                   // BFINAL = 0, BTYPE = 00
+        off = (off + 7u) & ~7u;
+        fz_ring_put32(w, ring, off, 0xFFFF0000u, 32u);   // LEN = 0, NLEN = 0xFFFF
+        off += 32u;
+        P = off;
+    }
+    P = w.shfl(P, 0);
+    w.sync();
+    const uint32_t total = P >> 3;
+    if (total >= limit) return stored;
+    ro.flush(w, (P + 127u) >> 7, total);
+    if (w.ballot(ro.bad != 0)) return stored;
+    return total;
+}

@@ -10,8 +10,10 @@
 // No tensor cores: nothing here is a contraction.  Integer / byte work only.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fz_deflate_enc.cuh"
+#include "fz_enc2.cuh"
 #include "fz_inflate.cuh"
 #include "fz_kernels.h"
 
@@ -784,10 +786,208 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     }
 }
 
+
+// =================================================================================================
+// encoder v2 (fz_enc2.cuh): warp-interleaved steps, one pass, coalesced loads and stores
+// =================================================================================================
+struct GlobVec16 {   // 16-byte aligned source: one streaming 128-bit load per lane, 512 contiguous bytes per warp
+    const uint8_t *src;
+    __device__ __forceinline__ FzVec16 operator()(uint32_t i) const
+    {
+        const uint4 v = fz_ld_stream((const uint4 *)(src + i));
+        FzVec16 r;
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        return r;
+    }
+};
+
+// most frequent byte of a 256-bin histogram, ignoring `skip`: count << 8 | byte (warp-wide)
+__device__ __forceinline__ uint32_t fz_warp_hist_mode(const uint32_t *hist, uint32_t skip, int lane)
+{
+    uint32_t best = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t b = (uint32_t)lane * 8u + (uint32_t)i;
+        const uint32_t key = b == skip ? 0u : ((hist[b] << 8) | b);
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o > best ? o : best;
+    }
+    return best;
+}
+
+#define FZ_HIST2_SKIP_MIN 160u   // of 2048 sample bytes: below ~8 % a private counter costs more than the conflicts it saves
+
+__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
+fz_hist2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist, uint32_t *__restrict__ sizes,
+                const uint32_t *__restrict__ zero_hist, uint32_t zero_planes, uint64_t zero_from, FzStatus *status)
+{
+    __shared__ uint32_t hist_sh[FZ_ENC_WARPS][288];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
+    if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
+    uint32_t s, k, n;
+    if (!fz_slot(g, t, s, k, n)) return;
+    uint32_t *hist = hist_sh[warp];
+    const uint8_t *src = fz_sub_src(planes, g, s, k);
+    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+    if (n == FZ_SUB && ((zero_planes >> (s & 3u)) & 1u) && (uint64_t)(s >> 2) * g.chk + (uint64_t)k * FZ_SUB >= zero_from) {
+        // the mask erases this whole byte plane (8 or more bits erased) and the sub-block lies behind the exempt
+        // header words: 16 KiB of zeros, known without reading them
+        if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
+        for (int i = lane; i < 288; i += 32) {
+            const uint32_t v = zero_hist[i];
+            if (v) atomicAdd(gh + i, v);
+        }
+        return;
+    }
+    for (int i = lane; i < 288; i += 32) hist[i] = 0;
+    __syncwarp();
+    uint32_t skip1 = 0x100u, skip2 = 0x100u;
+    const bool aligned = n == FZ_SUB && ((uintptr_t)src & 15u) == 0;
+    if (aligned) {
+        // ---- sample pass: 64 bytes out of every 512 (2 KiB in all)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = *(const uint4 *)(src + lane * (FZ_SUB / 32) + 16 * q);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int b = 0; b < 16; b++) atomicAdd(&hist[(w[b >> 2] >> ((b & 3) * 8)) & 0xffu], 1u);
+        }
+        __syncwarp();
+        float acc = 0.f;
+        for (int i = lane; i < 256; i += 32) {
+            const float f = (float)hist[i];
+            if (f > 0.f) acc += f * __log2f(f);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        const float bits = 11.f - acc * (1.f / 2048.f);  // log2(2048) - sum f log2 f / N
+        if (bits > FZ_SAMPLE_BITS) {
+            if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
+            return;
+        }
+        if (hist[0] == 2048u) {
+            // The sample is all zeros: one OR over the 16 KiB settles whether the sub-block is; then its tokens are known
+            // without scanning (zero_hist, made once by fz_zero_hist_kernel with this very tokeniser), and the emit kernel
+            // encodes only the first zero sub-block of each group -- the others are copies of its fragment.
+            uint32_t any = 0;
+#pragma unroll 4
+            for (uint32_t i = lane * 16; i < FZ_SUB; i += FZ_WARP * 16) {
+                const uint4 v = *(const uint4 *)(src + i);
+                any |= v.x | v.y | v.z | v.w;
+            }
+            if (!__any_sync(0xffffffffu, any != 0)) {
+                if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
+                for (int i = lane; i < 288; i += 32) {
+                    const uint32_t v = zero_hist[i];
+                    if (v) atomicAdd(gh + i, v);
+                }
+                return;
+            }
+        }
+        // the two most frequent bytes of the sample are counted in registers (same-address shared atomics serialise)
+        const uint32_t m1 = fz_warp_hist_mode(hist, 0x100u, lane);
+        if ((m1 >> 8) >= FZ_HIST2_SKIP_MIN) {
+            skip1 = m1 & 0xffu;
+            const uint32_t m2 = fz_warp_hist_mode(hist, skip1, lane);
+            if ((m2 >> 8) >= FZ_HIST2_SKIP_MIN) skip2 = m2 & 0xffu;
+        }
+        __syncwarp();
+        for (int i = lane; i < 288; i += 32) hist[i] = 0;
+        __syncwarp();
+    }
+    if (lane == 0) sizes[t] = 0;  // to be decided by the emit kernel
+    const FzWarp w{lane};
+    if (aligned) fz_hist2_subblock(w, hist, GlobVec16{src}, n, skip1, skip2);
+    else fz_hist2_subblock(w, hist, GlobLoad16{src}, n, skip1, skip2);
+    for (int i = lane; i < 288; i += 32) {
+        const uint32_t v = hist[i];
+        if (v) atomicAdd(gh + i, v);
+    }
+}
+
+__global__ void __launch_bounds__(FZ_WARP)
+fz_zero_hist2_kernel(uint32_t *__restrict__ zero_hist)
+{
+    __shared__ uint32_t hist[288];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 288; i += 32) hist[i] = 0;
+    __syncwarp();
+    const FzWarp w{lane};
+    fz_hist2_subblock(w, hist, ZeroLoad16{}, FZ_SUB, 0x100u, 0x100u);
+    for (int i = lane; i < 288; i += 32) zero_hist[i] = hist[i];
+}
+
+struct __align__(16) FzEmit2Smem {
+    uint32_t ring[FZ_E2_RING_WORDS];
+    uint32_t gc_hot[FZ_GROUP_CODE_HOT_BYTES / 4];
+    uint32_t tt[FZ_E2_MAX_QUADS];   // the group's run tokens
+};
+
+__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
+fz_emit2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupCode *__restrict__ gcodes,
+                uint8_t *__restrict__ scratch, uint32_t *__restrict__ sizes, FzStatus *status)
+{
+    __shared__ FzEmit2Smem smem[FZ_ENC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
+    if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
+    uint32_t s, k, n;
+    if (!fz_slot(g, t, s, k, n)) return;
+    const uint32_t sz0 = sizes[t];
+    if (sz0 & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
+    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
+    if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to emit
+        if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
+        return;
+    }
+    if (sz0 & FZ_SIZE_ZERO_FLAG) {
+        // all-zero sub-blocks of a group are the same bytes coded with the same code: only the first one is encoded,
+        // the layout kernel gives the others its size and the gather kernel copies its fragment
+        const uint32_t kb = k & ~(uint32_t)(FZ_GROUP_SUBS - 1);
+        const uint32_t other = (kb + lane < g.nsub_full) ? sizes[t - (k - kb) + lane] : 0u;
+        const uint32_t zmask = __ballot_sync(0xffffffffu, (other & FZ_SIZE_ZERO_FLAG) != 0);
+        if ((uint32_t)(__ffs((int)zmask) - 1) != k - kb) return;
+    }
+    FzEmit2Smem *sm = &smem[warp];
+    {
+        const uint32_t *src = (const uint32_t *)ggc;
+        for (uint32_t i = lane; i < FZ_GROUP_CODE_HOT_BYTES / 4; i += 32) sm->gc_hot[i] = src[i];
+    }
+    __syncwarp();
+    const uint8_t *src = fz_sub_src(planes, g, s, k);
+    uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
+    const FzGroupCode *hot = (const FzGroupCode *)sm->gc_hot;
+    const FzWarp w{lane};
+    uint32_t r;
+    if (sz0 & FZ_SIZE_ZERO_FLAG) r = fz_emit2_subblock(w, hot->cl, ggc->hdr, hot->hdr_nbits, sm->ring, sm->tt, ZeroLoad16{}, n, out);
+    else if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) r = fz_emit2_subblock(w, hot->cl, ggc->hdr, hot->hdr_nbits, sm->ring, sm->tt, GlobVec16{src}, n, out);
+    else r = fz_emit2_subblock(w, hot->cl, ggc->hdr, hot->hdr_nbits, sm->ring, sm->tt, GlobLoad16{src}, n, out);
+    if (lane == 0) {
+        sizes[t] = r | (sz0 & FZ_SIZE_ZERO_FLAG);
+        if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
+    }
+}
+
 size_t fz_encode_smem_bytes() { return sizeof(FzEmitSmem) * FZ_ENC_WARPS; }
+
+static int fz_encoder_version()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MRCZIP_ENCODER");   // 1: the first (piece-per-lane, two-pass) encoder, kept for A/B runs
+        v = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return v;
+}
 
 void fz_launch_zero_hist(uint32_t *zero_hist, cudaStream_t st)
 {
+    if (fz_encoder_version() == 2) { fz_zero_hist2_kernel<<<1, FZ_WARP, 0, st>>>(zero_hist); return; }
     cudaFuncSetAttribute(fz_zero_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzHistSmem));
     fz_zero_hist_kernel<<<1, FZ_WARP, sizeof(FzHistSmem), st>>>(zero_hist);
 }
@@ -800,12 +1000,19 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
     const uint32_t gps = (g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS;
     const uint32_t ngroups = nstreams * gps;
     const unsigned grid = (total + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS;
-    cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzHistSmem) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
+    cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
+    if (fz_encoder_version() == 2) {
+        fz_hist2_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, 0, st>>>(planes, g, ghist, sizes, zero_hist, zero_planes, zero_from, status);
+        fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
+            ghist, g, (FzGroupCode *)gcodes);
+        fz_emit2_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, 0, st>>>(planes, g, (const FzGroupCode *)gcodes, scratch, sizes, status);
+        return;
+    }
+    cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzHistSmem) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEmitSmem) * FZ_ENC_WARPS));
     cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
     fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, zero_hist, zero_planes, zero_from, status);
     fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
         ghist, g, (FzGroupCode *)gcodes);

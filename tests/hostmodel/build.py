@@ -11,7 +11,7 @@ def build():
     deps = [src] + list((HERE.parent.parent / "datacompressionfloat_b200" / "csrc").glob("*.cuh"))
     if OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return OUT
-    subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(OUT), str(src)],
+    subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", str(OUT), str(src)],
                    check=True)
     return OUT
 

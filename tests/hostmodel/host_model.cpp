@@ -11,6 +11,9 @@
 #include <vector>
 
 #include "../../datacompressionfloat_b200/csrc/fz_deflate_enc.cuh"
+#include "../../datacompressionfloat_b200/csrc/fz_enc2.cuh"
+#include <functional>
+#include <thread>
 #include "../../datacompressionfloat_b200/csrc/fz_inflate.cuh"
 #include "../../datacompressionfloat_b200/csrc/fz_blockpar.cuh"
 
@@ -158,6 +161,160 @@ uint64_t hm_encode_stream_interleaved(const uint8_t *in, uint64_t n, uint8_t *ou
         }
     }
     free(st); free(gc); free(es);
+    if (nstored) *nstored = ns;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// encoder v2 (fz_enc2.cuh): the device source run by 32 host threads in lock step, next to a plain sequential
+// restatement of the token rule and the bit layout -- the two must produce the same bytes
+}  // extern "C"
+namespace {
+void run_warp(const std::function<void(const FzWarp &)> &fn)
+{
+    FzWarpShared sh;
+    pthread_barrier_init(&sh.bar, nullptr, 32);
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++) th.emplace_back([&, l] { FzWarp w{l, &sh}; fn(w); });
+    for (auto &t : th) t.join();
+    pthread_barrier_destroy(&sh.bar);
+}
+
+template <class Lit, class Match>
+void seq_tokens(const uint8_t *p, uint32_t n, Lit &&lit, Match &&match)
+{
+    // the quad rule of fz_enc2.cuh, one quad after the other
+    uint32_t m = 0;
+    bool prevE = false;
+    for (uint32_t q0 = 0; q0 < n; q0 += 4) {
+        const uint32_t nb = n - q0 < 4 ? n - q0 : 4;
+        bool E = nb == 4 && q0 > 0;
+        for (uint32_t i = 0; E && i < 4; i++) E = p[q0 + i] == p[q0 + i - 1];
+        if (E && prevE) {
+            if (++m == FZ_E2_MAX_QUADS) { match(4 * FZ_E2_MAX_QUADS); m = 0; }
+        } else {
+            if (m) { match(4 * m); m = 0; }
+            for (uint32_t i = 0; i < nb; i++) lit(p[q0 + i]);
+        }
+        prevE = E;
+    }
+    if (m) match(4 * m);
+}
+
+struct SeqBits {
+    std::vector<uint8_t> b;
+    uint64_t nbits = 0;
+    void put(uint32_t v, uint32_t n)
+    {
+        for (uint32_t i = 0; i < n; i++, nbits++) {
+            if ((nbits & 7) == 0) b.push_back(0);
+            b.back() |= (uint8_t)(((v >> i) & 1u) << (nbits & 7));
+        }
+    }
+};
+
+// the fragment of one sub-block, or empty = stored
+std::vector<uint8_t> seq_emit(const FzGroupCode *gc, const uint8_t *p, uint32_t n)
+{
+    SeqBits sb;
+    for (uint32_t i = 0; i < gc->hdr_nbits; i++) sb.put((gc->hdr[i >> 5] >> (i & 31)) & 1u, 1);
+    seq_tokens(p, n,
+               [&](uint32_t c) { sb.put(gc->cl[c] & 0xffffu, gc->cl[c] >> 16); },
+               [&](uint32_t len) {
+                   uint32_t lc, eb, ev;
+                   fz_len_code(len, lc, eb, ev);
+                   sb.put(gc->cl[257 + lc] & 0xffffu, gc->cl[257 + lc] >> 16);
+                   sb.put(ev, eb);
+                   sb.put(0, 1);
+               });
+    sb.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
+    sb.put(0, 3);
+    while (sb.nbits & 7) sb.put(0, 1);
+    sb.put(0xFFFF0000u, 32);
+    const uint32_t limit = fz_stored_size(n) - (n >> FZ_MIN_GAIN_SHIFT);
+    if (sb.b.size() >= limit) return {};
+    for (size_t i = 0; i + 4 < sb.b.size(); i++)
+        if (sb.b[i] == 0 && sb.b[i + 1] == 0 && sb.b[i + 2] == 0xFF && sb.b[i + 3] == 0xFF) return {};
+    return sb.b;
+}
+}  // namespace
+extern "C" {
+
+// mode 0: the device source under the thread model; mode 1: the sequential restatement.  skip: pass the sample's two
+// most frequent bytes to the histogram (what the kernel does) or not.
+uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, int mode, int skip, uint64_t *nstored)
+{
+    uint64_t o = 0, ns = 0;
+    std::vector<uint8_t> pad(FZ_SUB + 64);
+    std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8);
+    FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
+    FzGroupCode *gc = (FzGroupCode *)malloc(sizeof(FzGroupCode));
+    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
+    for (uint64_t g0 = 0; g0 < n; g0 += gbytes) {
+        const uint64_t gn = (n - g0) < gbytes ? (n - g0) : gbytes;
+        const uint32_t nsub = (uint32_t)((gn + FZ_SUB - 1) / FZ_SUB);
+        memset(st, 0xCD, sizeof(FzEncState));
+        memset(st->hist, 0, sizeof(st->hist));
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
+            memset(pad.data(), 0x5A, pad.size());   // what lies behind a ragged sub-block is arbitrary
+            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
+            uint32_t h[288];
+            memset(h, 0, sizeof(h));
+            if (mode == 0) {
+                uint32_t s1 = 0x100, s2 = 0x100;
+                if (skip) {   // two most frequent bytes of the first 2 KiB
+                    uint32_t cnt[256] = {0};
+                    for (uint32_t i = 0; i < m && i < 2048; i++) cnt[pad[i]]++;
+                    s1 = 0;
+                    for (uint32_t c = 1; c < 256; c++) if (cnt[c] > cnt[s1]) s1 = c;
+                    s2 = s1 == 0 ? 1 : 0;
+                    for (uint32_t c = 0; c < 256; c++) if (c != s1 && cnt[c] > cnt[s2]) s2 = c;
+                }
+                HostLoad16 ld{pad.data()};
+                run_warp([&](const FzWarp &w) { fz_hist2_subblock(w, h, ld, m, s1, s2); });
+            } else {
+                seq_tokens(pad.data(), m, [&](uint32_t c) { h[c]++; },
+                           [&](uint32_t len) { uint32_t lc, eb, ev; fz_len_code(len, lc, eb, ev); h[257 + lc]++; });
+            }
+            for (int i = 0; i < 288; i++) st->hist[i] += h[i];
+        }
+        st->hist[FZ_EOB] = nsub;
+        memset(gc, 0xEE, sizeof(FzGroupCode));
+        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0);
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
+            memset(pad.data(), 0x5A, pad.size());
+            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
+            uint32_t r = fz_stored_size(m) | FZ_SIZE_STORED_FLAG;
+            if (!gc->stored) {
+                if (mode == 0) {
+                    for (auto &w : slot) w = 0xDEADBEEFu;
+                    std::vector<uint32_t> ring(FZ_E2_RING_WORDS, 0xABABABABu), tt(64, 0xCDCDCDCDu);
+                    HostLoad16 ld{pad.data()};
+                    uint32_t res[32];
+                    run_warp([&](const FzWarp &w) {
+                        res[w.lane] = fz_emit2_subblock(w, gc->cl, gc->hdr, gc->hdr_nbits, ring.data(), tt.data(), ld, m, slot.data());
+                    });
+                    for (int l = 1; l < 32; l++) if (res[l] != res[0]) return (uint64_t)-2;
+                    r = res[0];
+                } else {
+                    const std::vector<uint8_t> f = seq_emit(gc, pad.data(), m);
+                    if (!f.empty()) { r = (uint32_t)f.size(); memcpy(slot.data(), f.data(), f.size()); }
+                }
+            }
+            if (r & FZ_SIZE_STORED_FLAG) {
+                if (o + fz_stored_size(m) > cap) return (uint64_t)-1;
+                o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
+                ns++;
+            } else {
+                if (o + r > cap) return (uint64_t)-1;
+                memcpy(out + o, slot.data(), r);
+                o += r;
+            }
+        }
+    }
+    free(st); free(gc);
     if (nstored) *nstored = ns;
     return o;
 }

@@ -37,6 +37,20 @@ def encode_stream_interleaved(a: np.ndarray):
     return out[:n].copy(), int(ns.value)
 
 
+_L.hm_encode_stream_v2.restype = C.c_uint64
+_L.hm_encode_stream_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+
+
+def encode_stream_v2(a: np.ndarray, sequential: bool = False, skip: bool = True):
+    """encoder v2 (fz_enc2.cuh): the device source under the 32-thread warp model, or its sequential restatement"""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    out = np.empty(a.size + (a.size // SUB + 1) * 64 + 64, dtype=np.uint8)
+    ns = C.c_uint64()
+    n = _L.hm_encode_stream_v2(a.ctypes.data, a.size, out.ctypes.data, out.size, int(sequential), int(skip), C.byref(ns))
+    assert n < 2**64 - 2, n
+    return out[:n].copy(), int(ns.value)
+
+
 def inflate(b: np.ndarray, n_out: int):
     b = np.ascontiguousarray(b, dtype=np.uint8)
     out = np.empty(n_out + 8, dtype=np.uint8)

@@ -167,6 +167,55 @@ def test_model_encoder_streams_inflate_with_zlib(hostmodel, oracle, name):
 
 
 @pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
+def test_model_encoder_v2_matches_sequential_rule_and_zlib(hostmodel, oracle, name):
+    """Encoder v2 (fz_enc2.cuh, what the kernels run): the device source under the 32-thread warp model produces the
+    very bytes of a plain sequential restatement of the token rule, and those inflate with zlib."""
+    a = _plane_cases()[name]
+    c, ns = hostmodel.encode_stream_v2(a, sequential=False, skip=True)
+    cs, ns_s = hostmodel.encode_stream_v2(a, sequential=True)
+    assert ns == ns_s and np.array_equal(c, cs)
+    d = zlib.decompressobj(-15)
+    assert d.decompress(c.tobytes()) == a.tobytes()
+    assert not d.eof and d.unused_data == b""
+    out, used = oracle.inflate_raw(c, a.size)
+    assert np.array_equal(out, a) and used == c.size
+    assert c[-4:].tobytes() == b"\x00\x00\xff\xff"
+    rc, o, used = hostmodel.inflate(c, a.size)
+    assert rc == 0 and np.array_equal(o, a) and used == c.size
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+    z = co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH)
+    nsub = a.size // hostmodel.SUB + 1
+    assert c.size <= 1.09 * len(z) + 128 * nsub or c.size <= len(z) + 0.05 * a.size
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 511, 512, 513, 1000, 8191, 16383])
+def test_model_encoder_v2_ragged_sizes(hostmodel, n):
+    """ragged sub-blocks (the last one of a file, odd chunk sizes): runs that end exactly at, before and after lane
+    and step boundaries"""
+    rng = np.random.default_rng(n)
+    for a in (np.zeros(n, np.uint8), rng.choice([3, 4], n, p=[.9, .1]).astype(np.uint8),
+              np.repeat(rng.integers(0, 256, n // 9 + 1).astype(np.uint8), 9)[:n]):
+        c, _ = hostmodel.encode_stream_v2(a, sequential=False, skip=False)
+        cs, _ = hostmodel.encode_stream_v2(a, sequential=True)
+        assert np.array_equal(c, cs)
+        assert zlib.decompressobj(-15).decompress(c.tobytes()) == a.tobytes()
+
+
+def test_model_encoder_v2_runs_across_every_boundary(hostmodel):
+    """long runs of 258 k + r bytes placed so that their ends and 258-byte cuts fall on every lane position"""
+    rng = np.random.default_rng(3)
+    parts = []
+    for i in range(40):
+        parts.append(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8))
+        parts.append(np.full(int(rng.integers(1, 900)), int(rng.integers(0, 256)), np.uint8))
+    a = np.concatenate(parts)[:3 * hostmodel.SUB]
+    c, _ = hostmodel.encode_stream_v2(a, sequential=False, skip=True)
+    cs, _ = hostmodel.encode_stream_v2(a, sequential=True)
+    assert np.array_equal(c, cs)
+    assert zlib.decompressobj(-15).decompress(c.tobytes()) == a.tobytes()
+
+
+@pytest.mark.parametrize("name", sorted(_plane_cases().keys()))
 def test_model_interleaved_geometry_streams_inflate_with_zlib(hostmodel, oracle, name):
     """The window-interleaved piece geometry (fz_emit_subblock_interleaved: 64-byte pieces, one window of 32 pieces at
     a time, no counting pass over the whole sub-block -- DESIGN 9 lead #1, not used by the kernels yet) produces valid
