@@ -28,6 +28,18 @@
         }                                                                                    \
     } while (0)
 
+// inside the host-buffer pipelines: copies and kernels may still be running against the caller's buffers when a call
+// fails -- nothing returns before the three streams are idle
+#define FZ_CHECK_PIPE(call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            fprintf(stderr, "[mrczip_b200] %s:%d CUDA error: %s\n", __FILE__, __LINE__,      \
+                    cudaGetErrorString(e_));                                                 \
+            return pipe_fail(c, MZB_E_CUDA);                                                 \
+        }                                                                                    \
+    } while (0)
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -56,6 +68,15 @@ struct mzb_ctx {
     size_t ev_used = 0;
     float stage_ms[FZ_ST_COUNT] = {0};
 };
+
+static int pipe_fail(mzb_ctx *c, int rc)
+{
+    if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+    cudaGetLastError();
+    return rc;
+}
 
 static void prof_mark(void *user, int stage)
 {
@@ -454,7 +475,15 @@ extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwo
         const uint64_t w0 = c0 * chk;
         const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
         const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
-        compress_enqueue_batch(c, (const uint32_t *)d_words + w0, nw, nb, chk, pstride, mask, exempt, (uint8_t *)d_out, out_cap);
+        const uint32_t *src = (const uint32_t *)d_words + w0;
+        if ((uintptr_t)src & 15u) {
+            // chunk sizes that are not a multiple of 4 words put later chunks off the 16-byte grid the split kernel's
+            // 128-bit loads need (never written by the reference; one chunk per batch here): go through an aligned copy
+            if ((rc = ensure(c->io_in, nw * 4 + 16))) return rc;
+            FZ_CHECK(cudaMemcpyAsync(c->io_in.p, src, nw * 4, cudaMemcpyDeviceToDevice, c->stream));
+            src = (const uint32_t *)c->io_in.p;
+        }
+        compress_enqueue_batch(c, src, nw, nb, chk, pstride, mask, exempt, (uint8_t *)d_out, out_cap);
         launches += compress_launches(nw);
     }
     if ((rc = status_fetch(c))) return rc;
@@ -507,8 +536,12 @@ extern "C" int mzb_decompress_device(mzb_ctx *c, const void *d_in, size_t in_siz
         const uint32_t nb = (uint32_t)((nchunks_total - c0) < bmax ? (nchunks_total - c0) : bmax);
         const uint64_t w0 = c0 * chk;
         const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
+        uint32_t *dst = (uint32_t *)d_words_out + w0;
+        const bool staged = ((uintptr_t)dst & 15u) != 0;   // see mzb_compress_device: odd chunk sizes, one chunk per batch
+        if (staged && (rc = ensure(c->io_out, nw * 4 + 16))) return rc;
         decompress_enqueue_batch(c, (const uint8_t *)d_in, in_size, make_geom(nb, chk, nw, pstride), ib,
-                                 (uint32_t *)d_words_out + w0, in_place_raw);
+                                 staged ? (uint32_t *)c->io_out.p : dst, in_place_raw);
+        if (staged) FZ_CHECK(cudaMemcpyAsync(dst, c->io_out.p, nw * 4, cudaMemcpyDeviceToDevice, c->stream));
         launches += decompress_launches(nw, in_place_raw);
     }
     if ((rc = status_fetch(c))) return rc;
@@ -589,27 +622,28 @@ extern "C" int mzb_compress_host(mzb_ctx *c, const void *h_words, uint64_t nword
             const uint64_t w0 = c0 * chk;
             const uint64_t nw = (w0 + (uint64_t)nb * chk <= nwords) ? (uint64_t)nb * chk : nwords - w0;
             uint8_t *d_in = (uint8_t *)c->io_in.p + (b & 1) * in_stride;
-            if (b >= 2) FZ_CHECK(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b - 2], 0));  // staging buffer free again
-            FZ_CHECK(cudaMemcpyAsync(d_in, (const uint32_t *)h_words + w0, nw * 4, cudaMemcpyHostToDevice, c->s_h2d));
-            FZ_CHECK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
-            FZ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+            if (b >= 2) FZ_CHECK_PIPE(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b - 2], 0));  // staging buffer free again
+            FZ_CHECK_PIPE(cudaMemcpyAsync(d_in, (const uint32_t *)h_words + w0, nw * 4, cudaMemcpyHostToDevice, c->s_h2d));
+            FZ_CHECK_PIPE(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+            FZ_CHECK_PIPE(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
             const uint64_t exempt = exempt_words > w0 ? exempt_words - w0 : 0;
             compress_enqueue_batch(c, (const uint32_t *)d_in, nw, nb, chk, pstride, mask, exempt, d_out, bound);
-            FZ_CHECK(cudaMemcpyAsync(&c->h_ends[b], &c->d_status->out_end, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-            FZ_CHECK(cudaEventRecord(c->ev_comp[b], c->stream));
+            FZ_CHECK_PIPE(cudaMemcpyAsync(&c->h_ends[b], &c->d_status->out_end, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            FZ_CHECK_PIPE(cudaEventRecord(c->ev_comp[b], c->stream));
             launches += compress_launches(nw);
         }
         if (b >= 1) {  // batch b-1 is done (or about to be): ship its part of the container while batch b computes
-            FZ_CHECK(cudaEventSynchronize(c->ev_comp[b - 1]));
+            FZ_CHECK_PIPE(cudaEventSynchronize(c->ev_comp[b - 1]));
             const uint64_t end = c->h_ends[b - 1];
             if (end > out_cap) { result = MZB_E_SPACE; break; }
             if (end > copied_to)
-                FZ_CHECK(cudaMemcpyAsync((uint8_t *)h_out + copied_to, d_out + copied_to, end - copied_to, cudaMemcpyDeviceToHost, c->s_d2h));
+                FZ_CHECK_PIPE(cudaMemcpyAsync((uint8_t *)h_out + copied_to, d_out + copied_to, end - copied_to, cudaMemcpyDeviceToHost, c->s_d2h));
             copied_to = end;
         }
     }
-    FZ_CHECK(cudaStreamSynchronize(c->s_d2h));
-    if ((rc = status_fetch(c))) return rc;
+    FZ_CHECK_PIPE(cudaStreamSynchronize(c->s_h2d));
+    FZ_CHECK_PIPE(cudaStreamSynchronize(c->s_d2h));
+    if ((rc = status_fetch(c))) return pipe_fail(c, rc);
     prof_collect(c);
     fill_compress_stats(c, nwords, nchunks_total, launches);
     if (result != MZB_OK) return result;
@@ -683,21 +717,21 @@ extern "C" int mzb_decompress_host(mzb_ctx *c, const void *h_in, size_t in_size,
         const size_t rbytes = (size_t)(rec_off[b + 1] - rec_off[b]);
         uint8_t *d_rec = (uint8_t *)c->io_in.p + (b & 1) * in_stride;
         uint32_t *d_w = (uint32_t *)((uint8_t *)c->io_out.p + (b & 1) * out_stride);
-        if (b >= 2) FZ_CHECK(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b - 2], 0));
-        FZ_CHECK(cudaMemcpyAsync(d_rec, in + rec_off[b], rbytes, cudaMemcpyHostToDevice, c->s_h2d));
-        FZ_CHECK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
-        FZ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
-        if (b >= 2) FZ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_d2h[b - 2], 0));  // output staging buffer free again
-        FZ_CHECK(cudaMemsetAsync(&c->d_status->out_end, 0, sizeof(unsigned long long), c->stream));  // records start at 0
+        if (b >= 2) FZ_CHECK_PIPE(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b - 2], 0));
+        FZ_CHECK_PIPE(cudaMemcpyAsync(d_rec, in + rec_off[b], rbytes, cudaMemcpyHostToDevice, c->s_h2d));
+        FZ_CHECK_PIPE(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+        FZ_CHECK_PIPE(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+        if (b >= 2) FZ_CHECK_PIPE(cudaStreamWaitEvent(c->stream, c->ev_d2h[b - 2], 0));  // output staging buffer free again
+        FZ_CHECK_PIPE(cudaMemsetAsync(&c->d_status->out_end, 0, sizeof(unsigned long long), c->stream));  // records start at 0
         decompress_enqueue_batch(c, d_rec, rbytes, make_geom(nb, chk, nw, pstride), ib, d_w, in_place_raw);
-        FZ_CHECK(cudaEventRecord(c->ev_comp[b], c->stream));
-        FZ_CHECK(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
-        FZ_CHECK(cudaMemcpyAsync((uint32_t *)h_words_out + w0, d_w, nw * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-        FZ_CHECK(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
+        FZ_CHECK_PIPE(cudaEventRecord(c->ev_comp[b], c->stream));
+        FZ_CHECK_PIPE(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+        FZ_CHECK_PIPE(cudaMemcpyAsync((uint32_t *)h_words_out + w0, d_w, nw * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        FZ_CHECK_PIPE(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
         launches += decompress_launches(nw, in_place_raw);
     }
-    FZ_CHECK(cudaStreamSynchronize(c->s_d2h));
-    if ((rc = status_fetch(c))) return rc;
+    FZ_CHECK_PIPE(cudaStreamSynchronize(c->s_d2h));
+    if ((rc = status_fetch(c))) return pipe_fail(c, rc);
     prof_collect(c);
     fill_decompress_stats(c, off, nwords, nchunks_total, launches);
     if (c->h_status->error) return c->h_status->error;

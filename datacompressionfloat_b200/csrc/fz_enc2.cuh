@@ -4,13 +4,13 @@
 // reference zip.c:164-196): distance-1 run matches of 3..258 bytes, one dynamic-Huffman block with the group's code,
 // then an empty stored block (the sync-flush marker).  What changed is HOW the 32 lanes of the warp share the work:
 //
-//   * step geometry: in step s lane l owns the 16 bytes [s*512 + l*16, +16) of the sub-block.  The warp reads 512
-//     contiguous bytes per step (one coalesced 128-bit load per lane, no staging), and the token order is simply
-//     the byte order -- there are no piece boundaries inside a sub-block any more.
+//   * step geometry: in step s lane l owns the 32 bytes [s*1024 + l*32, +32) of the sub-block.  The warp reads 1 KiB
+//     of contiguous bytes per step (two 128-bit loads per lane, no staging), and the token order is simply the byte
+//     order -- there are no piece boundaries inside a sub-block any more.
 //   * the run tokeniser is data parallel and works on aligned quads of 4 bytes: a quad is "held" (part of a distance-1
 //     match) when its bytes and the quad before it repeat one byte; one shuffle brings the neighbour's flag, one
 //     ballot the lanes whose four quads are all held, and that is all the cross-lane traffic a run needs.  Runs are
-//     therefore multiples of 4 bytes at multiples of 4: a lane's output is four slots, each either the codes of
+//     therefore multiples of 4 bytes at multiples of 4: a lane's output is eight slots, each either the codes of
 //     four literals or one match token -- the same instructions either way.
 //   * ONE pass: every lane looks its 16 codes up, a warp prefix sum over the lanes' bit counts gives each lane its
 //     bit offset, and the bits are ORed into a 2 KiB ring in shared memory (shared-memory atomics: neighbouring
@@ -110,9 +110,15 @@ FZ_HD uint32_t fz_warp_incl_sum(const W &w, uint32_t v)
 //   Quad q is HELD iff E[q] and E[q-1]: its bytes continue a run that is at least 5 bytes long already.  Every byte
 //   outside a held quad is a literal.  A maximal run of held quads leaves as distance-1 matches: one of 256 bytes at
 //   every 64th quad of the run, and one of 4 * (count mod 64) bytes at its last quad.  Tokens leave in byte order.
-// (The first encoder withheld bytes one by one; quads make a lane's output four uniform slots, cost nothing measurable
-//  on float planes -- tools/token_rule_study.py -- and let an inflater copy runs as whole words.)
+// (The first encoder withheld bytes one by one; quads make a lane's output uniform slots, cost nothing measurable on
+//  float planes, and let an inflater copy runs as whole words.)
 #define FZ_E2_MAX_QUADS 64u    // 256 bytes: the longest match the encoder writes
+#define FZ_E2_LQ 8             // quads per lane and step
+#define FZ_E2_LB (4u * FZ_E2_LQ)        // bytes per lane and step
+#define FZ_E2_STEP (32u * FZ_E2_LB)     // bytes per warp and step
+#define FZ_E2_LQ_MASK ((1u << FZ_E2_LQ) - 1u)
+
+struct FzLaneQuads { uint32_t w[FZ_E2_LQ]; };
 
 // what the warp carries from step to step (the same value in every lane)
 struct FzTokCarry {
@@ -122,35 +128,20 @@ struct FzTokCarry {
     FZ_HD void init() { prev = 0x100u; prevE = 0; m = 0; }
 };
 
-// this lane's four quads, tokenised
+// this lane's quads, tokenised
 struct FzTok {
-    uint32_t hq;      // bit 4g: quad g is held
+    uint32_t hq;      // bit g: quad g is held
     uint32_t m_in;    // held quads pending in front of quad 0 (0..63)
 };
 
-// 16 equality flags of v against the byte before each byte (`before` = byte before byte 0)
-FZ_HD uint32_t fz_eq_flags(const FzVec16 &v, uint32_t before)
-{
-    uint32_t eq = 0;
-    uint32_t b = before << 24;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t x = v.w[j] ^ ((v.w[j] << 8) | (b >> 24));
-        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
-        eq |= ((z * 0x00204081u) >> 28) << (4 * j);
-        b = v.w[j];
-    }
-    return eq;
-}
-
-// bit k: byte k of v equals the byte splatted in `splat4` (b * 0x01010101)
-FZ_HD uint32_t fz_byte_eq_mask(const FzVec16 &v, uint32_t splat4)
+// bit k: byte k of the 16 bytes x[0..3] equals the byte splatted in `splat4` (b * 0x01010101)
+FZ_HD uint32_t fz_byte_eq_mask(const uint32_t *x4, uint32_t splat4)
 {
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t x = v.w[j] ^ splat4;
-        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        const uint32_t x = x4[j] ^ splat4;
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
         m |= ((z * 0x00204081u) >> 28) << (4 * j);
     }
     return m;
@@ -165,57 +156,81 @@ FZ_HD void fz_store_vec16(uint32_t *p, uint32_t x0, uint32_t x1, uint32_t x2, ui
 #endif
 }
 
-// Tokenise one step.  nv = valid bytes of this lane (0..16; < 16 only in the ragged last step of a short sub-block).
-// Returns true (in every lane) when the step has runs to book-keep (t.hq / t.m_in say which); otherwise every valid
-// byte is a literal.  `c` is advanced.
+FZ_HD uint32_t fz_splat_top_byte(uint32_t w)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0, 0x3333);
+#else
+    return (w >> 24) * 0x01010101u;
+#endif
+}
+
+// this lane's bytes of step s: [s * FZ_E2_STEP + lane * FZ_E2_LB, + FZ_E2_LB), as far as they exist
+template <class Load16>
+FZ_HD FzLaneQuads fz_lane_load(const Load16 &ld, uint32_t pos, uint32_t n)
+{
+    FzLaneQuads v;
+#pragma unroll
+    for (int h = 0; h < FZ_E2_LQ / 4; h++) {
+        FzVec16 x;
+        x.w[0] = x.w[1] = x.w[2] = x.w[3] = 0;
+        if (pos + 16u * h < n) x = ld(pos + 16u * h);
+        v.w[4 * h] = x.w[0]; v.w[4 * h + 1] = x.w[1]; v.w[4 * h + 2] = x.w[2]; v.w[4 * h + 3] = x.w[3];
+    }
+    return v;
+}
+
+// Tokenise one step.  nv = valid bytes of this lane (0..FZ_E2_LB; fewer only in the ragged last step of a short
+// sub-block).  Returns true (in every lane) when the step has runs to book-keep (t.hq / t.m_in say which); otherwise
+// every valid byte is a literal.  `c` is advanced.
 template <class W>
-FZ_HD bool fz_tok_step(const W &w, const FzVec16 &v, uint32_t nv, FzTokCarry &c, FzTok &t)
+FZ_HD bool fz_tok_step(const W &w, const FzLaneQuads &v, uint32_t nv, FzTokCarry &c, FzTok &t)
 {
     const int lane = w.lane;
-    const uint32_t lastb = v.w[3] >> 24;
+    const uint32_t lastb = v.w[FZ_E2_LQ - 1] >> 24;
     uint32_t pb = w.shfl_up(lastb, 1);
     if (lane == 0) pb = c.prev;
-    uint32_t eq = fz_eq_flags(v, pb & 0xffu);
-    if (pb > 0xffu) eq &= ~1u;                       // no byte before the sub-block
-    uint32_t E = eq & (eq >> 1);
-    E &= E >> 2;
-    E &= 0x1111u & ((1u << (nv & ~3u)) - 1u);        // bit 4g: quad g is whole and repeats the byte before it
-    uint32_t pE = w.shfl_up(E >> 12, 1);
+    // E: a quad whose four bytes equal the byte before it is that byte splatted
+    uint32_t E = (pb <= 0xffu && v.w[0] == pb * 0x01010101u) ? 1u : 0u;
+#pragma unroll
+    for (int g = 1; g < FZ_E2_LQ; g++) E |= (v.w[g] == fz_splat_top_byte(v.w[g - 1]) ? 1u : 0u) << g;
+    E &= (1u << (nv >> 2)) - 1u;                     // whole quads only
+    uint32_t pE = w.shfl_up(E >> (FZ_E2_LQ - 1), 1);
     if (lane == 0) pE = c.prevE;
-    const uint32_t hq = E & ((E << 4) | pE);
+    const uint32_t hq = E & ((E << 1) | pE);
     t.hq = hq;
     t.m_in = 0;
     const uint32_t anyh = w.ballot(hq != 0);
     const uint32_t m0 = c.m;
     c.prev = w.shfl(lastb, 31);
-    c.prevE = w.shfl(E >> 12, 31);
+    c.prevE = w.shfl(E >> (FZ_E2_LQ - 1), 31);
     if (anyh == 0 && m0 == 0) return false;
-    // ---- runs.  A lane "passes" when its four quads are held: the run goes through it.
-    const bool passes = hq == 0x1111u;
+    // ---- runs.  A lane "passes" when all of its quads are held: the run goes through it.
+    const bool passes = hq == FZ_E2_LQ_MASK;
     const uint32_t B = w.ballot(passes);
     // held quads at the top of a lane that does not pass: what it hands to the next lane
-    const uint32_t top = (hq & 0x1000u) ? ((hq & 0x0100u) ? ((hq & 0x0010u) ? 3u : 2u) : 1u) : 0u;
+    const uint32_t top = passes ? 0u : fz_clz32(~(hq << (32 - FZ_E2_LQ)));
     const uint32_t below = ~B & ((1u << lane) - 1u);          // lanes before this one that do not pass
     const int j = below ? 31 - (int)fz_clz32(below) : 0;
     const uint32_t tj = w.shfl(top, j);
-    const uint32_t m = (below ? tj + 4u * (uint32_t)(lane - 1 - j) : m0 + 4u * (uint32_t)lane) & (FZ_E2_MAX_QUADS - 1u);
+    const uint32_t m = (below ? tj + FZ_E2_LQ * (uint32_t)(lane - 1 - j) : m0 + FZ_E2_LQ * (uint32_t)lane) & (FZ_E2_MAX_QUADS - 1u);
     t.m_in = m;
-    c.m = w.shfl(passes ? ((m + 4u) & (FZ_E2_MAX_QUADS - 1u)) : top, 31);
+    c.m = w.shfl(passes ? ((m + FZ_E2_LQ) & (FZ_E2_MAX_QUADS - 1u)) : top, 31);
     return true;
 }
 
 // the run tokens of a tokenised lane, as lengths in quads (0 = none): tin = in front of quad 0 (the run ended with the
 // lane before), tl[g] = at held quad g
-FZ_HD void fz_tok_lens(const FzTok &t, uint32_t &tin, uint32_t tl[4])
+FZ_HD void fz_tok_lens(const FzTok &t, uint32_t &tin, uint32_t tl[FZ_E2_LQ])
 {
     uint32_t cnt = t.m_in;
     tin = (t.hq & 1u) ? 0u : cnt;
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
+    for (int g = 0; g < FZ_E2_LQ; g++) {
         tl[g] = 0;
-        if ((t.hq >> (4 * g)) & 1u) {
+        if ((t.hq >> g) & 1u) {
             cnt = (cnt + 1u) & (FZ_E2_MAX_QUADS - 1u);
-            const bool more = g < 3 ? ((t.hq >> (4 * g + 4)) & 1u) != 0 : true;   // quad 3: the next lane knows
+            const bool more = g < FZ_E2_LQ - 1 ? ((t.hq >> (g + 1)) & 1u) != 0 : true;   // last quad: the next lane knows
             if (cnt == 0) tl[g] = FZ_E2_MAX_QUADS;
             else if (!more) tl[g] = cnt;
         } else cnt = 0;
@@ -242,43 +257,45 @@ FZ_HD void fz_hist2_subblock(const W &w, uint32_t *hist, const Load16 &ld, uint3
     FzTokCarry c;
     c.init();
     uint32_t n1 = 0, n2 = 0;
-    const uint32_t nsteps = (n + 511u) / 512u;
+    const uint32_t nsteps = (n + FZ_E2_STEP - 1u) / FZ_E2_STEP;
     const uint32_t s1 = (skip1 & 0xffu) * 0x01010101u, s2 = (skip2 & 0xffu) * 0x01010101u;
-    FzVec16 v;
-    v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0;
-    if ((uint32_t)lane * 16u < n) v = ld((uint32_t)lane * 16u);
+    FzLaneQuads v = fz_lane_load(ld, (uint32_t)lane * FZ_E2_LB, n);
     for (uint32_t s = 0; s < nsteps; s++) {
-        const uint32_t pos = s * 512u + (uint32_t)lane * 16u;
-        const uint32_t nv = n > pos ? (n - pos < 16u ? n - pos : 16u) : 0u;
-        FzVec16 vn;
-        vn.w[0] = vn.w[1] = vn.w[2] = vn.w[3] = 0;
-        if (pos + 512u < n) vn = ld(pos + 512u);
+        const uint32_t pos = s * FZ_E2_STEP + (uint32_t)lane * FZ_E2_LB;
+        const uint32_t nv = n > pos ? (n - pos < FZ_E2_LB ? n - pos : FZ_E2_LB) : 0u;
+        const FzLaneQuads vn = fz_lane_load(ld, pos + FZ_E2_STEP, n);
         FzTok t;
         const bool slow = fz_tok_step(w, v, nv, c, t);
-        uint32_t lit = ((1u << nv) - 1u) & ~(t.hq * 15u);
-        if (skip1 < 0x100u) {
-            const uint32_t m1 = fz_byte_eq_mask(v, s1) & lit;
-            n1 += fz_popc32(m1);
-            lit &= ~m1;
-        }
-        if (skip2 < 0x100u) {
-            const uint32_t m2 = fz_byte_eq_mask(v, s2) & lit;
-            n2 += fz_popc32(m2);
-            lit &= ~m2;
-        }
-        if (lit == 0xffffu) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) w.atom_add(&hist[FZ_BYTE_OF(v, k)], 1u);
-        } else {
+        for (int h = 0; h < FZ_E2_LQ / 4; h++) {
+            const uint32_t nvh = nv > 16u * h ? (nv - 16u * h < 16u ? nv - 16u * h : 16u) : 0u;
+            const uint32_t hn = (t.hq >> (4 * h)) & 15u;                                   // held quads of these 16 bytes
+            const uint32_t hb = ((hn | (hn << 3) | (hn << 6) | (hn << 9)) & 0x1111u) * 15u;  // ... as byte flags
+            uint32_t lit = ((1u << nvh) - 1u) & ~hb;
+            if (skip1 < 0x100u) {
+                const uint32_t m1 = fz_byte_eq_mask(&v.w[4 * h], s1) & lit;
+                n1 += fz_popc32(m1);
+                lit &= ~m1;
+            }
+            if (skip2 < 0x100u) {
+                const uint32_t m2 = fz_byte_eq_mask(&v.w[4 * h], s2) & lit;
+                n2 += fz_popc32(m2);
+                lit &= ~m2;
+            }
+            if (lit == 0xffffu) {
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                if ((lit >> k) & 1u) w.atom_add(&hist[FZ_BYTE_OF(v, k)], 1u);
+                for (int k = 0; k < 16; k++) w.atom_add(&hist[(v.w[4 * h + (k >> 2)] >> ((k & 3) * 8)) & 0xffu], 1u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if ((lit >> k) & 1u) w.atom_add(&hist[(v.w[4 * h + (k >> 2)] >> ((k & 3) * 8)) & 0xffu], 1u);
+            }
         }
         if (slow) {
-            uint32_t tin, tl[4];
+            uint32_t tin, tl[FZ_E2_LQ];
             fz_tok_lens(t, tin, tl);
 #pragma unroll
-            for (int g = -1; g < 4; g++) {
+            for (int g = -1; g < FZ_E2_LQ; g++) {
                 const uint32_t nq = g < 0 ? tin : tl[g < 0 ? 0 : g];
                 if (nq) {
                     uint32_t lc, eb, ev;
@@ -300,7 +317,7 @@ FZ_HD void fz_hist2_subblock(const W &w, uint32_t *hist, const Load16 &ld, uint3
 }
 
 // ---- emission ------------------------------------------------------------------------------------------------------
-#define FZ_E2_RING_WORDS 512u                      // 2 KiB: < 33 vectors waiting + at most 32 x (16 x 15 + 21) bits of a step
+#define FZ_E2_RING_WORDS 1024u                     // 4 KiB: < 33 vectors waiting + at most 32 x (32 x 15 + 21) bits of a step
 #define FZ_E2_RING_MASK (FZ_E2_RING_WORDS - 1u)
 #define FZ_E2_FLUSH_VECS 32u                       // vectors leave the ring 32 at a time (one per lane)
 
@@ -324,15 +341,17 @@ FZ_HD void fz_ring_put64(const W &w, uint32_t *ring, uint32_t off, uint64_t bits
     if (s + nbits > 64u) w.atom_or(&ring[(wi + 2u) & FZ_E2_RING_MASK], (uint32_t)(bits >> (64u - s)));
 }
 
-// Does the 20-byte window prev | v show 00 00 FF FF at byte offsets 1..16 (i.e. ending inside v)?  bit o - 1 of the result.
+// Does the 20-byte window prev | x0..x3 show 00 00 FF FF at byte offsets 1..16 (i.e. ending inside x0..x3)?
+// bit o - 1 of the result.  The filter in front (two adjacent FF bytes anywhere) lets one vector in three thousand through.
 FZ_HD uint32_t fz_marker_in20(uint32_t prev, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3)
 {
     const uint32_t a[5] = {prev, x0, x1, x2, x3};
     uint32_t any = 0;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
-        const uint32_t x = ~a[k];
-        any |= (x - 0x01010101u) & ~x & 0x80808080u;          // non-zero iff a[k] has an FF byte
+        const uint32_t nx = k < 4 ? a[k + 1] : 0u;
+        const uint32_t t = a[k] & ((a[k] >> 8) | (nx << 24));   // byte i: bytes i and i + 1 ANDed
+        any |= (~t - 0x01010101u) & t & 0x80808080u;            // non-zero iff some byte of t is FF
     }
     if (any == 0) return 0;
     uint32_t F = 0, Z = 0;
@@ -428,31 +447,27 @@ FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t 
 
     FzTokCarry c;
     c.init();
-    const uint32_t nsteps = (n + 511u) / 512u;
-    FzVec16 v;
-    v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0;
-    if ((uint32_t)lane * 16u < n) v = ld((uint32_t)lane * 16u);
+    const uint32_t nsteps = (n + FZ_E2_STEP - 1u) / FZ_E2_STEP;
+    FzLaneQuads v = fz_lane_load(ld, (uint32_t)lane * FZ_E2_LB, n);
     for (uint32_t s = 0; s < nsteps; s++) {
-        const uint32_t pos = s * 512u + (uint32_t)lane * 16u;
-        const uint32_t nv = n > pos ? (n - pos < 16u ? n - pos : 16u) : 0u;
-        FzVec16 vn;
-        vn.w[0] = vn.w[1] = vn.w[2] = vn.w[3] = 0;
-        if (pos + 512u < n) vn = ld(pos + 512u);
+        const uint32_t pos = s * FZ_E2_STEP + (uint32_t)lane * FZ_E2_LB;
+        const uint32_t nv = n > pos ? (n - pos < FZ_E2_LB ? n - pos : FZ_E2_LB) : 0u;
+        const FzLaneQuads vn = fz_lane_load(ld, pos + FZ_E2_STEP, n);
         FzTok t;
         const bool slow = fz_tok_step(w, v, nv, c, t);
-        uint32_t e[16];
+        // one slot per quad: the codes of its four literals ...
+        uint64_t qv[FZ_E2_LQ];
+        uint32_t ql[FZ_E2_LQ];
 #pragma unroll
-        for (int k = 0; k < 16; k++) e[k] = cl[FZ_BYTE_OF(v, k)];
-        if (nv != 16u) {   // the ragged last step of a short sub-block
-#pragma unroll
-            for (int k = 0; k < 16; k++) if ((uint32_t)k >= nv) e[k] = 0;
-        }
-        // four slots: the codes of four literals each ...
-        uint64_t qv[4];
-        uint32_t ql[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const uint32_t e0 = e[4 * g], e1 = e[4 * g + 1], e2 = e[4 * g + 2], e3 = e[4 * g + 3];
+        for (int g = 0; g < FZ_E2_LQ; g++) {
+            const uint32_t x = v.w[g];
+            uint32_t e0 = cl[x & 0xffu], e1 = cl[(x >> 8) & 0xffu], e2 = cl[(x >> 16) & 0xffu], e3 = cl[x >> 24];
+            if (nv < FZ_E2_LB) {   // the ragged last step of a short sub-block
+                if (4u * g + 0u >= nv) e0 = 0;
+                if (4u * g + 1u >= nv) e1 = 0;
+                if (4u * g + 2u >= nv) e2 = 0;
+                if (4u * g + 3u >= nv) e3 = 0;
+            }
             const uint32_t l0 = e0 >> 16, l2 = e2 >> 16;
             const uint32_t p0 = (e0 & 0xffffu) | ((e1 & 0xffffu) << l0), pl0 = l0 + (e1 >> 16);
             const uint32_t p1 = (e2 & 0xffffu) | ((e3 & 0xffffu) << l2), pl1 = l2 + (e3 >> 16);
@@ -461,23 +476,25 @@ FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t 
         }
         uint32_t tinb = 0, tinl = 0;
         if (slow) {   // ... or, for a held quad, its run token (if a run ends or reaches 256 bytes there) or nothing
-            uint32_t tin, tl[4];
+            uint32_t tin, tl[FZ_E2_LQ];
             fz_tok_lens(t, tin, tl);
             if (tin) { const uint32_t x = tt[tin - 1u]; tinb = x & 0xffffffu; tinl = x >> 24; }
 #pragma unroll
-            for (int g = 0; g < 4; g++)
-                if ((t.hq >> (4 * g)) & 1u) {
+            for (int g = 0; g < FZ_E2_LQ; g++)
+                if ((t.hq >> g) & 1u) {
                     const uint32_t x = tl[g] ? tt[tl[g] - 1u] : 0u;
                     qv[g] = x & 0xffffffu;
                     ql[g] = x >> 24;
                 }
         }
-        const uint32_t tot = tinl + ql[0] + ql[1] + ql[2] + ql[3];
+        uint32_t tot = tinl;
+#pragma unroll
+        for (int g = 0; g < FZ_E2_LQ; g++) tot += ql[g];
         const uint32_t inc = fz_warp_incl_sum(w, tot);
         uint32_t off = P + inc - tot;
         if (tinl) { fz_ring_put32(w, ring, off, tinb, tinl); off += tinl; }
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
+        for (int g = 0; g < FZ_E2_LQ; g++) {
             if (ql[g]) fz_ring_put64(w, ring, off, qv[g], ql[g]);
             off += ql[g];
         }

@@ -708,7 +708,13 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
         return;
     }
     __syncwarp();
-    if (lane == 0) st->hist[FZ_EOB] = nsub;  // one end-of-block per sub-block
+    if (st->hist[287]) {
+        // some sub-blocks of the group were not tokenised (fz_hist2_kernel): every literal and every run length gets a code
+        for (int i = lane; i < 286; i += 32)
+            if (i != FZ_EOB && st->hist[i] == 0) st->hist[i] = 1;
+    }
+    __syncwarp();
+    if (lane == 0) { st->hist[FZ_EOB] = nsub; st->hist[286] = 0; st->hist[287] = 0; }  // one end-of-block per sub-block
     __syncwarp();
     fz_build_group_code(st, gn, nsub, gcodes + gi, lane);
 }
@@ -819,6 +825,9 @@ __device__ __forceinline__ uint32_t fz_warp_hist_mode(const uint32_t *hist, uint
     return best;
 }
 
+#ifndef FZ_HIST_SAMPLE
+#define FZ_HIST_SAMPLE 4u   // 1 = every sub-block is tokenised for the histogram
+#endif
 #define FZ_HIST2_SKIP_MIN 160u   // of 2048 sample bytes: below ~8 % a private counter costs more than the conflicts it saves
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
@@ -901,12 +910,20 @@ fz_hist2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__r
         __syncwarp();
     }
     if (lane == 0) sizes[t] = 0;  // to be decided by the emit kernel
+    if (aligned && (k % FZ_HIST_SAMPLE) != 0) {
+        // The group's code is built from every FZ_HIST_SAMPLE-th sub-block (a group is 512 KiB of one plane: a quarter of
+        // it is 8 K..128 K tokens).  Slot 287 of the group histogram counts the sub-blocks left out: the code builder then
+        // gives every literal and every run length a code, so whatever they hold can be coded.
+        if (lane == 0) atomicAdd(gh + 287, 1u);
+        return;
+    }
     const FzWarp w{lane};
     if (aligned) fz_hist2_subblock(w, hist, GlobVec16{src}, n, skip1, skip2);
     else fz_hist2_subblock(w, hist, GlobLoad16{src}, n, skip1, skip2);
-    for (int i = lane; i < 288; i += 32) {
+    const uint32_t weight = aligned ? FZ_HIST_SAMPLE : 1u;
+    for (int i = lane; i < 286; i += 32) {
         const uint32_t v = hist[i];
-        if (v) atomicAdd(gh + i, v);
+        if (v) atomicAdd(gh + i, v * weight);
     }
 }
 

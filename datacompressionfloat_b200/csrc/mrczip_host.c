@@ -7,6 +7,7 @@
  */
 #define _FILE_OFFSET_BITS 64
 #define _GNU_SOURCE
+#include <fcntl.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -263,17 +264,36 @@ static void *io_slice_run(void *p)
     return NULL;
 }
 
+static int g_io_threads = 0; /* 0 = not set: MRCZIP_IO_THREADS, else 4 */
+static pthread_once_t g_io_once = PTHREAD_ONCE_INIT;
+static int g_io_env = 4;
+static void io_threads_init(void)
+{
+    const char *e = getenv("MRCZIP_IO_THREADS");
+    const int w = e ? atoi(e) : 4;
+    g_io_env = w < 1 ? 1 : (w > IO_THREADS ? IO_THREADS : w);
+}
+static int io_threads(void)
+{
+    const int set = __atomic_load_n(&g_io_threads, __ATOMIC_RELAXED);
+    if (set > 0) return set;
+    pthread_once(&g_io_once, io_threads_init);
+    return g_io_env;
+}
+
+int mzb_set_io_threads(int n)
+{
+    if (n < 0 || n > IO_THREADS) return MZB_E_ARG;
+    __atomic_store_n(&g_io_threads, n, __ATOMIC_RELAXED);
+    return MZB_OK;
+}
+
 /* n bytes at file offset off, split over up to IO_THREADS threads; returns the contiguous byte count done */
 static size_t io_parallel(int fd, int wr, void *buf, size_t n, off_t off)
 {
     io_slice_t sl[IO_THREADS];
     pthread_t th[IO_THREADS];
-    static int want = 0;
-    if (want == 0) {
-        const char *e = getenv("MRCZIP_IO_THREADS");
-        int w = e ? atoi(e) : 4;
-        want = w < 1 ? 1 : (w > IO_THREADS ? IO_THREADS : w);
-    }
+    const int want = io_threads();
     int k = (int)(n / IO_SLICE_MIN);
     if (k < 1) k = 1;
     if (k > want) k = want;
@@ -335,7 +355,12 @@ static int io_seekable(FILE *fp, int for_write, off_t *pos)
     const int fd = fileno(fp);
     struct stat st;
     if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return -1;
-    if (for_write && fflush(fp) != 0) return -1;
+    if (for_write) {
+        /* pwrite ignores its offset on a descriptor opened with O_APPEND: such a FILE* takes the plain fwrite loop */
+        const int fl = fcntl(fd, F_GETFL);
+        if (fl < 0 || (fl & O_APPEND)) return -1;
+        if (fflush(fp) != 0) return -1;
+    }
     *pos = ftello(fp);
     return *pos < 0 ? -1 : fd;
 }
@@ -416,23 +441,33 @@ static int compress_overlapped(thread_state_t *ts, FILE *fin, int fdin, off_t po
 }
 
 /* extent of the next batch of a container: up to bchunks chunk records starting at file offset off */
-static int walk_batch(int fd, off_t off, uint64_t bchunks, uint64_t words_left, uint32_t chk, size_t *bytes, uint64_t *bw)
+/* A plane header of a chunk of num words: RAW payloads are the num plane bytes (zip.c:186-190), COMPRESSED ones are
+ * only written when they save more than their 4-byte header (zip.c:177: inlen > len + 4).  Anything else cannot come
+ * from the reference or from this library, and would overrun the staging buffers sized for chk bytes per plane. */
+static int plane_header_ok(btype_t bt, uint32_t len, uint64_t num)
+{
+    return bt == RAW ? (uint64_t)len == num : (uint64_t)len + 4u < num;
+}
+
+static int walk_batch(int fd, off_t off, uint64_t bchunks, uint64_t words_left, uint32_t chk, size_t cap, size_t *bytes, uint64_t *bw)
 {
     size_t fill = 0;
     uint64_t w = 0;
     for (uint64_t c = 0; c < bchunks && w < words_left; c++) {
         unsigned char h[16];
         if (pread(fd, h, 16, off + (off_t)fill) != 16) return MZB_E_FORMAT;
+        const uint64_t num = (words_left - w) < chk ? (words_left - w) : chk;
         size_t payload = 0;
         for (int j = 0; j < MZB_PLANES; j++) {
             btype_t bt;
             uint32_t len;
             unpack_header((const char *)h + 4 * j, &bt, &len);
-            if (len > chk + 4u) return MZB_E_FORMAT; /* the reference's reader buffer is chk + 4 (zip.c:334) */
+            if (!plane_header_ok(bt, len, num)) return MZB_E_FORMAT;
             payload += len;
         }
+        if (fill + 16 + payload > cap) return MZB_E_FORMAT;
         fill += 16 + payload;
-        w += (words_left - w) < chk ? (words_left - w) : chk;
+        w += num;
     }
     *bytes = fill;
     *bw = w;
@@ -445,7 +480,7 @@ static int uncompress_overlapped(thread_state_t *ts, FILE *fin, int fdin, off_t 
 {
     const uint64_t nchunks = (words + chk - 1) / chk;
     if (bchunks > nchunks && nchunks > 0) bchunks = nchunks;
-    const size_t in_cap = (size_t)(bchunks * (16 + 4ull * chk)) + 64, out_cap = (size_t)bchunks * chk * 4 + 64;
+    const size_t in_cap = (size_t)(bchunks * (16 + 4ull * (chk + 4ull))) + 64, out_cap = (size_t)bchunks * chk * 4 + 64;
     if (pin_pair(ts, in_cap, out_cap, nchunks > bchunks)) {
         fprintf(stderr, "[%s:%d] ERROR: fail to alloc mem\n", __FILE__, __LINE__);
         return MZB_E_NOMEM;
@@ -464,14 +499,14 @@ static int uncompress_overlapped(thread_state_t *ts, FILE *fin, int fdin, off_t 
     size_t bytes = 0, nbytes = 0;
     uint64_t bw = 0, nbw = 0;
     off_t off = pos_in;
-    if (words > 0 && (rc = walk_batch(fdin, off, bchunks, words, chk, &bytes, &bw)) == MZB_OK)
+    if (words > 0 && (rc = walk_batch(fdin, off, bchunks, words, chk, in_cap, &bytes, &bw)) == MZB_OK)
         io_job_start(&jr, fdin, 0, in[0], bytes, off);
     uint64_t b = 0;
     for (uint64_t w0 = 0; w0 < words && rc == MZB_OK; b++) {
         if (io_job_wait(&jr) != bytes) { rc = MZB_E_FORMAT; break; }   /* truncated container */
         off += (off_t)bytes;
         if (w0 + bw < words) {
-            if ((rc = walk_batch(fdin, off, bchunks, words - w0 - bw, chk, &nbytes, &nbw)) != MZB_OK) break;
+            if ((rc = walk_batch(fdin, off, bchunks, words - w0 - bw, chk, in_cap, &nbytes, &nbw)) != MZB_OK) break;
             io_job_start(&jr, fdin, 0, in[(b + 1) & 1], nbytes, off);
         }
         uint64_t nw = 0;
@@ -613,7 +648,7 @@ int run_uncompress(FILE *fin, ctx_t *ctx, mrczip_header_t *hd, FILE *fout, const
             return rc2;
         }
     }
-    const size_t in_cap = (size_t)(bchunks * (16 + 4ull * chk)) + 64;
+    const size_t in_cap = (size_t)(bchunks * (16 + 4ull * (chk + 4ull))) + 64;
     if (pin_reserve(&ts->pin_in, &ts->pin_in_cap, in_cap) || pin_reserve(&ts->pin_out, &ts->pin_out_cap, (size_t)bchunks * chk * 4 + 64)) {
         fprintf(stderr, "[%s:%d] ERROR: fail to alloc mem\n", __FILE__, __LINE__);
         return MZB_E_NOMEM;
@@ -635,10 +670,11 @@ int run_uncompress(FILE *fin, ctx_t *ctx, mrczip_header_t *hd, FILE *fout, const
                 btype_t bt;
                 uint32_t len;
                 unpack_header((const char *)in + fill + 4 * j, &bt, &len);
-                if (len > chk + 4u) { rc = MZB_E_FORMAT; break; } /* the reference's reader buffer is chk + 4 (zip.c:334) */
+                if (!plane_header_ok(bt, len, num)) { rc = MZB_E_FORMAT; break; }
                 payload += len;
             }
             if (rc != MZB_OK) break;
+            if (fill + 16 + payload > in_cap) { rc = MZB_E_FORMAT; break; }
             if (fread(in + fill + 16, 1, payload, fin) != payload) { rc = MZB_E_FORMAT; break; }
             fill += 16 + payload;
             bw += num;

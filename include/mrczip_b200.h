@@ -115,6 +115,10 @@ int mzb_set_batch_chunks(mzb_ctx *ctx, uint32_t chunks);
 /* kernel variant selectors used by the benchmarks (0 = default) */
 int mzb_set_variant(mzb_ctx *ctx, int split_variant, int merge_variant);
 
+/* Threads that pread / pwrite one batch of the FILE* entry points (1..16; 0 = back to the default: the environment
+ * variable MRCZIP_IO_THREADS, else 4).  Process wide. */
+int mzb_set_io_threads(int n);
+
 /* Upper bound of the container for nwords words cut in chk-word chunks (header included). */
 size_t mzb_compress_bound(uint64_t nwords, uint32_t chk);
 

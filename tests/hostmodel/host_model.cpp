@@ -242,6 +242,8 @@ extern "C" {
 
 // mode 0: the device source under the thread model; mode 1: the sequential restatement.  skip: pass the sample's two
 // most frequent bytes to the histogram (what the kernel does) or not.
+int hm_hist_sample = 0;
+void hm_set_hist_sample(int k) { hm_hist_sample = k; }
 uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, int mode, int skip, uint64_t *nstored)
 {
     uint64_t o = 0, ns = 0;
@@ -277,7 +279,15 @@ uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64
                 seq_tokens(pad.data(), m, [&](uint32_t c) { h[c]++; },
                            [&](uint32_t len) { uint32_t lc, eb, ev; fz_len_code(len, lc, eb, ev); h[257 + lc]++; });
             }
+            if (hm_hist_sample > 1) {
+                if (k % hm_hist_sample != 0) continue;
+                for (int i = 0; i < 288; i++) h[i] *= hm_hist_sample;
+            }
             for (int i = 0; i < 288; i++) st->hist[i] += h[i];
+        }
+        if (hm_hist_sample > 1) {
+            for (int i = 0; i < 256; i++) st->hist[i] += 1;
+            for (uint32_t q = 1; q <= FZ_E2_MAX_QUADS; q++) { uint32_t lc, eb, ev; fz_len_code(4 * q, lc, eb, ev); if (st->hist[257 + lc] == 0) st->hist[257 + lc] = 1; }
         }
         st->hist[FZ_EOB] = nsub;
         memset(gc, 0xEE, sizeof(FzGroupCode));
