@@ -52,7 +52,7 @@ struct mzb_ctx {
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist, err_partial;
     bool zero_hist_ready = false;
     // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -149,6 +149,13 @@ static void release(DevBuf &b)
     b.p = nullptr; b.cap = 0;
 }
 
+extern "C" int mzb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 extern "C" const char *mzb_version(void) { return "mrczip_b200 0.1 (sm_100a; sub-block " "16 KiB" ")"; }
 
 extern "C" const char *mzb_strerror(int code)
@@ -212,7 +219,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist, &c->err_partial};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
@@ -416,6 +423,7 @@ static void fill_compress_stats(mzb_ctx *c, uint64_t nwords, uint64_t nchunks_to
     c->stats.streams = (uint32_t)nchunks_total * FZ_PLANES;
     c->stats.raw_streams = c->h_status->n_raw_streams;
     c->stats.stored_subblocks = c->h_status->n_stored_sub;
+    c->stats.zero_subblocks = c->h_status->n_zero_sub;
     c->stats.kernel_launches = launches;
 }
 
@@ -749,4 +757,121 @@ extern "C" void *mzb_host_alloc(size_t bytes)
 extern "C" void mzb_host_free(void *p)
 {
     if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// error report (reference src/tool/erroranalysis.c:188-220) and the MRC header fields (src/tool/mrcviewer.c:20-71)
+static void err_merge(FzErrPartial &r, const FzErrPartial &p, uint64_t base)
+{
+    if (p.i_abs != ~0ull && (p.max_abs > r.max_abs || (p.max_abs == r.max_abs && p.i_abs + base < r.i_abs))) { r.max_abs = p.max_abs; r.i_abs = p.i_abs + base; }
+    if (p.i_rel != ~0ull && (p.max_rel > r.max_rel || (p.max_rel == r.max_rel && p.i_rel + base < r.i_rel))) { r.max_rel = p.max_rel; r.i_rel = p.i_rel + base; }
+    r.sum += p.sum;
+    r.nan += p.nan;
+}
+
+static void err_finish(const FzErrPartial &r, uint64_t nwords, float a1, float a2, float r1, float r2, mzb_error_report_t *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->count = nwords;
+    out->nan_count = r.nan;
+    out->max_abs_index = r.i_abs;
+    out->max_rel_index = r.i_rel;
+    out->max_abs_err = r.i_abs == ~0ull ? 0.f : r.max_abs;
+    out->max_rel_err = r.i_rel == ~0ull ? 0.f : r.max_rel;
+    out->max_abs_n1 = a1; out->max_abs_n2 = a2; out->max_rel_n1 = r1; out->max_rel_n2 = r2;
+    out->sum_abs_err = r.sum;
+}
+
+static float err_other_value(uint32_t a, uint64_t i, int bits, uint32_t exempt)
+{
+    const uint32_t b = i >= exempt ? (a & fz_mask_for_bits(bits)) : a;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+extern "C" int mzb_error_report_device(mzb_ctx *c, const void *d_orig, const void *d_other, uint64_t nwords, int bits,
+                                       uint32_t exempt_words, mzb_error_report_t *out)
+{
+    if (!c || !out || !d_orig || ((uintptr_t)d_orig & 3) || ((uintptr_t)d_other & 3) || (!d_other && (bits < 0 || bits > 32)))
+        return MZB_E_ARG;
+    FZ_CHECK(cudaSetDevice(c->device));
+    FzErrPartial r;
+    r.max_abs = -1.f; r.max_rel = -1.f; r.i_abs = ~0ull; r.i_rel = ~0ull; r.sum = 0.0; r.nan = 0;
+    float v[4] = {0, 0, 0, 0};
+    if (nwords) {
+        int rc;
+        if ((rc = ensure(c->err_partial, (size_t)fz_error_partials() * sizeof(FzErrPartial)))) return rc;
+        fz_launch_error((const uint32_t *)d_orig, (const uint32_t *)d_other, nwords, fz_mask_for_bits(d_other ? 0 : bits), exempt_words,
+                        (FzErrPartial *)c->err_partial.p, c->stream);
+        FZ_CHECK(cudaGetLastError());
+        FzErrPartial p;
+        FZ_CHECK(cudaMemcpyAsync(&p, c->err_partial.p, sizeof(p), cudaMemcpyDeviceToHost, c->stream));
+        FZ_CHECK(cudaStreamSynchronize(c->stream));
+        err_merge(r, p, 0);
+        const uint64_t idx[2] = {r.i_abs, r.i_rel};
+        for (int k = 0; k < 2; k++) {
+            if (idx[k] == ~0ull) continue;
+            uint32_t a = 0, b = 0;
+            FZ_CHECK(cudaMemcpy(&a, (const uint32_t *)d_orig + idx[k], 4, cudaMemcpyDeviceToHost));
+            memcpy(&v[2 * k], &a, 4);
+            if (d_other) { FZ_CHECK(cudaMemcpy(&b, (const uint32_t *)d_other + idx[k], 4, cudaMemcpyDeviceToHost)); memcpy(&v[2 * k + 1], &b, 4); }
+            else v[2 * k + 1] = err_other_value(a, idx[k], bits, exempt_words);
+        }
+    }
+    err_finish(r, nwords, v[0], v[1], v[2], v[3], out);
+    return MZB_OK;
+}
+
+extern "C" int mzb_error_report_host(mzb_ctx *c, const void *h_orig, const void *h_other, uint64_t nwords, int bits,
+                                     uint32_t exempt_words, mzb_error_report_t *out)
+{
+    if (!c || !out || !h_orig || (!h_other && (bits < 0 || bits > 32))) return MZB_E_ARG;
+    FZ_CHECK(cudaSetDevice(c->device));
+    const uint64_t batch = 64ull << 20;   // words per batch (256 MiB per buffer)
+    const uint64_t bw = nwords < batch ? nwords : batch;
+    int rc;
+    if (nwords && ((rc = ensure(c->io_in, bw * 4 + 16)) || (h_other && (rc = ensure(c->io_out, bw * 4 + 16))) ||
+                   (rc = ensure(c->err_partial, (size_t)fz_error_partials() * sizeof(FzErrPartial)))))
+        return rc;
+    FzErrPartial r;
+    r.max_abs = -1.f; r.max_rel = -1.f; r.i_abs = ~0ull; r.i_rel = ~0ull; r.sum = 0.0; r.nan = 0;
+    const uint32_t *ho = (const uint32_t *)h_orig, *hx = (const uint32_t *)h_other;
+    for (uint64_t w0 = 0; w0 < nwords; w0 += bw) {
+        const uint64_t n = nwords - w0 < bw ? nwords - w0 : bw;
+        FZ_CHECK(cudaMemcpyAsync(c->io_in.p, ho + w0, n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (hx) FZ_CHECK(cudaMemcpyAsync(c->io_out.p, hx + w0, n * 4, cudaMemcpyHostToDevice, c->stream));
+        const uint64_t ex = exempt_words > w0 ? exempt_words - w0 : 0;
+        fz_launch_error((const uint32_t *)c->io_in.p, hx ? (const uint32_t *)c->io_out.p : nullptr, n, fz_mask_for_bits(hx ? 0 : bits), ex,
+                        (FzErrPartial *)c->err_partial.p, c->stream);
+        FzErrPartial p;
+        FZ_CHECK(cudaMemcpyAsync(&p, c->err_partial.p, sizeof(p), cudaMemcpyDeviceToHost, c->stream));
+        FZ_CHECK(cudaStreamSynchronize(c->stream));
+        FZ_CHECK(cudaGetLastError());
+        err_merge(r, p, w0);
+    }
+    float v[4] = {0, 0, 0, 0};
+    const uint64_t idx[2] = {r.i_abs, r.i_rel};
+    for (int k = 0; k < 2; k++) {
+        if (idx[k] == ~0ull) continue;
+        memcpy(&v[2 * k], ho + idx[k], 4);
+        if (hx) memcpy(&v[2 * k + 1], hx + idx[k], 4);
+        else v[2 * k + 1] = err_other_value(ho[idx[k]], idx[k], bits, exempt_words);
+    }
+    err_finish(r, nwords, v[0], v[1], v[2], v[3], out);
+    return MZB_OK;
+}
+
+extern "C" int mzb_mrc_parse(const void *header, size_t len, mzb_mrc_info *out)
+{
+    if (!header || !out || len < 1024) return MZB_E_ARG;
+    int32_t w[24];
+    memcpy(w, header, sizeof(w));
+    memset(out, 0, sizeof(*out));
+    out->nx = w[0]; out->ny = w[1]; out->nz = w[2]; out->mode = w[3]; out->next = w[23];
+    out->is_float32 = w[3] == 2;
+    out->data_offset = 1024ull + (uint64_t)(w[23] > 0 ? w[23] : 0);
+    const bool mode_ok = w[3] == 0 || w[3] == 1 || w[3] == 2 || w[3] == 3 || w[3] == 4 || w[3] == 6 || w[3] == 12 || w[3] == 16 || w[3] == 101;
+    if (w[0] <= 0 || w[1] <= 0 || w[2] <= 0 || !mode_ok || w[23] < 0) return MZB_E_FORMAT;
+    return MZB_OK;
 }

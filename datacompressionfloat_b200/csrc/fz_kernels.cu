@@ -1070,6 +1070,7 @@ fz_layout_streams_kernel(uint32_t *__restrict__ sizes, FzBatchGeom g, uint32_t *
         // one iteration = one group: all-zero sub-blocks take size (and fragment) of the group's first one
         const uint32_t zmask = __ballot_sync(0xffffffffu, (raw & FZ_SIZE_ZERO_FLAG) != 0);
         if (zmask) {
+            if (lane == 0) atomicAdd(&status->n_zero_sub, (unsigned int)__popc(zmask));
             const int leader = __ffs((int)zmask) - 1;
             const uint32_t lv = __shfl_sync(0xffffffffu, raw, leader);
             if ((raw & FZ_SIZE_ZERO_FLAG) && lane != leader) {
@@ -2289,4 +2290,97 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
         fz_rawcopy_kernel<<<(total + 3) / 4, 128, 0, st>>>(container, container_size, g, stream_hdr, stream_off, planes, status);
         if (mark) mark(mark_user, FZ_ST_RAWCOPY);
     }
+}
+
+// =================================================================================================
+// error report: what the reference's erroranalysis tool prints after a lossy round trip (src/tool/erroranalysis.c:188-220,
+// calculateDiff): err = |n2 - n1|, relative error err / |n1| where |n1| > 10E-4 (0 elsewhere); here the maxima, where they
+// are, and the sum, in one HBM-bound pass.  `other` == nullptr compares the words with their own masked form (n2 = n1 &
+// mask behind the exempt header words): the error of apply_mask (workers.c:82-101) without a round trip.
+// =================================================================================================
+#define FZ_ERR_THREADS 256
+#define FZ_ERR_BLOCKS (FZ_SM_COUNT * 8)
+
+__device__ __forceinline__ void fz_err_better(float &best, unsigned long long &bi, float v, unsigned long long i)
+{
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+}
+
+__global__ void __launch_bounds__(FZ_ERR_THREADS)
+fz_error_kernel(const uint32_t *__restrict__ orig, const uint32_t *__restrict__ other, uint64_t nwords, uint32_t mask,
+                uint64_t exempt, FzErrPartial *__restrict__ partial)
+{
+    __shared__ FzErrPartial sh[FZ_ERR_THREADS / 32];
+    float ma = -1.f, mr = -1.f, sum = 0.f;
+    unsigned long long ia = ~0ull, ir = ~0ull, nan = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * FZ_ERR_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * FZ_ERR_THREADS + threadIdx.x; i < nwords; i += stride) {
+        const uint32_t a = fz_ld_stream32(orig + i);
+        const uint32_t b = other ? fz_ld_stream32(other + i) : (i >= exempt ? (a & mask) : a);
+        const float n1 = __uint_as_float(a), n2 = __uint_as_float(b);
+        const float err = fabsf(n2 - n1);
+        if (err != err) { nan++; continue; }             // NaN or Inf - Inf: counted, not ranked
+        const float rel = fabsf(n1) > 10E-4f ? err / fabsf(n1) : 0.f;
+        sum += err;
+        fz_err_better(ma, ia, err, i);
+        if (rel == rel) fz_err_better(mr, ir, rel, i);
+    }
+    double dsum = (double)sum;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, ma, d), orl = __shfl_xor_sync(0xffffffffu, mr, d);
+        const unsigned long long oia = __shfl_xor_sync(0xffffffffu, ia, d), oir = __shfl_xor_sync(0xffffffffu, ir, d);
+        fz_err_better(ma, ia, oa, oia);
+        fz_err_better(mr, ir, orl, oir);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, d);
+        nan += __shfl_xor_sync(0xffffffffu, nan, d);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[warp].max_abs = ma; sh[warp].i_abs = ia; sh[warp].max_rel = mr; sh[warp].i_rel = ir; sh[warp].sum = dsum; sh[warp].nan = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        FzErrPartial r = sh[0];
+        for (int w = 1; w < FZ_ERR_THREADS / 32; w++) {
+            fz_err_better(r.max_abs, r.i_abs, sh[w].max_abs, sh[w].i_abs);
+            fz_err_better(r.max_rel, r.i_rel, sh[w].max_rel, sh[w].i_rel);
+            r.sum += sh[w].sum;
+            r.nan += sh[w].nan;
+        }
+        partial[blockIdx.x] = r;
+    }
+}
+
+// one block folds the per-block results into partial[0]
+__global__ void __launch_bounds__(FZ_ERR_THREADS) fz_error_fold_kernel(FzErrPartial *__restrict__ partial, uint32_t n)
+{
+    __shared__ FzErrPartial sh[FZ_ERR_THREADS];
+    FzErrPartial r;
+    r.max_abs = -1.f; r.max_rel = -1.f; r.i_abs = ~0ull; r.i_rel = ~0ull; r.sum = 0.0; r.nan = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += FZ_ERR_THREADS) {
+        const FzErrPartial p = partial[i];
+        fz_err_better(r.max_abs, r.i_abs, p.max_abs, p.i_abs);
+        fz_err_better(r.max_rel, r.i_rel, p.max_rel, p.i_rel);
+        r.sum += p.sum;
+        r.nan += p.nan;
+    }
+    sh[threadIdx.x] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < FZ_ERR_THREADS; t++) {
+            fz_err_better(r.max_abs, r.i_abs, sh[t].max_abs, sh[t].i_abs);
+            fz_err_better(r.max_rel, r.i_rel, sh[t].max_rel, sh[t].i_rel);
+            r.sum += sh[t].sum;
+            r.nan += sh[t].nan;
+        }
+        partial[0] = r;
+    }
+}
+
+uint32_t fz_error_partials() { return FZ_ERR_BLOCKS; }
+
+void fz_launch_error(const uint32_t *orig, const uint32_t *other, uint64_t nwords, uint32_t mask, uint64_t exempt,
+                     FzErrPartial *partial, cudaStream_t st)
+{
+    fz_error_kernel<<<FZ_ERR_BLOCKS, FZ_ERR_THREADS, 0, st>>>(orig, other, nwords, mask, exempt, partial);
+    fz_error_fold_kernel<<<1, FZ_ERR_THREADS, 0, st>>>(partial, FZ_ERR_BLOCKS);
 }

@@ -29,6 +29,8 @@ struct FzStatus {
     unsigned int n_stored_sub;    // sub-blocks emitted as stored blocks
     unsigned int n_raw_streams;   // streams written RAW
     unsigned int n_blockpar;      // general streams decoded block-parallel (the rest took the serial inflater)
+    unsigned int n_zero_sub;      // sub-blocks found to be all zero bytes (encode)
+    unsigned int pad0;
 };
 
 // optional per-stage timing hook: called after the launches of a stage were enqueued
@@ -112,3 +114,15 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, co
                              cudaStream_t st);
 
 size_t fz_encode_smem_bytes();
+
+// ---- error report (reference src/tool/erroranalysis.c:188-220)
+struct FzErrPartial {
+    float max_abs, max_rel;
+    unsigned long long i_abs, i_rel;   // word index of the maxima (~0: none)
+    double sum;                        // sum of the absolute errors
+    unsigned long long nan;            // pairs whose error is not a number
+};
+uint32_t fz_error_partials();
+// other == nullptr: compare the words with their own masked form (mask behind `exempt` words); result in partial[0]
+void fz_launch_error(const uint32_t *orig, const uint32_t *other, uint64_t nwords, uint32_t mask, uint64_t exempt,
+                     FzErrPartial *partial, cudaStream_t st);

@@ -29,10 +29,11 @@ class MzbError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("chunks", C.c_uint32), ("streams", C.c_uint32),
                 ("raw_streams", C.c_uint32), ("stored_subblocks", C.c_uint32), ("general_streams", C.c_uint32),
-                ("fast_failed", C.c_uint32), ("kernel_launches", C.c_uint32), ("blockpar_streams", C.c_uint32)]
+                ("fast_failed", C.c_uint32), ("kernel_launches", C.c_uint32), ("blockpar_streams", C.c_uint32),
+                ("zero_subblocks", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "pad"}
+        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k not in ("pad", "reserved")}
 
 
 class CtxT(C.Structure):
@@ -52,7 +53,7 @@ EXPORTS = [
     "init_context", "reset_context", "update_context", "print_context_info", "init_mrczip_header",
     "read_mrczip_header", "write_mrczip_header", "print_mrczip_header", "get_file_size", "now_sec",
     "isTestThroughput",
-    "mzb_create", "mzb_create_on_stream", "mzb_destroy", "mzb_set_io_threads", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_compress_bound",
+    "mzb_create", "mzb_create_on_stream", "mzb_destroy", "mzb_set_io_threads", "mzb_device_count", "mzb_set_devices", "mzb_mrc_parse", "mzb_set_mrc_aware", "mzb_error_report_device", "mzb_error_report_host", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_compress_bound",
     "mzb_compress_device", "mzb_decompress_device", "mzb_mask_split_device", "mzb_merge_device",
     "mzb_compress_host", "mzb_decompress_host", "mzb_host_alloc", "mzb_host_free", "mzb_last_stats",
     "mzb_set_profiling", "mzb_stage_count", "mzb_stage_name", "mzb_stage_ms",

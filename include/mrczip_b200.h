@@ -115,6 +115,14 @@ int mzb_set_batch_chunks(mzb_ctx *ctx, uint32_t chunks);
 /* kernel variant selectors used by the benchmarks (0 = default) */
 int mzb_set_variant(mzb_ctx *ctx, int split_variant, int merge_variant);
 
+/* CUDA devices visible to the process (0 without a driver / device). */
+int mzb_device_count(void);
+/* The devices the FILE* entry points use (process wide).  Default (also n = 0): every visible device, or the
+ * environment variables MRCZIP_DEVICES=0,2,3 / MRCZIP_DEVICE=<n>.  Calling threads are dealt devices round robin
+ * (mrc_tarx's N workers, reference mrc_tarx.c:145-161, land on N GPUs); one file of more than one 16-chunk batch is
+ * cut over all of them, batch by batch, and its container is byte-identical to the one-device container. */
+int mzb_set_devices(const int *devices, int n);
+
 /* Threads that pread / pwrite one batch of the FILE* entry points (1..16; 0 = back to the default: the environment
  * variable MRCZIP_IO_THREADS, else 4).  Process wide. */
 int mzb_set_io_threads(int n);
@@ -156,6 +164,44 @@ int mzb_compress_host(mzb_ctx *ctx, const void *h_words, uint64_t nwords, int bi
 int mzb_decompress_host(mzb_ctx *ctx, const void *h_in, size_t in_size, int has_file_header, uint32_t chk,
                         uint64_t nwords, void *h_words_out, uint64_t out_cap_words, uint64_t *nwords_out);
 
+/* ---- MRC awareness and the error report ------------------------------------------------------------
+ * The reference treats the first 1024 bytes of every file as the MRC header and masks everything behind it
+ * (workers.c:90-94), whatever the header says.  mzb_mrc_parse reads the fields that matter (reference
+ * src/tool/mrcviewer.c:20-71: nx, ny, nz, mod at words 0..3, next = bytes of extended header at word 23). */
+typedef struct {
+    int32_t nx, ny, nz;
+    int32_t mode;          /* 2 = float32, the only mode whose low mantissa bits may be erased */
+    int32_t next;          /* bytes of extended header between the 1024-byte header and the data */
+    int32_t is_float32;
+    uint64_t data_offset;  /* 1024 + next */
+} mzb_mrc_info;
+/* header: at least 1024 bytes.  MZB_E_FORMAT when the fields are not those of an MRC header (non-positive
+ * dimensions, unknown mode, negative next). */
+int mzb_mrc_parse(const void *header, size_t len, mzb_mrc_info *out);
+/* Process wide, default 0 (byte-compatible with the reference).  1: run_compress / zip_compress read the header and
+ * (a) leave 1024 + next bytes unmasked instead of 1024, (b) erase no bits at all when the mode is not float32
+ * (the file is then stored losslessly; a note goes to stderr), (c) fall back to the reference's behaviour when the
+ * first 1024 bytes are not an MRC header.  The environment variable MRCZIP_MRC_AWARE=1 does the same. */
+int mzb_set_mrc_aware(int on);
+
+/* What the reference's erroranalysis tool reports after a lossy round trip (src/tool/erroranalysis.c:188-220):
+ * err = |n2 - n1|, relative error err / |n1| where |n1| > 10E-4 and 0 elsewhere; here the two maxima, where they
+ * are, and the sum, from one pass on the GPU. */
+typedef struct {
+    uint64_t count;          /* pairs compared */
+    uint64_t nan_count;      /* pairs whose error is not a number (NaN on either side, Inf - Inf): not ranked */
+    float max_abs_err, max_abs_n1, max_abs_n2, max_rel_err, max_rel_n1, max_rel_n2;
+    uint64_t max_abs_index, max_rel_index;   /* word index (lowest on ties); ~0 when nothing was ranked */
+    double sum_abs_err;      /* mean absolute error = sum_abs_err / (count - nan_count) */
+} mzb_error_report_t;
+/* d_orig / d_other: nwords float32 each on the device.  d_other == NULL: n2 = n1 with `bits` low bits erased behind
+ * `exempt_words` words -- the error of the mask itself, no round trip needed (bits is ignored otherwise). */
+int mzb_error_report_device(mzb_ctx *ctx, const void *d_orig, const void *d_other, uint64_t nwords, int bits,
+                            uint32_t exempt_words, mzb_error_report_t *out);
+/* the same on host buffers (staged through the device in batches) */
+int mzb_error_report_host(mzb_ctx *ctx, const void *h_orig, const void *h_other, uint64_t nwords, int bits,
+                          uint32_t exempt_words, mzb_error_report_t *out);
+
 /* pinned (page-locked) host memory for callers written in C without the CUDA headers */
 void *mzb_host_alloc(size_t bytes);
 void mzb_host_free(void *p);
@@ -170,6 +216,8 @@ typedef struct {
     uint32_t fast_failed;      /* decode: streams whose sub-block decode failed validation (fell back) */
     uint32_t kernel_launches;  /* kernels launched by the call */
     uint32_t blockpar_streams; /* decode: general streams inflated block-parallel (the rest: one thread per stream) */
+    uint32_t zero_subblocks;   /* encode: 16 KiB sub-blocks that are all zero bytes (coded once per group of 32) */
+    uint32_t reserved;
 } mzb_stats;
 int mzb_last_stats(mzb_ctx *ctx, mzb_stats *out);
 

@@ -23,6 +23,9 @@ FILE_HEADER_BYTES = 17
 def build(ref: bool = True) -> None:
     """Compile the restatement (and, when /root/reference exists, the reference itself)."""
     targets = ["all"] + (["ref"] if ref else [])
+    # the reference's own mains linked against the product library (the drop-in proof): needs the built .so
+    if ref and (HERE.parent / "datacompressionfloat_b200" / "libmrczip_b200.so").exists():
+        targets.append("dropin")
     subprocess.run(["make", "-s", "-C", str(HERE)] + targets, check=True)
 
 

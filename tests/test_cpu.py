@@ -450,3 +450,28 @@ def test_model_blockpar_tile_records_and_pool_exhaustion(hostmodel):
             assert (hostmodel.table_blocks() == ncand) == expect_all, (cap, hostmodel.table_blocks(), ncand)
     finally:
         hostmodel.set_tile_pool_cap(4096)
+
+
+def test_mrc_header_parse_needs_no_gpu():
+    """mzb_mrc_parse (reference src/tool/mrcviewer.c:20-71: nx, ny, nz, mod at words 0..3, next at word 23)"""
+    import ctypes as C
+    from datacompressionfloat_b200 import lib
+    L = lib.load()
+
+    class Info(C.Structure):
+        _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("mode", C.c_int32), ("next", C.c_int32),
+                    ("is_float32", C.c_int32), ("data_offset", C.c_uint64)]
+    h = np.zeros(256, dtype=np.int32)
+    h[0:3] = (4096, 4096, 40)
+    h[3] = 2
+    h[23] = 131072
+    info = Info()
+    assert L.mzb_mrc_parse(C.c_void_p(h.ctypes.data), C.c_size_t(1024), C.byref(info)) == 0
+    assert (info.nx, info.ny, info.nz, info.mode, info.next, info.is_float32, info.data_offset) == (4096, 4096, 40, 2, 131072, 1, 1024 + 131072)
+    h[3] = 6
+    assert L.mzb_mrc_parse(C.c_void_p(h.ctypes.data), C.c_size_t(1024), C.byref(info)) == 0 and info.is_float32 == 0
+    h[3] = 77
+    assert L.mzb_mrc_parse(C.c_void_p(h.ctypes.data), C.c_size_t(1024), C.byref(info)) == lib.E_FORMAT
+    h[3] = 2; h[1] = 0
+    assert L.mzb_mrc_parse(C.c_void_p(h.ctypes.data), C.c_size_t(1024), C.byref(info)) == lib.E_FORMAT
+    assert L.mzb_mrc_parse(C.c_void_p(h.ctypes.data), C.c_size_t(512), C.byref(info)) == lib.E_ARG

@@ -2,7 +2,7 @@
 # developer helper: bench line per (distribution, bits) for the results table
 for kb in "$@"; do
   k=${kb:0:1}; b=${kb:1}
-  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --kind $k --bits $b 2>/dev/null > /tmp/m_$kb.json
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-matrix --kind $k --bits $b 2>/dev/null > /tmp/m_$kb.json
   python - "$kb" <<'PY'
 import sys, json
 kb = sys.argv[1]
