@@ -1,8 +1,8 @@
 /*
  * mrc_tarx_b200 -- multi-file front end with the reference's flags (src/main/mrc_tarx.c:345-420):
  *     mrc_tarx_b200 -i <file list> -o <output dir> [-t zip|unzip] [-b bits] [-n threads] [-d 0|1]
- * One worker thread per file at a time, like the reference's pool (mrc_tarx.c:41-176, queue adapt.c:337-356);
- * every worker owns a GPU context, so files overlap on the device.  Output names follow
+ * N worker threads like the reference's pool (mrc_tarx.c:41-176, queue adapt.c:337-356); every worker owns a GPU
+ * context (on its own GPU when there are several), and small files are gathered into shared passes of the kernels.  Output names follow
  * adapt.c:297-304: x.mrc -> DIR/x.mrc.zip, x.mrc.zip -> DIR/x.mrc.  -d 1 sets isTestThroughput (no writes).
  */
 #include <getopt.h>
@@ -17,7 +17,7 @@ typedef struct {
     char **srcs, **dsts;
     int n, next;
     pthread_mutex_t lock;
-    int unzip, bits;
+    int unzip, bits, group;
     ctx_t total;
     int failed;
 } job_t;
@@ -60,6 +60,11 @@ static int load_list(job_t *j, const char *list, const char *dir)
     return 0;
 }
 
+/* Workers take runs of GROUP consecutive list entries and hand them to zip_compress_many / zip_uncompress_many: small
+ * files of a run share passes of the GPU kernels (at most 32 chunks per pass), large ones go through one by one --
+ * and every worker thread sits on its own GPU when there are several (the library deals devices round robin). */
+#define GROUP 32
+
 static void *worker(void *arg)
 {
     job_t *j = (job_t *)arg;
@@ -67,10 +72,14 @@ static void *worker(void *arg)
     init_context(&ctx);
     for (;;) {
         pthread_mutex_lock(&j->lock);
-        const int i = j->next < j->n ? j->next++ : -1;
+        const int i0 = j->next;
+        int cnt = j->n - i0 < j->group ? j->n - i0 : j->group;
+        if (cnt < 0) cnt = 0;
+        j->next += cnt;
         pthread_mutex_unlock(&j->lock);
-        if (i < 0) break;
-        const int rc = j->unzip ? zip_uncompress(&ctx, j->srcs[i], j->dsts[i]) : zip_compress(&ctx, j->srcs[i], j->dsts[i], j->bits);
+        if (cnt == 0) break;
+        const int rc = j->unzip ? zip_uncompress_many(&ctx, cnt, (const char *const *)j->srcs + i0, (const char *const *)j->dsts + i0)
+                                : zip_compress_many(&ctx, cnt, (const char *const *)j->srcs + i0, (const char *const *)j->dsts + i0, j->bits);
         if (rc != 0) { pthread_mutex_lock(&j->lock); j->failed++; pthread_mutex_unlock(&j->lock); }
     }
     pthread_mutex_lock(&j->lock);
@@ -103,6 +112,8 @@ int main(int argc, char *argv[])
     j.unzip = strcmp(op, "unzip") == 0;
     if (load_list(&j, list, dir) != 0) return 1;
     if (threads < 1) threads = 1;
+    /* runs of list entries per worker turn: everything in GROUPs, but never fewer turns than threads */
+    j.group = j.n / threads < GROUP ? (j.n / threads > 0 ? j.n / threads : 1) : GROUP;
     if (threads > j.n) threads = j.n > 0 ? j.n : 1;
     pthread_mutex_init(&j.lock, NULL);
     init_context(&j.total);

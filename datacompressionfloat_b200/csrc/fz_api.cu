@@ -52,7 +52,7 @@ struct mzb_ctx {
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist, err_partial;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist, err_partial, chunk_tab;
     bool zero_hist_ready = false;
     // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -219,7 +219,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist, &c->err_partial};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist, &c->err_partial, &c->chunk_tab};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
@@ -295,6 +295,8 @@ static FzBatchGeom make_geom(uint32_t nchunks, uint32_t chk, uint64_t nwords_bat
     g.last_n = (uint32_t)(nwords_batch - (uint64_t)(nchunks - 1) * chk);
     g.nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
     g.plane_stride = plane_stride;
+    g.chunk_n = nullptr;
+    g.chunk_exempt = nullptr;
     return g;
 }
 
@@ -347,10 +349,18 @@ static int compress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t *p
     return MZB_OK;
 }
 
+static unsigned long long g_passes[2] = {0, 0};
+extern "C" void mzb_pass_counts(uint64_t *zp, uint64_t *up)
+{
+    if (zp) *zp = __atomic_load_n(&g_passes[0], __ATOMIC_RELAXED);
+    if (up) *up = __atomic_load_n(&g_passes[1], __ATOMIC_RELAXED);
+}
+
 static void compress_enqueue_batch(mzb_ctx *c, const uint32_t *d_words, uint64_t nw, uint32_t nb, uint32_t chk, uint64_t pstride,
                                    uint32_t mask, uint64_t exempt, uint8_t *d_out, size_t out_cap)
 {
     const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
+    __atomic_fetch_add(&g_passes[0], 1ull, __ATOMIC_RELAXED);
     fz_launch_split(d_words, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
     prof_mark(c, FZ_ST_SPLIT);
     if (!c->zero_hist_ready) { fz_launch_zero_hist((uint32_t *)c->zero_hist.p, c->stream); c->zero_hist_ready = true; }
@@ -401,6 +411,7 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
 static void decompress_enqueue_batch(mzb_ctx *c, const uint8_t *d_in, size_t in_size, FzBatchGeom g, const FzInflateBufs &ib,
                                      uint32_t *d_words_out, bool in_place_raw)
 {
+    __atomic_fetch_add(&g_passes[1], 1ull, __ATOMIC_RELAXED);
     fz_launch_walk(d_in, in_size, g, (uint32_t *)c->stream_hdr.p, (unsigned long long *)c->stream_off.p, c->d_status, c->stream);
     prof_mark(c, FZ_ST_WALK);
     fz_launch_inflate(d_in, in_size, g, (const uint32_t *)c->stream_hdr.p, (const unsigned long long *)c->stream_off.p, ib,
@@ -873,5 +884,152 @@ extern "C" int mzb_mrc_parse(const void *header, size_t len, mzb_mrc_info *out)
     out->data_offset = 1024ull + (uint64_t)(w[23] > 0 ? w[23] : 0);
     const bool mode_ok = w[3] == 0 || w[3] == 1 || w[3] == 2 || w[3] == 3 || w[3] == 4 || w[3] == 6 || w[3] == 12 || w[3] == 16 || w[3] == 101;
     if (w[0] <= 0 || w[1] <= 0 || w[2] <= 0 || !mode_ok || w[23] < 0) return MZB_E_FORMAT;
+    return MZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// several small inputs in one pass of the kernels: every chunk of the batch gets its own word count and exemption
+// (FzBatchGeom::chunk_n / chunk_exempt), item i owns the chunk slots [first[i], first[i + 1])
+extern "C" int mzb_compress_host_many(mzb_ctx *c, mzb_zip_item *items, uint32_t n, int bits, uint32_t chk, int write_file_header)
+{
+    if (!c || (!items && n) || bits < 0 || bits > 32 || chk == 0 || chk >= 0x80000000u || (chk % 16u)) return MZB_E_ARG;
+    memset(&c->stats, 0, sizeof(c->stats));
+    std::vector<uint32_t> first(n + 1, 0), tab;
+    for (uint32_t i = 0; i < n; i++) {
+        items[i].out_size = 0;
+        if (!items[i].h_out || (items[i].nwords && !items[i].h_words)) return MZB_E_ARG;
+        first[i + 1] = first[i] + (uint32_t)((items[i].nwords + chk - 1) / chk);
+    }
+    const uint32_t nchunks = first[n];
+    if (nchunks > c->batch_chunks) return MZB_E_ARG;
+    if (nchunks == 0) return MZB_OK;   // empty inputs write nothing, not even the header (workers.c:757-764)
+    FZ_CHECK(cudaSetDevice(c->device));
+    tab.resize(2 * (size_t)nchunks);
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t k = first[i]; k < first[i + 1]; k++) {
+            const uint64_t w0 = (uint64_t)(k - first[i]) * chk;
+            tab[k] = (uint32_t)(items[i].nwords - w0 < chk ? items[i].nwords - w0 : chk);
+            tab[nchunks + k] = (uint32_t)(items[i].exempt_words > w0 ? (items[i].exempt_words - w0 < chk ? items[i].exempt_words - w0 : chk) : 0);
+        }
+    const size_t slot_bytes = (size_t)chk * 4;
+    const size_t bound = (size_t)nchunks * (FZ_CHUNK_HEADER_BYTES + slot_bytes) + 64;
+    uint64_t pstride;
+    int rc;
+    if ((rc = compress_reserve(c, nchunks, chk, &pstride)) || (rc = ensure(c->io_in, (size_t)nchunks * slot_bytes + 256)) ||
+        (rc = ensure(c->io_out, bound + 256)) || (rc = ensure(c->chunk_tab, tab.size() * 4)) ||
+        (rc = ensure(c->stream_hdr, (size_t)nchunks * FZ_PLANES * 4)))
+        return rc;
+    if ((rc = status_reset(c, 0))) return rc;
+    prof_begin(c);
+    FZ_CHECK_PIPE(cudaMemcpyAsync(c->chunk_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    for (uint32_t i = 0; i < n; i++)
+        if (items[i].nwords)
+            FZ_CHECK_PIPE(cudaMemcpyAsync((uint8_t *)c->io_in.p + (size_t)first[i] * slot_bytes, items[i].h_words, items[i].nwords * 4,
+                                          cudaMemcpyHostToDevice, c->stream));
+    FzBatchGeom g = make_geom(nchunks, chk, (uint64_t)nchunks * chk, pstride);
+    g.chunk_n = (const uint32_t *)c->chunk_tab.p;
+    g.chunk_exempt = g.chunk_n + nchunks;
+    const uint32_t mask = fz_mask_for_bits(bits);
+    uint8_t *d_out = (uint8_t *)c->io_out.p;
+    __atomic_fetch_add(&g_passes[0], 1ull, __ATOMIC_RELAXED);
+    fz_launch_split_slots((const uint32_t *)c->io_in.p, nchunks, chk, mask, g.chunk_exempt, (uint8_t *)c->planes.p, pstride, c->stream);
+    prof_mark(c, FZ_ST_SPLIT);
+    if (!c->zero_hist_ready) { fz_launch_zero_hist((uint32_t *)c->zero_hist.p, c->stream); c->zero_hist_ready = true; }
+    uint32_t zero_planes = 0;
+    for (int j = 0; j < FZ_PLANES; j++)
+        if (((mask >> (8 * j)) & 0xffu) == 0) zero_planes |= 1u << j;
+    fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p, (uint32_t *)c->sizes.p,
+                     (const uint32_t *)c->zero_hist.p, zero_planes, 0, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_ENCODE);
+    fz_launch_layout((uint32_t *)c->sizes.p, g, (uint32_t *)c->sub_off.p, (uint32_t *)c->stream_hdr.p, (unsigned long long *)c->stream_off.p,
+                     d_out, bound, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_LAYOUT);
+    fz_launch_gather((const uint8_t *)c->planes.p, (const uint8_t *)c->scratch.p, (const uint32_t *)c->sizes.p, (const uint32_t *)c->sub_off.p,
+                     (const uint32_t *)c->stream_hdr.p, (const unsigned long long *)c->stream_off.p, g, d_out, c->d_status, c->stream);
+    prof_mark(c, FZ_ST_GATHER);
+    // record sizes of every chunk -> where each item's records lie in the batch's container
+    std::vector<uint32_t> hdr((size_t)nchunks * FZ_PLANES);
+    FZ_CHECK_PIPE(cudaMemcpyAsync(hdr.data(), c->stream_hdr.p, hdr.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = status_fetch(c))) return pipe_fail(c, rc);
+    prof_collect(c);
+    fill_compress_stats(c, 0, nchunks, 8);
+    if (c->h_status->error) return c->h_status->error;
+    uint64_t off = 0;
+    int result = MZB_OK;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t bytes = 0;
+        for (uint32_t k = first[i]; k < first[i + 1]; k++) {
+            bytes += FZ_CHUNK_HEADER_BYTES;
+            for (int j = 0; j < FZ_PLANES; j++) bytes += hdr[(size_t)k * FZ_PLANES + j] & ~FZ_RAW_FLAG;
+        }
+        c->stats.bytes_in += items[i].nwords * 4;
+        if (items[i].nwords == 0) continue;
+        const size_t hb = write_file_header ? MZB_FILE_HEADER_BYTES : 0;
+        if (items[i].out_cap < hb + bytes) { result = MZB_E_SPACE; off += bytes; continue; }
+        uint8_t *o = (uint8_t *)items[i].h_out;
+        if (write_file_header) {   // common.c:137-149
+            memset(o, 0, MZB_FILE_HEADER_BYTES);
+            memcpy(o, &items[i].fsz, 8);
+            memcpy(o + 8, &chk, 4);
+        }
+        FZ_CHECK_PIPE(cudaMemcpyAsync(o + hb, d_out + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+        items[i].out_size = hb + bytes;
+        off += bytes;
+    }
+    FZ_CHECK_PIPE(cudaStreamSynchronize(c->stream));
+    return result;
+}
+
+extern "C" int mzb_decompress_host_many(mzb_ctx *c, mzb_unzip_item *items, uint32_t n, uint32_t chk)
+{
+    if (!c || (!items && n) || chk == 0 || chk >= 0x80000000u || (chk % 16u)) return MZB_E_ARG;
+    memset(&c->stats, 0, sizeof(c->stats));
+    std::vector<uint32_t> first(n + 1, 0), tab;
+    size_t in_total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (items[i].nwords > items[i].out_cap_words) return MZB_E_SPACE;
+        if (items[i].nwords && (!items[i].h_in || !items[i].h_words_out)) return MZB_E_ARG;
+        first[i + 1] = first[i] + (uint32_t)((items[i].nwords + chk - 1) / chk);
+        if (items[i].nwords) in_total += items[i].in_size;
+    }
+    const uint32_t nchunks = first[n];
+    if (nchunks > c->batch_chunks) return MZB_E_ARG;
+    if (nchunks == 0) return MZB_OK;
+    FZ_CHECK(cudaSetDevice(c->device));
+    tab.resize(nchunks);
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t k = first[i]; k < first[i + 1]; k++) {
+            const uint64_t w0 = (uint64_t)(k - first[i]) * chk;
+            tab[k] = (uint32_t)(items[i].nwords - w0 < chk ? items[i].nwords - w0 : chk);
+        }
+    const size_t slot_bytes = (size_t)chk * 4;
+    uint64_t pstride;
+    FzInflateBufs ib;
+    int rc;
+    if ((rc = decompress_reserve(c, nchunks, chk, &pstride, &ib)) || (rc = ensure(c->io_in, in_total + 256)) ||
+        (rc = ensure(c->io_out, (size_t)nchunks * slot_bytes + 256)) || (rc = ensure(c->chunk_tab, tab.size() * 4)))
+        return rc;
+    if ((rc = status_reset(c, 0))) return rc;
+    prof_begin(c);
+    FZ_CHECK_PIPE(cudaMemcpyAsync(c->chunk_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    size_t at = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (items[i].nwords) {   // the items' records back to back: one chain for the walk
+            FZ_CHECK_PIPE(cudaMemcpyAsync((uint8_t *)c->io_in.p + at, items[i].h_in, items[i].in_size, cudaMemcpyHostToDevice, c->stream));
+            at += items[i].in_size;
+        }
+    FzBatchGeom g = make_geom(nchunks, chk, (uint64_t)nchunks * chk, pstride);
+    g.chunk_n = (const uint32_t *)c->chunk_tab.p;
+    decompress_enqueue_batch(c, (const uint8_t *)c->io_in.p, in_total, g, ib, (uint32_t *)c->io_out.p, true);
+    for (uint32_t i = 0; i < n; i++)
+        if (items[i].nwords)
+            FZ_CHECK_PIPE(cudaMemcpyAsync(items[i].h_words_out, (const uint8_t *)c->io_out.p + (size_t)first[i] * slot_bytes, items[i].nwords * 4,
+                                          cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = status_fetch(c))) return pipe_fail(c, rc);
+    prof_collect(c);
+    fill_decompress_stats(c, in_total, 0, nchunks, decompress_launches(0, true));
+    for (uint32_t i = 0; i < n; i++) c->stats.bytes_out += items[i].nwords * 4;
+    if (c->h_status->error) return c->h_status->error;
+    if (c->h_status->out_end != in_total) return MZB_E_FORMAT;   // an item's records are longer or shorter than it said
     return MZB_OK;
 }

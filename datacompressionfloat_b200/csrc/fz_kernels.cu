@@ -19,6 +19,12 @@
 
 #define FZ_WARP 32
 
+// words of chunk c of the batch: uniform chunks with a ragged last one, or -- several small files in one batch -- a table
+__device__ __forceinline__ uint32_t fz_chunk_n(const FzBatchGeom &g, uint32_t c)
+{
+    return g.chunk_n ? g.chunk_n[c] : (c == g.nchunks - 1 ? g.last_n : g.chk);
+}
+
 // =================================================================================================
 // helpers
 // =================================================================================================
@@ -175,6 +181,43 @@ fz_split_kernel_v1(const uint4 *__restrict__ words4, uint64_t nvec, uint32_t mas
     }
 }
 
+// several small files in one batch: chunk c occupies the slot [c * chk, (c + 1) * chk) of the word buffer and of every
+// plane (chk % 4 == 0), its first chunk_exempt[c] words keep their bits; words behind chunk_n[c] are never looked at by
+// the later stages, so the slots are simply processed whole
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
+fz_split_slots_kernel(const uint4 *__restrict__ words4, uint64_t nvec, uint32_t mask, uint32_t chk, const uint32_t *__restrict__ chunk_exempt,
+                      uint8_t *__restrict__ planes, uint64_t plane_stride)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL) + threadIdx.x;
+    uint32_t *p0 = (uint32_t *)planes, *p1 = (uint32_t *)(planes + plane_stride);
+    uint32_t *p2 = (uint32_t *)(planes + 2 * plane_stride), *p3 = (uint32_t *)(planes + 3 * plane_stride);
+#pragma unroll
+    for (int k = 0; k < FZ_SPLIT_UNROLL; k++) {
+        const uint64_t i = base + (uint64_t)k * FZ_SPLIT_THREADS;
+        if (i < nvec) {
+            uint4 w = fz_ld_stream(words4 + i);
+            const uint64_t wi = i * 4;
+            const uint32_t c = (uint32_t)(wi / chk);
+            const uint64_t local = wi - (uint64_t)c * chk, ex = chunk_exempt[c];
+            if (local + 0 >= ex) w.x &= mask;
+            if (local + 1 >= ex) w.y &= mask;
+            if (local + 2 >= ex) w.z &= mask;
+            if (local + 3 >= ex) w.w &= mask;
+            uint32_t a, b, cc, d;
+            fz_transpose4(w.x, w.y, w.z, w.w, a, b, cc, d);
+            p0[i] = a; p1[i] = b; p2[i] = cc; p3[i] = d;
+        }
+    }
+}
+
+void fz_launch_split_slots(const uint32_t *words, uint32_t nchunks, uint32_t chk, uint32_t mask, const uint32_t *chunk_exempt, uint8_t *planes,
+                           uint64_t plane_stride, cudaStream_t st)
+{
+    const uint64_t nvec = (uint64_t)nchunks * chk / 4;
+    const uint64_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
+    fz_split_slots_kernel<<<(unsigned)((nvec + per - 1) / per), FZ_SPLIT_THREADS, 0, st>>>((const uint4 *)words, nvec, mask, chk, chunk_exempt, planes, plane_stride);
+}
+
 // ragged tail: the last nwords % 4 words
 __global__ void fz_split_tail_kernel(const uint32_t *__restrict__ words, uint64_t first, uint64_t nwords, uint32_t mask,
                                      uint64_t exempt, uint8_t *__restrict__ planes, uint64_t plane_stride)
@@ -303,7 +346,7 @@ fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__res
                         uint32_t *__restrict__ words)
 {
     const uint32_t c = blockIdx.y;
-    const uint32_t n_c = (c == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_c = fz_chunk_n(g, c);
     const uint32_t nvec = n_c / 4;
     const uint8_t *src[4];
     const uint8_t *end[4];
@@ -539,7 +582,7 @@ __device__ __forceinline__ bool fz_slot(const FzBatchGeom &g, uint32_t t, uint32
 {
     s = t / g.nsub_full;
     k = t - s * g.nsub_full;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     const uint32_t off = k * FZ_SUB;
     if (off >= n_s) return false;
     n = min((uint32_t)FZ_SUB, n_s - off);
@@ -693,7 +736,7 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
     const uint32_t gi = blockIdx.x * FZ_ENC_WARPS + warp;
     if (gi >= g.nchunks * FZ_PLANES * gps) return;
     const uint32_t s = gi / gps, gk = gi - s * gps;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
     if ((uint64_t)gk * gbytes >= n_s) return;
     const uint32_t gn = (uint32_t)min((uint64_t)n_s - (uint64_t)gk * gbytes, gbytes);
@@ -843,7 +886,8 @@ fz_hist2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__r
     uint32_t *hist = hist_sh[warp];
     const uint8_t *src = fz_sub_src(planes, g, s, k);
     uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
-    if (n == FZ_SUB && ((zero_planes >> (s & 3u)) & 1u) && (uint64_t)(s >> 2) * g.chk + (uint64_t)k * FZ_SUB >= zero_from) {
+    const uint64_t masked_from = g.chunk_exempt ? (uint64_t)(s >> 2) * g.chk + g.chunk_exempt[s >> 2] : zero_from;
+    if (n == FZ_SUB && ((zero_planes >> (s & 3u)) & 1u) && (uint64_t)(s >> 2) * g.chk + (uint64_t)k * FZ_SUB >= masked_from) {
         // the mask erases this whole byte plane (8 or more bits erased) and the sub-block lies behind the exempt
         // header words: 16 KiB of zeros, known without reading them
         if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
@@ -1061,7 +1105,7 @@ fz_layout_streams_kernel(uint32_t *__restrict__ sizes, FzBatchGeom g, uint32_t *
     const int lane = threadIdx.x & 31;
     const uint32_t s = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (s >= g.nchunks * FZ_PLANES) return;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     const uint32_t nsub = (n_s + FZ_SUB - 1) / FZ_SUB;
     uint32_t carry = 0;
     for (uint32_t k0 = 0; k0 < nsub; k0 += 32) {
@@ -1176,7 +1220,7 @@ fz_gather_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__
     const uint32_t total = g.nchunks * FZ_PLANES * g.nsub_full;
     if (t >= total || status->error) return;
     const uint32_t s = t / g.nsub_full, k = t - s * g.nsub_full;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     const uint32_t off = k * FZ_SUB;
     if (off >= n_s) return;
     const uint32_t n = min((uint32_t)FZ_SUB, n_s - off);
@@ -1274,7 +1318,7 @@ __global__ void fz_walk_kernel(const uint8_t *__restrict__ container, uint64_t c
 #pragma unroll
         for (int i = 0; i < 16; i++) b[i] = container[off + i];
         off += FZ_CHUNK_HEADER_BYTES;
-        const uint32_t n_s = (c == g.nchunks - 1) ? g.last_n : g.chk;
+        const uint32_t n_s = fz_chunk_n(g, c);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             // unpack_header (reference zip.c:394-399)
@@ -1493,7 +1537,7 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
     if (status->error) { stream_mode[s] = 0; return; }
     const uint32_t h = stream_hdr[s];
     if (h & FZ_RAW_FLAG) { stream_mode[s] = 0; return; }
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     const uint32_t h0 = tile_off[s * tiles_per_stream], h1 = tile_off[(s + 1) * tiles_per_stream];
     const uint32_t m = h1 - h0;
     uint32_t mode = 2;
@@ -1559,7 +1603,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     FzGroupSmem *sm = &smem[warp];
     const uint32_t k = gk * FZ_GROUP_SUBS + lane;
     const bool valid = k < m;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     uint32_t start = 0, end = 0, expect = 0;
     uint8_t *out = nullptr;
     if (valid) {
@@ -1925,7 +1969,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
     if (mode == 2u && par_ok[s]) { atomicAdd(&status->n_blockpar, 1u); return; }   // decoded block-parallel
     if (zero_flags) for (uint32_t k = 0; k < g.nsub_full; k++) zero_flags[(size_t)s * g.nsub_full + k] = 0;   // all of it gets written
     const uint32_t len = stream_hdr[s] & ~FZ_RAW_FLAG;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     uint8_t *out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk;
     FzInfTab<1> tab{tabs, tabs + 288, tabs + 320};
     uint32_t out_n = 0;
@@ -1945,7 +1989,7 @@ fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, 
 
 __device__ __forceinline__ uint32_t fz_bp_stream_n(const FzBatchGeom &g, uint32_t s)
 {
-    return (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    return fz_chunk_n(g, s / FZ_PLANES);
 }
 
 // candidates: every bit position p of the payload with a plausible dynamic-block header.
@@ -2241,7 +2285,7 @@ fz_rawcopy_kernel(const uint8_t *__restrict__ container, uint64_t container_size
     if (t >= total || status->error) return;
     const uint32_t s = t / g.nsub_full, k = t - s * g.nsub_full;
     if (!(stream_hdr[s] & FZ_RAW_FLAG)) return;
-    const uint32_t n_s = (s / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     const uint32_t off = k * FZ_SUB;
     if (off >= n_s) return;
     const uint32_t n = min((uint32_t)FZ_SUB, n_s - off);

@@ -13,12 +13,12 @@ struct FzBatchGeom {
     uint32_t last_n;       // words in the last chunk of the batch (== chk unless it is the ragged file tail)
     uint32_t nsub_full;    // ceil(chk / FZ_SUB): sub-block slots reserved per stream
     uint64_t plane_stride; // bytes between plane j and plane j+1 in the plane buffer
+    // several small files in one batch (device tables, nullptr otherwise): chunk c has chunk_n[c] <= chk words in the
+    // slot [c * chk, (c + 1) * chk) of the word buffer and of every plane; its first chunk_exempt[c] words are not masked
+    const uint32_t *chunk_n;
+    const uint32_t *chunk_exempt;
 };
 
-static inline uint32_t fz_stream_n(const FzBatchGeom &g, uint32_t stream)
-{
-    return (stream / FZ_PLANES == g.nchunks - 1) ? g.last_n : g.chk;
-}
 
 // device status block (one per context)
 struct FzStatus {
@@ -46,6 +46,9 @@ void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint
                      uint8_t *planes, uint64_t plane_stride, int variant, cudaStream_t st);
 void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwords, uint32_t *words,
                      int variant, cudaStream_t st);
+// the split of a batch of chunk slots with a per-chunk exemption table (several small files in one batch; chk % 4 == 0)
+void fz_launch_split_slots(const uint32_t *words, uint32_t nchunks, uint32_t chk, uint32_t mask, const uint32_t *chunk_exempt,
+                           uint8_t *planes, uint64_t plane_stride, cudaStream_t st);
 
 // ---- deflate side
 // ghist: 288 uint32 per group (zeroed by the call); gcodes: fz_group_code_bytes() per group;

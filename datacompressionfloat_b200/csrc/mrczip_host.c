@@ -24,11 +24,15 @@ int isTestThroughput = 0; /* reference workers.c:39 */
 
 /* chunks handed to the GPU per call from the FILE* API (bounds pinned + device memory per thread) */
 #define HOST_BATCH_CHUNKS 16
+/* small files share one pass of the kernels (zip_compress_many): at most this many chunks per pass, files of at most
+ * MANY_FILE_CHUNKS chunks each (larger ones fill the GPU on their own) */
+#define MANY_BATCH_CHUNKS 32
+#define MANY_FILE_CHUNKS 8
 /* file I/O of the FILE* API: batches are read / written by IO_THREADS threads with pread / pwrite (a single
  * thread copies page cache <-> pinned memory at a few GB/s, an order of magnitude below what the GPU path takes),
  * and the read of batch b+1 and the write of batch b-1 overlap the GPU work on batch b (two buffers each way).
  * Streams that cannot seek (pipes) take the plain fread / fwrite loop. */
-#define IO_THREADS 16 /* upper bound; MRCZIP_IO_THREADS (default 4) says how many are used */
+#define IO_THREADS 16 /* upper bound; MRCZIP_IO_THREADS (default 8) says how many are used */
 #define IO_SLICE_MIN ((size_t)8 << 20)
 
 /* ------------------------------------------------------------------ common.c equivalents */
@@ -247,7 +251,7 @@ static thread_state_t *thread_state(void)
         free(ts);
         return NULL;
     }
-    mzb_set_batch_chunks(ts->ctx, HOST_BATCH_CHUNKS);
+    mzb_set_batch_chunks(ts->ctx, MANY_BATCH_CHUNKS);
     pthread_setspecific(g_key, ts);
     return ts;
 }
@@ -405,11 +409,11 @@ static void *io_slice_run(void *p)
 
 static int g_io_threads = 0; /* 0 = not set: MRCZIP_IO_THREADS, else 4 */
 static pthread_once_t g_io_once = PTHREAD_ONCE_INIT;
-static int g_io_env = 4;
+static int g_io_env = 8;
 static void io_threads_init(void)
 {
     const char *e = getenv("MRCZIP_IO_THREADS");
-    const int w = e ? atoi(e) : 4;
+    const int w = e ? atoi(e) : 8;
     g_io_env = w < 1 ? 1 : (w > IO_THREADS ? IO_THREADS : w);
 }
 static int io_threads(void)
@@ -1190,4 +1194,191 @@ int zip_uncompress(ctx_t *ctx, const char *src, const char *dst)
     fclose(fout);
     fclose(fin);
     return rc;
+}
+
+/* ------------------------------------------------------------------ many small files, one pass of the kernels each
+ * (the reference's deployment shape is thousands of small MRC stacks, mrc_tarx.c:134-176; one at a
+ * time they under-fill a GPU).  Files of at most MANY_FILE_CHUNKS chunks are gathered, in list order, into groups of
+ * at most MANY_BATCH_CHUNKS chunks that go through mzb_compress_host_many / mzb_decompress_host_many; every output
+ * file is byte-identical to what zip_compress / zip_uncompress write for it.  Larger files (and, MRC-aware, files
+ * that are not float32) take the one-file path. */
+typedef struct {
+    FILE *fin;
+    uint64_t fsz, words;
+    uint32_t chunks;
+    int idx;
+} many_file_t;
+
+static int many_flush_zip(thread_state_t *ts, ctx_t *ctx, many_file_t *f, int nf, const char *const *dsts, int bits)
+{
+    if (nf <= 0 || nf > MANY_BATCH_CHUNKS) return MZB_OK;
+    const double begin = now_sec();
+    size_t in_need = 0, out_need = 0;
+    for (int i = 0; i < nf; i++) {
+        in_need += (size_t)f[i].words * 4 + 64;
+        out_need += mzb_compress_bound(f[i].words, MZB_CHUNK_WORDS) + 64;
+    }
+    int rc = MZB_OK;
+    if (pin_reserve(&ts->pin_in, &ts->pin_in_cap, in_need) || pin_reserve(&ts->pin_out, &ts->pin_out_cap, out_need)) rc = MZB_E_NOMEM;
+    mzb_zip_item *it = (mzb_zip_item *)calloc((size_t)nf, sizeof(*it));
+    if (!it) rc = MZB_E_NOMEM;
+    size_t ia = 0, oa = 0;
+    for (int i = 0; i < nf && rc == MZB_OK; i++) {
+        unsigned char *in = (unsigned char *)ts->pin_in + ia;
+        if (fread(in, 4, (size_t)f[i].words, f[i].fin) != (size_t)f[i].words) { rc = MZB_E_IO; break; }
+        int b2 = bits;
+        it[i].h_words = in;
+        it[i].nwords = f[i].words;
+        it[i].exempt_words = (uint32_t)head_exempt_words(in, (size_t)f[i].words * 4, f[i].fsz, &b2);
+        it[i].fsz = f[i].fsz;
+        it[i].h_out = (unsigned char *)ts->pin_out + oa;
+        it[i].out_cap = mzb_compress_bound(f[i].words, MZB_CHUNK_WORDS);
+        ia += (size_t)f[i].words * 4 + 64;
+        ia &= ~(size_t)15;
+        oa += it[i].out_cap + 64;
+        oa &= ~(size_t)15;
+    }
+    if (rc == MZB_OK) rc = mzb_compress_host_many(ts->ctx, it, (uint32_t)nf, bits, MZB_CHUNK_WORDS, 1);
+    if (rc != MZB_OK) fprintf(stderr, "[%s:%d] ERROR: GPU compress of a group of %d files failed: %s\n", __FILE__, __LINE__, nf, mzb_strerror(rc));
+    for (int i = 0; i < nf; i++) {
+        if (rc == MZB_OK && isTestThroughput != 1) {
+            FILE *fo = fopen(dsts[f[i].idx], "wb");
+            if (!fo) { fprintf(stderr, "[%s:%d] ERROR: fail open:%s\n", __FILE__, __LINE__, dsts[f[i].idx]); exit(-1); }
+            if (it[i].out_size && fwrite(it[i].h_out, 1, (size_t)it[i].out_size, fo) != (size_t)it[i].out_size) rc = MZB_E_IO;
+            fclose(fo);
+        }
+        if (rc == MZB_OK) {
+            ctx->fileCount += 1;
+            ctx->allFileSize += f[i].fsz;
+            ctx->allZipFileSize += it[i].out_size > MZB_FILE_HEADER_BYTES ? it[i].out_size - MZB_FILE_HEADER_BYTES : 0;
+        }
+        fclose(f[i].fin);
+    }
+    ctx->zipTime += now_sec() - begin;
+    free(it);
+    return rc;
+}
+
+int zip_compress_many(ctx_t *ctx, int n, const char *const *srcs, const char *const *dsts, int bitsToLoss)
+{
+    if (!ctx || n < 0 || (n && (!srcs || !dsts)) || bitsToLoss < 0 || bitsToLoss > 32) return MZB_E_ARG;
+    thread_state_t *ts = thread_state();
+    if (!ts) return MZB_E_CUDA;
+    many_file_t grp[MANY_BATCH_CHUNKS];
+    int ng = 0, rc = MZB_OK;
+    uint32_t chunks = 0;
+    for (int i = 0; i < n; i++) {
+        FILE *fin = fopen(srcs[i], "rb");
+        if (!fin) { fprintf(stderr, "[%s:%d] ERROR: fail open:%s\n", __FILE__, __LINE__, srcs[i]); exit(-1); }
+        const uint64_t fsz = get_file_size(fin), words = fsz / 4;
+        const uint64_t ch = (words + MZB_CHUNK_WORDS - 1) / MZB_CHUNK_WORDS;
+        int single = ch == 0 || ch > MANY_FILE_CHUNKS;
+        if (!single && mrc_aware() && bitsToLoss) {   /* a file that is not float32 is stored with no bits erased: its own pass */
+            unsigned char head[1024];
+            int b2 = bitsToLoss;
+            const size_t got = fread(head, 1, sizeof head, fin);
+            rewind(fin);
+            head_exempt_words(head, got, fsz, &b2);
+            single = b2 != bitsToLoss;
+        }
+        if (single) {
+            fclose(fin);
+            const int r = zip_compress(ctx, srcs[i], dsts[i], bitsToLoss);
+            if (r != MZB_OK && rc == MZB_OK) rc = r;
+            continue;
+        }
+        if (chunks + ch > MANY_BATCH_CHUNKS || ng == MANY_BATCH_CHUNKS) {
+            const int r = many_flush_zip(ts, ctx, grp, ng, dsts, bitsToLoss);
+            if (r != MZB_OK && rc == MZB_OK) rc = r;
+            ng = 0; chunks = 0;
+        }
+        grp[ng].fin = fin; grp[ng].fsz = fsz; grp[ng].words = words; grp[ng].chunks = (uint32_t)ch; grp[ng].idx = i;
+        ng++;
+        chunks += (uint32_t)ch;
+    }
+    const int r = many_flush_zip(ts, ctx, grp, ng, dsts, bitsToLoss);
+    return rc != MZB_OK ? rc : r;
+}
+
+static int many_flush_unzip(thread_state_t *ts, ctx_t *ctx, many_file_t *f, int nf, const char *const *dsts)
+{
+    if (nf <= 0 || nf > MANY_BATCH_CHUNKS) return MZB_OK;
+    const double begin = now_sec();
+    size_t in_need = 0, out_need = 0;
+    for (int i = 0; i < nf; i++) {
+        in_need += (size_t)f[i].fsz + 64;          /* fsz: bytes of chunk records here */
+        out_need += (size_t)f[i].words * 4 + 64;
+    }
+    int rc = MZB_OK;
+    if (pin_reserve(&ts->pin_in, &ts->pin_in_cap, in_need) || pin_reserve(&ts->pin_out, &ts->pin_out_cap, out_need)) rc = MZB_E_NOMEM;
+    mzb_unzip_item *it = (mzb_unzip_item *)calloc((size_t)nf, sizeof(*it));
+    if (!it) rc = MZB_E_NOMEM;
+    size_t ia = 0, oa = 0;
+    for (int i = 0; i < nf && rc == MZB_OK; i++) {
+        unsigned char *in = (unsigned char *)ts->pin_in + ia;
+        if (fread(in, 1, (size_t)f[i].fsz, f[i].fin) != (size_t)f[i].fsz) { rc = MZB_E_FORMAT; break; }
+        it[i].h_in = in;
+        it[i].in_size = (size_t)f[i].fsz;
+        it[i].nwords = f[i].words;
+        it[i].h_words_out = (unsigned char *)ts->pin_out + oa;
+        it[i].out_cap_words = f[i].words;
+        ia = (ia + (size_t)f[i].fsz + 64) & ~(size_t)15;
+        oa = (oa + (size_t)f[i].words * 4 + 64) & ~(size_t)15;
+    }
+    if (rc == MZB_OK) rc = mzb_decompress_host_many(ts->ctx, it, (uint32_t)nf, MZB_CHUNK_WORDS);
+    if (rc != MZB_OK) fprintf(stderr, "[%s:%d] ERROR: GPU decompress of a group of %d files failed: %s\n", __FILE__, __LINE__, nf, mzb_strerror(rc));
+    for (int i = 0; i < nf; i++) {
+        if (rc == MZB_OK && isTestThroughput != 1) {
+            FILE *fo = fopen(dsts[f[i].idx], "wb");
+            if (!fo) { fprintf(stderr, "[%s:%d] ERROR: fail open:%s\n", __FILE__, __LINE__, dsts[f[i].idx]); exit(-1); }
+            if (fwrite(it[i].h_words_out, 4, (size_t)f[i].words, fo) != (size_t)f[i].words) rc = MZB_E_IO;
+            fclose(fo);
+        }
+        if (rc == MZB_OK) {
+            ctx->fileCount += 1;
+            ctx->allFileSize += f[i].words * 4;
+            ctx->allZipFileSize += f[i].fsz;
+        }
+        fclose(f[i].fin);
+    }
+    ctx->unzipTime += now_sec() - begin;
+    free(it);
+    return rc;
+}
+
+int zip_uncompress_many(ctx_t *ctx, int n, const char *const *srcs, const char *const *dsts)
+{
+    if (!ctx || n < 0 || (n && (!srcs || !dsts))) return MZB_E_ARG;
+    thread_state_t *ts = thread_state();
+    if (!ts) return MZB_E_CUDA;
+    many_file_t grp[MANY_BATCH_CHUNKS];
+    int ng = 0, rc = MZB_OK;
+    uint32_t chunks = 0;
+    for (int i = 0; i < n; i++) {
+        FILE *fin = fopen(srcs[i], "rb");
+        if (!fin) { fprintf(stderr, "[%s:%d] ERROR: fail open:%s\n", __FILE__, __LINE__, srcs[i]); exit(-1); }
+        const uint64_t zsz = get_file_size(fin);
+        mrczip_header_t hd;
+        init_mrczip_header(&hd, 0);
+        int single = zsz < MZB_FILE_HEADER_BYTES || read_mrczip_header(fin, &hd) != 0 || hd.chk != MZB_CHUNK_WORDS;
+        const uint64_t words = hd.fsz / MZB_PLANES, ch = (words + MZB_CHUNK_WORDS - 1) / MZB_CHUNK_WORDS;
+        for (int j = 0; j < MZB_PLANES; j++) single |= hd.ztypes[j] != 0;
+        single |= ch == 0 || ch > MANY_FILE_CHUNKS;
+        if (single) {   /* large, empty, odd chunk size or malformed: the one-file path (and its error handling) */
+            fclose(fin);
+            const int r = zip_uncompress(ctx, srcs[i], dsts[i]);
+            if (r != MZB_OK && rc == MZB_OK) rc = r;
+            continue;
+        }
+        if (chunks + ch > MANY_BATCH_CHUNKS || ng == MANY_BATCH_CHUNKS) {
+            const int r = many_flush_unzip(ts, ctx, grp, ng, dsts);
+            if (r != MZB_OK && rc == MZB_OK) rc = r;
+            ng = 0; chunks = 0;
+        }
+        grp[ng].fin = fin; grp[ng].fsz = zsz - MZB_FILE_HEADER_BYTES; grp[ng].words = words; grp[ng].chunks = (uint32_t)ch; grp[ng].idx = i;
+        ng++;
+        chunks += (uint32_t)ch;
+    }
+    const int r = many_flush_unzip(ts, ctx, grp, ng, dsts);
+    return rc != MZB_OK ? rc : r;
 }

@@ -49,11 +49,11 @@ class MrczipHeaderT(C.Structure):
 
 # every symbol include/mrczip_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "run_compress", "run_uncompress", "zip_compress", "zip_uncompress", "pack_header", "unpack_header",
+    "run_compress", "run_uncompress", "zip_compress", "zip_uncompress", "zip_compress_many", "zip_uncompress_many", "pack_header", "unpack_header",
     "init_context", "reset_context", "update_context", "print_context_info", "init_mrczip_header",
     "read_mrczip_header", "write_mrczip_header", "print_mrczip_header", "get_file_size", "now_sec",
     "isTestThroughput",
-    "mzb_create", "mzb_create_on_stream", "mzb_destroy", "mzb_set_io_threads", "mzb_device_count", "mzb_set_devices", "mzb_mrc_parse", "mzb_set_mrc_aware", "mzb_error_report_device", "mzb_error_report_host", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_compress_bound",
+    "mzb_create", "mzb_create_on_stream", "mzb_destroy", "mzb_set_io_threads", "mzb_pass_counts", "mzb_compress_host_many", "mzb_decompress_host_many", "mzb_device_count", "mzb_set_devices", "mzb_mrc_parse", "mzb_set_mrc_aware", "mzb_error_report_device", "mzb_error_report_host", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_compress_bound",
     "mzb_compress_device", "mzb_decompress_device", "mzb_mask_split_device", "mzb_merge_device",
     "mzb_compress_host", "mzb_decompress_host", "mzb_host_alloc", "mzb_host_free", "mzb_last_stats",
     "mzb_set_profiling", "mzb_stage_count", "mzb_stage_name", "mzb_stage_ms",

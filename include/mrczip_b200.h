@@ -83,6 +83,13 @@ int run_uncompress(FILE *fin, ctx_t *ctx, mrczip_header_t *hd, FILE *fout, const
 int zip_compress(ctx_t *ctx, const char *src, const char *dst, int bitsToLoss);
 int zip_uncompress(ctx_t *ctx, const char *src, const char *dst);
 
+/* Extension for list front ends (reference mrc_tarx.c:134-176 feeds zip_compress one file at a time): n files at
+ * once; files of at most 8 chunks are gathered into groups of at most 32 chunks that take ONE pass of the GPU kernels
+ * each (small stacks under-fill a GPU one by one).  Every output file is byte-identical to zip_compress's /
+ * zip_uncompress's; ctx is accumulated the same way. */
+int zip_compress_many(ctx_t *ctx, int n, const char *const *srcs, const char *const *dsts, int bitsToLoss);
+int zip_uncompress_many(ctx_t *ctx, int n, const char *const *srcs, const char *const *dsts);
+
 /* mrczip.h:123-124 / zip.c:381-399 */
 void pack_header(char *buf, btype_t btype, uint32_t len);
 void unpack_header(const char *buf, btype_t *btype, uint32_t *len);
@@ -124,7 +131,7 @@ int mzb_device_count(void);
 int mzb_set_devices(const int *devices, int n);
 
 /* Threads that pread / pwrite one batch of the FILE* entry points (1..16; 0 = back to the default: the environment
- * variable MRCZIP_IO_THREADS, else 4).  Process wide. */
+ * variable MRCZIP_IO_THREADS, else 8).  Process wide. */
 int mzb_set_io_threads(int n);
 
 /* Upper bound of the container for nwords words cut in chk-word chunks (header included). */
@@ -202,9 +209,39 @@ int mzb_error_report_device(mzb_ctx *ctx, const void *d_orig, const void *d_othe
 int mzb_error_report_host(mzb_ctx *ctx, const void *h_orig, const void *h_other, uint64_t nwords, int bits,
                           uint32_t exempt_words, mzb_error_report_t *out);
 
+/* ---- several small inputs in ONE pass of the kernels (thousands of small MRC stacks under-fill a GPU
+ * one at a time).  Every item is its own file: own header exemption, own ragged last chunk, own container.  All items
+ * share chk (a multiple of 16) and bits; their chunk counts must add up to at most the context's batch size
+ * (mzb_set_batch_chunks, default 192).  Results are byte-identical to one mzb_compress_host / mzb_decompress_host
+ * call per item. */
+typedef struct {
+    const void *h_words;    /* in:  nwords uint32 */
+    uint64_t nwords;
+    uint32_t exempt_words;  /* in:  leading words that keep their bits (256 for an MRC file) */
+    uint32_t reserved;
+    uint64_t fsz;           /* in:  original file size for the 17-byte header */
+    void *h_out;            /* out: container (17-byte header when write_file_header, then the chunk records) */
+    size_t out_cap;
+    uint64_t out_size;      /* out */
+} mzb_zip_item;
+int mzb_compress_host_many(mzb_ctx *ctx, mzb_zip_item *items, uint32_t n, int bits, uint32_t chk, int write_file_header);
+
+typedef struct {
+    const void *h_in;        /* in:  chunk records of the item (no 17-byte header) */
+    size_t in_size;
+    uint64_t nwords;         /* in:  words the records inflate to */
+    void *h_words_out;       /* out: nwords uint32 */
+    uint64_t out_cap_words;
+} mzb_unzip_item;
+int mzb_decompress_host_many(mzb_ctx *ctx, mzb_unzip_item *items, uint32_t n, uint32_t chk);
+
 /* pinned (page-locked) host memory for callers written in C without the CUDA headers */
 void *mzb_host_alloc(size_t bytes);
 void mzb_host_free(void *p);
+
+/* passes of the kernel pipelines since the process started (one per batch of chunks handed to the GPU): what a list
+ * front end looks at to see that small files really share passes */
+void mzb_pass_counts(uint64_t *compress_passes, uint64_t *decompress_passes);
 
 /* counters of the last compress / decompress call */
 typedef struct {
