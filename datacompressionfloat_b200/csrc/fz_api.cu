@@ -337,7 +337,7 @@ static int compress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t *p
     const uint64_t pstride = plane_stride_for(bmax, chk);
     const uint32_t nsub_full = (chk + FZ_SUB - 1) / FZ_SUB;
     const size_t nslots = (size_t)bmax * FZ_PLANES * nsub_full;
-    const size_t ngroups = (size_t)bmax * FZ_PLANES * ((nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
+    const size_t ngroups = (size_t)bmax * FZ_PLANES * ((nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS);
     int rc;
     if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->scratch, nslots * FZ_SLOT_STRIDE + 256)) ||
         (rc = ensure(c->sizes, nslots * 4)) || (rc = ensure(c->sub_off, nslots * 4)) ||

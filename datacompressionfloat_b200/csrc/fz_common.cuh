@@ -35,7 +35,8 @@
 #endif
 #define FZ_SUB (1u << FZ_SUB_LOG2)        // 16 KiB (8 KiB: +5 % speed at 4 GiB, 2x decode speed on small inputs, +0.5..1.5 % size)
 #define FZ_SLOT_STRIDE (FZ_SUB + 32u)     // scratch bytes reserved per encoded sub-block
-#define FZ_GROUP_SUBS 32u                 // sub-blocks that share one Huffman code (= one warp of the inflater)
+#define FZ_GROUP_SUBS 32u                 // sub-blocks one warp of the inflater decodes (and the unit in which all-zero sub-blocks share a fragment)
+#define FZ_CODE_SUBS 128u                 // sub-blocks that share one Huffman code: 4 groups = one CTA of the inflater, one lookup table
 // A stored sub-block is written as TWO stored blocks (5-byte headers) + the empty stored block (5 bytes): the
 // split point is chosen so that the raw bytes can never show the sync marker 00 00 FF FF to the inflater's
 // marker scan (see fz_stored_split).  One-byte sub-blocks use a single stored block.

@@ -108,11 +108,12 @@ FZ_HD uint32_t fz_warp_incl_sum(const W &w, uint32_t v)
 //   the sub-block is cut into aligned quads of 4 bytes.  E[q] = the four bytes of quad q all equal the byte before
 //   them (E = 0 for the first quad, which has no byte before it, and for a ragged last quad of fewer than 4 bytes).
 //   Quad q is HELD iff E[q] and E[q-1]: its bytes continue a run that is at least 5 bytes long already.  Every byte
-//   outside a held quad is a literal.  A maximal run of held quads leaves as distance-1 matches: one of 256 bytes at
-//   every 64th quad of the run, and one of 4 * (count mod 64) bytes at its last quad.  Tokens leave in byte order.
+//   outside a held quad is a literal.  A maximal run of held quads leaves as distance-1 matches: with m the bytes of
+//   the run not yet emitted, every held quad adds 4 to m and a match of 258 leaves at the quad where m reaches 258
+//   (m -= 258); at the last quad of the run the rest leaves, as a match for m >= 3, as m literals for m = 1, 2.
+//   Tokens leave in byte order.
 // (The first encoder withheld bytes one by one; quads make a lane's output uniform slots, cost nothing measurable on
 //  float planes, and let an inflater copy runs as whole words.)
-#define FZ_E2_MAX_QUADS 64u    // 256 bytes: the longest match the encoder writes
 #define FZ_E2_LQ 8             // quads per lane and step
 #define FZ_E2_LB (4u * FZ_E2_LQ)        // bytes per lane and step
 #define FZ_E2_STEP (32u * FZ_E2_LB)     // bytes per warp and step
@@ -124,14 +125,15 @@ struct FzLaneQuads { uint32_t w[FZ_E2_LQ]; };
 struct FzTokCarry {
     uint32_t prev;     // last byte of the step before; 0x100 = none (start of the sub-block)
     uint32_t prevE;    // E of its last quad
-    uint32_t m;        // held quads pending (0..63)
+    uint32_t m;        // bytes of the current run not yet emitted (0..257)
     FZ_HD void init() { prev = 0x100u; prevE = 0; m = 0; }
 };
 
 // this lane's quads, tokenised
 struct FzTok {
     uint32_t hq;      // bit g: quad g is held
-    uint32_t m_in;    // held quads pending in front of quad 0 (0..63)
+    uint32_t m_in;    // bytes of a run pending in front of quad 0 (0..257)
+    uint32_t pb;      // the byte before quad 0 (what such a run repeats)
 };
 
 // bit k: byte k of the 16 bytes x[0..3] equals the byte splatted in `splat4` (b * 0x01010101)
@@ -200,6 +202,7 @@ FZ_HD bool fz_tok_step(const W &w, const FzLaneQuads &v, uint32_t nv, FzTokCarry
     const uint32_t hq = E & ((E << 1) | pE);
     t.hq = hq;
     t.m_in = 0;
+    t.pb = pb & 0xffu;
     const uint32_t anyh = w.ballot(hq != 0);
     const uint32_t m0 = c.m;
     c.prev = w.shfl(lastb, 31);
@@ -213,37 +216,58 @@ FZ_HD bool fz_tok_step(const W &w, const FzLaneQuads &v, uint32_t nv, FzTokCarry
     const uint32_t below = ~B & ((1u << lane) - 1u);          // lanes before this one that do not pass
     const int j = below ? 31 - (int)fz_clz32(below) : 0;
     const uint32_t tj = w.shfl(top, j);
-    const uint32_t m = (below ? tj + FZ_E2_LQ * (uint32_t)(lane - 1 - j) : m0 + FZ_E2_LQ * (uint32_t)lane) & (FZ_E2_MAX_QUADS - 1u);
+    const uint32_t m = (below ? 4u * tj + FZ_E2_LB * (uint32_t)(lane - 1 - j) : m0 + FZ_E2_LB * (uint32_t)lane) % FZ_MAX_MATCH;
     t.m_in = m;
-    c.m = w.shfl(passes ? ((m + FZ_E2_LQ) & (FZ_E2_MAX_QUADS - 1u)) : top, 31);
+    c.m = w.shfl(passes ? (m + FZ_E2_LB) % FZ_MAX_MATCH : 4u * top, 31);
     return true;
 }
 
-// the run tokens of a tokenised lane, as lengths in quads (0 = none): tin = in front of quad 0 (the run ended with the
-// lane before), tl[g] = at held quad g
-FZ_HD void fz_tok_lens(const FzTok &t, uint32_t &tin, uint32_t tl[FZ_E2_LQ])
+// the run tokens of a tokenised lane: tin = bytes of the run that ended with the lane before (its rest leaves in front
+// of quad 0; 0 = none); for held quad g: cross[g] = a match of 258 leaves there, tl[g] = bytes of the rest that leaves
+// there because the run ends (0 = none; the last quad of the lane never ends a run: the next lane knows)
+FZ_HD void fz_tok_lens(const FzTok &t, uint32_t &tin, uint32_t &cross, uint32_t tl[FZ_E2_LQ])
 {
     uint32_t cnt = t.m_in;
     tin = (t.hq & 1u) ? 0u : cnt;
+    cross = 0;
 #pragma unroll
     for (int g = 0; g < FZ_E2_LQ; g++) {
         tl[g] = 0;
         if ((t.hq >> g) & 1u) {
-            cnt = (cnt + 1u) & (FZ_E2_MAX_QUADS - 1u);
-            const bool more = g < FZ_E2_LQ - 1 ? ((t.hq >> (g + 1)) & 1u) != 0 : true;   // last quad: the next lane knows
-            if (cnt == 0) tl[g] = FZ_E2_MAX_QUADS;
-            else if (!more) tl[g] = cnt;
+            cnt += 4u;
+            if (cnt >= FZ_MAX_MATCH) { cnt -= FZ_MAX_MATCH; cross |= 1u << g; }
+            const bool more = g < FZ_E2_LQ - 1 ? ((t.hq >> (g + 1)) & 1u) != 0 : true;
+            if (!more) { tl[g] = cnt; cnt = 0; }
         } else cnt = 0;
     }
 }
 
-// the bits of a match of 4 * nq bytes at distance 1: bits | nbits << 24 (<= 21 bits).  cl[] = code | len << 16.
-FZ_HD uint32_t fz_run_token(const uint32_t *cl, uint32_t nq)
+// the bits of what is left of a run of `byte`: a match of n bytes at distance 1 for n >= 3, n literals for n = 1, 2
+// (<= 30 bits).  cl[] = code | len << 16.
+FZ_HD void fz_run_token(const uint32_t *cl, uint32_t n, uint32_t byte, uint32_t &bits, uint32_t &nbits)
 {
-    uint32_t lc, eb, ev;
-    fz_len_code(4u * nq, lc, eb, ev);
-    const uint32_t e = cl[257 + lc];
-    return (e & 0xffffu) | (ev << (e >> 16)) | (((e >> 16) + eb + 1u) << 24);   // length code, extra bits, 1-bit distance code '0'
+    if (n >= FZ_MIN_MATCH) {
+        uint32_t lc, eb, ev;
+        fz_len_code(n, lc, eb, ev);
+        const uint32_t e = cl[257 + lc];
+        bits = (e & 0xffffu) | (ev << (e >> 16));   // length code, extra bits, then the 1-bit distance code '0'
+        nbits = (e >> 16) + eb + 1u;
+    } else {
+        const uint32_t e = cl[byte], l = e >> 16;
+        bits = (e & 0xffffu) | (n == 2u ? (e & 0xffffu) << l : 0u);
+        nbits = l * n;
+    }
+}
+
+// ... and what it adds to a token histogram
+template <class W>
+FZ_HD void fz_run_count(const W &w, uint32_t *hist, uint32_t n, uint32_t byte)
+{
+    if (n >= FZ_MIN_MATCH) {
+        uint32_t lc, eb, ev;
+        fz_len_code(n, lc, eb, ev);
+        w.atom_add(&hist[257 + lc], 1u);
+    } else if (n) w.atom_add(&hist[byte], n);
 }
 
 // ---- histogram of one sub-block's tokens -------------------------------------------------------------------------
@@ -292,25 +316,17 @@ FZ_HD void fz_hist2_subblock(const W &w, uint32_t *hist, const Load16 &ld, uint3
             }
         }
         if (slow) {
-            uint32_t tin, tl[FZ_E2_LQ];
-            fz_tok_lens(t, tin, tl);
+            uint32_t tin, cross, tl[FZ_E2_LQ];
+            fz_tok_lens(t, tin, cross, tl);
+            if (tin) fz_run_count(w, hist, tin, t.pb);
+            if (cross) w.atom_add(&hist[285], fz_popc32(cross));     // matches of 258
 #pragma unroll
-            for (int g = -1; g < FZ_E2_LQ; g++) {
-                const uint32_t nq = g < 0 ? tin : tl[g < 0 ? 0 : g];
-                if (nq) {
-                    uint32_t lc, eb, ev;
-                    fz_len_code(4u * nq, lc, eb, ev);
-                    w.atom_add(&hist[257 + lc], 1u);
-                }
-            }
+            for (int g = 0; g < FZ_E2_LQ; g++)
+                if (tl[g]) fz_run_count(w, hist, tl[g], v.w[g] & 0xffu);
         }
         v = vn;
     }
-    if (lane == 0 && c.m) {   // the run that reaches the end of the sub-block
-        uint32_t lc, eb, ev;
-        fz_len_code(4u * c.m, lc, eb, ev);
-        w.atom_add(&hist[257 + lc], 1u);
-    }
+    if (lane == 0 && c.m) fz_run_count(w, hist, c.m, c.prev & 0xffu);   // the run that reaches the end of the sub-block
     if (n1) w.atom_add(&hist[skip1 & 0xffu], n1);
     if (n2) w.atom_add(&hist[skip2 & 0xffu], n2);
     w.sync();
@@ -417,7 +433,7 @@ struct FzRingOut {
 //   cl[288]   the group's code table (code | len << 16), in shared memory on the device
 //   hdr       the group's block header (hdr_nbits bits)
 //   ring      FZ_E2_RING_WORDS words of this warp (any content)
-//   tt        64 words of this warp: filled here with the group's run tokens (fz_run_token)
+//   tt        256 words of this warp: filled here with the group's match tokens (lengths 3..258)
 //   out       FZ_SLOT_STRIDE bytes, 16-byte aligned
 template <class W, class Load16>
 FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t *hdr, uint32_t hdr_nbits, uint32_t *ring,
@@ -428,9 +444,13 @@ FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t 
     const uint32_t limit = fz_stored_size(n) - (n >> FZ_MIN_GAIN_SHIFT);   // a coded fragment must stay below this many bytes
     if ((hdr_nbits >> 3) + 5u >= limit) return stored;
     for (uint32_t i = lane; i < FZ_E2_RING_WORDS; i += 32u) ring[i] = 0;
-    tt[lane] = fz_run_token(cl, (uint32_t)lane + 1u);
-    tt[lane + 32] = fz_run_token(cl, (uint32_t)lane + 33u);
+    for (uint32_t i = lane; i < 256u; i += 32u) {   // the bits of a match of i + 3 bytes: bits | nbits << 24 (<= 21 bits)
+        uint32_t b, l;
+        fz_run_token(cl, i + 3u, 0u, b, l);
+        tt[i] = b | (l << 24);
+    }
     w.sync();
+    const uint32_t t258 = tt[255];
     {   // the block header (<= 160 words)
         const uint32_t nw = (hdr_nbits + 31u) >> 5;
         for (uint32_t i = lane; i < nw; i += 32u) {
@@ -475,16 +495,29 @@ FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t 
             ql[g] = pl0 + pl1;
         }
         uint32_t tinb = 0, tinl = 0;
-        if (slow) {   // ... or, for a held quad, its run token (if a run ends or reaches 256 bytes there) or nothing
-            uint32_t tin, tl[FZ_E2_LQ];
-            fz_tok_lens(t, tin, tl);
-            if (tin) { const uint32_t x = tt[tin - 1u]; tinb = x & 0xffffffu; tinl = x >> 24; }
+        if (slow) {   // ... or, for a held quad, what leaves there: a match of 258, the rest of a run that ends, or nothing
+            uint32_t tin, cross, tl[FZ_E2_LQ];
+            fz_tok_lens(t, tin, cross, tl);
+            if (tin >= FZ_MIN_MATCH) { const uint32_t x = tt[tin - 3u]; tinb = x & 0xffffffu; tinl = x >> 24; }
+            else if (tin) fz_run_token(cl, tin, t.pb, tinb, tinl);
 #pragma unroll
             for (int g = 0; g < FZ_E2_LQ; g++)
                 if ((t.hq >> g) & 1u) {
-                    const uint32_t x = tl[g] ? tt[tl[g] - 1u] : 0u;
-                    qv[g] = x & 0xffffffu;
-                    ql[g] = x >> 24;
+                    uint64_t b = 0;
+                    uint32_t l = 0;
+                    if ((cross >> g) & 1u) { b = t258 & 0xffffffu; l = t258 >> 24; }
+                    if (tl[g] >= FZ_MIN_MATCH) {
+                        const uint32_t x = tt[tl[g] - 3u];
+                        b |= (uint64_t)(x & 0xffffffu) << l;
+                        l += x >> 24;
+                    } else if (tl[g]) {   // one or two bytes left over behind a match of 258: literals
+                        uint32_t eb, el;
+                        fz_run_token(cl, tl[g], v.w[g] & 0xffu, eb, el);
+                        b |= (uint64_t)eb << l;
+                        l += el;
+                    }
+                    qv[g] = b;
+                    ql[g] = l;
                 }
         }
         uint32_t tot = tinl;
@@ -508,9 +541,10 @@ FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t 
     if (lane == 0) {
         uint32_t off = P;
         if (c.m) {
-            const uint32_t x = tt[c.m - 1u];
-            fz_ring_put32(w, ring, off, x & 0xffffffu, x >> 24);
-            off += x >> 24;
+            uint32_t b, l;
+            fz_run_token(cl, c.m, c.prev & 0xffu, b, l);
+            fz_ring_put32(w, ring, off, b, l);
+            off += l;
         }
         fz_ring_put32(w, ring, off, cl[FZ_EOB] & 0xffffu, cl[FZ_EOB] >> 16);
         off += cl[FZ_EOB] >> 16;

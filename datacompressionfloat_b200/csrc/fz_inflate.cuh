@@ -250,22 +250,22 @@ FZ_HD int fz_decode_idx(const FzCode &r, uint32_t bits15, uint32_t &idx)
     return len <= 15 ? (int)len : 0;
 }
 
-// first-level table entry for the FZ_LUT_BITS-bit pattern e: the first symbol and up to two more literals
-template <class Tab>
-FZ_HD uint32_t fz_lut_entry(const FzCode &LL, const Tab &tab, uint32_t e)
+// first-level table entry for the LUT_BITS-bit pattern e: the first symbol and up to two more literals
+template <int LUT_BITS, class Tab>
+FZ_HD uint32_t fz_lut_entry_bits(const FzCode &LL, const Tab &tab, uint32_t e)
 {
     uint32_t idx;
     int l = fz_decode_idx(LL, e, idx);
-    if (!(l >= 1 && l <= FZ_LUT_BITS && idx < 288)) return 0;
+    if (!(l >= 1 && l <= LUT_BITS && idx < 288)) return 0;
     const uint32_t s1 = tab.L((int)idx);
     uint32_t s2 = 0, s3 = 0, cnt = 1, total = (uint32_t)l;
-    if (s1 < 256u && total < FZ_LUT_BITS) {
+    if (s1 < 256u && total < (uint32_t)LUT_BITS) {
         l = fz_decode_idx(LL, e >> total, idx);
-        if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && tab.L((int)idx) < 256u) {
+        if (l >= 1 && total + l <= (uint32_t)LUT_BITS && idx < 288 && tab.L((int)idx) < 256u) {
             s2 = tab.L((int)idx); total += l; cnt = 2;
-            if (total < FZ_LUT_BITS) {
+            if (total < (uint32_t)LUT_BITS) {
                 l = fz_decode_idx(LL, e >> total, idx);
-                if (l >= 1 && total + l <= FZ_LUT_BITS && idx < 288 && tab.L((int)idx) < 256u) {
+                if (l >= 1 && total + l <= (uint32_t)LUT_BITS && idx < 288 && tab.L((int)idx) < 256u) {
                     s3 = tab.L((int)idx); total += l; cnt = 3;
                 }
             }
@@ -277,6 +277,8 @@ FZ_HD uint32_t fz_lut_entry(const FzCode &LL, const Tab &tab, uint32_t e)
     if (s1 >= 257u && s1 <= 285u) ent |= FZ_LUT_MATCH | (fz_len_base(s1 - 257u) << 9) | (fz_len_extra_bits(s1 - 257u) << 18);
     return ent;
 }
+template <class Tab>
+FZ_HD uint32_t fz_lut_entry(const FzCode &LL, const Tab &tab, uint32_t e) { return fz_lut_entry_bits<FZ_LUT_BITS>(LL, tab, e); }
 
 // Which value of a 1-bit distance code means "distance 1" (what run-length streams use): 0 or 1, or 2 = this block's
 // distance code is not of that kind (see FzInflater::dd1).
@@ -308,6 +310,7 @@ struct FzInflater {
     bool last, in_body;
     bool shared_tab;  // tables are shared with other lanes: this lane must not rebuild them (no further coded block)
     uint32_t *own_lut;  // optional FZ_LUT_SIZE-entry table this thread (re)builds after every block header
+    int lut_bits;       // index width of the table handed to step_lut (FZ_LUT_BITS unless the caller built a wider one)
     bool one_block;     // stop after the first coded block (block-parallel decode of zlib-made streams)
     bool saw_eob;       // ... and it ended properly with its end-of-block symbol
     int ll_left, dd_left;  // Kraft remainders of the last dynamic header (0 = complete code)
@@ -326,6 +329,7 @@ struct FzInflater {
         in_body = false;
         shared_tab = false;
         own_lut = nullptr;
+        lut_bits = FZ_LUT_BITS;
         one_block = false; saw_eob = false; ll_left = 0; dd_left = 0; eob_len = 1; dd1 = 0;
     }
     // start `bit` bits into the input (block-parallel decode)
@@ -370,7 +374,7 @@ struct FzInflater {
         if (bw.dry && br.bits_left() < 0) return fail(FZ_INF_E_INPUT);
         uint32_t idx, sym;
         int l;
-        const uint32_t e = lut ? lut[br.peek(FZ_LUT_BITS)] : 0u;
+        const uint32_t e = lut ? lut[br.peek(lut_bits)] : 0u;
         if (e) {
             const uint32_t cnt = e >> 29;
             sym = e & 511u;

@@ -589,9 +589,10 @@ __device__ __forceinline__ bool fz_slot(const FzBatchGeom &g, uint32_t t, uint32
     return true;
 }
 
+// code groups (FZ_CODE_SUBS sub-blocks that share one Huffman code) per stream
 __device__ __forceinline__ uint32_t fz_groups_per_stream(const FzBatchGeom &g)
 {
-    return (g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS;
+    return (g.nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS;
 }
 
 struct __align__(16) FzHistSmem {
@@ -623,7 +624,7 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
         // the mask erases this whole byte plane (8 or more bits erased) and the sub-block lies behind the exempt
         // header words: 16 KiB of zeros, known without reading them
         if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
-        uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+        uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
         for (int i = lane; i < 288; i += 32) {
             const uint32_t v = zero_hist[i];
             if (v) atomicAdd(gh + i, v);
@@ -667,7 +668,7 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
             }
             if (!__any_sync(0xffffffffu, any != 0)) {
                 if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
-                uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+                uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
                 for (int i = lane; i < 288; i += 32) {
                     const uint32_t v = zero_hist[i];
                     if (v) atomicAdd(gh + i, v);
@@ -706,7 +707,7 @@ fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__re
     }
 #endif
     __syncwarp();
-    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
     for (int i = lane; i < 288; i += 32) {
         const uint32_t v = sm->hist[i];
         if (v) atomicAdd(gh + i, v);
@@ -737,7 +738,7 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
     if (gi >= g.nchunks * FZ_PLANES * gps) return;
     const uint32_t s = gi / gps, gk = gi - s * gps;
     const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
-    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
+    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_CODE_SUBS;
     if ((uint64_t)gk * gbytes >= n_s) return;
     const uint32_t gn = (uint32_t)min((uint64_t)n_s - (uint64_t)gk * gbytes, gbytes);
     const uint32_t nsub = (gn + FZ_SUB - 1) / FZ_SUB;
@@ -786,7 +787,7 @@ fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupC
     if (!fz_slot(g, t, s, k, n)) return;
     const uint32_t sz0 = sizes[t];
     if (sz0 & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
-    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
+    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS);
     if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to stage or emit
         if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
         return;
@@ -885,7 +886,7 @@ fz_hist2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__r
     if (!fz_slot(g, t, s, k, n)) return;
     uint32_t *hist = hist_sh[warp];
     const uint8_t *src = fz_sub_src(planes, g, s, k);
-    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS) * 288;
+    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
     const uint64_t masked_from = g.chunk_exempt ? (uint64_t)(s >> 2) * g.chk + g.chunk_exempt[s >> 2] : zero_from;
     if (n == FZ_SUB && ((zero_planes >> (s & 3u)) & 1u) && (uint64_t)(s >> 2) * g.chk + (uint64_t)k * FZ_SUB >= masked_from) {
         // the mask erases this whole byte plane (8 or more bits erased) and the sub-block lies behind the exempt
@@ -986,10 +987,13 @@ fz_zero_hist2_kernel(uint32_t *__restrict__ zero_hist)
 struct __align__(16) FzEmit2Smem {
     uint32_t ring[FZ_E2_RING_WORDS];
     uint32_t gc_hot[FZ_GROUP_CODE_HOT_BYTES / 4];
-    uint32_t tt[FZ_E2_MAX_QUADS];   // the group's run tokens
+    uint32_t tt[256];   // the group's match tokens
 };
 
-__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
+#ifndef FZ_EMIT_MINBLOCKS
+#define FZ_EMIT_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP, FZ_EMIT_MINBLOCKS)
 fz_emit2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupCode *__restrict__ gcodes,
                 uint8_t *__restrict__ scratch, uint32_t *__restrict__ sizes, FzStatus *status)
 {
@@ -1001,7 +1005,7 @@ fz_emit2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroup
     if (!fz_slot(g, t, s, k, n)) return;
     const uint32_t sz0 = sizes[t];
     if (sz0 & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
-    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_GROUP_SUBS);
+    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS);
     if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to emit
         if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
         return;
@@ -1058,7 +1062,7 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t total = nstreams * g.nsub_full;
-    const uint32_t gps = (g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS;
+    const uint32_t gps = (g.nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS;
     const uint32_t ngroups = nstreams * gps;
     const unsigned grid = (total + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS;
     cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
@@ -1561,7 +1565,7 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 #define FZ_INF_CARVEOUT_PCT 100    // all of the 228 KB as shared memory: 4 CTAs x 54 KB
 #endif
 #ifndef FZ_INF_MINBLOCKS
-#define FZ_INF_MINBLOCKS 1
+#define FZ_INF_MINBLOCKS 4            // measured: 4 CTAs (102 registers) beat 5 and 6 on the exponent planes; 12-bit table on the 4-bit planes
 #endif
 #define FZ_ZERO_PROBE_BYTES 96u   // 16 KiB of zeros is ~70 bytes of run codes
 #ifndef FZ_RING_CHUNKS
@@ -1574,11 +1578,22 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 #ifndef FZ_FAST_ITERS
 #define FZ_FAST_ITERS 16
 #endif
+#ifndef FZ_GLUT_BITS
+#define FZ_GLUT_BITS 12                          // the CTA's table: 4096 entries, three literals of 4 bits in one lookup
+#endif
+#define FZ_GLUT_SIZE (1u << FZ_GLUT_BITS)
+#define FZ_CODE_WARPS (FZ_CODE_SUBS / FZ_GROUP_SUBS)
+static_assert(FZ_INF_WARPS == FZ_CODE_WARPS, "one CTA of the group inflater decodes one code group");
 struct FzGroupSmem {
-    alignas(16) uint32_t ring[FZ_WARP * FZ_RING_ROW_WORDS];  // every lane's window on its fragment (cp.async)
-    uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse (shared by the warp)
-    uint32_t lut[FZ_LUT_SIZE];
-    FzCode LL, DD;                 // the group's codes (long codes and distances; the LUT covers the rest)
+    // shared by the CTA: the code of the group (its sub-blocks carry the same block header)
+    alignas(16) uint32_t lut[FZ_GLUT_SIZE];
+    uint16_t tab[FZ_INF_TAB_U16];  // sorted symbols + counters of the leader's parse
+    FzCode LL, DD;                 // long codes and distances; the table covers the rest
+    uint32_t wmask[FZ_INF_WARPS];  // coded lanes of every warp
+    uint32_t hdr_bits, leader_ok, dd1, pad;
+    unsigned long long lfrag;      // the leader's fragment
+    // per warp: every lane's window on its fragment (cp.async)
+    alignas(16) uint32_t ring[FZ_INF_WARPS][FZ_WARP * FZ_RING_ROW_WORDS];
 };
 
 __global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP, FZ_INF_MINBLOCKS)
@@ -1589,20 +1604,18 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                         const FzStatus *status)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
-    FzGroupSmem *smem = (FzGroupSmem *)fz_smem;
+    FzGroupSmem *sm = (FzGroupSmem *)fz_smem;
     if (status->error) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t gps = fz_groups_per_stream(g);
-    const uint32_t gi = blockIdx.x * FZ_INF_WARPS + warp;
-    if (gi >= g.nchunks * FZ_PLANES * gps) return;  // warp-uniform
-    const uint32_t s = gi / gps, gk = gi - s * gps;
-    if ((stream_mode[s] & 0xffu) != 1u) return;      // warp-uniform
+    const uint32_t cps = fz_groups_per_stream(g);      // code groups per stream
+    const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
+    if ((stream_mode[s] & 0xffu) != 1u) return;      // CTA-uniform
     const uint32_t h0 = tile_off[s * tiles_per_stream], h1 = tile_off[(s + 1) * tiles_per_stream];
     const uint32_t m = h1 - h0;                      // sub-blocks in the stream
-    if (gk * FZ_GROUP_SUBS >= m) return;             // warp-uniform
-    FzGroupSmem *sm = &smem[warp];
+    if (ck * FZ_CODE_SUBS >= m) return;              // CTA-uniform
+    const uint32_t gk = ck * FZ_CODE_WARPS + (uint32_t)warp;
     const uint32_t k = gk * FZ_GROUP_SUBS + lane;
-    const bool valid = k < m;
+    const bool valid = k < m;                        // (a warp past the end of the stream idles through the barriers below)
     const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
     uint32_t start = 0, end = 0, expect = 0;
     uint8_t *out = nullptr;
@@ -1622,33 +1635,42 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     bool live = false, bad = false;
     if (valid) { inf.start(frag, flen, out, expect, tab); inf.shared_tab = true; live = true; }
     inf.bind_codes(&sm->LL, &sm->DD);
+    inf.lut_bits = FZ_GLUT_BITS;
 
     // block type of every lane's first block: 2 (dynamic) lanes share the leader's code
     uint32_t first3 = 7;
     if (valid && flen >= 1) first3 = frag[0] & 7u;   // BFINAL (must be 0) | BTYPE << 1
     const bool coded = valid && first3 == 4u;        // BFINAL = 0, BTYPE = 10
     const uint32_t coded_mask = __ballot_sync(0xffffffffu, coded);
+    if (lane == 0) sm->wmask[warp] = coded_mask;
+    __syncthreads();
+    int lw = -1;
+#pragma unroll
+    for (int w2 = FZ_INF_WARPS - 1; w2 >= 0; w2--) if (sm->wmask[w2]) lw = w2;
+    const bool any_coded = lw >= 0;                  // CTA-uniform
     uint32_t hdr_bits = 0;
-    if (coded_mask) {
-        const int leader = __ffs((int)coded_mask) - 1;
-        if (lane == leader) {
+    if (any_coded) {
+        const int leader = __ffs((int)sm->wmask[lw]) - 1;
+        const bool is_leader = warp == lw && lane == leader;
+        if (is_leader) {
             inf.shared_tab = false;
-            const bool okh = inf.block_header();     // parses the header, fills sm->tab, LL / DD in registers
+            const bool okh = inf.block_header();     // parses the header, fills sm->tab, LL / DD
             inf.shared_tab = true;
             if (!okh || !inf.in_body) { bad = true; live = false; }
-            hdr_bits = (uint32_t)((int64_t)flen * 8 - inf.br.bits_left());
+            sm->hdr_bits = (uint32_t)((int64_t)flen * 8 - inf.br.bits_left());
+            sm->leader_ok = bad ? 0u : 1u;
+            sm->dd1 = inf.dd1;
+            sm->lfrag = (unsigned long long)(uintptr_t)frag;
         }
-        __syncwarp();
-        const uint32_t leader_ok = __shfl_sync(0xffffffffu, (uint32_t)(!bad), leader);
-        hdr_bits = __shfl_sync(0xffffffffu, hdr_bits, leader);
-        inf.dd1 = __shfl_sync(0xffffffffu, inf.dd1, leader);
-        if (!leader_ok) {
+        __syncthreads();
+        hdr_bits = sm->hdr_bits;
+        inf.dd1 = sm->dd1;
+        if (!sm->leader_ok) {
             if (coded) { bad = true; live = false; }
         } else {
             // every other coded lane: its first hdr_bits must equal the leader's, then skip them
-            const unsigned long long lfrag = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)frag, leader);
-            if (coded && lane != leader) {
-                const uint8_t *lf = (const uint8_t *)(uintptr_t)lfrag;
+            if (coded && !is_leader) {
+                const uint8_t *lf = (const uint8_t *)(uintptr_t)sm->lfrag;
                 const uint32_t nby = hdr_bits >> 3, rem = hdr_bits & 7u;
                 bool same = (uint64_t)flen * 8 > hdr_bits;
                 if (same) {
@@ -1665,10 +1687,11 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                 }
             }
             // first-level table: entry e = the first symbol (and up to two more literals) coded by the bit pattern e
-            for (uint32_t e = lane; e < FZ_LUT_SIZE; e += 32) sm->lut[e] = fz_lut_entry(sm->LL, tab, e);
+            for (uint32_t e = threadIdx.x; e < FZ_GLUT_SIZE; e += FZ_INF_WARPS * FZ_WARP) sm->lut[e] = fz_lut_entry_bits<FZ_GLUT_BITS>(sm->LL, tab, e);
         }
-        __syncwarp();
+        __syncthreads();
     }
+    if (gk * FZ_GROUP_SUBS >= m) return;             // warp-uniform: nothing of the stream left for this warp
     // Stored sub-blocks (incompressible bytes: two stored blocks and the empty one) are copied by the whole warp, 16
     // bytes per lane and step; left to their lane they would be a word-by-word loop that the 31 others wait for.
     // Anything but exactly that layout stays with its lane and the general code.
@@ -1698,7 +1721,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
         }
     }
     // lock-step drive: lanes reconverge after every symbol
-    const uint32_t *lut = coded_mask ? sm->lut : nullptr;
+    const uint32_t *lut = any_coded ? sm->lut : nullptr;
     const uint32_t run_bit = fz_dd1_run_bit(inf.dd1);
     // Tiny fragments are almost always sub-blocks of zero bytes (mask bits >= 8 zero whole byte planes).  Count them
     // first without storing: if the fragment is valid and all zero it is only flagged -- the merge supplies the
@@ -1771,7 +1794,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
         const uint32_t mis = (uint32_t)((uintptr_t)frag & 15u);
         const uint8_t *gbase = frag - mis;                               // chunk 0
         const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
-        uint32_t *row = sm->ring + lane * FZ_RING_ROW_WORDS;
+        uint32_t *row = sm->ring[warp] + lane * FZ_RING_ROW_WORDS;
         const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(row);
         uint64_t acc = 0;
         uint32_t nxt = 0, rp = 0, fetched = 0;
@@ -1825,7 +1848,7 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                     nacc += need ? 32 : 0;
                     rp += need ? 1u : 0u;
                     nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
-                    const uint32_t e = lut[(uint32_t)acc & (FZ_LUT_SIZE - 1)];
+                    const uint32_t e = lut[(uint32_t)acc & (FZ_GLUT_SIZE - 1)];
                     if (e & 0x100u) {
                         // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
                         if (!(e & FZ_LUT_MATCH) || run_bit > 1u) { slow = true; break; }
@@ -2309,13 +2332,13 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     if (zf) cudaMemsetAsync(zf, 0, (size_t)nstreams * g.nsub_full * 4, st);
     fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, b.bp, status);
     if (mark) mark(mark_user, FZ_ST_CLASSIFY);
-    const uint32_t ngroups = nstreams * ((g.nsub_full + FZ_GROUP_SUBS - 1) / FZ_GROUP_SUBS);
+    const uint32_t ncode = nstreams * ((g.nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS);   // one CTA per code group
     // Every lane streams its own fragment: what little L1 the shared-memory carve-out leaves decides how often an input
     // word is an L2 round trip.  164 KB of shared memory (4 CTAs of 37 KB) and 92 KB of L1 beat 228 KB / 6 CTAs by
     // 20-25 % on every input measured (sweep in profiles/README.md).
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FZ_INF_CARVEOUT_PCT);
-    cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzGroupSmem) * FZ_INF_WARPS));
-    fz_inflate_group_kernel<<<(ngroups + FZ_INF_WARPS - 1) / FZ_INF_WARPS, FZ_INF_WARPS * FZ_WARP, sizeof(FzGroupSmem) * FZ_INF_WARPS, st>>>(
+    cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzGroupSmem));
+    fz_inflate_group_kernel<<<ncode, FZ_INF_WARPS * FZ_WARP, sizeof(FzGroupSmem), st>>>(
         container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater

@@ -184,21 +184,27 @@ template <class Lit, class Match>
 void seq_tokens(const uint8_t *p, uint32_t n, Lit &&lit, Match &&match)
 {
     // the quad rule of fz_enc2.cuh, one quad after the other
-    uint32_t m = 0;
+    uint32_t m = 0, runb = 0;
     bool prevE = false;
+    auto rest = [&]() {
+        if (m >= FZ_MIN_MATCH) match(m); else for (uint32_t i = 0; i < m; i++) lit(runb);
+        m = 0;
+    };
     for (uint32_t q0 = 0; q0 < n; q0 += 4) {
         const uint32_t nb = n - q0 < 4 ? n - q0 : 4;
         bool E = nb == 4 && q0 > 0;
         for (uint32_t i = 0; E && i < 4; i++) E = p[q0 + i] == p[q0 + i - 1];
         if (E && prevE) {
-            if (++m == FZ_E2_MAX_QUADS) { match(4 * FZ_E2_MAX_QUADS); m = 0; }
+            runb = p[q0];
+            m += 4;
+            if (m >= FZ_MAX_MATCH) { match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
         } else {
-            if (m) { match(4 * m); m = 0; }
+            if (m) rest();
             for (uint32_t i = 0; i < nb; i++) lit(p[q0 + i]);
         }
         prevE = E;
     }
-    if (m) match(4 * m);
+    if (m) rest();
 }
 
 struct SeqBits {
@@ -251,7 +257,7 @@ uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64
     std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8);
     FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
     FzGroupCode *gc = (FzGroupCode *)malloc(sizeof(FzGroupCode));
-    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
+    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_CODE_SUBS;
     for (uint64_t g0 = 0; g0 < n; g0 += gbytes) {
         const uint64_t gn = (n - g0) < gbytes ? (n - g0) : gbytes;
         const uint32_t nsub = (uint32_t)((gn + FZ_SUB - 1) / FZ_SUB);
@@ -287,7 +293,7 @@ uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64
         }
         if (hm_hist_sample > 1) {
             for (int i = 0; i < 256; i++) st->hist[i] += 1;
-            for (uint32_t q = 1; q <= FZ_E2_MAX_QUADS; q++) { uint32_t lc, eb, ev; fz_len_code(4 * q, lc, eb, ev); if (st->hist[257 + lc] == 0) st->hist[257 + lc] = 1; }
+            for (int i = 257; i < 286; i++) if (st->hist[i] == 0) st->hist[i] = 1;
         }
         st->hist[FZ_EOB] = nsub;
         memset(gc, 0xEE, sizeof(FzGroupCode));
@@ -300,7 +306,7 @@ uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64
             if (!gc->stored) {
                 if (mode == 0) {
                     for (auto &w : slot) w = 0xDEADBEEFu;
-                    std::vector<uint32_t> ring(FZ_E2_RING_WORDS, 0xABABABABu), tt(64, 0xCDCDCDCDu);
+                    std::vector<uint32_t> ring(FZ_E2_RING_WORDS, 0xABABABABu), tt(256, 0xCDCDCDCDu);
                     HostLoad16 ld{pad.data()};
                     uint32_t res[32];
                     run_warp([&](const FzWarp &w) {
