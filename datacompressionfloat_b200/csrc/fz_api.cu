@@ -386,20 +386,19 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
     const uint32_t nstreams = bmax * FZ_PLANES;
     ib->tiles_per_stream = chk / 65536 + 2;  // FZ_TILE_BYTES
     const size_t ntiles = (size_t)nstreams * ib->tiles_per_stream;
-    ib->hits_cap = (uint32_t)((size_t)nstreams * nsub_full * 2 + 1024);
-    const size_t nbsum = (ntiles + 4095) / 4096 + 4;
+    ib->hits_per_stream = nsub_full * 2 + 16;   // twice what our own framing produces: more markers than that is a foreign stream
     int rc;
     if ((rc = ensure(c->planes, pstride * FZ_PLANES + 256)) || (rc = ensure(c->stream_hdr, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_off, (size_t)nstreams * 8)) || (rc = ensure(c->stream_mode, (size_t)nstreams * 4)) ||
         (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
-        (rc = ensure(c->block_sums, nbsum * 4)) || (rc = ensure(c->hits, (size_t)ib->hits_cap * 4)) ||
+        (rc = ensure(c->block_sums, (size_t)nstreams * 4)) || (rc = ensure(c->hits, (size_t)nstreams * ib->hits_per_stream * 4)) ||
         (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams, chk))) ||
         (rc = ensure(c->zero_flags, (size_t)nstreams * nsub_full * 4)))
         return rc;
     ib->zero_flags = (uint32_t *)c->zero_flags.p;
     ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams, chk);
     ib->tile_cnt = (uint32_t *)c->tile_cnt.p;
-    ib->block_sums = (uint32_t *)c->block_sums.p;
+    ib->stream_cnt = (uint32_t *)c->block_sums.p;
     ib->hits = (uint32_t *)c->hits.p;
     ib->stream_mode = (uint32_t *)c->stream_mode.p;
     ib->stream_fail = (uint32_t *)c->stream_fail.p;
@@ -417,7 +416,7 @@ static void decompress_enqueue_batch(mzb_ctx *c, const uint8_t *d_in, size_t in_
     fz_launch_inflate(d_in, in_size, g, (const uint32_t *)c->stream_hdr.p, (const unsigned long long *)c->stream_off.p, ib,
                       (uint8_t *)c->planes.p, c->d_status, c->stream, prof_mark, c, !in_place_raw);
     if (in_place_raw)
-        fz_launch_merge_streams((const uint8_t *)c->planes.p, d_in, (const uint32_t *)c->stream_hdr.p,
+        fz_launch_merge_streams((const uint8_t *)c->planes.p, d_in, in_size, (const uint32_t *)c->stream_hdr.p,
                                 (const unsigned long long *)c->stream_off.p, ib.zero_flags, g, d_words_out, c->stream);
     else
         fz_launch_merge((const uint8_t *)c->planes.p, g.plane_stride, (uint64_t)(g.nchunks - 1) * g.chk + g.last_n, d_words_out,
@@ -453,7 +452,9 @@ static void fill_decompress_stats(mzb_ctx *c, uint64_t bytes_in, uint64_t nwords
 static uint32_t compress_launches(uint64_t nw) { return 7 + ((nw & 3) ? 1 : 0); }
 static uint32_t decompress_launches(uint64_t nw, bool in_place_raw)
 {
-    return 1 + 8 + 6 + (in_place_raw ? 0 : 1) + 1 + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+    // walk, marker scan, classify, group inflate, six block-parallel kernels, general inflate, then either the
+    // in-place merge or RAW copy + merge (+ tail)
+    return 1 + 2 + 1 + 6 + 1 + (in_place_raw ? 1 : 2) + ((!in_place_raw && (nw & 3)) ? 1 : 0);
 }
 
 extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,

@@ -1,16 +1,15 @@
-// fz_deflate_enc.cuh -- warp-cooperative deflate encoder for ONE sub-block (<= FZ_SUB bytes) of a byte plane.
+// fz_deflate_enc.cuh -- the Huffman code and dynamic-block header of a CODE GROUP, built by one warp.
 //
-// Replaces, for one sub-block, what the reference gets from zlib's deflate(Z_RLE, level 6) behind
-// mzlib_def (reference zip.c:164-196, constants constant.h:22-24): distance-1 run matches of
-// 3..258 bytes, one dynamic-Huffman block, then an empty stored block (the sync-flush marker) so
-// the next sub-block starts byte aligned.  BFINAL is never set (reference decoder requirement,
-// SURVEY.md 7.2).  The produced bytes are a valid raw-deflate fragment, not zlib's bytes.
+// The encoder replaces what the reference gets from zlib's deflate(Z_RLE, level 6) behind mzlib_def (reference
+// zip.c:164-196, constants constant.h:22-24): distance-1 run matches of 3..258 bytes, dynamic-Huffman blocks, an empty
+// stored block (the sync-flush marker) behind every sub-block so that the next one starts byte aligned; BFINAL is
+// never set (reference decoder requirement).  The bytes are valid raw deflate, not zlib's bytes.
 //
-// One Huffman code serves a GROUP of FZ_GROUP_SUBS consecutive sub-blocks of a stream (512 KiB): the
-// histogram of the group is collected first, the code and the block header are built once per group
-// (fz_build_group_code), and every sub-block is then emitted as its own dynamic block carrying that
-// same header.  The GPU inflater exploits this: the 32 lanes of a warp decode the 32 sub-blocks of a
-// group with ONE shared lookup table (it verifies the headers really are identical).
+// One Huffman code serves FZ_CODE_SUBS consecutive sub-blocks of a stream (2 MiB of a plane): the token histogram of
+// the group is collected first (fz_enc2.cuh), the code and the block header are built once per group here
+// (fz_build_group_code), and every sub-block is then emitted as its own dynamic block carrying that same header
+// (fz_enc2.cuh).  The GPU inflater exploits this: the four warps of a CTA decode the 128 sub-blocks of a group with
+// ONE shared lookup table (it verifies that the headers really are identical).
 //
 // SPMD style: `lane` is 0..31; a phase may only communicate through FzEncState (shared memory on the
 // GPU).  FZ_PHASE(x) runs x for this lane and then __syncwarp() on the device; on the host
@@ -66,19 +65,6 @@ struct FzEncState {
     uint32_t fw_idx[32], fw_bits[32], tw_bits[32], crossed[32];
 };
 
-// -------------------------------------------------------------------------------------------------
-// Run tokeniser (distance-1 matches only, the reference's Z_RLE strategy).  A byte equal to its
-// predecessor is a "repeat".  The first FZ_HOLD_AFTER repeats of a run are emitted as literals right
-// away; from the next repeat on bytes are withheld and leave as one match (3..258) when the run ends
-// or 258 are pending -- or as 1-2 literals if fewer than 3 were withheld.  (zlib withholds from the
-// first repeat.  Short runs of a frequent symbol cost about the same either way; starting late keeps
-// "a run starts inside this 16-byte group" rare -- with 32 lanes scanning 32 pieces in lock step that
-// event is what serialises the warp: at FZ_HOLD_AFTER = 2 it hit 13 % of the groups of a float
-// exponent plane, i.e. nearly every warp iteration; at 6 it is 0.02 %.)
-// `prev_init` < 0 means "no byte before `begin`" (sub-block start: sub-blocks never reference earlier data).
-// -------------------------------------------------------------------------------------------------
-#define FZ_HOLD_AFTER 6
-
 FZ_HD int fz_ctz32(uint32_t v)  // v != 0
 {
 #if defined(__CUDA_ARCH__)
@@ -88,273 +74,7 @@ FZ_HD int fz_ctz32(uint32_t v)  // v != 0
 #endif
 }
 
-FZ_HD uint32_t fz_byte_dyn(const FzVec16 &v, uint32_t k)  // byte k (0..15) of a register-resident group
-{
-    const uint32_t w = k < 8 ? (k < 4 ? v.w[0] : v.w[1]) : (k < 12 ? v.w[2] : v.w[3]);
-    return (w >> ((k & 3) * 8)) & 0xffu;
-}
-
-// number of consecutive bits equal to bit 0 of x, starting at bit 0 (x != 0 and x != ~0 is not required: capped by `width`)
-FZ_HD uint32_t fz_run_len(uint32_t x, uint32_t width)
-{
-    const uint32_t y = (x & 1u) ? ~x : x;  // now the run is a run of zeros
-    const uint32_t r = y ? (uint32_t)fz_ctz32(y) : 32u;
-    return r < width ? r : width;
-}
-
-// The tokeniser's state between 16-byte groups (so that a caller can feed a piece window by window).
-struct FzScan {
-    int prev;        // last byte seen, -1 = none
-    uint32_t rep;    // repeats of `prev` seen so far in this run (saturates at FZ_HOLD_AFTER)
-    uint32_t m;      // withheld bytes
-    FZ_HD void init(int prev_init) { prev = prev_init; rep = 0; m = 0; }
-
-    // Whole 16-byte group at once.  Bit k+H of eq = byte k equals its predecessor (H = FZ_HOLD_AFTER); the
-    // H bits below stand for the bytes before the group (from `rep`).  Byte k is withheld iff the
-    // H+1 flags ending at k are all set.
-    template <class Sink>
-    FZ_HD void group16(const FzVec16 &v, Sink &sink)
-    {
-        // four bytes per step: XOR each word with itself shifted up one byte (the predecessor of byte 0 comes from
-        // the word before), find the zero bytes exactly, gather their flags with one multiply
-        uint32_t eq = 0;
-        uint32_t before = (uint32_t)prev << 24;   // prev = -1 (no predecessor) gives 0xFF...: compared as 0xFF, fixed below
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t w = v.w[j];
-            const uint32_t x = w ^ ((w << 8) | (before >> 24));
-            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte of x
-            eq |= ((z * 0x00204081u) >> 28) << (4 * j + FZ_HOLD_AFTER);
-            before = w;
-        }
-        if (prev < 0) eq &= ~(1u << FZ_HOLD_AFTER);   // the first byte of a piece has no predecessor
-        const int p = (int)(v.w[3] >> 24);
-        const uint32_t hist_bits = ((1u << rep) - 1u) << (FZ_HOLD_AFTER - rep);  // the last `rep` flags before the group
-        const uint32_t ext = eq | hist_bits;
-        uint32_t held = ext;
-#pragma unroll
-        for (int j = 1; j <= FZ_HOLD_AFTER; j++) held &= ext << j;
-        held >>= FZ_HOLD_AFTER;  // 16 bits: byte k of the group is withheld
-        if (!Sink::kOrdered) {
-            // token order is irrelevant (histogram, bit count): every byte that is not withheld is a literal,
-            // all lanes run the same code whatever their data; runs are book-kept below (rare)
-            // (when no lane of the warp withholds anything the unpredicated form is a little cheaper)
-            if (FZ_WARP_ALL(held == 0)) sink.literal16(v);
-            else if (!FZ_WARP_ALL(held == 0xffffu)) sink.literal_masked(v, ~held & 0xffffu);  // (all-run groups: nothing)
-        } else if (held == 0 && m == 0) {
-            sink.literal16(v);                 // the common case of the ordered (emitting) pass
-        }
-        if (held | m) {
-            // runs: walk the alternating segments of `held`
-            uint32_t pos = 0;
-            while (pos < 16) {
-                const uint32_t rest = held >> pos;
-                const uint32_t r = fz_run_len(rest, 16 - pos);
-                if (rest & 1u) {               // withheld bytes
-                    m += r;
-                    pos += r;
-                    if (m >= FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
-                    if (pos < 16) {            // the run ends inside the group
-                        if (m >= FZ_MIN_MATCH) sink.match(m); else if (m) sink.literal(fz_byte_dyn(v, pos - 1), m);
-                        m = 0;
-                    }
-                } else {                       // ordinary bytes
-                    if (m) {                   // a run carried over from the previous group ends here (pos == 0)
-                        if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-                        m = 0;
-                    }
-                    if (Sink::kOrdered)
-                        for (uint32_t k = pos; k < pos + r; k++) sink.literal(fz_byte_dyn(v, k), 1);
-                    pos += r;
-                }
-            }
-        }
-        // repeats at the end of the group: trailing ones of the flag word, saturated
-        const uint32_t inv = ~(ext >> FZ_HOLD_AFTER) & 0xffffu;        // zero flag = run break
-        const uint32_t t = inv ? (uint32_t)(15 - fz_ilog2(inv)) : 16u + rep;  // flags set after the last break
-        rep = t > FZ_HOLD_AFTER ? FZ_HOLD_AFTER : t;
-        prev = p;
-    }
-
-    // one byte (ragged tails)
-    template <class Sink>
-    FZ_HD void byte(int c, Sink &sink)
-    {
-        const bool e = c == prev;
-        if (e && rep >= FZ_HOLD_AFTER) {
-            if (++m == FZ_MAX_MATCH) { sink.match(FZ_MAX_MATCH); m = 0; }
-        } else {
-            if (m) {
-                if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-                m = 0;
-            }
-            rep = e ? rep + 1 : 0;
-            prev = c;
-            sink.literal((uint32_t)c, 1);
-        }
-    }
-
-    // end of the piece: what is still withheld leaves
-    template <class Sink>
-    FZ_HD void finish(Sink &sink)
-    {
-        if (m) {
-            if (m >= FZ_MIN_MATCH) sink.match(m); else sink.literal((uint32_t)prev, m);
-            m = 0;
-        }
-    }
-};
-
-template <class Load16, class LoadByte, class Sink>
-FZ_HD void fz_scan_piece(const Load16 &ld, const LoadByte &lb, uint32_t begin, uint32_t end, int prev_init, Sink &sink)
-{
-    FzScan sc;
-    sc.init(prev_init);
-    for (uint32_t i = begin; i < end; i += 16) {
-        const uint32_t lim = end - i;
-        if (lim >= 16) { sc.group16(ld(i), sink); continue; }
-        for (uint32_t k = 0; k < lim; k++) sc.byte((int)lb(i + k), sink);   // ragged tail (< 16 bytes): byte by byte
-    }
-    sc.finish(sink);
-}
-
-// A "piece scan" feeds this lane's piece of a sub-block through the tokeniser into a sink: scan(sink, lane).
-// Generic form: lane l owns bytes [l*P, min(n, (l+1)*P)) behind random-access loaders.  (The device's fast path
-// streams the pieces through a small shared-memory window instead: FzWindowScan in fz_kernels.cu.)
-FZ_HD uint32_t fz_piece_len(uint32_t n);
-template <class Load16, class LoadByte>
-struct FzPieceScan {
-    const Load16 &ld;
-    const LoadByte &lb;
-    uint32_t n;
-    template <class Sink>
-    FZ_HD void operator()(Sink &sink, int lane) const
-    {
-        const uint32_t P = fz_piece_len(n);
-        uint32_t b = lane * P, e = b + P;
-        if (e > n) e = n;
-        if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
-    }
-};
-
-FZ_HD void fz_atomic_add(uint32_t *p, uint32_t v)
-{
-#if defined(__CUDA_ARCH__)
-    atomicAdd(p, v);
-#else
-    *p += v;
-#endif
-}
-
 #define FZ_BYTE_OF(v, k) (((v).w[(k) >> 2] >> (((k) & 3) * 8)) & 0xffu)
-
-struct FzHistSink {
-    static constexpr bool kOrdered = false;
-    uint32_t *hist;  // 288 counters (shared memory on the GPU)
-    FZ_HD void literal_masked(const FzVec16 &v, uint32_t mask)
-    {
-#pragma unroll
-        for (int k = 0; k < 16; k++) if ((mask >> k) & 1u) fz_atomic_add(&hist[FZ_BYTE_OF(v, k)], 1);
-    }
-    FZ_HD void literal(uint32_t c, uint32_t n) { fz_atomic_add(&hist[c], n); }
-    FZ_HD void literal16(const FzVec16 &v)
-    {
-#pragma unroll
-        for (int k = 0; k < 16; k++) fz_atomic_add(&hist[FZ_BYTE_OF(v, k)], 1);
-    }
-    FZ_HD void match(uint32_t len)
-    {
-        uint32_t lc, eb, ev;
-        fz_len_code(len, lc, eb, ev);
-        fz_atomic_add(&hist[257 + lc], 1);
-    }
-};
-
-// cl[sym] = bit-reversed code | code length << 16
-struct FzCountSink {
-    static constexpr bool kOrdered = false;
-    const uint32_t *cl;
-    uint32_t bits;
-    FZ_HD void literal_masked(const FzVec16 &v, uint32_t mask)
-    {
-        uint32_t b = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) b += ((mask >> k) & 1u) ? (cl[FZ_BYTE_OF(v, k)] >> 16) : 0u;
-        bits += b;
-    }
-    FZ_HD void literal(uint32_t c, uint32_t n) { bits += n * (cl[c] >> 16); }
-    FZ_HD void literal16(const FzVec16 &v)
-    {
-        uint32_t b = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) b += cl[FZ_BYTE_OF(v, k)] >> 16;
-        bits += b;
-    }
-    FZ_HD void match(uint32_t mlen)
-    {
-        uint32_t lc, eb, ev;
-        fz_len_code(mlen, lc, eb, ev);
-        bits += (cl[257 + lc] >> 16) + eb + 1;  // + 1-bit distance code
-    }
-};
-
-// LSB-first bit writer into 32-bit words.  The first word a lane touches and its last partial
-// word are NOT stored: they are returned for the cross-lane merge (several lanes may share a word).
-struct FzBitWriter {
-    uint32_t *out;       // word-addressed output (4-byte aligned)
-    uint64_t acc;
-    uint32_t nbits;      // valid bits in acc (< 32 between puts)
-    uint32_t widx;       // index of the word acc's low 32 bits go to
-    uint32_t first_idx, first_bits;
-    bool crossed;
-    FZ_HD void init(uint32_t *o, uint32_t bit_off)
-    {
-        out = o; acc = 0; nbits = bit_off & 31; widx = bit_off >> 5;
-        first_idx = widx; first_bits = 0; crossed = false;
-    }
-    FZ_HD void put(uint32_t v, uint32_t n)  // n <= 32
-    {
-        acc |= (uint64_t)v << nbits;
-        nbits += n;
-        if (nbits >= 32) {
-            const uint32_t w = (uint32_t)acc;
-            if (!crossed) { first_bits = w; crossed = true; } else out[widx] = w;
-            widx++; acc >>= 32; nbits -= 32;
-        }
-    }
-    FZ_HD void align_byte() { nbits = (nbits + 7) & ~7u; if (nbits >= 32) put(0, 0); }
-    FZ_HD uint32_t bitpos() const { return widx * 32 + nbits; }
-};
-
-struct FzEmitSink {
-    static constexpr bool kOrdered = true;
-    const uint32_t *cl;
-    FzBitWriter bw;
-    FZ_HD void literal_masked(const FzVec16 &, uint32_t) {}
-    FZ_HD void literal(uint32_t c, uint32_t n)
-    {
-        const uint32_t e = cl[c];
-        for (uint32_t i = 0; i < n; i++) bw.put(e & 0xffffu, e >> 16);
-    }
-    FZ_HD void literal16(const FzVec16 &v)
-    {
-        // two codes (<= 15 bits each) per append
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            const uint32_t e0 = cl[FZ_BYTE_OF(v, k)], e1 = cl[FZ_BYTE_OF(v, k + 1)];
-            const uint32_t l0 = e0 >> 16;
-            bw.put((e0 & 0xffffu) | ((e1 & 0xffffu) << l0), l0 + (e1 >> 16));
-        }
-    }
-    FZ_HD void match(uint32_t mlen)
-    {
-        uint32_t lc, eb, ev;
-        fz_len_code(mlen, lc, eb, ev);
-        const uint32_t e = cl[257 + lc];
-        bw.put(e & 0xffffu, e >> 16);
-        bw.put(ev, eb + 1);  // extra bits, then the 1-bit distance code '0' (distance 1)
-    }
-};
 
 // -------------------------------------------------------------------------------------------------
 // Huffman construction phases (literal/length alphabet).
@@ -637,24 +357,6 @@ FZ_HD void fz_ph_cost_partial(FzEncState *st, int lane)
     st->lane_bits[lane] = (uint32_t)(b >> 32);
 }
 
-// -------------------------------------------------------------------------------------------------
-// Piece geometry: lane l owns bytes [l*P, min(n, (l+1)*P)), P a multiple of 16.
-// -------------------------------------------------------------------------------------------------
-FZ_HD uint32_t fz_piece_len(uint32_t n) { return (((n + 31) / 32) + 15) & ~15u; }
-
-// histogram of one sub-block's tokens into hist[288] (must be zeroed; one warp's shared memory)
-template <class Scan>
-FZ_HD void fz_ph_hist_sc(uint32_t *hist, const Scan &scan, int lane)
-{
-    FzHistSink sink{hist};
-    scan(sink, lane);
-}
-template <class Load16, class LoadByte>
-FZ_HD void fz_ph_hist(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
-{
-    fz_ph_hist_sc(hist, FzPieceScan<Load16, LoadByte>{ld, lb, n}, lane);
-}
-
 // The code of a group as the emit kernel consumes it (global memory, copied to shared memory per warp)
 struct FzGroupCode {
     // hot part (copied to shared memory by every emitting warp): FZ_GROUP_CODE_HOT_BYTES
@@ -710,288 +412,3 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
 #endif
 }
 
-// per-warp scratch of the emit stage
-struct FzEmitState {
-    uint32_t lane_bits[32];
-    uint32_t fw_idx[32], fw_bits[32], tw_bits[32], crossed[32];
-    uint32_t total_bits;
-    uint32_t false_marker;  // the fragment contains 00 00 FF FF before its final four bytes
-    uint32_t pad[2];
-};
-
-template <class Scan>
-FZ_HD void fz_ph_count(const FzGroupCode *gc, FzEmitState *es, const Scan &scan, int lane)
-{
-    FzCountSink sink{gc->cl, 0};
-    scan(sink, lane);
-    if (lane == 0) sink.bits += gc->hdr_nbits;
-    es->lane_bits[lane] = sink.bits;
-}
-
-// emit this lane's tokens at its bit offset; lane 0 prepends the block header, lane 31 appends
-// EOB + the empty stored block (000, pad to byte, 00 00 FF FF)
-template <class Scan>
-FZ_HD void fz_ph_emit(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Scan &scan, uint32_t *out, int lane)
-{
-    uint32_t off = 0;
-    for (int l = 0; l < lane; l++) off += es->lane_bits[l];
-    FzEmitSink sink;
-    sink.cl = gc->cl;
-    sink.bw.init(out, off);
-    if (lane == 0) {
-        uint32_t nb = gc->hdr_nbits, w = 0;
-        while (nb >= 32) { sink.bw.put(hdr[w++], 32); nb -= 32; }
-        if (nb) sink.bw.put(hdr[w] & ((1u << nb) - 1), nb);
-    }
-    scan(sink, lane);
-    if (lane == 31) {
-        sink.bw.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
-        sink.bw.put(0, 3);
-        sink.bw.align_byte();
-        sink.bw.put(0x0000u, 16);
-        sink.bw.put(0xFFFFu, 16);
-        es->total_bits = sink.bw.bitpos();  // total bits of the sub-block fragment (byte aligned)
-    }
-    es->fw_idx[lane] = sink.bw.first_idx;
-    es->crossed[lane] = sink.bw.crossed ? 1u : 0u;
-    if (sink.bw.crossed) { es->fw_bits[lane] = sink.bw.first_bits; es->tw_bits[lane] = (uint32_t)sink.bw.acc; }
-    else { es->fw_bits[lane] = (uint32_t)sink.bw.acc; es->tw_bits[lane] = 0; }
-}
-
-// words shared by several lanes: the lane that completes a word ORs in what earlier lanes left there
-FZ_HD void fz_ph_merge(FzEmitState *es, uint32_t *out, int lane)
-{
-    uint32_t carry = 0;
-    for (int j = lane - 1; j >= 0; j--) {
-        if (es->crossed[j]) { carry |= es->tw_bits[j]; break; }
-        carry |= es->fw_bits[j];
-    }
-    if (es->crossed[lane]) out[es->fw_idx[lane]] = es->fw_bits[lane] | carry;
-    if (lane == 31) {
-        const uint32_t total_bits = es->total_bits;
-        if (total_bits & 31) out[total_bits >> 5] = es->crossed[31] ? es->tw_bits[31] : (es->fw_bits[31] | carry);
-    }
-}
-
-// Does the emitted fragment show the sync marker anywhere but in its last four bytes?  (About one
-// fragment in a million does; the inflater finds sub-blocks by that marker, so such a fragment is
-// emitted stored instead.)  out[] was written by this warp; volatile reads keep L1 out of the way.
-FZ_HD void fz_ph_check_marker(FzEmitState *es, const uint32_t *out, uint32_t total_bytes, int lane)
-{
-    const volatile uint32_t *o = (const volatile uint32_t *)out;
-    const uint32_t nwords = (total_bytes + 3) / 4;
-    bool hit = false;
-    for (uint32_t i = lane; i < nwords; i += 32) {
-        const uint32_t w0 = o[i];
-        const uint32_t w1 = (i + 1 < nwords) ? o[i + 1] : 0u;
-        for (uint32_t k = 0; k < 4; k++) {
-            const uint32_t v = k ? ((w0 >> (8 * k)) | (w1 << (32 - 8 * k))) : w0;
-            if (v == FZ_MARKER_LE && i * 4 + k + 4 < total_bytes) hit = true;  // position + 4 == total_bytes is the real one
-        }
-    }
-    if (hit) es->false_marker = 1;
-}
-
-// -------------------------------------------------------------------------------------------------
-// Emit one sub-block with its group's code.  Returns the fragment size in bytes, or
-// n + FZ_STORED_OVERHEAD with FZ_SIZE_STORED_FLAG set when a stored block is smaller; then nothing is
-// written to `out` (the gather kernel synthesises stored blocks from the plane bytes).
-// On the device every lane of the warp calls this with its own `lane`; on the host `lane` is unused.
-// `out` needs room for FZ_SLOT_STRIDE bytes.
-// -------------------------------------------------------------------------------------------------
-// `gc` needs only the hot part of FzGroupCode (FZ_GROUP_CODE_HOT_BYTES); `hdr` points at the group's header words.
-// `scan` is the piece scan of the sub-block (it runs twice: size, then emission).
-template <class Scan>
-FZ_HD uint32_t fz_emit_subblock_sc(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Scan &scan, uint32_t n,
-                                   uint32_t *out, int lane)
-{
-    (void)lane;
-    const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
-    if (gc->stored) return stored;
-    FZ_PHASE(fz_ph_count(gc, es, scan, lane));
-    uint32_t bits = gc->cl[FZ_EOB] >> 16;
-    for (int l = 0; l < 32; l++) bits += es->lane_bits[l];
-    // dynamic fragment = block bits + 3 (empty stored header) -> byte boundary + 4 marker bytes
-    const uint32_t dyn_bytes = (bits + 3 + 7) / 8 + 4;
-    if (dyn_bytes + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
-    FZ_PHASE(if (lane == 0) es->false_marker = 0; fz_ph_emit(gc, hdr, es, scan, out, lane));
-    FZ_PHASE(fz_ph_merge(es, out, lane));
-    FZ_PHASE(fz_ph_check_marker(es, out, es->total_bits / 8, lane));
-    if (es->false_marker) return stored;
-    return es->total_bits / 8;
-}
-
-template <class Load16, class LoadByte>
-FZ_HD uint32_t fz_emit_subblock(const FzGroupCode *gc, const uint32_t *hdr, FzEmitState *es, const Load16 &ld,
-                                const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
-{
-    return fz_emit_subblock_sc(gc, hdr, es, FzPieceScan<Load16, LoadByte>{ld, lb, n}, n, out, lane);
-}
-
-// =================================================================================================
-// Window-interleaved piece geometry (lead #1) -- NOT used by the kernels yet; checked on the CPU by
-// tests/hostmodel against zlib.
-//
-// Today lane l owns ONE contiguous 512-byte piece of the sub-block, so the bit offset of lane l + 1 is known only
-// after lane l's whole piece has been counted: fz_emit_subblock scans the sub-block twice (count, emit).  Here the
-// sub-block is cut into windows of 32 pieces of FZ_IPIECE bytes, piece p = window p / 32, lane p % 32, emitted in
-// piece order.  Inside a window the count, the warp prefix and the emission all work on the 2 KiB the warp already
-// holds in shared memory, and the only thing carried from window to window is the running bit position and the
-// partial word at its end.  The tokeniser restarts at every piece start, as it does today at the 32 piece starts;
-// tools/piece_geometry_study.py: no measurable size cost except on all-zero sub-blocks.
-// =================================================================================================
-#define FZ_IPIECE 64u
-#define FZ_IWIN (FZ_IPIECE * 32u)
-
-template <class Load16, class LoadByte>
-struct FzWindowPieceScan {
-    const Load16 &ld;
-    const LoadByte &lb;
-    uint32_t n, w;
-    template <class Sink>
-    FZ_HD void operator()(Sink &sink, int lane) const
-    {
-        const uint32_t b = w * FZ_IWIN + (uint32_t)lane * FZ_IPIECE;
-        uint32_t e = b + FZ_IPIECE;
-        if (e > n) e = n;
-        if (b < e) fz_scan_piece(ld, lb, b, e, b ? (int)lb(b - 1) : -1, sink);
-    }
-};
-
-template <class Load16, class LoadByte>
-FZ_HD void fz_ph_hist_interleaved(uint32_t *hist, const Load16 &ld, const LoadByte &lb, uint32_t n, int lane)
-{
-    for (uint32_t w = 0; w * FZ_IWIN < n; w++) fz_ph_hist_sc(hist, FzWindowPieceScan<Load16, LoadByte>{ld, lb, n, w}, lane);
-}
-
-struct FzEmitStateI {
-    FzEmitState es;        // per-window lane exchange (lane_bits, first / last word of every lane)
-    uint32_t base_bits;    // bits emitted by the windows before this one
-    uint32_t carry_in;     // what they left in the word that holds bit `base_bits` (its low base_bits & 31 bits)
-    uint32_t carry_next;
-    uint32_t pad;
-};
-
-template <class Scan>
-FZ_HD void fz_ph_count_window(const FzGroupCode *gc, FzEmitStateI *st, const Scan &scan, bool first, int lane)
-{
-    FzCountSink cs{gc->cl, 0};
-    scan(cs, lane);
-    if (first && lane == 0) cs.bits += gc->hdr_nbits;
-    st->es.lane_bits[lane] = cs.bits;
-}
-
-template <class Scan>
-FZ_HD void fz_ph_emit_window(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, const Scan &scan, bool first, bool last,
-                             uint32_t *out, int lane)
-{
-    FzEmitState *es = &st->es;
-    uint32_t off = st->base_bits;
-    for (int l = 0; l < lane; l++) off += es->lane_bits[l];
-    FzEmitSink sink;
-    sink.cl = gc->cl;
-    sink.bw.init(out, off);
-    if (first && lane == 0) {
-        uint32_t nb = gc->hdr_nbits, w = 0;
-        while (nb >= 32) { sink.bw.put(hdr[w++], 32); nb -= 32; }
-        if (nb) sink.bw.put(hdr[w] & ((1u << nb) - 1), nb);
-    }
-    scan(sink, lane);
-    if (last && lane == 31) {
-        sink.bw.put(gc->cl[FZ_EOB] & 0xffffu, gc->cl[FZ_EOB] >> 16);
-        sink.bw.put(0, 3);
-        sink.bw.align_byte();
-        sink.bw.put(0x0000u, 16);
-        sink.bw.put(0xFFFFu, 16);
-        es->total_bits = sink.bw.bitpos();
-    }
-    es->fw_idx[lane] = sink.bw.first_idx;
-    es->crossed[lane] = sink.bw.crossed ? 1u : 0u;
-    if (sink.bw.crossed) { es->fw_bits[lane] = sink.bw.first_bits; es->tw_bits[lane] = (uint32_t)sink.bw.acc; }
-    else { es->fw_bits[lane] = (uint32_t)sink.bw.acc; es->tw_bits[lane] = 0; }
-}
-
-// words shared by several lanes (and by the window before): the lane that completes a word ORs in what the others left
-FZ_HD void fz_ph_merge_window(FzEmitStateI *st, bool last, uint32_t *out, int lane)
-{
-    FzEmitState *es = &st->es;
-    uint32_t carry = 0;
-    int j = lane - 1;
-    for (; j >= 0; j--) {
-        if (es->crossed[j]) { carry |= es->tw_bits[j]; break; }
-        carry |= es->fw_bits[j];
-    }
-    if (j < 0) carry |= st->carry_in;   // nobody before this lane completed a word: the previous window's bits are still in it
-    if (es->crossed[lane]) out[es->fw_idx[lane]] = es->fw_bits[lane] | carry;
-    if (lane == 31) {
-        const uint32_t tail = es->crossed[31] ? es->tw_bits[31] : (es->fw_bits[31] | carry);
-        if (last) {
-            const uint32_t total_bits = es->total_bits;
-            if (total_bits & 31) out[total_bits >> 5] = tail;
-        } else st->carry_next = tail;
-    }
-}
-
-FZ_HD void fz_ph_advance_window(FzEmitStateI *st, int lane)
-{
-    if (lane != 0) return;
-    uint32_t b = st->base_bits;
-    for (int l = 0; l < 32; l++) b += st->es.lane_bits[l];
-    st->base_bits = b;
-    st->carry_in = st->carry_next;
-}
-
-// Emit one sub-block with its group's code, window by window.  Same contract as fz_emit_subblock_sc; the exact size
-// is known only after the emission (nothing is lost: a stored result ignores what was written to `out`).
-// `win` supplies the windows: win.enter(w, lane) / win.leave(w, lane) bracket the work on window w (the device stages
-// the 2 KiB there), win.scan(w) is the piece scan of that window.
-template <class Windows>
-FZ_HD uint32_t fz_emit_subblock_iw(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, Windows &win, uint32_t n,
-                                   uint32_t *out, int lane)
-{
-    (void)lane;
-    const uint32_t stored = fz_stored_size(n) | FZ_SIZE_STORED_FLAG;
-    if (gc->stored) return stored;
-    FZ_PHASE(if (lane == 0) { st->base_bits = 0; st->carry_in = 0; st->carry_next = 0; st->es.false_marker = 0; st->es.total_bits = 0; });
-    const uint32_t nwin = (n + FZ_IWIN - 1) / FZ_IWIN;
-    for (uint32_t w = 0; w < nwin; w++) {
-        const bool first = w == 0, last = w + 1 == nwin;
-        FZ_PHASE(win.enter(w, lane));
-        FZ_PHASE(fz_ph_count_window(gc, st, win.scan(w), first, lane));
-        {   // Stop as soon as the sub-block cannot beat a stored block any more: nothing beyond the slot is ever
-            // written (a stored block is smaller than FZ_SLOT_STRIDE), and hopeless sub-blocks cost one count.
-            // Every lane reads the same 32 counts, so the decision is uniform.  + 64 bits: end of block and marker.
-            uint32_t tot = st->base_bits;
-            for (int l = 0; l < 32; l++) tot += st->es.lane_bits[l];
-            if ((tot + 64u) / 8u + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
-        }
-        FZ_PHASE(fz_ph_emit_window(gc, hdr, st, win.scan(w), first, last, out, lane));
-        FZ_PHASE(fz_ph_merge_window(st, last, out, lane));
-        FZ_PHASE(fz_ph_advance_window(st, lane));
-        FZ_PHASE(win.leave(w, lane));
-    }
-    const uint32_t total_bytes = st->es.total_bits / 8;
-    if (total_bytes + (n >> FZ_MIN_GAIN_SHIFT) >= fz_stored_size(n)) return stored;
-    FZ_PHASE(fz_ph_check_marker(&st->es, out, total_bytes, lane));
-    if (st->es.false_marker) return stored;
-    return total_bytes;
-}
-
-// windows behind random-access loaders (the CPU model; ragged or unaligned sub-blocks on the device)
-template <class Load16, class LoadByte>
-struct FzLoaderWindows {
-    const Load16 &ld;
-    const LoadByte &lb;
-    uint32_t n;
-    FZ_HD void enter(uint32_t, int) {}
-    FZ_HD void leave(uint32_t, int) {}
-    FZ_HD FzWindowPieceScan<Load16, LoadByte> scan(uint32_t w) const { return FzWindowPieceScan<Load16, LoadByte>{ld, lb, n, w}; }
-};
-
-template <class Load16, class LoadByte>
-FZ_HD uint32_t fz_emit_subblock_interleaved(const FzGroupCode *gc, const uint32_t *hdr, FzEmitStateI *st, const Load16 &ld,
-                                            const LoadByte &lb, uint32_t n, uint32_t *out, int lane)
-{
-    FzLoaderWindows<Load16, LoadByte> win{ld, lb, n};
-    return fz_emit_subblock_iw(gc, hdr, st, win, n, out, lane);
-}

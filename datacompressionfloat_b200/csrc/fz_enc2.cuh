@@ -383,6 +383,20 @@ FZ_HD uint32_t fz_marker_in20(uint32_t prev, uint32_t x0, uint32_t x1, uint32_t 
     return ((Z & (Z >> 1) & (F >> 2) & (F >> 3)) >> 1) & 0xffffu;
 }
 
+// vector vi of a fragment (pw = the word before it): does a sync marker END inside it that is not the fragment's own last
+// four bytes?  total_bytes = 0: the fragment goes on.
+FZ_HD bool fz_marker_vec(uint32_t pw, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t vi, uint32_t total_bytes)
+{
+    uint32_t m = fz_marker_in20(pw, x0, x1, x2, x3);
+    if (m && total_bytes) {
+        // window o (1..16) starts at byte 16 vi - 4 + o; only starts below total_bytes - 4 count
+        const int64_t lim = (int64_t)total_bytes - 1 - (int64_t)vi * 16;   // number of counted windows
+        if (lim <= 0) m = 0;
+        else if (lim < 16) m &= (1u << lim) - 1u;
+    }
+    return m != 0;
+}
+
 // the ring's flush state (the same in every lane)
 struct FzRingOut {
     uint32_t *ring;
@@ -409,16 +423,7 @@ struct FzRingOut {
             }
             uint32_t pw = w.shfl_up(x3, 1);
             if (w.lane == 0) pw = tailw;
-            if (act) {
-                uint32_t m = fz_marker_in20(pw, x0, x1, x2, x3);
-                if (m && total_bytes) {
-                    // window o (1..16) starts at byte 16 vi - 4 + o; only starts below total_bytes - 4 count
-                    const int64_t lim = (int64_t)total_bytes - 1 - (int64_t)vi * 16;   // number of counted windows
-                    if (lim <= 0) m = 0;
-                    else if (lim < 16) m &= (1u << lim) - 1u;
-                }
-                if (m) bad = 1;
-            }
+            if (act && fz_marker_vec(pw, x0, x1, x2, x3, vi, total_bytes)) bad = 1;
             const uint32_t last = vend - base < 32u ? vend - base - 1u : 31u;
             tailw = w.shfl(x3, (int)last);
         }

@@ -340,12 +340,84 @@ __device__ __forceinline__ uint32_t fz_ld_u32_unaligned(const uint8_t *src, uint
     return __funnelshift_r(w0, w1, sk * 8);
 }
 
-__global__ void __launch_bounds__(FZ_SPLIT_THREADS)
-fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
-                        const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ zero_flags, FzBatchGeom g,
-                        uint32_t *__restrict__ words)
+// chunks whose reads are mostly unaligned RAW payloads (two or more RAW planes) go to the 16-words-per-thread kernel
+__device__ __forceinline__ bool fz_merge_wide(const uint32_t *__restrict__ stream_hdr, uint32_t c)
+{
+    const uint4 h = __ldg((const uint4 *)stream_hdr + c);
+    return ((h.x >> 31) + (h.y >> 31) + (h.z >> 31) + (h.w >> 31)) >= 2u;
+}
+
+// Chunks with two or more RAW planes, 16 words per thread: one 128-bit load per plane -- two and a funnel shift for a RAW payload, which
+// sits at whatever address the container gives it -- and four 128-bit stores (a quarter of a 128-byte line each: that
+// costs more than the 4-byte loads above save unless unaligned RAW payloads dominate the reads).  Same CTA shape:
+// 4096 words, a quarter of one sub-block of every plane.
+#define FZ_MERGE16_THREADS FZ_SPLIT_THREADS
+__device__ __forceinline__ void
+fz_merge_streams16(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint8_t *container_end,
+                          const uint32_t *__restrict__ stream_hdr, const unsigned long long *__restrict__ stream_off,
+                          const uint32_t *__restrict__ zero_flags, FzBatchGeom g, uint32_t *__restrict__ words)
 {
     const uint32_t c = blockIdx.y;
+    const uint32_t n_c = fz_chunk_n(g, c);
+    const uint32_t w0 = (blockIdx.x * FZ_MERGE16_THREADS + threadIdx.x) * 16u;   // first word of this thread
+    if (blockIdx.x * FZ_MERGE16_THREADS * 16u >= n_c) return;
+    const uint32_t sub = (blockIdx.x * FZ_MERGE16_THREADS * 16u) >> FZ_SUB_LOG2;
+    uint32_t h[4], zf[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        h[j] = __ldg(stream_hdr + c * 4 + j);
+        zf[j] = zero_flags ? __ldg(zero_flags + (size_t)(c * 4 + j) * g.nsub_full + sub) : 0u;
+    }
+    const uint8_t *src[4];
+    bool zero[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool raw = (h[j] & FZ_RAW_FLAG) != 0;
+        src[j] = raw ? container + stream_off[c * 4 + j] : planes + (uint64_t)j * g.plane_stride + (uint64_t)c * g.chk;
+        zero[j] = zf[j] != 0 && !raw;
+    }
+    uint32_t *out = words + (uint64_t)c * g.chk;
+    if (w0 + 16u <= n_c) {
+        uint4 p[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (zero[j]) { p[j] = make_uint4(0, 0, 0, 0); continue; }
+            const uint8_t *a = src[j] + w0;
+            const uint32_t sh = (uint32_t)((uintptr_t)a & 15u);
+            if (sh == 0) p[j] = fz_ld_stream((const uint4 *)a);
+            else {
+                const uint4 *a0 = (const uint4 *)(a - sh);
+                const uint4 A = __ldg(a0);
+                const uint4 B = ((const uint8_t *)(a0 + 1) < container_end) ? __ldg(a0 + 1) : A;
+                p[j] = fz_funnel16(A, B, sh);
+            }
+        }
+        uint4 w;
+        uint4 *o4 = (uint4 *)(out + w0);
+        fz_transpose4(p[0].x, p[1].x, p[2].x, p[3].x, w.x, w.y, w.z, w.w); o4[0] = w;
+        fz_transpose4(p[0].y, p[1].y, p[2].y, p[3].y, w.x, w.y, w.z, w.w); o4[1] = w;
+        fz_transpose4(p[0].z, p[1].z, p[2].z, p[3].z, w.x, w.y, w.z, w.w); o4[2] = w;
+        fz_transpose4(p[0].w, p[1].w, p[2].w, p[3].w, w.x, w.y, w.z, w.w); o4[3] = w;
+    } else {
+        for (uint32_t i = w0; i < n_c; i++) {   // the ragged end of a chunk
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) w |= (zero[j] ? 0u : (uint32_t)src[j][i]) << (8 * j);
+            out[i] = w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FZ_SPLIT_THREADS, 8)
+fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
+                        const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ zero_flags, FzBatchGeom g,
+                        uint32_t *__restrict__ words, bool wide_split, const uint8_t *container_end)
+{
+    const uint32_t c = blockIdx.y;
+    if (wide_split && fz_merge_wide(stream_hdr, c)) {
+        fz_merge_streams16(planes, container, container_end, stream_hdr, stream_off, zero_flags, g, words);
+        return;
+    }
     const uint32_t n_c = fz_chunk_n(g, c);
     const uint32_t nvec = n_c / 4;
     const uint8_t *src[4];
@@ -402,13 +474,25 @@ fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__res
     }
 }
 
-void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, const uint32_t *stream_hdr,
+void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, uint64_t container_size, const uint32_t *stream_hdr,
                              const unsigned long long *stream_off, const uint32_t *zero_flags, FzBatchGeom g, uint32_t *words,
                              cudaStream_t st)
 {
-    const uint32_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
-    dim3 grid((g.chk / 4 + per - 1) / per, g.nchunks);
-    fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words);
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MRCZIP_MERGE"); v = (e && atoi(e) == 1) ? 1 : 2; }   // 1: the 4-bytes-per-plane kernel (A/B runs)
+    if (v == 1) {
+        const uint32_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
+        dim3 grid((g.chk / 4 + per - 1) / per, g.nchunks);
+        fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words, false, container + container_size);
+        return;
+    }
+    // one launch: a CTA of a chunk with two or more RAW planes takes the 16-words-per-thread path, the others the
+    // 4-bytes-per-plane one (measured per 4 GiB: G b=0, three RAW planes, 1.92 -> 1.70 ms with the first; P b=0, two
+    // all-zero planes, 0.99 -> 1.32 ms: hence the split; two launches that each skip the other's chunks cost 0.15 ms more)
+    const uint32_t per4 = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
+    dim3 grid4((g.chk / 4 + per4 - 1) / per4, g.nchunks);
+    fz_merge_streams_kernel<<<grid4, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words, true,
+                                                                container + container_size);
 }
 
 // =================================================================================================
@@ -420,22 +504,6 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, co
 #ifndef FZ_ENC_WARPS
 #define FZ_ENC_WARPS 4
 #endif
-// ---- how a warp reads its sub-block --------------------------------------------------------------------------
-// Lane l tokenises the contiguous piece [l*512, (l+1)*512) of the 16 KiB sub-block.  The pieces stream through a
-// two-stage shared-memory window of 64 bytes per lane: cp.async (16 B per lane and instruction, four per window,
-// arranged so that one instruction covers 8 pieces x 64 contiguous bytes = whole 32-byte sectors) fills stage
-// (w+1)&1 while the lanes tokenise window w out of stage w&1.  Rows are 80 bytes apart, which makes the per-lane
-// 128-bit reads bank-conflict free.  5 KB per warp instead of the 17 KB a fully staged sub-block took: 32 warps per
-// SM instead of 12, and no exposed load latency.
-#ifndef FZ_WIN_BYTES
-#define FZ_WIN_BYTES 64
-#endif
-#define FZ_WIN_C (FZ_WIN_BYTES / 16)     // 16-byte chunks per lane and window = cp.async instructions per window
-#define FZ_WIN_ROW (FZ_WIN_BYTES + 16)
-#define FZ_WIN_STAGE (FZ_WARP * FZ_WIN_ROW)
-#define FZ_WIN_SMEM (2 * FZ_WIN_STAGE)
-#define FZ_PIECE (FZ_SUB / FZ_WARP)
-
 __device__ __forceinline__ void fz_cp_async16(uint32_t smem_addr, const void *gptr)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -443,49 +511,6 @@ __device__ __forceinline__ void fz_cp_async16(uint32_t smem_addr, const void *gp
 __device__ __forceinline__ void fz_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void fz_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// piece scan of a full, 16-byte aligned sub-block (all 32 lanes must call it: it synchronises the warp)
-struct FzWindowScan {
-    uint8_t *win;        // this warp's FZ_WIN_SMEM bytes
-    const uint8_t *src;  // FZ_SUB bytes
-    template <class Sink>
-    __device__ __forceinline__ void operator()(Sink &sink, int lane) const
-    {
-        const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win);
-        const uint32_t part = (uint32_t)lane % FZ_WIN_C, prow = (uint32_t)lane / FZ_WIN_C;
-        const uint8_t *gsrc = src + prow * FZ_PIECE + part * 16;
-        const uint32_t sdst = wbase + prow * FZ_WIN_ROW + part * 16;
-        // window w -> stage w & 1
-#define FZ_WIN_ISSUE(w)                                                                                              \
-        do {                                                                                                         \
-            const uint32_t st_ = sdst + ((w) & 1u) * FZ_WIN_STAGE;                                                   \
-            const uint8_t *g_ = gsrc + (w) * FZ_WIN_BYTES;                                                           \
-            _Pragma("unroll") for (int q_ = 0; q_ < FZ_WIN_C; q_++)                                                  \
-                fz_cp_async16(st_ + q_ * (32 / FZ_WIN_C) * FZ_WIN_ROW, g_ + q_ * (32 / FZ_WIN_C) * FZ_PIECE);        \
-            fz_cp_async_commit();                                                                                    \
-        } while (0)
-        FZ_WIN_ISSUE(0u);
-        FzScan sc;
-        sc.init(lane ? (int)src[lane * FZ_PIECE - 1] : -1);
-#pragma unroll 1
-        for (uint32_t w = 0; w < FZ_PIECE / FZ_WIN_BYTES; w++) {
-            if (w + 1 < FZ_PIECE / FZ_WIN_BYTES) { FZ_WIN_ISSUE(w + 1); fz_cp_async_wait<1>(); }
-            else fz_cp_async_wait<0>();
-            __syncwarp();
-            const uint8_t *row = win + (w & 1u) * FZ_WIN_STAGE + lane * FZ_WIN_ROW;
-#pragma unroll 1
-            for (uint32_t q = 0; q < FZ_WIN_BYTES / 16; q++) {
-                const uint4 v = *(const uint4 *)(row + q * 16);
-                FzVec16 r;
-                r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-                sc.group16(r, sink);
-            }
-            __syncwarp();   // everyone is done with this stage before window w + 2 lands in it
-        }
-#undef FZ_WIN_ISSUE
-        sc.finish(sink);
-    }
-};
 
 // ragged (last sub-block of a file) or unaligned (chunk sizes that are not a multiple of 16) sub-blocks: straight
 // from global memory, no staging -- rare, small, and not worth shared memory that would cost the fast path occupancy
@@ -506,70 +531,9 @@ struct GlobLoad16 {
         return r;
     }
 };
-struct GlobLoadByte {
-    const uint8_t *src;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return src[i]; }
-};
 struct ZeroLoad16 {
     __device__ __forceinline__ FzVec16 operator()(uint32_t) const { FzVec16 r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0; return r; }
 };
-struct ZeroLoadByte {
-    __device__ __forceinline__ uint32_t operator()(uint32_t) const { return 0; }
-};
-
-#ifdef FZ_INTERLEAVED_PIECES
-// EXPERIMENTAL (lead #1; off by default, never run on a GPU yet): the window-interleaved piece geometry of
-// fz_emit_subblock_iw on the device.  Window w is the 2 KiB [w * 2048, (w + 1) * 2048) of the sub-block, lane l owns its
-// bytes [l * 64, l * 64 + 64): the cp.async fill is plainly coalesced, the rows are the same 80-byte pitch.
-static_assert(FZ_WIN_BYTES == FZ_IPIECE, "the interleaved geometry uses one window row per piece");
-struct FzDevWinScan {
-    const uint8_t *row;   // this lane's 64 bytes
-    int prev;             // the byte before them, -1 at the start of the sub-block
-    template <class Sink>
-    __device__ __forceinline__ void operator()(Sink &sink, int) const
-    {
-        FzScan sc;
-        sc.init(prev);
-#pragma unroll 1
-        for (uint32_t q = 0; q < FZ_IPIECE / 16; q++) {
-            const uint4 v = *(const uint4 *)(row + q * 16);
-            FzVec16 r;
-            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-            sc.group16(r, sink);
-        }
-        sc.finish(sink);
-    }
-};
-struct FzDevWindows {
-    uint8_t *win;         // this warp's FZ_WIN_SMEM bytes (two stages)
-    const uint8_t *src;   // FZ_SUB bytes, 16-byte aligned
-    int prev0;            // last byte of the window before (lane 0's predecessor)
-    int lane_;
-    __device__ __forceinline__ void issue(uint32_t w) const
-    {
-        const uint32_t st = (uint32_t)__cvta_generic_to_shared(win) + (w & 1u) * FZ_WIN_STAGE;
-#pragma unroll
-        for (uint32_t q = 0; q < FZ_IWIN / (16 * FZ_WARP); q++) {
-            const uint32_t c = (uint32_t)lane_ + FZ_WARP * q;   // 16-byte chunk of the window
-            fz_cp_async16(st + (c >> 2) * FZ_WIN_ROW + (c & 3u) * 16u, src + w * FZ_IWIN + c * 16u);
-        }
-        fz_cp_async_commit();
-    }
-    __device__ __forceinline__ void enter(uint32_t w, int)
-    {
-        if (w == 0) issue(0);
-        if (w + 1 < FZ_SUB / FZ_IWIN) { issue(w + 1); fz_cp_async_wait<1>(); }
-        else fz_cp_async_wait<0>();
-        // (the caller's FZ_PHASE synchronises the warp: every lane's copies have landed)
-    }
-    __device__ __forceinline__ const uint8_t *row(uint32_t w, int l) const { return win + (w & 1u) * FZ_WIN_STAGE + l * FZ_WIN_ROW; }
-    __device__ __forceinline__ void leave(uint32_t w, int) { prev0 = (int)row(w, FZ_WARP - 1)[FZ_IPIECE - 1]; }
-    __device__ __forceinline__ FzDevWinScan scan(uint32_t w) const
-    {
-        return FzDevWinScan{row(w, lane_), lane_ ? (int)row(w, lane_ - 1)[FZ_IPIECE - 1] : (w ? prev0 : -1)};
-    }
-};
-#endif
 
 __device__ __forceinline__ const uint8_t *fz_sub_src(const uint8_t *planes, const FzBatchGeom &g, uint32_t s, uint32_t k)
 {
@@ -595,11 +559,6 @@ __device__ __forceinline__ uint32_t fz_groups_per_stream(const FzBatchGeom &g)
     return (g.nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS;
 }
 
-struct __align__(16) FzHistSmem {
-    alignas(16) uint8_t win[FZ_WIN_SMEM];
-    uint32_t hist[288];
-};
-
 // Sub-blocks whose byte distribution is (nearly) flat cannot be entropy coded: a 2 KiB sample (the first 64
 // bytes of every lane piece) decides that before the 16 KiB are even read.  The plug-in entropy of 2048
 // samples of uniform bytes is about 7.91 bits (bias -255 / (2 N ln 2)); anything above FZ_SAMPLE_BITS is
@@ -607,126 +566,6 @@ struct __align__(16) FzHistSmem {
 #ifndef FZ_SAMPLE_BITS
 #define FZ_SAMPLE_BITS 7.85f
 #endif
-
-__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
-fz_hist_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, uint32_t *__restrict__ ghist, uint32_t *__restrict__ sizes,
-               const uint32_t *__restrict__ zero_hist, uint32_t zero_planes, uint64_t zero_from, FzStatus *status)
-{
-    extern __shared__ __align__(16) uint8_t fz_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
-    if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
-    uint32_t s, k, n;
-    if (!fz_slot(g, t, s, k, n)) return;
-    FzHistSmem *sm = (FzHistSmem *)fz_smem + warp;
-    const uint8_t *src = fz_sub_src(planes, g, s, k);
-    if (n == FZ_SUB && ((zero_planes >> (s & 3u)) & 1u) && (uint64_t)(s >> 2) * g.chk + (uint64_t)k * FZ_SUB >= zero_from) {
-        // the mask erases this whole byte plane (8 or more bits erased) and the sub-block lies behind the exempt
-        // header words: 16 KiB of zeros, known without reading them
-        if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
-        uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
-        for (int i = lane; i < 288; i += 32) {
-            const uint32_t v = zero_hist[i];
-            if (v) atomicAdd(gh + i, v);
-        }
-        return;
-    }
-    for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
-    __syncwarp();
-    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
-        // ---- sample pass
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint4 v = *(const uint4 *)(src + lane * (FZ_SUB / 32) + 16 * q);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int b = 0; b < 16; b++) atomicAdd(&sm->hist[(w[b >> 2] >> ((b & 3) * 8)) & 0xffu], 1u);
-        }
-        __syncwarp();
-        float acc = 0.f;
-        for (int i = lane; i < 256; i += 32) {
-            const float f = (float)sm->hist[i];
-            if (f > 0.f) acc += f * __log2f(f);
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        const float bits = 11.f - acc * (1.f / 2048.f);  // log2(2048) - sum f log2 f / N
-        if (bits > FZ_SAMPLE_BITS) {
-            if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
-            return;
-        }
-        if (sm->hist[0] == 2048u) {
-            // The sample is all zeros: mask bits >= 8 zero whole byte planes, so most likely the sub-block is.  One OR
-            // over its 16 KiB settles it; then its tokens are known without scanning (the same for every such
-            // sub-block: zero_hist, made once by fz_zero_hist_kernel with this very tokeniser), and the emit kernel
-            // encodes only the first zero sub-block of each group -- the others are copies of its fragment.
-            uint32_t any = 0;
-#pragma unroll 4
-            for (uint32_t i = lane * 16; i < FZ_SUB; i += FZ_WARP * 16) {
-                const uint4 v = *(const uint4 *)(src + i);
-                any |= v.x | v.y | v.z | v.w;
-            }
-            if (!__any_sync(0xffffffffu, any != 0)) {
-                if (lane == 0) sizes[t] = FZ_SIZE_ZERO_FLAG;
-                uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
-                for (int i = lane; i < 288; i += 32) {
-                    const uint32_t v = zero_hist[i];
-                    if (v) atomicAdd(gh + i, v);
-                }
-                return;
-            }
-        }
-        __syncwarp();
-        for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
-        __syncwarp();
-    }
-    if (lane == 0) sizes[t] = 0;  // to be decided by the emit kernel
-#ifdef FZ_INTERLEAVED_PIECES
-    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
-        FzDevWindows win{sm->win, src, -1, lane};
-        for (uint32_t w = 0; w < FZ_SUB / FZ_IWIN; w++) {
-            win.enter(w, lane);
-            __syncwarp();
-            fz_ph_hist_sc(sm->hist, win.scan(w), lane);
-            __syncwarp();
-            win.leave(w, lane);
-            __syncwarp();
-        }
-    } else {
-        GlobLoad16 ld{src};
-        GlobLoadByte lb{src};
-        fz_ph_hist_interleaved(sm->hist, ld, lb, n, lane);
-    }
-#else
-    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
-        fz_ph_hist_sc(sm->hist, FzWindowScan{sm->win, src}, lane);
-    } else {
-        GlobLoad16 ld{src};
-        GlobLoadByte lb{src};
-        fz_ph_hist(sm->hist, ld, lb, n, lane);
-    }
-#endif
-    __syncwarp();
-    uint32_t *gh = ghist + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS) * 288;
-    for (int i = lane; i < 288; i += 32) {
-        const uint32_t v = sm->hist[i];
-        if (v) atomicAdd(gh + i, v);
-    }
-}
-
-// token histogram of a sub-block of FZ_SUB zero bytes, by the tokeniser itself (one warp, once per context)
-__global__ void __launch_bounds__(FZ_WARP)
-fz_zero_hist_kernel(uint32_t *__restrict__ zero_hist)
-{
-    extern __shared__ __align__(16) uint8_t fz_smem[];
-    const int lane = threadIdx.x;
-    FzHistSmem *sm = (FzHistSmem *)fz_smem;
-    for (int i = lane; i < 288; i += 32) sm->hist[i] = 0;
-    __syncwarp();
-    fz_ph_hist(sm->hist, ZeroLoad16{}, ZeroLoadByte{}, FZ_SUB, lane);
-    __syncwarp();
-    for (int i = lane; i < 288; i += 32) zero_hist[i] = sm->hist[i];
-}
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
 fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupCode *__restrict__ gcodes)
@@ -763,82 +602,8 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
     fz_build_group_code(st, gn, nsub, gcodes + gi, lane);
 }
 
-struct __align__(16) FzEmitSmem {
-    alignas(16) uint8_t win[FZ_WIN_SMEM];
-    uint32_t gc_hot[FZ_GROUP_CODE_HOT_BYTES / 4];  // the hot part of the group's FzGroupCode
-#ifdef FZ_INTERLEAVED_PIECES
-    FzEmitStateI esi;
-#define FZ_EMIT_ES(sm_) (&(sm_)->esi.es)
-#else
-    FzEmitState es;
-#define FZ_EMIT_ES(sm_) (&(sm_)->es)
-#endif
-};
-
-__global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
-fz_emit_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroupCode *__restrict__ gcodes,
-               uint8_t *__restrict__ scratch, uint32_t *__restrict__ sizes, FzStatus *status)
-{
-    extern __shared__ __align__(16) uint8_t fz_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * FZ_ENC_WARPS + warp;
-    if (t >= g.nchunks * FZ_PLANES * g.nsub_full) return;
-    uint32_t s, k, n;
-    if (!fz_slot(g, t, s, k, n)) return;
-    const uint32_t sz0 = sizes[t];
-    if (sz0 & FZ_SIZE_STORED_FLAG) return;  // the histogram kernel already ruled this sub-block incompressible
-    const FzGroupCode *ggc = gcodes + ((uint64_t)s * fz_groups_per_stream(g) + k / FZ_CODE_SUBS);
-    if (ggc->stored) {  // the whole group cannot beat stored blocks: nothing to stage or emit
-        if (lane == 0) { sizes[t] = fz_stored_size(n) | FZ_SIZE_STORED_FLAG; atomicAdd(&status->n_stored_sub, 1u); }
-        return;
-    }
-    if (sz0 & FZ_SIZE_ZERO_FLAG) {
-        // all-zero sub-blocks of a group are the same bytes coded with the same code: only the first one is encoded,
-        // the layout kernel gives the others its size and the gather kernel copies its fragment (bit 30 of a size
-        // word never changes while this kernel runs, so every warp sees the same leader)
-        const uint32_t kb = k & ~(uint32_t)(FZ_GROUP_SUBS - 1);
-        const uint32_t other = (kb + lane < g.nsub_full) ? sizes[t - (k - kb) + lane] : 0u;
-        const uint32_t zmask = __ballot_sync(0xffffffffu, (other & FZ_SIZE_ZERO_FLAG) != 0);
-        if ((uint32_t)(__ffs((int)zmask) - 1) != k - kb) return;
-    }
-    FzEmitSmem *sm = (FzEmitSmem *)fz_smem + warp;
-    {   // code table of the group -> shared memory (word copy of the hot part)
-        const uint32_t *src = (const uint32_t *)ggc;
-        for (uint32_t i = lane; i < FZ_GROUP_CODE_HOT_BYTES / 4; i += 32) sm->gc_hot[i] = src[i];
-    }
-    __syncwarp();
-    const uint8_t *src = fz_sub_src(planes, g, s, k);
-    uint32_t *out = (uint32_t *)(scratch + (uint64_t)t * FZ_SLOT_STRIDE);
-    uint32_t r;
-#ifdef FZ_INTERLEAVED_PIECES
-    if (sz0 & FZ_SIZE_ZERO_FLAG) {   // the leader of the group's all-zero sub-blocks: contiguous pieces, like fz_zero_hist_kernel
-        r = fz_emit_subblock_sc((const FzGroupCode *)sm->gc_hot, ggc->hdr, FZ_EMIT_ES(sm), FzWindowScan{sm->win, src}, n, out, lane);
-    } else if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
-        FzDevWindows win{sm->win, src, -1, lane};
-        r = fz_emit_subblock_iw((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->esi, win, n, out, lane);
-    } else {
-        GlobLoad16 ld{src};
-        GlobLoadByte lb{src};
-        r = fz_emit_subblock_interleaved((const FzGroupCode *)sm->gc_hot, ggc->hdr, &sm->esi, ld, lb, n, out, lane);
-    }
-#else
-    if (n == FZ_SUB && ((uintptr_t)src & 15u) == 0) {
-        r = fz_emit_subblock_sc((const FzGroupCode *)sm->gc_hot, ggc->hdr, FZ_EMIT_ES(sm), FzWindowScan{sm->win, src}, n, out, lane);
-    } else {
-        GlobLoad16 ld{src};
-        GlobLoadByte lb{src};
-        r = fz_emit_subblock((const FzGroupCode *)sm->gc_hot, ggc->hdr, FZ_EMIT_ES(sm), ld, lb, n, out, lane);
-    }
-#endif
-    if (lane == 0) {
-        sizes[t] = r | (sz0 & FZ_SIZE_ZERO_FLAG);
-        if (r & FZ_SIZE_STORED_FLAG) atomicAdd(&status->n_stored_sub, 1u);
-    }
-}
-
-
 // =================================================================================================
-// encoder v2 (fz_enc2.cuh): warp-interleaved steps, one pass, coalesced loads and stores
+// histogram and emission (fz_enc2.cuh): warp-interleaved steps, one pass, coalesced loads and stores
 // =================================================================================================
 struct GlobVec16 {   // 16-byte aligned source: one streaming 128-bit load per lane, 512 contiguous bytes per warp
     const uint8_t *src;
@@ -1038,23 +803,9 @@ fz_emit2_kernel(const uint8_t *__restrict__ planes, FzBatchGeom g, const FzGroup
     }
 }
 
-size_t fz_encode_smem_bytes() { return sizeof(FzEmitSmem) * FZ_ENC_WARPS; }
-
-static int fz_encoder_version()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("MRCZIP_ENCODER");   // 1: the first (piece-per-lane, two-pass) encoder, kept for A/B runs
-        v = (e && atoi(e) == 1) ? 1 : 2;
-    }
-    return v;
-}
-
 void fz_launch_zero_hist(uint32_t *zero_hist, cudaStream_t st)
 {
-    if (fz_encoder_version() == 2) { fz_zero_hist2_kernel<<<1, FZ_WARP, 0, st>>>(zero_hist); return; }
-    cudaFuncSetAttribute(fz_zero_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzHistSmem));
-    fz_zero_hist_kernel<<<1, FZ_WARP, sizeof(FzHistSmem), st>>>(zero_hist);
+    fz_zero_hist2_kernel<<<1, FZ_WARP, 0, st>>>(zero_hist);
 }
 
 void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, void *gcodes, uint8_t *scratch, uint32_t *sizes,
@@ -1067,22 +818,10 @@ void fz_launch_encode(const uint8_t *planes, FzBatchGeom g, uint32_t *ghist, voi
     const unsigned grid = (total + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS;
     cudaFuncSetAttribute(fz_group_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEncState) * FZ_ENC_WARPS));
     cudaMemsetAsync(ghist, 0, (size_t)ngroups * 288 * sizeof(uint32_t), st);
-    if (fz_encoder_version() == 2) {
-        fz_hist2_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, 0, st>>>(planes, g, ghist, sizes, zero_hist, zero_planes, zero_from, status);
-        fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
-            ghist, g, (FzGroupCode *)gcodes);
-        fz_emit2_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, 0, st>>>(planes, g, (const FzGroupCode *)gcodes, scratch, sizes, status);
-        return;
-    }
-    cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzHistSmem) * FZ_ENC_WARPS));
-    cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FzEmitSmem) * FZ_ENC_WARPS));
-    cudaFuncSetAttribute(fz_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fz_emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    fz_hist_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzHistSmem) * FZ_ENC_WARPS, st>>>(planes, g, ghist, sizes, zero_hist, zero_planes, zero_from, status);
+    fz_hist2_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, 0, st>>>(planes, g, ghist, sizes, zero_hist, zero_planes, zero_from, status);
     fz_group_code_kernel<<<(ngroups + FZ_ENC_WARPS - 1) / FZ_ENC_WARPS, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEncState) * FZ_ENC_WARPS, st>>>(
         ghist, g, (FzGroupCode *)gcodes);
-    fz_emit_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, sizeof(FzEmitSmem) * FZ_ENC_WARPS, st>>>(planes, g, (const FzGroupCode *)gcodes,
-                                                                                          scratch, sizes, status);
+    fz_emit2_kernel<<<grid, FZ_ENC_WARPS * FZ_WARP, 0, st>>>(planes, g, (const FzGroupCode *)gcodes, scratch, sizes, status);
 }
 
 size_t fz_group_code_bytes() { return sizeof(FzGroupCode); }
@@ -1389,147 +1128,104 @@ __device__ __forceinline__ uint32_t fz_marker_mask(const uint8_t *base, uint32_t
     return m;
 }
 
-template <bool WRITE>
+// One pass.  Block b scans tile b % tiles_per_stream of stream b / tiles_per_stream: the 16 slices' hit masks stay in
+// registers, the tile's count is published, the counts of the tiles before it IN THE SAME STREAM are collected by a
+// decoupled look-back (tile_state: flag << 30 | value; 1 = this tile's count, 2 = inclusive prefix), and the hits go
+// straight to their place
+// hits[s * hits_per_stream + rank].  stream_cnt[s] = markers of the whole stream.
+#define FZ_TILE_SLICES (FZ_TILE_BYTES / FZ_SLICE_BYTES)
 __global__ void __launch_bounds__(FZ_SCAN_THREADS)
 fz_marker_kernel(const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
-                 const unsigned long long *__restrict__ stream_off, uint32_t tiles_per_stream, uint32_t *__restrict__ tile_cnt,
-                 uint32_t *__restrict__ hits, uint32_t hits_cap, const FzStatus *status)
+                 const unsigned long long *__restrict__ stream_off, uint32_t tiles_per_stream, uint32_t *__restrict__ tile_state,
+                 uint32_t *__restrict__ stream_cnt, uint32_t *__restrict__ hits, uint32_t hits_per_stream, const FzStatus *status)
 {
     __shared__ uint32_t wsum[FZ_SCAN_THREADS / 32];
-    const uint32_t b = blockIdx.x;
-    if (status->error) {  // a broken chunk chain leaves the stream table undefined: touch nothing
-        if (!WRITE && threadIdx.x == 0) tile_cnt[b] = 0;
+    __shared__ uint32_t excl_sh;
+    // tiles are handed out in the order the blocks START (a ticket), not by blockIdx: a tile then only ever waits for
+    // tiles whose blocks are already running, whatever order the hardware dispatches blocks in
+    if (threadIdx.x == 0) excl_sh = atomicAdd(tile_state + (size_t)gridDim.x, 1u);
+    __syncthreads();
+    const uint32_t b = excl_sh;
+    __syncthreads();
+    const uint32_t s = b / tiles_per_stream, tile = b - s * tiles_per_stream;
+    if (status->error) {  // a broken chunk chain leaves the stream table undefined: touch nothing else
+        if (tile == 0 && threadIdx.x == 0) stream_cnt[s] = 0;
         return;
     }
-    const uint32_t s = b / tiles_per_stream, tile = b - s * tiles_per_stream;
     const uint32_t h = stream_hdr[s];
     const uint32_t len = h & ~FZ_RAW_FLAG;
     const bool skip = (h & FZ_RAW_FLAG) || (uint64_t)tile * FZ_TILE_BYTES + 4 > len;
-    uint32_t out_base = 0;
-    if (WRITE) {
-        out_base = tile_cnt[b];
-        if (skip || tile_cnt[b + 1] == out_base) return;
-    } else if (skip) {
-        if (threadIdx.x == 0) tile_cnt[b] = 0;
+    if (skip) {   // (tiles behind a skipped one are skipped too: nobody looks back at it)
+        if (tile == 0 && threadIdx.x == 0) stream_cnt[s] = 0;
         return;
     }
+    const bool last_tile = tile + 1 == tiles_per_stream || (uint64_t)(tile + 1) * FZ_TILE_BYTES + 4 > len;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *base = container + stream_off[s];
-    uint32_t acc = 0;  // markers found in the earlier slices of this tile
-    for (uint32_t slice = 0; slice < FZ_TILE_BYTES / FZ_SLICE_BYTES; slice++) {
-        const uint32_t q0 = tile * FZ_TILE_BYTES + slice * FZ_SLICE_BYTES;
-        if ((uint64_t)q0 + 4 > len) break;  // block-uniform
-        const uint32_t p0 = q0 + threadIdx.x * 16;
-        const uint32_t m = fz_marker_mask(base, len, p0);
-        const uint32_t cnt = __popc(m);
-        const uint32_t inc = fz_warp_incl_scan(cnt, lane);
-        __syncthreads();
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        uint32_t wbase = 0, total = 0;
+    uint32_t mk[FZ_TILE_SLICES / 2], rk[FZ_TILE_SLICES / 2];   // per slice: hit mask, rank inside the tile (16 bits each)
 #pragma unroll
-        for (int w = 0; w < FZ_SCAN_THREADS / 32; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
-        if (WRITE) {
-            uint32_t o = out_base + acc + wbase + inc - cnt;
-            uint32_t mm = m;
+    for (int i = 0; i < FZ_TILE_SLICES / 2; i++) { mk[i] = 0; rk[i] = 0; }
+    uint32_t acc = 0;  // markers found in the earlier slices of this tile
+#pragma unroll
+    for (uint32_t slice = 0; slice < FZ_TILE_SLICES; slice++) {
+        const uint32_t q0 = tile * FZ_TILE_BYTES + slice * FZ_SLICE_BYTES;
+        if ((uint64_t)q0 + 4 <= len) {   // block-uniform
+            const uint32_t m = fz_marker_mask(base, len, q0 + threadIdx.x * 16);
+            const uint32_t cnt = __popc(m);
+            if (__syncthreads_or(cnt != 0)) {   // (a slice of compressed bytes holds a marker about once in three)
+                const uint32_t inc = fz_warp_incl_scan(cnt, lane);
+                if (lane == 31) wsum[warp] = inc;
+                __syncthreads();
+                uint32_t wbase = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < FZ_SCAN_THREADS / 32; w++) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+                mk[slice >> 1] |= m << (16 * (slice & 1));
+                rk[slice >> 1] |= ((acc + wbase + inc - cnt) & 0xffffu) << (16 * (slice & 1));
+                acc += total;
+                __syncthreads();
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        volatile uint32_t *st = tile_state + (size_t)s * tiles_per_stream;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            st[tile] = (1u << 30) | acc;
+            __threadfence();
+            for (int t = (int)tile - 1; t >= 0; t--) {
+                uint32_t v;
+                do { v = st[t]; } while ((v >> 30) == 0);
+                excl += v & 0x3fffffffu;
+                if ((v >> 30) == 2u) break;
+            }
+        }
+        st[tile] = (2u << 30) | (excl + acc);
+        __threadfence();
+        excl_sh = excl;
+        if (last_tile) stream_cnt[s] = excl + acc;
+    }
+    __syncthreads();
+    const uint32_t excl = excl_sh;
+    uint32_t *hout = hits + (size_t)s * hits_per_stream;
+#pragma unroll
+    for (uint32_t slice = 0; slice < FZ_TILE_SLICES; slice++) {
+        uint32_t mm = (mk[slice >> 1] >> (16 * (slice & 1))) & 0xffffu;
+        if (mm) {
+            uint32_t o = excl + ((rk[slice >> 1] >> (16 * (slice & 1))) & 0xffffu);
+            const uint32_t p0 = tile * FZ_TILE_BYTES + slice * FZ_SLICE_BYTES + threadIdx.x * 16;
             while (mm) {
                 const int bit = __ffs((int)mm) - 1;
                 mm &= mm - 1;
-                if (o < hits_cap) hits[o] = p0 + (uint32_t)bit;
+                if (o < hits_per_stream) hout[o] = p0 + (uint32_t)bit;
                 o++;
             }
         }
-        acc += total;
     }
-    if (!WRITE && threadIdx.x == 0) tile_cnt[b] = acc;
-}
-
-// ---- exclusive scan of a uint32 array (n elements, writes n + 1: the last is the total)
-#define FZ_XS_THREADS 256
-#define FZ_XS_ITEMS 16
-#define FZ_XS_TILE (FZ_XS_THREADS * FZ_XS_ITEMS)
-
-__global__ void __launch_bounds__(FZ_XS_THREADS)
-fz_xscan_reduce_kernel(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ bsum)
-{
-    __shared__ uint32_t wsum[FZ_XS_THREADS / 32];
-    const uint32_t base = blockIdx.x * FZ_XS_TILE + threadIdx.x * FZ_XS_ITEMS;
-    uint32_t v = 0;
-#pragma unroll
-    for (int i = 0; i < FZ_XS_ITEMS; i++) if (base + i < n) v += a[base + i];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < FZ_XS_THREADS / 32; w++) t += wsum[w];
-        bsum[blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(1024) fz_xscan_top_kernel(uint32_t *__restrict__ bsum, uint32_t nb)
-{
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry_sh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_sh = 0;
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < nb; i0 += 1024) {
-        const uint32_t i = i0 + threadIdx.x;
-        const uint32_t v = i < nb ? bsum[i] : 0u;
-        const uint32_t inc = fz_warp_incl_scan(v, lane);
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t ws = wsum[lane];
-            const uint32_t wi = fz_warp_incl_scan(ws, lane);
-            wsum[lane] = wi - ws;
-        }
-        __syncthreads();
-        const uint32_t carry = carry_sh;
-        const uint32_t ex = carry + wsum[warp] + inc - v;
-        if (i < nb) bsum[i] = ex;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_sh = ex + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) bsum[nb] = carry_sh;
-}
-
-__global__ void __launch_bounds__(FZ_XS_THREADS)
-fz_xscan_apply_kernel(uint32_t *__restrict__ a, uint32_t n, const uint32_t *__restrict__ bsum, uint32_t nb)
-{
-    __shared__ uint32_t wsum[FZ_XS_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t base = blockIdx.x * FZ_XS_TILE + threadIdx.x * FZ_XS_ITEMS;
-    uint32_t x[FZ_XS_ITEMS];
-    uint32_t v = 0;
-#pragma unroll
-    for (int i = 0; i < FZ_XS_ITEMS; i++) { x[i] = base + i < n ? a[base + i] : 0u; v += x[i]; }
-    const uint32_t inc = fz_warp_incl_scan(v, lane);
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wbase = 0;
-#pragma unroll
-    for (int w = 0; w < FZ_XS_THREADS / 32; w++) if (w < warp) wbase += wsum[w];
-    uint32_t run = bsum[blockIdx.x] + wbase + inc - v;
-#pragma unroll
-    for (int i = 0; i < FZ_XS_ITEMS; i++) { if (base + i < n) a[base + i] = run; run += x[i]; }
-    if (blockIdx.x == nb - 1 && threadIdx.x == 0) a[n] = bsum[nb];
-}
-
-static void fz_exclusive_scan(uint32_t *a, uint32_t n, uint32_t *bsum, cudaStream_t st)
-{
-    const uint32_t nb = (n + FZ_XS_TILE - 1) / FZ_XS_TILE;
-    fz_xscan_reduce_kernel<<<nb, FZ_XS_THREADS, 0, st>>>(a, n, bsum);
-    fz_xscan_top_kernel<<<1, 1024, 0, st>>>(bsum, nb);
-    fz_xscan_apply_kernel<<<nb, FZ_XS_THREADS, 0, st>>>(a, n, bsum, nb);
 }
 
 // ---- classify streams: RAW, fast (our sub-block framing: one marker per sub-block, last one ends the payload), general
-__global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBatchGeom g, const uint32_t *__restrict__ tile_off,
-                                   uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, uint32_t hits_cap,
+__global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBatchGeom g, const uint32_t *__restrict__ stream_cnt,
+                                   const uint32_t *__restrict__ hits, uint32_t hits_per_stream,
                                    uint32_t *__restrict__ stream_mode, uint32_t *__restrict__ stream_fail, FzBlockParBufs bp,
                                    const FzStatus *status)
 {
@@ -1542,10 +1238,9 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
     const uint32_t h = stream_hdr[s];
     if (h & FZ_RAW_FLAG) { stream_mode[s] = 0; return; }
     const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
-    const uint32_t h0 = tile_off[s * tiles_per_stream], h1 = tile_off[(s + 1) * tiles_per_stream];
-    const uint32_t m = h1 - h0;
+    const uint32_t m = stream_cnt[s];
     uint32_t mode = 2;
-    if (m >= 1 && h1 <= hits_cap && hits[h1 - 1] + 4 == h) {
+    if (m >= 1 && m <= hits_per_stream && hits[(size_t)s * hits_per_stream + m - 1] + 4 == h) {
         // our framing: one marker per FZ_SUB-byte sub-block
         if (((n_s + FZ_SUB - 1) >> FZ_SUB_LOG2) == m) mode = 1u | ((uint32_t)FZ_SUB_LOG2 << 8);
     }
@@ -1598,8 +1293,8 @@ struct FzGroupSmem {
 
 __global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP, FZ_INF_MINBLOCKS)
 fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
-                        const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ tile_off,
-                        uint32_t tiles_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
+                        const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_cnt,
+                        uint32_t hits_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
                         uint32_t *__restrict__ stream_fail, uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes,
                         const FzStatus *status)
 {
@@ -1610,8 +1305,8 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     const uint32_t cps = fz_groups_per_stream(g);      // code groups per stream
     const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
     if ((stream_mode[s] & 0xffu) != 1u) return;      // CTA-uniform
-    const uint32_t h0 = tile_off[s * tiles_per_stream], h1 = tile_off[(s + 1) * tiles_per_stream];
-    const uint32_t m = h1 - h0;                      // sub-blocks in the stream
+    const size_t h0 = (size_t)s * hits_per_stream;
+    const uint32_t m = stream_cnt[s];                // sub-blocks in the stream
     if (ck * FZ_CODE_SUBS >= m) return;              // CTA-uniform
     const uint32_t gk = ck * FZ_CODE_WARPS + (uint32_t)warp;
     const uint32_t k = gk * FZ_GROUP_SUBS + lane;
@@ -2322,15 +2017,15 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
 {
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t ntiles = nstreams * b.tiles_per_stream;
-    fz_marker_kernel<false><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
-    fz_exclusive_scan(b.tile_cnt, ntiles, b.block_sums, st);
-    fz_marker_kernel<true><<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.hits, b.hits_cap, status);
+    cudaMemsetAsync(b.tile_cnt, 0, ((size_t)ntiles + 1) * 4, st);   // look-back state of the marker scan + its ticket counter
+    fz_marker_kernel<<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.stream_cnt, b.hits,
+                                                         b.hits_per_stream, status);
     if (mark) mark(mark_user, FZ_ST_MARKERS);
     cudaMemsetAsync(b.bp.ctl, 0, 64, st);
     // zero-sub-block flags only when the merge that follows reads them (copy_raw: the plain merge reads the plane buffer)
     uint32_t *zf = copy_raw ? nullptr : b.zero_flags;
     if (zf) cudaMemsetAsync(zf, 0, (size_t)nstreams * g.nsub_full * 4, st);
-    fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.tile_cnt, b.tiles_per_stream, b.hits, b.hits_cap, b.stream_mode, b.stream_fail, b.bp, status);
+    fz_classify_kernel<<<(nstreams + 127) / 128, 128, 0, st>>>(stream_hdr, g, b.stream_cnt, b.hits, b.hits_per_stream, b.stream_mode, b.stream_fail, b.bp, status);
     if (mark) mark(mark_user, FZ_ST_CLASSIFY);
     const uint32_t ncode = nstreams * ((g.nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS);   // one CTA per code group
     // Every lane streams its own fragment: what little L1 the shared-memory carve-out leaves decides how often an input
@@ -2339,7 +2034,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FZ_INF_CARVEOUT_PCT);
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzGroupSmem));
     fz_inflate_group_kernel<<<ncode, FZ_INF_WARPS * FZ_WARP, sizeof(FzGroupSmem), st>>>(
-        container, g, stream_hdr, stream_off, b.tile_cnt, b.tiles_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, status);
+        container, g, stream_hdr, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
     const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;

@@ -98,10 +98,10 @@ size_t fz_blockpar_bytes(uint32_t nstreams, uint32_t chk);
 FzBlockParBufs fz_blockpar_carve(void *blob, uint32_t nstreams, uint32_t chk);
 
 struct FzInflateBufs {
-    uint32_t *tile_cnt;      // [nstreams * tiles_per_stream + 1] counts -> exclusive offsets
-    uint32_t *block_sums;    // scan scratch
-    uint32_t *hits;          // marker positions (stream relative), capacity hits_cap
-    uint32_t hits_cap;
+    uint32_t *tile_cnt;      // [nstreams * tiles_per_stream] look-back state of the marker scan (zeroed per batch)
+    uint32_t *stream_cnt;    // [nstreams] markers found in every stream
+    uint32_t *hits;          // marker positions (stream relative): stream s at hits + s * hits_per_stream, in order
+    uint32_t hits_per_stream;
     uint32_t *stream_mode;   // [nstreams] 0 raw, 1 fast | sub_log2 << 8, 2 general
     uint32_t *stream_fail;   // [nstreams]
     uint32_t *zero_flags;    // [nstreams * nsub_full] 1 = the sub-block is all zero bytes and was NOT written to the plane buffer
@@ -112,11 +112,10 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status,
                        cudaStream_t st, fz_mark_fn mark, void *mark_user, bool copy_raw);
 // merge that reads RAW streams in place from the container (needs chk % 16 == 0)
-void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, const uint32_t *stream_hdr,
+void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, uint64_t container_size, const uint32_t *stream_hdr,
                              const unsigned long long *stream_off, const uint32_t *zero_flags, FzBatchGeom g, uint32_t *words,
                              cudaStream_t st);
 
-size_t fz_encode_smem_bytes();
 
 // ---- error report (reference src/tool/erroranalysis.c:188-220)
 struct FzErrPartial {

@@ -52,121 +52,8 @@ size_t put_stored(uint8_t *o, const uint8_t *in, uint32_t n)
 
 extern "C" {
 
-// a whole plane stream (any n): groups of FZ_GROUP_SUBS sub-blocks share one code, exactly like the
-// three GPU kernels (histogram, group code, emit) do it
-uint64_t hm_encode_stream(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint32_t sub, uint64_t *nstored)
-{
-    uint64_t o = 0, ns = 0;
-    if (sub != FZ_SUB) return (uint64_t)-1;
-    std::vector<uint8_t> pad(FZ_SUB + 32);
-    std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8);
-    FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
-    FzGroupCode *gc = (FzGroupCode *)malloc(sizeof(FzGroupCode));
-    FzEmitState *es = (FzEmitState *)malloc(sizeof(FzEmitState));
-    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
-    for (uint64_t g0 = 0; g0 < n; g0 += gbytes) {
-        const uint64_t gn = (n - g0) < gbytes ? (n - g0) : gbytes;
-        const uint32_t nsub = (uint32_t)((gn + FZ_SUB - 1) / FZ_SUB);
-        memset(st, 0xCD, sizeof(FzEncState));
-        memset(st->hist, 0, sizeof(st->hist));
-        // stage 1: histogram of the group's tokens
-        for (uint32_t k = 0; k < nsub; k++) {
-            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
-            memset(pad.data(), 0, pad.size());
-            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
-            HostLoad16 ld{pad.data()};
-            HostLoadByte lb{pad.data()};
-            uint32_t h[288];
-            memset(h, 0, sizeof(h));
-            for (int lane = 0; lane < 32; lane++) fz_ph_hist(h, ld, lb, m, lane);
-            for (int i = 0; i < 288; i++) st->hist[i] += h[i];
-        }
-        st->hist[FZ_EOB] = nsub;
-        // stage 2: one code + header for the group
-        memset(gc, 0xEE, sizeof(FzGroupCode));
-        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0);
-        // stage 3: emit every sub-block with it
-        for (uint32_t k = 0; k < nsub; k++) {
-            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
-            memset(pad.data(), 0, pad.size());
-            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
-            HostLoad16 ld{pad.data()};
-            HostLoadByte lb{pad.data()};
-            for (auto &w : slot) w = 0xDEADBEEFu;  // garbage: the encoder must write every word it owns
-            memset(es, 0xAB, sizeof(FzEmitState));
-            const uint32_t r = fz_emit_subblock(gc, gc->hdr, es, ld, lb, m, slot.data(), 0);
-            if (r & FZ_SIZE_STORED_FLAG) {
-                if (o + fz_stored_size(m) > cap) return (uint64_t)-1;
-                o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
-                ns++;
-            } else {
-                if (o + r > cap) return (uint64_t)-1;
-                memcpy(out + o, slot.data(), r);
-                o += r;
-            }
-        }
-    }
-    free(st); free(gc); free(es);
-    if (nstored) *nstored = ns;
-    return o;
-}
-
-// the same with the window-interleaved piece geometry (fz_emit_subblock_interleaved; not used by the kernels yet)
-uint64_t hm_encode_stream_interleaved(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *nstored)
-{
-    uint64_t o = 0, ns = 0;
-    std::vector<uint8_t> pad(FZ_SUB + 32);
-    std::vector<uint32_t> slot(FZ_SLOT_STRIDE / 4 + 8);
-    FzEncState *st = (FzEncState *)malloc(sizeof(FzEncState));
-    FzGroupCode *gc = (FzGroupCode *)malloc(sizeof(FzGroupCode));
-    FzEmitStateI *es = (FzEmitStateI *)malloc(sizeof(FzEmitStateI));
-    const uint64_t gbytes = (uint64_t)FZ_SUB * FZ_GROUP_SUBS;
-    for (uint64_t g0 = 0; g0 < n; g0 += gbytes) {
-        const uint64_t gn = (n - g0) < gbytes ? (n - g0) : gbytes;
-        const uint32_t nsub = (uint32_t)((gn + FZ_SUB - 1) / FZ_SUB);
-        memset(st, 0xCD, sizeof(FzEncState));
-        memset(st->hist, 0, sizeof(st->hist));
-        for (uint32_t k = 0; k < nsub; k++) {
-            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
-            memset(pad.data(), 0, pad.size());
-            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
-            HostLoad16 ld{pad.data()};
-            HostLoadByte lb{pad.data()};
-            uint32_t h[288];
-            memset(h, 0, sizeof(h));
-            for (int lane = 0; lane < 32; lane++) fz_ph_hist_interleaved(h, ld, lb, m, lane);
-            for (int i = 0; i < 288; i++) st->hist[i] += h[i];
-        }
-        st->hist[FZ_EOB] = nsub;
-        memset(gc, 0xEE, sizeof(FzGroupCode));
-        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0);
-        for (uint32_t k = 0; k < nsub; k++) {
-            const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
-            memset(pad.data(), 0, pad.size());
-            memcpy(pad.data(), in + g0 + (uint64_t)k * FZ_SUB, m);
-            HostLoad16 ld{pad.data()};
-            HostLoadByte lb{pad.data()};
-            for (auto &w : slot) w = 0xDEADBEEFu;  // garbage: the encoder must write every word it owns
-            memset(es, 0xAB, sizeof(FzEmitStateI));
-            const uint32_t r = fz_emit_subblock_interleaved(gc, gc->hdr, es, ld, lb, m, slot.data(), 0);
-            if (r & FZ_SIZE_STORED_FLAG) {
-                if (o + fz_stored_size(m) > cap) return (uint64_t)-1;
-                o += put_stored(out + o, in + g0 + (uint64_t)k * FZ_SUB, m);
-                ns++;
-            } else {
-                if (o + r > cap) return (uint64_t)-1;
-                memcpy(out + o, slot.data(), r);
-                o += r;
-            }
-        }
-    }
-    free(st); free(gc); free(es);
-    if (nstored) *nstored = ns;
-    return o;
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// encoder v2 (fz_enc2.cuh): the device source run by 32 host threads in lock step, next to a plain sequential
+// the encoder (fz_enc2.cuh): the device source run by 32 host threads in lock step, next to a plain sequential
 // restatement of the token rule and the bit layout -- the two must produce the same bytes
 }  // extern "C"
 namespace {
@@ -357,15 +244,18 @@ int hm_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint32_t out_ca
     return rc;
 }
 
-// test hooks: the false-marker check of the emit stage, and the stored form
+// test hooks: the false-marker check of the emit stage (what FzRingOut::flush does vector by vector), and the stored form
 uint32_t hm_check_marker(const uint8_t *frag, uint32_t total_bytes)
 {
-    std::vector<uint32_t> w((total_bytes + 7) / 4 + 1, 0);
+    std::vector<uint32_t> w((total_bytes + 15) / 16 * 4 + 4, 0);
     memcpy(w.data(), frag, total_bytes);
-    FzEmitState es;
-    memset(&es, 0, sizeof es);
-    for (int lane = 0; lane < 32; lane++) fz_ph_check_marker(&es, w.data(), total_bytes, lane);
-    return es.false_marker;
+    uint32_t pw = 0x55555555u, bad = 0;
+    for (uint32_t vi = 0; vi < (total_bytes + 15) / 16; vi++) {
+        const uint32_t *x = &w[vi * 4];
+        bad |= fz_marker_vec(pw, x[0], x[1], x[2], x[3], vi, total_bytes) ? 1u : 0u;
+        pw = x[3];
+    }
+    return bad;
 }
 uint32_t hm_put_stored(const uint8_t *in, uint32_t n, uint8_t *out) { return (uint32_t)put_stored(out, in, n); }
 

@@ -6,35 +6,10 @@ import numpy as np
 from . import build as _build
 
 _L = C.CDLL(str(_build.build()))
-_L.hm_encode_stream.restype = C.c_uint64
-_L.hm_encode_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
 _L.hm_inflate.restype = C.c_int
 _L.hm_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
 _L.hm_sub_bytes.restype = C.c_uint32
 SUB = int(_L.hm_sub_bytes())
-
-
-def encode_stream(a: np.ndarray, sub: int = SUB):
-    a = np.ascontiguousarray(a, dtype=np.uint8)
-    out = np.empty(a.size + (a.size // sub + 1) * 64 + 64, dtype=np.uint8)
-    ns = C.c_uint64()
-    n = _L.hm_encode_stream(a.ctypes.data, a.size, out.ctypes.data, out.size, sub, C.byref(ns))
-    assert n != 2**64 - 1
-    return out[:n].copy(), int(ns.value)
-
-
-_L.hm_encode_stream_interleaved.restype = C.c_uint64
-_L.hm_encode_stream_interleaved.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
-
-
-def encode_stream_interleaved(a: np.ndarray):
-    """the window-interleaved piece geometry (fz_emit_subblock_interleaved): not used by the kernels yet"""
-    a = np.ascontiguousarray(a, dtype=np.uint8)
-    out = np.empty(a.size + (a.size // SUB + 1) * 64 + 64, dtype=np.uint8)
-    ns = C.c_uint64()
-    n = _L.hm_encode_stream_interleaved(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ns))
-    assert n != 2**64 - 1
-    return out[:n].copy(), int(ns.value)
 
 
 _L.hm_encode_stream_v2.restype = C.c_uint64
@@ -49,6 +24,11 @@ def encode_stream_v2(a: np.ndarray, sequential: bool = False, skip: bool = True)
     n = _L.hm_encode_stream_v2(a.ctypes.data, a.size, out.ctypes.data, out.size, int(sequential), int(skip), C.byref(ns))
     assert n < 2**64 - 2, n
     return out[:n].copy(), int(ns.value)
+
+
+def encode_stream(a: np.ndarray):
+    """a whole plane stream through the encoder the kernels run (device source, 32-thread warp model)"""
+    return encode_stream_v2(a, sequential=False, skip=True)
 
 
 def inflate(b: np.ndarray, n_out: int):
