@@ -648,7 +648,7 @@ def run_b200(a):
                         torch.cuda.synchronize()
                         ms = evs[0].elapsed_time(evs[1]) / 3
                         st = codec.stats()
-                        exp = orig & np.uint32(0xFFFFFFFF << bits if bits < 32 else 0)
+                        exp = orig & np.uint32((0xFFFFFFFF << bits) & 0xFFFFFFFF if bits < 32 else 0)
                         wpf = rf.words_per_file
                         for i in range(rf.cores):   # every file kept its own 256 header words unmasked
                             exp[i * wpf:i * wpf + HDR_WORDS] = orig[i * wpf:i * wpf + HDR_WORDS]

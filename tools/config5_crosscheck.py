@@ -66,7 +66,7 @@ ok_local = torch.tensor([int(torch.equal(ref, back))], device="cuda")
 dist.all_reduce(ok_local, op=dist.ReduceOp.MIN)
 dist.barrier()
 if rank == 0:
-    rec = dict(config=5, n_gpus=world, volume_bytes=total_words * 4, container_bytes=total, ratio=(total - 17) / (total_words * 4),
+    rec = dict(config=5, commit=os.environ.get("MRCZIP_COMMIT"), n_gpus=world, volume_bytes=total_words * 4, container_bytes=total, ratio=(total - 17) / (total_words * 4),
                gpu_shard_roundtrip_ok=bool(ok_local.item()))
     if O.have_ref():
         t0 = time.time()
@@ -78,5 +78,7 @@ if rank == 0:
     print(json.dumps(rec), flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path("gpurun_out/config5.json").write_text(json.dumps(rec))
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
     subprocess.run(["rm", "-rf", tmp])
 dist.destroy_process_group()
