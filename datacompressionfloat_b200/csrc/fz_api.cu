@@ -52,7 +52,7 @@ struct mzb_ctx {
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
     int split_variant = 0, merge_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
-    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist, err_partial, chunk_tab;
+    DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist, err_partial, chunk_tab, group_desc;
     bool zero_hist_ready = false;
     // host-buffer pipeline: copy streams, events, pinned per-batch end offsets
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -219,7 +219,7 @@ extern "C" void mzb_destroy(mzb_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->planes, &c->scratch, &c->sizes, &c->sub_off, &c->stream_hdr, &c->stream_off, &c->stream_mode,
-                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist, &c->err_partial, &c->chunk_tab};
+                     &c->stream_fail, &c->tile_cnt, &c->block_sums, &c->hits, &c->io_in, &c->io_out, &c->ghist, &c->gcodes, &c->blockpar, &c->zero_flags, &c->zero_hist, &c->err_partial, &c->chunk_tab, &c->group_desc};
     for (DevBuf *b : all) release(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto *v : {&c->ev_h2d, &c->ev_comp, &c->ev_d2h})
@@ -393,8 +393,10 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
         (rc = ensure(c->stream_fail, (size_t)nstreams * 4)) || (rc = ensure(c->tile_cnt, (ntiles + 1) * 4)) ||
         (rc = ensure(c->block_sums, (size_t)nstreams * 4)) || (rc = ensure(c->hits, (size_t)nstreams * ib->hits_per_stream * 4)) ||
         (rc = ensure(c->blockpar, fz_blockpar_bytes(nstreams, chk))) ||
-        (rc = ensure(c->zero_flags, (size_t)nstreams * nsub_full * 4)))
+        (rc = ensure(c->zero_flags, (size_t)nstreams * nsub_full * 4)) ||
+        (rc = ensure(c->group_desc, fz_group_desc_bytes(nstreams, nsub_full))))
         return rc;
+    ib->group_desc = c->group_desc.p;
     ib->zero_flags = (uint32_t *)c->zero_flags.p;
     ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams, chk);
     ib->tile_cnt = (uint32_t *)c->tile_cnt.p;
@@ -452,9 +454,9 @@ static void fill_decompress_stats(mzb_ctx *c, uint64_t bytes_in, uint64_t nwords
 static uint32_t compress_launches(uint64_t nw) { return 7 + ((nw & 3) ? 1 : 0); }
 static uint32_t decompress_launches(uint64_t nw, bool in_place_raw)
 {
-    // walk, marker scan, classify, group inflate, six block-parallel kernels, general inflate, then either the
-    // in-place merge or RAW copy + merge (+ tail)
-    return 1 + 2 + 1 + 6 + 1 + (in_place_raw ? 1 : 2) + ((!in_place_raw && (nw & 3)) ? 1 : 0);
+    // walk, marker scan, classify, header pass + lean inflate + full group inflate, six block-parallel kernels, general
+    // inflate, then either the in-place merge or RAW copy + merge (+ tail)
+    return 1 + 2 + 3 + 6 + 1 + (in_place_raw ? 1 : 2) + ((!in_place_raw && (nw & 3)) ? 1 : 0);
 }
 
 extern "C" int mzb_compress_device(mzb_ctx *c, const void *d_words, uint64_t nwords, int bits, uint32_t exempt_words,

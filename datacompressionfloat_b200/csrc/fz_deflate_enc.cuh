@@ -385,7 +385,7 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
         for (uint32_t k = 2; k <= np2; k <<= 1)
             for (uint32_t j = k >> 1; j > 0; j >>= 1) FZ_PHASE(fz_ph_bitonic(st->keys, np2, k, j, lane));
     }
-    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, 15, lane));
+    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, FZ_MAX_CODE_BITS, lane));
     FZ_PHASE(fz_ph_scatter_len(st, lane));
     FZ_PHASE(fz_ph_rank_count(st, lane));
     FZ_PHASE(fz_ph_rank_scan(st, lane));

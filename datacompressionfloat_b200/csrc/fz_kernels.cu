@@ -1279,6 +1279,19 @@ __global__ void fz_classify_kernel(const uint32_t *__restrict__ stream_hdr, FzBa
 #define FZ_GLUT_SIZE (1u << FZ_GLUT_BITS)
 #define FZ_CODE_WARPS (FZ_CODE_SUBS / FZ_GROUP_SUBS)
 static_assert(FZ_INF_WARPS == FZ_CODE_WARPS, "one CTA of the group inflater decodes one code group");
+// what fz_inflate_prep_kernel leaves per code group (see the lean inflater below)
+struct FzGroupDesc {
+    uint32_t state;      // 0: nothing for the group kernels here, 1: the lean kernel decodes it, 2: the full kernel does
+    uint32_t hdr_bits;   // bits of the dynamic block header every coded sub-block of the group starts with
+    uint32_t run_bit;    // value of the one distance bit that means "distance 1" (fz_dd1_run_bit), 2: no such code
+    uint32_t leader;     // sub-block (stream relative) whose header was parsed, ~0: the group has no coded sub-block
+    FzCode LL;
+    uint32_t pad;
+    uint16_t sym[288];   // literal/length symbols sorted by (code length, value)
+};
+static_assert(sizeof(FzGroupDesc) == 656, "descriptor layout (copied to shared memory word by word)");
+#define FZ_DESC_CODE_WORD0 4u                                     // first word of LL in the descriptor
+#define FZ_DESC_CODE_WORDS ((sizeof(FzGroupDesc) / 4u) - FZ_DESC_CODE_WORD0)
 struct FzGroupSmem {
     // shared by the CTA: the code of the group (its sub-blocks carry the same block header)
     alignas(16) uint32_t lut[FZ_GLUT_SIZE];
@@ -1296,11 +1309,12 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
                         const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_cnt,
                         uint32_t hits_per_stream, const uint32_t *__restrict__ hits, const uint32_t *__restrict__ stream_mode,
                         uint32_t *__restrict__ stream_fail, uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes,
-                        const FzStatus *status)
+                        const FzGroupDesc *__restrict__ desc, const FzStatus *status)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     FzGroupSmem *sm = (FzGroupSmem *)fz_smem;
     if (status->error) return;
+    if (desc && desc[blockIdx.x].state != 2u) return;   // CTA-uniform: the lean kernel decoded this group (or there is nothing to decode)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cps = fz_groups_per_stream(g);      // code groups per stream
     const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
@@ -1667,6 +1681,381 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
     }
 }
 
+// =================================================================================================
+// The lean group inflater: what decodes our own streams.  The kernel above carries the whole resumable inflater in
+// registers (102 per thread: 4 CTAs = 16 warps per SM) although all but a few thousand of a sub-block's symbols are table
+// hits.  Here the work is cut in two:
+//   fz_inflate_prep_kernel  one warp per code group: finds the group's first coded sub-block, parses its block header
+//                           with the general inflater and leaves the literal/length code (15 packed limits + sorted
+//                           symbols), the header's bit count and the run bit in a 656-byte descriptor;
+//   fz_inflate_lean_kernel  one CTA per code group: builds the 12-bit table from the descriptor, every lane checks that
+//                           its own header bits equal the leader's and then runs nothing but the table loop: literals
+//                           (1..3 per hit), distance-1 runs, and the end of block followed by the closing empty stored
+//                           block, all validated in place.  No general state machine, no canonical search: the encoder
+//                           limits its codes to FZ_MAX_CODE_BITS = FZ_GLUT_BITS.
+// Anything else -- codes longer than the table (streams of earlier encoder versions), a second coded block, a distance
+// code that is not the 1-bit run code, a parse or size error -- marks the GROUP (desc.state = 2) and the kernel above
+// decodes it again from scratch; what that one refuses goes to the general inflater, as before.
+// =================================================================================================
+
+__global__ void __launch_bounds__(FZ_WARP)
+fz_inflate_prep_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const unsigned long long *__restrict__ stream_off,
+                       const uint32_t *__restrict__ stream_cnt, uint32_t hits_per_stream, const uint32_t *__restrict__ hits,
+                       const uint32_t *__restrict__ stream_mode, FzGroupDesc *__restrict__ desc, const uint8_t *planes,
+                       const FzStatus *status)
+{
+    __shared__ uint16_t tabs[FZ_INF_TAB_U16];
+    __shared__ FzCode codes[2];
+    __shared__ uint32_t res[4];
+    const int lane = threadIdx.x;
+    FzGroupDesc *d = desc + blockIdx.x;
+    const uint32_t cps = fz_groups_per_stream(g);
+    const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
+    const uint32_t m = stream_cnt[s];
+    if (status->error || (stream_mode[s] & 0xffu) != 1u || ck * FZ_CODE_SUBS >= m) {
+        if (lane == 0) d->state = 0;
+        return;
+    }
+    const size_t h0 = (size_t)s * hits_per_stream;
+    const uint8_t *base = container + stream_off[s];
+    uint32_t leader = ~0u;
+#pragma unroll
+    for (uint32_t j = 0; j < FZ_CODE_SUBS / FZ_WARP; j++) {
+        const uint32_t k = ck * FZ_CODE_SUBS + j * FZ_WARP + (uint32_t)lane;
+        bool coded = false;
+        if (k < m) {
+            const uint32_t start = k ? hits[h0 + k - 1] + 4 : 0u, end = hits[h0 + k] + 4;
+            coded = end > start && (base[start] & 7u) == 4u;      // BFINAL = 0, BTYPE = 10
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, coded);
+        if (mask && leader == ~0u) leader = ck * FZ_CODE_SUBS + j * FZ_WARP + (uint32_t)(__ffs((int)mask) - 1);
+    }
+    if (lane == 0) {
+        uint32_t state = 1, hdr_bits = 0, run_bit = 2;
+        const uintptr_t o = (uintptr_t)(planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk);
+        if (o & 15u) state = 2;                                   // the lean writer stores 16 bytes at a time
+        if (leader != ~0u && state == 1u) {
+            const uint32_t start = leader ? hits[h0 + leader - 1] + 4 : 0u, end = hits[h0 + leader] + 4;
+            typedef FzInfTab<1> Tab;
+            Tab tab{tabs, tabs + 288, tabs + 320};
+            FzInflater<Tab> inf;
+            inf.start(base + start, end - start, (uint8_t *)nullptr, FZ_SUB, tab);
+            inf.bind_codes(&codes[0], &codes[1]);
+            const bool okh = inf.block_header() && inf.in_body && inf.rc == FZ_INF_OK;
+            // a complete code whose longest word fits the table: the left-aligned limit of length FZ_GLUT_BITS is 2^15
+            if (!okh || inf.ll_left != 0 || (((const uint32_t *)&codes[0])[FZ_GLUT_BITS - 1] >> 16) != 0x8000u) state = 2;
+            else {
+                hdr_bits = (uint32_t)((int64_t)(end - start) * 8 - inf.br.bits_left());
+                run_bit = fz_dd1_run_bit(inf.dd1);
+            }
+        }
+        res[0] = state; res[1] = hdr_bits; res[2] = run_bit; res[3] = leader;
+    }
+    __syncwarp();
+    if (lane < 4) ((uint32_t *)d)[lane] = res[lane];
+    if (res[0] == 1u && leader != ~0u) {
+        const uint32_t *ll = (const uint32_t *)&codes[0];
+        uint32_t *dw = (uint32_t *)d + FZ_DESC_CODE_WORD0;
+        for (uint32_t i = lane; i < 15u; i += FZ_WARP) dw[i] = ll[i];
+        const uint32_t *sy = (const uint32_t *)tabs;              // 288 sorted literal/length symbols = 144 words
+        for (uint32_t i = lane; i < 144u; i += FZ_WARP) dw[16u + i] = sy[i];
+    }
+}
+
+#ifndef FZ_LEAN_MINBLOCKS
+#define FZ_LEAN_MINBLOCKS 6          // 6 CTAs x 4 warps per SM: 80 registers, 35 KB of shared memory each
+#endif
+struct FzSymTab {
+    const uint16_t *ll;
+    __device__ __forceinline__ uint16_t L(int i) const { return ll[i]; }
+};
+struct FzLeanSmem {
+    alignas(16) uint32_t lut[FZ_GLUT_SIZE];
+    // every lane's window on its fragment (cp.async); before the table exists the first words hold the group's code
+    alignas(16) uint32_t ring[FZ_INF_WARPS * FZ_WARP * FZ_RING_ROW_WORDS];
+};
+static_assert(FZ_DESC_CODE_WORDS * 4u <= sizeof(((FzLeanSmem *)0)->ring), "the code fits where the ring will be");
+
+// 32 stream bits from bit position `pos` of the aligned words b32[0 .. nw): zero bits past the end
+__device__ __forceinline__ uint32_t fz_peek32(const uint32_t *b32, uint32_t nw, uint32_t pos)
+{
+    const uint32_t i = pos >> 5;
+    const uint32_t w0 = i < nw ? b32[i] : 0u, w1 = i + 1 < nw ? b32[i + 1] : 0u;
+    return __funnelshift_r(w0, w1, pos & 31u);
+}
+
+__global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP, FZ_LEAN_MINBLOCKS)
+fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const unsigned long long *__restrict__ stream_off,
+                       const uint32_t *__restrict__ stream_cnt, uint32_t hits_per_stream, const uint32_t *__restrict__ hits,
+                       FzGroupDesc *__restrict__ desc, uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    FzLeanSmem *sm = (FzLeanSmem *)fz_smem;
+    FzGroupDesc *d = desc + blockIdx.x;
+    if (d->state != 1u) return;                           // CTA-uniform (covers a raised error and streams of other kinds)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cps = fz_groups_per_stream(g);
+    const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
+    const uint32_t m = stream_cnt[s];
+    const size_t h0 = (size_t)s * hits_per_stream;
+    const uint32_t hdr_bits = d->hdr_bits, run_bit = d->run_bit, leader = d->leader;
+    const bool any_coded = leader != ~0u;                 // CTA-uniform
+    if (any_coded) {
+        const uint32_t *dw = (const uint32_t *)d + FZ_DESC_CODE_WORD0;
+        for (uint32_t i = threadIdx.x; i < FZ_DESC_CODE_WORDS; i += FZ_INF_WARPS * FZ_WARP) sm->ring[i] = dw[i];
+        __syncthreads();
+        const FzCode &LL = *(const FzCode *)sm->ring;
+        const FzSymTab tab{(const uint16_t *)(sm->ring + 16)};
+        for (uint32_t e = threadIdx.x; e < FZ_GLUT_SIZE; e += FZ_INF_WARPS * FZ_WARP) sm->lut[e] = fz_lut_entry_bits<FZ_GLUT_BITS>(LL, tab, e);
+        __syncthreads();                                  // the table stands; the ring may overwrite the code
+    }
+    const uint32_t gk = ck * FZ_CODE_WARPS + (uint32_t)warp;
+    if (gk * FZ_GROUP_SUBS >= m) return;                  // warp-uniform: nothing of the stream left for this warp
+    const uint32_t k = gk * FZ_GROUP_SUBS + lane;
+    const bool valid = k < m;
+    const uint32_t n_s = fz_chunk_n(g, s / FZ_PLANES);
+    uint32_t start = 0, end = 0, cap = 0;
+    uint8_t *out = nullptr;
+    if (valid) {
+        start = k ? hits[h0 + k - 1] + 4 : 0u;
+        end = hits[h0 + k] + 4;
+        const uint32_t obeg = k << FZ_SUB_LOG2;
+        cap = min((uint32_t)FZ_SUB, n_s - obeg);
+        out = planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk + obeg;
+    }
+    const uint8_t *sbase = container + stream_off[s];
+    const uint8_t *frag = sbase + start;
+    const uint32_t flen = end - start;
+    uint32_t first3 = 7;
+    if (valid && flen >= 1) first3 = frag[0] & 7u;        // BFINAL (must be 0) | BTYPE << 1
+    const bool coded = valid && first3 == 4u;
+    bool failed = valid && first3 != 4u && first3 != 0u;  // fixed-code or final blocks: not ours
+    if (coded && k != leader) {
+        // the first hdr_bits of the fragment must equal the leader's: then the group's table is this sub-block's
+        const uint8_t *lf = sbase + (leader ? hits[h0 + leader - 1] + 4 : 0u);
+        const uint32_t nby = hdr_bits >> 3, rem = hdr_bits & 7u;
+        bool same = (uint64_t)flen * 8 > hdr_bits;
+        if (same) {
+            for (uint32_t i = 0; i < nby; i++) same &= frag[i] == lf[i];
+            if (rem) same &= ((frag[nby] ^ lf[nby]) & ((1u << rem) - 1u)) == 0;
+        }
+        failed |= !same;
+    }
+    // stored sub-blocks (two stored blocks and the empty one): copied by the whole warp, 16 bytes per lane and step
+    {
+        uint32_t stored_mask = __ballot_sync(0xffffffffu, valid && first3 == 0u);
+        while (stored_mask) {
+            const int j = __ffs((int)stored_mask) - 1;
+            stored_mask &= stored_mask - 1;
+            const uint8_t *f = (const uint8_t *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)frag, j);
+            uint8_t *o = (uint8_t *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)out, j);
+            const uint32_t fl = __shfl_sync(0xffffffffu, flen, j), ex = __shfl_sync(0xffffffffu, cap, j);
+            uint32_t pos = 0, prod = 0;
+            bool ok = false;
+            for (int blk = 0; blk < 4; blk++) {   // warp-uniform: every lane reads the same header bytes
+                if (pos + 5 > fl) break;
+                const uint32_t b0 = f[pos], len = (uint32_t)f[pos + 1] | ((uint32_t)f[pos + 2] << 8);
+                const uint32_t nlen = (uint32_t)f[pos + 3] | ((uint32_t)f[pos + 4] << 8);
+                if ((b0 & 7u) != 0u || (len ^ 0xffffu) != nlen) break;      // BFINAL = 0, BTYPE = 00, LEN = ~NLEN
+                if (len == 0) { ok = pos + 5 == fl && prod == ex; break; }   // the empty block must close the fragment
+                if (prod + len > ex || pos + 5 + len > fl) break;
+                fz_warp_copy(o + prod, f + pos + 5, len, f + fl, lane);
+                pos += 5 + len;
+                prod += len;
+            }
+            if (lane == j && !ok) failed = true;
+        }
+    }
+    const uint32_t *lut = sm->lut;
+    const uint32_t mis = (uint32_t)((uintptr_t)frag & 15u);
+    const uint32_t endbit = (mis + flen) * 8u;            // ring coordinates: bit 0 = first bit of the 16-byte chunk of frag[0]
+    // Tiny fragments are almost always sub-blocks of zero bytes (mask bits >= 8 zero whole byte planes): walk the tokens
+    // without storing; if the fragment is valid and all zero it is only flagged -- the merge supplies the zeros.
+    bool all_zero = false;
+    if (zero_flags && coded && !failed && flen <= FZ_ZERO_PROBE_BYTES) {
+        const uint32_t sk = (uint32_t)((uintptr_t)frag & 3u);
+        const uint32_t *b32 = (const uint32_t *)(frag - sk);
+        const uint32_t nw = (sk + flen + 3u) >> 2, zend = (sk + flen) * 8u;
+        uint32_t pos = sk * 8u + hdr_bits, prod = 0;
+        bool ok = false;
+        while (pos < zend) {
+            const uint32_t w = fz_peek32(b32, nw, pos);
+            const uint32_t e = lut[w & (FZ_GLUT_SIZE - 1)];
+            if (e == 0) break;
+            if (e & 0x100u) {
+                if (!(e & FZ_LUT_MATCH)) {                // the end of block and the closing empty stored block, or garbage
+                    const uint32_t tl = (e >> 25) & 15u, after = pos + tl + 3u;
+                    ok = (e & 511u) == FZ_EOB && ((w >> tl) & 7u) == 0u && ((after + 7u) & ~7u) + 32u == zend && prod == cap;
+                    break;
+                }
+                const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u, a = w >> cl;
+                const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
+                if (((a >> xb) & 1u) != run_bit || prod == 0 || prod + len > cap) break;
+                pos += cl + xb + 1u;
+                prod += len;
+            } else {
+                const uint32_t cnt = e >> 29;
+                if (((e & 255u) | ((e >> 1) & 0xffff00u)) != 0u || prod + cnt > cap) break;   // a byte that is not zero
+                pos += (e >> 25) & 15u;
+                prod += cnt;
+            }
+        }
+        all_zero = ok;
+    }
+    if (zero_flags && valid) zero_flags[(size_t)s * g.nsub_full + k] = all_zero ? 1u : 0u;
+
+    // ---- the table loop.  The lane reads its fragment through a ring of FZ_RING_CHUNKS 16-byte chunks in shared memory
+    // that cp.async tops up once per round (<= 3 chunks; a round takes at most 16 x 18 bits), two rounds ahead of the
+    // decoder.  Completed output words wait in pw0..pw2 until the fourth of their 16-byte group arrives and leave as one
+    // 128-bit store.
+    bool live = coded && !failed && !all_zero;
+    bool done_ok = false;
+    uint32_t op = 0, ow = 0, pw0 = 0, pw1 = 0, pw2 = 0, lastw = 0;
+    {
+        const uint8_t *gbase = frag - mis;                               // chunk 0
+        const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
+        uint32_t *row = sm->ring + (warp * FZ_WARP + lane) * FZ_RING_ROW_WORDS;
+        const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(row);
+        const uint32_t abs_bit = mis * 8u + hdr_bits;
+        uint64_t acc = 0;
+        uint32_t nxt = 0, rp = abs_bit >> 5, fetched = rp >> 2;
+        int nacc = 0;
+        if (live) {
+#pragma unroll
+            for (uint32_t q = 0; q < FZ_RING_CHUNKS; q++) {
+                if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
+                fetched++;
+            }
+        }
+        fz_cp_async_commit();
+        fz_cp_async_wait<0>();
+        if (live) {
+            acc = (uint64_t)(row[rp & (FZ_RING_CHUNKS * 4 - 1)] >> (abs_bit & 31u));
+            nacc = 32 - (int)(abs_bit & 31u);
+            rp++;
+            nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
+        }
+#define FZ_LEAN_WORD_DONE(w_, kq_, gaddr_)                                                      \
+        do {                                                                                    \
+            if ((kq_) == 3u) *(uint4 *)(gaddr_) = make_uint4(pw0, pw1, pw2, (w_));              \
+            pw0 = (kq_) == 0u ? (w_) : pw0;                                                     \
+            pw1 = (kq_) == 1u ? (w_) : pw1;                                                     \
+            pw2 = (kq_) == 2u ? (w_) : pw2;                                                     \
+            lastw = (w_);                                                                       \
+        } while (0)
+        while (__any_sync(0xffffffffu, live)) {
+            if (live) {
+                // chunks below this one are used up (the bit buffer holds at most two words behind rp)
+                const uint32_t cons = (rp >= 2u ? rp - 2u : 0u) >> 2;
+#pragma unroll
+                for (int q = 0; q < FZ_RING_TOPUPS; q++) {
+                    if (fetched < cons + FZ_RING_CHUNKS) {
+                        if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
+                        fetched++;
+                    }
+                }
+            }
+            fz_cp_async_commit();
+            fz_cp_async_wait<1>();
+            if (live) {
+#pragma unroll 1
+                for (int it = 0; it < FZ_FAST_ITERS; ++it) {
+                    // refill without a branch: ORing the next word in early is harmless (its bits land where they
+                    // belong and are ORed there again once they count), and `nxt` is re-read every iteration
+                    acc |= (uint64_t)nxt << nacc;
+                    const bool need = nacc < 32;
+                    nacc += need ? 32 : 0;
+                    rp += need ? 1u : 0u;
+                    nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
+                    const uint32_t e = lut[(uint32_t)acc & (FZ_GLUT_SIZE - 1)];
+                    if (e & 0x100u) {
+                        if (!(e & FZ_LUT_MATCH)) {
+                            // end of block: what follows must be the empty stored block (000, pad to the byte, 00 00 FF FF
+                            // -- the marker the scan found) that closes the fragment, and the sub-block must be complete
+                            const uint32_t tl = (e >> 25) & 15u;
+                            const uint32_t after = rp * 32u - (uint32_t)nacc + tl + 3u;
+                            done_ok = (e & 511u) == FZ_EOB && (((uint32_t)(acc >> tl)) & 7u) == 0u &&
+                                      ((after + 7u) & ~7u) + 32u == endbit && op == cap;
+                            live = false;
+                            break;
+                        }
+                        // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
+                        const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
+                        const uint32_t a = (uint32_t)(acc >> cl);
+                        const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
+                        if (((a >> xb) & 1u) != run_bit || op + len > cap || op == 0u) { live = false; break; }
+                        acc >>= (cl + xb + 1u);
+                        nacc -= (int)(cl + xb + 1u);
+                        {   // len copies of the byte before, through the pending-word logic (no read of what was written)
+                            const uint32_t r = op & 3u;
+                            const uint32_t c = r ? (ow >> ((r - 1u) * 8u)) & 0xffu : lastw >> 24;
+                            const uint32_t cw = c * 0x01010101u;
+                            uint32_t left = len;
+                            if (r) {   // complete the pending word first
+                                const uint32_t take = left < 4u - r ? left : 4u - r;
+                                ow |= (cw & (0xffffffffu >> (32u - 8u * take))) << (8u * r);
+                                left -= take;
+                                if (r + take == 4u) {
+                                    FZ_LEAN_WORD_DONE(ow, (op >> 2) & 3u, out + (op & ~15u));
+                                    ow = 0;
+                                }
+                                op += take;
+                            }
+                            while (left >= 4u) {
+                                const uint32_t kq = (op >> 2) & 3u;
+                                if (kq == 0u && left >= 16u) {
+                                    *(uint4 *)(out + op) = make_uint4(cw, cw, cw, cw);
+                                    lastw = cw;
+                                    op += 16u;
+                                    left -= 16u;
+                                } else {
+                                    FZ_LEAN_WORD_DONE(cw, kq, out + (op & ~15u));
+                                    op += 4u;
+                                    left -= 4u;
+                                }
+                            }
+                            if (left) { ow = cw & (0xffffffffu >> (32u - 8u * left)); op += left; }
+                        }
+                        continue;
+                    }
+                    // 1..3 literals: sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that
+                    // count) appended to the pending word.  e == 0 (no code of <= FZ_GLUT_BITS bits) has cnt == 0.
+                    const uint32_t cnt = e >> 29, tl = (e >> 25) & 15u;
+                    if (cnt == 0u || op + cnt > cap) { live = false; break; }
+                    const uint32_t v = (e & 255u) | ((e >> 1) & 0xffff00u);
+                    const uint32_t sh = (op & 3u) * 8u;
+                    const uint64_t t = (uint64_t)ow | ((uint64_t)v << sh);
+                    const uint32_t kq = (op >> 2) & 3u;     // place of the pending word in its 16-byte group
+                    op += cnt;
+                    const bool full = sh + cnt * 8u >= 32u;
+                    if (full && kq == 3u) *(uint4 *)(out + ((op & ~3u) - 16u)) = make_uint4(pw0, pw1, pw2, (uint32_t)t);
+                    pw0 = (full && kq == 0u) ? (uint32_t)t : pw0;
+                    pw1 = (full && kq == 1u) ? (uint32_t)t : pw1;
+                    pw2 = (full && kq == 2u) ? (uint32_t)t : pw2;
+                    lastw = full ? (uint32_t)t : lastw;
+                    ow = full ? (uint32_t)(t >> 32) : (uint32_t)t;
+                    acc >>= tl;
+                    nacc -= (int)tl;
+                }
+            }
+        }
+#undef FZ_LEAN_WORD_DONE
+    }
+    if (coded && !failed && !all_zero) {
+        if (done_ok) {
+            // what is still pending: the completed words of the last 16-byte group, then the bytes of the last word
+            const uint32_t kq = (op >> 2) & 3u;
+            uint32_t *q = (uint32_t *)(out + (op & ~15u));
+            if (kq > 0) q[0] = pw0;
+            if (kq > 1) q[1] = pw1;
+            if (kq > 2) q[2] = pw2;
+            const uint32_t r = op & 3u, w0 = op - r;
+            for (uint32_t i = 0; i < r; i++) out[w0 + i] = (uint8_t)(ow >> (8u * i));
+        } else failed = true;
+    }
+    if (failed) d->state = 2u;    // the full group kernel decodes this group again
+}
+
 // ---- general path: one thread per stream (reference-made streams: back-to-back blocks, no byte alignment between them)
 __global__ void __launch_bounds__(32)
 fz_inflate_general_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const uint32_t *__restrict__ stream_hdr,
@@ -2011,6 +2400,11 @@ fz_rawcopy_kernel(const uint8_t *__restrict__ container, uint64_t container_size
     fz_warp_copy(dst, container + stream_off[s] + off, n, container + container_size, lane);
 }
 
+size_t fz_group_desc_bytes(uint32_t nstreams, uint32_t nsub_full)
+{
+    return (size_t)nstreams * ((nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS) * sizeof(FzGroupDesc);
+}
+
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status, cudaStream_t st,
                        fz_mark_fn mark, void *mark_user, bool copy_raw)
@@ -2031,10 +2425,17 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     // Every lane streams its own fragment: what little L1 the shared-memory carve-out leaves decides how often an input
     // word is an L2 round trip.  164 KB of shared memory (4 CTAs of 37 KB) and 92 KB of L1 beat 228 KB / 6 CTAs by
     // 20-25 % on every input measured (sweep in profiles/README.md).
+    FzGroupDesc *desc = (FzGroupDesc *)b.group_desc;
+    fz_inflate_prep_kernel<<<ncode, FZ_WARP, 0, st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, desc, planes, status);
+    cudaFuncSetAttribute(fz_inflate_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(fz_inflate_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzLeanSmem));
+    fz_inflate_lean_kernel<<<ncode, FZ_INF_WARPS * FZ_WARP, sizeof(FzLeanSmem), st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits,
+                                                                                     desc, zf, planes);
+    // groups the lean kernel does not take or gave up on (desc.state == 2): the full inflater, one warp per 32 sub-blocks
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FZ_INF_CARVEOUT_PCT);
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzGroupSmem));
     fz_inflate_group_kernel<<<ncode, FZ_INF_WARPS * FZ_WARP, sizeof(FzGroupSmem), st>>>(
-        container, g, stream_hdr, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, status);
+        container, g, stream_hdr, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, b.stream_fail, zf, planes, desc, status);
     if (mark) mark(mark_user, FZ_ST_INFLATE_FAST);
     // zlib-made streams (the reference's own containers): block-parallel; whatever that refuses goes to the serial inflater
     const uint32_t segs = (g.chk + 16 + 4 * FZ_BP_SEG_WORDS - 1) / (4 * FZ_BP_SEG_WORDS) + 1;

@@ -106,8 +106,10 @@ struct FzInflateBufs {
     uint32_t *stream_fail;   // [nstreams]
     uint32_t *zero_flags;    // [nstreams * nsub_full] 1 = the sub-block is all zero bytes and was NOT written to the plane buffer
     uint32_t tiles_per_stream;
+    void *group_desc;        // [fz_group_desc_bytes()] one descriptor per code group: what the header pass leaves for the lean inflater
     FzBlockParBufs bp;
 };
+size_t fz_group_desc_bytes(uint32_t nstreams, uint32_t nsub_full);
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
                        const unsigned long long *stream_off, FzInflateBufs b, uint8_t *planes, FzStatus *status,
                        cudaStream_t st, fz_mark_fn mark, void *mark_user, bool copy_raw);

@@ -136,6 +136,8 @@ def _plane_cases():
         "16k+1": rng.choice([1, 2, 3], 16385).astype(np.uint8),
         "run258": np.concatenate([np.full(259, 5, np.uint8), np.full(260, 6, np.uint8), np.full(517, 7, np.uint8), [1, 2]]).astype(np.uint8),
         "mid_entropy": rng.integers(0, 200, 33000).astype(np.uint8),
+        # halving probabilities: an unlimited Huffman code would reach 20+ bits; the encoder stops at FZ_MAX_CODE_BITS (12)
+        "skewed_long_codes": rng.choice(np.arange(30), 70000, p=np.r_[0.5 ** np.arange(1, 30), 0.5 ** 29]).astype(np.uint8),
     }
     g = synth_words("G", 65536).view(np.uint8).reshape(-1, 4)
     p = synth_words("P", 65536).view(np.uint8).reshape(-1, 4)
