@@ -53,10 +53,10 @@
 #define FZ_SIZE_COPY_FLAG 0x20000000u     // its fragment is byte-identical to the one of sub-block (bits 24..28) of its group
 #define FZ_SIZE_MASK 0x00FFFFFFu          // the size itself
 
-// Longest literal/length code the encoder hands out.  Deflate allows 15; 12 is the index width of the group
-// inflater's lookup table (FZ_GLUT_BITS), so every symbol of our own streams is one table hit -- the canonical
-// search for longer codes ran with 4 of 32 lanes active and was 15 % of the inflater's instructions on planes with
-// 30+ symbols.  Codes that long belong to symbols rarer than 1 in 4096: the size cost is not measurable.
+// Longest literal/length code the encoder gives a symbol its histogram sample SAW.  Deflate allows 15; 12 is the index
+// width of the group inflater's lookup table (FZ_GLUT_BITS), so every such symbol is one table hit -- the canonical
+// search for longer codes ran with 4 of 32 lanes active and was 15 % of the inflater's instructions on planes with 30+
+// symbols.  Symbols the sample did not see keep the 15-bit limit (fz_ph_lengths, two tiers).
 #ifndef FZ_MAX_CODE_BITS
 #define FZ_MAX_CODE_BITS 12
 #endif

@@ -126,10 +126,13 @@ FZ_HD void fz_ph_bitonic(uint32_t *keys, uint32_t np2, uint32_t k, uint32_t j, i
 
 // serial (lane 0): in-place minimum-redundancy code lengths (Moffat & Katajainen 1995) over the
 // ascending frequencies, then the length limit.  keys[] holds freq << 9 | sym on entry.
-FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n, int maxbits, int lane)
+// `seenbits` < maxbits asks for two tiers: symbols of frequency <= 1 (the stand-ins of fz_group_code_kernel: "may occur
+// in the sub-blocks that were not sampled") may take maxbits, every symbol the sample saw gets at most seenbits.
+FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n, int maxbits, int lane, int seenbits = 0)
 {
     if (lane != 0) return;
-    for (int i = 0; i < n; i++) { const uint32_t k = A[i]; ssym[i] = (uint16_t)(k & 511u); A[i] = k >> 9; }
+    int nlow = 0;   // keys ascend: the symbols of frequency <= 1 come first
+    for (int i = 0; i < n; i++) { const uint32_t k = A[i]; ssym[i] = (uint16_t)(k & 511u); A[i] = k >> 9; if (A[i] <= 1u) nlow = i + 1; }
     for (int l = 0; l < 32; l++) num_codes[l] = 0;
     if (n == 1) { A[0] = 1; num_codes[1] = 1; return; }
     // phase 1: internal node weights + parent pointers
@@ -149,6 +152,37 @@ FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n
         while (root >= 0 && (int)A[root] == dpth) { used++; root--; }
         while (avbl > used) { A[next--] = (uint32_t)dpth; avbl--; }
         avbl = 2 * used; dpth++; used = 0;
+    }
+    if (seenbits > 0 && seenbits < maxbits) {
+        // Two tiers.  Limiting all 286 symbols to the 12 bits of the inflater's table would hand 286 / 4096 = 7 % of the
+        // code space to stand-ins that hardly ever occur (+1..2 % size, measured); at 15 bits they cost 0.9 %, and the
+        // symbols that do occur are still one table lookup each.  Clamp per tier, then repair the Kraft sum K (in units
+        // of 2^-maxbits): lengthen the least frequent symbols that still may grow (A[] descends, so the first one found
+        // gives the smallest step), then hand back what that overshot by shortening whatever fits, most frequent first.
+        const uint32_t full = 1u << maxbits;
+        uint32_t K = 0;
+        for (int i = 0; i < n; i++) {
+            const uint32_t lim = (uint32_t)(i < nlow ? maxbits : seenbits);
+            if (A[i] > lim) A[i] = lim;
+            K += 1u << ((uint32_t)maxbits - A[i]);
+        }
+        while (K > full) {
+            for (int i = 0; i < n && K > full; i++) {
+                const uint32_t lim = (uint32_t)(i < nlow ? maxbits : seenbits);
+                if (A[i] < lim) { K -= 1u << ((uint32_t)maxbits - A[i] - 1u); A[i]++; }
+            }
+        }
+        uint32_t D = full - K;
+        while (D) {
+            bool moved = false;
+            for (int i = n - 1; i >= 0 && D; i--) {
+                const uint32_t gain = 1u << ((uint32_t)maxbits - A[i]);
+                if (A[i] > 1u && gain <= D) { A[i]--; D -= gain; moved = true; }
+            }
+            if (!moved) break;   // (cannot happen: D is a multiple of the step of the longest code present)
+        }
+        for (int i = 0; i < n; i++) num_codes[A[i]]++;
+        return;
     }
     // histogram of lengths, clamped at 31
     for (int i = 0; i < n; i++) { uint32_t l = A[i]; if (l > 31) l = 31; num_codes[l]++; }
@@ -385,7 +419,7 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
         for (uint32_t k = 2; k <= np2; k <<= 1)
             for (uint32_t j = k >> 1; j > 0; j >>= 1) FZ_PHASE(fz_ph_bitonic(st->keys, np2, k, j, lane));
     }
-    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, FZ_MAX_CODE_BITS, lane));
+    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, 15, lane, FZ_MAX_CODE_BITS));
     FZ_PHASE(fz_ph_scatter_len(st, lane));
     FZ_PHASE(fz_ph_rank_count(st, lane));
     FZ_PHASE(fz_ph_rank_scan(st, lane));

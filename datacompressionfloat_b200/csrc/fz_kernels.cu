@@ -1742,8 +1742,7 @@ fz_inflate_prep_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
             inf.start(base + start, end - start, (uint8_t *)nullptr, FZ_SUB, tab);
             inf.bind_codes(&codes[0], &codes[1]);
             const bool okh = inf.block_header() && inf.in_body && inf.rc == FZ_INF_OK;
-            // a complete code whose longest word fits the table: the left-aligned limit of length FZ_GLUT_BITS is 2^15
-            if (!okh || inf.ll_left != 0 || (((const uint32_t *)&codes[0])[FZ_GLUT_BITS - 1] >> 16) != 0x8000u) state = 2;
+            if (!okh || inf.ll_left != 0) state = 2;               // (an incomplete code: not ours)
             else {
                 hdr_bits = (uint32_t)((int64_t)(end - start) * 8 - inf.br.bits_left());
                 run_bit = fz_dd1_run_bit(inf.dd1);
@@ -1763,18 +1762,37 @@ fz_inflate_prep_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
 }
 
 #ifndef FZ_LEAN_MINBLOCKS
-#define FZ_LEAN_MINBLOCKS 6          // 6 CTAs x 4 warps per SM: 80 registers, 35 KB of shared memory each
+#define FZ_LEAN_MINBLOCKS 7          // 7 CTAs x 4 warps per SM (<= 72 registers, <= 31.4 KB of shared memory each): the two coded
+                                     // planes of a 4 GiB volume (1026 code groups) are resident at once on 148 SMs
 #endif
+#define FZ_LEAN_CHUNKS 7u            // 16-byte chunks of input per lane (the ring is indexed modulo 7 by wrap-around counters)
+#define FZ_LEAN_ROW_WORDS (FZ_LEAN_CHUNKS * 4u)
+#define FZ_LEAN_TOPUPS 3             // chunks a round can use up
+#define FZ_LEAN_ITERS 12             // table hits per round: 12 x 21 bits (15-bit code, 5 extra bits, distance bit) < 8 words, so
+                                     // a round reads at most chunk cons + 3 while chunks < cons + 4 have landed (see the loop)
 struct FzSymTab {
     const uint16_t *ll;
     __device__ __forceinline__ uint16_t L(int i) const { return ll[i]; }
 };
 struct FzLeanSmem {
     alignas(16) uint32_t lut[FZ_GLUT_SIZE];
-    // every lane's window on its fragment (cp.async); before the table exists the first words hold the group's code
-    alignas(16) uint32_t ring[FZ_INF_WARPS * FZ_WARP * FZ_RING_ROW_WORDS];
+    alignas(16) uint32_t ring[FZ_INF_WARPS * FZ_WARP * FZ_LEAN_ROW_WORDS];   // every lane's window on its fragment (cp.async)
+    alignas(16) uint32_t code[FZ_DESC_CODE_WORDS];                           // FzCode LL, pad, 288 sorted symbols
 };
-static_assert(FZ_DESC_CODE_WORDS * 4u <= sizeof(((FzLeanSmem *)0)->ring), "the code fits where the ring will be");
+static_assert(sizeof(FzLeanSmem) + 1024 <= (227 * 1024) / FZ_LEAN_MINBLOCKS, "shared memory of FZ_LEAN_MINBLOCKS CTAs per SM");
+
+// Table entry of a code longer than the table's index, decoded the canonical way: one symbol, its real length (<= 15)
+// in the length field.  Only symbols the encoder's sample never saw have such codes.  0 = no such code.
+__device__ __noinline__ uint32_t fz_lean_long_entry(const uint32_t *code, uint32_t bits15)
+{
+    uint32_t idx;
+    const int l = fz_decode_idx(*(const FzCode *)code, bits15, idx);
+    if (l == 0 || idx >= 288u) return 0u;
+    const uint32_t s1 = ((const uint16_t *)(code + 16))[idx];
+    uint32_t ent = FZ_LUT_ENTRY(s1, 0, 0, l, 1);
+    if (s1 >= 257u && s1 <= 285u) ent |= FZ_LUT_MATCH | (fz_len_base(s1 - 257u) << 9) | (fz_len_extra_bits(s1 - 257u) << 18);
+    return ent;
+}
 
 // 32 stream bits from bit position `pos` of the aligned words b32[0 .. nw): zero bits past the end
 __device__ __forceinline__ uint32_t fz_peek32(const uint32_t *b32, uint32_t nw, uint32_t pos)
@@ -1791,23 +1809,27 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     FzLeanSmem *sm = (FzLeanSmem *)fz_smem;
-    FzGroupDesc *d = desc + blockIdx.x;
+    // CTAs in PLANE-major order: the code groups of one byte plane cost about the same and those of another plane may
+    // cost nothing (RAW, all zero), so consecutive CTAs -- which the block scheduler deals round the SMs -- are alike
+    // and every SM gets its share of the expensive ones (chunk-major order left some SMs with 6 of them, others with 2)
+    const uint32_t cps = fz_groups_per_stream(g);
+    const uint32_t q = blockIdx.x / cps, ck = blockIdx.x - q * cps;
+    const uint32_t s = (q % g.nchunks) * FZ_PLANES + q / g.nchunks;
+    FzGroupDesc *d = desc + (size_t)s * cps + ck;
     if (d->state != 1u) return;                           // CTA-uniform (covers a raised error and streams of other kinds)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cps = fz_groups_per_stream(g);
-    const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
     const uint32_t m = stream_cnt[s];
     const size_t h0 = (size_t)s * hits_per_stream;
     const uint32_t hdr_bits = d->hdr_bits, run_bit = d->run_bit, leader = d->leader;
     const bool any_coded = leader != ~0u;                 // CTA-uniform
     if (any_coded) {
         const uint32_t *dw = (const uint32_t *)d + FZ_DESC_CODE_WORD0;
-        for (uint32_t i = threadIdx.x; i < FZ_DESC_CODE_WORDS; i += FZ_INF_WARPS * FZ_WARP) sm->ring[i] = dw[i];
+        for (uint32_t i = threadIdx.x; i < FZ_DESC_CODE_WORDS; i += FZ_INF_WARPS * FZ_WARP) sm->code[i] = dw[i];
         __syncthreads();
-        const FzCode &LL = *(const FzCode *)sm->ring;
-        const FzSymTab tab{(const uint16_t *)(sm->ring + 16)};
+        const FzCode &LL = *(const FzCode *)sm->code;
+        const FzSymTab tab{(const uint16_t *)(sm->code + 16)};
         for (uint32_t e = threadIdx.x; e < FZ_GLUT_SIZE; e += FZ_INF_WARPS * FZ_WARP) sm->lut[e] = fz_lut_entry_bits<FZ_GLUT_BITS>(LL, tab, e);
-        __syncthreads();                                  // the table stands; the ring may overwrite the code
+        __syncthreads();
     }
     const uint32_t gk = ck * FZ_CODE_WARPS + (uint32_t)warp;
     if (gk * FZ_GROUP_SUBS >= m) return;                  // warp-uniform: nothing of the stream left for this warp
@@ -1880,7 +1902,8 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
         bool ok = false;
         while (pos < zend) {
             const uint32_t w = fz_peek32(b32, nw, pos);
-            const uint32_t e = lut[w & (FZ_GLUT_SIZE - 1)];
+            uint32_t e = lut[w & (FZ_GLUT_SIZE - 1)];
+            if (e == 0) e = fz_lean_long_entry(sm->code, w & 0x7fffu);
             if (e == 0) break;
             if (e & 0x100u) {
                 if (!(e & FZ_LUT_MATCH)) {                // the end of block and the closing empty stored block, or garbage
@@ -1904,36 +1927,43 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
     }
     if (zero_flags && valid) zero_flags[(size_t)s * g.nsub_full + k] = all_zero ? 1u : 0u;
 
-    // ---- the table loop.  The lane reads its fragment through a ring of FZ_RING_CHUNKS 16-byte chunks in shared memory
-    // that cp.async tops up once per round (<= 3 chunks; a round takes at most 16 x 18 bits), two rounds ahead of the
-    // decoder.  Completed output words wait in pw0..pw2 until the fourth of their 16-byte group arrives and leave as one
-    // 128-bit store.
+    // ---- the table loop.  The lane reads its fragment through a ring of FZ_LEAN_CHUNKS 16-byte chunks in shared memory
+    // that cp.async tops up once per round, two rounds ahead of the decoder: `cp.async.wait_group 1` leaves only the
+    // newest top-up in flight.  Why a round never reads what has not landed: with cons = (rp - 2) / 4 the first chunk still
+    // in use at the start of a round, rp <= 4 cons + 5; a round advances rp by at most 8 words (FZ_LEAN_ITERS), so it reads
+    // words <= 4 cons + 13: chunk cons + 3.  The previous round left fetched = cons' + 7 >= cons + 4 (cons moves by at
+    // most 3 chunks per round, which FZ_LEAN_TOPUPS = 3 makes up), and all of that has landed.  Completed output words
+    // wait in pw0..pw2 until the fourth of their 16-byte group arrives and leave as one 128-bit store.
     bool live = coded && !failed && !all_zero;
     bool done_ok = false;
     uint32_t op = 0, ow = 0, pw0 = 0, pw1 = 0, pw2 = 0, lastw = 0;
     {
         const uint8_t *gbase = frag - mis;                               // chunk 0
         const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
-        uint32_t *row = sm->ring + (warp * FZ_WARP + lane) * FZ_RING_ROW_WORDS;
+        uint32_t *row = sm->ring + (warp * FZ_WARP + lane) * FZ_LEAN_ROW_WORDS;
         const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(row);
         const uint32_t abs_bit = mis * 8u + hdr_bits;
         uint64_t acc = 0;
         uint32_t nxt = 0, rp = abs_bit >> 5, fetched = rp >> 2;
+        uint32_t ri = rp % FZ_LEAN_ROW_WORDS;                            // rp modulo the ring's words
+        uint32_t fs = fetched % FZ_LEAN_CHUNKS;                          // fetched modulo the ring's chunks
         int nacc = 0;
         if (live) {
 #pragma unroll
-            for (uint32_t q = 0; q < FZ_RING_CHUNKS; q++) {
-                if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
+            for (uint32_t c = 0; c < FZ_LEAN_CHUNKS; c++) {
+                if (fetched < nchunks) fz_cp_async16(row_s + fs * 16u, gbase + (size_t)fetched * 16u);
                 fetched++;
+                fs = fs + 1u == FZ_LEAN_CHUNKS ? 0u : fs + 1u;
             }
         }
         fz_cp_async_commit();
         fz_cp_async_wait<0>();
         if (live) {
-            acc = (uint64_t)(row[rp & (FZ_RING_CHUNKS * 4 - 1)] >> (abs_bit & 31u));
+            acc = (uint64_t)(row[ri] >> (abs_bit & 31u));
             nacc = 32 - (int)(abs_bit & 31u);
             rp++;
-            nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
+            ri = ri + 1u == FZ_LEAN_ROW_WORDS ? 0u : ri + 1u;
+            nxt = row[ri];
         }
 #define FZ_LEAN_WORD_DONE(w_, kq_, gaddr_)                                                      \
         do {                                                                                    \
@@ -1948,10 +1978,11 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
                 // chunks below this one are used up (the bit buffer holds at most two words behind rp)
                 const uint32_t cons = (rp >= 2u ? rp - 2u : 0u) >> 2;
 #pragma unroll
-                for (int q = 0; q < FZ_RING_TOPUPS; q++) {
-                    if (fetched < cons + FZ_RING_CHUNKS) {
-                        if (fetched < nchunks) fz_cp_async16(row_s + (fetched & (FZ_RING_CHUNKS - 1)) * 16u, gbase + (size_t)fetched * 16u);
+                for (int c = 0; c < FZ_LEAN_TOPUPS; c++) {
+                    if (fetched < cons + FZ_LEAN_CHUNKS) {
+                        if (fetched < nchunks) fz_cp_async16(row_s + fs * 16u, gbase + (size_t)fetched * 16u);
                         fetched++;
+                        fs = fs + 1u == FZ_LEAN_CHUNKS ? 0u : fs + 1u;
                     }
                 }
             }
@@ -1959,15 +1990,18 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
             fz_cp_async_wait<1>();
             if (live) {
 #pragma unroll 1
-                for (int it = 0; it < FZ_FAST_ITERS; ++it) {
+                for (int it = 0; it < FZ_LEAN_ITERS; ++it) {
                     // refill without a branch: ORing the next word in early is harmless (its bits land where they
                     // belong and are ORed there again once they count), and `nxt` is re-read every iteration
                     acc |= (uint64_t)nxt << nacc;
                     const bool need = nacc < 32;
                     nacc += need ? 32 : 0;
                     rp += need ? 1u : 0u;
-                    nxt = row[rp & (FZ_RING_CHUNKS * 4 - 1)];
-                    const uint32_t e = lut[(uint32_t)acc & (FZ_GLUT_SIZE - 1)];
+                    ri += need ? 1u : 0u;
+                    ri = ri == FZ_LEAN_ROW_WORDS ? 0u : ri;
+                    nxt = row[ri];
+                    uint32_t e = lut[(uint32_t)acc & (FZ_GLUT_SIZE - 1)];
+                    if (e == 0u) e = fz_lean_long_entry(sm->code, (uint32_t)acc & 0x7fffu);   // a symbol the encoder's sample never saw
                     if (e & 0x100u) {
                         if (!(e & FZ_LUT_MATCH)) {
                             // end of block: what follows must be the empty stored block (000, pad to the byte, 00 00 FF FF
@@ -2019,7 +2053,7 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
                         continue;
                     }
                     // 1..3 literals: sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that
-                    // count) appended to the pending word.  e == 0 (no code of <= FZ_GLUT_BITS bits) has cnt == 0.
+                    // count) appended to the pending word.  e == 0 (no such code at all) has cnt == 0.
                     const uint32_t cnt = e >> 29, tl = (e >> 25) & 15u;
                     if (cnt == 0u || op + cnt > cap) { live = false; break; }
                     const uint32_t v = (e & 255u) | ((e >> 1) & 0xffff00u);
