@@ -1688,27 +1688,29 @@ fz_inflate_group_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, co
 //   fz_inflate_prep_kernel  one warp per code group: finds the group's first coded sub-block, parses its block header
 //                           with the general inflater and leaves the literal/length code (15 packed limits + sorted
 //                           symbols), the header's bit count and the run bit in a 656-byte descriptor;
-//   fz_inflate_lean_kernel  one CTA per code group: builds the 12-bit table from the descriptor, every lane checks that
-//                           its own header bits equal the leader's and then runs nothing but the table loop: literals
+//   fz_inflate_lean_kernel  one CTA per code group at a time: builds the 12-bit table from the descriptor, every lane checks
+//                           that its own header bits equal the leader's and then runs nothing but the table loop: literals
 //                           (1..3 per hit), distance-1 runs, and the end of block followed by the closing empty stored
-//                           block, all validated in place.  No general state machine, no canonical search: the encoder
-//                           limits its codes to FZ_MAX_CODE_BITS = FZ_GLUT_BITS.
-// Anything else -- codes longer than the table (streams of earlier encoder versions), a second coded block, a distance
-// code that is not the 1-bit run code, a parse or size error -- marks the GROUP (desc.state = 2) and the kernel above
-// decodes it again from scratch; what that one refuses goes to the general inflater, as before.
+//                           block, all validated in place.  No general state machine; the encoder gives every symbol its
+//                           sample saw a code of at most FZ_MAX_CODE_BITS = FZ_GLUT_BITS bits, the rare longer ones are
+//                           turned into a table entry on the spot (fz_lean_long_entry).
+// Anything else -- a second coded block, a distance code that is not the 1-bit run code, a parse or size error -- marks
+// the GROUP (desc.state = 2) and the kernel above decodes it again from scratch; what that one refuses goes to the general
+// inflater, as before.
 // =================================================================================================
 
 __global__ void __launch_bounds__(FZ_WARP)
 fz_inflate_prep_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const unsigned long long *__restrict__ stream_off,
                        const uint32_t *__restrict__ stream_cnt, uint32_t hits_per_stream, const uint32_t *__restrict__ hits,
-                       const uint32_t *__restrict__ stream_mode, FzGroupDesc *__restrict__ desc, const uint8_t *planes,
-                       const FzStatus *status)
+                       const uint32_t *__restrict__ stream_mode, FzGroupDesc *__restrict__ desc, uint32_t *__restrict__ qctr,
+                       const uint8_t *planes, const FzStatus *status)
 {
     __shared__ uint16_t tabs[FZ_INF_TAB_U16];
     __shared__ FzCode codes[2];
     __shared__ uint32_t res[4];
     const int lane = threadIdx.x;
     FzGroupDesc *d = desc + blockIdx.x;
+    if (blockIdx.x == 0) for (uint32_t i = lane; i < FZ_SM_COUNT; i += FZ_WARP) qctr[i] = 0;   // the lean kernel's work queues
     const uint32_t cps = fz_groups_per_stream(g);
     const uint32_t s = blockIdx.x / cps, ck = blockIdx.x - s * cps;
     const uint32_t m = stream_cnt[s];
@@ -1778,6 +1780,7 @@ struct FzLeanSmem {
     alignas(16) uint32_t lut[FZ_GLUT_SIZE];
     alignas(16) uint32_t ring[FZ_INF_WARPS * FZ_WARP * FZ_LEAN_ROW_WORDS];   // every lane's window on its fragment (cp.async)
     alignas(16) uint32_t code[FZ_DESC_CODE_WORDS];                           // FzCode LL, pad, 288 sorted symbols
+    uint32_t item, pad[3];                                                   // the code group the CTA works on
 };
 static_assert(sizeof(FzLeanSmem) + 1024 <= (227 * 1024) / FZ_LEAN_MINBLOCKS, "shared memory of FZ_LEAN_MINBLOCKS CTAs per SM");
 
@@ -1802,21 +1805,13 @@ __device__ __forceinline__ uint32_t fz_peek32(const uint32_t *b32, uint32_t nw, 
     return __funnelshift_r(w0, w1, pos & 31u);
 }
 
-__global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP, FZ_LEAN_MINBLOCKS)
-fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const unsigned long long *__restrict__ stream_off,
-                       const uint32_t *__restrict__ stream_cnt, uint32_t hits_per_stream, const uint32_t *__restrict__ hits,
-                       FzGroupDesc *__restrict__ desc, uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes)
+// one code group (stream s, group ck of the stream), all threads of the CTA
+__device__ __forceinline__ void
+fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *d, const uint8_t *__restrict__ container,
+              const FzBatchGeom &g, const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ stream_cnt,
+              uint32_t hits_per_stream, const uint32_t *__restrict__ hits, uint32_t *__restrict__ zero_flags,
+              uint8_t *__restrict__ planes)
 {
-    extern __shared__ __align__(16) uint8_t fz_smem[];
-    FzLeanSmem *sm = (FzLeanSmem *)fz_smem;
-    // CTAs in PLANE-major order: the code groups of one byte plane cost about the same and those of another plane may
-    // cost nothing (RAW, all zero), so consecutive CTAs -- which the block scheduler deals round the SMs -- are alike
-    // and every SM gets its share of the expensive ones (chunk-major order left some SMs with 6 of them, others with 2)
-    const uint32_t cps = fz_groups_per_stream(g);
-    const uint32_t q = blockIdx.x / cps, ck = blockIdx.x - q * cps;
-    const uint32_t s = (q % g.nchunks) * FZ_PLANES + q / g.nchunks;
-    FzGroupDesc *d = desc + (size_t)s * cps + ck;
-    if (d->state != 1u) return;                           // CTA-uniform (covers a raised error and streams of other kinds)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t m = stream_cnt[s];
     const size_t h0 = (size_t)s * hits_per_stream;
@@ -2074,6 +2069,7 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
             }
         }
 #undef FZ_LEAN_WORD_DONE
+        fz_cp_async_wait<0>();   // nothing of this group may still be landing in the ring when the CTA's next group fills it
     }
     if (coded && !failed && !all_zero) {
         if (done_ok) {
@@ -2088,6 +2084,54 @@ fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
         } else failed = true;
     }
     if (failed) d->state = 2u;    // the full group kernel decodes this group again
+}
+
+// Work distribution.  A code group of a compressible plane keeps its CTA busy for about as long as the whole kernel
+// runs (128 threads x 16 KiB, one symbol chain each), groups of RAW or all-zero planes cost nothing, and a 4 GiB volume
+// has only 3.5 expensive groups per SM and coded plane: where they land decides the kernel's time.  Left to the block
+// scheduler (one CTA per group) some SMs held 6 or 7 of them and others none.  So the grid is FZ_LEAN_MINBLOCKS resident
+// CTAs per SM and the groups are dealt by hand: in PLANE-major order (groups of one plane cost the same) item i belongs
+// to SM i mod 148, whose CTAs take them one after the other from the SM's counter; a CTA whose SM has nothing left helps
+// itself from the other SMs' queues, so any placement of the CTAs works.
+__device__ __forceinline__ uint32_t fz_lean_pull(uint32_t *qctr, uint32_t nitems, const FzGroupDesc *desc, const FzBatchGeom &g,
+                                                 uint32_t cps)
+{
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    smid %= FZ_SM_COUNT;
+    for (uint32_t v = 0; v < FZ_SM_COUNT; v++) {
+        const uint32_t j = smid + v >= FZ_SM_COUNT ? smid + v - FZ_SM_COUNT : smid + v;
+        for (;;) {
+            if (*(volatile uint32_t *)(qctr + j) * FZ_SM_COUNT + j >= nitems) break;   // (a look before the atomic: nothing left there)
+            const uint32_t i = atomicAdd(qctr + j, 1u) * FZ_SM_COUNT + j;
+            if (i >= nitems) break;
+            const uint32_t q = i / cps, ck = i - q * cps;
+            const uint32_t s = (q % g.nchunks) * FZ_PLANES + q / g.nchunks;
+            if (desc[(size_t)s * cps + ck].state == 1u) return i;                       // everything else is not the lean kernel's
+        }
+    }
+    return ~0u;
+}
+
+__global__ void __launch_bounds__(FZ_INF_WARPS * FZ_WARP, FZ_LEAN_MINBLOCKS)
+fz_inflate_lean_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const unsigned long long *__restrict__ stream_off,
+                       const uint32_t *__restrict__ stream_cnt, uint32_t hits_per_stream, const uint32_t *__restrict__ hits,
+                       FzGroupDesc *__restrict__ desc, uint32_t *__restrict__ qctr, uint32_t nitems,
+                       uint32_t *__restrict__ zero_flags, uint8_t *__restrict__ planes)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    FzLeanSmem *sm = (FzLeanSmem *)fz_smem;
+    const uint32_t cps = fz_groups_per_stream(g);
+    for (;;) {
+        __syncthreads();                                  // the previous group's table and ring are done with
+        if (threadIdx.x == 0) sm->item = fz_lean_pull(qctr, nitems, desc, g, cps);
+        __syncthreads();
+        const uint32_t i = sm->item;
+        if (i == ~0u) break;
+        const uint32_t q = i / cps, ck = i - q * cps;
+        const uint32_t s = (q % g.nchunks) * FZ_PLANES + q / g.nchunks;
+        fz_lean_group(sm, s, ck, desc + (size_t)s * cps + ck, container, g, stream_off, stream_cnt, hits_per_stream, hits, zero_flags, planes);
+    }
 }
 
 // ---- general path: one thread per stream (reference-made streams: back-to-back blocks, no byte alignment between them)
@@ -2436,7 +2480,7 @@ fz_rawcopy_kernel(const uint8_t *__restrict__ container, uint64_t container_size
 
 size_t fz_group_desc_bytes(uint32_t nstreams, uint32_t nsub_full)
 {
-    return (size_t)nstreams * ((nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS) * sizeof(FzGroupDesc);
+    return (size_t)nstreams * ((nsub_full + FZ_CODE_SUBS - 1) / FZ_CODE_SUBS) * sizeof(FzGroupDesc) + FZ_SM_COUNT * 4u + 16u;
 }
 
 void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatchGeom g, const uint32_t *stream_hdr,
@@ -2460,11 +2504,13 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     // word is an L2 round trip.  164 KB of shared memory (4 CTAs of 37 KB) and 92 KB of L1 beat 228 KB / 6 CTAs by
     // 20-25 % on every input measured (sweep in profiles/README.md).
     FzGroupDesc *desc = (FzGroupDesc *)b.group_desc;
-    fz_inflate_prep_kernel<<<ncode, FZ_WARP, 0, st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, desc, planes, status);
+    uint32_t *qctr = (uint32_t *)(desc + ncode);             // FZ_SM_COUNT work-queue counters behind the descriptors
+    fz_inflate_prep_kernel<<<ncode, FZ_WARP, 0, st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, desc, qctr, planes, status);
     cudaFuncSetAttribute(fz_inflate_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(fz_inflate_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzLeanSmem));
-    fz_inflate_lean_kernel<<<ncode, FZ_INF_WARPS * FZ_WARP, sizeof(FzLeanSmem), st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits,
-                                                                                     desc, zf, planes);
+    const uint32_t nlean = ncode < FZ_SM_COUNT * FZ_LEAN_MINBLOCKS ? ncode : FZ_SM_COUNT * FZ_LEAN_MINBLOCKS;
+    fz_inflate_lean_kernel<<<nlean, FZ_INF_WARPS * FZ_WARP, sizeof(FzLeanSmem), st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits,
+                                                                                     desc, qctr, ncode, zf, planes);
     // groups the lean kernel does not take or gave up on (desc.state == 2): the full inflater, one warp per 32 sub-blocks
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FZ_INF_CARVEOUT_PCT);
     cudaFuncSetAttribute(fz_inflate_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzGroupSmem));
