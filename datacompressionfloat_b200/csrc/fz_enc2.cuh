@@ -107,13 +107,20 @@ FZ_HD uint32_t fz_warp_incl_sum(const W &w, uint32_t v)
 // Token rule (sequential definition; seq_tokens in tests/hostmodel restates it quad by quad):
 //   the sub-block is cut into aligned quads of 4 bytes.  E[q] = the four bytes of quad q all equal the byte before
 //   them (E = 0 for the first quad, which has no byte before it, and for a ragged last quad of fewer than 4 bytes).
-//   Quad q is HELD iff E[q] and E[q-1]: its bytes continue a run that is at least 5 bytes long already.  Every byte
-//   outside a held quad is a literal.  A maximal run of held quads leaves as distance-1 matches: with m the bytes of
+//   Quad q is HELD iff E[q], E[q-1] and E[q-2] (FZ_E2_LEAD_QUADS = 2 quads of lead): its bytes continue a run that is at
+//   least 9 bytes long already.  Every byte outside a held quad is a literal.  (One quad of lead -- E[q] and E[q-1] --
+//   was the first rule: on exponent and count planes, where a byte repeats its neighbour with p = 0.45, it turned 4 % of
+//   the quads into 4..8-byte matches that save no bits over 1..2-bit literals but made a quarter of the inflater's
+//   instructions, executed by 1.5 lanes of 32; with two quads of lead such data has no matches at all, long runs --
+//   zero planes, flat regions -- keep theirs.)  A maximal run of held quads leaves as distance-1 matches: with m the bytes of
 //   the run not yet emitted, every held quad adds 4 to m and a match of 258 leaves at the quad where m reaches 258
 //   (m -= 258); at the last quad of the run the rest leaves, as a match for m >= 3, as m literals for m = 1, 2.
 //   Tokens leave in byte order.
 // (The first encoder withheld bytes one by one; quads make a lane's output uniform slots, cost nothing measurable on
 //  float planes, and let an inflater copy runs as whole words.)
+#ifndef FZ_E2_LEAD_QUADS
+#define FZ_E2_LEAD_QUADS 2     // all-equal quads in front of a held quad
+#endif
 #define FZ_E2_LQ 8             // quads per lane and step
 #define FZ_E2_LB (4u * FZ_E2_LQ)        // bytes per lane and step
 #define FZ_E2_STEP (32u * FZ_E2_LB)     // bytes per warp and step
@@ -124,7 +131,7 @@ struct FzLaneQuads { uint32_t w[FZ_E2_LQ]; };
 // what the warp carries from step to step (the same value in every lane)
 struct FzTokCarry {
     uint32_t prev;     // last byte of the step before; 0x100 = none (start of the sub-block)
-    uint32_t prevE;    // E of its last quad
+    uint32_t prevE;    // E of its last two quads (bit 1 = the last one)
     uint32_t m;        // bytes of the current run not yet emitted (0..257)
     FZ_HD void init() { prev = 0x100u; prevE = 0; m = 0; }
 };
@@ -197,16 +204,21 @@ FZ_HD bool fz_tok_step(const W &w, const FzLaneQuads &v, uint32_t nv, FzTokCarry
 #pragma unroll
     for (int g = 1; g < FZ_E2_LQ; g++) E |= (v.w[g] == fz_splat_top_byte(v.w[g - 1]) ? 1u : 0u) << g;
     E &= (1u << (nv >> 2)) - 1u;                     // whole quads only
-    uint32_t pE = w.shfl_up(E >> (FZ_E2_LQ - 1), 1);
+    // pE: E of the two quads before quad 0 (bit 1 = the last quad of the lane before, bit 0 = the one before that)
+    uint32_t pE = w.shfl_up((E >> (FZ_E2_LQ - 2)) & 3u, 1);
     if (lane == 0) pE = c.prevE;
-    const uint32_t hq = E & ((E << 1) | pE);
+#if FZ_E2_LEAD_QUADS == 2
+    const uint32_t hq = E & ((E << 1) | (pE >> 1)) & ((E << 2) | pE);
+#else
+    const uint32_t hq = E & ((E << 1) | (pE >> 1));
+#endif
     t.hq = hq;
     t.m_in = 0;
     t.pb = pb & 0xffu;
     const uint32_t anyh = w.ballot(hq != 0);
     const uint32_t m0 = c.m;
     c.prev = w.shfl(lastb, 31);
-    c.prevE = w.shfl(E >> (FZ_E2_LQ - 1), 31);
+    c.prevE = w.shfl((E >> (FZ_E2_LQ - 2)) & 3u, 31);
     if (anyh == 0 && m0 == 0) return false;
     // ---- runs.  A lane "passes" when all of its quads are held: the run goes through it.
     const bool passes = hq == FZ_E2_LQ_MASK;

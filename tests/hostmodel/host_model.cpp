@@ -72,7 +72,7 @@ void seq_tokens(const uint8_t *p, uint32_t n, Lit &&lit, Match &&match)
 {
     // the quad rule of fz_enc2.cuh, one quad after the other
     uint32_t m = 0, runb = 0;
-    bool prevE = false;
+    bool prevE = false, prevE2 = false;
     auto rest = [&]() {
         if (m >= FZ_MIN_MATCH) match(m); else for (uint32_t i = 0; i < m; i++) lit(runb);
         m = 0;
@@ -81,7 +81,7 @@ void seq_tokens(const uint8_t *p, uint32_t n, Lit &&lit, Match &&match)
         const uint32_t nb = n - q0 < 4 ? n - q0 : 4;
         bool E = nb == 4 && q0 > 0;
         for (uint32_t i = 0; E && i < 4; i++) E = p[q0 + i] == p[q0 + i - 1];
-        if (E && prevE) {
+        if (E && prevE && (FZ_E2_LEAD_QUADS < 2 || prevE2)) {
             runb = p[q0];
             m += 4;
             if (m >= FZ_MAX_MATCH) { match(FZ_MAX_MATCH); m -= FZ_MAX_MATCH; }
@@ -89,6 +89,7 @@ void seq_tokens(const uint8_t *p, uint32_t n, Lit &&lit, Match &&match)
             if (m) rest();
             for (uint32_t i = 0; i < nb; i++) lit(p[q0 + i]);
         }
+        prevE2 = prevE;
         prevE = E;
     }
     if (m) rest();
