@@ -77,6 +77,10 @@ class Codec:
     def set_variant(self, split: int = 0, merge: int = 0):
         check(self._L.mzb_set_variant(self._h, split, merge), "mzb_set_variant")
 
+    def set_inflate_variant(self, v: int = 0):
+        """0: lean table-loop inflater first (default); 1: the full group inflater alone (its fallback)."""
+        check(self._L.mzb_set_inflate_variant(self._h, v), "mzb_set_inflate_variant")
+
     def set_batch_chunks(self, n: int):
         check(self._L.mzb_set_batch_chunks(self._h, n), "mzb_set_batch_chunks")
 

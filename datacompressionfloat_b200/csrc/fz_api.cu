@@ -50,7 +50,7 @@ struct mzb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint32_t batch_chunks = 192;  // 4.5 GiB of input per kernel batch: one batch for a 1024^3 volume
-    int split_variant = 0, merge_variant = 0;
+    int split_variant = 0, merge_variant = 0, inflate_variant = 0;
     DevBuf planes, scratch, sizes, sub_off, stream_hdr, stream_off, stream_mode, stream_fail;
     DevBuf tile_cnt, block_sums, hits, io_in, io_out, ghist, gcodes, blockpar, zero_flags, zero_hist, err_partial, chunk_tab, group_desc;
     bool zero_hist_ready = false;
@@ -248,6 +248,13 @@ extern "C" int mzb_set_variant(mzb_ctx *c, int split_variant, int merge_variant)
     return MZB_OK;
 }
 
+extern "C" int mzb_set_inflate_variant(mzb_ctx *c, int variant)
+{
+    if (!c || variant < 0 || variant > 1) return MZB_E_ARG;
+    c->inflate_variant = variant;
+    return MZB_OK;
+}
+
 extern "C" size_t mzb_compress_bound(uint64_t nwords, uint32_t chk)
 {
     if (chk == 0) return 0;
@@ -361,12 +368,21 @@ static void compress_enqueue_batch(mzb_ctx *c, const uint32_t *d_words, uint64_t
 {
     const FzBatchGeom g = make_geom(nb, chk, nw, pstride);
     __atomic_fetch_add(&g_passes[0], 1ull, __ATOMIC_RELAXED);
-    fz_launch_split(d_words, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream);
-    prof_mark(c, FZ_ST_SPLIT);
-    if (!c->zero_hist_ready) { fz_launch_zero_hist((uint32_t *)c->zero_hist.p, c->stream); c->zero_hist_ready = true; }
     uint32_t zero_planes = 0;
     for (int j = 0; j < FZ_PLANES; j++)
         if (((mask >> (8 * j)) & 0xffu) == 0) zero_planes |= 1u << j;
+    // Planes the mask erases are not even written where the histogram kernel flags whole sub-blocks all-zero without
+    // reading them (full sub-blocks behind the exempt words; sub-block starts are multiples of FZ_SUB in the batch when
+    // the chunk size is): 1 GiB of stores less per erased plane and 4 GiB volume.
+    uint64_t skip_lo = 0, skip_hi = 0;
+    if (zero_planes && chk % FZ_SUB == 0 && c->split_variant == 0) {
+        skip_lo = (exempt + FZ_SUB - 1) / FZ_SUB * FZ_SUB;
+        skip_hi = nw / FZ_SUB * FZ_SUB;
+    }
+    fz_launch_split(d_words, nw, mask, exempt, (uint8_t *)c->planes.p, pstride, c->split_variant, c->stream,
+                    skip_hi > skip_lo ? zero_planes : 0u, skip_lo, skip_hi);
+    prof_mark(c, FZ_ST_SPLIT);
+    if (!c->zero_hist_ready) { fz_launch_zero_hist((uint32_t *)c->zero_hist.p, c->stream); c->zero_hist_ready = true; }
     fz_launch_encode((const uint8_t *)c->planes.p, g, (uint32_t *)c->ghist.p, c->gcodes.p, (uint8_t *)c->scratch.p,
                      (uint32_t *)c->sizes.p, (const uint32_t *)c->zero_hist.p, zero_planes, exempt, c->d_status, c->stream);
     prof_mark(c, FZ_ST_ENCODE);
@@ -397,6 +413,7 @@ static int decompress_reserve(mzb_ctx *c, uint32_t bmax, uint32_t chk, uint64_t 
         (rc = ensure(c->group_desc, fz_group_desc_bytes(nstreams, nsub_full))))
         return rc;
     ib->group_desc = c->group_desc.p;
+    ib->full_only = c->inflate_variant == 1;
     ib->zero_flags = (uint32_t *)c->zero_flags.p;
     ib->bp = fz_blockpar_carve(c->blockpar.p, nstreams, chk);
     ib->tile_cnt = (uint32_t *)c->tile_cnt.p;

@@ -106,7 +106,7 @@ __device__ __forceinline__ void fz_warp_copy(uint8_t *dst, const uint8_t *src, u
 // store instruction covers one full 128-byte line.
 __global__ void __launch_bounds__(FZ_SPLIT_THREADS)
 fz_split_kernel_v0(const uint4 *__restrict__ words4, uint64_t nvec, uint32_t mask, uint64_t exempt,
-                   uint8_t *__restrict__ planes, uint64_t plane_stride)
+                   uint8_t *__restrict__ planes, uint64_t plane_stride, uint32_t skip_planes, uint64_t skip_lo, uint64_t skip_hi)
 {
     const uint64_t base = (uint64_t)blockIdx.x * (FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL) + threadIdx.x;
     uint4 v[FZ_SPLIT_UNROLL];
@@ -132,7 +132,13 @@ fz_split_kernel_v0(const uint4 *__restrict__ words4, uint64_t nvec, uint32_t mas
             }
             uint32_t a, b, c, d;
             fz_transpose4(w.x, w.y, w.z, w.w, a, b, c, d);
-            p0[i] = a; p1[i] = b; p2[i] = c; p3[i] = d;
+            // planes the mask erases entirely are not written where the encoder will not read them: whole sub-blocks
+            // behind the exempt header words (fz_hist2_kernel flags those all-zero without a look)
+            const uint32_t sk = (wi >= skip_lo && wi < skip_hi) ? skip_planes : 0u;
+            if (!(sk & 1u)) p0[i] = a;
+            if (!(sk & 2u)) p1[i] = b;
+            if (!(sk & 4u)) p2[i] = c;
+            if (!(sk & 8u)) p3[i] = d;
         }
     }
 }
@@ -230,7 +236,7 @@ __global__ void fz_split_tail_kernel(const uint32_t *__restrict__ words, uint64_
 }
 
 void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint64_t exempt_words, uint8_t *planes,
-                     uint64_t plane_stride, int variant, cudaStream_t st)
+                     uint64_t plane_stride, int variant, cudaStream_t st, uint32_t skip_planes, uint64_t skip_lo, uint64_t skip_hi)
 {
     const uint64_t nvec = nwords / 4;
     if (nvec) {
@@ -241,7 +247,8 @@ void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint
         } else {
             const uint64_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
             const unsigned grid = (unsigned)((nvec + per - 1) / per);
-            fz_split_kernel_v0<<<grid, FZ_SPLIT_THREADS, 0, st>>>((const uint4 *)words, nvec, mask, exempt_words, planes, plane_stride);
+            fz_split_kernel_v0<<<grid, FZ_SPLIT_THREADS, 0, st>>>((const uint4 *)words, nvec, mask, exempt_words, planes, plane_stride,
+                                                                  skip_planes, skip_lo, skip_hi);
         }
     }
     if (nwords & 3) fz_split_tail_kernel<<<1, 4, 0, st>>>(words, nvec * 4, nwords, mask, exempt_words, planes, plane_stride);
@@ -1703,7 +1710,7 @@ __global__ void __launch_bounds__(FZ_WARP)
 fz_inflate_prep_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const unsigned long long *__restrict__ stream_off,
                        const uint32_t *__restrict__ stream_cnt, uint32_t hits_per_stream, const uint32_t *__restrict__ hits,
                        const uint32_t *__restrict__ stream_mode, FzGroupDesc *__restrict__ desc, uint32_t *__restrict__ qctr,
-                       const uint8_t *planes, const FzStatus *status)
+                       const uint8_t *planes, uint32_t full_only, const FzStatus *status)
 {
     __shared__ uint16_t tabs[FZ_INF_TAB_U16];
     __shared__ FzCode codes[2];
@@ -1733,7 +1740,7 @@ fz_inflate_prep_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, con
         if (mask && leader == ~0u) leader = ck * FZ_CODE_SUBS + j * FZ_WARP + (uint32_t)(__ffs((int)mask) - 1);
     }
     if (lane == 0) {
-        uint32_t state = 1, hdr_bits = 0, run_bit = 2;
+        uint32_t state = full_only ? 2u : 1u, hdr_bits = 0, run_bit = 2;
         const uintptr_t o = (uintptr_t)(planes + (uint64_t)(s & 3) * g.plane_stride + (uint64_t)(s >> 2) * g.chk);
         if (o & 15u) state = 2;                                   // the lean writer stores 16 bytes at a time
         if (leader != ~0u && state == 1u) {
@@ -2505,7 +2512,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     // 20-25 % on every input measured (sweep in profiles/README.md).
     FzGroupDesc *desc = (FzGroupDesc *)b.group_desc;
     uint32_t *qctr = (uint32_t *)(desc + ncode);             // FZ_SM_COUNT work-queue counters behind the descriptors
-    fz_inflate_prep_kernel<<<ncode, FZ_WARP, 0, st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, desc, qctr, planes, status);
+    fz_inflate_prep_kernel<<<ncode, FZ_WARP, 0, st>>>(container, g, stream_off, b.stream_cnt, b.hits_per_stream, b.hits, b.stream_mode, desc, qctr, planes, b.full_only ? 1u : 0u, status);
     cudaFuncSetAttribute(fz_inflate_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(fz_inflate_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FzLeanSmem));
     const uint32_t nlean = ncode < FZ_SM_COUNT * FZ_LEAN_MINBLOCKS ? ncode : FZ_SM_COUNT * FZ_LEAN_MINBLOCKS;

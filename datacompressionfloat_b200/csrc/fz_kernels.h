@@ -42,8 +42,11 @@ enum {
 };
 
 // ---- mask + byte-plane split / merge (HBM-bound)
+// skip_planes (variant 0 only): bit j = byte plane j is not written for words in [skip_lo, skip_hi) -- the caller knows
+// the mask erases that plane and that nothing reads those bytes (whole sub-blocks the encoder flags all-zero unseen)
 void fz_launch_split(const uint32_t *words, uint64_t nwords, uint32_t mask, uint64_t exempt_words,
-                     uint8_t *planes, uint64_t plane_stride, int variant, cudaStream_t st);
+                     uint8_t *planes, uint64_t plane_stride, int variant, cudaStream_t st,
+                     uint32_t skip_planes = 0, uint64_t skip_lo = 0, uint64_t skip_hi = 0);
 void fz_launch_merge(const uint8_t *planes, uint64_t plane_stride, uint64_t nwords, uint32_t *words,
                      int variant, cudaStream_t st);
 // the split of a batch of chunk slots with a per-chunk exemption table (several small files in one batch; chk % 4 == 0)
@@ -107,6 +110,7 @@ struct FzInflateBufs {
     uint32_t *zero_flags;    // [nstreams * nsub_full] 1 = the sub-block is all zero bytes and was NOT written to the plane buffer
     uint32_t tiles_per_stream;
     void *group_desc;        // [fz_group_desc_bytes()] one descriptor per code group: what the header pass leaves for the lean inflater
+    bool full_only;          // tests: every group goes to the full group inflater (the lean kernel's fallback)
     FzBlockParBufs bp;
 };
 size_t fz_group_desc_bytes(uint32_t nstreams, uint32_t nsub_full);

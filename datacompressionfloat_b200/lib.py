@@ -53,7 +53,7 @@ EXPORTS = [
     "init_context", "reset_context", "update_context", "print_context_info", "init_mrczip_header",
     "read_mrczip_header", "write_mrczip_header", "print_mrczip_header", "get_file_size", "now_sec",
     "isTestThroughput",
-    "mzb_create", "mzb_create_on_stream", "mzb_destroy", "mzb_set_io_threads", "mzb_pass_counts", "mzb_compress_host_many", "mzb_decompress_host_many", "mzb_device_count", "mzb_set_devices", "mzb_mrc_parse", "mzb_set_mrc_aware", "mzb_error_report_device", "mzb_error_report_host", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_compress_bound",
+    "mzb_create", "mzb_create_on_stream", "mzb_destroy", "mzb_set_io_threads", "mzb_pass_counts", "mzb_compress_host_many", "mzb_decompress_host_many", "mzb_device_count", "mzb_set_devices", "mzb_mrc_parse", "mzb_set_mrc_aware", "mzb_error_report_device", "mzb_error_report_host", "mzb_set_batch_chunks", "mzb_set_variant", "mzb_set_inflate_variant", "mzb_compress_bound",
     "mzb_compress_device", "mzb_decompress_device", "mzb_mask_split_device", "mzb_merge_device",
     "mzb_compress_host", "mzb_decompress_host", "mzb_host_alloc", "mzb_host_free", "mzb_last_stats",
     "mzb_set_profiling", "mzb_stage_count", "mzb_stage_name", "mzb_stage_ms",
@@ -93,6 +93,8 @@ def load():
     L.mzb_set_batch_chunks.argtypes = [vp, u32]
     L.mzb_set_variant.restype = i32
     L.mzb_set_variant.argtypes = [vp, i32, i32]
+    L.mzb_set_inflate_variant.restype = i32
+    L.mzb_set_inflate_variant.argtypes = [vp, i32]
     L.mzb_compress_bound.restype = sz
     L.mzb_compress_bound.argtypes = [u64, u32]
     L.mzb_compress_device.restype = i32

@@ -121,6 +121,9 @@ void mzb_destroy(mzb_ctx *ctx);
 int mzb_set_batch_chunks(mzb_ctx *ctx, uint32_t chunks);
 /* kernel variant selectors used by the benchmarks (0 = default) */
 int mzb_set_variant(mzb_ctx *ctx, int split_variant, int merge_variant);
+/* inflater of our own streams: 0 = the lean table-loop kernel with the full group kernel behind it (default), 1 = the
+ * full group kernel alone (what decodes a code group the lean kernel gives up on; the tests run both) */
+int mzb_set_inflate_variant(mzb_ctx *ctx, int variant);
 
 /* CUDA devices visible to the process (0 without a driver / device). */
 int mzb_device_count(void);

@@ -317,6 +317,53 @@ def test_roundtrip_equals_erasebytes_all_bits(codec, oracle, bits):
     assert codec.stats()["general_streams"] == 0 and codec.stats()["fast_failed"] == 0   # own streams: sub-block path
 
 
+@pytest.mark.parametrize("kind,bits,chk", [("G", 8, 1 << 20), ("P", 0, 1 << 20), ("S", 12, 1 << 20), ("Z", 3, 1 << 20), ("R", 5, 1 << 20),
+                                           ("S", 4, 65536), ("P", 1, 1000)])
+def test_lean_and_full_group_inflaters_agree(codec, oracle, kind, bits, chk):
+    """Our own streams are decoded by the lean table-loop kernel (fz_inflate_lean_kernel); the full group kernel behind it
+    decodes whatever code group the lean one gives up on.  Both must produce the erasebytes bytes, flag the same all-zero
+    sub-blocks for the merge, and neither may need the serial inflater."""
+    w = synth_words(kind, 5 * (1 << 19) + 777)        # several code groups per stream, ragged last chunk and sub-block
+    want = oracle.erasebytes(w.view(np.uint8), bits)
+    cont = codec.compress(dev(w), bits, chk=chk)
+    try:
+        for variant in (0, 1, 0):
+            codec.set_inflate_variant(variant)
+            back = codec.decompress(cont)
+            assert np.array_equal(host_u32(back).view(np.uint8), want), (kind, bits, variant)
+            st = codec.stats()
+            assert st["general_streams"] == 0 and st["fast_failed"] == 0, (variant, st)
+    finally:
+        codec.set_inflate_variant(0)
+
+
+def test_lean_inflater_decodes_codes_longer_than_its_table(codec, oracle):
+    """Symbols the encoder's histogram sample never saw keep 13..15-bit codes (fz_ph_lengths, two tiers); when one of them
+    does occur the lean kernel turns it into a table entry on the spot (fz_lean_long_entry).  Bytes that appear ONLY in
+    sub-blocks the sample skips (it takes every fourth sub-block of a group) are such symbols."""
+    rng = np.random.default_rng(5)
+    n = 1 << 20                                        # one plane stream of 64 sub-blocks
+    plane = rng.choice(np.array([1, 2, 3, 4], np.uint8), n, p=[.4, .3, .2, .1])
+    for k in range(n // 16384):
+        if k % 4:                                      # not sampled: sprinkle values nobody counted
+            idx = rng.integers(0, 16384, 40) + k * 16384
+            plane[idx] = rng.integers(100, 250, 40).astype(np.uint8)
+    w = np.zeros(256 + n, np.uint32)
+    w[:256] = synth_words("Z", 4)[:256]
+    w[256:] = plane.astype(np.uint32) << 24
+    cont = codec.compress(dev(w), 0, chk=1 << 20)
+    assert np.array_equal(oracle.decompress(cont.cpu().numpy()), w.view(np.uint8))      # valid deflate for the reference
+    try:
+        for variant in (0, 1):
+            codec.set_inflate_variant(variant)
+            back = codec.decompress(cont)
+            assert np.array_equal(host_u32(back), w), variant
+            st = codec.stats()
+            assert st["general_streams"] == 0 and st["fast_failed"] == 0, (variant, st)
+    finally:
+        codec.set_inflate_variant(0)
+
+
 @pytest.mark.parametrize("nwords", [1, 2, 255, 256, 257, 4095, 4096, 4097, 16384, 16385, 65536 * 2, 65536 * 2 + 1])
 @pytest.mark.parametrize("chk", [4096, 1000])
 def test_roundtrip_edge_sizes(codec, oracle, nwords, chk):
