@@ -353,7 +353,7 @@ def touched_bytes(nb, out_bytes, cs, bits):
     payload_scanned = max(out_bytes - raw_bytes, 0)
     stored_nonraw = max(stored_sub * SUB - raw_bytes, 0)
     return {
-        "split": 2 * nb,
+        "split": nb + nb * (4 - min(bits // 8, 4)) / 4,   # byte planes the mask erases are not written (nor read again)
         "encode": stored_sub * 2048 + coded_sub * (2048 + SUB / 4 + SUB) + zero_sub * (0 if known_zero else 2048 + SUB) + coded_out,
         "gather": 2 * out_bytes,
         "markers": payload_scanned,

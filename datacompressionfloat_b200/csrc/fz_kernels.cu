@@ -347,6 +347,14 @@ __device__ __forceinline__ uint32_t fz_ld_u32_unaligned(const uint8_t *src, uint
     return __funnelshift_r(w0, w1, sk * 8);
 }
 
+// one 256-bit store (32-byte aligned address)
+__device__ __forceinline__ void fz_st256(void *p, uint4 a, uint4 b)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                 "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // chunks whose reads are mostly unaligned RAW payloads (two or more RAW planes) go to the 16-words-per-thread kernel
 __device__ __forceinline__ bool fz_merge_wide(const uint32_t *__restrict__ stream_hdr, uint32_t c)
 {
@@ -399,12 +407,24 @@ fz_merge_streams16(const uint8_t *__restrict__ planes, const uint8_t *__restrict
                 p[j] = fz_funnel16(A, B, sh);
             }
         }
-        uint4 w;
+        uint4 w, x;
         uint4 *o4 = (uint4 *)(out + w0);
-        fz_transpose4(p[0].x, p[1].x, p[2].x, p[3].x, w.x, w.y, w.z, w.w); o4[0] = w;
-        fz_transpose4(p[0].y, p[1].y, p[2].y, p[3].y, w.x, w.y, w.z, w.w); o4[1] = w;
-        fz_transpose4(p[0].z, p[1].z, p[2].z, p[3].z, w.x, w.y, w.z, w.w); o4[2] = w;
-        fz_transpose4(p[0].w, p[1].w, p[2].w, p[3].w, w.x, w.y, w.z, w.w); o4[3] = w;
+        if (((uintptr_t)o4 & 31u) == 0) {
+            // two 256-bit stores (sm_100: STG.256): every store instruction writes whole 32-byte sectors.  With four
+            // 128-bit stores per thread each sector was written in two halves by two instructions: twice the write
+            // requests on the way to L2 (ncu: lg_throttle was the second stall reason of this kernel).
+            fz_transpose4(p[0].x, p[1].x, p[2].x, p[3].x, w.x, w.y, w.z, w.w);
+            fz_transpose4(p[0].y, p[1].y, p[2].y, p[3].y, x.x, x.y, x.z, x.w);
+            fz_st256(o4, w, x);
+            fz_transpose4(p[0].z, p[1].z, p[2].z, p[3].z, w.x, w.y, w.z, w.w);
+            fz_transpose4(p[0].w, p[1].w, p[2].w, p[3].w, x.x, x.y, x.z, x.w);
+            fz_st256(o4 + 2, w, x);
+        } else {
+            fz_transpose4(p[0].x, p[1].x, p[2].x, p[3].x, w.x, w.y, w.z, w.w); o4[0] = w;
+            fz_transpose4(p[0].y, p[1].y, p[2].y, p[3].y, w.x, w.y, w.z, w.w); o4[1] = w;
+            fz_transpose4(p[0].z, p[1].z, p[2].z, p[3].z, w.x, w.y, w.z, w.w); o4[2] = w;
+            fz_transpose4(p[0].w, p[1].w, p[2].w, p[3].w, w.x, w.y, w.z, w.w); o4[3] = w;
+        }
     } else {
         for (uint32_t i = w0; i < n_c; i++) {   // the ragged end of a chunk
             uint32_t w = 0;

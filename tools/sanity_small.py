@@ -13,13 +13,16 @@ from oracle import oracle as O  # noqa: E402
 
 codec = Codec(0)
 for kind, bits, n, chk in [("G", 8, 70001, 16384), ("P", 0, 50000, 65536), ("R", 0, 40003, 16384), ("Z", 3, 33000, 1000),
-                           ("S", 12, 20000, 4096), ("G", 16, 3, 16384)]:
+                           ("S", 12, 20000, 4096), ("G", 16, 3, 16384), ("S", 12, 2300000, 1 << 21), ("P", 0, 2200000, 1 << 21)]:
     w = synth_words(kind, n)[: max(n, 1)]
     d = torch.from_numpy(w.view(np.int32)).cuda()
     cont = codec.compress(d, bits, chk=chk)
     back = codec.decompress(cont)
     gold = O.erasebytes(w.view(np.uint8), bits)
     assert np.array_equal(back.cpu().numpy().view(np.uint8), gold), (kind, bits)
+    codec.set_inflate_variant(1)          # the full group inflater alone (the lean kernel's fallback)
+    assert np.array_equal(codec.decompress(cont).cpu().numpy().view(np.uint8), gold), (kind, bits, "full")
+    codec.set_inflate_variant(0)
     assert np.array_equal(O.decompress(cont.cpu().numpy()), gold)
     ref = O.compress(w.view(np.uint8), bits, chk=chk)
     back2 = codec.decompress(torch.from_numpy(ref).cuda())
