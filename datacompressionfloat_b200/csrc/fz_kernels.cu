@@ -356,10 +356,10 @@ __device__ __forceinline__ void fz_st256(void *p, uint4 a, uint4 b)
 }
 
 // chunks whose reads are mostly unaligned RAW payloads (two or more RAW planes) go to the 16-words-per-thread kernel
-__device__ __forceinline__ bool fz_merge_wide(const uint32_t *__restrict__ stream_hdr, uint32_t c)
+__device__ __forceinline__ bool fz_merge_wide(const uint32_t *__restrict__ stream_hdr, uint32_t c, uint32_t wide_min)
 {
     const uint4 h = __ldg((const uint4 *)stream_hdr + c);
-    return ((h.x >> 31) + (h.y >> 31) + (h.z >> 31) + (h.w >> 31)) >= 2u;
+    return ((h.x >> 31) + (h.y >> 31) + (h.z >> 31) + (h.w >> 31)) >= wide_min;
 }
 
 // Chunks with two or more RAW planes, 16 words per thread: one 128-bit load per plane -- two and a funnel shift for a RAW payload, which
@@ -438,10 +438,10 @@ fz_merge_streams16(const uint8_t *__restrict__ planes, const uint8_t *__restrict
 __global__ void __launch_bounds__(FZ_SPLIT_THREADS, 8)
 fz_merge_streams_kernel(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
                         const unsigned long long *__restrict__ stream_off, const uint32_t *__restrict__ zero_flags, FzBatchGeom g,
-                        uint32_t *__restrict__ words, bool wide_split, const uint8_t *container_end)
+                        uint32_t *__restrict__ words, uint32_t wide_min, const uint8_t *container_end)
 {
     const uint32_t c = blockIdx.y;
-    if (wide_split && fz_merge_wide(stream_hdr, c)) {
+    if (fz_merge_wide(stream_hdr, c, wide_min)) {   // (wide_min 0: every chunk, 5 or more: none)
         fz_merge_streams16(planes, container, container_end, stream_hdr, stream_off, zero_flags, g, words);
         return;
     }
@@ -505,12 +505,16 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, ui
                              const unsigned long long *stream_off, const uint32_t *zero_flags, FzBatchGeom g, uint32_t *words,
                              cudaStream_t st)
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("MRCZIP_MERGE"); v = (e && atoi(e) == 1) ? 1 : 2; }   // 1: the 4-bytes-per-plane kernel (A/B runs)
+    static int v = -1, wide_min = 0;
+    if (v < 0) {
+        const char *e = getenv("MRCZIP_MERGE"), *m = getenv("MRCZIP_MERGE_WIDE_MIN");   // (A/B runs)
+        if (m && atoi(m) >= 0 && atoi(m) <= 5) wide_min = atoi(m);   // RAW planes a chunk needs for the 16-words-per-thread path (5: never)
+        v = (e && atoi(e) == 1) ? 1 : 2;   // 1: the 4-bytes-per-plane kernel only
+    }
     if (v == 1) {
         const uint32_t per = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
         dim3 grid((g.chk / 4 + per - 1) / per, g.nchunks);
-        fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words, false, container + container_size);
+        fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words, 9u, container + container_size);
         return;
     }
     // one launch: a CTA of a chunk with two or more RAW planes takes the 16-words-per-thread path, the others the
@@ -518,8 +522,8 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, ui
     // all-zero planes, 0.99 -> 1.32 ms: hence the split; two launches that each skip the other's chunks cost 0.15 ms more)
     const uint32_t per4 = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
     dim3 grid4((g.chk / 4 + per4 - 1) / per4, g.nchunks);
-    fz_merge_streams_kernel<<<grid4, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words, true,
-                                                                container + container_size);
+    fz_merge_streams_kernel<<<grid4, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words,
+                                                                (uint32_t)wide_min, container + container_size);
 }
 
 // =================================================================================================
@@ -1163,29 +1167,40 @@ __device__ __forceinline__ uint32_t fz_marker_mask(const uint8_t *base, uint32_t
 #define FZ_TILE_SLICES (FZ_TILE_BYTES / FZ_SLICE_BYTES)
 __global__ void __launch_bounds__(FZ_SCAN_THREADS)
 fz_marker_kernel(const uint8_t *__restrict__ container, const uint32_t *__restrict__ stream_hdr,
-                 const unsigned long long *__restrict__ stream_off, uint32_t tiles_per_stream, uint32_t *__restrict__ tile_state,
-                 uint32_t *__restrict__ stream_cnt, uint32_t *__restrict__ hits, uint32_t hits_per_stream, const FzStatus *status)
+                 const unsigned long long *__restrict__ stream_off, uint32_t tiles_per_stream, uint32_t ntickets,
+                 uint32_t *__restrict__ tile_state, uint32_t *__restrict__ stream_cnt, uint32_t *__restrict__ hits, uint32_t hits_per_stream,
+                 const FzStatus *status)
 {
     __shared__ uint32_t wsum[FZ_SCAN_THREADS / 32];
-    __shared__ uint32_t excl_sh;
-    // tiles are handed out in the order the blocks START (a ticket), not by blockIdx: a tile then only ever waits for
-    // tiles whose blocks are already running, whatever order the hardware dispatches blocks in
-    if (threadIdx.x == 0) excl_sh = atomicAdd(tile_state + (size_t)gridDim.x, 1u);
-    __syncthreads();
-    const uint32_t b = excl_sh;
-    __syncthreads();
-    const uint32_t s = b / tiles_per_stream, tile = b - s * tiles_per_stream;
+    __shared__ uint32_t excl_sh, tick_sh;
     if (status->error) {  // a broken chunk chain leaves the stream table undefined: touch nothing else
-        if (tile == 0 && threadIdx.x == 0) stream_cnt[s] = 0;
+        for (uint32_t s = blockIdx.x * FZ_SCAN_THREADS + threadIdx.x; s * tiles_per_stream < ntickets; s += gridDim.x * FZ_SCAN_THREADS) stream_cnt[s] = 0;
         return;
     }
+    // A persistent grid: tiles are handed out by a ticket, in order, to whichever block is free -- a tile then only ever
+    // waits (look-back) for tiles whose blocks are already running.  Most tickets are not worth a block: RAW streams are
+    // not scanned and a stream's payload ends long before its last tile slot (one block per slot spent half of this
+    // kernel's time starting and ending 61,000 blocks that had nothing to do); thread 0 passes over those on its own.
+    for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t;
+        for (;;) {
+            t = atomicAdd(tile_state + (size_t)ntickets, 1u);
+            if (t >= ntickets) { t = ~0u; break; }
+            const uint32_t s1 = t / tiles_per_stream, tile1 = t - s1 * tiles_per_stream;
+            const uint32_t h1 = stream_hdr[s1];
+            if (!((h1 & FZ_RAW_FLAG) || (uint64_t)tile1 * FZ_TILE_BYTES + 4 > (h1 & ~FZ_RAW_FLAG))) break;
+            if (tile1 == 0) stream_cnt[s1] = 0;   // (tiles behind a skipped one are skipped too: nobody looks back at it)
+        }
+        tick_sh = t;
+    }
+    __syncthreads();
+    const uint32_t b = tick_sh;
+    if (b == ~0u) return;
+    const uint32_t s = b / tiles_per_stream, tile = b - s * tiles_per_stream;
     const uint32_t h = stream_hdr[s];
     const uint32_t len = h & ~FZ_RAW_FLAG;
-    const bool skip = (h & FZ_RAW_FLAG) || (uint64_t)tile * FZ_TILE_BYTES + 4 > len;
-    if (skip) {   // (tiles behind a skipped one are skipped too: nobody looks back at it)
-        if (tile == 0 && threadIdx.x == 0) stream_cnt[s] = 0;
-        return;
-    }
     const bool last_tile = tile + 1 == tiles_per_stream || (uint64_t)(tile + 1) * FZ_TILE_BYTES + 4 > len;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *base = container + stream_off[s];
@@ -1248,6 +1263,7 @@ fz_marker_kernel(const uint8_t *__restrict__ container, const uint32_t *__restri
             }
         }
     }
+    }   // next ticket
 }
 
 // ---- classify streams: RAW, fast (our sub-block framing: one marker per sub-block, last one ends the payload), general
@@ -2517,8 +2533,9 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t ntiles = nstreams * b.tiles_per_stream;
     cudaMemsetAsync(b.tile_cnt, 0, ((size_t)ntiles + 1) * 4, st);   // look-back state of the marker scan + its ticket counter
-    fz_marker_kernel<<<ntiles, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, b.tile_cnt, b.stream_cnt, b.hits,
-                                                         b.hits_per_stream, status);
+    const uint32_t nscan = ntiles < FZ_SM_COUNT * 6u ? ntiles : FZ_SM_COUNT * 6u;   // 38 registers: 6 blocks of 256 threads per SM
+    fz_marker_kernel<<<nscan, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, ntiles, b.tile_cnt, b.stream_cnt, b.hits,
+                                                        b.hits_per_stream, status);
     if (mark) mark(mark_user, FZ_ST_MARKERS);
     cudaMemsetAsync(b.bp.ctl, 0, 64, st);
     // zero-sub-block flags only when the merge that follows reads them (copy_raw: the plain merge reads the plane buffer)
