@@ -1119,29 +1119,17 @@ void fz_launch_walk(const uint8_t *container, uint64_t container_size, FzBatchGe
 #define FZ_SLICE_BYTES 4096   // bytes the block covers per iteration (256 threads x 16 positions)
 #define FZ_SCAN_THREADS 256
 
-// the six aligned words that hold the 19 bytes [p0, p0 + 19) of the payload (zero past its end)
-struct FzMarkWin { uint32_t W[6]; };
-__device__ __forceinline__ FzMarkWin fz_marker_load(const uint8_t *base, uint32_t len, uint32_t p0)
+__device__ __forceinline__ uint32_t fz_marker_mask(const uint8_t *base, uint32_t len, uint32_t p0)
 {
-    FzMarkWin r;
-#pragma unroll
-    for (int k = 0; k < 6; k++) r.W[k] = 0;
-    if (p0 + 4 > len) return r;
+    // 16 candidate positions p0 .. p0+15; needs bytes [p0, p0+19)
+    if (p0 + 4 > len) return 0;
     const uint8_t *addr = base + p0;
     const uint32_t sk = (uint32_t)((uintptr_t)addr & 3u);
     const uint32_t *a0 = (const uint32_t *)(addr - sk);
     const uint32_t *aend = (const uint32_t *)(((uintptr_t)(base + len) + 3u) & ~(uintptr_t)3u);
+    uint32_t W[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) r.W[k] = (a0 + k) < aend ? a0[k] : 0u;
-    return r;
-}
-
-__device__ __forceinline__ uint32_t fz_marker_mask(const FzMarkWin &win, const uint8_t *base, uint32_t len, uint32_t p0)
-{
-    // 16 candidate positions p0 .. p0+15; needs bytes [p0, p0+19)
-    if (p0 + 4 > len) return 0;
-    const uint32_t sk = (uint32_t)((uintptr_t)(base + p0) & 3u);
-    const uint32_t *W = win.W;
+    for (int k = 0; k < 6; k++) W[k] = (a0 + k) < aend ? a0[k] : 0u;
     uint32_t V[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) V[k] = __funnelshift_r(W[k], W[k + 1], sk * 8);
@@ -1220,16 +1208,11 @@ fz_marker_kernel(const uint8_t *__restrict__ container, const uint32_t *__restri
 #pragma unroll
     for (int i = 0; i < FZ_TILE_SLICES / 2; i++) { mk[i] = 0; rk[i] = 0; }
     uint32_t acc = 0;  // markers found in the earlier slices of this tile
-    // the words of the next slice are asked for before this slice's barrier (a barrier orders memory accesses: left to
-    // the compiler every slice waited a full round trip to DRAM behind the one before it)
-    FzMarkWin win = fz_marker_load(base, len, tile * FZ_TILE_BYTES + threadIdx.x * 16);
 #pragma unroll
     for (uint32_t slice = 0; slice < FZ_TILE_SLICES; slice++) {
         const uint32_t q0 = tile * FZ_TILE_BYTES + slice * FZ_SLICE_BYTES;
-        const FzMarkWin cur = win;
-        if (slice + 1 < FZ_TILE_SLICES && (uint64_t)q0 + FZ_SLICE_BYTES + 4 <= len) win = fz_marker_load(base, len, q0 + FZ_SLICE_BYTES + threadIdx.x * 16);
         if ((uint64_t)q0 + 4 <= len) {   // block-uniform
-            const uint32_t m = fz_marker_mask(cur, base, len, q0 + threadIdx.x * 16);
+            const uint32_t m = fz_marker_mask(base, len, q0 + threadIdx.x * 16);
             const uint32_t cnt = __popc(m);
             if (__syncthreads_or(cnt != 0)) {   // (a slice of compressed bytes holds a marker about once in three)
                 const uint32_t inc = fz_warp_incl_scan(cnt, lane);
@@ -2550,11 +2533,7 @@ void fz_launch_inflate(const uint8_t *container, uint64_t container_size, FzBatc
     const uint32_t nstreams = g.nchunks * FZ_PLANES;
     const uint32_t ntiles = nstreams * b.tiles_per_stream;
     cudaMemsetAsync(b.tile_cnt, 0, ((size_t)ntiles + 1) * 4, st);   // look-back state of the marker scan + its ticket counter
-    static int scan_per_sm = 0;   // resident blocks per SM (registers decide: 5 of 256 threads)
-    if (scan_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_per_sm, fz_marker_kernel, FZ_SCAN_THREADS, 0) != cudaSuccess || scan_per_sm < 1) scan_per_sm = 4;
-    }
-    const uint32_t nscan = ntiles < FZ_SM_COUNT * (uint32_t)scan_per_sm ? ntiles : FZ_SM_COUNT * (uint32_t)scan_per_sm;
+    const uint32_t nscan = ntiles < FZ_SM_COUNT * 6u ? ntiles : FZ_SM_COUNT * 6u;   // 38 registers: 6 blocks of 256 threads per SM
     fz_marker_kernel<<<nscan, FZ_SCAN_THREADS, 0, st>>>(container, stream_hdr, stream_off, b.tiles_per_stream, ntiles, b.tile_cnt, b.stream_cnt, b.hits,
                                                         b.hits_per_stream, status);
     if (mark) mark(mark_user, FZ_ST_MARKERS);
