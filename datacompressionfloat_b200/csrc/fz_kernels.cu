@@ -1827,6 +1827,23 @@ struct FzLeanSmem {
 };
 static_assert(sizeof(FzLeanSmem) + 1024 <= (227 * 1024) / FZ_LEAN_MINBLOCKS, "shared memory of FZ_LEAN_MINBLOCKS CTAs per SM");
 
+// The lean kernel's table entry (the ALU pipe is what bounds the kernel: every field is where one instruction finds it):
+//   bits 28..31  code bits the entry consumes (<= 15)
+//   bits 24..25  cnt: 1..3 literals, their bytes in bits 0..23 (unused slots zero); 0: not a literal --
+//   bit  26      ... a length symbol: base length in bits 0..8, number of extra bits in bits 9..11
+//   bit  27      ... the end-of-block symbol
+//   0            no code (of <= FZ_GLUT_BITS bits) for this bit pattern
+#define FZ_LE_MATCH (1u << 26)
+#define FZ_LE_EOB (1u << 27)
+__device__ __forceinline__ uint32_t fz_lean_entry_from(uint32_t x)   // from the entry format of fz_lut_entry_bits
+{
+    if (x == 0u) return 0u;
+    const uint32_t s1 = x & 511u, tl = (x >> 25) & 15u;
+    if (s1 < 256u) return ((x & 255u) | ((x >> 1) & 0xffff00u)) | ((x >> 29) << 24) | (tl << 28);
+    if (x & FZ_LUT_MATCH) return ((x >> 9) & 511u) | (((x >> 18) & 7u) << 9) | FZ_LE_MATCH | (tl << 28);
+    return s1 == FZ_EOB ? (FZ_LE_EOB | (tl << 28)) : 0u;
+}
+
 // Table entry of a code longer than the table's index, decoded the canonical way: one symbol, its real length (<= 15)
 // in the length field.  Only symbols the encoder's sample never saw have such codes.  0 = no such code.
 __device__ __noinline__ uint32_t fz_lean_long_entry(const uint32_t *code, uint32_t bits15)
@@ -1837,7 +1854,7 @@ __device__ __noinline__ uint32_t fz_lean_long_entry(const uint32_t *code, uint32
     const uint32_t s1 = ((const uint16_t *)(code + 16))[idx];
     uint32_t ent = FZ_LUT_ENTRY(s1, 0, 0, l, 1);
     if (s1 >= 257u && s1 <= 285u) ent |= FZ_LUT_MATCH | (fz_len_base(s1 - 257u) << 9) | (fz_len_extra_bits(s1 - 257u) << 18);
-    return ent;
+    return fz_lean_entry_from(ent);
 }
 
 // 32 stream bits from bit position `pos` of the aligned words b32[0 .. nw): zero bits past the end
@@ -1866,7 +1883,7 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
         __syncthreads();
         const FzCode &LL = *(const FzCode *)sm->code;
         const FzSymTab tab{(const uint16_t *)(sm->code + 16)};
-        for (uint32_t e = threadIdx.x; e < FZ_GLUT_SIZE; e += FZ_INF_WARPS * FZ_WARP) sm->lut[e] = fz_lut_entry_bits<FZ_GLUT_BITS>(LL, tab, e);
+        for (uint32_t e = threadIdx.x; e < FZ_GLUT_SIZE; e += FZ_INF_WARPS * FZ_WARP) sm->lut[e] = fz_lean_entry_from(fz_lut_entry_bits<FZ_GLUT_BITS>(LL, tab, e));
         __syncthreads();
     }
     const uint32_t gk = ck * FZ_CODE_WARPS + (uint32_t)warp;
@@ -1943,21 +1960,21 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
             uint32_t e = lut[w & (FZ_GLUT_SIZE - 1)];
             if (e == 0) e = fz_lean_long_entry(sm->code, w & 0x7fffu);
             if (e == 0) break;
-            if (e & 0x100u) {
-                if (!(e & FZ_LUT_MATCH)) {                // the end of block and the closing empty stored block, or garbage
-                    const uint32_t tl = (e >> 25) & 15u, after = pos + tl + 3u;
-                    ok = (e & 511u) == FZ_EOB && ((w >> tl) & 7u) == 0u && ((after + 7u) & ~7u) + 32u == zend && prod == cap;
+            const uint32_t cnt = (e >> 24) & 3u, tl = e >> 28;
+            if (cnt == 0u) {
+                if (e & FZ_LE_EOB) {                      // the end of block and the closing empty stored block
+                    const uint32_t after = pos + tl + 3u;
+                    ok = ((w >> tl) & 7u) == 0u && ((after + 7u) & ~7u) + 32u == zend && prod == cap;
                     break;
                 }
-                const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u, a = w >> cl;
-                const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
+                const uint32_t xb = (e >> 9) & 7u, a = w >> tl;
+                const uint32_t len = (e & 511u) + (a & ((1u << xb) - 1u));
                 if (((a >> xb) & 1u) != run_bit || prod == 0 || prod + len > cap) break;
-                pos += cl + xb + 1u;
+                pos += tl + xb + 1u;
                 prod += len;
             } else {
-                const uint32_t cnt = e >> 29;
-                if (((e & 255u) | ((e >> 1) & 0xffff00u)) != 0u || prod + cnt > cap) break;   // a byte that is not zero
-                pos += (e >> 25) & 15u;
+                if ((e & 0xffffffu) != 0u || prod + cnt > cap) break;   // a byte that is not zero
+                pos += tl;
                 prod += cnt;
             }
         }
@@ -1974,7 +1991,10 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
     // wait in pw0..pw2 until the fourth of their 16-byte group arrives and leave as one 128-bit store.
     bool live = coded && !failed && !all_zero;
     bool done_ok = false;
-    uint32_t op = 0, ow = 0, pw0 = 0, pw1 = 0, pw2 = 0, lastw = 0;
+    // Output: `ow` collects the bytes of the word being written; completed words wait in pw0, pw1, pw2 (oldest first: a
+    // new word shifts them along -- three predicated moves, no selects) until the fourth of their 16-byte group arrives
+    // and the group leaves as one 128-bit store.  pw2 is always the last completed word: a run repeats its top byte.
+    uint32_t op = 0, ow = 0, pw0 = 0, pw1 = 0, pw2 = 0;
     {
         const uint8_t *gbase = frag - mis;                               // chunk 0
         const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
@@ -1986,6 +2006,7 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
         uint32_t ri = rp % FZ_LEAN_ROW_WORDS;                            // rp modulo the ring's words
         uint32_t fs = fetched % FZ_LEAN_CHUNKS;                          // fetched modulo the ring's chunks
         int nacc = 0;
+        int room = (int)cap;                                             // bytes the sub-block still takes
         if (live) {
 #pragma unroll
             for (uint32_t c = 0; c < FZ_LEAN_CHUNKS; c++) {
@@ -2003,13 +2024,11 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
             ri = ri + 1u == FZ_LEAN_ROW_WORDS ? 0u : ri + 1u;
             nxt = row[ri];
         }
-#define FZ_LEAN_WORD_DONE(w_, kq_, gaddr_)                                                      \
+        // word w_ completes the place (op >> 2) & 3 of its 16-byte group
+#define FZ_LEAN_WORD_DONE(w_)                                                                   \
         do {                                                                                    \
-            if ((kq_) == 3u) *(uint4 *)(gaddr_) = make_uint4(pw0, pw1, pw2, (w_));              \
-            pw0 = (kq_) == 0u ? (w_) : pw0;                                                     \
-            pw1 = (kq_) == 1u ? (w_) : pw1;                                                     \
-            pw2 = (kq_) == 2u ? (w_) : pw2;                                                     \
-            lastw = (w_);                                                                       \
+            if ((op & 12u) == 12u) *(uint4 *)(out + (op & ~15u)) = make_uint4(pw0, pw1, pw2, (w_)); \
+            pw0 = pw1; pw1 = pw2; pw2 = (w_);                                                   \
         } while (0)
         while (__any_sync(0xffffffffu, live)) {
             if (live) {
@@ -2039,73 +2058,75 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
                     ri = ri == FZ_LEAN_ROW_WORDS ? 0u : ri;
                     nxt = row[ri];
                     uint32_t e = lut[(uint32_t)acc & (FZ_GLUT_SIZE - 1)];
-                    if (e == 0u) e = fz_lean_long_entry(sm->code, (uint32_t)acc & 0x7fffu);   // a symbol the encoder's sample never saw
-                    if (e & 0x100u) {
-                        if (!(e & FZ_LUT_MATCH)) {
-                            // end of block: what follows must be the empty stored block (000, pad to the byte, 00 00 FF FF
-                            // -- the marker the scan found) that closes the fragment, and the sub-block must be complete
-                            const uint32_t tl = (e >> 25) & 15u;
-                            const uint32_t after = rp * 32u - (uint32_t)nacc + tl + 3u;
-                            done_ok = (e & 511u) == FZ_EOB && (((uint32_t)(acc >> tl)) & 7u) == 0u &&
-                                      ((after + 7u) & ~7u) + 32u == endbit && op == cap;
-                            live = false;
-                            break;
+                    uint32_t cnt = (e >> 24) & 3u;
+                    if (cnt == 0u) {
+                        if (e == 0u) {   // a symbol the encoder's sample never saw (a code longer than the table's index), or garbage
+                            e = fz_lean_long_entry(sm->code, (uint32_t)acc & 0x7fffu);
+                            cnt = (e >> 24) & 3u;
+                            if (e == 0u) { live = false; break; }
                         }
-                        // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
-                        const uint32_t cl = (e >> 25) & 15u, xb = (e >> 18) & 7u;
-                        const uint32_t a = (uint32_t)(acc >> cl);
-                        const uint32_t len = ((e >> 9) & 511u) + (a & ((1u << xb) - 1u));
-                        if (((a >> xb) & 1u) != run_bit || op + len > cap || op == 0u) { live = false; break; }
-                        acc >>= (cl + xb + 1u);
-                        nacc -= (int)(cl + xb + 1u);
-                        {   // len copies of the byte before, through the pending-word logic (no read of what was written)
-                            const uint32_t r = op & 3u;
-                            const uint32_t c = r ? (ow >> ((r - 1u) * 8u)) & 0xffu : lastw >> 24;
-                            const uint32_t cw = c * 0x01010101u;
-                            uint32_t left = len;
-                            if (r) {   // complete the pending word first
-                                const uint32_t take = left < 4u - r ? left : 4u - r;
-                                ow |= (cw & (0xffffffffu >> (32u - 8u * take))) << (8u * r);
-                                left -= take;
-                                if (r + take == 4u) {
-                                    FZ_LEAN_WORD_DONE(ow, (op >> 2) & 3u, out + (op & ~15u));
-                                    ow = 0;
-                                }
-                                op += take;
+                        if (cnt == 0u) {
+                            const uint32_t tl = e >> 28;
+                            if (e & FZ_LE_EOB) {
+                                // end of block: what follows must be the empty stored block (000, pad to the byte, 00 00 FF FF
+                                // -- the marker the scan found) that closes the fragment, and the sub-block must be complete
+                                const uint32_t after = rp * 32u - (uint32_t)nacc + tl + 3u;
+                                done_ok = (((uint32_t)(acc >> tl)) & 7u) == 0u && ((after + 7u) & ~7u) + 32u == endbit && room == 0;
+                                live = false;
+                                break;
                             }
-                            while (left >= 4u) {
-                                const uint32_t kq = (op >> 2) & 3u;
-                                if (kq == 0u && left >= 16u) {
-                                    *(uint4 *)(out + op) = make_uint4(cw, cw, cw, cw);
-                                    lastw = cw;
-                                    op += 16u;
-                                    left -= 16u;
-                                } else {
-                                    FZ_LEAN_WORD_DONE(cw, kq, out + (op & ~15u));
-                                    op += 4u;
-                                    left -= 4u;
+                            // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
+                            const uint32_t xb = (e >> 9) & 7u;
+                            const uint32_t a = (uint32_t)(acc >> tl);
+                            const uint32_t len = (e & 511u) + (a & ((1u << xb) - 1u));
+                            room -= (int)len;
+                            if (((a >> xb) & 1u) != run_bit || room < 0 || op == 0u) { live = false; break; }
+                            acc >>= (tl + xb + 1u);
+                            nacc -= (int)(tl + xb + 1u);
+                            {   // len copies of the byte before, through the pending-word logic (no read of what was written)
+                                const uint32_t r = op & 3u;
+                                const uint32_t c = r ? (ow >> ((r - 1u) * 8u)) & 0xffu : pw2 >> 24;
+                                const uint32_t cw = c * 0x01010101u;
+                                uint32_t left = len;
+                                if (r) {   // complete the pending word first
+                                    const uint32_t take = left < 4u - r ? left : 4u - r;
+                                    ow |= (cw & (0xffffffffu >> (32u - 8u * take))) << (8u * r);
+                                    left -= take;
+                                    if (r + take == 4u) {
+                                        FZ_LEAN_WORD_DONE(ow);
+                                        ow = 0;
+                                    }
+                                    op += take;
                                 }
+                                while (left >= 4u) {
+                                    if ((op & 12u) == 0u && left >= 16u) {
+                                        *(uint4 *)(out + op) = make_uint4(cw, cw, cw, cw);
+                                        pw2 = cw;
+                                        op += 16u;
+                                        left -= 16u;
+                                    } else {
+                                        FZ_LEAN_WORD_DONE(cw);
+                                        op += 4u;
+                                        left -= 4u;
+                                    }
+                                }
+                                if (left) { ow = cw & (0xffffffffu >> (32u - 8u * left)); op += left; }
                             }
-                            if (left) { ow = cw & (0xffffffffu >> (32u - 8u * left)); op += left; }
+                            continue;
                         }
-                        continue;
                     }
                     // 1..3 literals: sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that
-                    // count) appended to the pending word.  e == 0 (no such code at all) has cnt == 0.
-                    const uint32_t cnt = e >> 29, tl = (e >> 25) & 15u;
-                    if (cnt == 0u || op + cnt > cap) { live = false; break; }
-                    const uint32_t v = (e & 255u) | ((e >> 1) & 0xffff00u);
+                    // count) appended to the pending word
+                    room -= (int)cnt;
+                    if (room < 0) { live = false; break; }
+                    const uint32_t v = e & 0xffffffu, tl = e >> 28;
                     const uint32_t sh = (op & 3u) * 8u;
                     const uint64_t t = (uint64_t)ow | ((uint64_t)v << sh);
-                    const uint32_t kq = (op >> 2) & 3u;     // place of the pending word in its 16-byte group
-                    op += cnt;
                     const bool full = sh + cnt * 8u >= 32u;
-                    if (full && kq == 3u) *(uint4 *)(out + ((op & ~3u) - 16u)) = make_uint4(pw0, pw1, pw2, (uint32_t)t);
-                    pw0 = (full && kq == 0u) ? (uint32_t)t : pw0;
-                    pw1 = (full && kq == 1u) ? (uint32_t)t : pw1;
-                    pw2 = (full && kq == 2u) ? (uint32_t)t : pw2;
-                    lastw = full ? (uint32_t)t : lastw;
+                    if (full && (op & 12u) == 12u) *(uint4 *)(out + (op & ~15u)) = make_uint4(pw0, pw1, pw2, (uint32_t)t);
+                    if (full) { pw0 = pw1; pw1 = pw2; pw2 = (uint32_t)t; }
                     ow = full ? (uint32_t)(t >> 32) : (uint32_t)t;
+                    op += cnt;
                     acc >>= tl;
                     nacc -= (int)tl;
                 }
@@ -2116,12 +2137,13 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
     }
     if (coded && !failed && !all_zero) {
         if (done_ok) {
-            // what is still pending: the completed words of the last 16-byte group, then the bytes of the last word
+            // what is still pending: the completed words of the last 16-byte group (the newest in pw2), then the bytes of
+            // the last word
             const uint32_t kq = (op >> 2) & 3u;
             uint32_t *q = (uint32_t *)(out + (op & ~15u));
-            if (kq > 0) q[0] = pw0;
-            if (kq > 1) q[1] = pw1;
-            if (kq > 2) q[2] = pw2;
+            if (kq == 1u) q[0] = pw2;
+            if (kq == 2u) { q[0] = pw1; q[1] = pw2; }
+            if (kq == 3u) { q[0] = pw0; q[1] = pw1; q[2] = pw2; }
             const uint32_t r = op & 3u, w0 = op - r;
             for (uint32_t i = 0; i < r; i++) out[w0 + i] = (uint8_t)(ow >> (8u * i));
         } else failed = true;
