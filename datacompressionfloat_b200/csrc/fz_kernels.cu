@@ -1857,6 +1857,13 @@ __device__ __noinline__ uint32_t fz_lean_long_entry(const uint32_t *code, uint32
     return fz_lean_entry_from(ent);
 }
 
+__device__ __forceinline__ uint32_t fz_lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // 32 stream bits from bit position `pos` of the aligned words b32[0 .. nw): zero bits past the end
 __device__ __forceinline__ uint32_t fz_peek32(const uint32_t *b32, uint32_t nw, uint32_t pos)
 {
@@ -1989,8 +1996,8 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
     // words <= 4 cons + 13: chunk cons + 3.  The previous round left fetched = cons' + 7 >= cons + 4 (cons moves by at
     // most 3 chunks per round, which FZ_LEAN_TOPUPS = 3 makes up), and all of that has landed.  Completed output words
     // wait in pw0..pw2 until the fourth of their 16-byte group arrives and leave as one 128-bit store.
-    bool live = coded && !failed && !all_zero;
-    bool done_ok = false;
+    uint32_t live = (coded && !failed && !all_zero) ? 1u : 0u;   // (words, not bools: the compiler packed bools into one register
+    uint32_t done_ok = 0;                                        //  and re-packed it in every iteration)
     // Output: `ow` collects the bytes of the word being written; completed words wait in pw0, pw1, pw2 (oldest first: a
     // new word shifts them along -- three predicated moves, no selects) until the fourth of their 16-byte group arrives
     // and the group leaves as one 128-bit store.  pw2 is always the last completed word: a run repeats its top byte.
@@ -2000,12 +2007,17 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
         const uint32_t nchunks = (mis + flen + 15u) >> 4;                // chunks that hold bytes of the fragment
         uint32_t *row = sm->ring + (warp * FZ_WARP + lane) * FZ_LEAN_ROW_WORDS;
         const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(row);
+        const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(sm->lut);
+        // Bit reader: lo and hi are two consecutive words of the fragment, bo (0..31) the bits of lo already used -- one
+        // funnel shift gives the next 32 stream bits, which is all a table hit, a run (<= 21 bits) or the end of block
+        // (<= 18) needs.  nxt is the word behind hi, read from the ring one iteration before it can become hi; rp its
+        // word index (ri = rp modulo the ring's words).  Selects are written as x += flag * (y - x) with flag 0 / 1: the
+        // multiply-add pipe is idle in this kernel, the ALU pipe (shifts, logic, compares, selects) is what bounds it.
         const uint32_t abs_bit = mis * 8u + hdr_bits;
-        uint64_t acc = 0;
-        uint32_t nxt = 0, rp = abs_bit >> 5, fetched = rp >> 2;
+        uint32_t lo = 0, hi = 0, nxt = 0, bo = abs_bit & 31u;
+        uint32_t rp = abs_bit >> 5, fetched = rp >> 2;
         uint32_t ri = rp % FZ_LEAN_ROW_WORDS;                            // rp modulo the ring's words
         uint32_t fs = fetched % FZ_LEAN_CHUNKS;                          // fetched modulo the ring's chunks
-        int nacc = 0;
         int room = (int)cap;                                             // bytes the sub-block still takes
         if (live) {
 #pragma unroll
@@ -2018,11 +2030,12 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
         fz_cp_async_commit();
         fz_cp_async_wait<0>();
         if (live) {
-            acc = (uint64_t)(row[ri] >> (abs_bit & 31u));
-            nacc = 32 - (int)(abs_bit & 31u);
-            rp++;
+            lo = row[ri];
+            ri = ri + 1u == FZ_LEAN_ROW_WORDS ? 0u : ri + 1u;
+            hi = row[ri];
             ri = ri + 1u == FZ_LEAN_ROW_WORDS ? 0u : ri + 1u;
             nxt = row[ri];
+            rp += 2u;
         }
         // word w_ completes the place (op >> 2) & 3 of its 16-byte group
 #define FZ_LEAN_WORD_DONE(w_)                                                                   \
@@ -2030,10 +2043,23 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
             if ((op & 12u) == 12u) *(uint4 *)(out + (op & ~15u)) = make_uint4(pw0, pw1, pw2, (w_)); \
             pw0 = pw1; pw1 = pw2; pw2 = (w_);                                                   \
         } while (0)
-        while (__any_sync(0xffffffffu, live)) {
+        // tl_ bits are used up: move on by a word when lo is spent (flag arithmetic, see above)
+#define FZ_LEAN_CONSUME(tl_)                                                                    \
+        do {                                                                                    \
+            bo += (tl_);                                                                        \
+            const uint32_t ni_ = bo >> 5;                                                       \
+            bo &= 31u;                                                                          \
+            lo += ni_ * (hi - lo);                                                              \
+            hi += ni_ * (nxt - hi);                                                             \
+            rp += ni_;                                                                          \
+            ri += ni_;                                                                          \
+            ri = ri == FZ_LEAN_ROW_WORDS ? 0u : ri;                                             \
+            nxt = row[ri];                                                                      \
+        } while (0)
+        while (__any_sync(0xffffffffu, live != 0u)) {
             if (live) {
-                // chunks below this one are used up (the bit buffer holds at most two words behind rp)
-                const uint32_t cons = (rp >= 2u ? rp - 2u : 0u) >> 2;
+                // chunks below this one are used up (lo is word rp - 2)
+                const uint32_t cons = (rp - 2u) >> 2;
 #pragma unroll
                 for (int c = 0; c < FZ_LEAN_TOPUPS; c++) {
                     if (fetched < cons + FZ_LEAN_CHUNKS) {
@@ -2048,41 +2074,32 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
             if (live) {
 #pragma unroll 1
                 for (int it = 0; it < FZ_LEAN_ITERS; ++it) {
-                    // refill without a branch: ORing the next word in early is harmless (its bits land where they
-                    // belong and are ORed there again once they count), and `nxt` is re-read every iteration
-                    acc |= (uint64_t)nxt << nacc;
-                    const bool need = nacc < 32;
-                    nacc += need ? 32 : 0;
-                    rp += need ? 1u : 0u;
-                    ri += need ? 1u : 0u;
-                    ri = ri == FZ_LEAN_ROW_WORDS ? 0u : ri;
-                    nxt = row[ri];
-                    uint32_t e = lut[(uint32_t)acc & (FZ_GLUT_SIZE - 1)];
-                    uint32_t cnt = (e >> 24) & 3u;
+                    const uint32_t win = __funnelshift_r(lo, hi, bo);      // the next 32 stream bits
+                    uint32_t e = fz_lds32(lut_s + ((win & (FZ_GLUT_SIZE - 1)) << 2));   // (a shared-space load: through the generic
+                    uint32_t cnt = (e >> 24) & 3u;                                      //  pointer the window base was rebuilt per iteration)
                     if (cnt == 0u) {
                         if (e == 0u) {   // a symbol the encoder's sample never saw (a code longer than the table's index), or garbage
-                            e = fz_lean_long_entry(sm->code, (uint32_t)acc & 0x7fffu);
+                            e = fz_lean_long_entry(sm->code, win & 0x7fffu);
                             cnt = (e >> 24) & 3u;
-                            if (e == 0u) { live = false; break; }
+                            if (e == 0u) { live = 0u; break; }
                         }
                         if (cnt == 0u) {
                             const uint32_t tl = e >> 28;
                             if (e & FZ_LE_EOB) {
                                 // end of block: what follows must be the empty stored block (000, pad to the byte, 00 00 FF FF
                                 // -- the marker the scan found) that closes the fragment, and the sub-block must be complete
-                                const uint32_t after = rp * 32u - (uint32_t)nacc + tl + 3u;
-                                done_ok = (((uint32_t)(acc >> tl)) & 7u) == 0u && ((after + 7u) & ~7u) + 32u == endbit && room == 0;
-                                live = false;
+                                const uint32_t after = (rp - 2u) * 32u + bo + tl + 3u;
+                                done_ok = (((win >> tl) & 7u) == 0u && ((after + 7u) & ~7u) + 32u == endbit && room == 0) ? 1u : 0u;
+                                live = 0u;
                                 break;
                             }
                             // a run (distance-1 match) whole: length code, its extra bits, the one distance bit
                             const uint32_t xb = (e >> 9) & 7u;
-                            const uint32_t a = (uint32_t)(acc >> tl);
+                            const uint32_t a = win >> tl;
                             const uint32_t len = (e & 511u) + (a & ((1u << xb) - 1u));
                             room -= (int)len;
-                            if (((a >> xb) & 1u) != run_bit || room < 0 || op == 0u) { live = false; break; }
-                            acc >>= (tl + xb + 1u);
-                            nacc -= (int)(tl + xb + 1u);
+                            if (((a >> xb) & 1u) != run_bit || room < 0 || op == 0u) { live = 0u; break; }
+                            FZ_LEAN_CONSUME(tl + xb + 1u);
                             {   // len copies of the byte before, through the pending-word logic (no read of what was written)
                                 const uint32_t r = op & 3u;
                                 const uint32_t c = r ? (ow >> ((r - 1u) * 8u)) & 0xffu : pw2 >> 24;
@@ -2118,20 +2135,23 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
                     // 1..3 literals: sym1 | sym2 << 8 | sym3 << 16 (unused slots are zero and lie above the bytes that
                     // count) appended to the pending word
                     room -= (int)cnt;
-                    if (room < 0) { live = false; break; }
+                    if (room < 0) { live = 0u; break; }
                     const uint32_t v = e & 0xffffffu, tl = e >> 28;
                     const uint32_t sh = (op & 3u) * 8u;
                     const uint64_t t = (uint64_t)ow | ((uint64_t)v << sh);
-                    const bool full = sh + cnt * 8u >= 32u;
-                    if (full && (op & 12u) == 12u) *(uint4 *)(out + (op & ~15u)) = make_uint4(pw0, pw1, pw2, (uint32_t)t);
-                    if (full) { pw0 = pw1; pw1 = pw2; pw2 = (uint32_t)t; }
-                    ow = full ? (uint32_t)(t >> 32) : (uint32_t)t;
+                    const uint32_t t0 = (uint32_t)t, t1 = (uint32_t)(t >> 32);
+                    const uint32_t fi = ((op & 3u) + cnt) >> 2;             // 1: the pending word is complete
+                    if (fi != 0u && (op & 12u) == 12u) *(uint4 *)(out + (op & ~15u)) = make_uint4(pw0, pw1, pw2, t0);
+                    pw0 += fi * (pw1 - pw0);
+                    pw1 += fi * (pw2 - pw1);
+                    pw2 += fi * (t0 - pw2);
+                    ow = t0 + fi * (t1 - t0);
                     op += cnt;
-                    acc >>= tl;
-                    nacc -= (int)tl;
+                    FZ_LEAN_CONSUME(tl);
                 }
             }
         }
+#undef FZ_LEAN_CONSUME
 #undef FZ_LEAN_WORD_DONE
         fz_cp_async_wait<0>();   // nothing of this group may still be landing in the ring when the CTA's next group fills it
     }
