@@ -43,7 +43,7 @@ struct FzEncState {
     uint32_t ntok;           // code-length RLE tokens
     uint32_t hdr_nbits;      // bits in hdr[] (block header incl. the 3 type bits)
     uint32_t dyn_bits;       // exact size of the dynamic block incl. header and EOB
-    uint32_t pad0;
+    uint32_t n_low;          // stand-in symbols (frequency 1 in a group with unsampled sub-blocks): outside the tree
     uint32_t keys[512];      // sort workspace; then Moffat-Katajainen array
     uint16_t ssym[320];      // symbols in ascending frequency order
     uint16_t code[288];      // bit-reversed canonical codes
@@ -86,30 +86,36 @@ FZ_HD void fz_ph_zero_len(FzEncState *st, int lane)
     for (int i = lane; i < 288; i += 32) st->len[i] = 0;
 }
 
-FZ_HD void fz_ph_count_active(FzEncState *st, int lane)
+// `low` = the frequency that marks a stand-in (1 when the group has unsampled sub-blocks, 0 = there are none): such
+// symbols do not take part in the sort or the tree -- they get the longest code afterwards (fz_ph_standins)
+FZ_HD void fz_ph_count_active(FzEncState *st, uint32_t low, int lane)
 {
-    uint32_t c = 0;
-    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
-        const int s = lane * FZ_SYMS_PER_LANE + k;
-        c += st->hist[s] != 0 ? 1u : 0u;
-    }
-    st->lane_cnt[lane] = c;
-}
-
-FZ_HD void fz_ph_compact(FzEncState *st, int lane)
-{
-    uint32_t off = 0, total = 0;
-    for (int l = 0; l < 32; l++) { const uint32_t c = st->lane_cnt[l]; if (l < lane) off += c; total += c; }
+    uint32_t c = 0, cl = 0;
     for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
         const int s = lane * FZ_SYMS_PER_LANE + k;
         const uint32_t f = st->hist[s];
-        if (f) st->keys[off++] = (f << 9) | (uint32_t)s;
+        c += f > low ? 1u : 0u;
+        cl += (f != 0 && f <= low) ? 1u : 0u;
+    }
+    st->lane_cnt[lane] = c;
+    st->lane_bits[lane] = cl;
+}
+
+FZ_HD void fz_ph_compact(FzEncState *st, uint32_t low, int lane)
+{
+    uint32_t off = 0, total = 0, nlow = 0;
+    for (int l = 0; l < 32; l++) { const uint32_t c = st->lane_cnt[l]; if (l < lane) off += c; total += c; nlow += st->lane_bits[l]; }
+    for (int k = 0; k < FZ_SYMS_PER_LANE; k++) {
+        const int s = lane * FZ_SYMS_PER_LANE + k;
+        const uint32_t f = st->hist[s];
+        if (f > low) st->keys[off++] = (f << 9) | (uint32_t)s;
+        else if (f != 0) st->len[s] = 15;   // a stand-in: the longest code deflate allows (fz_ph_standins may shorten a few)
     }
     // pad to the next power of two with +inf keys for the bitonic network
     uint32_t np2 = 32;
     while (np2 < total) np2 <<= 1;
     for (uint32_t i = total + lane; i < np2; i += 32) st->keys[i] = 0xFFFFFFFFu;
-    if (lane == 0) st->n_active = total;
+    if (lane == 0) { st->n_active = total; st->n_low = nlow; }
 }
 
 // one compare-exchange layer (k, j) of the bitonic network over np2 keys
@@ -126,13 +132,10 @@ FZ_HD void fz_ph_bitonic(uint32_t *keys, uint32_t np2, uint32_t k, uint32_t j, i
 
 // serial (lane 0): in-place minimum-redundancy code lengths (Moffat & Katajainen 1995) over the
 // ascending frequencies, then the length limit.  keys[] holds freq << 9 | sym on entry.
-// `seenbits` < maxbits asks for two tiers: symbols of frequency <= 1 (the stand-ins of fz_group_code_kernel: "may occur
-// in the sub-blocks that were not sampled") may take maxbits, every symbol the sample saw gets at most seenbits.
-FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n, int maxbits, int lane, int seenbits = 0)
+FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n, int maxbits, int lane)
 {
     if (lane != 0) return;
-    int nlow = 0;   // keys ascend: the symbols of frequency <= 1 come first
-    for (int i = 0; i < n; i++) { const uint32_t k = A[i]; ssym[i] = (uint16_t)(k & 511u); A[i] = k >> 9; if (A[i] <= 1u) nlow = i + 1; }
+    for (int i = 0; i < n; i++) { const uint32_t k = A[i]; ssym[i] = (uint16_t)(k & 511u); A[i] = k >> 9; }
     for (int l = 0; l < 32; l++) num_codes[l] = 0;
     if (n == 1) { A[0] = 1; num_codes[1] = 1; return; }
     // phase 1: internal node weights + parent pointers
@@ -152,37 +155,6 @@ FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n
         while (root >= 0 && (int)A[root] == dpth) { used++; root--; }
         while (avbl > used) { A[next--] = (uint32_t)dpth; avbl--; }
         avbl = 2 * used; dpth++; used = 0;
-    }
-    if (seenbits > 0 && seenbits < maxbits) {
-        // Two tiers.  Limiting all 286 symbols to the 12 bits of the inflater's table would hand 286 / 4096 = 7 % of the
-        // code space to stand-ins that hardly ever occur (+1..2 % size, measured); at 15 bits they cost 0.9 %, and the
-        // symbols that do occur are still one table lookup each.  Clamp per tier, then repair the Kraft sum K (in units
-        // of 2^-maxbits): lengthen the least frequent symbols that still may grow (A[] descends, so the first one found
-        // gives the smallest step), then hand back what that overshot by shortening whatever fits, most frequent first.
-        const uint32_t full = 1u << maxbits;
-        uint32_t K = 0;
-        for (int i = 0; i < n; i++) {
-            const uint32_t lim = (uint32_t)(i < nlow ? maxbits : seenbits);
-            if (A[i] > lim) A[i] = lim;
-            K += 1u << ((uint32_t)maxbits - A[i]);
-        }
-        while (K > full) {
-            for (int i = 0; i < n && K > full; i++) {
-                const uint32_t lim = (uint32_t)(i < nlow ? maxbits : seenbits);
-                if (A[i] < lim) { K -= 1u << ((uint32_t)maxbits - A[i] - 1u); A[i]++; }
-            }
-        }
-        uint32_t D = full - K;
-        while (D) {
-            bool moved = false;
-            for (int i = n - 1; i >= 0 && D; i--) {
-                const uint32_t gain = 1u << ((uint32_t)maxbits - A[i]);
-                if (A[i] > 1u && gain <= D) { A[i]--; D -= gain; moved = true; }
-            }
-            if (!moved) break;   // (cannot happen: D is a multiple of the step of the longest code present)
-        }
-        for (int i = 0; i < n; i++) num_codes[A[i]]++;
-        return;
     }
     // histogram of lengths, clamped at 31
     for (int i = 0; i < n; i++) { uint32_t l = A[i]; if (l > 31) l = 31; num_codes[l]++; }
@@ -204,6 +176,47 @@ FZ_HD void fz_ph_lengths(uint32_t *A, uint16_t *ssym, uint32_t *num_codes, int n
     int i = 0;
     for (int l = maxbits; l > 0; l--)
         for (uint32_t c = 0; c < num_codes[l]; c++) A[i++] = (uint32_t)l;
+}
+
+// serial (lane 0): make room in the code for the stand-ins.  On entry keys[0 .. n_active) are the code lengths of the
+// symbols the sample saw (a complete code of at most FZ_MAX_CODE_BITS bits, ascending frequency = descending length),
+// len[s] = 15 for every stand-in s, num_codes[] counts the former.  The Kraft sum K (units of 2^-15) is then over by
+// one unit per stand-in: lengthen the least frequent seen symbols that may still grow (never past FZ_MAX_CODE_BITS: a
+// seen symbol stays one table lookup in the inflater), then hand back what that overshot by shortening whatever fits --
+// seen symbols, most frequent first, then stand-ins.  (Stand-ins used to go through the sort and the tree like everybody
+// else: 286 symbols instead of 20..60, and a 12-bit limit for all of them cost 1..2 % in size.)
+FZ_HD void fz_ph_standins(FzEncState *st, int lane)
+{
+    if (lane != 0 || st->n_low == 0) return;
+    uint32_t *A = st->keys;
+    const int n = (int)st->n_active;
+    const uint32_t full = 1u << 15, lim = FZ_MAX_CODE_BITS;
+    uint32_t K = st->n_low;
+    for (int i = 0; i < n; i++) K += 1u << (15u - A[i]);
+    while (K > full) {
+        bool moved = false;
+        for (int i = 0; i < n && K > full; i++)
+            if (A[i] < lim) { K -= 1u << (14u - A[i]); A[i]++; moved = true; }
+        if (!moved) break;   // (cannot happen: 286 symbols at their limits fill 7 % of the code space)
+    }
+    uint32_t D = K <= full ? full - K : 0u;
+    while (D) {
+        bool moved = false;
+        for (int i = n - 1; i >= 0 && D; i--) {
+            const uint32_t gain = 1u << (15u - A[i]);
+            if (A[i] > 1u && gain <= D) { A[i]--; D -= gain; moved = true; }
+        }
+        for (int s2 = 0; s2 < FZ_NUM_LL && D; s2++) {
+            if (st->hist[s2] != 1u || st->len[s2] == 0) continue;   // stand-ins only (len is still 0 for the seen symbols)
+            const uint32_t l = st->len[s2], gain = 1u << (15u - l);
+            if (l > 1u && gain <= D) { st->len[s2] = (uint8_t)(l - 1u); D -= gain; moved = true; }
+        }
+        if (!moved) break;   // (cannot happen: D is a multiple of the step of the longest code present)
+    }
+    for (int l = 0; l < 32; l++) st->num_codes[l] = 0;
+    for (int i = 0; i < n; i++) st->num_codes[A[i]]++;
+    for (int s2 = 0; s2 < FZ_NUM_LL; s2++)
+        if (st->hist[s2] == 1u && st->len[s2] != 0) st->num_codes[st->len[s2]]++;
 }
 
 FZ_HD void fz_ph_scatter_len(FzEncState *st, int lane)
@@ -406,20 +419,23 @@ struct FzGroupCode {
 // Build the group's Huffman code and block header from its token histogram.
 //   st->hist[0..287] = token frequencies of the whole group, st->hist[256] = number of sub-blocks (EOBs)
 //   group_bytes = plane bytes in the group, nsub = sub-blocks in the group
+//   standins: symbols of frequency 1 stand for "may occur in the sub-blocks the histogram did not sample"
 template <int DUMMY = 0>
-FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t nsub, FzGroupCode *out, int lane)
+FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t nsub, FzGroupCode *out, int lane, bool standins = false)
 {
     (void)lane;
+    const uint32_t low = standins ? 1u : 0u;
     FZ_PHASE(fz_ph_zero_len(st, lane));
-    FZ_PHASE(fz_ph_count_active(st, lane));
-    FZ_PHASE(fz_ph_compact(st, lane));
+    FZ_PHASE(fz_ph_count_active(st, low, lane));
+    FZ_PHASE(fz_ph_compact(st, low, lane));
     {
         uint32_t np2 = 32;
         while (np2 < st->n_active) np2 <<= 1;
         for (uint32_t k = 2; k <= np2; k <<= 1)
             for (uint32_t j = k >> 1; j > 0; j >>= 1) FZ_PHASE(fz_ph_bitonic(st->keys, np2, k, j, lane));
     }
-    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, 15, lane, FZ_MAX_CODE_BITS));
+    FZ_PHASE(fz_ph_lengths(st->keys, st->ssym, st->num_codes, (int)st->n_active, FZ_MAX_CODE_BITS, lane));
+    FZ_PHASE(fz_ph_standins(st, lane));
     FZ_PHASE(fz_ph_scatter_len(st, lane));
     FZ_PHASE(fz_ph_rank_count(st, lane));
     FZ_PHASE(fz_ph_rank_scan(st, lane));

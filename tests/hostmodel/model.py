@@ -26,6 +26,12 @@ def encode_stream_v2(a: np.ndarray, sequential: bool = False, skip: bool = True)
     return out[:n].copy(), int(ns.value)
 
 
+def set_hist_sample(k: int):
+    """0 / 1: the group's code is built from every sub-block; k > 1: from every k-th one (what the kernels do, k = 4), with
+    a stand-in count of 1 for every symbol nobody counted."""
+    _L.hm_set_hist_sample(C.c_int(k))
+
+
 def encode_stream(a: np.ndarray):
     """a whole plane stream through the encoder the kernels run (device source, 32-thread warp model)"""
     return encode_stream_v2(a, sequential=False, skip=True)
