@@ -1082,32 +1082,16 @@ void fz_launch_gather(const uint8_t *planes, const uint8_t *scratch, const uint3
 // =================================================================================================
 
 // chunk-header chain (reference workers.c:61-69): serial by nature, 16 bytes per hop
-// One warp, every lane walks the same chain (the loads coalesce into one request); what the lanes do on their own is
-// PREFETCH: a hop costs one round trip to DRAM (0.7 us; 171 of them for a 4 GiB volume) because nothing tells where the
-// next header lies before this one is read -- but chunk records of one file are nearly the same size, so while header c
-// is on its way the 32 KiB around "record c + 1 is as long as record c - 1 was" are pulled into L2 (one prefetch per 128-byte
-// line, 8 per lane), and the load of header c + 1 then usually finds its line there.
-__global__ void __launch_bounds__(FZ_WARP)
-fz_walk_kernel(const uint8_t *__restrict__ container, uint64_t container_size, FzBatchGeom g,
-               uint32_t *__restrict__ stream_hdr, unsigned long long *__restrict__ stream_off, FzStatus *status)
+// One thread: the chain is serial by format (16 bytes per hop, one round trip to memory each: 0.12 ms for the 171 chunk
+// records of a 4 GiB volume).  Measured and not kept: pulling the 32 KiB around the guessed position of the next header
+// into L2 while this one is on its way (records of one file are nearly equally long) changed nothing.
+__global__ void fz_walk_kernel(const uint8_t *__restrict__ container, uint64_t container_size, FzBatchGeom g,
+                               uint32_t *__restrict__ stream_hdr, unsigned long long *__restrict__ stream_off, FzStatus *status)
 {
-    if (status->error) return;
-    const int lane = threadIdx.x;
-    unsigned long long off = status->out_end, prev_size = 0;
-    int err = 0;
+    if (threadIdx.x != 0 || status->error) return;
+    unsigned long long off = status->out_end;
     for (uint32_t c = 0; c < g.nchunks; c++) {
-        if (off + FZ_CHUNK_HEADER_BYTES > container_size) { err = 1; break; }
-        if (prev_size) {
-            // where header c + 1 would be if record c were as long as record c - 1: 16 KiB either side of it
-            const unsigned long long guess = off + prev_size;
-            const unsigned long long lo = guess > 16384ull ? guess - 16384ull : 0ull;
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const unsigned long long a = ((lo + (unsigned long long)(lane * 8 + q) * 128ull) & ~127ull);
-                if (a + 128ull <= container_size) asm volatile("prefetch.global.L2 [%0];" ::"l"(container + a));
-            }
-        }
-        const unsigned long long rec = off;
+        if (off + FZ_CHUNK_HEADER_BYTES > container_size) { status->error = FZ_E_FORMAT; return; }
         uint8_t b[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) b[i] = container[off + i];
@@ -1118,19 +1102,14 @@ fz_walk_kernel(const uint8_t *__restrict__ container, uint64_t container_size, F
             // unpack_header (reference zip.c:394-399)
             const uint32_t h = (uint32_t)b[4 * j] | ((uint32_t)b[4 * j + 1] << 8) | ((uint32_t)b[4 * j + 2] << 16) | ((uint32_t)b[4 * j + 3] << 24);
             const uint32_t len = h & ~FZ_RAW_FLAG;
-            if ((h & FZ_RAW_FLAG) && len != n_s) err = 1;
-            if (off + len > container_size) err = 1;
-            if (err) break;
-            if (lane == 0) { stream_hdr[c * 4 + j] = h; stream_off[c * 4 + j] = off; }
+            if ((h & FZ_RAW_FLAG) && len != n_s) { status->error = FZ_E_FORMAT; return; }
+            if (off + len > container_size) { status->error = FZ_E_FORMAT; return; }
+            stream_hdr[c * 4 + j] = h;
+            stream_off[c * 4 + j] = off;
             off += len;
         }
-        if (err) break;
-        prev_size = off - rec;
     }
-    if (lane == 0) {
-        if (err) status->error = FZ_E_FORMAT;
-        else status->out_end = off;
-    }
+    status->out_end = off;
 }
 
 void fz_launch_walk(const uint8_t *container, uint64_t container_size, FzBatchGeom g, uint32_t *stream_hdr,
