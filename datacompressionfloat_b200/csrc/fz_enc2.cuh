@@ -369,37 +369,6 @@ FZ_HD void fz_ring_put64(const W &w, uint32_t *ring, uint32_t off, uint64_t bits
     if (s + nbits > 64u) w.atom_or(&ring[(wi + 2u) & FZ_E2_RING_MASK], (uint32_t)(bits >> (64u - s)));
 }
 
-// A lane's bits of one step, concatenated in registers before they touch the ring: of the words its span covers only
-// the first and the last are shared with the neighbouring lanes (atomic OR), the ones in between are its own -- plain
-// stores into words the flush left zero.  (One put per quad straight into the ring was 16..24 shared-memory atomics per
-// lane and step, mostly on words two lanes fight over: `short_scoreboard` was the emit kernel's first stall reason.)
-template <class W>
-struct FzLaneOut {
-    uint32_t *ring;
-    uint64_t acc;       // bits not yet written; the low `fill` bits of the word at wi are in it (zeros below the lane's start)
-    uint32_t wi, fill;
-    bool first;
-    FZ_HD void init(uint32_t *r, uint32_t off) { ring = r; acc = 0; wi = off >> 5; fill = off & 31u; first = true; }
-    FZ_HD void put(const W &w, uint32_t bits, uint32_t n)   // n <= 32, no bits above n
-    {
-        acc |= (uint64_t)bits << fill;
-        fill += n;
-        if (fill >= 32u) {
-            uint32_t *p = &ring[wi & FZ_E2_RING_MASK];
-            if (first) w.atom_or(p, (uint32_t)acc);
-            else *p = (uint32_t)acc;
-            first = false;
-            wi++;
-            acc >>= 32;
-            fill -= 32u;
-        }
-    }
-    FZ_HD void finish(const W &w)
-    {
-        if ((uint32_t)acc) w.atom_or(&ring[wi & FZ_E2_RING_MASK], (uint32_t)acc);
-    }
-};
-
 // Does the 20-byte window prev | x0..x3 show 00 00 FF FF at byte offsets 1..16 (i.e. ending inside x0..x3)?
 // bit o - 1 of the result.  The filter in front (two adjacent FF bytes anywhere) lets one vector in three thousand through.
 FZ_HD uint32_t fz_marker_in20(uint32_t prev, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3)
@@ -572,16 +541,13 @@ FZ_HD uint32_t fz_emit2_subblock(const W &w, const uint32_t *cl, const uint32_t 
 #pragma unroll
         for (int g = 0; g < FZ_E2_LQ; g++) tot += ql[g];
         const uint32_t inc = fz_warp_incl_sum(w, tot);
-        FzLaneOut<W> lo;
-        lo.init(ring, P + inc - tot);
-        if (tinl) lo.put(w, tinb, tinl);
+        uint32_t off = P + inc - tot;
+        if (tinl) { fz_ring_put32(w, ring, off, tinb, tinl); off += tinl; }
 #pragma unroll
         for (int g = 0; g < FZ_E2_LQ; g++) {
-            const uint32_t l = ql[g];
-            lo.put(w, (uint32_t)qv[g], l < 32u ? l : 32u);
-            if (l > 32u) lo.put(w, (uint32_t)(qv[g] >> 32), l - 32u);
+            if (ql[g]) fz_ring_put64(w, ring, off, qv[g], ql[g]);
+            off += ql[g];
         }
-        lo.finish(w);
         P += w.shfl(inc, 31);
         w.sync();
         if ((P >> 3) + 5u >= limit) return stored;   // cannot beat a stored block any more (and must not outgrow the slot)
