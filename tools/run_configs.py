@@ -134,5 +134,7 @@ if __name__ == "__main__":
     allr = []
     for c in a.configs.split(","):
         allr += {"1": config1, "2": config2, "4": config4}[c]()
+    for r in allr:
+        r["commit"] = os.environ.get("MRCZIP_COMMIT")
     Path("gpurun_out").mkdir(exist_ok=True)
     Path("gpurun_out/configs.json").write_text(json.dumps(allr, indent=1))
