@@ -2023,6 +2023,7 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
         uint32_t ri = rp % FZ_LEAN_ROW_WORDS;                            // rp modulo the ring's words
         uint32_t fs = fetched % FZ_LEAN_CHUNKS;                          // fetched modulo the ring's chunks
         int room = (int)cap;                                             // bytes the sub-block still takes
+        uint32_t pend_n = 0, pend_op = 0, pend_cw = 0;                   // 16-byte groups of a long run left to the warp
         if (live) {
 #pragma unroll
             for (uint32_t c = 0; c < FZ_LEAN_CHUNKS; c++) {
@@ -2119,17 +2120,28 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
                                     }
                                     op += take;
                                 }
+                                while (left >= 4u && (op & 12u) != 0u) {   // words up to the next 16-byte boundary
+                                    FZ_LEAN_WORD_DONE(cw);
+                                    op += 4u;
+                                    left -= 4u;
+                                }
+                                if (left >= 16u) {
+                                    // whole 16-byte groups, one store each: by this lane -- or, when there are several
+                                    // and the lane's slot is free, by the whole warp at the end of the round (a lane
+                                    // on its own walks them with 1.3 lanes of 32 active; planes that keep one exponent
+                                    // for a while have runs of 30..258 bytes)
+                                    const uint32_t nv = left >> 4;
+                                    if (nv >= 3u && pend_n == 0u) { pend_n = nv; pend_op = op; pend_cw = cw; }
+                                    else
+                                        for (uint32_t q = 0; q < nv; q++) *(uint4 *)(out + op + 16u * q) = make_uint4(cw, cw, cw, cw);
+                                    pw2 = cw;
+                                    op += nv << 4;
+                                    left &= 15u;
+                                }
                                 while (left >= 4u) {
-                                    if ((op & 12u) == 0u && left >= 16u) {
-                                        *(uint4 *)(out + op) = make_uint4(cw, cw, cw, cw);
-                                        pw2 = cw;
-                                        op += 16u;
-                                        left -= 16u;
-                                    } else {
-                                        FZ_LEAN_WORD_DONE(cw);
-                                        op += 4u;
-                                        left -= 4u;
-                                    }
+                                    FZ_LEAN_WORD_DONE(cw);
+                                    op += 4u;
+                                    left -= 4u;
                                 }
                                 if (left) { ow = cw & (0xffffffffu >> (32u - 8u * left)); op += left; }
                             }
@@ -2154,6 +2166,17 @@ fz_lean_group(FzLeanSmem *sm, const uint32_t s, const uint32_t ck, FzGroupDesc *
                     FZ_LEAN_CONSUME(tl);
                 }
             }
+            // the long runs of this round: every lane stores one 16-byte group of each
+            uint32_t pm = __ballot_sync(0xffffffffu, pend_n != 0u);
+            while (pm) {
+                const int j = __ffs((int)pm) - 1;
+                pm &= pm - 1u;
+                const uint32_t n_j = __shfl_sync(0xffffffffu, pend_n, j), cw_j = __shfl_sync(0xffffffffu, pend_cw, j);
+                const uint32_t op_j = __shfl_sync(0xffffffffu, pend_op, j);
+                uint8_t *o_j = (uint8_t *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)out, j);
+                if ((uint32_t)lane < n_j) *(uint4 *)(o_j + op_j + 16u * (uint32_t)lane) = make_uint4(cw_j, cw_j, cw_j, cw_j);
+            }
+            pend_n = 0u;
         }
 #undef FZ_LEAN_CONSUME
 #undef FZ_LEAN_WORD_DONE
