@@ -306,7 +306,8 @@ FZ_HD int fz_chain_resolve(const uint8_t *in, uint32_t in_len, uint32_t n_out, u
 #define FZ_HD_NOINLINE inline
 #endif
 
-#define FZ_BP_SUB_BITS 2048u
+#define FZ_BP_SUB_BITS 2048u         // bits of a sub-range (one lane's share of a tile) when nothing is known about the block ...
+#define FZ_BP_SUB_MIN 768u           // ... and the least it is cut down to when the block is known to be short (fz_sy_block, len_hint)
 #define FZ_BP_PROBE_BITS 320u       // first probe length of a block ...
 #define FZ_BP_PROBE_MAX 1280u       // ... doubled after every tile that needed a redo round, up to this
 #define FZ_SY_EOB 1u        // the sub-range ended with the end-of-block symbol
@@ -355,6 +356,7 @@ struct FzSyncState {
     int tile_carry;
     uint32_t rec_idx, rec_prev;   // tile record being written / the one before it
     uint32_t probe_bits;          // length of the probe decode; grows when a block's code is slow to fall into step
+    uint32_t sub_bits;            // bits per sub-range in this block (FZ_BP_SUB_MIN .. FZ_BP_SUB_BITS, a multiple of 64)
 };
 
 FZ_HD uint32_t fz_tile_alloc(const FzTilePool &pool)
@@ -398,7 +400,7 @@ FZ_HD_NOINLINE void fz_sy_decode(FzSyncState *st, const uint8_t *in, uint32_t in
 {
     typedef FzInfTab<1> Tab;
     const Tab tab{st->tab, st->tab + 288, st->tab + 320};
-    const uint32_t grid = tile_pos + (uint32_t)lane * FZ_BP_SUB_BITS;
+    const uint32_t grid = tile_pos + (uint32_t)lane * st->sub_bits;
     const uint32_t start = probe ? grid : st->start[lane];
     const uint64_t range_end = probe ? (uint64_t)grid + st->probe_bits : (uint64_t)st->rend[lane];
     const bool write = out != nullptr;
@@ -539,11 +541,11 @@ FZ_HD void fz_sy_ph_probe(FzSyncState *st, const uint8_t *in, uint32_t in_len, u
 }
 FZ_HD void fz_sy_ph_longer_probe(FzSyncState *st, int lane)
 {
-    if (lane == 0 && st->probe_bits < FZ_BP_PROBE_MAX) st->probe_bits *= 2;
+    if (lane == 0 && st->probe_bits < FZ_BP_PROBE_MAX && st->probe_bits * 2u < st->sub_bits) st->probe_bits *= 2;
 }
 FZ_HD void fz_sy_ph_ranges(FzSyncState *st, uint32_t tile_pos, int lane)
 {
-    st->rend[lane] = lane < 31 ? st->start[lane + 1] : tile_pos + 32u * FZ_BP_SUB_BITS;
+    st->rend[lane] = lane < 31 ? st->start[lane + 1] : tile_pos + 32u * st->sub_bits;
 }
 FZ_HD void fz_sy_ph_spec(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t tile_pos, int lane)
 {
@@ -671,6 +673,12 @@ FZ_HD void fz_sy_block_from_table(FzSyncState *st, const uint8_t *in, uint32_t i
 {
     (void)lane;
     FZ_PHASE(fz_sy_ph_header(st, in, in_len, bit, lane));
+#if defined(__CUDA_ARCH__)
+    if (lane == 0) st->sub_bits = FZ_BP_SUB_BITS;   // (not used when the records say where every sub-range starts)
+    __syncwarp();
+#else
+    st->sub_bits = FZ_BP_SUB_BITS;
+#endif
     bool good = st->hdr_ok != 0;
     uint32_t produced = 0, end_bit = bit, rec = first_rec;
     bool done = false;
@@ -703,10 +711,29 @@ FZ_HD void fz_sy_block_from_table(FzSyncState *st, const uint8_t *in, uint32_t i
 template <bool WRITE>
 FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint32_t bit, uint8_t *out, uint32_t out_len,
                        int prev_byte, uint32_t expect_end, FzBlockInfo *bi, bool *ok, int lane,
-                       const FzTilePool *pool = nullptr, uint32_t *first_rec = nullptr)
+                       const FzTilePool *pool = nullptr, uint32_t *first_rec = nullptr, uint32_t len_hint = 0)
 {
     (void)lane;
     FZ_PHASE(fz_sy_ph_header(st, in, in_len, bit, lane));
+    // len_hint: bits from this header to the next candidate header of the stream (0 = unknown).  zlib closes a block after
+    // 16383 symbols, which on exponent or count planes is 30..45 thousand bits: at 2048 bits per sub-range only 16..22 of
+    // the 32 lanes had work.  The block is cut into 32 equal sub-ranges instead (never shorter than FZ_BP_SUB_MIN: the probe
+    // decode in front of every sub-range does not shrink with it).  A hint that is off costs speed, not correctness.
+    {
+        uint32_t sub = FZ_BP_SUB_BITS;
+        const uint32_t hdr = st->hdr_end > bit ? st->hdr_end - bit : 0u;
+        if (len_hint > hdr) {
+            sub = (((len_hint - hdr + 31u) >> 5) + 63u) & ~63u;
+            sub = sub < FZ_BP_SUB_MIN ? FZ_BP_SUB_MIN : (sub > FZ_BP_SUB_BITS ? FZ_BP_SUB_BITS : sub);
+        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+        if (lane == 0) st->sub_bits = sub;
+        __syncwarp();
+#else
+        st->sub_bits = sub;
+#endif
+    }
     uint32_t flags = 0, produced = 0, end_bit = bit;
     uint32_t rec0 = FZ_TILE_NONE;
     bool table_ok = !WRITE && pool != nullptr;
@@ -722,7 +749,7 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
     if (good) {
         FZ_PHASE(fz_sy_ph_lut(st, lane));
         uint32_t tile_pos = st->hdr_end;
-        const uint32_t max_tiles = (uint32_t)(((uint64_t)in_len * 8 - tile_pos) / (32u * FZ_BP_SUB_BITS)) + 2u;
+        const uint32_t max_tiles = (uint32_t)(((uint64_t)in_len * 8 - tile_pos) / (32u * st->sub_bits)) + 2u;
         for (uint32_t tile = 0; tile < max_tiles && good && !done; tile++) {
             FZ_PHASE(fz_sy_ph_probe(st, in, in_len, tile_pos, lane));
             FZ_PHASE(fz_sy_ph_ranges(st, tile_pos, lane));

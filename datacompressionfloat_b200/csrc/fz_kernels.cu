@@ -2467,7 +2467,10 @@ fz_bp_sync_kernel(const uint8_t *__restrict__ container, FzBatchGeom g, const ui
         } else {
             FzBlockInfo bi;
             uint32_t rec = FZ_TILE_NONE;
-            fz_sy_block<false>(st, in, len, bit, nullptr, 0, -1, 0, &bi, nullptr, lane, &pool, &rec);
+            // bits to the next candidate header of the stream (the candidates are sorted): how long this block probably is
+            const uint32_t idx = (uint32_t)(ci - (size_t)s * FZ_BP_CAP);
+            const uint32_t hint = (idx + 1u < bp.cand_cnt[s] ? bp.cand_pos[ci + 1] : len * 8u) - bit;
+            fz_sy_block<false>(st, in, len, bit, nullptr, 0, -1, 0, &bi, nullptr, lane, &pool, &rec, hint);
             if (lane == 0) { bp.info[ci] = bi; bp.first_rec[ci] = rec; }
         }
         __syncwarp();
@@ -2535,7 +2538,10 @@ fz_bp_stored_kernel(const uint8_t *__restrict__ container, uint64_t container_si
 // tile per block; false candidates may burn a few more.  When the pool runs dry the write pass searches again.
 static uint32_t fz_bp_tiles_cap(uint32_t nstreams, uint32_t chk)
 {
-    const uint64_t per_stream = (uint64_t)chk * 8 / (32u * FZ_BP_SUB_BITS) + 64;
+    // short blocks take one (smaller) tile each: room for one per candidate -- a block per 512 bytes of payload at the most
+    // (a pool that runs out only makes the write pass search again)
+    const uint64_t blocks = (uint64_t)chk / 512 + 1 < FZ_BP_CAP ? (uint64_t)chk / 512 + 1 : FZ_BP_CAP;
+    const uint64_t per_stream = (uint64_t)chk * 8 / (32u * FZ_BP_SUB_BITS) + blocks + 64;
     const uint64_t cap = per_stream * nstreams;
     return (uint32_t)(cap < 0x7FFFFFFFu ? cap : 0x7FFFFFFFu);
 }

@@ -271,6 +271,8 @@ int hm_blockpar_sync = 1;      // 1: warp-synchronising block decoder (what the 
 void hm_set_blockpar_sync(int on) { hm_blockpar_sync = on; }
 uint64_t hm_precheck_passes = 0;
 uint64_t hm_last_precheck_passes(void) { return hm_precheck_passes; }
+int hm_blockpar_hint = 1;   // pass the distance to the next candidate to the measure pass (what the kernel does)
+void hm_set_blockpar_hint(int on) { hm_blockpar_hint = on; }
 uint64_t hm_quick_passes = 0;  // positions that passed fz_block_quick_test in the last hm_inflate_blockpar call
 uint64_t hm_last_quick_passes(void) { return hm_quick_passes; }
 
@@ -323,7 +325,9 @@ int hm_inflate_blockpar(const uint8_t *in_, uint32_t in_len, uint8_t *out_, uint
     std::vector<uint32_t> first_rec(cap, FZ_TILE_NONE);
     for (uint32_t i = 0; i < ncand; i++) {
         if (hm_blockpar_sync) {
-            fz_sy_block<false>(sy.data(), in, in_len, cand[i], nullptr, 0, -1, 0, &info[i], nullptr, 0, &pool, &first_rec[i]);
+            // the hint the kernel gives: bits to the next candidate header (the candidates are in ascending order here)
+            const uint32_t hint = hm_blockpar_hint ? (i + 1 < ncand ? cand[i + 1] - cand[i] : (uint32_t)(total_bits - cand[i])) : 0u;
+            fz_sy_block<false>(sy.data(), in, in_len, cand[i], nullptr, 0, -1, 0, &info[i], nullptr, 0, &pool, &first_rec[i], hint);
             FzBlockInfo ref;   // the serial measure must agree exactly
             fz_block_measure(in, in_len, cand[i], tab, lut.data(), &ref);
             const bool ref_usable = (ref.flags & FZ_BLK_OK) && !(ref.flags & FZ_BLK_NON_RLE);
