@@ -716,14 +716,19 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
     (void)lane;
     FZ_PHASE(fz_sy_ph_header(st, in, in_len, bit, lane));
     // len_hint: bits from this header to the next candidate header of the stream (0 = unknown).  zlib closes a block after
-    // 16383 symbols, which on exponent or count planes is 30..45 thousand bits: at 2048 bits per sub-range only 16..22 of
-    // the 32 lanes had work.  The block is cut into 32 equal sub-ranges instead (never shorter than FZ_BP_SUB_MIN: the probe
-    // decode in front of every sub-range does not shrink with it).  A hint that is off costs speed, not correctness.
+    // a fixed number of symbols (16383 or 32767), whatever bits that takes: at 2048 bits per sub-range the last tile of a
+    // block had work for some of its 32 lanes only.  The block is cut into equal sub-ranges instead (never shorter than
+    // FZ_BP_SUB_MIN: the probe decode in front of every sub-range does not shrink with it).  A hint that is off costs
+    // speed, not correctness.
     {
         uint32_t sub = FZ_BP_SUB_BITS;
         const uint32_t hdr = st->hdr_end > bit ? st->hdr_end - bit : 0u;
         if (len_hint > hdr) {
-            sub = (((len_hint - hdr + 31u) >> 5) + 63u) & ~63u;
+            // as many tiles as sub-ranges of FZ_BP_SUB_BITS would need, all of them full: a block of 1.35 tiles (an exponent
+            // plane at zlib's 32767 symbols per block) took two tile times with a third of the lanes idle in the second
+            const uint32_t body = len_hint - hdr;
+            const uint32_t tiles = (body + 32u * FZ_BP_SUB_BITS - 1u) / (32u * FZ_BP_SUB_BITS);
+            sub = (((body + 32u * tiles - 1u) / (32u * tiles)) + 63u) & ~63u;
             sub = sub < FZ_BP_SUB_MIN ? FZ_BP_SUB_MIN : (sub > FZ_BP_SUB_BITS ? FZ_BP_SUB_BITS : sub);
         }
 #if defined(__CUDA_ARCH__)
