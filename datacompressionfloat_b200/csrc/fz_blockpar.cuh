@@ -385,11 +385,33 @@ FZ_HD_NOINLINE void fz_sy_ph_header(FzSyncState *st, const uint8_t *in, uint32_t
     st->dd1 = inf.dd1;
 }
 
-FZ_HD void fz_sy_ph_lut(FzSyncState *st, int lane)
+// the block's lookup table, in two kinds of phases (fz_inflate.cuh): every lane fills its share of single-symbol entries,
+// then the entries are packed with further literals from the top down, 32 at a time
+FZ_HD void fz_sy_ph_lut_fill(FzSyncState *st, int lane)
 {
     const FzInfTab<1> tab{st->tab, st->tab + 288, st->tab + 320};
-    for (uint32_t e = (uint32_t)lane; e < FZ_LUT_SIZE; e += 32) st->lut[e] = fz_lut_entry(st->LL, tab, e);
+    fz_lut_fill_lane<FZ_LUT_BITS>(st->lut, st->LL, tab, lane);
 }
+FZ_HD void fz_sy_ph_lut_pack_put(FzSyncState *st, uint32_t batch, int lane)   // batch >= 1: reads entries below the batch only
+{
+    const uint32_t e = batch * 32u + (uint32_t)lane;
+    st->lut[e] = fz_lut_pack<FZ_LUT_BITS>(st->lut, e);
+}
+FZ_HD void fz_sy_ph_lut_pack0(FzSyncState *st, int lane)   // batch 0 reads entries of its own batch: compute, then store
+{
+    st->want[lane] = fz_lut_pack<FZ_LUT_BITS>(st->lut, (uint32_t)lane);   // (want[] is free here)
+}
+FZ_HD void fz_sy_ph_lut_put0(FzSyncState *st, int lane)
+{
+    st->lut[lane] = st->want[lane];
+}
+#define FZ_SY_BUILD_LUT(st, lane)                                                          \
+    do {                                                                                    \
+        FZ_PHASE(fz_sy_ph_lut_fill(st, lane));                                              \
+        for (uint32_t b_ = FZ_LUT_SIZE / 32u - 1u; b_ >= 1u; b_--) FZ_PHASE(fz_sy_ph_lut_pack_put(st, b_, lane)); \
+        FZ_PHASE(fz_sy_ph_lut_pack0(st, lane));                                             \
+        FZ_PHASE(fz_sy_ph_lut_put0(st, lane));                                              \
+    } while (0)
 
 // decode the sub-range of `lane` in tile `tile_pos` from st->start[lane]; out == nullptr: count only
 // probe = true: decode FZ_BP_PROBE_BITS from the grid position of the lane and leave the boundary reached there in
@@ -683,7 +705,7 @@ FZ_HD void fz_sy_block_from_table(FzSyncState *st, const uint8_t *in, uint32_t i
     uint32_t produced = 0, end_bit = bit, rec = first_rec;
     bool done = false;
     if (good) {
-        FZ_PHASE(fz_sy_ph_lut(st, lane));
+        FZ_SY_BUILD_LUT(st, lane);
         for (uint32_t guard = 0; guard < pool.cap && good && !done; guard++) {
             if (rec == FZ_TILE_NONE || rec >= pool.cap) { good = false; break; }
             const FzTileRec *r = &pool.recs[rec];
@@ -752,7 +774,7 @@ FZ_HD void fz_sy_block(FzSyncState *st, const uint8_t *in, uint32_t in_len, uint
     int carry = WRITE ? prev_byte : -1;
     bool good = st->hdr_ok != 0, done = false;
     if (good) {
-        FZ_PHASE(fz_sy_ph_lut(st, lane));
+        FZ_SY_BUILD_LUT(st, lane);
         uint32_t tile_pos = st->hdr_end;
         const uint32_t max_tiles = (uint32_t)(((uint64_t)in_len * 8 - tile_pos) / (32u * st->sub_bits)) + 2u;
         for (uint32_t tile = 0; tile < max_tiles && good && !done; tile++) {

@@ -280,6 +280,67 @@ FZ_HD uint32_t fz_lut_entry_bits(const FzCode &LL, const Tab &tab, uint32_t e)
 template <class Tab>
 FZ_HD uint32_t fz_lut_entry(const FzCode &LL, const Tab &tab, uint32_t e) { return fz_lut_entry_bits<FZ_LUT_BITS>(LL, tab, e); }
 
+// The same table (entry for entry what fz_lut_entry_bits gives), built by the 32 lanes of a warp WITHOUT a canonical search
+// per entry.  In MSB-first order the patterns of a canonical code are consecutive intervals, one per symbol in sorted
+// order: every lane takes 2^LUT_BITS / 32 consecutive patterns, finds the symbol its first one belongs to (one search) and
+// walks on from there; the bit-reversed pattern is the table index.  Two and three literals per entry then come from
+// looking the rest of the pattern up in the table itself -- entries are packed from the top down, 32 at a time, because
+// pattern e only ever looks at patterns below e / 2, which are still single symbols then.  (Per block of a zlib stream
+// the table cost 6144 searches of ~50 instructions: a third of the block-parallel decoder's instructions.)
+// Call with all 32 lanes (the host model loops them: `phase` 0 = fill, 1.. = packing batches; see fz_lut_build_phases).
+template <int LUT_BITS>
+FZ_HD uint32_t fz_lut_single(uint32_t sym, uint32_t l)
+{
+    uint32_t ent = FZ_LUT_ENTRY(sym, 0, 0, l, 1);
+    if (sym >= 257u && sym <= 285u) ent |= FZ_LUT_MATCH | (fz_len_base(sym - 257u) << 9) | (fz_len_extra_bits(sym - 257u) << 18);
+    return ent;
+}
+
+template <int LUT_BITS, class Tab>
+FZ_HD void fz_lut_fill_lane(uint32_t *lut, const FzCode &LL, const Tab &tab, int lane)
+{
+    const uint32_t per = (1u << LUT_BITS) / 32u;
+    const uint32_t *P = (const uint32_t *)&LL;          // P[L - 1] = limit_L << 16 | delta_L
+    uint32_t m = (uint32_t)lane * per;                  // first pattern of this lane, MSB-first, LUT_BITS bits
+    // patterns below code_end_L << (LUT_BITS - L) start with a code of at most L bits; the interval of length L begins
+    // where the one of length L - 1 ended (first_code_L = 2 * code_end_{L-1})
+    uint32_t L = 0, code_end = 0;
+    for (uint32_t i = 0; i < per; i++, m++) {
+        while (L <= (uint32_t)LUT_BITS && m >= (code_end << ((uint32_t)LUT_BITS - L))) {   // (empty lengths are skipped)
+            L++;
+            if (L <= (uint32_t)LUT_BITS) code_end = (P[L - 1] >> 16) >> (15u - L);
+        }
+        uint32_t ent = 0;                                // past the last interval: a longer code (or none)
+        if (L <= (uint32_t)LUT_BITS) {
+            const uint32_t code = m >> ((uint32_t)LUT_BITS - L);                   // the L-bit code this pattern starts with
+            const uint32_t idx = (code + (P[L - 1] & 0xffffu)) & 0xffffu;          // index into the sorted symbols
+            if (idx < 288u) ent = fz_lut_single<LUT_BITS>(tab.L((int)idx), L);
+        }
+        lut[fz_bitrev(m, LUT_BITS)] = ent;
+    }
+}
+
+// entry e with up to two more literals looked up in the (still single-symbol) entries below it
+template <int LUT_BITS>
+FZ_HD uint32_t fz_lut_pack(const uint32_t *lut, uint32_t e)
+{
+    const uint32_t a = lut[e];
+    const uint32_t s1 = a & 511u;
+    uint32_t total = (a >> 25) & 15u;
+    if (a == 0 || s1 >= 256u || total >= (uint32_t)LUT_BITS) return a;
+    const uint32_t b = lut[e >> total];
+    const uint32_t l2 = (b >> 25) & 15u;
+    if (b == 0 || (b & 511u) >= 256u || total + l2 > (uint32_t)LUT_BITS) return a;
+    uint32_t s2 = b & 511u, s3 = 0, cnt = 2;
+    total += l2;
+    if (total < (uint32_t)LUT_BITS) {
+        const uint32_t c = lut[e >> total];
+        const uint32_t l3 = (c >> 25) & 15u;
+        if (c != 0 && (c & 511u) < 256u && total + l3 <= (uint32_t)LUT_BITS) { s3 = c & 511u; total += l3; cnt = 3; }
+    }
+    return FZ_LUT_ENTRY(s1, s2, s3, total, cnt);
+}
+
 // Which value of a 1-bit distance code means "distance 1" (what run-length streams use): 0 or 1, or 2 = this block's
 // distance code is not of that kind (see FzInflater::dd1).
 FZ_HD uint32_t fz_dd1_run_bit(uint32_t dd1)

@@ -271,6 +271,33 @@ int hm_blockpar_sync = 1;      // 1: warp-synchronising block decoder (what the 
 void hm_set_blockpar_sync(int on) { hm_blockpar_sync = on; }
 uint64_t hm_precheck_passes = 0;
 uint64_t hm_last_precheck_passes(void) { return hm_precheck_passes; }
+// Builds the lookup table of a literal/length code given by its 288 code lengths both ways -- one canonical search per
+// entry (fz_lut_entry_bits) and the warp's interval walk + in-table packing (fz_lut_fill_lane / fz_lut_pack) -- and returns
+// the number of entries that differ (-1: the lengths are over-subscribed).
+int hm_lut_compare(const uint8_t *lens)
+{
+    uint16_t ll[288], dd[32], cnt[32];
+    FzInfTab<1> tab{ll, dd, cnt};
+    for (int l = 0; l < 32; l++) cnt[l] = 0;
+    for (int i = 0; i < 288; i++) if (lens[i]) cnt[lens[i]]++;
+    FzCode LL;
+    auto rd = [&](int l) -> uint32_t { return cnt[l]; };
+    auto wr = [&](int l, uint32_t v) { cnt[l] = (uint16_t)v; };
+    if (fz_code_build(LL, rd, wr) < 0) return -1;
+    for (int i = 0; i < 288; i++) if (lens[i]) ll[cnt[lens[i]]++] = (uint16_t)i;
+    std::vector<uint32_t> a(FZ_LUT_SIZE), b(FZ_LUT_SIZE, 0xDEADBEEFu);
+    for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) a[e] = fz_lut_entry(LL, tab, e);
+    for (int lane = 0; lane < 32; lane++) fz_lut_fill_lane<FZ_LUT_BITS>(b.data(), LL, tab, lane);
+    for (uint32_t bt = FZ_LUT_SIZE / 32u - 1u; bt >= 1u; bt--)
+        for (uint32_t lane = 0; lane < 32; lane++) b[bt * 32u + lane] = fz_lut_pack<FZ_LUT_BITS>(b.data(), bt * 32u + lane);
+    uint32_t first[32];
+    for (uint32_t lane = 0; lane < 32; lane++) first[lane] = fz_lut_pack<FZ_LUT_BITS>(b.data(), lane);
+    for (uint32_t lane = 0; lane < 32; lane++) b[lane] = first[lane];
+    int diff = 0;
+    for (uint32_t e = 0; e < FZ_LUT_SIZE; e++) diff += a[e] != b[e];
+    return diff;
+}
+
 int hm_blockpar_hint = 1;   // pass the distance to the next candidate to the measure pass (what the kernel does)
 void hm_set_blockpar_hint(int on) { hm_blockpar_hint = on; }
 uint64_t hm_quick_passes = 0;  // positions that passed fz_block_quick_test in the last hm_inflate_blockpar call

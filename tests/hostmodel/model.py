@@ -85,3 +85,15 @@ def table_blocks() -> int:
     """Blocks the last inflate_blockpar call wrote from tile records."""
     _L.hm_get_table_blocks.restype = C.c_uint32
     return int(_L.hm_get_table_blocks())
+
+
+_L.hm_lut_compare.restype = C.c_int
+_L.hm_lut_compare.argtypes = [C.c_void_p]
+
+
+def lut_compare(lens: np.ndarray) -> int:
+    """entries that differ between the two ways of building the inflater's lookup table for the literal/length code with
+    these 288 code lengths (-1: over-subscribed lengths)"""
+    lens = np.ascontiguousarray(lens, dtype=np.uint8)
+    assert lens.size == 288
+    return int(_L.hm_lut_compare(lens.ctypes.data))

@@ -393,6 +393,66 @@ def test_model_blockpar_inflate_of_reference_streams(hostmodel):
     assert rc != 0
 
 
+def test_model_warp_built_lookup_table_equals_the_searched_one(hostmodel):
+    """The block-parallel decoder's table is built by interval walk + in-table packing (fz_lut_fill_lane / fz_lut_pack)
+    instead of one canonical search per entry: entry for entry the same table, for complete, incomplete, skewed, flat and
+    single-symbol codes."""
+    rng = np.random.default_rng(11)
+
+    def lengths_from_freq(f):          # a Huffman code for frequencies f through zlib-like limiting: use package-free heuristic
+        import heapq
+        n = len(f)
+        heap = [(int(w), i, None, None) for i, w in enumerate(f) if w > 0]
+        lens = np.zeros(n, np.int64)
+        if len(heap) == 1:
+            lens[heap[0][1]] = 1
+            return lens
+        heapq.heapify(heap)
+        nodes = {}
+        uid = n
+        while len(heap) > 1:
+            a = heapq.heappop(heap); b = heapq.heappop(heap)
+            nodes[uid] = (a, b)
+            heapq.heappush(heap, (a[0] + b[0], uid, a, b))
+            uid += 1
+        stack = [(heap[0], 0)]
+        while stack:
+            (w, i, a, b), d = stack.pop()
+            if a is None:
+                lens[i] = max(d, 1)
+            else:
+                stack.append((a, d + 1)); stack.append((b, d + 1))
+        return lens
+
+    cases = []
+    for trial in range(40):
+        nsym = int(rng.integers(2, 287))
+        syms = rng.choice(286, nsym, replace=False)
+        f = np.zeros(288, np.int64)
+        kind = trial % 4
+        if kind == 0:
+            f[syms] = rng.integers(1, 1000, nsym)
+        elif kind == 1:
+            f[syms] = (2.0 ** rng.integers(0, 14, nsym)).astype(np.int64)
+        elif kind == 2:
+            f[syms] = 1
+        else:
+            f[syms] = np.maximum(1, (1e6 * 0.6 ** np.arange(nsym))).astype(np.int64)
+        f[256] = max(f[256], 1)
+        lens = lengths_from_freq(f)
+        if lens.max() > 15:
+            continue
+        cases.append(lens.astype(np.uint8))
+    one = np.zeros(288, np.uint8); one[65] = 1                       # a single code of one bit: incomplete
+    two = np.zeros(288, np.uint8); two[0] = 1; two[256] = 1
+    fixed = np.r_[np.full(144, 8), np.full(112, 9), np.full(24, 7), np.full(8, 8)].astype(np.uint8)   # the fixed code of RFC 1951
+    gap = np.zeros(288, np.uint8); gap[[1, 2, 3]] = 2; gap[256] = 5   # incomplete: patterns without a code
+    cases += [one, two, fixed, gap]
+    assert len(cases) > 20
+    for lens in cases:
+        assert hostmodel.lut_compare(lens) == 0, lens.tolist()
+
+
 def test_model_blockpar_tile_records_and_pool_exhaustion(hostmodel):
     """The measure pass leaves tile records so that the write pass decodes every sub-range once; when the pool is
     too small the write pass searches again -- same bytes either way."""
