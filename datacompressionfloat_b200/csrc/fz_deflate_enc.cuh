@@ -445,7 +445,7 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
     FZ_PHASE(fz_ph_cl_tokens(st, lane));
     FZ_PHASE(fz_ph_header(st, lane));
     FZ_PHASE(fz_ph_cost_partial(st, lane));
-    // group decision: all sub-blocks dynamic vs all stored (the per-sub-block decision is exact, in fz_emit_subblock)
+    // group decision: all sub-blocks dynamic vs all stored (the per-sub-block decision is exact, in fz_emit2_subblock)
     uint64_t bits = (uint64_t)nsub * (st->hdr_nbits + 3 + 4 + 32);  // header + empty stored block (avg pad 4) per sub-block
     for (int l = 0; l < 32; l++) bits += ((uint64_t)st->lane_bits[l] << 32) | st->lane_cnt[l];
     const uint64_t stored_bits = 8ull * ((uint64_t)group_bytes + (uint64_t)FZ_STORED_OVERHEAD * nsub);

@@ -355,17 +355,18 @@ __device__ __forceinline__ void fz_st256(void *p, uint4 a, uint4 b)
                  : "memory");
 }
 
-// chunks whose reads are mostly unaligned RAW payloads (two or more RAW planes) go to the 16-words-per-thread kernel
+// which chunks take the 16-words-per-thread path: those with at least wide_min RAW planes (0: all of them, the default)
 __device__ __forceinline__ bool fz_merge_wide(const uint32_t *__restrict__ stream_hdr, uint32_t c, uint32_t wide_min)
 {
     const uint4 h = __ldg((const uint4 *)stream_hdr + c);
     return ((h.x >> 31) + (h.y >> 31) + (h.z >> 31) + (h.w >> 31)) >= wide_min;
 }
 
-// Chunks with two or more RAW planes, 16 words per thread: one 128-bit load per plane -- two and a funnel shift for a RAW payload, which
-// sits at whatever address the container gives it -- and four 128-bit stores (a quarter of a 128-byte line each: that
-// costs more than the 4-byte loads above save unless unaligned RAW payloads dominate the reads).  Same CTA shape:
-// 4096 words, a quarter of one sub-block of every plane.
+// 16 words per thread: one 128-bit load per plane -- two and a funnel shift for a RAW payload, which sits at whatever
+// address the container gives it -- and two 256-bit stores.  (With four 128-bit stores this path only paid for chunks
+// with two or more RAW planes; with 256-bit stores it beats the 4-bytes-per-plane path below on every input measured:
+// G b=8 1.42 -> 1.20 ms, S b=12 1.41 -> 1.13, G b=16 1.27 -> 1.02, P b=0 1.03 -> 0.94 per 4 GiB.)  CTA shape: 4096 words,
+// a quarter of one sub-block of every plane.
 #define FZ_MERGE16_THREADS FZ_SPLIT_THREADS
 __device__ __forceinline__ void
 fz_merge_streams16(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ container, const uint8_t *container_end,
@@ -517,9 +518,7 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, ui
         fz_merge_streams_kernel<<<grid, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words, 9u, container + container_size);
         return;
     }
-    // one launch: a CTA of a chunk with two or more RAW planes takes the 16-words-per-thread path, the others the
-    // 4-bytes-per-plane one (measured per 4 GiB: G b=0, three RAW planes, 1.92 -> 1.70 ms with the first; P b=0, two
-    // all-zero planes, 0.99 -> 1.32 ms: hence the split; two launches that each skip the other's chunks cost 0.15 ms more)
+    // one launch; every chunk takes the 16-words-per-thread path unless MRCZIP_MERGE_WIDE_MIN asks for the old split
     const uint32_t per4 = FZ_SPLIT_THREADS * FZ_SPLIT_UNROLL;
     dim3 grid4((g.chk / 4 + per4 - 1) / per4, g.nchunks);
     fz_merge_streams_kernel<<<grid4, FZ_SPLIT_THREADS, 0, st>>>(planes, container, stream_hdr, stream_off, zero_flags, g, words,
@@ -528,9 +527,10 @@ void fz_launch_merge_streams(const uint8_t *planes, const uint8_t *container, ui
 
 // =================================================================================================
 // deflate: three kernels
-//   fz_hist_kernel        one warp per 16 KiB sub-block: token histogram, accumulated per group of 32 sub-blocks
-//   fz_group_code_kernel  one warp per group: Huffman code + block header (once per 512 KiB of plane)
-//   fz_emit_kernel        one warp per sub-block: exact size, stored-vs-dynamic decision, lane-parallel bit emission
+//   fz_hist2_kernel       one warp per 16 KiB sub-block: 2 KiB sample (stored / all-zero decisions), token histogram of
+//                         every fourth sub-block, accumulated per code group of FZ_CODE_SUBS = 128 sub-blocks
+//   fz_group_code_kernel  one warp per code group: Huffman code + block header (once per 2 MiB of plane)
+//   fz_emit2_kernel       one warp per sub-block: one pass, lane-parallel bit emission, stored-vs-dynamic decision
 // =================================================================================================
 #ifndef FZ_ENC_WARPS
 #define FZ_ENC_WARPS 4
