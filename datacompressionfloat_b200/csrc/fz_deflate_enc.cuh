@@ -419,12 +419,13 @@ struct FzGroupCode {
 // Build the group's Huffman code and block header from its token histogram.
 //   st->hist[0..287] = token frequencies of the whole group, st->hist[256] = number of sub-blocks (EOBs)
 //   group_bytes = plane bytes in the group, nsub = sub-blocks in the group
-//   standins: symbols of frequency 1 stand for "may occur in the sub-blocks the histogram did not sample"
+//   sample: 0 = the histogram counts every sub-block; k > 1 = it counts every k-th sub-block k times over, and symbols of
+//   frequency 1 are stand-ins for "may occur in the sub-blocks that were not sampled"
 template <int DUMMY = 0>
-FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t nsub, FzGroupCode *out, int lane, bool standins = false)
+FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t nsub, FzGroupCode *out, int lane, uint32_t sample = 0)
 {
     (void)lane;
-    const uint32_t low = standins ? 1u : 0u;
+    const uint32_t low = sample > 1u ? 1u : 0u;
     FZ_PHASE(fz_ph_zero_len(st, lane));
     FZ_PHASE(fz_ph_count_active(st, low, lane));
     FZ_PHASE(fz_ph_compact(st, low, lane));
@@ -447,7 +448,12 @@ FZ_HD void fz_build_group_code(FzEncState *st, uint32_t group_bytes, uint32_t ns
     FZ_PHASE(fz_ph_cost_partial(st, lane));
     // group decision: all sub-blocks dynamic vs all stored (the per-sub-block decision is exact, in fz_emit2_subblock)
     uint64_t bits = (uint64_t)nsub * (st->hdr_nbits + 3 + 4 + 32);  // header + empty stored block (avg pad 4) per sub-block
-    for (int l = 0; l < 32; l++) bits += ((uint64_t)st->lane_bits[l] << 32) | st->lane_cnt[l];
+    uint64_t payload = 0;
+    for (int l = 0; l < 32; l++) payload += ((uint64_t)st->lane_bits[l] << 32) | st->lane_cnt[l];
+    // a sampled histogram stands for ceil(nsub / sample) * sample sub-blocks: in a ragged group (the end of a stream, small
+    // chunks) that is more than the nsub it has, and the estimate would call compressible groups incompressible
+    if (sample > 1u) payload = payload * nsub / ((uint64_t)((nsub + sample - 1u) / sample) * sample);
+    bits += payload;
     const uint64_t stored_bits = 8ull * ((uint64_t)group_bytes + (uint64_t)FZ_STORED_OVERHEAD * nsub);
     const uint32_t stored = bits + (stored_bits >> FZ_MIN_GAIN_SHIFT) >= stored_bits ? 1u : 0u;
 #if defined(__CUDA_ARCH__)

@@ -598,6 +598,9 @@ __device__ __forceinline__ uint32_t fz_groups_per_stream(const FzBatchGeom &g)
 #define FZ_SAMPLE_BITS 7.85f
 #endif
 
+#ifndef FZ_HIST_SAMPLE
+#define FZ_HIST_SAMPLE 4u   // 1 = every sub-block is tokenised for the histogram
+#endif
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)
 fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupCode *__restrict__ gcodes)
 {
@@ -631,7 +634,7 @@ fz_group_code_kernel(const uint32_t *__restrict__ ghist, FzBatchGeom g, FzGroupC
     __syncwarp();
     if (lane == 0) { st->hist[FZ_EOB] = nsub; st->hist[286] = 0; st->hist[287] = 0; }  // one end-of-block per sub-block
     __syncwarp();
-    fz_build_group_code(st, gn, nsub, gcodes + gi, lane, standins);
+    fz_build_group_code(st, gn, nsub, gcodes + gi, lane, standins ? FZ_HIST_SAMPLE : 0u);
 }
 
 // =================================================================================================
@@ -666,9 +669,6 @@ __device__ __forceinline__ uint32_t fz_warp_hist_mode(const uint32_t *hist, uint
     return best;
 }
 
-#ifndef FZ_HIST_SAMPLE
-#define FZ_HIST_SAMPLE 4u   // 1 = every sub-block is tokenised for the histogram
-#endif
 #define FZ_HIST2_SKIP_MIN 160u   // of 2048 sample bytes: below ~8 % a private counter costs more than the conflicts it saves
 
 __global__ void __launch_bounds__(FZ_ENC_WARPS * FZ_WARP)

@@ -185,7 +185,7 @@ uint64_t hm_encode_stream_v2(const uint8_t *in, uint64_t n, uint8_t *out, uint64
         }
         st->hist[FZ_EOB] = nsub;
         memset(gc, 0xEE, sizeof(FzGroupCode));
-        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0, hm_hist_sample > 1);
+        fz_build_group_code(st, (uint32_t)gn, nsub, gc, 0, hm_hist_sample > 1 ? (uint32_t)hm_hist_sample : 0u);
         for (uint32_t k = 0; k < nsub; k++) {
             const uint32_t m = (uint32_t)((gn - (uint64_t)k * FZ_SUB) < FZ_SUB ? (gn - (uint64_t)k * FZ_SUB) : FZ_SUB);
             memset(pad.data(), 0x5A, pad.size());

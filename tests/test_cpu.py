@@ -195,6 +195,31 @@ def test_model_encoder_with_sampled_histogram_and_standins(hostmodel, oracle, na
     assert c.size <= 1.03 * c0.size + 64 * nsub or c.size <= a.size + 15 * nsub
 
 
+def test_model_nearly_incompressible_plane_costs_at_most_the_gain_threshold(hostmodel):
+    """A sub-block (and a group) is coded only if that saves at least 1 / 2^FZ_MIN_GAIN_SHIFT = 3 % (nearly incompressible
+    bytes decode at one symbol per table hit for a gain nobody would miss), and a sample entropy above 7.85 bits stores it
+    unseen: planes zlib would shrink by 1..3 % -- typical mid-mantissa bytes -- come out stored.  The price is bounded: never
+    more than 3 % (+ framing) above zlib's size, and never above the stored size."""
+    rng = np.random.default_rng(3)
+    n = 6 * hostmodel.SUB
+    for bits_of_entropy, p_extra in ((7.8, 0.18), (7.6, 0.30), (7.95, 0.05)):
+        # a flat byte distribution with a bump: p_extra of the mass on 16 symbols
+        a = rng.integers(0, 256, n).astype(np.uint8)
+        bump = rng.random(n) < p_extra
+        a[bump] = rng.integers(0, 16, int(bump.sum())).astype(np.uint8)
+        hostmodel.set_hist_sample(4)
+        try:
+            c, ns = hostmodel.encode_stream(a)
+        finally:
+            hostmodel.set_hist_sample(0)
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_RLE)
+        z = co.compress(a.tobytes()) + co.flush(zlib.Z_FULL_FLUSH)
+        nsub = n // hostmodel.SUB
+        assert zlib.decompressobj(-15).decompress(c.tobytes()) == a.tobytes()
+        assert c.size <= n + 15 * nsub + 16, (bits_of_entropy, c.size, n)                     # never above stored
+        assert c.size <= len(z) * 1.035 + 80 * nsub, (bits_of_entropy, c.size, len(z))        # at most the threshold above zlib
+
+
 @pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 511, 512, 513, 1000, 8191, 16383])
 def test_model_encoder_ragged_sizes(hostmodel, n):
     """ragged sub-blocks (the last one of a file, odd chunk sizes): runs that end exactly at, before and after lane
